@@ -1,0 +1,134 @@
+/* kpf_b200.h -- C ABI of libkpf_b200.so: the B200 (sm_100a) kernels of the KeypointFusion fusion hot path.
+ *
+ * The reference (ru1ven/KeypointFusion) has no FFI: its boundary is Python object identity.
+ * Each entry point below is what a ctypes binding in the reference would call instead of the cited
+ * Python/PyTorch function; the host-side drop-in classes in keypointfusion_b200/ do exactly that.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch storage); nothing is allocated here;
+ *   - tensors are dense row-major in the layout stated per function; "strided depth" arguments let the
+ *     caller pass either the down-sampled map [B,1,fs,fs] or the full crop with row/col strides (the fused
+ *     nearest down-sample of model.py:409);
+ *   - launches are asynchronous on `stream`; no host synchronisation, no global state, re-entrant;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative KPF_ERR_* code.  No C++ exceptions.
+ */
+#ifndef KPF_B200_H
+#define KPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+enum { KPF_F32 = 0, KPF_BF16 = 1 };
+enum { KPF_ERR_BAD_ARGUMENT = -1, KPF_ERR_UNSUPPORTED = -2 };
+
+/* Library ABI version (bumped on any signature change). */
+int kpf_abi_version(void);
+
+/* ---- a1-a3  util/img2pcl.py:11-40 Pcl_utils.getpcl  ==  dataloader/loader.py:843-893 + :1173-1186 ------------
+ * img [B,1,S,S] f32 (background == 1.0), com3D [B,3], cube [B,3], M [B,3,3], cam [B,4] (fx,fy,fu,fv), S <= 256.
+ * pcl_out [B,sample_num,3] f32, count_out [B] i32 (number of valid pixels P; may be NULL).
+ * ranks: NULL -> built-in counter-based permutation keyed by (seed, b); else [B,sample_num] i32 ranks into the
+ * row-major ordered list of valid pixels (clamped to P-1).  P == 0 -> zeros.  clamp != 0 -> clip to [-1,1]. */
+int kpf_getpcl(const float* img, const float* com3D, const float* cube, const float* M, const float* cam, int B, int S,
+               int sample_num, const int32_t* ranks, uint32_t seed, int clamp, float flip, float* pcl_out, int32_t* count_out,
+               cudaStream_t stream);
+
+/* Every valid point in row-major pixel order (loader.py:843-893 without the resample):
+ * xyz_out [B,S*S,3] (rows >= P zero), pix_out [B,S*S] i32 flat pixel index (-1 padding; may be NULL), count_out [B]. */
+int kpf_backproject_all(const float* img, const float* com3D, const float* cube, const float* M, const float* cam, int B, int S,
+                        float flip, float* xyz_out, int32_t* pix_out, int32_t* count_out, cudaStream_t stream);
+
+/* ---- a5  dataloader/loader.py:775-789 uvd_nl2xyznl_tensor, :821-834 xyz_nl2uvdnl_tensor ----------------------
+ * [B,P,3] f32 -> [B,P,3] f32.  M^-1 is a closed-form fp64 adjugate (no torch.linalg.inv host sync). */
+int kpf_uvd2xyz(const float* uvd, const float* center, const float* M, const float* cube, const float* cam, int B, int P,
+                float img_size, float flip, float* out, cudaStream_t stream);
+int kpf_xyz2uvd(const float* xyz, const float* center, const float* M, const float* cube, const float* cam, int B, int P,
+                float img_size, float flip, float* out, cudaStream_t stream);
+
+/* ---- a6  dataloader/loader.py:936-967 img2pcl_index ---------------------------------------------------------------
+ * pcl [B,N,3]; depth element (b,r,c) at depth[b*depth_bs + r*depth_rs + c*depth_cs], r,c < fs.
+ * closeness [B,N,K] f32; index64 [B,N,K] i64 and/or index32 [B,N,K] i32 (either may be NULL): flat cell index
+ * row*fs+col of the K nearest cells in normalised 3-D space, ascending distance, ties -> lower index. K in 1..9 or 16. */
+int kpf_img2pcl_index(const float* pcl, const float* depth, long long depth_bs, int depth_rs, int depth_cs, const float* center,
+                      const float* M, const float* cube, const float* cam, int B, int N, int fs, float img_size, float flip, int K,
+                      float* closeness, long long* index64, int32_t* index32, cudaStream_t stream);
+
+/* ---- a4  model/model.py:466-500 offset2joint_weight (== util/generateFeature.py:166-195) ------------------------
+ * offset [B,5J,fs,fs] (dtype), depth [B,1,S,S] f32 (nearest down-sampled to fs inside), kernel_vec [J] f32.
+ * joint_out [B,J,3] f32 (uvd). */
+int kpf_offset2joint_weight(const void* offset, int dtype, const float* depth, int B, int J, int fs, int S,
+                            const float* kernel_vec, float* joint_out, cudaStream_t stream);
+
+/* ---- a7  model/model.py:503-525 pcl_joint2offset -> out [B,N,4J] f32 (3J joint-major unit vectors, then J closeness) */
+int kpf_pcl_joint2offset(const float* joint, const float* pcl, const float* kernel_vec, int B, int J, int N, float* out,
+                         cudaStream_t stream);
+
+/* ---- a8  model/model.py:297-306 K-tap weighted gathers ------------------------------------------------------------
+ * feat: [B,C,HW] (dtype) with batch stride feat_batch_stride elements (lets a channel slice of a wider map be
+ * passed); index [B,N,K] i64 (index_is_i64 != 0) or i32; closeness [B,N,K] f32.
+ * out (dtype): element (b,n,c) at out[(b*N+n)*out_stride + out_c0 + c]  (out_stride >= out_c0 + C). */
+int kpf_gather_taps(const void* feat, int dtype, long long feat_batch_stride, int B, int C, int HW, const void* index,
+                    int index_is_i64, const float* closeness, int N, int K, void* out, int out_stride, int out_c0,
+                    cudaStream_t stream);
+
+/* ---- a10  util/generateFeature.py:584-600 GFM.joint2heatmap: joint [B,J,joint_stride>=2] -> out [B,J,S,S] -------- */
+int kpf_joint2heatmap(const float* joint, int joint_stride, int B, int J, int S, float stdv, float sigma, float* out,
+                      cudaStream_t stream);
+
+/* ---- a11  dataloader/loader.py:791-819 img2anchor_dis: joint_uvd [B,J,3] -> out [B,J,fs,fs] ---------------------- */
+int kpf_img2anchor_dis(const float* joint_uvd, const float* depth, long long depth_bs, int depth_rs, int depth_cs,
+                       const float* center, const float* M, const float* cube, const float* cam, int B, int J, int fs,
+                       float img_size, float flip, float gamma, float* out, cudaStream_t stream);
+
+/* ---- a16  util/generateFeature.py:59-84 GFM.joint2offset (eps 1e-8) / model/model.py:440-463 (eps 0) --------------
+ * joint [B,J,3], depth [B,1,S,S] -> out [B,4J,fs,fs] f32. */
+int kpf_joint2offset(const float* joint, const float* depth, int B, int J, int S, int fs, const float* kernel_vec, float eps,
+                     float* out, cudaStream_t stream);
+
+/* ---- a12 (+a10,a11 fused)  model/model.py:334-344 ---------------------------------------------------------------
+ * feat_rgb [B,C,fs,fs] (dtype); joints [B,J,3] = refined_3d_joints (treated as uvd, like the reference);
+ * Wa [J,C+J] = atten_spatial.weight, ba [J]; weight_dis [1]; fc_w [fs*fs], fc_b [1]; prev [B,J,C] or NULL.
+ * sw_out [B,J,fs,fs] f32 (spatial_weight_loss), feat_j_out [B,J,C] f32; hm_out / gam_out [B,J,fs,fs] optional. */
+int kpf_spatial_aggregate(const void* feat_rgb, int dtype, const float* joints, const float* depth, long long depth_bs,
+                          int depth_rs, int depth_cs, const float* center, const float* M, const float* cube, const float* cam,
+                          const float* Wa, const float* ba, const float* weight_dis, const float* fc_w, const float* fc_b,
+                          const float* prev, int B, int C, int J, int fs, float img_size, float flip, float hm_std, float hm_sigma,
+                          float gamma, float* sw_out, float* feat_j_out, float* hm_out, float* gam_out, cudaStream_t stream);
+
+/* ---- a13  model/transfusion_head.py:684-708 updatedDecoder.forward (its one live TransformerDecoderLayer) ------
+ * anchor [B,J,C] (queries), tokens [B,J,C] (keys = values), out_cj [B,C,J] and/or out_jc (element (b,t,c) at
+ * out_jc[(b*J+t)*out_jc_stride + out_jc_c0 + c]); either may be NULL.
+ * wpack (f32, contiguous): self_posembed[J*C] cross_posembed[J*C] WqT[C*C] bq[C] WkvT[C*2C] bkv[2C] WoT[C*C] bo[C]
+ *   norm2.w[C] norm2.b[C] W1T[C*F] b1[F] W2T[F*C] b2[C] norm3.w[C] norm3.b[C];  "T" = transposed ([in][out]). */
+int kpf_cross_decoder_layer(const float* anchor, const float* tokens, const float* wpack, int B, int J, int C, int F, int heads,
+                            float* out_cj, float* out_jc, int out_jc_stride, int out_jc_c0, cudaStream_t stream);
+
+/* ---- a14  model/fusion_layer.py:56-83 RGBDFusion.forward ------------------------------------------------------------
+ * rgb, depth [B,C,HW] (dtype); gate_w [2][2C] = (gate_rgb.weight, gate_depth.weight), gate_b [2];
+ * outputs (dtype) [B,C,HW]; attn_sum [2] f32 (pre-zeroed) accumulates the two attention maps (train_writer path) or NULL. */
+int kpf_rgbd_fusion(const void* rgb, const void* depth, int dtype, const float* gate_w, const float* gate_b, int B, int C, int HW,
+                    void* rgb_out, void* depth_out, void* merge_out, float* attn_sum, cudaStream_t stream);
+
+/* AdaptiveAvgPool2d(1): x [rows,HW] (dtype) -> out [rows] f32. */
+int kpf_channel_mean(const void* x, int dtype, int rows, int HW, float* out, cudaStream_t stream);
+
+/* ---- a15  model/fusion_layer.py:101-116 ACFusion.forward (means from kpf_channel_mean) ---------------------------- */
+int kpf_ac_fusion(const void* rgb, const void* depth, int dtype, const float* mean_rgb, const float* mean_depth,
+                  const float* w_rgb, const float* b_rgb, const float* w_depth, const float* b_depth, int B, int C, int HW,
+                  void* rgb_out, void* depth_out, void* merge_out, cudaStream_t stream);
+
+/* ---- a15  model/fusion_layer.py:28-37 FSP.forward (FilterLayer :6-22): out = main + sigmoid(fc2(relu(fc0(mean(cat))))) * guide */
+int kpf_fsp(const void* guide, const void* mainp, int dtype, const float* mean_guide, const float* mean_main, const float* w0,
+            const float* b0, const float* w2, const float* b2, int B, int C, int Hd, int HW, void* out, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KPF_B200_H */

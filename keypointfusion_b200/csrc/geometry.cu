@@ -1,0 +1,402 @@
+// Geometry + per-joint feature kernels (kernels K2, K4a-d).
+// All are HBM / ALU bound CUDA-core kernels: coalesced loads, shared-memory staging of the per-sample
+// cell cloud, warp-shuffle reductions.  Index-producing arithmetic follows the oracle's fp32 operation
+// order without FMA contraction (common.cuh x* helpers) so indices are bit-exact.
+#include "common.cuh"
+
+namespace kpf {
+
+// ------------------------------------------------------------------------------------------------
+// a5: uvd_nl2xyznl_tensor / xyz_nl2uvdnl_tensor   dataloader/loader.py:775-789, :821-841
+// ------------------------------------------------------------------------------------------------
+__global__ void uvd2xyz_kernel(const float* __restrict__ uvd, const float* __restrict__ center, const float* __restrict__ M,
+                               const float* __restrict__ cube, const float* __restrict__ cam, int P, float img_size, float flip,
+                               float* __restrict__ out) {
+    const int b = blockIdx.y;
+    __shared__ CamF c;
+    if (threadIdx.x == 0) load_cam(c, b, center, M, cube, cam, img_size, flip);
+    __syncthreads();
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const float* s = uvd + ((size_t)b * P + p) * 3;
+        const float3 o = uvd2xyz(c, s[0], s[1], s[2]);
+        float* d = out + ((size_t)b * P + p) * 3;
+        d[0] = o.x;
+        d[1] = o.y;
+        d[2] = o.z;
+    }
+}
+
+__global__ void xyz2uvd_kernel(const float* __restrict__ xyz, const float* __restrict__ center, const float* __restrict__ M,
+                               const float* __restrict__ cube, const float* __restrict__ cam, int P, float img_size, float flip,
+                               float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const float* m = M + 9 * b;
+    const float cx = center[3 * b], cy = center[3 * b + 1], cz = center[3 * b + 2];
+    const float sx = cube[3 * b], sy = cube[3 * b + 1], sz = cube[3 * b + 2];
+    const float fx = cam[4 * b], fy = cam[4 * b + 1], fu = cam[4 * b + 2], fv = cam[4 * b + 3];
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const float* s = xyz + ((size_t)b * P + p) * 3;
+        const float X = xadd(xdiv(xmul(s[0], sx), 2.0f), cx);  // loader.py:828
+        const float Y = xadd(xdiv(xmul(s[1], sy), 2.0f), cy);
+        const float Z = xadd(xdiv(xmul(s[2], sz), 2.0f), cz);
+        const float pu = xadd(xdiv(xmul(X, fx), xadd(Z, 1e-8f)), fu);  // loader.py:281-283
+        const float pv = xadd(xdiv(xmul(xmul(flip, Y), fy), Z), fv);   // loader.py:284-286
+        const float tu = xadd(xadd(xmul(m[0], pu), xmul(m[1], pv)), m[2]);
+        const float tv = xadd(xadd(xmul(m[3], pu), xmul(m[4], pv)), m[5]);
+        float* d = out + ((size_t)b * P + p) * 3;
+        d[0] = xsub(xmul(xdiv(tu, img_size), 2.0f), 1.0f);  // loader.py:831
+        d[1] = xsub(xmul(xdiv(tv, img_size), 2.0f), 1.0f);
+        d[2] = xdiv(xsub(Z, cz), xdiv(sz, 2.0f));           // loader.py:832
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 / a6: img2pcl_index   dataloader/loader.py:936-967
+//   cell cloud of the sample (H*W x float4) lives in shared memory; one thread per point keeps a sorted
+//   top-K in registers; ties -> lower cell index (strict '<' while scanning cells in ascending order).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ depth, long long depth_bs, int depth_rs,
+                     int depth_cs, const float* __restrict__ center, const float* __restrict__ M,
+                     const float* __restrict__ cube, const float* __restrict__ cam, int N, int fs, float img_size, float flip,
+                     float* __restrict__ closeness, long long* __restrict__ index64, int32_t* __restrict__ index32) {
+    extern __shared__ __align__(16) float4 cells[];
+    __shared__ CamF c;
+    const int b = blockIdx.y, HW = fs * fs;
+    if (threadIdx.x == 0) load_cam(c, b, center, M, cube, cam, img_size, flip);
+    __syncthreads();
+    const float ffs = (float)fs;
+    for (int m = threadIdx.x; m < HW; m += blockDim.x) {
+        const int r = m / fs, col = m - r * fs;
+        const float d = __ldg(depth + (size_t)b * depth_bs + (size_t)r * depth_rs + (size_t)col * depth_cs);
+        const float3 q = uvd2xyz(c, cell_coord(col, ffs), cell_coord(r, ffs), d);  // ch0 = column, ch1 = row (:948-951)
+        cells[m] = make_float4(q.x, q.y, q.z, 0.f);
+    }
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* pp = pcl + ((size_t)b * N + n) * 3;
+    const float px = pp[0], py = pp[1], pz = pp[2];
+    float bd[K];
+    int bi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        bd[k] = INFINITY;
+        bi[k] = 0;
+    }
+    for (int m = 0; m < HW; ++m) {
+        const float4 q = cells[m];
+        const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
+        const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));  // loader.py:956
+        if (d2 < bd[K - 1]) {
+            float cd = d2;
+            int ci = m;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (cd < bd[k]) {
+                    const float td = bd[k];
+                    const int ti = bi[k];
+                    bd[k] = cd;
+                    bi[k] = ci;
+                    cd = td;
+                    ci = ti;
+                }
+            }
+        }
+    }
+    float cv[K];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        cv[k] = xdiv(1.0f, xadd(bd[k], 1e-8f));  // loader.py:959
+        s = k == 0 ? cv[0] : xadd(s, cv[k]);
+    }
+    const float den = xadd(s, 1e-8f);  // loader.py:960
+    const size_t o = ((size_t)b * N + n) * K;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        closeness[o + k] = xdiv(cv[k], den);
+        if (index64) index64[o + k] = bi[k];
+        if (index32) index32[o + k] = bi[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a / a4: offset2joint_weight   model/model.py:466-500 == util/generateFeature.py:166-195
+//   one CTA per (joint, sample); two passes over the 5 channel rows (max, then softmax-weighted sums).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+offset2joint_kernel(const T* __restrict__ offset, const float* __restrict__ depth, int S, int J, int fs,
+                    const float* __restrict__ kernel_vec, float* __restrict__ joint_out) {
+    __shared__ float scratch[32];
+    const int j = blockIdx.x, b = blockIdx.y, HW = fs * fs;
+    const T* base = offset + (size_t)b * 5 * J * HW;
+    const T* ux = base + (size_t)(3 * j) * HW;
+    const T* heat = base + (size_t)(3 * J + j) * HW;
+    const T* wgt = base + (size_t)(4 * J + j) * HW;
+    const float* dimg = depth + (size_t)b * S * S;
+    const float ks = kernel_vec[j];
+    const float ffs = (float)fs;
+    float mx = -INFINITY;
+    for (int m = threadIdx.x; m < HW; m += blockDim.x) {
+        const int r = m / fs, col = m - r * fs;
+        const float d = __ldg(dimg + (size_t)nearest_src(r, S, fs) * S + nearest_src(col, S, fs));
+        const float w = d > 0.99f ? -1e8f : to_f32(wgt[m]);  // masked_fill(depth.gt(0.99), -1e8)  :488
+        mx = fmaxf(mx, w);
+    }
+    mx = block_max(mx, scratch);
+    float se = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    for (int m = threadIdx.x; m < HW; m += blockDim.x) {
+        const int r = m / fs, col = m - r * fs;
+        const float d = __ldg(dimg + (size_t)nearest_src(r, S, fs) * S + nearest_src(col, S, fs));
+        const float w = d > 0.99f ? -1e8f : to_f32(wgt[m]);
+        const float e = expf(w - mx);
+        const float msk = d < 0.99f ? 1.f : 0.f;                       // depth.lt(0.99)  :485
+        const float dist = ks - (to_f32(heat[m]) * msk) * ks;         // :495
+        const float ox = to_f32(ux[m]) * msk, oy = to_f32(ux[HW + m]) * msk, oz = to_f32(ux[2 * HW + m]) * msk;
+        se += e;
+        ax += (ox * dist + cell_coord(col, ffs)) * e;                 // coords ch0 = column  :481
+        ay += (oy * dist + cell_coord(r, ffs)) * e;
+        az += (oz * dist + d) * e;
+    }
+    se = block_sum(se, scratch);
+    ax = block_sum(ax, scratch);
+    ay = block_sum(ay, scratch);
+    az = block_sum(az, scratch);
+    if (threadIdx.x == 0) {
+        float* o = joint_out + ((size_t)b * J + j) * 3;
+        o[0] = ax / se;
+        o[1] = ay / se;
+        o[2] = az / se;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b / a7: pcl_joint2offset   model/model.py:503-525 -> [B,N,4J] (3J joint-major unit vectors, then J closeness)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pcl_joint2offset_kernel(const float* __restrict__ joint, const float* __restrict__ pcl, const float* __restrict__ kernel_vec,
+                        int J, int N, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int j = threadIdx.x;                       // blockDim.x = 32 >= J handled by loop below
+    const int n = blockIdx.x * blockDim.y + threadIdx.y;
+    if (n >= N) return;
+    const float* p = pcl + ((size_t)b * N + n) * 3;
+    const float px = p[0], py = p[1], pz = p[2];
+    float* o = out + ((size_t)b * N + n) * 4 * J;
+    for (int jj = j; jj < J; jj += blockDim.x) {
+        const float* q = joint + ((size_t)b * J + jj) * 3;
+        const float ox = q[0] - px, oy = q[1] - py, oz = q[2] - pz;
+        const float dis = sqrtf(ox * ox + oy * oy + oz * oz);
+        const float inv = 1.0f / (dis + 1e-8f);
+        const float ks = kernel_vec[jj];
+        const float heat = (ks - dis) / ks;
+        const float msk = (heat >= 0.f && pz < 0.99f) ? 1.f : 0.f;  // :522
+        o[3 * jj + 0] = ox * inv * msk;
+        o[3 * jj + 1] = oy * inv * msk;
+        o[3 * jj + 2] = oz * inv * msk;
+        o[3 * J + jj] = heat * msk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4c / a10: GFM.joint2heatmap   util/generateFeature.py:584-600
+// ------------------------------------------------------------------------------------------------
+__global__ void joint2heatmap_kernel(const float* __restrict__ joint, int joint_stride, int J, int S, float stdv, float sigma,
+                                     float* __restrict__ out) {
+    const int bj = blockIdx.y;  // b*J + j
+    const float jx = (joint[(size_t)bj * joint_stride + 0] + 1.f) / 2.f * (float)S;
+    const float jy = (joint[(size_t)bj * joint_stride + 1] + 1.f) / 2.f * (float)S;
+    const float inv2s2 = 1.f / (2.f * sigma * sigma);
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < S * S; m += gridDim.x * blockDim.x) {
+        const int r = m / S, col = m - r * S;
+        const float dx = ((float)col + 0.5f - jx) / stdv, dy = ((float)r + 0.5f - jy) / stdv;
+        out[(size_t)bj * S * S + m] = expf(-(dx * dx + dy * dy) * inv2s2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4c / a11: loader.img2anchor_dis   dataloader/loader.py:791-819 -> GAM [B,J,H,W]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+img2anchor_dis_kernel(const float* __restrict__ joint_uvd, const float* __restrict__ depth, long long depth_bs, int depth_rs,
+                      int depth_cs, const float* __restrict__ center, const float* __restrict__ M,
+                      const float* __restrict__ cube, const float* __restrict__ cam, int J, int fs, float img_size, float flip,
+                      float gamma, float* __restrict__ out) {
+    extern __shared__ float jxyz[];  // [J*3]
+    __shared__ CamF c;
+    const int b = blockIdx.y, HW = fs * fs;
+    if (threadIdx.x == 0) load_cam(c, b, center, M, cube, cam, img_size, flip);
+    __syncthreads();
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const float* s = joint_uvd + ((size_t)b * J + j) * 3;
+        const float3 q = uvd2xyz(c, s[0], s[1], s[2]);
+        jxyz[3 * j] = q.x;
+        jxyz[3 * j + 1] = q.y;
+        jxyz[3 * j + 2] = q.z;
+    }
+    __syncthreads();
+    const float ffs = (float)fs;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < HW; m += gridDim.x * blockDim.x) {
+        const int r = m / fs, col = m - r * fs;
+        const float d = __ldg(depth + (size_t)b * depth_bs + (size_t)r * depth_rs + (size_t)col * depth_cs);
+        const float3 q = uvd2xyz(c, cell_coord(col, ffs), cell_coord(r, ffs), d);
+        for (int j = 0; j < J; ++j) {
+            const float dx = q.x - jxyz[3 * j], dy = q.y - jxyz[3 * j + 1], dz = q.z - jxyz[3 * j + 2];
+            out[((size_t)b * J + j) * HW + m] = 1.f / (gamma * (dx * dx + dy * dy + dz * dz) + 1.f);  // :814-818
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4d / a16: GFM.joint2offset   util/generateFeature.py:59-84 (eps=1e-8) / model.py:440-463 (eps=0)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+joint2offset_kernel(const float* __restrict__ joint, const float* __restrict__ depth, int S, int J, int fs,
+                    const float* __restrict__ kernel_vec, float eps, float* __restrict__ out) {
+    extern __shared__ float js[];  // [J*4]: xyz + kernel
+    const int b = blockIdx.y, HW = fs * fs;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        js[4 * j] = joint[((size_t)b * J + j) * 3];
+        js[4 * j + 1] = joint[((size_t)b * J + j) * 3 + 1];
+        js[4 * j + 2] = joint[((size_t)b * J + j) * 3 + 2];
+        js[4 * j + 3] = kernel_vec[j];
+    }
+    __syncthreads();
+    const float ffs = (float)fs;
+    float* ob = out + (size_t)b * 4 * J * HW;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < HW; m += gridDim.x * blockDim.x) {
+        const int r = m / fs, col = m - r * fs;
+        const float d = __ldg(depth + (size_t)b * S * S + (size_t)nearest_src(r, S, fs) * S + nearest_src(col, S, fs));
+        const float u = cell_coord(col, ffs), v = cell_coord(r, ffs);
+        const float fg = d < 0.99f ? 1.f : 0.f;
+        for (int j = 0; j < J; ++j) {
+            const float ox = js[4 * j] - u, oy = js[4 * j + 1] - v, oz = js[4 * j + 2] - d;
+            const float dist = sqrtf(ox * ox + oy * oy + oz * oz + eps);
+            const float ks = js[4 * j + 3];
+            const float heat = (ks - dist) / ks;
+            const float msk = heat >= 0.f ? fg : 0.f;
+            ob[(size_t)(3 * j) * HW + m] = ox / dist * msk;
+            ob[(size_t)(3 * j + 1) * HW + m] = oy / dist * msk;
+            ob[(size_t)(3 * j + 2) * HW + m] = oz / dist * msk;
+            ob[(size_t)(3 * J + j) * HW + m] = heat * msk;
+        }
+    }
+}
+
+}  // namespace kpf
+
+using namespace kpf;
+
+extern "C" int kpf_uvd2xyz(const float* uvd, const float* center, const float* M, const float* cube, const float* cam, int B,
+                           int P, float img_size, float flip, float* out, cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && P >= 0);
+    if (B == 0 || P == 0) return 0;
+    dim3 grid((P + 255) / 256 > 64 ? 64 : (P + 255) / 256, B);
+    uvd2xyz_kernel<<<grid, 256, 0, stream>>>(uvd, center, M, cube, cam, P, img_size, flip, out);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_xyz2uvd(const float* xyz, const float* center, const float* M, const float* cube, const float* cam, int B,
+                           int P, float img_size, float flip, float* out, cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && P >= 0);
+    if (B == 0 || P == 0) return 0;
+    dim3 grid((P + 255) / 256 > 64 ? 64 : (P + 255) / 256, B);
+    xyz2uvd_kernel<<<grid, 256, 0, stream>>>(xyz, center, M, cube, cam, P, img_size, flip, out);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long depth_bs, int depth_rs, int depth_cs,
+                                 const float* center, const float* M, const float* cube, const float* cam, int B, int N, int fs,
+                                 float img_size, float flip, int K, float* closeness, long long* index64, int32_t* index32,
+                                 cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && N >= 0 && fs >= 1 && fs * fs <= 8192 && K >= 1 && K <= fs * fs);
+    if (B == 0 || N == 0) return 0;
+    dim3 grid((N + 255) / 256, B);
+    const size_t smem = (size_t)fs * fs * sizeof(float4);
+#define KPF_LAUNCH_K2(KK)                                                                                                    \
+    case KK: {                                                                                                               \
+        cudaError_t e = cudaFuncSetAttribute(nearest_cells_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e;                                                                                 \
+        nearest_cells_kernel<KK><<<grid, 256, smem, stream>>>(pcl, depth, depth_bs, depth_rs, depth_cs, center, M, cube, cam, N, \
+                                                             fs, img_size, flip, closeness, index64, index32);               \
+    } break;
+    switch (K) {
+        KPF_LAUNCH_K2(1)
+        KPF_LAUNCH_K2(2)
+        KPF_LAUNCH_K2(3)
+        KPF_LAUNCH_K2(4)
+        KPF_LAUNCH_K2(5)
+        KPF_LAUNCH_K2(6)
+        KPF_LAUNCH_K2(7)
+        KPF_LAUNCH_K2(8)
+        KPF_LAUNCH_K2(9)
+        KPF_LAUNCH_K2(16)
+        default:
+            return KPF_ERR_UNSUPPORTED;
+    }
+#undef KPF_LAUNCH_K2
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_offset2joint_weight(const void* offset, int dtype, const float* depth, int B, int J, int fs, int S,
+                                       const float* kernel_vec, float* joint_out, cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && J >= 1 && fs >= 1 && S >= fs);
+    if (B == 0) return 0;
+    dim3 grid(J, B);
+    if (dtype == KPF_F32)
+        offset2joint_kernel<float><<<grid, 256, 0, stream>>>((const float*)offset, depth, S, J, fs, kernel_vec, joint_out);
+    else if (dtype == KPF_BF16)
+        offset2joint_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)offset, depth, S, J, fs, kernel_vec, joint_out);
+    else
+        return KPF_ERR_UNSUPPORTED;
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_pcl_joint2offset(const float* joint, const float* pcl, const float* kernel_vec, int B, int J, int N,
+                                    float* out, cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && J >= 1 && N >= 0);
+    if (B == 0 || N == 0) return 0;
+    dim3 block(32, 8), grid((N + 7) / 8, B);
+    pcl_joint2offset_kernel<<<grid, block, 0, stream>>>(joint, pcl, kernel_vec, J, N, out);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_joint2heatmap(const float* joint, int joint_stride, int B, int J, int S, float stdv, float sigma, float* out,
+                                 cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && J >= 1 && S >= 1 && joint_stride >= 2);
+    if (B == 0) return 0;
+    dim3 grid((S * S + 255) / 256 > 16 ? 16 : (S * S + 255) / 256, B * J);
+    joint2heatmap_kernel<<<grid, 256, 0, stream>>>(joint, joint_stride, J, S, stdv, sigma, out);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_img2anchor_dis(const float* joint_uvd, const float* depth, long long depth_bs, int depth_rs, int depth_cs,
+                                  const float* center, const float* M, const float* cube, const float* cam, int B, int J, int fs,
+                                  float img_size, float flip, float gamma, float* out, cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && J >= 1 && fs >= 1);
+    if (B == 0) return 0;
+    dim3 grid((fs * fs + 255) / 256, B);
+    img2anchor_dis_kernel<<<grid, 256, (size_t)J * 3 * sizeof(float), stream>>>(joint_uvd, depth, depth_bs, depth_rs, depth_cs,
+                                                                              center, M, cube, cam, J, fs, img_size, flip, gamma, out);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_joint2offset(const float* joint, const float* depth, int B, int J, int S, int fs, const float* kernel_vec,
+                                float eps, float* out, cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && J >= 1 && fs >= 1 && S >= fs);
+    if (B == 0) return 0;
+    dim3 grid((fs * fs + 255) / 256, B);
+    joint2offset_kernel<<<grid, 256, (size_t)J * 4 * sizeof(float), stream>>>(joint, depth, S, J, fs, kernel_vec, eps, out);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,295 @@
+"""Tensor-level wrappers over the C ABI (include/kpf_b200.h) + `torch.library` custom-op registration.
+
+Each function validates shapes/dtypes/devices in Python, allocates outputs with torch (PyTorch owns all memory) and
+launches the kernel on `torch.cuda.current_stream()`.  There is NO fallback: non-CUDA tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("keypointfusion_b200 kernels need CUDA tensors (no CPU fallback exists for this path)")
+
+
+def _f32(t):
+    _need_cuda(t)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _feat(t):
+    _need_cuda(t)
+    if t.dtype not in _DT:
+        t = t.float()
+    return t.contiguous()
+
+
+def _call(name, *args):
+    rc = getattr(_lib.lib(), name)(*args, _stream())
+    _lib.check(rc, name)
+
+
+_kvec_cache = {}
+
+
+def kernel_vec(kernel_size, J, device):
+    """float or per-joint tensor (generateFeature.py:76-80, :188-192) -> device [J] f32."""
+    if torch.is_tensor(kernel_size):
+        return kernel_size.to(device=device, dtype=torch.float32).reshape(-1).expand(J).contiguous()
+    key = (float(kernel_size), J, str(device))
+    v = _kvec_cache.get(key)
+    if v is None:
+        v = _kvec_cache[key] = torch.full((J,), float(kernel_size), device=device, dtype=torch.float32)
+    return v
+
+
+def _depth_view(img, fs=None):
+    """[B,1,S,S] -> (tensor, batch stride, row stride, col stride, fs) addressing the nearest-down-sampled map
+    (model.py:409) without copying when S/fs is an integer."""
+    _need_cuda(img)
+    if img.dtype != torch.float32:
+        img = img.float()
+    B, _, S, S2 = img.shape
+    fs = S if fs is None else fs
+    if S != fs:
+        if S % fs == 0:
+            img = img[:, :, ::S // fs, ::S // fs]
+        else:
+            img = torch.nn.functional.interpolate(img, [fs, fs])
+    return img, img.stride(0), img.stride(2), img.stride(3), fs
+
+
+# ------------------------------------------------------------------------------------------------ a1-a3
+def getpcl(img, com3D, cube, M, cam, sample_num=1024, ranks=None, seed=0, clamp=False, flip=1.0):
+    img, com3D, cube, M, cam = _f32(img), _f32(com3D), _f32(cube), _f32(M), _f32(cam)
+    B, S = img.shape[0], img.shape[-1]
+    pcl = torch.empty(B, sample_num, 3, device=img.device, dtype=torch.float32)
+    count = torch.empty(B, device=img.device, dtype=torch.int32)
+    if ranks is not None:
+        _need_cuda(ranks)
+        ranks = ranks.to(torch.int32).contiguous()
+    _call("kpf_getpcl", _p(img), _p(com3D), _p(cube), _p(M), _p(cam), B, S, sample_num, _p(ranks), int(seed) & 0xFFFFFFFF,
+          int(bool(clamp)), float(flip), _p(pcl), _p(count))
+    return pcl, count
+
+
+def backproject_all(img, com3D, cube, M, cam, flip=1.0):
+    img, com3D, cube, M, cam = _f32(img), _f32(com3D), _f32(cube), _f32(M), _f32(cam)
+    B, S = img.shape[0], img.shape[-1]
+    xyz = torch.empty(B, S * S, 3, device=img.device, dtype=torch.float32)
+    pix = torch.empty(B, S * S, device=img.device, dtype=torch.int32)
+    count = torch.empty(B, device=img.device, dtype=torch.int32)
+    _call("kpf_backproject_all", _p(img), _p(com3D), _p(cube), _p(M), _p(cam), B, S, float(flip), _p(xyz), _p(pix), _p(count))
+    return xyz, pix, count
+
+
+# ------------------------------------------------------------------------------------------------ a5
+def uvd2xyz(uvd, center, M, cube, cam, img_size, flip=1.0):
+    uvd, center, M, cube, cam = _f32(uvd), _f32(center), _f32(M), _f32(cube), _f32(cam)
+    B, P, _ = uvd.shape
+    out = torch.empty_like(uvd)
+    _call("kpf_uvd2xyz", _p(uvd), _p(center), _p(M), _p(cube), _p(cam), B, P, float(img_size), float(flip), _p(out))
+    return out
+
+
+def xyz2uvd(xyz, center, M, cube, cam, img_size, flip=1.0):
+    xyz, center, M, cube, cam = _f32(xyz), _f32(center), _f32(M), _f32(cube), _f32(cam)
+    B, P, _ = xyz.shape
+    out = torch.empty_like(xyz)
+    _call("kpf_xyz2uvd", _p(xyz), _p(center), _p(M), _p(cube), _p(cam), B, P, float(img_size), float(flip), _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a6
+def img2pcl_index(pcl, img, center, M, cube, cam, img_size, select_num=9, flip=1.0, fs=None, want_i64=True, want_i32=False):
+    pcl, center, M, cube, cam = _f32(pcl), _f32(center), _f32(M), _f32(cube), _f32(cam)
+    d, bs, rs, cs, fs = _depth_view(img, fs)
+    B, N, _ = pcl.shape
+    close = torch.empty(B, N, select_num, device=pcl.device, dtype=torch.float32)
+    i64 = torch.empty(B, N, select_num, device=pcl.device, dtype=torch.int64) if want_i64 else None
+    i32 = torch.empty(B, N, select_num, device=pcl.device, dtype=torch.int32) if want_i32 else None
+    _call("kpf_img2pcl_index", _p(pcl), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam), B, N, fs, float(img_size),
+          float(flip), select_num, _p(close), _p(i64), _p(i32))
+    return close, i64, i32
+
+
+# ------------------------------------------------------------------------------------------------ a4
+def offset2joint_weight(offset, depth, kernel_size):
+    offset, depth = _feat(offset), _f32(depth)
+    B, C5, fs, _ = offset.shape
+    J = C5 // 5
+    out = torch.empty(B, J, 3, device=offset.device, dtype=torch.float32)
+    _call("kpf_offset2joint_weight", _p(offset), _DT[offset.dtype], _p(depth), B, J, fs, depth.shape[-1],
+          _p(kernel_vec(kernel_size, J, offset.device)), _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a7
+def pcl_joint2offset(joint, pcl, kernel_size):
+    joint, pcl = _f32(joint), _f32(pcl)
+    B, J, _ = joint.shape
+    N = pcl.shape[1]
+    out = torch.empty(B, N, 4 * J, device=pcl.device, dtype=torch.float32)
+    _call("kpf_pcl_joint2offset", _p(joint), _p(pcl), _p(kernel_vec(kernel_size, J, pcl.device)), B, J, N, _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a8
+def gather_taps(feat, index, closeness, out=None, out_c0=0):
+    """feat [B,C,H,W] or [B,C,HW] (a channel slice of a contiguous map is fine) -> [B,N,C] in feat's dtype."""
+    _need_cuda(feat, index, closeness)
+    if feat.dtype not in _DT:
+        feat = feat.float()
+    B, C = feat.shape[:2]
+    HW = feat[0, 0].numel()
+    inner_ok = feat[0].is_contiguous() if feat.dim() == 3 else feat[0].reshape(C, HW).is_contiguous()
+    if not inner_ok:
+        feat = feat.contiguous()
+    bs = feat.stride(0)
+    closeness = _f32(closeness)
+    N, K = index.shape[1:]
+    if index.dtype not in (torch.int64, torch.int32):
+        index = index.long()
+    index = index.contiguous()
+    if out is None:
+        out = torch.empty(B, N, C, device=feat.device, dtype=feat.dtype)
+        out_c0 = 0
+    assert out.dtype == feat.dtype and out.is_contiguous()
+    _call("kpf_gather_taps", _p(feat), _DT[feat.dtype], bs, B, C, HW, _p(index), int(index.dtype == torch.int64), _p(closeness), N, K,
+          _p(out), out.shape[-1], out_c0)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a10, a11, a16
+def joint2heatmap(joint, std, heatmap_size, sigma=1.5):
+    joint = _f32(joint)
+    B, J, D = joint.shape
+    out = torch.empty(B, J, heatmap_size, heatmap_size, device=joint.device, dtype=torch.float32)
+    _call("kpf_joint2heatmap", _p(joint), D, B, J, heatmap_size, float(std), float(sigma), _p(out))
+    return out
+
+
+def img2anchor_dis(joint_uvd, img, center, M, cube, cam, img_size, gamma=10, flip=1.0, fs=None):
+    joint_uvd, center, M, cube, cam = _f32(joint_uvd), _f32(center), _f32(M), _f32(cube), _f32(cam)
+    d, bs, rs, cs, fs = _depth_view(img, fs)
+    B, J, _ = joint_uvd.shape
+    out = torch.empty(B, J, fs, fs, device=joint_uvd.device, dtype=torch.float32)
+    _call("kpf_img2anchor_dis", _p(joint_uvd), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam), B, J, fs, float(img_size),
+          float(flip), float(gamma), _p(out))
+    return out
+
+
+def joint2offset(joint, img, kernel_size, feature_size, eps=1e-8):
+    img = _f32(img)
+    B, S = img.shape[0], img.shape[-1]
+    joint = _f32(joint.reshape(B, -1, 3))
+    J = joint.shape[1]
+    out = torch.empty(B, 4 * J, feature_size, feature_size, device=img.device, dtype=torch.float32)
+    _call("kpf_joint2offset", _p(joint), _p(img), B, J, S, feature_size, _p(kernel_vec(kernel_size, J, img.device)), float(eps), _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a12
+def spatial_aggregate(feat_rgb, joints, img, center, M, cube, cam, Wa, ba, weight_dis, fc_w, fc_b, prev=None, img_size=128,
+                      flip=1.0, hm_std=0.8, hm_sigma=1.0, gamma=10.0, want_maps=False):
+    feat_rgb = _feat(feat_rgb)
+    B, C, fs, _ = feat_rgb.shape
+    joints, center, M, cube, cam = _f32(joints), _f32(center), _f32(M), _f32(cube), _f32(cam)
+    J = joints.shape[1]
+    d, bs, rs, cs, fs = _depth_view(img, fs)
+    Wa, ba, weight_dis, fc_w, fc_b = _f32(Wa.reshape(J, C + J)), _f32(ba), _f32(weight_dis), _f32(fc_w.reshape(-1)), _f32(fc_b)
+    prev = _f32(prev) if prev is not None else None
+    dev = feat_rgb.device
+    sw = torch.empty(B, J, fs, fs, device=dev, dtype=torch.float32)
+    fj = torch.empty(B, J, C, device=dev, dtype=torch.float32)
+    hm = torch.empty_like(sw) if want_maps else None
+    gam = torch.empty_like(sw) if want_maps else None
+    _call("kpf_spatial_aggregate", _p(feat_rgb), _DT[feat_rgb.dtype], _p(joints), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube),
+          _p(cam), _p(Wa), _p(ba), _p(weight_dis), _p(fc_w), _p(fc_b), _p(prev), B, C, J, fs, float(img_size), float(flip),
+          float(hm_std), float(hm_sigma), float(gamma), _p(sw), _p(fj), _p(hm), _p(gam))
+    return (sw, fj, hm, gam) if want_maps else (sw, fj)
+
+
+# ------------------------------------------------------------------------------------------------ a13
+def pack_decoder_layer(sd, prefix, J, C):
+    """state_dict of one TransformerDecoderLayer -> the f32 blob kpf_cross_decoder_layer expects (kpf_b200.h)."""
+    g = lambda k: sd[prefix + k].detach().float()
+    Wi, bi = g("multihead_attn.in_proj_weight"), g("multihead_attn.in_proj_bias")
+    parts = [g("self_posembed.weight")[:J], g("cross_posembed.weight")[:J], Wi[:C].t(), bi[:C], Wi[C:].t(), bi[C:],
+             g("multihead_attn.out_proj.weight").t(), g("multihead_attn.out_proj.bias"), g("norm2.weight"), g("norm2.bias"),
+             g("linear1.weight").t(), g("linear1.bias"), g("linear2.weight").t(), g("linear2.bias"), g("norm3.weight"),
+             g("norm3.bias")]
+    return torch.cat([p.contiguous().reshape(-1) for p in parts]).contiguous()
+
+
+def cross_decoder_layer(anchor, tokens, wpack, heads, ffn, out_jc=None, out_jc_c0=0, want_cj=True):
+    anchor, tokens, wpack = _f32(anchor), _f32(tokens), _f32(wpack)
+    B, J, C = anchor.shape
+    out_cj = torch.empty(B, C, J, device=anchor.device, dtype=torch.float32) if want_cj else None
+    stride = out_jc.shape[-1] if out_jc is not None else 0
+    _call("kpf_cross_decoder_layer", _p(anchor), _p(tokens), _p(wpack), B, J, C, ffn, heads, _p(out_cj), _p(out_jc), stride, out_jc_c0)
+    return out_cj
+
+
+# ------------------------------------------------------------------------------------------------ a14, a15
+def channel_mean(x):
+    x = _feat(x)
+    B, C = x.shape[:2]
+    out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    _call("kpf_channel_mean", _p(x), _DT[x.dtype], B * C, x[0, 0].numel(), _p(out))
+    return out
+
+
+def rgbd_fusion(rgb, depth, gate_w, gate_b, want_attn_mean=False):
+    rgb, depth = _feat(rgb), _feat(depth)
+    if depth.dtype != rgb.dtype:
+        depth = depth.to(rgb.dtype)
+    B, C = rgb.shape[:2]
+    HW = rgb[0, 0].numel()
+    ro, do, mg = torch.empty_like(rgb), torch.empty_like(rgb), torch.empty_like(rgb)
+    asum = torch.zeros(2, device=rgb.device, dtype=torch.float32) if want_attn_mean else None
+    _call("kpf_rgbd_fusion", _p(rgb), _p(depth), _DT[rgb.dtype], _p(_f32(gate_w)), _p(_f32(gate_b)), B, C, HW, _p(ro), _p(do), _p(mg),
+          _p(asum))
+    return ro, do, mg, (asum / (B * HW) if want_attn_mean else None)
+
+
+def ac_fusion(rgb, depth, w_rgb, b_rgb, w_depth, b_depth):
+    rgb, depth = _feat(rgb), _feat(depth)
+    if depth.dtype != rgb.dtype:
+        depth = depth.to(rgb.dtype)
+    B, C = rgb.shape[:2]
+    HW = rgb[0, 0].numel()
+    mr, md = channel_mean(rgb), channel_mean(depth)
+    ro, do, mg = torch.empty_like(rgb), torch.empty_like(rgb), torch.empty_like(rgb)
+    _call("kpf_ac_fusion", _p(rgb), _p(depth), _DT[rgb.dtype], _p(mr), _p(md), _p(_f32(w_rgb.reshape(C, C))), _p(_f32(b_rgb)),
+          _p(_f32(w_depth.reshape(C, C))), _p(_f32(b_depth)), B, C, HW, _p(ro), _p(do), _p(mg))
+    return ro, do, mg
+
+
+def fsp(guide, main, w0, b0, w2, b2):
+    guide, main = _feat(guide), _feat(main)
+    if main.dtype != guide.dtype:
+        main = main.to(guide.dtype)
+    B, C = guide.shape[:2]
+    HW = guide[0, 0].numel()
+    out = torch.empty_like(main)
+    _call("kpf_fsp", _p(guide), _p(main), _DT[guide.dtype], _p(channel_mean(guide)), _p(channel_mean(main)), _p(_f32(w0)), _p(_f32(b0)),
+          _p(_f32(w2)), _p(_f32(b2)), B, C, w0.shape[0], HW, _p(out))
+    return out

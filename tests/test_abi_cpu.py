@@ -1,0 +1,30 @@
+"""CPU: the C-ABI library builds/loads and exports every symbol include/kpf_b200.h declares (no compute calls)."""
+import ctypes
+import os
+
+import pytest
+
+from keypointfusion_b200 import _lib
+
+
+def test_header_declares_entry_points():
+    protos = _lib.parse_header()
+    assert "kpf_getpcl" in protos and "kpf_img2pcl_index" in protos and "kpf_cross_decoder_layer" in protos
+    assert all(params[-1][1] == "stream" for name, params in protos.items() if name != "kpf_abi_version")
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        from keypointfusion_b200 import build
+        build.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _lib.parse_header():
+        assert hasattr(L, name), f"{name} declared in kpf_b200.h but not exported"
+    assert _lib.lib().kpf_abi_version() >= 1
+
+
+def test_no_fallback_on_cpu_tensors():
+    import torch
+    from keypointfusion_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.uvd2xyz(torch.zeros(1, 2, 3), torch.zeros(1, 3), torch.eye(3)[None], torch.ones(1, 3), torch.ones(1, 4), 128)
