@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- fusion-path throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--no-cpu-baseline]
+
+A "step" is one pass of the hot path over one batch of synthetic RGB-D crops: depth crop -> point cloud (K1) ->
+initial joints (K4a) -> nearest-cell indices (K2) -> 2 x Block_KPFusion -> final joints, fed with bf16 backbone feature
+maps of the default config (BASELINE.json configs[1]: fusion path only, batch 64, bf16, 1 x B200).  With N > 1 every
+rank runs its own batch (weak scaling; the path shards by sample) and the per-sample joints are all-gathered over NCCL,
+the one exchange step the path has.
+
+Prints ONE JSON line.  `--impl reference` times the reference algorithm's CPU implementation (the oracle port: the
+Python reference itself cannot travel to the GPU box) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from keypointfusion_b200.utils import synth  # noqa: E402
+
+J, C, S, N_PTS = 21, 128, 128, 1024
+H = S // 4
+# algorithmic bytes / FLOPs per sample of the whole fusion path (bf16 features)
+PATH_BYTES_PER_SAMPLE = (2 * C + 5 * J) * H * H * 2 + S * S * 4 + 76 + 4 * J * 12 + 2 * J * H * H * 4 + 2 * J * C * 4
+PATH_FLOPS_PER_SAMPLE = 871.5e6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_net(device):
+    from keypointfusion_b200.model.model import KPFusion
+    net = KPFusion(joint_num=J)
+    synth.fill_state_dict(net, seed=0)
+    return net.to(device).eval()
+
+
+def host_inputs(B, seed):
+    inp = synth.make_inputs(B, S, J, C, seed=seed)
+    for k in ("img_feat", "img_feat_rgb", "img_offset"):
+        inp[k] = inp[k].bfloat16()
+    inp.pop("img_rgb")
+    return inp
+
+
+def run_step(net, loader, d, seed):
+    """One pass of the hot path; returns the final joints [B,J,3] (normalised xyz)."""
+    from keypointfusion_b200 import ops
+    pcl, _ = ops.getpcl(d["img"], d["center"], d["cube"], d["M"], d["cam"], N_PTS, seed=seed)
+    res, sw, _ = net.forward_path(d["img_offset"], d["img_feat"], None, d["img_feat_rgb"], d["img"], pcl, loader, d["center"], d["M"],
+                                  d["cube"], d["cam"], 0.8)
+    return res[-1]
+
+
+def cpu_reference_leg(B, iters, warm=1):
+    """The reference algorithm on the host cores (oracle port), whole fusion path incl. getpcl. -> samples/s."""
+    from oracle import kpf_oracle as O  # cpu_baseline leg only
+    from keypointfusion_b200.model.model import KPFusion
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = KPFusion(joint_num=J)
+    p = synth.fill_state_dict(net, seed=0)
+    inp = synth.make_inputs(B, S, J, C, seed=100)
+    g = [inp[k].numpy() for k in ("center", "M", "cube", "cam")]
+
+    def once():
+        pcl = np.stack([O.getpcl_sample(inp["img"][b, 0].numpy(), g[0][b], g[2][b], g[1][b], g[3][b], seed=0, b=b)[0] for b in range(B)])
+        with torch.no_grad():
+            O.fusion_path(p, inp["img"], torch.from_numpy(pcl), inp["img_offset"], inp["img_feat"], inp["img_feat_rgb"], *g)
+    for _ in range(warm):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        once()
+    dt = time.perf_counter() - t0
+    return B * iters / dt, dt / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="kpf_b200")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also print per-stage CUDA-event times to stderr")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    B = a.batch
+    config = {"workload": "fusion path only (getpcl + offset2joint + img2pcl_index + 2 x Block_KPFusion), batch 64 synthetic RGB-D crops "
+                          "128x128, 21 joints, 1024 points, bf16 feature maps [BASELINE.json configs[1]]",
+              "batch_per_gpu": B, "parallelism": f"batch-sharded x{world}",
+              "l2": "inputs rotate over 4 resident sets (~200 MB) > 126 MB L2; no flush kernel inside the timed region"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sample_B = 16
+        iters = max(1, min(a.steps, 6))
+        v, s_it = cpu_reference_leg(sample_B, iters, warm=min(a.warmup, 1))
+        cores = os.cpu_count()
+        line = {"impl": "reference", "metric": "fusion-path RGB-D samples/sec", "value": v, "unit": "samples/s", "n_gpus": a.gpus,
+                "steps": iters, "warmup": min(a.warmup, 1), "ms_per_step": s_it * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                                 "sample": f"{iters} passes over a {sample_B}-crop slice of the batch-64 workload, torch threads={cores}"},
+                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the fusion path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from keypointfusion_b200 import ops
+    from keypointfusion_b200.dataloader.loader import loader as Loader
+    net = build_net(dev)
+    ldr = Loader(img_size=S)
+    NSETS = 4
+    hosts = [host_inputs(B, seed=1000 * rank + s) for s in range(NSETS)]
+    sets = [{k: v.to(dev) for k, v in h.items()} for h in hosts]
+    pinned = [{k: v.pin_memory() for k, v in h.items()} for h in hosts]
+    gathered = torch.empty(world * B, J, 3, device=dev) if world > 1 else None
+
+    def step(i, d):
+        joints = run_step(net, ldr, d, seed=i)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, joints.contiguous())  # the path's one exchange step
+        return joints
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for i in range(warmup):
+                fn(i)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                fn(warmup + i)
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    W = max(a.warmup, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = ops.launch_count()
+    ms = timed(lambda i: step(i, sets[i % NSETS]), a.steps, W)
+    launches = (ops.launch_count() - n0) * a.steps // (a.steps + W)
+    clocks = sampler.stop()
+
+    # end to end through the public API: pinned host buffers -> H2D -> path -> D2H joints, every step
+    h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
+    out_host = torch.empty(B, J, 3).pin_memory()
+
+    def e2e_step(i):
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % NSETS].items()}
+        out_host.copy_(step(i, d), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the joints on the host every step
+    ms_e2e = timed(e2e_step, a.steps, W)
+
+    value = world * B * a.steps / (ms / 1e3)
+    e2e = world * B * a.steps / (ms_e2e / 1e3)
+    hbm, tfl, which = load_peaks()
+
+    # dominant kernel of the step: measured live, CUDA events on the launching stream
+    roof = dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, a.breakdown and rank == 0)
+
+    line = {"metric": "fusion-path RGB-D samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": W,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * J * 3 * 4},
+            "gpu_launches": launches, "roofline": roof,
+            "path_roofline": {"hbm_frac": value / world * PATH_BYTES_PER_SAMPLE / (hbm * 1e9),
+                              "tensor_frac": value / world * PATH_FLOPS_PER_SAMPLE / (tfl * 1e12), "peaks": which}}
+    if rank == 0:
+        if world == 1 and not a.no_cpu_baseline:
+            sample_B, iters = 16, 3
+            v, s_it = cpu_reference_leg(sample_B, iters)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{iters} passes over a {sample_B}-crop slice of the workload, torch threads={os.cpu_count()}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
+    """Time each stage of the step alone with CUDA events (inputs rotate so they come from HBM, not L2) and report the
+    roofline of the heaviest of OUR kernels."""
+    from keypointfusion_b200 import ops
+    d0 = sets[0]
+    B = d0["img"].shape[0]
+    with torch.no_grad():
+        pcl, _ = ops.getpcl(d0["img"], d0["center"], d0["cube"], d0["M"], d0["cam"], N_PTS, seed=0)
+        close, _, idx = ops.img2pcl_index(pcl, d0["img"], d0["center"], d0["M"], d0["cube"], d0["cam"], S, 4, fs=H, want_i64=False, want_i32=True)
+        joints = torch.rand(B, J, 3, device=pcl.device) * 1.2 - 0.6
+    blk = net.block1
+    e = 2  # bf16
+    stages = {
+        "backproject_kernel (K1)": (lambda d: ops.getpcl(d["img"], d["center"], d["cube"], d["M"], d["cam"], N_PTS, seed=0),
+                                    B * (S * S * 4 + 76 + N_PTS * 12), "hbm"),
+        "nearest_cells_kernel (K2)": (lambda d: ops.img2pcl_index(pcl, d["img"], d["center"], d["M"], d["cube"], d["cam"], S, 4, fs=H,
+                                                                  want_i64=False, want_i32=True),
+                                      B * (N_PTS * 12 + H * H * 4 + 76 + N_PTS * 4 * 8), "hbm"),
+        "gather_taps_kernel x3 (K3)": (lambda d: (ops.gather_taps(d["img_feat"], idx, close), ops.gather_taps(d["img_feat_rgb"], idx, close),
+                                                  ops.gather_taps(d["img_offset"][:, 4 * J:], idx, close)),
+                                       B * ((2 * C + J) * H * H * e + N_PTS * 4 * 8 + (2 * C + J) * N_PTS * e), "hbm"),
+        "offset2joint_kernel (K4a)": (lambda d: ops.offset2joint_weight(d["img_offset"], d["img"], 0.8), B * (5 * J * H * H * e + H * H * 4), "hbm"),
+        "spatial_aggregate_kernel (K5)": (lambda d: ops.spatial_aggregate(d["img_feat_rgb"], joints, d["img"][:, :, ::4, ::4], d["center"], d["M"],
+                                                                           d["cube"], d["cam"], blk.atten_spatial.weight, blk.atten_spatial.bias,
+                                                                           blk.weight_dis, blk.fc_spatial2joint_feature.weight,
+                                                                           blk.fc_spatial2joint_feature.bias),
+                                          B * (C * H * H * e + J * H * H * 4 + J * C * 4), "hbm"),
+    }
+    res = {}
+    for name, (fn, alg_bytes, bound) in stages.items():
+        with torch.no_grad():
+            for i in range(3):
+                fn(sets[i % len(sets)])
+            torch.cuda.synchronize()
+            reps = 20
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                fn(sets[i % len(sets)])
+            e1.record()
+            torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        res[name] = (us, alg_bytes)
+        if verbose:
+            print(f"[breakdown] {name:34s} {us:9.1f} us  {alg_bytes / us / 1e3:8.1f} GB/s algorithmic", file=sys.stderr)
+    top = max(res, key=lambda k: res[k][0])
+    us, alg = res[top]
+    ach = alg / (us * 1e-6) / 1e9
+    return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+            "us_per_launch": us, "algorithmic_bytes": alg, "peaks": which}
+
+
+if __name__ == "__main__":
+    main()

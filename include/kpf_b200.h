@@ -128,6 +128,12 @@ int kpf_ac_fusion(const void* rgb, const void* depth, int dtype, const float* me
 int kpf_fsp(const void* guide, const void* mainp, int dtype, const float* mean_guide, const float* mean_main, const float* w0,
             const float* b0, const float* w2, const float* b2, int B, int C, int Hd, int HW, void* out, cudaStream_t stream);
 
+/* ---- 8f-1  model/model.py:158,:174 pointnet2_ops QueryAndGroup's ball query (pointnet2_ops 3.0.0, not vendored) ----
+ * xyz [B,Np,3], centers [B,J,3] -> idx_out [B,J,nsample] i32: first nsample indices (ascending) with d2 < r^2,
+ * remaining slots = first hit (0 if none). */
+int kpf_ball_query(const float* xyz, const float* centers, int B, int Np, int J, float radius, int nsample, int32_t* idx_out,
+                   cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

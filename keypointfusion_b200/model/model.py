@@ -1,0 +1,420 @@
+"""Drop-in for the hot-path part of the reference's model/model.py: module functions (model.py:429-585),
+TR_Encoder / KP_Interaction_TR (:30-126), DESA (:129-204), Block_KPFusion (:207-351) and the KPFusion glue (:354-426),
+with the reference's names, forward signatures, tensor layouts and state_dict keys (tests/golden/golden_meta.json).
+
+Everything after the two backbones runs on the B200 kernels behind include/kpf_b200.h.  Inference only: BatchNorm uses
+running statistics (folded into the preceding 1x1 conv), dropout is identity, no autograd through the kernels.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..util.generateFeature import GFM
+from ..util.img2pcl import Pcl_utils
+from .transfusion_head import updatedDecoder
+
+BN_MOMENTUM = 0.1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# module-level functions (model/model.py:429-585)
+# ----------------------------------------------------------------------------------------------------------------------
+def img2pcl(img):  # model.py:429-437
+    B, _, W, H = img.size()
+    t = 2.0 * (torch.arange(W, device=img.device, dtype=torch.float32) + 0.5) / W - 1.0
+    u = t.view(1, 1, 1, W).expand(B, 1, W, W)
+    v = t.view(1, 1, W, 1).expand(B, 1, W, W)
+    return torch.cat((u, v, img), dim=1).view(B, 3, H * W).permute(0, 2, 1)
+
+
+def joint2offset(joint, img, kernel_size, feature_size):  # model.py:440-463 (no +1e-8 under the sqrt, :455)
+    return ops.joint2offset(joint, img, kernel_size, feature_size, eps=0.0)
+
+
+def offset2joint_weight(offset, depth, kernel_size):  # model.py:466-500
+    return ops.offset2joint_weight(offset, depth, kernel_size)
+
+
+def pcl_joint2offset(joint, pcl, kernel_size):  # model.py:503-525
+    return ops.pcl_joint2offset(joint, pcl, kernel_size)
+
+
+def pcl_offset2joint_weight(pcl_result, pcl, kernel_size):  # model.py:528-555 (no caller in the reference)
+    B, N, C5 = pcl_result.shape
+    J = C5 // 5
+    r = pcl_result.permute(0, 2, 1)
+    offset, heat, weight = r[:, :J * 3].reshape(B, J, 3, N), r[:, J * 3:J * 4].reshape(B, J, 1, N), r[:, J * 4:].reshape(B, J, 1, N)
+    w = F.softmax(weight.masked_fill(pcl[:, :, 2].gt(0.99).view(B, 1, 1, N), -1e8), dim=-1)
+    k = ops.kernel_vec(kernel_size, J, pcl.device).view(1, J, 1, 1)
+    return torch.sum((offset * (k - heat * k) + pcl.permute(0, 2, 1).reshape(B, 1, 3, N)) * w, dim=-1)
+
+
+def _fold_bn(conv_w, conv_b, bn):
+    """eval-mode BatchNorm folded into the preceding 1x1 conv: y = s*(Wx+b-mean)+beta."""
+    s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    W = conv_w.reshape(conv_w.shape[0], -1) * s[:, None]
+    b = (conv_b - bn.running_mean) * s + bn.bias
+    return W.contiguous(), b.contiguous()
+
+
+class _KernelCache:
+    """Mixin: lazily built, device-resident folded/packed weights, dropped whenever parameters move or are reloaded."""
+
+    def invalidate(self):
+        self.__dict__["_kc"] = None
+        for m in self.children():
+            if hasattr(m, "invalidate"):
+                m.invalidate()
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__["_kc"] = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self.invalidate()
+        return super().load_state_dict(*a, **k)
+
+    def kc(self):
+        c = self.__dict__.get("_kc")
+        if c is None:
+            with torch.no_grad():
+                c = self._build_kc()
+            self.__dict__["_kc"] = c
+        return c
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BERT-style token encoder (model/model.py:30-126; transformers 4.25.1 BertEncoder).  Own minimal module tree with the
+# reference's state_dict keys -- including the BertEmbeddings / BertPooler tables the reference constructs but never
+# calls (model.py:35, :37) -- so checkpoints load unchanged and `transformers` is not needed on the path.
+# ----------------------------------------------------------------------------------------------------------------------
+class _Cfg:
+    def __init__(self, **kw):
+        self.vocab_size, self.max_position_embeddings, self.type_vocab_size = 30522, 512, 2  # config/config.json
+        self.hidden_size, self.num_hidden_layers, self.num_attention_heads, self.intermediate_size = 128, 4, 4, 16
+        self.layer_norm_eps, self.initializer_range, self.hidden_dropout_prob = 1e-12, 0.02, 0.1
+        self.img_feature_dim, self.output_feature_dim = 128, 3
+        self.__dict__.update(kw)
+
+
+class _BertEmbeddings(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(c.vocab_size, c.hidden_size)
+        self.position_embeddings = nn.Embedding(c.max_position_embeddings, c.hidden_size)
+        self.token_type_embeddings = nn.Embedding(c.type_vocab_size, c.hidden_size)
+        self.LayerNorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+
+
+class _BertSelfAttention(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.query, self.key, self.value = (nn.Linear(c.hidden_size, c.hidden_size) for _ in range(3))
+
+
+class _BertSelfOutput(nn.Module):
+    def __init__(self, c, d_in):
+        super().__init__()
+        self.dense = nn.Linear(d_in, c.hidden_size)
+        self.LayerNorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+
+
+class _BertAttention(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.self = _BertSelfAttention(c)
+        self.output = _BertSelfOutput(c, c.hidden_size)
+
+
+class _BertIntermediate(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.dense = nn.Linear(c.hidden_size, c.intermediate_size)
+
+
+class _BertLayer(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.attention = _BertAttention(c)
+        self.intermediate = _BertIntermediate(c)
+        self.output = _BertSelfOutput(c, c.intermediate_size)
+
+
+class _BertEncoder(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.layer = nn.ModuleList([_BertLayer(c) for _ in range(c.num_hidden_layers)])
+
+
+class _BertPooler(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.dense = nn.Linear(c.hidden_size, c.hidden_size)
+
+
+def _bert_init(module, std):
+    for m in module.modules():  # BertPreTrainedModel._init_weights
+        if isinstance(m, nn.Linear):
+            m.weight.data.normal_(mean=0.0, std=std)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, nn.Embedding):
+            m.weight.data.normal_(mean=0.0, std=std)
+        elif isinstance(m, nn.LayerNorm):
+            m.bias.data.zero_()
+            m.weight.data.fill_(1.0)
+
+
+class TR_Encoder(nn.Module):  # model.py:30-103
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.embeddings = _BertEmbeddings(config)
+        self.encoder = _BertEncoder(config)
+        self.pooler = _BertPooler(config)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size)
+        self.img_dim = config.img_feature_dim
+        self.img_embedding = nn.Linear(self.img_dim, config.hidden_size, bias=True)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        _bert_init(self, config.initializer_range)
+
+
+class KP_Interaction_TR(_KernelCache, nn.Module):  # model.py:106-126
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.bert = TR_Encoder(config)
+        self.cls_head = nn.Linear(config.hidden_size, config.output_feature_dim)
+        self.residual = nn.Linear(config.img_feature_dim, config.output_feature_dim)
+        _bert_init(self, config.initializer_range)
+
+    def _build_kc(self):
+        return None
+
+    def forward(self, img_feats, *unused, **unused_kw):
+        """img_feats [B,J,D] -> (tokens [B,J,hidden], pred [B,J,3]).  model.py:45-103, :116-126."""
+        c = self.config
+        B, L, _ = img_feats.shape
+        x = img_feats.float()
+        h = self.bert.position_embeddings.weight[:L].unsqueeze(0) + F.linear(x, self.bert.img_embedding.weight, self.bert.img_embedding.bias)
+        H, hd = c.num_attention_heads, c.hidden_size // c.num_attention_heads
+        for lyr in self.bert.encoder.layer:
+            a = lyr.attention
+            q = a.self.query(h).view(B, L, H, hd).transpose(1, 2)
+            k = a.self.key(h).view(B, L, H, hd).transpose(1, 2)
+            v = a.self.value(h).view(B, L, H, hd).transpose(1, 2)
+            ctx = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, c.hidden_size)
+            h = a.output.LayerNorm(a.output.dense(ctx) + h)
+            h = lyr.output.LayerNorm(lyr.output.dense(F.gelu(lyr.intermediate.dense(h))) + h)
+        pred = self.cls_head(h) + self.residual(x)
+        return h, pred
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# DESA (model/model.py:129-204) -- pointnet2_ops' QueryAndGroup replaced by the kpf_ball_query kernel
+# ----------------------------------------------------------------------------------------------------------------------
+class DESA(_KernelCache, nn.Module):
+    def __init__(self, in_channel, mlp, S=[64, 64, 64], radius=[0.1, 0.2, 0, 4]):
+        super(DESA, self).__init__()
+        self.S, self.radius, self.scale_num = S, radius, len(radius)
+        self.groupers = nn.ModuleList()  # parameter-free in the reference (QueryAndGroup)
+        self.conv_blocks, self.bn_blocks = nn.ModuleList(), nn.ModuleList()
+        self.conv_l0_blocks, self.conv_f0_blocks = nn.ModuleList(), nn.ModuleList()
+        self.bn_l0_blocks, self.bn_f0_blocks = nn.ModuleList(), nn.ModuleList()
+        for i in range(self.scale_num):
+            self.conv_l0_blocks.append(nn.Conv2d(3, mlp[0], 1))
+            self.conv_f0_blocks.append(nn.Conv2d(in_channel, mlp[0], 1))
+            self.bn_l0_blocks.append(nn.BatchNorm2d(mlp[0]))
+            self.bn_f0_blocks.append(nn.BatchNorm2d(mlp[0]))
+            last_channel = mlp[0]
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            for out_channel in mlp[1:]:
+                convs.append(nn.Conv2d(last_channel, out_channel, 1))
+                bns.append(nn.BatchNorm2d(out_channel))
+                last_channel = out_channel
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self.fusion = nn.Sequential(nn.Conv1d(in_channel + mlp[-1] * self.scale_num, in_channel, 1), nn.BatchNorm1d(in_channel),
+                                    nn.ReLU())
+
+    def _build_kc(self):
+        k = {"l0": [], "f0": [], "mlp": []}
+        for i in range(self.scale_num):
+            k["l0"].append(_fold_bn(self.conv_l0_blocks[i].weight, self.conv_l0_blocks[i].bias, self.bn_l0_blocks[i]))
+            k["f0"].append(_fold_bn(self.conv_f0_blocks[i].weight, self.conv_f0_blocks[i].bias, self.bn_f0_blocks[i]))
+            k["mlp"].append([_fold_bn(c.weight, c.bias, b) for c, b in zip(self.conv_blocks[i], self.bn_blocks[i])])
+        k["fusion"] = _fold_bn(self.fusion[0].weight, self.fusion[0].bias, self.fusion[1])
+        return k
+
+    def forward(self, pcl_feat, node_feat, pcl_xyz, node_xyz):
+        """pcl_feat [B,N,C], node_feat [B,J,C], pcl_xyz [B,N,3], node_xyz [B,J,3] -> [B,J,C].  model.py:166-204."""
+        k = self.kc()
+        B, J, C = node_feat.shape
+        xyz = torch.cat((pcl_xyz, node_xyz), dim=1).contiguous()
+        feat = torch.cat((pcl_feat, node_feat), dim=1)
+        bi = torch.arange(B, device=xyz.device).view(B, 1, 1)
+        outs = []
+        for i in range(self.scale_num):
+            r = self.radius[i]
+            idx = ops.ball_query(xyz, node_xyz, r, self.S[i]).long()
+            gx = (xyz[bi, idx] - node_xyz.unsqueeze(2)) / r
+            gf = feat[bi, idx] - node_feat.unsqueeze(2)
+            g = F.relu(F.linear(gx, *k["l0"][i]) + F.linear(gf, *k["f0"][i]))
+            for W, b in k["mlp"][i]:
+                g = F.relu(F.linear(g, W, b))
+            outs.append(g.max(dim=2)[0])
+        outs.append(node_feat)
+        return F.relu(F.linear(torch.cat(outs, dim=-1), *k["fusion"]))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Block_KPFusion (model/model.py:207-351)
+# ----------------------------------------------------------------------------------------------------------------------
+class Block_KPFusion(_KernelCache, nn.Module):
+    def __init__(self, joint_num=21, feature_size=128, num_points=4):
+        super(Block_KPFusion, self).__init__()
+        self.joint_num = joint_num
+        self.dim = 128
+        self.feature_size = feature_size
+        self.num_points = num_points
+        # unused by forward in the reference too, kept for the state_dict contract (model.py:217-219)
+        self.sampling_offsets = nn.Linear(self.feature_size, 2 * self.num_points, bias=True)
+        self.attention_weights = nn.Linear(self.feature_size, self.num_points, bias=True)
+        self.sampling_feature_embding = nn.Linear(self.dim, self.dim, bias=True)
+
+        self.FA = DESA(128, [128, 128], [64, 64, 64], [0.1, 0.2, 0.4])
+        self.init_TR = KP_Interaction_TR(_Cfg(img_feature_dim=128))     # model.py:222-233
+        self.final_TR = KP_Interaction_TR(_Cfg(img_feature_dim=131))    # model.py:235-245
+        self.crossTR = updatedDecoder(joint_num=joint_num, hidden_channel=128, num_heads=4, ffn_channel=128, dropout=0.1,
+                                      num_decoder_layers=4, activation='relu')  # model.py:246-252
+
+        def cb(i, o):
+            return nn.Sequential(nn.Conv1d(i, o, 1), nn.BatchNorm1d(o))
+        self.pcl_feat_emb = cb(self.dim, self.dim)
+        self.pcl_xyz_emb = cb(3, self.dim)
+        self.pcl_pose_emb = cb(self.joint_num * 5, self.dim)
+        self.joint_feat_emb = cb(self.dim, self.dim)
+        self.joint_xyz_emb = cb(3, self.dim)
+        self.pcl_feat_emb_RGB = cb(self.dim, self.dim)
+
+        self.sigmoid = nn.Sigmoid()
+        self.atten_spatial = nn.Conv2d(feature_size + joint_num, joint_num, kernel_size=1, stride=1, bias=True)
+        self.fc_spatial2joint_feature = nn.Linear(32 * 32, 1, bias=True)
+        self.reduction_joint_feature = nn.Linear(self.dim * 2, self.dim, bias=True)
+        self.reduction_joint_feature_update = nn.Conv1d(joint_num * 3, joint_num, kernel_size=1, stride=1)
+        self.softmax = nn.Softmax(dim=-1)
+        self.apply(self._init_weights)                                  # model.py:269
+        self.cls_head = nn.Linear(128, 3)                               # model.py:270 (after apply)
+        self.weight_dis = nn.Parameter(torch.zeros([1]))
+        self.GFM_ = GFM()
+
+    def _init_weights(self, m):  # model.py:275-285
+        if isinstance(m, nn.Conv2d):
+            n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+            m.weight.data.normal_(0, math.sqrt(2. / n))
+        elif isinstance(m, nn.BatchNorm2d):
+            m.weight.data.fill_(1)
+            m.bias.data.zero_()
+        elif isinstance(m, nn.Linear):
+            m.weight.data.normal_(0, 0.001)
+        elif isinstance(m, nn.ConvTranspose2d):
+            nn.init.normal_(m.weight, std=0.001)
+
+    def _build_kc(self):
+        Wf, bf = _fold_bn(self.pcl_feat_emb[0].weight, self.pcl_feat_emb[0].bias, self.pcl_feat_emb[1])
+        Wx, bx = _fold_bn(self.pcl_xyz_emb[0].weight, self.pcl_xyz_emb[0].bias, self.pcl_xyz_emb[1])
+        Wp, bp = _fold_bn(self.pcl_pose_emb[0].weight, self.pcl_pose_emb[0].bias, self.pcl_pose_emb[1])
+        Wr, br = _fold_bn(self.pcl_feat_emb_RGB[0].weight, self.pcl_feat_emb_RGB[0].bias, self.pcl_feat_emb_RGB[1])
+        Wj, bj = _fold_bn(self.joint_feat_emb[0].weight, self.joint_feat_emb[0].bias, self.joint_feat_emb[1])
+        Wjx, bjx = _fold_bn(self.joint_xyz_emb[0].weight, self.joint_xyz_emb[0].bias, self.joint_xyz_emb[1])
+        return dict(W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
+                    W_joint=torch.cat([Wj, Wjx], 1).contiguous(), b_joint=(bj + bjx).contiguous())
+
+    def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
+                img_down, center, M, cube, cam_para, writer=None, ii=0):
+        k = self.kc()
+        B, N, _ = pcl.shape
+        C, H = img_feat.shape[1], img_feat.shape[2]
+        J = self.joint_num
+        pcl = pcl.float().contiguous()
+        joint_xyz = joint_xyz.detach().float().contiguous()
+        # RGB keypoint aggregation (model.py:295-306): K4b + K3
+        pcl_offset = ops.pcl_joint2offset(joint_xyz, pcl, 0.8)
+        pcl_feat = ops.gather_taps(img_feat, pcl_index, pcl_closeness).float()
+        pcl_feat_rgb = ops.gather_taps(img_feature_rgb, pcl_index, pcl_closeness).float()
+        pcl_weight = ops.gather_taps(img_offset[:, J * 4:], pcl_index, pcl_closeness).float()
+        # decoupled generation of RGB-D point features (model.py:312-317): folded Conv1d+BN embeddings
+        e = F.relu(F.linear(torch.cat((pcl_feat, pcl, pcl_weight, pcl_offset), dim=-1), k["W_pcl"], k["b_pcl"]))
+        e = F.relu(e + F.linear(pcl_feat_rgb, k["W_rgb"], k["b_rgb"]))
+        attention = F.softmax(pcl_weight.permute(0, 2, 1), dim=-1)                       # model.py:319
+        joint_feat = torch.matmul(attention, e)                                          # model.py:320
+        joint_feat = F.relu(F.linear(torch.cat((joint_feat, joint_xyz), dim=-1), k["W_joint"], k["b_joint"]))  # :323-325
+        joint_feat = self.FA(e, joint_feat, pcl, joint_xyz)                              # model.py:327
+        outfeature_init_TR, refined_3d_joints = self.init_TR(joint_feat)                 # model.py:330
+        # depth keypoint aggregation (model.py:334-344): K4c + K5 fused
+        spatial_weight_loss, img_feat_j = ops.spatial_aggregate(
+            img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, self.atten_spatial.weight,
+            self.atten_spatial.bias, self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias,
+            prev=updated_2d_feature, img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)
+        # inter-modal keypoint feature interaction (model.py:347-349): K6 writes straight into final_TR's input
+        tr_in = torch.empty(B, J, 3 + self.dim, device=pcl.device, dtype=torch.float32)
+        tr_in[:, :, :3] = refined_3d_joints
+        self.crossTR(img_feat_j, outfeature_init_TR, out_jc=tr_in, out_jc_c0=3, want_cj=False)
+        _, refined_2d_joints = self.final_TR(tr_in)
+        return refined_3d_joints, refined_2d_joints, img_feat_j, spatial_weight_loss, None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# KPFusion glue (model/model.py:354-426)
+# ----------------------------------------------------------------------------------------------------------------------
+class KPFusion(nn.Module):
+    """The reference builds its two backbones by name (model.py:363-373); they stay stock PyTorch and are passed in here
+    (`backbone_rgb`, `backbone_d`: img -> (img_offset [B,5J,H,W], img_feat [B,128,H,W])).  With no backbones the module
+    is the fusion path only (BASELINE.json config 2) and is driven through `forward_path`."""
+
+    def __init__(self, net='KPFusion', pretrain='', joint_num=21, dataset='dexycb', mano_dir='', kernel_size=1, backbone_rgb=None,
+                 backbone_d=None):
+        super(KPFusion, self).__init__()
+        self.joint_num, self.kernel_size, self.dim, self.classify_out, self.num_stages, self.net = joint_num, kernel_size, 128, 3, 2, net
+        if backbone_rgb is not None:
+            self.backbone_rgb = backbone_rgb
+        if backbone_d is not None:
+            self.backbone_d = backbone_d
+        self.sigmoid = nn.Sigmoid()
+        self.softmax = nn.Softmax(dim=-1)
+        self.pcl_utils = Pcl_utils()
+        for i in range(self.num_stages):
+            setattr(self, f"block{i + 1}", Block_KPFusion(joint_num=joint_num))
+
+    def forward_path(self, img_offset, img_feat, img_offset_rgb, img_feat_rgb, img, pcl, loader, center, M, cube, cam_para, kernel=0.8,
+                     writer=None, ii=0):
+        """model.py:399-426: everything after the backbones."""
+        J = self.joint_num
+        H = img_feat.shape[2]
+        joint_uvd = ops.offset2joint_weight(img_offset, img, kernel)                                     # :399
+        result = [img_offset, img_offset_rgb]
+        S = img.shape[-1]
+        img_down = img[:, :, ::S // H, ::S // H] if S % H == 0 else F.interpolate(img, [H, H])           # :409, zero-copy view
+        joint_xyz = ops.uvd2xyz(joint_uvd, center, M, cube, cam_para, loader.img_size, loader.flip)      # :410
+        pcl_closeness, _, pcl_index = ops.img2pcl_index(pcl, img_down, center, M, cube, cam_para, loader.img_size, 4, loader.flip,
+                                                        want_i64=False, want_i32=True)                  # :411
+        updated_2d_feature = [None] * (self.num_stages + 1)
+        spatial_weight = [None] * self.num_stages
+        for i in range(self.num_stages):                                                                 # :417-424
+            block = getattr(self, f"block{i + 1}")
+            r3d, r2d, updated_2d_feature[i + 1], spatial_weight[i], _ = block(
+                img_feat, img_feat_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature[i], loader, img_down,
+                center, M, cube, cam_para, writer, ii)
+            result.append(r3d)
+            result.append(r2d)
+            joint_xyz = r2d
+        return result, spatial_weight, None
+
+    def forward(self, img_rgb, img, pcl, loader, center, M, cube, cam_para, kernel=0.8, writer=None, ii=0):
+        img_offset, img_feat = self.backbone_d(img)              # model.py:397 (stock PyTorch)
+        img_offset_rgb, img_feat_rgb = self.backbone_rgb(img_rgb)  # model.py:398
+        return self.forward_path(img_offset.detach(), img_feat, img_offset_rgb, img_feat_rgb, img, pcl, loader, center, M, cube,
+                                 cam_para, kernel, writer, ii)

@@ -41,9 +41,19 @@ def _feat(t):
     return t.contiguous()
 
 
+_launches = 0
+
+
+def launch_count():
+    """Number of kernel-launching C-ABI calls made so far by this process (bench.py's `gpu_launches` evidence)."""
+    return _launches
+
+
 def _call(name, *args):
+    global _launches
     rc = getattr(_lib.lib(), name)(*args, _stream())
     _lib.check(rc, name)
+    _launches += 1
 
 
 _kvec_cache = {}
@@ -136,8 +146,8 @@ def offset2joint_weight(offset, depth, kernel_size):
     B, C5, fs, _ = offset.shape
     J = C5 // 5
     out = torch.empty(B, J, 3, device=offset.device, dtype=torch.float32)
-    _call("kpf_offset2joint_weight", _p(offset), _DT[offset.dtype], _p(depth), B, J, fs, depth.shape[-1],
-          _p(kernel_vec(kernel_size, J, offset.device)), _p(out))
+    kv = kernel_vec(kernel_size, J, offset.device)
+    _call("kpf_offset2joint_weight", _p(offset), _DT[offset.dtype], _p(depth), B, J, fs, depth.shape[-1], _p(kv), _p(out))
     return out
 
 
@@ -147,7 +157,8 @@ def pcl_joint2offset(joint, pcl, kernel_size):
     B, J, _ = joint.shape
     N = pcl.shape[1]
     out = torch.empty(B, N, 4 * J, device=pcl.device, dtype=torch.float32)
-    _call("kpf_pcl_joint2offset", _p(joint), _p(pcl), _p(kernel_vec(kernel_size, J, pcl.device)), B, J, N, _p(out))
+    kv = kernel_vec(kernel_size, J, pcl.device)
+    _call("kpf_pcl_joint2offset", _p(joint), _p(pcl), _p(kv), B, J, N, _p(out))
     return out
 
 
@@ -202,7 +213,8 @@ def joint2offset(joint, img, kernel_size, feature_size, eps=1e-8):
     joint = _f32(joint.reshape(B, -1, 3))
     J = joint.shape[1]
     out = torch.empty(B, 4 * J, feature_size, feature_size, device=img.device, dtype=torch.float32)
-    _call("kpf_joint2offset", _p(joint), _p(img), B, J, S, feature_size, _p(kernel_vec(kernel_size, J, img.device)), float(eps), _p(out))
+    kv = kernel_vec(kernel_size, J, img.device)
+    _call("kpf_joint2offset", _p(joint), _p(img), B, J, S, feature_size, _p(kv), float(eps), _p(out))
     return out
 
 
@@ -265,8 +277,8 @@ def rgbd_fusion(rgb, depth, gate_w, gate_b, want_attn_mean=False):
     HW = rgb[0, 0].numel()
     ro, do, mg = torch.empty_like(rgb), torch.empty_like(rgb), torch.empty_like(rgb)
     asum = torch.zeros(2, device=rgb.device, dtype=torch.float32) if want_attn_mean else None
-    _call("kpf_rgbd_fusion", _p(rgb), _p(depth), _DT[rgb.dtype], _p(_f32(gate_w)), _p(_f32(gate_b)), B, C, HW, _p(ro), _p(do), _p(mg),
-          _p(asum))
+    gate_w, gate_b = _f32(gate_w), _f32(gate_b)
+    _call("kpf_rgbd_fusion", _p(rgb), _p(depth), _DT[rgb.dtype], _p(gate_w), _p(gate_b), B, C, HW, _p(ro), _p(do), _p(mg), _p(asum))
     return ro, do, mg, (asum / (B * HW) if want_attn_mean else None)
 
 
@@ -278,8 +290,9 @@ def ac_fusion(rgb, depth, w_rgb, b_rgb, w_depth, b_depth):
     HW = rgb[0, 0].numel()
     mr, md = channel_mean(rgb), channel_mean(depth)
     ro, do, mg = torch.empty_like(rgb), torch.empty_like(rgb), torch.empty_like(rgb)
-    _call("kpf_ac_fusion", _p(rgb), _p(depth), _DT[rgb.dtype], _p(mr), _p(md), _p(_f32(w_rgb.reshape(C, C))), _p(_f32(b_rgb)),
-          _p(_f32(w_depth.reshape(C, C))), _p(_f32(b_depth)), B, C, HW, _p(ro), _p(do), _p(mg))
+    w_rgb, b_rgb, w_depth, b_depth = _f32(w_rgb.reshape(C, C)), _f32(b_rgb), _f32(w_depth.reshape(C, C)), _f32(b_depth)
+    _call("kpf_ac_fusion", _p(rgb), _p(depth), _DT[rgb.dtype], _p(mr), _p(md), _p(w_rgb), _p(b_rgb), _p(w_depth), _p(b_depth), B, C, HW,
+          _p(ro), _p(do), _p(mg))
     return ro, do, mg
 
 
@@ -290,6 +303,18 @@ def fsp(guide, main, w0, b0, w2, b2):
     B, C = guide.shape[:2]
     HW = guide[0, 0].numel()
     out = torch.empty_like(main)
-    _call("kpf_fsp", _p(guide), _p(main), _DT[guide.dtype], _p(channel_mean(guide)), _p(channel_mean(main)), _p(_f32(w0)), _p(_f32(b0)),
-          _p(_f32(w2)), _p(_f32(b2)), B, C, w0.shape[0], HW, _p(out))
+    mg, mm = channel_mean(guide), channel_mean(main)  # keep references alive until the launch is enqueued
+    w0, b0, w2, b2 = _f32(w0), _f32(b0), _f32(w2), _f32(b2)
+    _call("kpf_fsp", _p(guide), _p(main), _DT[guide.dtype], _p(mg), _p(mm), _p(w0), _p(b0), _p(w2), _p(b2), B, C, w0.shape[0], HW,
+          _p(out))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ 8f-1 DESA
+def ball_query(xyz, centers, radius, nsample):
+    xyz, centers = _f32(xyz), _f32(centers)
+    B, Np, _ = xyz.shape
+    J = centers.shape[1]
+    idx = torch.empty(B, J, nsample, device=xyz.device, dtype=torch.int32)
+    _call("kpf_ball_query", _p(xyz), _p(centers), B, Np, J, float(radius), nsample, _p(idx))
+    return idx

@@ -153,22 +153,49 @@ def sample_key(seed, b):
     return _mix32((seed & 0xFFFFFFFF) ^ _mix32((b + 0x85EBCA6B) & 0xFFFFFFFF))
 
 
+def _mix32_v(x):
+    x = x.astype(np.uint64) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(13)
+    x = (x * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def feistel_perm_v(i, n, key):
+    """Vectorised feistel_perm over an index array (same integer arithmetic)."""
+    bits = max(2, (n - 1).bit_length())
+    bits += bits & 1
+    half = np.uint64(bits // 2)
+    mask = np.uint64((1 << (bits // 2)) - 1)
+    x = np.asarray(i, np.uint64).copy()
+    todo = np.ones(x.shape, bool)
+    while todo.any():
+        l, r = x[todo] >> half, x[todo] & mask
+        for rnd in range(4):
+            l, r = r, l ^ (_mix32_v(r ^ np.uint64(key) ^ np.uint64((rnd * 0x9E3779B9) & 0xFFFFFFFF)) & mask)
+        x[todo] = (l << half) | r
+        todo &= x >= n
+    return x.astype(np.int64)
+
+
 def resample_ranks(P, sample_num, seed, b):
     """Deterministic stand-in for loader.py:1176-1185: a random `sample_num`-subset (P>=sample_num) or the
     multiset {each index floor(sample_num/P) times + distinct random remainder} (P<sample_num), in random order."""
     if P == 0:
         return np.zeros(sample_num, np.int32)
     key = sample_key(seed, b)
-    out = np.empty(sample_num, np.int32)
+    j = np.arange(sample_num)
     if P >= sample_num:
-        for j in range(sample_num):
-            out[j] = feistel_perm(j, P, key)
-    else:
-        tmp = sample_num // P
-        for j in range(sample_num):
-            t = feistel_perm(j, sample_num, key ^ 0x1234567)
-            out[j] = t // tmp if t < tmp * P else feistel_perm(t - tmp * P, P, key)
-    return out
+        return feistel_perm_v(j, P, key).astype(np.int32)
+    tmp = sample_num // P
+    t = feistel_perm_v(j, sample_num, key ^ 0x1234567)
+    out = t // tmp
+    rem = t >= tmp * P
+    if rem.any():
+        out[rem] = feistel_perm_v(t[rem] - tmp * P, P, key)
+    return out.astype(np.int32)
 
 
 def getpcl_sample(imgD, com3D, cube, M, cam, sample_num=1024, ranks=None, seed=0, b=0, clamp=False, flip=1.0):
@@ -251,12 +278,22 @@ def img2pcl_index(pcl, img_down, center, M, cube, cam, img_size, select_num=4, f
     B, N, _ = pcl.shape
     idx = np.empty((B, N, select_num), np.int64)
     val = np.empty((B, N, select_num), f32)
+    HW = cells.shape[1]
+    kc = min(HW, select_num + 8)  # candidates: exact unless > 8 cells tie at the K-th distance (then full stable sort)
     for b in range(B):
         d = pcl[b][:, None, :] - cells[b][None, :, :]
         d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
-        order = np.argsort(d2, axis=1, kind="stable")[:, :select_num]
-        idx[b] = order
-        val[b] = np.take_along_axis(d2, order, 1)
+        cv, ci = torch.topk(torch.from_numpy(d2), kc, dim=1, largest=False, sorted=True)
+        cv, ci = cv.numpy(), ci.numpy()
+        order = np.lexsort((ci, cv), axis=1)  # (distance, then lower index)
+        ci = np.take_along_axis(ci, order, 1)
+        cv = np.take_along_axis(cv, order, 1)
+        amb = np.flatnonzero(cv[:, select_num - 1] == cv[:, kc - 1]) if kc < HW else []
+        for n in amb:
+            o = np.argsort(d2[n], kind="stable")[:kc]
+            ci[n], cv[n] = o, d2[n][o]
+        idx[b] = ci[:, :select_num]
+        val[b] = cv[:, :select_num]
     c = f32(1) / (val + f32(1e-8))
     s = c[..., 0]
     for k in range(1, select_num):

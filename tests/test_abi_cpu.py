@@ -14,9 +14,9 @@ def test_header_declares_entry_points():
 
 
 def test_library_exports_every_declared_symbol():
-    if not os.path.exists(_lib.LIB_PATH):
-        from keypointfusion_b200 import build
-        build.build()
+    from keypointfusion_b200 import build
+    if os.path.exists(build.NVCC):
+        build.build()  # incremental: recompiles only stale objects
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in _lib.parse_header():
         assert hasattr(L, name), f"{name} declared in kpf_b200.h but not exported"

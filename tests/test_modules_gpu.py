@@ -1,0 +1,125 @@
+"""GPU: the drop-in nn.Modules (reference signatures) vs the reference's golden outputs and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from keypointfusion_b200.utils import synth
+from oracle import kpf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def close(a, b, rtol=1e-3, atol=1e-5):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    assert np.all(err <= atol + rtol * np.abs(b)), f"max abs err {err.max():.3e} (ref max {np.abs(b).max():.3e})"
+
+
+def mm_err(a, b):
+    return float(np.linalg.norm((a.detach().float().cpu().numpy() - np.asarray(b)) * 125.0, axis=-1).mean())  # cube/2 = 125 mm
+
+
+@pytest.fixture(scope="module")
+def net(path_params):
+    from keypointfusion_b200.model.model import KPFusion
+    n = KPFusion(joint_num=21)
+    n.load_state_dict(path_params)
+    return n.to(DEV).eval()
+
+
+def test_blocks_vs_reference_golden(net, golden, golden_inputs):
+    """Feed the two drop-in blocks the reference's own pcl / indices / closeness (golden) so differences are float-only."""
+    from keypointfusion_b200.dataloader.loader import loader
+    i = {k: v.to(DEV) for k, v in golden_inputs.items()}
+    L = loader(img_size=128)
+    pcl = torch.from_numpy(golden["pcl_sample"]).to(DEV)
+    idx = torch.from_numpy(golden["a6_index"].astype(np.int64)).to(DEV)
+    cl = torch.from_numpy(golden["a6_closeness"]).to(DEV)
+    jx = torch.from_numpy(golden["joint_xyz0"]).to(DEV)
+    img_down = torch.from_numpy(golden["img_down"]).to(DEV)
+    prev = None
+    with torch.no_grad():
+        for b, blk in ((1, net.block1), (2, net.block2)):
+            r3d, r2d, prev, sw, _ = blk(i["img_feat"], i["img_feat_rgb"], pcl, jx, cl, idx, i["img_offset"], prev, L, img_down,
+                                        i["center"], i["M"], i["cube"], i["cam"])
+            close(prev, golden[f"b{b}_img_feat_j"], atol=5e-5)
+            close(sw[:1], golden[f"b{b}_sw0"], atol=5e-6)
+            for name, v in (("r3d", r3d), ("r2d", r2d)):
+                assert mm_err(v, golden[f"b{b}_{name}"]) <= 0.05, (b, name)      # north_star: <= 0.05 mm mean
+                close(v, golden[f"b{b}_{name}"], atol=5e-5)
+            jx = r2d
+
+
+def test_fusion_path_end_to_end(net, golden, golden_inputs, path_params):
+    """KPFusion.forward_path from raw depth crop: K1 (explicit ranks) -> K4a -> a5 -> K2 -> 2 blocks."""
+    from keypointfusion_b200.dataloader.loader import loader
+    from keypointfusion_b200 import ops
+    i = {k: v.to(DEV) for k, v in golden_inputs.items()}
+    ranks = np.stack([synth.explicit_ranks(int(golden["getpcl_counts"][b]), 1024, 7 + b) for b in range(2)])
+    with torch.no_grad():
+        pcl, _ = ops.getpcl(i["img"], i["center"], i["cube"], i["M"], i["cam"], ranks=torch.from_numpy(ranks).to(DEV))
+        res, sws, _ = net.forward_path(i["img_offset"], i["img_feat"], None, i["img_feat_rgb"], i["img"], pcl, loader(img_size=128),
+                                       i["center"], i["M"], i["cube"], i["cam"], 0.8)
+    for k, name in ((2, "b1_r3d"), (3, "b1_r2d"), (4, "b2_r3d"), (5, "b2_r2d")):
+        assert mm_err(res[k], golden[name]) <= 0.05, name
+    close(sws[1][:1], golden["b2_sw0"], atol=1e-5)
+    # and against the oracle's whole path on a different seed / batch
+    inp = synth.make_inputs(3, 128, 21, 128, seed=21)
+    c = {k: v.to(DEV) for k, v in inp.items()}
+    with torch.no_grad():
+        pcl, _ = ops.getpcl(c["img"], c["center"], c["cube"], c["M"], c["cam"], seed=4)
+        res, sws, _ = net.forward_path(c["img_offset"], c["img_feat"], None, c["img_feat_rgb"], c["img"], pcl, loader(img_size=128),
+                                       c["center"], c["M"], c["cube"], c["cam"], 0.8)
+    ores, osw, _ = O.fusion_path(path_params, inp["img"], pcl.cpu(), inp["img_offset"], inp["img_feat"], inp["img_feat_rgb"],
+                                 inp["center"].numpy(), inp["M"].numpy(), inp["cube"].numpy(), inp["cam"].numpy())
+    for k in range(4):
+        assert mm_err(res[2 + k], ores[k].numpy()) <= 0.05, k
+
+
+def test_updated_decoder_module(golden, golden_meta):
+    from keypointfusion_b200.model.transfusion_head import updatedDecoder
+    dec = updatedDecoder(joint_num=21, hidden_channel=128, num_heads=4, ffn_channel=128, dropout=0.1, num_decoder_layers=4)
+    dec.load_state_dict(synth.fill_state_dict({k: torch.zeros(s) for k, s in golden_meta["updatedDecoder_keys"].items()}, golden_meta["seed"]))
+    dec = dec.to(DEV).eval()
+    out = dec(torch.from_numpy(golden["a13_anchor"]).to(DEV), torch.from_numpy(golden["a13_key"]).to(DEV))
+    assert out.shape == (2, 128, 21)
+    close(out, golden["a13_out"], atol=2e-5)
+
+
+def test_fusion_layer_modules(golden, golden_meta):
+    from keypointfusion_b200.model.fusion_layer import ACFusion, FSP, RGBDFusion
+    seed = golden_meta["seed"]
+    for name, cls in (("rgbd", RGBDFusion), ("ac", ACFusion)):
+        m = cls(64, 64)
+        m.load_state_dict(synth.fill_state_dict({k: torch.zeros(s) for k, s in golden_meta[f"{cls.__name__}_keys"].items()}, seed))
+        m = m.to(DEV).eval()
+        (ro, do), mg = m([torch.from_numpy(golden[f"a14_{name}_rgb"]).to(DEV), torch.from_numpy(golden[f"a14_{name}_depth"]).to(DEV)])
+        close(ro, golden[f"a14_{name}_rgb_out"], atol=2e-6), close(do, golden[f"a14_{name}_depth_out"], atol=2e-6)
+        close(mg, golden[f"a14_{name}_merge"], atol=2e-6)
+    f = FSP(64, 64)
+    f.load_state_dict(synth.fill_state_dict({k: torch.zeros(s) for k, s in golden_meta["FSP_keys"].items()}, seed))
+    f = f.to(DEV).eval()
+    close(f(torch.from_numpy(golden["a14_rgbd_rgb"]).to(DEV), torch.from_numpy(golden["a14_rgbd_depth"]).to(DEV)), golden["a15_fsp_out"], atol=2e-6)
+
+
+def test_helper_objects(golden, golden_inputs):
+    from keypointfusion_b200.dataloader.loader import loader
+    from keypointfusion_b200.util.generateFeature import GFM
+    from keypointfusion_b200.util.img2pcl import Pcl_utils
+    i = {k: v.to(DEV) for k, v in golden_inputs.items()}
+    L, g = loader(img_size=128), GFM()
+    close(L.uvd_nl2xyznl_tensor(torch.from_numpy(golden["a5_uvd"]).to(DEV), i["center"], i["M"], i["cube"], i["cam"]), golden["a5_xyz"],
+          rtol=1e-4, atol=2e-6)
+    c, idx = L.img2pcl_index(torch.from_numpy(golden["pcl_sample"]).to(DEV), torch.from_numpy(golden["img_down"]).to(DEV), i["center"],
+                             i["M"], i["cube"], i["cam"], select_num=4)
+    assert idx.dtype == torch.int64 and c.dtype == torch.float32 and idx.shape == (2, 1024, 4)
+    j3 = torch.from_numpy(golden["a10_joint"]).to(DEV)
+    close(g.joint2feature(j3, i["img"], [0.8], 32, ['weight_offset'])[:1], golden["a16_joint2feature"], atol=2e-6)
+    pix = torch.cat([g.joint2offset(j3, i["img"], 0.8, 32), torch.from_numpy(golden["a16_feature2joint_in_w"]).to(DEV)], 1)
+    close(g.feature2joint(i["img"], pix, ['weight_offset'], [0.8]), golden["a16_feature2joint"], atol=5e-6)
+    pu = Pcl_utils(seed=5)
+    pcl = pu.getpcl(i["img"], i["center"], i["cube"], i["M"], i["cam"])
+    assert pcl.shape == (2, 1024, 3) and np.array_equal(pu.last_count.cpu().numpy(), golden["getpcl_counts"])

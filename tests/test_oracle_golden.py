@@ -65,6 +65,7 @@ def test_feistel_is_permutation():
         key = O.sample_key(5, n)
         vals = [O.feistel_perm(i, n, key) for i in range(n)]
         assert sorted(vals) == list(range(n))
+        assert np.array_equal(O.feistel_perm_v(np.arange(n), n, key), np.array(vals))   # vectorised == scalar
     r = O.resample_ranks(5000, 1024, 1, 2)
     assert len(set(r.tolist())) == 1024 and r.max() < 5000
 

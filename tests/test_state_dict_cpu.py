@@ -1,0 +1,68 @@
+"""CPU: the drop-in modules expose exactly the reference's state_dict keys/shapes (SURVEY.md 8b contract; the key
+lists were dumped from the reference's own modules by tests/golden/make_golden.py)."""
+import pytest
+import torch
+
+from keypointfusion_b200.model.fusion_layer import ACFusion, FSP, RGBDFusion
+from keypointfusion_b200.model.model import Block_KPFusion, KPFusion
+from keypointfusion_b200.model.transfusion_head import MultiheadAttention, updatedDecoder
+from keypointfusion_b200.utils import synth
+
+
+def _same(mod, ref):
+    sd = {k: list(v.shape) for k, v in mod.state_dict().items()}
+    assert sd == ref
+
+
+def test_block_keys(golden_meta):
+    _same(Block_KPFusion(joint_num=21), golden_meta["Block_KPFusion_keys"])
+
+
+def test_decoder_and_fusion_keys(golden_meta):
+    _same(updatedDecoder(joint_num=21, num_decoder_layers=4), golden_meta["updatedDecoder_keys"])
+    _same(RGBDFusion(64, 64), golden_meta["RGBDFusion_keys"])
+    _same(ACFusion(64, 64), golden_meta["ACFusion_keys"])
+    _same(FSP(64, 64), golden_meta["FSP_keys"])
+
+
+def test_kpfusion_loads_reference_style_checkpoint(golden_meta, path_params):
+    net = KPFusion(joint_num=21)
+    missing, unexpected = net.load_state_dict(path_params, strict=True)
+    assert not missing and not unexpected
+    # DataParallel-style 'module.' prefix filtered like train.py:102-107
+    ck = {"module." + k: v for k, v in path_params.items()}
+    own = net.state_dict()
+    filt = {k[len("module."):]: v for k, v in ck.items() if k[len("module."):] in own}
+    assert len(filt) == len(own)
+
+
+def test_init_matches_reference_rules():
+    torch.manual_seed(0)
+    blk = Block_KPFusion()
+    # nn.Linear re-initialised by Block_KPFusion.apply(_init_weights) (model.py:269, :282-283) ...
+    assert blk.init_TR.cls_head.weight.std() < 0.002 and blk.crossTR.decoder[0].linear1.weight.std() < 0.002
+    # ... but in_proj_weight is a bare Parameter and keeps xavier_uniform (transfusion_head.py:668-672)
+    assert blk.crossTR.decoder[0].multihead_attn.in_proj_weight.std() > 0.05
+    assert float(blk.weight_dis) == 0.0
+
+
+def test_mha_generic_matches_torch_functional():
+    """MultiheadAttention general path (any L,S) == transfusion_head.py:303-556 semantics (checked against torch's own
+    multi_head_attention_forward, which that function was derived from)."""
+    torch.manual_seed(0)
+    m = MultiheadAttention(64, 4).eval()
+    synth.fill_state_dict(m, 3)
+    q, k = torch.randn(5, 2, 64), torch.randn(9, 2, 64)
+    o, w = m(q, k, k)
+    ro, rw = torch.nn.functional.multi_head_attention_forward(q, k, k, 64, 4, m.in_proj_weight, m.in_proj_bias, None, None, False, 0.0,
+                                                              m.out_proj.weight, m.out_proj.bias, training=False)
+    assert torch.allclose(o, ro, atol=1e-5) and torch.allclose(w, rw, atol=1e-6)
+
+
+def test_mha_matches_reference_golden(golden, golden_meta):
+    sd = synth.fill_state_dict({k: torch.zeros(s) for k, s in golden_meta["updatedDecoder_keys"].items()}, golden_meta["seed"])
+    m = MultiheadAttention(128, 4).eval()
+    m.load_state_dict({k[len("decoder.3.multihead_attn."):]: v for k, v in sd.items() if k.startswith("decoder.3.multihead_attn.")})
+    o, w = m(torch.from_numpy(golden["a13_mha_q"]), torch.from_numpy(golden["a13_mha_k"]), torch.from_numpy(golden["a13_mha_k"]))
+    assert torch.allclose(o, torch.from_numpy(golden["a13_mha_out"]), atol=2e-5)
+    assert torch.allclose(w, torch.from_numpy(golden["a13_mha_w"]), atol=1e-6)
