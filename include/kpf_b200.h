@@ -134,6 +134,11 @@ int kpf_fsp(const void* guide, const void* mainp, int dtype, const float* mean_g
 int kpf_ball_query(const float* xyz, const float* centers, int B, int Np, int J, float radius, int nsample, int32_t* idx_out,
                    cudaStream_t stream);
 
+/* ---- bring-up self-test of the tcgen05 primitives (csrc/umma.cuh): D[128,N] f32 = A * B^T with bf16 operands.
+ * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);
+ * b_mn == 0: B is [N,K] row-major, else B is given as [K,N]. */
+int kpf_umma_selftest(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,102 @@
+// tcgen05 / TMEM primitives for sm_100a, hand-written inline PTX (no CUTLASS dependency).
+// Descriptor bit layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables.
+//
+// Shared-memory operand layout used everywhere in this repo: SWIZZLE_NONE ("interleaved") canonical layout with
+// 8x16-byte core matrices stored chunk-major:
+//   K-major  operand X[rows][K] (bf16): element (r,k) at  (k/8)*LBO + (r/8)*SBO + (r%8)*16 + (k%8)*2
+//            with SBO = 128, LBO = rows*16  ==  uint4 smem[K/8][rows]   (one 16-byte chunk = 8 consecutive k)
+//   MN-major operand Y[K][MN]  (bf16): element (k,n) at  (k/8)*LBO + (n/8)*SBO + (k%8)*16 + (n%8)*2
+//            with SBO = 128, LBO = (MN/8)*128 == uint4 smem[K/8][MN/8][8]  (one chunk = 8 consecutive mn)
+// One tcgen05.mma consumes K=16 (two 8-k groups); the descriptor start address advances by 2*LBO per step.
+#pragma once
+#include "common.cuh"
+
+namespace kpf {
+
+// 64-bit shared-memory matrix descriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | swizzle none
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// 32-bit instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((a_mn_major ? 1u : 0u) << 15) |
+           ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T ; K % 16 == 0.  Issued by ONE thread.
+__device__ __forceinline__ void umma_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_addr,
+                                          uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int K, bool accumulate) {
+    for (int ks = 0; ks < K / 16; ++ks) {
+        umma_bf16(tmem_d, umma_smem_desc(a_addr + ks * 2 * a_lbo, a_lbo, a_sbo), umma_smem_desc(b_addr + ks * 2 * b_lbo, b_lbo, b_sbo),
+                  idesc, accumulate || ks > 0);
+    }
+}
+
+// all previously issued tcgen05.mma of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// TMEM allocation: one full warp; ncols power of two in [32,512]; the base address lands in *slot (shared)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread t of warp w reads lane 32*(w%4)+t, columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// pack 8 fp32 -> 8 bf16 (one 16-byte chunk of a canonical operand)
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    o.z = *reinterpret_cast<uint32_t*>(&c);
+    o.w = *reinterpret_cast<uint32_t*>(&d);
+    return o;
+}
+
+}  // namespace kpf
