@@ -134,6 +134,16 @@ int kpf_fsp(const void* guide, const void* mainp, int dtype, const float* mean_g
 int kpf_ball_query(const float* xyz, const float* centers, int B, int Np, int J, float radius, int nsample, int32_t* idx_out,
                    cudaStream_t stream);
 
+/* ---- a13 / 8f-2 on tensor cores: keypoint-token transformer stacks (csrc/token_stack.cu) ------------------------
+ * mode 0: KP_Interaction_TR.forward (model/model.py:45-126): x [B,J,D] (D = 128, or 128 < D <= 144 with the
+ *         extra D-128 inputs LEADING, like cat([joints, feats])) -> tokens_out [B,J,128], pred_out [B,J,3].
+ * mode 1: updatedDecoder's live layer (model/transfusion_head.py:684-708): x = anchor, y = tokens -> out_cj / out_jc
+ *         as in kpf_cross_decoder_layer.  bf16 tensor-core operands, fp32 accumulation / residual / LayerNorm / heads.
+ * wmat (bf16) / wvec (f32): packed by keypointfusion_b200.ops.pack_token_encoder / pack_token_cross. */
+int kpf_token_stack(const float* x, const float* y, const void* wmat, const float* wvec, int mode, int B, int J, int D, int L, int F,
+                    int act, float eps, float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride,
+                    int out_jc_c0, cudaStream_t stream);
+
 /* ---- bring-up self-test of the tcgen05 primitives (csrc/umma.cuh): D[128,N] f32 = A * B^T with bf16 operands.
  * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);
  * b_mn == 0: B is [N,K] row-major, else B is given as [K,N]. */

@@ -318,3 +318,78 @@ def ball_query(xyz, centers, radius, nsample):
     idx = torch.empty(B, J, nsample, device=xyz.device, dtype=torch.int32)
     _call("kpf_ball_query", _p(xyz), _p(centers), B, Np, J, float(radius), nsample, _p(idx))
     return idx
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core token stacks
+def _canon(W):
+    """[N,K] -> bf16 SWIZZLE_NONE canonical K-major operand [K/8][N][8] (csrc/umma.cuh), flattened."""
+    N, K = W.shape
+    assert K % 8 == 0
+    return W.detach().to(torch.bfloat16).reshape(N, K // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+def _pad(v, n):
+    v = v.detach().float().reshape(-1)
+    return torch.cat([v, v.new_zeros(n - v.numel())]) if v.numel() < n else v
+
+
+def pack_token_encoder(sd, prefix, J, C=128):
+    """KP_Interaction_TR state_dict -> (wmat bf16, wvec f32, D, L, F) for kpf_token_stack mode 0."""
+    g = lambda k: sd[prefix + k].detach().float()
+    Wemb = g("bert.img_embedding.weight")
+    D = Wemb.shape[1]
+    shift = D - C
+    mats = [_canon(Wemb[:, shift:])]
+    if shift > 0:
+        T = Wemb.new_zeros(C, 16)
+        T[:, :shift] = Wemb[:, :shift]
+        mats.append(_canon(T))
+    vecs = [g("bert.position_embeddings.weight")[:J].reshape(-1), g("bert.img_embedding.bias"), g("residual.weight").reshape(-1),
+            _pad(g("residual.bias"), 4), g("cls_head.weight").reshape(-1), _pad(g("cls_head.bias"), 4)]
+    L = 0
+    while f"{prefix}bert.encoder.layer.{L}.attention.self.query.weight" in sd:
+        lp = f"bert.encoder.layer.{L}."
+        F_ = g(lp + "intermediate.dense.weight").shape[0]
+        mats += [_canon(g(lp + "attention.self.query.weight")), _canon(g(lp + "attention.self.key.weight")),
+                 _canon(g(lp + "attention.self.value.weight")), _canon(g(lp + "attention.output.dense.weight")),
+                 _canon(g(lp + "intermediate.dense.weight")), _canon(g(lp + "output.dense.weight"))]
+        vecs += [g(lp + "attention.self.query.bias"), g(lp + "attention.self.key.bias"), g(lp + "attention.self.value.bias"),
+                 g(lp + "attention.output.dense.bias"), g(lp + "attention.output.LayerNorm.weight"),
+                 g(lp + "attention.output.LayerNorm.bias"), _pad(g(lp + "intermediate.dense.bias"), C), g(lp + "output.dense.bias"),
+                 g(lp + "output.LayerNorm.weight"), g(lp + "output.LayerNorm.bias")]
+        L += 1
+    return torch.cat(mats).contiguous(), torch.cat([v.reshape(-1) for v in vecs]).contiguous(), D, L, F_
+
+
+def pack_token_cross(sd, prefix, J, C=128):
+    """one TransformerDecoderLayer state_dict -> (wmat bf16, wvec f32, F) for kpf_token_stack mode 1."""
+    g = lambda k: sd[prefix + k].detach().float()
+    Wi, bi = g("multihead_attn.in_proj_weight"), g("multihead_attn.in_proj_bias")
+    F_ = g("linear1.weight").shape[0]
+    mats = [_canon(Wi[:C]), _canon(Wi[C:2 * C]), _canon(Wi[2 * C:]), _canon(g("multihead_attn.out_proj.weight")),
+            _canon(g("linear1.weight")), _canon(g("linear2.weight"))]
+    vecs = [g("self_posembed.weight")[:J].reshape(-1), g("cross_posembed.weight")[:J].reshape(-1), bi[:C], bi[C:2 * C], bi[2 * C:],
+            g("multihead_attn.out_proj.bias"), g("norm2.weight"), g("norm2.bias"), _pad(g("linear1.bias"), C), g("linear2.bias"),
+            g("norm3.weight"), g("norm3.bias")]
+    return torch.cat(mats).contiguous(), torch.cat([v.reshape(-1) for v in vecs]).contiguous(), F_
+
+
+def token_encoder(x, wmat, wvec, L, F, want_tokens=True):
+    """x [B,J,D] f32 -> (tokens [B,J,128] f32 | None, pred [B,J,3] f32)   (gelu, LayerNorm eps 1e-12)."""
+    x = _f32(x)
+    B, J, D = x.shape
+    tokens = torch.empty(B, J, 128, device=x.device, dtype=torch.float32) if want_tokens else None
+    pred = torch.empty(B, J, 3, device=x.device, dtype=torch.float32)
+    _call("kpf_token_stack", _p(x), None, _p(wmat), _p(wvec), 0, B, J, D, L, F, 1, 1e-12, _p(tokens), _p(pred), None, None, 0, 0)
+    return tokens, pred
+
+
+def token_cross(anchor, tokens, wmat, wvec, F, out_jc=None, out_jc_c0=0, want_cj=True):
+    """anchor, tokens [B,J,128] f32 -> out_cj [B,128,J] (and/or rows of out_jc)   (relu, LayerNorm eps 1e-5)."""
+    anchor, tokens = _f32(anchor), _f32(tokens)
+    B, J, C = anchor.shape
+    out_cj = torch.empty(B, C, J, device=anchor.device, dtype=torch.float32) if want_cj else None
+    stride = out_jc.shape[-1] if out_jc is not None else 0
+    _call("kpf_token_stack", _p(anchor), _p(tokens), _p(wmat), _p(wvec), 1, B, J, C, 1, F, 0, 1e-5, None, None, _p(out_cj), _p(out_jc),
+          stride, out_jc_c0)
+    return out_cj
