@@ -209,7 +209,7 @@ def main():
     sampler.start()
     n0 = ops.launch_count()
     ms = timed(lambda i: step(i, sets[i % NSETS]), a.steps, W)
-    launches = (ops.launch_count() - n0) * a.steps // (a.steps + W)
+    launches = (ops.launch_count() - n0) * a.steps // (a.steps + W)  # our C-ABI kernel launches inside the K timed steps
     clocks = sampler.stop()
 
     # end to end through the public API: pinned host buffers -> H2D -> path -> D2H joints, every step

@@ -144,6 +144,19 @@ int kpf_token_stack(const float* x, const float* y, const void* wmat, const floa
                     int act, float eps, float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride,
                     int out_jc_c0, cudaStream_t stream);
 
+/* ---- a7-a9 fused point stage (csrc/point_embed.cu), model/model.py:295-320 ------------------------------------------
+ * kpf_repack_features: f_d, f_rgb [B,128,HW], f_w [B,J,HW] (batch stride w_batch_stride elements; = img_offset[:,4J:])
+ *   -> out [B,HW,288] bf16 channels-last rows (128 | 128 | J zero-padded to 32).
+ * kpf_point_embed: featT from above; idx [B,N,4] i32 / clos [B,N,4] f32 from kpf_img2pcl_index (K = 4); pcl [B,N,3];
+ *   joint [B,J,3] (J <= 21); wmat/wvec from ops.pack_point_embed -> e_out [B,N,128] bf16 (point features after the four
+ *   folded Conv1d+BN embeddings and both relus), part_acc [B,N/128,128,32] f32 and part_ms [B,N/128,2,32] f32: per
+ *   128-point tile the softmax-aggregation numerators sum_n e[n][c]*exp(w[n][j]-max_tile) and (max_tile, sum_tile). */
+int kpf_repack_features(const void* f_d, const void* f_rgb, const void* f_w, long long w_batch_stride, int dtype, int B, int C, int J,
+                        int HW, void* out, cudaStream_t stream);
+int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint, const void* wmat,
+                    const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out, float* part_acc, float* part_ms,
+                    int num_sms, cudaStream_t stream);
+
 /* ---- bring-up self-test of the tcgen05 primitives (csrc/umma.cuh): D[128,N] f32 = A * B^T with bf16 operands.
  * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);
  * b_mn == 0: B is [N,K] row-major, else B is given as [K,N]. */

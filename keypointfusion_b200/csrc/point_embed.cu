@@ -1,0 +1,295 @@
+// Point stage of Block_KPFusion on tensor cores (model/model.py:295-320):
+//   K4b pcl_joint2offset + K3 4-tap gathers + the four folded Conv1d+BN point embeddings + relu/relu
+//   + the softmax-over-points aggregation numerators, in ONE persistent kernel; nothing of [B,N,*] but the final
+//   point features e (bf16) ever reaches HBM.
+//
+//   kpf_repack_features : NCHW (img_feat | img_feat_rgb | img_offset[4J:]) -> channels-last bf16 rows [B,HW,288]
+//                         so that one tap of a point is ONE contiguous 576-byte row.
+//   kpf_point_embed     : per 128-point tile (thread = point):
+//       A1[128 x 256] = [gather(img_feat) | gather(weight map) | unit offsets, closeness, xyz]   (bf16, smem)
+//       A2[128 x 128] =  gather(img_feat_rgb)
+//       e  = relu( relu(A1 W1^T + b1) + A2 W2^T + b2 )                     tcgen05, fp32 accumulators in TMEM
+//       p  = exp(w - max_tile w)  (softmax numerators of the gathered weight map, per joint)
+//       D[c][j] = sum_n e[n][c] p[n][j]                                    tcgen05 with MN-major operands
+//     outputs: e [B,N,128] bf16, and per tile (D, max, sum) partials that the DESA kernel combines flash-style.
+//   Weights (96 KB bf16) stay resident in shared memory; CTAs are persistent over tiles.
+#include "umma.cuh"
+
+namespace kpf {
+
+constexpr int PE_CP = 288;   // channels per repacked row: 128 depth-branch + 128 rgb-branch + 32 (J weight channels, zero padded)
+constexpr int PE_CH = PE_CP / 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+repack_kernel(const T* __restrict__ f_d, const T* __restrict__ f_rgb, const T* __restrict__ f_w, long long w_bs, int C, int J, int HW,
+              __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, h0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, h = h0 + tx;
+        float v = 0.f;
+        if (h < HW) {
+            if (c < C) v = to_f32(f_d[((size_t)b * C + c) * HW + h]);
+            else if (c < 2 * C) v = to_f32(f_rgb[((size_t)b * C + (c - C)) * HW + h]);
+            else if (c - 2 * C < J) v = to_f32(f_w[(size_t)b * w_bs + (size_t)(c - 2 * C) * HW + h]);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int h = h0 + r, c = c0 + tx;
+        if (h < HW && c < PE_CP) out[((size_t)b * HW + h) * PE_CP + c] = __float2bfloat16_rn(tile[tx][r]);
+    }
+}
+
+struct PointParams {
+    const uint4* featT;      // [B,HW,36] uint4 (288 bf16)
+    const int32_t* idx;      // [B,N,4]
+    const float* clos;       // [B,N,4]
+    const float* pcl;        // [B,N,3]
+    const float* joint;      // [B,J,3]
+    const uint4* wmat;       // W1a, W1b, W2: 3 x [16][128] uint4
+    const float* wvec;       // b1[128], b2[128]
+    __nv_bfloat16* e_out;    // [B,N,128]
+    float* part_acc;         // [B,T,128,32]
+    float* part_ms;          // [B,T,2,32]  (max, sum)
+    int B, N, J, HW;
+    float kernel_size;
+};
+
+__device__ __forceinline__ void bf16x8_fma(float* acc, const uint4& v, float w) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        acc[2 * i] += f.x * w;
+        acc[2 * i + 1] += f.y * w;
+    }
+}
+
+__global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p) {
+    extern __shared__ __align__(128) unsigned char pe_smem[];
+    uint4* sW = reinterpret_cast<uint4*>(pe_smem);   // [3][2048]
+    uint4* sA1 = sW + 3 * 2048;                       // [32][128]  (K = 256); after the MMAs: sP [16][4][8]
+    uint4* sA2 = sA1 + 4096;                          // [16][128]  (K = 128); after the MMAs: sE MN-major [16][16][8]
+    float* sJ = reinterpret_cast<float*>(sA2 + 2048); // [32][4] joints of the current sample
+    float* sRed = sJ + 128;                           // [4][32] cross-warp reductions
+    float* sB = sRed + 128;                           // b1[128], b2[128]
+    __shared__ __align__(8) uint64_t wbar, mma_bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int J = p.J, N = p.N, T = N / 128;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(&wbar, 1);
+        mbar_init(&mma_bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(&wbar, 3 * 2048 * 16);
+        for (int i = 0; i < 3; ++i) tma_bulk_g2s(sW + i * 2048, p.wmat + i * 2048, 2048 * 16, &wbar);
+    }
+    for (int i = tid; i < 256; i += 128) sB[i] = p.wvec[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = tmem_slot, tmem = tmem0 + lane_off;
+    const uint32_t ACC1 = 0, ACC2 = 128, ACC3 = 256;
+    uint32_t phase = 0;
+    bool w_ready = false;
+
+    for (int tile = blockIdx.x; tile < p.B * T; tile += gridDim.x) {
+        const int b = tile / T, t = tile - b * T, n = t * 128 + tid;
+        __syncthreads();  // previous tile's readers of sJ / sRed / sA* are done
+        if (tid < J) {
+            sJ[4 * tid] = p.joint[((size_t)b * J + tid) * 3];
+            sJ[4 * tid + 1] = p.joint[((size_t)b * J + tid) * 3 + 1];
+            sJ[4 * tid + 2] = p.joint[((size_t)b * J + tid) * 3 + 2];
+        }
+        const size_t pn = (size_t)b * N + n;
+        const int4 id = *reinterpret_cast<const int4*>(p.idx + pn * 4);
+        const float4 cw = *reinterpret_cast<const float4*>(p.clos + pn * 4);
+        const float px = p.pcl[pn * 3], py = p.pcl[pn * 3 + 1], pz = p.pcl[pn * 3 + 2];
+        const uint4* r0 = p.featT + ((size_t)b * p.HW + id.x) * PE_CH;
+        const uint4* r1 = p.featT + ((size_t)b * p.HW + id.y) * PE_CH;
+        const uint4* r2 = p.featT + ((size_t)b * p.HW + id.z) * PE_CH;
+        const uint4* r3 = p.featT + ((size_t)b * p.HW + id.w) * PE_CH;
+        // ---- K3: 4-tap gathers, 8 channels (one 16-byte chunk) at a time, 4 chunks in flight
+        float wraw[32];
+#pragma unroll
+        for (int c = 0; c < PE_CH; c += 4) {
+            uint4 v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u][0] = __ldg(r0 + c + u);
+                v[u][1] = __ldg(r1 + c + u);
+                v[u][2] = __ldg(r2 + c + u);
+                v[u][3] = __ldg(r3 + c + u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                bf16x8_fma(acc, v[u][0], cw.x);
+                bf16x8_fma(acc, v[u][1], cw.y);
+                bf16x8_fma(acc, v[u][2], cw.z);
+                bf16x8_fma(acc, v[u][3], cw.w);
+                const int cc = c + u;
+                if (cc < 16) sA1[cc * 128 + tid] = pack8_bf16(acc);             // depth-branch features
+                else if (cc < 32) sA2[(cc - 16) * 128 + tid] = pack8_bf16(acc);  // rgb-branch features
+                else {                                                           // weight map (J channels, zero padded)
+                    sA1[(16 + cc - 32) * 128 + tid] = pack8_bf16(acc);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wraw[(cc - 32) * 8 + i] = acc[i];
+                }
+            }
+        }
+        __syncthreads();  // sJ visible
+        // ---- K4b: unit offsets (joint-major xyz), closeness, then xyz; 96 values -> chunks 20..31 of A1
+        {
+            float buf[96];
+#pragma unroll
+            for (int i = 0; i < 96; ++i) buf[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 21; ++j) {
+                if (j < J) {
+                    const float ox = sJ[4 * j] - px, oy = sJ[4 * j + 1] - py, oz = sJ[4 * j + 2] - pz;
+                    const float dis = sqrtf(ox * ox + oy * oy + oz * oz);
+                    const float inv = 1.f / (dis + 1e-8f);
+                    const float heat = (p.kernel_size - dis) / p.kernel_size;
+                    const float msk = (heat >= 0.f && pz < 0.99f) ? 1.f : 0.f;
+                    buf[3 * j] = ox * inv * msk;
+                    buf[3 * j + 1] = oy * inv * msk;
+                    buf[3 * j + 2] = oz * inv * msk;
+                    buf[63 + j] = heat * msk;
+                }
+            }
+            buf[84] = px;
+            buf[85] = py;
+            buf[86] = pz;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) sA1[(20 + c) * 128 + tid] = pack8_bf16(buf + 8 * c);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            if (!w_ready) mbar_wait(&wbar, 0);
+            const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
+            umma_gemm(tmem0 + ACC1, smem_u32(sA1), 2048, 128, smem_u32(sW), 2048, 128, id128, 128, false);
+            umma_gemm(tmem0 + ACC1, smem_u32(sA1 + 2048), 2048, 128, smem_u32(sW + 2048), 2048, 128, id128, 128, true);
+            umma_gemm(tmem0 + ACC2, smem_u32(sA2), 2048, 128, smem_u32(sW + 4096), 2048, 128, id128, 128, false);
+            umma_commit(&mma_bar);
+        }
+        w_ready = true;
+        // ---- softmax numerators over this tile's points while the MMAs run: per joint max / exp / sum across 128 threads
+        float pj[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float m = warp_max(j < J ? wraw[j] : -INFINITY);
+            if (lane == 0) sRed[warp * 32 + j] = m;
+        }
+        __syncthreads();
+        float mt[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            mt[j] = fmaxf(fmaxf(sRed[j], sRed[32 + j]), fmaxf(sRed[64 + j], sRed[96 + j]));
+            pj[j] = j < J ? __bfloat162float(__float2bfloat16_rn(__expf(wraw[j] - mt[j]))) : 0.f;
+        }
+        float* ms = p.part_ms + ((size_t)b * T + t) * 64;
+        if (tid < 32) ms[tid] = fmaxf(fmaxf(sRed[tid], sRed[32 + tid]), fmaxf(sRed[64 + tid], sRed[96 + tid]));
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float s = warp_sum(pj[j]);
+            if (lane == 0) sRed[warp * 32 + j] = s;
+        }
+        __syncthreads();
+        if (tid < 32) ms[32 + tid] = sRed[tid] + sRed[32 + tid] + sRed[64 + tid] + sRed[96 + tid];
+        mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue: e = relu(relu(acc1 + b1) + acc2 + b2) -> global (bf16) and MN-major A operand (sA2 region)
+        __nv_bfloat16* eo = p.e_out + pn * 128;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            float a[32], r[32];
+            tmem_ld32(tmem + ACC1 + c0, a);
+            tmem_ld32(tmem + ACC2 + c0, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = fmaxf(fmaxf(a[i] + sB[c0 + i], 0.f) + r[i] + sB[128 + c0 + i], 0.f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 v = pack8_bf16(a + 8 * c);
+                *reinterpret_cast<uint4*>(eo + c0 + 8 * c) = v;
+                sA2[(tid >> 3) * 128 + (c0 / 8 + c) * 8 + (tid & 7)] = v;  // e^T: M = channel contiguous
+            }
+        }
+        // p as MN-major B operand [K = 128 points][N = 32 joints] over the (dead) head of sA1
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sA1[(tid >> 3) * 32 + c * 8 + (tid & 7)] = pack8_bf16(pj + 8 * c);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            umma_gemm(tmem0 + ACC3, smem_u32(sA2), 2048, 128, smem_u32(sA1), 512, 128, umma_idesc_bf16(128, 32, true, true), 128, false);
+            umma_commit(&mma_bar);
+        }
+        mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        {
+            float a[32];
+            tmem_ld32(tmem + ACC3, a);  // thread = channel c: D[c][0..31]
+            float4* o = reinterpret_cast<float4*>(p.part_acc + (((size_t)b * T + t) * 128 + tid) * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, 512);
+}
+
+constexpr size_t PE_SMEM = (size_t)(3 * 2048 + 4096 + 2048) * 16 + (128 + 128 + 256) * 4;
+
+}  // namespace kpf
+
+extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const void* f_w, long long w_batch_stride, int dtype, int B, int C,
+                                   int J, int HW, void* out, cudaStream_t stream) {
+    using namespace kpf;
+    KPF_REQUIRE(B >= 0 && C == 128 && J >= 1 && J <= 32 && HW >= 1);
+    if (B == 0) return 0;
+    dim3 grid((HW + 31) / 32, PE_CP / 32, B);
+    if (dtype == KPF_F32)
+        repack_kernel<float><<<grid, 256, 0, stream>>>((const float*)f_d, (const float*)f_rgb, (const float*)f_w, w_batch_stride, C, J, HW,
+                                                      (__nv_bfloat16*)out);
+    else if (dtype == KPF_BF16)
+        repack_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)f_d, (const __nv_bfloat16*)f_rgb,
+                                                              (const __nv_bfloat16*)f_w, w_batch_stride, C, J, HW, (__nv_bfloat16*)out);
+    else
+        return KPF_ERR_UNSUPPORTED;
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
+                               const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out,
+                               float* part_acc, float* part_ms, int num_sms, cudaStream_t stream) {
+    using namespace kpf;
+    KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && J >= 1 && J <= 21 && HW >= 1 && num_sms >= 1);
+    KPF_REQUIRE(((uintptr_t)featT % 16) == 0 && ((uintptr_t)wmat % 16) == 0 && ((uintptr_t)idx % 16) == 0 && ((uintptr_t)clos % 16) == 0);
+    if (B == 0) return 0;
+    PointParams p;
+    p.featT = (const uint4*)featT; p.idx = idx; p.clos = clos; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat; p.wvec = wvec;
+    p.e_out = (__nv_bfloat16*)e_out; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
+    p.kernel_size = kernel_size;
+    cudaError_t e = cudaFuncSetAttribute(point_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PE_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = B * (N / 128);
+    point_embed_kernel<<<tiles < num_sms ? tiles : num_sms, 128, PE_SMEM, stream>>>(p);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}

@@ -192,10 +192,23 @@ class KP_Interaction_TR(_KernelCache, nn.Module):  # model.py:106-126
         _bert_init(self, config.initializer_range)
 
     def _build_kc(self):
-        return None
+        dev = self.cls_head.weight.device
+        wmat, wvec, D, L, F_ = ops.pack_token_encoder(self.state_dict(), "", 64)
+        return dict(wmat=wmat.to(dev), wvec_J={}, L=L, F=F_)
 
-    def forward(self, img_feats, *unused, **unused_kw):
+    def forward_tc(self, img_feats, want_tokens=True):
+        """bf16 tensor-core path (csrc/token_stack.cu): same contract as forward()."""
+        k = self.kc()
+        J = img_feats.shape[1]
+        if J not in k["wvec_J"]:  # the position-embedding slice depends on the token count
+            _, wvec, _, _, _ = ops.pack_token_encoder(self.state_dict(), "", J)
+            k["wvec_J"][J] = wvec.to(img_feats.device)
+        return ops.token_encoder(img_feats, k["wmat"], k["wvec_J"][J], k["L"], k["F"], want_tokens)
+
+    def forward(self, img_feats, *unused, precision="fp32", **unused_kw):
         """img_feats [B,J,D] -> (tokens [B,J,hidden], pred [B,J,3]).  model.py:45-103, :116-126."""
+        if precision == "bf16":
+            return self.forward_tc(img_feats)
         c = self.config
         B, L, _ = img_feats.shape
         x = img_feats.float()
@@ -310,6 +323,7 @@ class Block_KPFusion(_KernelCache, nn.Module):
         self.cls_head = nn.Linear(128, 3)                               # model.py:270 (after apply)
         self.weight_dis = nn.Parameter(torch.zeros([1]))
         self.GFM_ = GFM()
+        self.precision = "auto"   # "auto": bf16 tensor-core path when the feature maps are bf16, fp32 otherwise
 
     def _init_weights(self, m):  # model.py:275-285
         if isinstance(m, nn.Conv2d):
@@ -330,8 +344,9 @@ class Block_KPFusion(_KernelCache, nn.Module):
         Wr, br = _fold_bn(self.pcl_feat_emb_RGB[0].weight, self.pcl_feat_emb_RGB[0].bias, self.pcl_feat_emb_RGB[1])
         Wj, bj = _fold_bn(self.joint_feat_emb[0].weight, self.joint_feat_emb[0].bias, self.joint_feat_emb[1])
         Wjx, bjx = _fold_bn(self.joint_xyz_emb[0].weight, self.joint_xyz_emb[0].bias, self.joint_xyz_emb[1])
+        pe_wmat, pe_wvec = ops.pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, self.joint_num)
         return dict(W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
-                    W_joint=torch.cat([Wj, Wjx], 1).contiguous(), b_joint=(bj + bjx).contiguous())
+                    W_joint=torch.cat([Wj, Wjx], 1).contiguous(), b_joint=(bj + bjx).contiguous(), pe_wmat=pe_wmat, pe_wvec=pe_wvec)
 
     def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
                 img_down, center, M, cube, cam_para, writer=None, ii=0):
@@ -339,6 +354,7 @@ class Block_KPFusion(_KernelCache, nn.Module):
         B, N, _ = pcl.shape
         C, H = img_feat.shape[1], img_feat.shape[2]
         J = self.joint_num
+        prec = self.precision if self.precision != "auto" else ("bf16" if img_feat.dtype == torch.bfloat16 else "fp32")
         pcl = pcl.float().contiguous()
         joint_xyz = joint_xyz.detach().float().contiguous()
         # RGB keypoint aggregation (model.py:295-306): K4b + K3
@@ -353,7 +369,7 @@ class Block_KPFusion(_KernelCache, nn.Module):
         joint_feat = torch.matmul(attention, e)                                          # model.py:320
         joint_feat = F.relu(F.linear(torch.cat((joint_feat, joint_xyz), dim=-1), k["W_joint"], k["b_joint"]))  # :323-325
         joint_feat = self.FA(e, joint_feat, pcl, joint_xyz)                              # model.py:327
-        outfeature_init_TR, refined_3d_joints = self.init_TR(joint_feat)                 # model.py:330
+        outfeature_init_TR, refined_3d_joints = self.init_TR(joint_feat, precision=prec)  # model.py:330
         # depth keypoint aggregation (model.py:334-344): K4c + K5 fused
         spatial_weight_loss, img_feat_j = ops.spatial_aggregate(
             img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, self.atten_spatial.weight,
@@ -362,8 +378,8 @@ class Block_KPFusion(_KernelCache, nn.Module):
         # inter-modal keypoint feature interaction (model.py:347-349): K6 writes straight into final_TR's input
         tr_in = torch.empty(B, J, 3 + self.dim, device=pcl.device, dtype=torch.float32)
         tr_in[:, :, :3] = refined_3d_joints
-        self.crossTR(img_feat_j, outfeature_init_TR, out_jc=tr_in, out_jc_c0=3, want_cj=False)
-        _, refined_2d_joints = self.final_TR(tr_in)
+        self.crossTR(img_feat_j, outfeature_init_TR, out_jc=tr_in, out_jc_c0=3, want_cj=False, precision=prec)
+        _, refined_2d_joints = self.final_TR(tr_in, precision=prec)
         return refined_3d_joints, refined_2d_joints, img_feat_j, spatial_weight_loss, None
 
 

@@ -89,6 +89,14 @@ class TransformerDecoderLayer(nn.Module):
         self.cross_posembed = cross_posembed
         self.d_model, self.nhead, self.dim_feedforward = d_model, nhead, dim_feedforward
         self._wpack = None
+        self._tc = None
+
+    def packed_tc(self, J):
+        dev = self.linear1.weight.device
+        if self._tc is None or self._tc[0].device != dev or self._tc[3] != J:
+            wmat, wvec, F_ = ops.pack_token_cross(self.state_dict(), "", J, self.d_model)
+            self._tc = (wmat.to(dev), wvec.to(dev), F_, J)
+        return self._tc
 
     def packed(self, J):
         if self._wpack is None or self._wpack.device != self.linear1.weight.device:
@@ -96,11 +104,16 @@ class TransformerDecoderLayer(nn.Module):
             self._wpack = ops.pack_decoder_layer(sd, "", J, self.d_model)
         return self._wpack
 
-    def forward(self, query, key, query_pos=None, key_pos=None, attn_mask=None, out_jc=None, out_jc_c0=0, want_cj=True):
-        """query [B,J,C], key [B,J,C] -> [B,C,J] (transfusion_head.py:132-173, cross_only, index position embeddings)."""
+    def forward(self, query, key, query_pos=None, key_pos=None, attn_mask=None, out_jc=None, out_jc_c0=0, want_cj=True,
+                precision="fp32"):
+        """query [B,J,C], key [B,J,C] -> [B,C,J] (transfusion_head.py:132-173, cross_only, index position embeddings).
+        precision "fp32": CUDA-core kernel (csrc/cross_attn.cu); "bf16": tcgen05 kernel (csrc/token_stack.cu)."""
         if not self.cross_only or attn_mask is not None or self.self_posembed is None or self.cross_posembed is None:
             raise NotImplementedError("only the cross_only configuration updatedDecoder builds (transfusion_head.py:652-661)")
         J = query.shape[1]
+        if precision == "bf16" and self.d_model == 128 and self.nhead == 4:
+            wmat, wvec, F_, _ = self.packed_tc(J)
+            return ops.token_cross(query, key, wmat, wvec, F_, out_jc, out_jc_c0, want_cj)
         return ops.cross_decoder_layer(query, key, self.packed(J), self.nhead, self.dim_feedforward, out_jc, out_jc_c0, want_cj)
 
 
@@ -132,6 +145,7 @@ class updatedDecoder(nn.Module):
     def invalidate(self):
         for layer in self.decoder:
             layer._wpack = None
+            layer._tc = None
 
     def _apply(self, fn, *a, **k):
         self.invalidate()
@@ -141,10 +155,10 @@ class updatedDecoder(nn.Module):
         self.invalidate()
         return super().load_state_dict(*a, **k)
 
-    def forward(self, anchor_feats, img_feats, out_jc=None, out_jc_c0=0, want_cj=True):
+    def forward(self, anchor_feats, img_feats, out_jc=None, out_jc_c0=0, want_cj=True, precision="fp32"):
         """anchor_feats [B,J,C] (queries), img_feats [B,J,C] (keys) -> [B,C,J].  Every layer of the reference gets the
         same inputs and only the last output is returned (transfusion_head.py:705-708): layers 0..n-2 are dead compute
         and are skipped; their parameters stay in the state_dict."""
         B, J, C = img_feats.shape
         assert anchor_feats.shape[1] == self.joint_num and J == self.joint_num
-        return self.decoder[-1](anchor_feats, img_feats, out_jc=out_jc, out_jc_c0=out_jc_c0, want_cj=want_cj)
+        return self.decoder[-1](anchor_feats, img_feats, out_jc=out_jc, out_jc_c0=out_jc_c0, want_cj=want_cj, precision=precision)

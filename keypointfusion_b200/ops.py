@@ -393,3 +393,72 @@ def token_cross(anchor, tokens, wmat, wvec, F, out_jc=None, out_jc_c0=0, want_cj
     _call("kpf_token_stack", _p(anchor), _p(tokens), _p(wmat), _p(wvec), 1, B, J, C, 1, F, 0, 1e-5, None, None, _p(out_cj), _p(out_jc),
           stride, out_jc_c0)
     return out_cj
+
+
+# ------------------------------------------------------------------------------------------------ fused point stage
+_sm_count = {}
+
+
+def sm_count(device):
+    i = torch.device(device).index or 0
+    if i not in _sm_count:
+        _sm_count[i] = torch.cuda.get_device_properties(i).multi_processor_count
+    return _sm_count[i]
+
+
+def repack_features(img_feat, img_feat_rgb, weight_map):
+    """NCHW maps -> channels-last bf16 rows [B,HW,288] (128 depth-branch | 128 rgb-branch | J weight channels padded to 32)."""
+    _need_cuda(img_feat, img_feat_rgb, weight_map)
+    dt = img_feat.dtype if img_feat.dtype in _DT else torch.float32
+    f_d, f_rgb = img_feat.to(dt).contiguous(), img_feat_rgb.to(dt).contiguous()
+    w = weight_map.to(dt)
+    B, C = f_d.shape[:2]
+    J = w.shape[1]
+    HW = f_d[0, 0].numel()
+    if not w[0].reshape(J, HW).is_contiguous():
+        w = w.contiguous()
+    out = torch.empty(B, HW, 288, device=f_d.device, dtype=torch.bfloat16)
+    _call("kpf_repack_features", _p(f_d), _p(f_rgb), _p(w), w.stride(0), _DT[dt], B, C, J, HW, _p(out))
+    return out
+
+
+def pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, J):
+    """BN-folded point-embedding weights (pcl_feat_emb, pcl_xyz_emb, pcl_pose_emb, pcl_feat_emb_RGB) -> (wmat bf16, wvec f32).
+    A1 column order: [depth feats 128 | weight map J (+pad to 32) | unit offsets 3J, closeness J, xyz 3 (+pad to 96)]."""
+    C = Wf.shape[0]
+    W1 = Wf.new_zeros(C, 256)
+    W1[:, :128] = Wf
+    W1[:, 128:128 + J] = Wp[:, :J]
+    W1[:, 160:160 + 4 * J] = Wp[:, J:5 * J]
+    W1[:, 160 + 4 * J:160 + 4 * J + 3] = Wx
+    wmat = torch.cat([_canon(W1[:, :128]), _canon(W1[:, 128:]), _canon(Wr)]).contiguous()
+    wvec = torch.cat([(bf + bx + bp).float(), br.float()]).contiguous()
+    return wmat, wvec
+
+
+def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8):
+    """-> e [B,N,128] bf16, part_acc [B,T,128,32] f32, part_ms [B,T,2,32] f32  (T = N/128)."""
+    _need_cuda(featT, idx32, clos, pcl, joint)
+    pcl, joint, clos = _f32(pcl), _f32(joint), _f32(clos)
+    idx32 = idx32.to(torch.int32).contiguous()
+    B, N, _ = pcl.shape
+    J = joint.shape[1]
+    HW = featT.shape[1]
+    T = N // 128
+    dev = pcl.device
+    e = torch.empty(B, N, 128, device=dev, dtype=torch.bfloat16)
+    acc = torch.empty(B, T, 128, 32, device=dev, dtype=torch.float32)
+    ms = torch.empty(B, T, 2, 32, device=dev, dtype=torch.float32)
+    _call("kpf_point_embed", _p(featT), _p(idx32), _p(clos), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, HW, float(kernel_size), _p(e),
+          _p(acc), _p(ms), sm_count(dev))
+    return e, acc, ms
+
+
+def combine_point_partials(acc, ms, J):
+    """flash-style combination of the per-tile softmax partials -> joint_agg [B,J,128] (torch glue used by tests / fp32 path)."""
+    m_t, s_t = ms[:, :, 0, :J], ms[:, :, 1, :J]                      # B T J
+    m = m_t.max(dim=1, keepdim=True)[0]
+    sc = torch.exp(m_t - m)                                          # B T J
+    num = (acc[:, :, :, :J] * sc.unsqueeze(2)).sum(1)                # B 128 J
+    den = (s_t * sc).sum(1)                                          # B J
+    return (num / den.unsqueeze(1)).permute(0, 2, 1).contiguous()

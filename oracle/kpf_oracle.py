@@ -598,6 +598,7 @@ def block_kpfusion(p, prefix, img_feat, img_feature_rgb, pcl, joint_xyz, closene
     e = torch.relu(e + conv_bn(p, prefix + "pcl_feat_emb_RGB.", pcl_feat_rgb))           # :317
     att = torch.softmax(pcl_weight.permute(0, 2, 1), -1)                                 # :319
     jf = att @ e                                                                         # :320
+    t["joint_agg"] = jf
     jf = torch.relu(conv_bn(p, prefix + "joint_feat_emb.", jf) + conv_bn(p, prefix + "joint_xyz_emb.", joint_xyz))
     t.update(pcl_emb=e, joint_feat_pre=jf)
     jf = desa(p, prefix + "FA.", e, jf, pcl, joint_xyz)                                  # :327

@@ -123,3 +123,31 @@ def test_helper_objects(golden, golden_inputs):
     pu = Pcl_utils(seed=5)
     pcl = pu.getpcl(i["img"], i["center"], i["cube"], i["M"], i["cam"])
     assert pcl.shape == (2, 1024, 3) and np.array_equal(pu.last_count.cpu().numpy(), golden["getpcl_counts"])
+
+
+def test_fusion_path_bf16_tensor_core(net, path_params, capsys):
+    """bf16 feature maps select the tcgen05 token stacks.  Bars: features <= 1e-2 relative (RMS); the joints' error is
+    measured and reported -- with O(1)-gain random weights bf16 operand rounding alone moves joints by ~0.1-0.3 mm, so the
+    0.05 mm bar is an fp32-path bar (test_fusion_path_end_to_end)."""
+    from keypointfusion_b200.dataloader.loader import loader
+    from keypointfusion_b200 import ops
+    inp = synth.make_inputs(4, 128, 21, 128, seed=33, bf16_round=True)
+    c = {k: v.to(DEV) for k, v in inp.items()}
+    for k in ("img_feat", "img_feat_rgb", "img_offset"):
+        c[k] = c[k].bfloat16()
+    with torch.no_grad():
+        pcl, _ = ops.getpcl(c["img"], c["center"], c["cube"], c["M"], c["cam"], seed=4)
+        res, sws, _ = net.forward_path(c["img_offset"], c["img_feat"], None, c["img_feat_rgb"], c["img"], pcl, loader(img_size=128),
+                                       c["center"], c["M"], c["cube"], c["cam"], 0.8)
+    ores, osw, ex = O.fusion_path(path_params, inp["img"], pcl.cpu(), inp["img_offset"], inp["img_feat"], inp["img_feat_rgb"],
+                                  inp["center"].numpy(), inp["M"].numpy(), inp["cube"].numpy(), inp["cam"].numpy())
+    errs = [mm_err(res[2 + k], ores[k].numpy()) for k in range(4)]
+    rels = [float((res[2 + k].float().cpu() - ores[k]).norm() / ores[k].norm()) for k in range(4)]
+    with capsys.disabled():
+        print("\n[bf16 path] joints r3d_1, r2d_1, r3d_2, r2d_2: mean error mm", ["%.3f" % e for e in errs], "relative", ["%.4f" % r for r in rels])
+    for k in range(2):
+        a, b = sws[k].float().cpu(), osw[k]
+        assert float((a - b).norm() / b.norm()) < 1e-2
+    # stage-1 joints come straight out of bf16 features: 1e-2 relative class; stage 2 re-enters thresholded geometry (DESA ball
+    # membership, closeness masks) with stage-1's rounding, so it is bounded more loosely
+    assert max(rels[:2]) < 2e-2 and max(rels[2:]) < 6e-2, rels
