@@ -157,6 +157,14 @@ int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, co
                     const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out, float* part_acc, float* part_ms,
                     int num_sms, cudaStream_t stream);
 
+/* ---- 8f-1 DESA on tensor cores (csrc/desa_fused.cu), model/model.py:129-204 + joint embeddings :323-325 ---------------
+ * e / part_acc / part_ms: outputs of kpf_point_embed; pcl [B,N,3]; joint [B,J,3]; S scales with radii r0..r3 and
+ * `nsample` grouped points each; wmat/wvec from ops.pack_desa.  -> desa_part [B,S,J,128] f32 (per-scale max-pooled MLP
+ * outputs) and jf_out [B,J,128] f32 (embedded joint features); the 512->128 fusion conv consumes [desa_part | jf]. */
+int kpf_desa_fused(const void* e, const float* part_acc, const float* part_ms, const float* pcl, const float* joint, const void* wmat,
+                   const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2, float r3, float* desa_part,
+                   float* jf_out, cudaStream_t stream);
+
 /* ---- bring-up self-test of the tcgen05 primitives (csrc/umma.cuh): D[128,N] f32 = A * B^T with bf16 operands.
  * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);
  * b_mn == 0: B is [N,K] row-major, else B is given as [K,N]. */

@@ -260,6 +260,8 @@ class DESA(_KernelCache, nn.Module):
             k["f0"].append(_fold_bn(self.conv_f0_blocks[i].weight, self.conv_f0_blocks[i].bias, self.bn_f0_blocks[i]))
             k["mlp"].append([_fold_bn(c.weight, c.bias, b) for c, b in zip(self.conv_blocks[i], self.bn_blocks[i])])
         k["fusion"] = _fold_bn(self.fusion[0].weight, self.fusion[0].bias, self.fusion[1])
+        k["scales"] = [(k["f0"][i][0], k["f0"][i][1], k["l0"][i][0], k["l0"][i][1], k["mlp"][i][0][0], k["mlp"][i][0][1])
+                       for i in range(self.scale_num)] if all(len(m) == 1 for m in k["mlp"]) else None
         return k
 
     def forward(self, pcl_feat, node_feat, pcl_xyz, node_xyz):
@@ -345,11 +347,12 @@ class Block_KPFusion(_KernelCache, nn.Module):
         Wj, bj = _fold_bn(self.joint_feat_emb[0].weight, self.joint_feat_emb[0].bias, self.joint_feat_emb[1])
         Wjx, bjx = _fold_bn(self.joint_xyz_emb[0].weight, self.joint_xyz_emb[0].bias, self.joint_xyz_emb[1])
         pe_wmat, pe_wvec = ops.pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, self.joint_num)
-        return dict(W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
+        ds_wmat, ds_wvec = ops.pack_desa(Wj, bj, Wjx, bjx, self.FA.kc()["scales"])
+        return dict(ds_wmat=ds_wmat, ds_wvec=ds_wvec, W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
                     W_joint=torch.cat([Wj, Wjx], 1).contiguous(), b_joint=(bj + bjx).contiguous(), pe_wmat=pe_wmat, pe_wvec=pe_wvec)
 
     def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
-                img_down, center, M, cube, cam_para, writer=None, ii=0):
+                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None):
         k = self.kc()
         B, N, _ = pcl.shape
         C, H = img_feat.shape[1], img_feat.shape[2]
@@ -357,18 +360,26 @@ class Block_KPFusion(_KernelCache, nn.Module):
         prec = self.precision if self.precision != "auto" else ("bf16" if img_feat.dtype == torch.bfloat16 else "fp32")
         pcl = pcl.float().contiguous()
         joint_xyz = joint_xyz.detach().float().contiguous()
-        # RGB keypoint aggregation (model.py:295-306): K4b + K3
-        pcl_offset = ops.pcl_joint2offset(joint_xyz, pcl, 0.8)
-        pcl_feat = ops.gather_taps(img_feat, pcl_index, pcl_closeness).float()
-        pcl_feat_rgb = ops.gather_taps(img_feature_rgb, pcl_index, pcl_closeness).float()
-        pcl_weight = ops.gather_taps(img_offset[:, J * 4:], pcl_index, pcl_closeness).float()
-        # decoupled generation of RGB-D point features (model.py:312-317): folded Conv1d+BN embeddings
-        e = F.relu(F.linear(torch.cat((pcl_feat, pcl, pcl_weight, pcl_offset), dim=-1), k["W_pcl"], k["b_pcl"]))
-        e = F.relu(e + F.linear(pcl_feat_rgb, k["W_rgb"], k["b_rgb"]))
-        attention = F.softmax(pcl_weight.permute(0, 2, 1), dim=-1)                       # model.py:319
-        joint_feat = torch.matmul(attention, e)                                          # model.py:320
-        joint_feat = F.relu(F.linear(torch.cat((joint_feat, joint_xyz), dim=-1), k["W_joint"], k["b_joint"]))  # :323-325
-        joint_feat = self.FA(e, joint_feat, pcl, joint_xyz)                              # model.py:327
+        if prec == "bf16" and N % 128 == 0 and J <= 21 and self.FA.kc()["scales"] is not None and len(set(self.FA.S)) == 1:
+            # tensor-core path: point stage (K4b + K3 + embeddings + softmax partials) and DESA, two fused kernels
+            if featT is None:
+                featT = ops.repack_features(img_feat, img_feature_rgb, img_offset[:, J * 4:])
+            e, p_acc, p_ms = ops.point_embed(featT, pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8)
+            part, jf = ops.desa_fused(e, p_acc, p_ms, pcl, joint_xyz, k["ds_wmat"], k["ds_wvec"], self.FA.radius, self.FA.S[0])
+            joint_feat = F.relu(F.linear(torch.cat((part.permute(0, 2, 1, 3).reshape(B, J, -1), jf), dim=-1), *self.FA.kc()["fusion"]))
+        else:
+            # RGB keypoint aggregation (model.py:295-306): K4b + K3
+            pcl_offset = ops.pcl_joint2offset(joint_xyz, pcl, 0.8)
+            pcl_feat = ops.gather_taps(img_feat, pcl_index, pcl_closeness).float()
+            pcl_feat_rgb = ops.gather_taps(img_feature_rgb, pcl_index, pcl_closeness).float()
+            pcl_weight = ops.gather_taps(img_offset[:, J * 4:], pcl_index, pcl_closeness).float()
+            # decoupled generation of RGB-D point features (model.py:312-317): folded Conv1d+BN embeddings
+            e = F.relu(F.linear(torch.cat((pcl_feat, pcl, pcl_weight, pcl_offset), dim=-1), k["W_pcl"], k["b_pcl"]))
+            e = F.relu(e + F.linear(pcl_feat_rgb, k["W_rgb"], k["b_rgb"]))
+            attention = F.softmax(pcl_weight.permute(0, 2, 1), dim=-1)                       # model.py:319
+            joint_feat = torch.matmul(attention, e)                                          # model.py:320
+            joint_feat = F.relu(F.linear(torch.cat((joint_feat, joint_xyz), dim=-1), k["W_joint"], k["b_joint"]))  # :323-325
+            joint_feat = self.FA(e, joint_feat, pcl, joint_xyz)                              # model.py:327
         outfeature_init_TR, refined_3d_joints = self.init_TR(joint_feat, precision=prec)  # model.py:330
         # depth keypoint aggregation (model.py:334-344): K4c + K5 fused
         spatial_weight_loss, img_feat_j = ops.spatial_aggregate(
@@ -419,11 +430,14 @@ class KPFusion(nn.Module):
                                                         want_i64=False, want_i32=True)                  # :411
         updated_2d_feature = [None] * (self.num_stages + 1)
         spatial_weight = [None] * self.num_stages
+        featT = None
+        if img_feat.dtype == torch.bfloat16 and self.block1.precision in ("auto", "bf16"):
+            featT = ops.repack_features(img_feat, img_feat_rgb, img_offset[:, J * 4:])   # shared by both blocks
         for i in range(self.num_stages):                                                                 # :417-424
             block = getattr(self, f"block{i + 1}")
             r3d, r2d, updated_2d_feature[i + 1], spatial_weight[i], _ = block(
                 img_feat, img_feat_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature[i], loader, img_down,
-                center, M, cube, cam_para, writer, ii)
+                center, M, cube, cam_para, writer, ii, featT=featT)
             result.append(r3d)
             result.append(r2d)
             joint_xyz = r2d

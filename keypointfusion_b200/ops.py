@@ -462,3 +462,32 @@ def combine_point_partials(acc, ms, J):
     num = (acc[:, :, :, :J] * sc.unsqueeze(2)).sum(1)                # B 128 J
     den = (s_t * sc).sum(1)                                          # B J
     return (num / den.unsqueeze(1)).permute(0, 2, 1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ fused DESA
+def pack_desa(Wj, bj, Wjx, bjx, scales):
+    """Wj [128,128], Wjx [128,3] (BN-folded joint_feat_emb / joint_xyz_emb); scales: list of (Wf0, bf0, Wl0, bl0, W2, b2), all BN-folded.
+    -> (wmat bf16, wvec f32) for kpf_desa_fused."""
+    mats = [_canon(Wj)]
+    wx = Wj.new_zeros(128, 4)
+    wx[:, :3] = Wjx
+    vecs = [(bj + bjx).float(), wx.reshape(-1).float()]
+    for Wf0, bf0, Wl0, bl0, W2, b2 in scales:
+        tail = Wf0.new_zeros(128, 16)
+        tail[:, :3] = Wl0
+        mats += [_canon(Wf0), _canon(tail), _canon(W2)]
+        vecs += [(bf0 + bl0).float(), b2.float()]
+    return torch.cat(mats).contiguous(), torch.cat(vecs).contiguous()
+
+
+def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample):
+    pcl, joint = _f32(pcl), _f32(joint)
+    B, N, _ = pcl.shape
+    J = joint.shape[1]
+    S = len(radius)
+    r = list(radius) + [0.0] * (4 - S)
+    part = torch.empty(B, S, J, 128, device=pcl.device, dtype=torch.float32)
+    jf = torch.empty(B, J, 128, device=pcl.device, dtype=torch.float32)
+    _call("kpf_desa_fused", _p(e), _p(part_acc), _p(part_ms), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, S, nsample, float(r[0]),
+          float(r[1]), float(r[2]), float(r[3]), _p(part), _p(jf))
+    return part, jf

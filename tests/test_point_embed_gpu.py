@@ -54,3 +54,39 @@ def test_point_embed(golden, golden_inputs, path_params, B):
     ragg = torch.softmax(pw.permute(0, 2, 1), -1) @ ee
     assert rms_rel(e, ee) < 1e-2, rms_rel(e, ee)
     assert rms_rel(agg, ragg) < 1e-2, rms_rel(agg, ragg)
+
+
+@pytest.mark.parametrize("B", [2, 3])
+def test_desa_fused(path_params, B):
+    """point stage -> DESA kernel vs the oracle's joint embeddings + DESA (same ball-query membership: centres are inputs)."""
+    from keypointfusion_b200 import ops
+    from keypointfusion_b200.model.model import Block_KPFusion
+    import torch.nn.functional as F
+    inp = synth.make_inputs(B, 128, 21, 128, seed=70 + B, bf16_round=True)
+    c = {k: v.to(DEV) for k, v in inp.items()}
+    pcl, _ = ops.getpcl(c["img"], c["center"], c["cube"], c["M"], c["cam"], seed=2)
+    close, _, idx = ops.img2pcl_index(pcl, c["img"], c["center"], c["M"], c["cube"], c["cam"], 128, 4, fs=32, want_i64=False, want_i32=True)
+    # joints placed on points of the cloud so that every ball is well populated
+    joint = pcl[:, ::48][:, :21].contiguous() + 0.01
+    blk = Block_KPFusion(21)
+    blk.load_state_dict({k[len("block1."):]: v for k, v in path_params.items() if k.startswith("block1.")})
+    blk = blk.to(DEV).eval()
+    k = blk.kc()
+    featT = ops.repack_features(c["img_feat"].bfloat16(), c["img_feat_rgb"].bfloat16(), c["img_offset"][:, 84:].bfloat16())
+    e, acc, ms = ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8)
+    part, jf = ops.desa_fused(e, acc, ms, pcl, joint, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0])
+    fu = blk.FA.kc()["fusion"]
+    out = F.relu(F.linear(torch.cat([part.permute(0, 2, 1, 3).reshape(B, 21, -1), jf], -1), *fu))
+    # oracle
+    p = path_params
+    pc, ix, cl, jt = pcl.cpu(), idx.cpu().long(), close.cpu(), joint.cpu()
+    off = O.pcl_joint2offset(jt, pc, 0.8)
+    pf, pr = O.gather_taps(inp["img_feat"], ix, cl), O.gather_taps(inp["img_feat_rgb"], ix, cl)
+    pw = O.gather_taps(inp["img_offset"][:, 84:], ix, cl)
+    ee = torch.relu(O.conv_bn(p, "block1.pcl_feat_emb.", pf) + O.conv_bn(p, "block1.pcl_xyz_emb.", pc) +
+                    O.conv_bn(p, "block1.pcl_pose_emb.", torch.cat([pw, off], -1)))
+    ee = torch.relu(ee + O.conv_bn(p, "block1.pcl_feat_emb_RGB.", pr))
+    rjf = torch.relu(O.conv_bn(p, "block1.joint_feat_emb.", torch.softmax(pw.permute(0, 2, 1), -1) @ ee) + O.conv_bn(p, "block1.joint_xyz_emb.", jt))
+    rout = O.desa(p, "block1.FA.", ee, rjf, pc, jt)
+    assert rms_rel(jf, rjf) < 1e-2, rms_rel(jf, rjf)
+    assert rms_rel(out, rout) < 1e-2, rms_rel(out, rout)
