@@ -1,0 +1,203 @@
+// K5 on tensor cores: depth-keypoint spatial attention + aggregation, model/model.py:334-344 (with K4c = a10, a11 fused).
+// Same math as csrc/spatial_agg.cu (see there for the reference mapping); here both contractions are tcgen05 MMAs:
+//
+//   GEMM A   S1[hw][j]  = sum_c F[c][hw] Wa[j][c] + sum_j' hm[j'][hw] Wa[j][C+j']        M = 128 cells, N = 32, K = 128 + 32
+//   epilogue sw = sigmoid(S1 + ba) -> global ; G[hw][j] = fc_w[hw] (sg GAM + (1-sg) sw)    (thread = cell)
+//   GEMM B   out[c][j] += sum_hw relu(F[c][hw]) G[hw][j]                                   M = 128 channels, N = 32, K = 128 cells
+//
+// The NCHW feature tile [128 c x 128 hw] is staged ONCE per tile with 16-byte cp.async into the SWIZZLE_NONE canonical
+// layout and read by GEMM A as an MN-major A operand (M = hw contiguous) and -- same bytes, LBO/SBO swapped, after an
+// in-place relu pass -- by GEMM B as a K-major A operand (K = hw contiguous).  One CTA per sample sweeps its HW/128
+// tiles, accumulating out[c][j] in TMEM; the next tile's features are prefetched while the current one is consumed.
+#include "umma.cuh"
+
+namespace kpf {
+
+struct SpatialParams {
+    const __nv_bfloat16* feat;   // [B,128,HW]
+    const float* joints;         // [B,J,3] (uvd)
+    const float* depth;
+    long long depth_bs;
+    int depth_rs, depth_cs;
+    const float *center, *M, *cube, *cam;
+    const uint4* wa;             // canonical bf16: Wa[:, :128] as [16][32], Wa[:, 128:] as [4][32]
+    const float *ba, *weight_dis, *fc_w, *fc_b, *prev;
+    float *sw_out, *feat_j_out;
+    int B, J, fs;
+    float img_size, flip, hm_std, hm_sigma, gamma;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const SpatialParams p) {
+    extern __shared__ __align__(128) unsigned char k5_smem[];
+    uint4* sF = reinterpret_cast<uint4*>(k5_smem);  // [2][2048] double-buffered raw feature tile, index (c/8)*128 + (hw/8)*8 + (c%8)
+    uint4* sFr = sF + 4096;                          // [2048]   relu copy
+    uint4* sHm = sFr + 2048;                         // [4][128] heat-map rows, K-major A operand (K = 32 joints)
+    uint4* sG = sHm + 512;                           // [16][4][8] G, MN-major B operand [K = 128 cells][N = 32]
+    uint4* sWa = sG + 512;                           // [16][32] + [4][32]
+    float* sJ = reinterpret_cast<float*>(sWa + 640); // [32][8]: hm centre (x,y), xyz
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ CamF cam;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.x, J = p.J, fs = p.fs, HW = fs * fs, T = HW / 128;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t ACC1 = 0, ACC2 = 32;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, 64);
+    if (tid == 0) {
+        mbar_init(&mma_bar, 1);
+        fence_mbar_init();
+        load_cam(cam, b, p.center, p.M, p.cube, p.cam, p.img_size, p.flip);
+    }
+    for (int i = tid; i < 640; i += 128) sWa[i] = p.wa[i];
+    const __nv_bfloat16* fb = p.feat + (size_t)b * 128 * HW;
+    // tile loader: thread -> (c%8 = tid%8, hw8 = tid/8); 16 passes over c/8
+    auto load_tile = [&](int t, uint4* dst) {
+        const int c8 = tid & 7, hw8 = tid >> 3;
+#pragma unroll 4
+        for (int cg = 0; cg < 16; ++cg)
+            cp_async16(dst + cg * 128 + hw8 * 8 + c8, fb + (size_t)(cg * 8 + c8) * HW + t * 128 + hw8 * 8);
+    };
+    load_tile(0, sF);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid < J) {
+        const float* s = p.joints + ((size_t)b * J + tid) * 3;
+        sJ[8 * tid + 0] = (s[0] + 1.f) / 2.f * (float)fs;  // generateFeature.py:592-593
+        sJ[8 * tid + 1] = (s[1] + 1.f) / 2.f * (float)fs;
+        const float3 q = uvd2xyz(cam, s[0], s[1], s[2]);   // loader.py:800
+        sJ[8 * tid + 2] = q.x;
+        sJ[8 * tid + 3] = q.y;
+        sJ[8 * tid + 4] = q.z;
+    }
+    const uint32_t tmem0 = tmem_slot, tmem = tmem0 + lane_off;
+    uint32_t phase = 0;
+    const float sg = 1.f / (1.f + __expf(-p.weight_dis[0]));
+    const float inv2s2 = 1.f / (2.f * p.hm_sigma * p.hm_sigma * p.hm_std * p.hm_std);
+    const float ffs = (float)fs;
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+        uint4* cur = sF + (t & 1) * 2048;
+        cp_async_wait_all();   // this thread's part of tile t has landed ...
+        __syncthreads();       // ... and everybody's; the other buffer's readers (tile t-1) are done
+        if (t + 1 < T) load_tile(t + 1, sF + ((t + 1) & 1) * 2048);  // overlaps the whole iteration
+        // ---- per-cell geometry (thread = cell): heat-map row (A operand) and GAM (registers)
+        const int m = t * 128 + tid, r = m / fs, col = m - r * fs;
+        const float d = __ldg(p.depth + (size_t)b * p.depth_bs + (size_t)r * p.depth_rs + (size_t)col * p.depth_cs);
+        const float3 q = uvd2xyz(cam, cell_coord(col, ffs), cell_coord(r, ffs), d);
+        float gam[32], hm[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < J) {
+                const float dx = (float)col + 0.5f - sJ[8 * j], dy = (float)r + 0.5f - sJ[8 * j + 1];
+                hm[j] = __expf(-(dx * dx + dy * dy) * inv2s2);
+                const float ex = q.x - sJ[8 * j + 2], ey = q.y - sJ[8 * j + 3], ez = q.z - sJ[8 * j + 4];
+                gam[j] = 1.f / (p.gamma * (ex * ex + ey * ey + ez * ez) + 1.f);
+            } else {
+                hm[j] = 0.f;
+                gam[j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sHm[c * 128 + tid] = pack8_bf16(hm + 8 * c);
+        // relu copy for GEMM B (same layout)
+        for (int i = tid; i < 2048; i += 128) {
+            uint4 v = cur[i];
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+            const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = __hmax2(h[k], z);
+            sFr[i] = v;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            // GEMM A: A = F tile MN-major (LBO 2048 between channel groups, SBO 128 between cell groups)
+            umma_gemm(tmem0 + ACC1, smem_u32(cur), 2048, 128, smem_u32(sWa), 512, 128, umma_idesc_bf16(128, 32, true, false), 128, false);
+            umma_gemm(tmem0 + ACC1, smem_u32(sHm), 2048, 128, smem_u32(sWa + 512), 512, 128, umma_idesc_bf16(128, 32, false, false), 32, true);
+            umma_commit(&mma_bar);
+        }
+        mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        {
+            float s1[32];
+            tmem_ld32(tmem + ACC1, s1);
+            const float fw = p.fc_w[m];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < J) {
+                    const float swv = 1.f / (1.f + __expf(-(s1[j] + __ldg(p.ba + j))));
+                    p.sw_out[((size_t)b * J + j) * HW + m] = swv;
+                    s1[j] = fw * (sg * gam[j] + (1.f - sg) * swv);  // model.py:337-338 and fc_spatial2joint_feature's weight
+                } else {
+                    s1[j] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sG[(tid >> 3) * 32 + c * 8 + (tid & 7)] = pack8_bf16(s1 + 8 * c);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            // GEMM B: A = relu(F) tile read K-major (K = cells): LBO 128 between cell groups, SBO 2048 between channel groups
+            umma_gemm(tmem0 + ACC2, smem_u32(sFr), 128, 2048, smem_u32(sG), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, t > 0);
+            umma_commit(&mma_bar);
+        }
+        mbar_wait(&mma_bar, phase);  // sFr / sG / sHm are rewritten by the next tile
+        phase ^= 1;
+        tc_fence_after();
+    }
+    {
+        float o[32];
+        tmem_ld32(tmem + ACC2, o);  // thread = channel c
+        const float fb0 = p.fc_b[0];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < J) {
+                float v = o[j] + fb0;
+                const size_t idx = ((size_t)b * J + j) * 128 + tid;
+                if (p.prev) v = fmaxf((v + p.prev[idx]) * 0.5f, 0.f);  // model.py:343-344
+                p.feat_j_out[idx] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, 64);
+}
+
+}  // namespace kpf
+
+extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joints, const float* depth, long long depth_bs, int depth_rs,
+                                        int depth_cs, const float* center, const float* M, const float* cube, const float* cam,
+                                        const void* wa_packed, const float* ba, const float* weight_dis, const float* fc_w,
+                                        const float* fc_b, const float* prev, int B, int C, int J, int fs, float img_size, float flip,
+                                        float hm_std, float hm_sigma, float gamma, float* sw_out, float* feat_j_out, cudaStream_t stream) {
+    using namespace kpf;
+    KPF_REQUIRE(B >= 0 && C == 128 && J >= 1 && J <= 32 && fs >= 1 && (fs * fs) % 128 == 0);
+    KPF_REQUIRE(((uintptr_t)feat_rgb % 16) == 0 && ((uintptr_t)wa_packed % 16) == 0);
+    if (B == 0) return 0;
+    SpatialParams p;
+    p.feat = (const __nv_bfloat16*)feat_rgb; p.joints = joints; p.depth = depth; p.depth_bs = depth_bs; p.depth_rs = depth_rs;
+    p.depth_cs = depth_cs; p.center = center; p.M = M; p.cube = cube; p.cam = cam; p.wa = (const uint4*)wa_packed; p.ba = ba;
+    p.weight_dis = weight_dis; p.fc_w = fc_w; p.fc_b = fc_b; p.prev = prev; p.sw_out = sw_out; p.feat_j_out = feat_j_out;
+    p.B = B; p.J = J; p.fs = fs; p.img_size = img_size; p.flip = flip; p.hm_std = hm_std; p.hm_sigma = hm_sigma; p.gamma = gamma;
+    const size_t smem = (size_t)(4096 + 2048 + 512 + 512 + 640) * 16 + 32 * 8 * 4;
+    cudaError_t e = cudaFuncSetAttribute(spatial_aggregate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    spatial_aggregate_tc_kernel<<<B, 128, smem, stream>>>(p);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}

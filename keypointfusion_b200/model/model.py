@@ -348,7 +348,8 @@ class Block_KPFusion(_KernelCache, nn.Module):
         Wjx, bjx = _fold_bn(self.joint_xyz_emb[0].weight, self.joint_xyz_emb[0].bias, self.joint_xyz_emb[1])
         pe_wmat, pe_wvec = ops.pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, self.joint_num)
         ds_wmat, ds_wvec = ops.pack_desa(Wj, bj, Wjx, bjx, self.FA.kc()["scales"])
-        return dict(ds_wmat=ds_wmat, ds_wvec=ds_wvec, W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
+        wa_packed = ops.pack_spatial_wa(self.atten_spatial.weight, self.joint_num, self.dim)
+        return dict(wa_packed=wa_packed, ds_wmat=ds_wmat, ds_wvec=ds_wvec, W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
                     W_joint=torch.cat([Wj, Wjx], 1).contiguous(), b_joint=(bj + bjx).contiguous(), pe_wmat=pe_wmat, pe_wvec=pe_wvec)
 
     def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
@@ -382,10 +383,16 @@ class Block_KPFusion(_KernelCache, nn.Module):
             joint_feat = self.FA(e, joint_feat, pcl, joint_xyz)                              # model.py:327
         outfeature_init_TR, refined_3d_joints = self.init_TR(joint_feat, precision=prec)  # model.py:330
         # depth keypoint aggregation (model.py:334-344): K4c + K5 fused
-        spatial_weight_loss, img_feat_j = ops.spatial_aggregate(
-            img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, self.atten_spatial.weight,
-            self.atten_spatial.bias, self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias,
-            prev=updated_2d_feature, img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)
+        if prec == "bf16" and img_feature_rgb.dtype == torch.bfloat16 and C == 128 and (H * H) % 128 == 0 and J <= 32:
+            spatial_weight_loss, img_feat_j = ops.spatial_aggregate_tc(
+                img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, k["wa_packed"], self.atten_spatial.bias,
+                self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias, prev=updated_2d_feature,
+                img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)
+        else:
+            spatial_weight_loss, img_feat_j = ops.spatial_aggregate(
+                img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, self.atten_spatial.weight,
+                self.atten_spatial.bias, self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias,
+                prev=updated_2d_feature, img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)
         # inter-modal keypoint feature interaction (model.py:347-349): K6 writes straight into final_TR's input
         tr_in = torch.empty(B, J, 3 + self.dim, device=pcl.device, dtype=torch.float32)
         tr_in[:, :, :3] = refined_3d_joints

@@ -491,3 +491,33 @@ def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample):
     _call("kpf_desa_fused", _p(e), _p(part_acc), _p(part_ms), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, S, nsample, float(r[0]),
           float(r[1]), float(r[2]), float(r[3]), _p(part), _p(jf))
     return part, jf
+
+
+# ------------------------------------------------------------------------------------------------ a12 on tensor cores
+def pack_spatial_wa(Wa, J, C=128):
+    """atten_spatial.weight [J, C+J(,1,1)] -> canonical bf16 B operands: Wa[:, :C] as [16][32][8], Wa[:, C:] as [4][32][8]."""
+    Wa = Wa.detach().float().reshape(J, C + J)
+    main = Wa.new_zeros(32, C)
+    main[:J] = Wa[:, :C]
+    hm = Wa.new_zeros(32, 32)
+    hm[:J, :J] = Wa[:, C:]
+    return torch.cat([_canon(main), _canon(hm)]).contiguous()
+
+
+def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed, ba, weight_dis, fc_w, fc_b, prev=None, img_size=128,
+                         flip=1.0, hm_std=0.8, hm_sigma=1.0, gamma=10.0):
+    _need_cuda(feat_rgb)
+    assert feat_rgb.dtype == torch.bfloat16
+    feat_rgb = feat_rgb.contiguous()
+    B, C, fs, _ = feat_rgb.shape
+    joints, center, M, cube, cam = _f32(joints), _f32(center), _f32(M), _f32(cube), _f32(cam)
+    J = joints.shape[1]
+    d, bs, rs, cs, fs = _depth_view(img, fs)
+    ba, weight_dis, fc_w, fc_b = _f32(ba), _f32(weight_dis), _f32(fc_w.reshape(-1)), _f32(fc_b)
+    prev = _f32(prev) if prev is not None else None
+    sw = torch.empty(B, J, fs, fs, device=feat_rgb.device, dtype=torch.float32)
+    fj = torch.empty(B, J, C, device=feat_rgb.device, dtype=torch.float32)
+    _call("kpf_spatial_aggregate_tc", _p(feat_rgb), _p(joints), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam), _p(wa_packed),
+          _p(ba), _p(weight_dis), _p(fc_w), _p(fc_b), _p(prev), B, C, J, fs, float(img_size), float(flip), float(hm_std), float(hm_sigma),
+          float(gamma), _p(sw), _p(fj))
+    return sw, fj

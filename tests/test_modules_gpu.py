@@ -148,6 +148,21 @@ def test_fusion_path_bf16_tensor_core(net, path_params, capsys):
     for k in range(2):
         a, b = sws[k].float().cpu(), osw[k]
         assert float((a - b).norm() / b.norm()) < 1e-2
-    # stage-1 joints come straight out of bf16 features: 1e-2 relative class; stage 2 re-enters thresholded geometry (DESA ball
-    # membership, closeness masks) with stage-1's rounding, so it is bounded more loosely
-    assert max(rels[:2]) < 2e-2 and max(rels[2:]) < 6e-2, rels
+    # stage-1 joints come straight out of bf16 features: 1e-2 relative class.  Stage 2 re-enters thresholded geometry (DESA ball
+    # membership, closeness masks) with stage-1's joints; the ORACLE itself amplifies a 1 % perturbation of those joints to
+    # ~12 % / ~7 % of r3d_2 / r2d_2 with these O(1)-gain random weights (measured, DESIGN.md "bf16 error budget"), so the
+    # end-to-end stage-2 bound is 12x the stage-1 error, and block 2 is pinned separately below on the oracle's stage-1 outputs.
+    assert max(rels[:2]) < 2e-2, rels
+    assert max(rels[2:]) < 12 * max(rels[:2]), rels
+    t1 = ex["block1"]
+    with torch.no_grad():
+        (o3, o2, ofj, osw1, _), _ = O.block_kpfusion(path_params, "block1.", inp["img_feat"], inp["img_feat_rgb"], pcl.cpu(), ex["joint_xyz0"],
+                                                     ex["closeness"], ex["index"], inp["img_offset"], None, O.nearest_down(inp["img"], 32),
+                                                     inp["center"].numpy(), inp["M"].numpy(), inp["cube"].numpy(), inp["cam"].numpy(), 128)
+        r3d, r2d, fj, sw, _ = net.block2(c["img_feat"], c["img_feat_rgb"], pcl, o2.to(DEV), ex["closeness"].to(DEV), ex["index"].to(DEV).int(),
+                                         c["img_offset"], ofj.to(DEV), loader(img_size=128), c["img"][:, :, ::4, ::4], c["center"], c["M"],
+                                         c["cube"], c["cam"])
+    iso = [float((r3d.float().cpu() - ores[2]).norm() / ores[2].norm()), float((r2d.float().cpu() - ores[3]).norm() / ores[3].norm())]
+    with capsys.disabled():
+        print("[bf16 path] block 2 in isolation (oracle stage-1 inputs): relative", ["%.4f" % r for r in iso])
+    assert iso[0] < 2e-2 and iso[1] < 3e-2, iso   # r2d stacks K5 + two more 4-layer bf16 token stacks on top of r3d
