@@ -135,14 +135,19 @@ int kpf_ball_query(const float* xyz, const float* centers, int B, int Np, int J,
                    cudaStream_t stream);
 
 /* ---- a13 / 8f-2 on tensor cores: keypoint-token transformer stacks (csrc/token_stack.cu) ------------------------
- * mode 0: KP_Interaction_TR.forward (model/model.py:45-126): x [B,J,D] (D = 128, or 128 < D <= 144 with the
- *         extra D-128 inputs LEADING, like cat([joints, feats])) -> tokens_out [B,J,128], pred_out [B,J,3].
- * mode 1: updatedDecoder's live layer (model/transfusion_head.py:684-708): x = anchor, y = tokens -> out_cj / out_jc
- *         as in kpf_cross_decoder_layer.  bf16 tensor-core operands, fp32 accumulation / residual / LayerNorm / heads.
- * wmat (bf16) / wvec (f32): packed by keypointfusion_b200.ops.pack_token_encoder / pack_token_cross. */
-int kpf_token_stack(const float* x, const float* y, const void* wmat, const float* wvec, int mode, int B, int J, int D, int L, int F,
-                    int act, float eps, float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride,
-                    int out_jc_c0, cudaStream_t stream);
+ * One launch runs, in this order and each optional:  cross != 0: updatedDecoder's live layer (transfusion_head.py:684-708)
+ * on x = anchor [B,J,128], y = tokens [B,J,128];  pre != 0: DESA's fusion conv on desa [B,3,J,128] | jf [B,J,128]
+ * (model.py:160-164);  L > 0: KP_Interaction_TR.forward (model.py:45-126) with L BertLayers on
+ *   - x [B,J,D] (D = 128, or 128 < D <= 144 with the D-128 extra inputs LEADING like cat([joints, feats])), or
+ *   - the fusion-conv output (pre), or
+ *   - cat([r3d [B,J,D-128], cross output]) (cross != 0: crossTR + final_TR fused, model.py:347-349).
+ * Outputs: L > 0 -> tokens_out [B,J,128] (may be NULL), pred_out [B,J,3];  cross only -> out_cj [B,128,J] and/or out_jc.
+ * wmat (bf16 canonical operands), wseq ((offset,count) int32 pairs, n_weights of them), wvec (f32): ops.pack_token_program.
+ * bf16 tensor-core operands; fp32 accumulation, residual stream, LayerNorm, softmax and regression heads.  J <= 32. */
+int kpf_token_stack(const float* x, const float* y, const float* r3d, const float* desa, const float* jf, const void* wmat,
+                    const void* wseq, const float* wvec, int n_weights, int cross, int pre, int B, int J, int D, int L, int F, int Fc,
+                    float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride, int out_jc_c0,
+                    cudaStream_t stream);
 
 /* ---- a7-a9 fused point stage (csrc/point_embed.cu), model/model.py:295-320 ------------------------------------------
  * kpf_repack_features: f_d, f_rgb [B,128,HW], f_w [B,J,HW] (batch stride w_batch_stride elements; = img_offset[:,4J:])

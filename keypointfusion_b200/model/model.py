@@ -192,18 +192,16 @@ class KP_Interaction_TR(_KernelCache, nn.Module):  # model.py:106-126
         _bert_init(self, config.initializer_range)
 
     def _build_kc(self):
-        dev = self.cls_head.weight.device
-        wmat, wvec, D, L, F_ = ops.pack_token_encoder(self.state_dict(), "", 64)
-        return dict(wmat=wmat.to(dev), wvec_J={}, L=L, F=F_)
+        return {}
 
     def forward_tc(self, img_feats, want_tokens=True):
         """bf16 tensor-core path (csrc/token_stack.cu): same contract as forward()."""
         k = self.kc()
         J = img_feats.shape[1]
-        if J not in k["wvec_J"]:  # the position-embedding slice depends on the token count
-            _, wvec, _, _, _ = ops.pack_token_encoder(self.state_dict(), "", J)
-            k["wvec_J"][J] = wvec.to(img_feats.device)
-        return ops.token_encoder(img_feats, k["wmat"], k["wvec_J"][J], k["L"], k["F"], want_tokens)
+        if J not in k:  # the position-embedding slice depends on the token count
+            k[J] = ops.pack_token_program(J, enc=(self.state_dict(), "")).to(img_feats.device)
+        tokens, pred, _ = ops.token_stack(k[J], x=img_feats, want_tokens=want_tokens)
+        return tokens, pred
 
     def forward(self, img_feats, *unused, precision="fp32", **unused_kw):
         """img_feats [B,J,D] -> (tokens [B,J,hidden], pred [B,J,3]).  model.py:45-103, :116-126."""
@@ -349,7 +347,11 @@ class Block_KPFusion(_KernelCache, nn.Module):
         pe_wmat, pe_wvec = ops.pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, self.joint_num)
         ds_wmat, ds_wvec = ops.pack_desa(Wj, bj, Wjx, bjx, self.FA.kc()["scales"])
         wa_packed = ops.pack_spatial_wa(self.atten_spatial.weight, self.joint_num, self.dim)
-        return dict(wa_packed=wa_packed, ds_wmat=ds_wmat, ds_wvec=ds_wvec, W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
+        dev = self.weight_dis.device
+        tok_init = ops.pack_token_program(self.joint_num, enc=(self.init_TR.state_dict(), ""), fusion=self.FA.kc()["fusion"]).to(dev)
+        tok_final = ops.pack_token_program(self.joint_num, cross=(self.crossTR.decoder[-1].state_dict(), ""),
+                                           enc=(self.final_TR.state_dict(), "")).to(dev)
+        return dict(tok_init=tok_init, tok_final=tok_final, wa_packed=wa_packed, ds_wmat=ds_wmat, ds_wvec=ds_wvec, W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
                     W_joint=torch.cat([Wj, Wjx], 1).contiguous(), b_joint=(bj + bjx).contiguous(), pe_wmat=pe_wmat, pe_wvec=pe_wvec)
 
     def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
@@ -361,26 +363,37 @@ class Block_KPFusion(_KernelCache, nn.Module):
         prec = self.precision if self.precision != "auto" else ("bf16" if img_feat.dtype == torch.bfloat16 else "fp32")
         pcl = pcl.float().contiguous()
         joint_xyz = joint_xyz.detach().float().contiguous()
-        if prec == "bf16" and N % 128 == 0 and J <= 21 and self.FA.kc()["scales"] is not None and len(set(self.FA.S)) == 1:
-            # tensor-core path: point stage (K4b + K3 + embeddings + softmax partials) and DESA, two fused kernels
+        fused = (prec == "bf16" and N % 128 == 0 and J <= 21 and self.FA.kc()["scales"] is not None and len(set(self.FA.S)) == 1
+                 and self.FA.scale_num == 3 and img_feature_rgb.dtype == torch.bfloat16 and C == 128 and (H * H) % 128 == 0)
+        if fused:
+            # tensor-core path, five launches per block:
+            #   point stage (K4b + K3 + embeddings + softmax partials) -> DESA -> [fusion conv + init_TR] -> K5 -> [crossTR + final_TR]
             if featT is None:
                 featT = ops.repack_features(img_feat, img_feature_rgb, img_offset[:, J * 4:])
             e, p_acc, p_ms = ops.point_embed(featT, pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8)
             part, jf = ops.desa_fused(e, p_acc, p_ms, pcl, joint_xyz, k["ds_wmat"], k["ds_wvec"], self.FA.radius, self.FA.S[0])
-            joint_feat = F.relu(F.linear(torch.cat((part.permute(0, 2, 1, 3).reshape(B, J, -1), jf), dim=-1), *self.FA.kc()["fusion"]))
-        else:
-            # RGB keypoint aggregation (model.py:295-306): K4b + K3
-            pcl_offset = ops.pcl_joint2offset(joint_xyz, pcl, 0.8)
-            pcl_feat = ops.gather_taps(img_feat, pcl_index, pcl_closeness).float()
-            pcl_feat_rgb = ops.gather_taps(img_feature_rgb, pcl_index, pcl_closeness).float()
-            pcl_weight = ops.gather_taps(img_offset[:, J * 4:], pcl_index, pcl_closeness).float()
-            # decoupled generation of RGB-D point features (model.py:312-317): folded Conv1d+BN embeddings
-            e = F.relu(F.linear(torch.cat((pcl_feat, pcl, pcl_weight, pcl_offset), dim=-1), k["W_pcl"], k["b_pcl"]))
-            e = F.relu(e + F.linear(pcl_feat_rgb, k["W_rgb"], k["b_rgb"]))
-            attention = F.softmax(pcl_weight.permute(0, 2, 1), dim=-1)                       # model.py:319
-            joint_feat = torch.matmul(attention, e)                                          # model.py:320
-            joint_feat = F.relu(F.linear(torch.cat((joint_feat, joint_xyz), dim=-1), k["W_joint"], k["b_joint"]))  # :323-325
-            joint_feat = self.FA(e, joint_feat, pcl, joint_xyz)                              # model.py:327
+            outfeature_init_TR, refined_3d_joints, _ = ops.token_stack(k["tok_init"], desa=part, jf=jf)        # model.py:203, :330
+            spatial_weight_loss, img_feat_j = ops.spatial_aggregate_tc(
+                img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, k["wa_packed"], self.atten_spatial.bias,
+                self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias, prev=updated_2d_feature,
+                img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)             # model.py:334-344
+            _, refined_2d_joints, _ = ops.token_stack(k["tok_final"], x=img_feat_j, y=outfeature_init_TR, r3d=refined_3d_joints,
+                                                      want_tokens=False)                                      # model.py:347-349
+            return refined_3d_joints, refined_2d_joints, img_feat_j, spatial_weight_loss, None
+        # general path (fp32 features, or shapes the fused kernels do not cover): per-row kernels + library GEMMs for the
+        # GEMM-shaped next-row pieces
+        # RGB keypoint aggregation (model.py:295-306): K4b + K3
+        pcl_offset = ops.pcl_joint2offset(joint_xyz, pcl, 0.8)
+        pcl_feat = ops.gather_taps(img_feat, pcl_index, pcl_closeness).float()
+        pcl_feat_rgb = ops.gather_taps(img_feature_rgb, pcl_index, pcl_closeness).float()
+        pcl_weight = ops.gather_taps(img_offset[:, J * 4:], pcl_index, pcl_closeness).float()
+        # decoupled generation of RGB-D point features (model.py:312-317): folded Conv1d+BN embeddings
+        e = F.relu(F.linear(torch.cat((pcl_feat, pcl, pcl_weight, pcl_offset), dim=-1), k["W_pcl"], k["b_pcl"]))
+        e = F.relu(e + F.linear(pcl_feat_rgb, k["W_rgb"], k["b_rgb"]))
+        attention = F.softmax(pcl_weight.permute(0, 2, 1), dim=-1)                       # model.py:319
+        joint_feat = torch.matmul(attention, e)                                          # model.py:320
+        joint_feat = F.relu(F.linear(torch.cat((joint_feat, joint_xyz), dim=-1), k["W_joint"], k["b_joint"]))  # :323-325
+        joint_feat = self.FA(e, joint_feat, pcl, joint_xyz)                              # model.py:327
         outfeature_init_TR, refined_3d_joints = self.init_TR(joint_feat, precision=prec)  # model.py:330
         # depth keypoint aggregation (model.py:334-344): K4c + K5 fused
         if prec == "bf16" and img_feature_rgb.dtype == torch.bfloat16 and C == 128 and (H * H) % 128 == 0 and J <= 32:

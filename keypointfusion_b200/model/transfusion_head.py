@@ -93,9 +93,8 @@ class TransformerDecoderLayer(nn.Module):
 
     def packed_tc(self, J):
         dev = self.linear1.weight.device
-        if self._tc is None or self._tc[0].device != dev or self._tc[3] != J:
-            wmat, wvec, F_ = ops.pack_token_cross(self.state_dict(), "", J, self.d_model)
-            self._tc = (wmat.to(dev), wvec.to(dev), F_, J)
+        if self._tc is None or self._tc.wmat.device != dev or self._tc.J != J:
+            self._tc = ops.pack_token_program(J, cross=(self.state_dict(), ""), C=self.d_model).to(dev)
         return self._tc
 
     def packed(self, J):
@@ -111,9 +110,8 @@ class TransformerDecoderLayer(nn.Module):
         if not self.cross_only or attn_mask is not None or self.self_posembed is None or self.cross_posembed is None:
             raise NotImplementedError("only the cross_only configuration updatedDecoder builds (transfusion_head.py:652-661)")
         J = query.shape[1]
-        if precision == "bf16" and self.d_model == 128 and self.nhead == 4:
-            wmat, wvec, F_, _ = self.packed_tc(J)
-            return ops.token_cross(query, key, wmat, wvec, F_, out_jc, out_jc_c0, want_cj)
+        if precision == "bf16" and self.d_model == 128 and self.nhead == 4 and J <= 32:
+            return ops.token_stack(self.packed_tc(J), x=query, y=key, out_jc=out_jc, out_jc_c0=out_jc_c0, want_cj=want_cj)[2]
         return ops.cross_decoder_layer(query, key, self.packed(J), self.nhead, self.dim_feedforward, out_jc, out_jc_c0, want_cj)
 
 

@@ -333,66 +333,93 @@ def _pad(v, n):
     return torch.cat([v, v.new_zeros(n - v.numel())]) if v.numel() < n else v
 
 
-def pack_token_encoder(sd, prefix, J, C=128):
-    """KP_Interaction_TR state_dict -> (wmat bf16, wvec f32, D, L, F) for kpf_token_stack mode 0."""
-    g = lambda k: sd[prefix + k].detach().float()
-    Wemb = g("bert.img_embedding.weight")
-    D = Wemb.shape[1]
-    shift = D - C
-    mats = [_canon(Wemb[:, shift:])]
-    if shift > 0:
-        T = Wemb.new_zeros(C, 16)
-        T[:, :shift] = Wemb[:, :shift]
-        mats.append(_canon(T))
-    vecs = [g("bert.position_embeddings.weight")[:J].reshape(-1), g("bert.img_embedding.bias"), g("residual.weight").reshape(-1),
-            _pad(g("residual.bias"), 4), g("cls_head.weight").reshape(-1), _pad(g("cls_head.bias"), 4)]
-    L = 0
-    while f"{prefix}bert.encoder.layer.{L}.attention.self.query.weight" in sd:
-        lp = f"bert.encoder.layer.{L}."
-        F_ = g(lp + "intermediate.dense.weight").shape[0]
-        mats += [_canon(g(lp + "attention.self.query.weight")), _canon(g(lp + "attention.self.key.weight")),
-                 _canon(g(lp + "attention.self.value.weight")), _canon(g(lp + "attention.output.dense.weight")),
-                 _canon(g(lp + "intermediate.dense.weight")), _canon(g(lp + "output.dense.weight"))]
-        vecs += [g(lp + "attention.self.query.bias"), g(lp + "attention.self.key.bias"), g(lp + "attention.self.value.bias"),
-                 g(lp + "attention.output.dense.bias"), g(lp + "attention.output.LayerNorm.weight"),
-                 g(lp + "attention.output.LayerNorm.bias"), _pad(g(lp + "intermediate.dense.bias"), C), g(lp + "output.dense.bias"),
-                 g(lp + "output.LayerNorm.weight"), g(lp + "output.LayerNorm.bias")]
-        L += 1
-    return torch.cat(mats).contiguous(), torch.cat([v.reshape(-1) for v in vecs]).contiguous(), D, L, F_
+class TokenProgram:
+    """Packed weights of one kpf_token_stack launch: optional cross layer, optional DESA-fusion prologue, optional encoder."""
+
+    def __init__(self, wmat, wseq, wvec, cross, pre, D, L, F, Fc, J):
+        self.wmat, self.wseq, self.wvec = wmat, wseq, wvec
+        self.cross, self.pre, self.D, self.L, self.F, self.Fc, self.J = cross, pre, D, L, F, Fc, J
+        self.n_weights = wseq.shape[0]
+
+    def to(self, device):
+        self.wmat, self.wseq, self.wvec = self.wmat.to(device), self.wseq.to(device), self.wvec.to(device)
+        return self
 
 
-def pack_token_cross(sd, prefix, J, C=128):
-    """one TransformerDecoderLayer state_dict -> (wmat bf16, wvec f32, F) for kpf_token_stack mode 1."""
-    g = lambda k: sd[prefix + k].detach().float()
-    Wi, bi = g("multihead_attn.in_proj_weight"), g("multihead_attn.in_proj_bias")
-    F_ = g("linear1.weight").shape[0]
-    mats = [_canon(Wi[:C]), _canon(Wi[C:2 * C]), _canon(Wi[2 * C:]), _canon(g("multihead_attn.out_proj.weight")),
-            _canon(g("linear1.weight")), _canon(g("linear2.weight"))]
-    vecs = [g("self_posembed.weight")[:J].reshape(-1), g("cross_posembed.weight")[:J].reshape(-1), bi[:C], bi[C:2 * C], bi[2 * C:],
-            g("multihead_attn.out_proj.bias"), g("norm2.weight"), g("norm2.bias"), _pad(g("linear1.bias"), C), g("linear2.bias"),
-            g("norm3.weight"), g("norm3.bias")]
-    return torch.cat(mats).contiguous(), torch.cat([v.reshape(-1) for v in vecs]).contiguous(), F_
+def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
+    """enc = (state_dict, prefix) of a KP_Interaction_TR; cross = (state_dict, prefix) of one TransformerDecoderLayer;
+    fusion = (W [128,512], b [128]) BN-folded DESA fusion conv.  Weight order = consumption order of csrc/token_stack.cu."""
+    mats, seq, vecs, off = [], [], [], 0
+
+    def add(m, in_seq=True):
+        nonlocal off
+        n = m.numel() // 8
+        if in_seq:
+            seq.append((off, n))
+        mats.append(m)
+        off += n
+    Fc = D = L = F_ = 0
+    if cross is not None:
+        sd, pf = cross
+        g = lambda k: sd[pf + k].detach().float()
+        Wi, bi = g("multihead_attn.in_proj_weight"), g("multihead_attn.in_proj_bias")
+        Fc = g("linear1.weight").shape[0]
+        for m in (Wi[:C], Wi[C:2 * C], Wi[2 * C:], g("multihead_attn.out_proj.weight"), g("linear1.weight"), g("linear2.weight")):
+            add(_canon(m))
+        vecs += [g("self_posembed.weight")[:J].reshape(-1), g("cross_posembed.weight")[:J].reshape(-1), bi[:C], bi[C:2 * C], bi[2 * C:],
+                 g("multihead_attn.out_proj.bias"), g("norm2.weight"), g("norm2.bias"), _pad(g("linear1.bias"), C), g("linear2.bias"),
+                 g("norm3.weight"), g("norm3.bias")]
+    if fusion is not None:
+        Wfu, bfu = fusion
+        for s_ in range(4):
+            add(_canon(Wfu.detach().float()[:, C * s_:C * (s_ + 1)]))
+        vecs.append(bfu.detach().float())
+    if enc is not None:
+        sd, pf = enc
+        g = lambda k: sd[pf + k].detach().float()
+        Wemb = g("bert.img_embedding.weight")
+        D = Wemb.shape[1]
+        shift = D - C
+        add(_canon(Wemb[:, shift:]))
+        if shift > 0:
+            T = Wemb.new_zeros(C, 16)
+            T[:, :shift] = Wemb[:, :shift]
+            add(_canon(T), in_seq=False)   # K-tail sits right behind the main part
+        vecs += [g("bert.position_embeddings.weight")[:J].reshape(-1), g("bert.img_embedding.bias"), g("residual.weight").reshape(-1),
+                 _pad(g("residual.bias"), 4), g("cls_head.weight").reshape(-1), _pad(g("cls_head.bias"), 4)]
+        while f"{pf}bert.encoder.layer.{L}.attention.self.query.weight" in sd:
+            lp = f"bert.encoder.layer.{L}."
+            F_ = g(lp + "intermediate.dense.weight").shape[0]
+            for k_ in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense",
+                       "intermediate.dense", "output.dense"):
+                add(_canon(g(lp + k_ + ".weight")))
+            vecs += [g(lp + "attention.self.query.bias"), g(lp + "attention.self.key.bias"), g(lp + "attention.self.value.bias"),
+                     g(lp + "attention.output.dense.bias"), g(lp + "attention.output.LayerNorm.weight"),
+                     g(lp + "attention.output.LayerNorm.bias"), _pad(g(lp + "intermediate.dense.bias"), C), g(lp + "output.dense.bias"),
+                     g(lp + "output.LayerNorm.weight"), g(lp + "output.LayerNorm.bias")]
+            L += 1
+    return TokenProgram(torch.cat(mats).contiguous(), torch.tensor(seq, dtype=torch.int32).contiguous(),
+                        torch.cat([v.reshape(-1) for v in vecs]).contiguous(), int(cross is not None), int(fusion is not None), D, L, F_, Fc, J)
 
 
-def token_encoder(x, wmat, wvec, L, F, want_tokens=True):
-    """x [B,J,D] f32 -> (tokens [B,J,128] f32 | None, pred [B,J,3] f32)   (gelu, LayerNorm eps 1e-12)."""
-    x = _f32(x)
-    B, J, D = x.shape
-    tokens = torch.empty(B, J, 128, device=x.device, dtype=torch.float32) if want_tokens else None
-    pred = torch.empty(B, J, 3, device=x.device, dtype=torch.float32)
-    _call("kpf_token_stack", _p(x), None, _p(wmat), _p(wvec), 0, B, J, D, L, F, 1, 1e-12, _p(tokens), _p(pred), None, None, 0, 0)
-    return tokens, pred
-
-
-def token_cross(anchor, tokens, wmat, wvec, F, out_jc=None, out_jc_c0=0, want_cj=True):
-    """anchor, tokens [B,J,128] f32 -> out_cj [B,128,J] (and/or rows of out_jc)   (relu, LayerNorm eps 1e-5)."""
-    anchor, tokens = _f32(anchor), _f32(tokens)
-    B, J, C = anchor.shape
-    out_cj = torch.empty(B, C, J, device=anchor.device, dtype=torch.float32) if want_cj else None
+def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=True, out_jc=None, out_jc_c0=0, want_cj=False):
+    """Run one packed token program.  Returns (tokens [B,J,128] | None, pred [B,J,3] | None, out_cj [B,128,J] | None)."""
+    ref = x if x is not None else desa
+    dev = ref.device
+    B = ref.shape[0]
+    J = pk.J
+    x = _f32(x) if x is not None else None
+    y = _f32(y) if y is not None else None
+    r3d = _f32(r3d) if r3d is not None else None
+    desa = _f32(desa) if desa is not None else None
+    jf = _f32(jf) if jf is not None else None
+    tokens = torch.empty(B, J, 128, device=dev, dtype=torch.float32) if (want_tokens and pk.L > 0) else None
+    pred = torch.empty(B, J, 3, device=dev, dtype=torch.float32) if pk.L > 0 else None
+    out_cj = torch.empty(B, 128, J, device=dev, dtype=torch.float32) if (want_cj and pk.L == 0) else None
     stride = out_jc.shape[-1] if out_jc is not None else 0
-    _call("kpf_token_stack", _p(anchor), _p(tokens), _p(wmat), _p(wvec), 1, B, J, C, 1, F, 0, 1e-5, None, None, _p(out_cj), _p(out_jc),
-          stride, out_jc_c0)
-    return out_cj
+    _call("kpf_token_stack", _p(x), _p(y), _p(r3d), _p(desa), _p(jf), _p(pk.wmat), _p(pk.wseq), _p(pk.wvec), pk.n_weights, pk.cross, pk.pre,
+          B, J, pk.D, pk.L, pk.F, pk.Fc, _p(tokens), _p(pred), _p(out_cj), _p(out_jc), stride, out_jc_c0)
+    return tokens, pred, out_cj
 
 
 # ------------------------------------------------------------------------------------------------ fused point stage
