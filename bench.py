@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--chains", type=int, default=1, help="sub-batch kernel chains captured on parallel streams inside the graph")
     ap.add_argument("--breakdown", action="store_true", help="also print per-stage CUDA-event times to stderr")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -178,7 +179,7 @@ def main():
     gathered = torch.empty(world * B, J, 3, device=dev) if world > 1 else None
 
     from keypointfusion_b200.runtime import GraphedFusionPath
-    graphed = None if a.no_graph else GraphedFusionPath(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0)
+    graphed = None if a.no_graph else GraphedFusionPath(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains)
 
     def step(i, d):
         """d: a dict of device tensors (resident inputs) or of pinned host tensors (e2e)."""

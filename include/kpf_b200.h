@@ -147,7 +147,7 @@ int kpf_ball_query(const float* xyz, const float* centers, int B, int Np, int J,
 int kpf_token_stack(const float* x, const float* y, const float* r3d, const float* desa, const float* jf, const void* wmat,
                     const void* wseq, const float* wvec, int n_weights, int cross, int pre, int B, int J, int D, int L, int F, int Fc,
                     float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride, int out_jc_c0,
-                    cudaStream_t stream);
+                    long long* dbg /* NULL, or 64 x int64 device: clock64 stamps of CTA 0 (profiling aid) */, cudaStream_t stream);
 
 /* ---- a7-a9 fused point stage (csrc/point_embed.cu), model/model.py:295-320 ------------------------------------------
  * kpf_repack_features: f_d, f_rgb [B,128,HW], f_w [B,J,HW] (batch stride w_batch_stride elements; = img_offset[:,4J:])
@@ -160,7 +160,7 @@ int kpf_repack_features(const void* f_d, const void* f_rgb, const void* f_w, lon
                         int HW, void* out, cudaStream_t stream);
 int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint, const void* wmat,
                     const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out, float* part_acc, float* part_ms,
-                    int num_sms, cudaStream_t stream);
+                    int num_sms, long long* dbg, cudaStream_t stream);
 
 /* ---- 8f-1 DESA on tensor cores (csrc/desa_fused.cu), model/model.py:129-204 + joint embeddings :323-325 ---------------
  * e / part_acc / part_ms: outputs of kpf_point_embed; pcl [B,N,3]; joint [B,J,3]; S scales with radii r0..r3 and
@@ -168,7 +168,7 @@ int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, co
  * outputs) and jf_out [B,J,128] f32 (embedded joint features); the 512->128 fusion conv consumes [desa_part | jf]. */
 int kpf_desa_fused(const void* e, const float* part_acc, const float* part_ms, const float* pcl, const float* joint, const void* wmat,
                    const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2, float r3, float* desa_part,
-                   float* jf_out, cudaStream_t stream);
+                   float* jf_out, long long* dbg, cudaStream_t stream);
 
 /* ---- a12 on tensor cores (csrc/spatial_agg_tc.cu): same contract as kpf_spatial_aggregate for bf16 feat_rgb [B,128,fs,fs]
  * with fs*fs % 128 == 0; wa_packed from ops.pack_spatial_wa (atten_spatial.weight in canonical bf16 operand layout). */
@@ -176,12 +176,15 @@ int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joints, const fl
                              const float* center, const float* M, const float* cube, const float* cam, const void* wa_packed,
                              const float* ba, const float* weight_dis, const float* fc_w, const float* fc_b, const float* prev, int B, int C,
                              int J, int fs, float img_size, float flip, float hm_std, float hm_sigma, float gamma, float* sw_out,
-                             float* feat_j_out, cudaStream_t stream);
+                             float* feat_j_out, long long* dbg, cudaStream_t stream);
 
 /* ---- bring-up self-test of the tcgen05 primitives (csrc/umma.cuh): D[128,N] f32 = A * B^T with bf16 operands.
  * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);
  * b_mn == 0: B is [N,K] row-major, else B is given as [K,N]. */
 int kpf_umma_selftest(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn, cudaStream_t stream);
+
+/* cycle micro-benchmarks of the tcgen05 building blocks (out: 8 x int64 device; see csrc/umma_probe.cu) */
+int kpf_umma_probe(long long* out, int N, int K, int reps, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

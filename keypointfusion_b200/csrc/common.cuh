@@ -172,9 +172,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.
+// try_wait may suspend the thread for an implementation-defined time, so the bound is on the clock, not the poll count.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-        if (spin > (1u << 24)) __trap();
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz
     }
 }
 // 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP); bytes % 16 == 0, 16 B aligned.

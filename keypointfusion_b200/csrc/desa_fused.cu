@@ -25,6 +25,7 @@ struct DesaParams {
     float* jf_out;            // [B,J,128]
     int B, N, J, T, S, nsample;
     float radius[4];
+    long long* dbg;
 };
 
 constexpr int DS_MAT_PER_SCALE = 2048 + 256 + 2048;
@@ -41,7 +42,8 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     float* sJF = reinterpret_cast<float*>(sPcl + (p.N + p.J + 3) / 4 * 4);  // [J][128] fp32 joint features
     float* sOut = sJF + p.J * 128;                     // [J][128]
     float* sMS = sOut + p.J * 128;                     // [T][2][32] partial max/sum, then [T][32] scale factors + den[32]
-    uint16_t* sIdx = reinterpret_cast<uint16_t*>(sMS + p.T * 64 + 64);  // [J][nsample]
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sMS + p.T * 64 + 64);  // [N + J] ball-query hit bits (one per centre)
+    uint16_t* sIdx = reinterpret_cast<uint16_t*>(sMask + ((p.N + p.J + 3) / 4 * 4));  // [J][nsample]
     __shared__ __align__(8) uint64_t wbar[2], mma_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -51,6 +53,12 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     const float radius = p.radius[sc];
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const uint32_t ACCE = 0, ACC1 = 128, ACC2 = 256;
+    int n_stamp = 0;
+    auto stamp = [&]() {
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 64) p.dbg[n_stamp] = clock64();
+        ++n_stamp;
+    };
+    stamp();
 
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
@@ -76,6 +84,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     tc_fence_after();
     const uint32_t tmem0 = tmem_slot, tmem = tmem0 + lane_off;
     uint32_t phase = 0;
+    stamp();
     // scale factors exp(m_t - m) and the softmax denominator, per joint
     if (tid < 32) {
         float m = -INFINITY;
@@ -138,20 +147,29 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
             }
         }
     }
-    // ---- ball query: warp w handles joints w, w+4, ...   (pointnet2_ops: first NS hits in index order, pad with the first)
+    stamp();
+    // ---- ball query (pointnet2_ops: first NS hits in index order, pad with the first hit).
+    // Phase 1: one thread per point tests all J centres (exact fp32 op order) -> hit bit mask per point.
+    // Phase 2: one warp per centre compacts the set bits in index order with ballots (no arithmetic in the serial loop).
     {
         const float r2 = xmul(radius, radius);
+        for (int n = tid; n < N + J; n += 128) {
+            const float4 q = sPcl[n];
+            uint32_t m = 0;
+#pragma unroll 7
+            for (int j = 0; j < J; ++j) {
+                const float4 c = sPcl[N + j];
+                const float dx = xsub(c.x, q.x), dy = xsub(c.y, q.y), dz = xsub(c.z, q.z);
+                m |= (xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz)) < r2 ? 1u : 0u) << j;
+            }
+            sMask[n] = m;
+        }
+        __syncthreads();
         for (int j = warp; j < J; j += 4) {
-            const float4 c = sPcl[N + j];
             int cnt = 0, first = 0;
             for (int base = 0; base < N + J && cnt < NS; base += 32) {
                 const int n = base + lane;
-                bool hit = false;
-                if (n < N + J) {
-                    const float4 q = sPcl[n];
-                    const float dx = xsub(c.x, q.x), dy = xsub(c.y, q.y), dz = xsub(c.z, q.z);
-                    hit = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz)) < r2;
-                }
+                const bool hit = n < N + J && ((sMask[n] >> j) & 1u);
                 const uint32_t bal = __ballot_sync(0xffffffffu, hit);
                 if (bal) {
                     if (cnt == 0) first = base + __ffs(bal) - 1;
@@ -161,7 +179,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
                 }
             }
             if (cnt > NS) cnt = NS;
-            for (int s = cnt + lane; s < NS; s += 32) sIdx[j * NS + s] = (uint16_t)first;
+            for (int s2 = cnt + lane; s2 < NS; s2 += 32) sIdx[j * NS + s2] = (uint16_t)first;
         }
     }
     const float b1 = p.wvec[128 + 512 + sc * 256 + tid], b2 = p.wvec[128 + 512 + sc * 256 + 128 + tid];
@@ -170,6 +188,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     if (tid == 0) mbar_wait(&wbar[1], 0);
 
     const int JPT = 128 / NS;  // joints per tile (2 for nsample = 64)
+    stamp();
     for (int j0 = 0; j0 < J; j0 += JPT) {
         // ---- gather: row r = tid -> (joint j0 + r/NS, slot r%NS)
         {
@@ -179,9 +198,12 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
             const float* cf = sJF + (ok ? jj : 0) * 128;
             if (ii < N) {
                 const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + ii) * 128);
-#pragma unroll 4
+                uint4 vv[16];
+#pragma unroll
+                for (int kc = 0; kc < 16; ++kc) vv[kc] = __ldg(src + kc);   // the whole 256-byte row in flight
+#pragma unroll
                 for (int kc = 0; kc < 16; ++kc) {
-                    const uint4 v = __ldg(src + kc);
+                    const uint4 v = vv[kc];
                     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
                     float f[8];
 #pragma unroll
@@ -212,6 +234,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
             sXt[tid] = pack8_bf16(t8);
             sXt[128 + tid] = make_uint4(0, 0, 0, 0);
         }
+        if (j0 == 0) stamp();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -225,6 +248,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (j0 == 0) stamp();
         // ---- layer-1 epilogue: h[c][r] = relu(D1 + b1) -> MN-major B operand [K = channel][N = row]
         for (int c0 = 0; c0 < 128; c0 += 32) {
             float a[32];
@@ -245,6 +269,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (j0 == 0) stamp();
         // ---- layer-2 epilogue: max over the NS grouped points of each joint  (model.py:197-198)
         for (int g = 0; g < JPT; ++g) {
             float mx = 0.f;  // relu output >= 0
@@ -257,7 +282,9 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
             if (j0 + g < J) sOut[(j0 + g) * 128 + tid] = mx;
         }
         tc_fence_before();
+        if (j0 == 0) stamp();
     }
+    stamp();
     __syncthreads();
     for (int i = tid; i < J * 128; i += 128) p.desa_part[(((size_t)b * p.S + sc) * J) * 128 + i] = sOut[i];
     __syncthreads();
@@ -268,7 +295,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
 
 extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
                               const void* wmat, const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2,
-                              float r3, float* desa_part, float* jf_out, cudaStream_t stream) {
+                              float r3, float* desa_part, float* jf_out, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && N + J <= 65535 && J >= 1 && J <= 32 && S >= 1 && S <= 4);
     KPF_REQUIRE(nsample == 32 || nsample == 64 || nsample == 128);
@@ -277,9 +304,10 @@ extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float*
     DesaParams p;
     p.e = (const __nv_bfloat16*)e; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;
     p.wvec = wvec; p.desa_part = desa_part; p.jf_out = jf_out; p.B = B; p.N = N; p.J = J; p.T = N / 128; p.S = S; p.nsample = nsample;
+    p.dbg = dbg;
     p.radius[0] = r0; p.radius[1] = r1; p.radius[2] = r2; p.radius[3] = r3;
     const size_t smem = (size_t)(2048 + 256 + 2048 + 2048 + 256 + 2048) * 16 + (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * 128 * 4 * 2 +
-                        (size_t)(p.T * 64 + 64) * 4 + (size_t)J * nsample * 2 + 64;
+                        (size_t)(p.T * 64 + 64) * 4 + (size_t)((N + J + 3) / 4 * 4) * 4 + (size_t)J * nsample * 2 + 64;
     KPF_REQUIRE(smem <= 227 * 1024);
     cudaError_t err = cudaFuncSetAttribute(desa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;

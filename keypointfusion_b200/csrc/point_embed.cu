@@ -57,6 +57,7 @@ struct PointParams {
     float* part_ms;          // [B,T,2,32]  (max, sum)
     int B, N, J, HW;
     float kernel_size;
+    long long* dbg;
 };
 
 __device__ __forceinline__ void bf16x8_fma(float* acc, const uint4& v, float w) {
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
     float* sJ = reinterpret_cast<float*>(sA2 + 2048); // [32][4] joints of the current sample
     float* sRed = sJ + 128;                           // [4][32] cross-warp reductions
     float* sB = sRed + 128;                           // b1[128], b2[128]
+    float* sT = sB + 256;                             // [21][129] transposed softmax scratch
     __shared__ __align__(8) uint64_t wbar, mma_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -99,6 +101,13 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
     const uint32_t ACC1 = 0, ACC2 = 128, ACC3 = 256;
     uint32_t phase = 0;
     bool w_ready = false;
+    const float inv_ks = 1.f / p.kernel_size;
+    int n_stamp = 0;
+    auto stamp = [&]() {
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 64) p.dbg[n_stamp] = clock64();
+        ++n_stamp;
+    };
+    stamp();
 
     for (int tile = blockIdx.x; tile < p.B * T; tile += gridDim.x) {
         const int b = tile / T, t = tile - b * T, n = t * 128 + tid;
@@ -116,20 +125,21 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
         const uint4* r1 = p.featT + ((size_t)b * p.HW + id.y) * PE_CH;
         const uint4* r2 = p.featT + ((size_t)b * p.HW + id.z) * PE_CH;
         const uint4* r3 = p.featT + ((size_t)b * p.HW + id.w) * PE_CH;
+        stamp();
         // ---- K3: 4-tap gathers, 8 channels (one 16-byte chunk) at a time, 4 chunks in flight
         float wraw[32];
 #pragma unroll
-        for (int c = 0; c < PE_CH; c += 4) {
-            uint4 v[4][4];
+        for (int c = 0; c < PE_CH; c += 6) {
+            uint4 v[6][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 6; ++u) {
                 v[u][0] = __ldg(r0 + c + u);
                 v[u][1] = __ldg(r1 + c + u);
                 v[u][2] = __ldg(r2 + c + u);
                 v[u][3] = __ldg(r3 + c + u);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 6; ++u) {
                 float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 bf16x8_fma(acc, v[u][0], cw.x);
                 bf16x8_fma(acc, v[u][1], cw.y);
@@ -145,6 +155,7 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
                 }
             }
         }
+        stamp();
         __syncthreads();  // sJ visible
         // ---- K4b: unit offsets (joint-major xyz), closeness, then xyz; 96 values -> chunks 20..31 of A1
         {
@@ -155,9 +166,10 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
             for (int j = 0; j < 21; ++j) {
                 if (j < J) {
                     const float ox = sJ[4 * j] - px, oy = sJ[4 * j + 1] - py, oz = sJ[4 * j + 2] - pz;
-                    const float dis = sqrtf(ox * ox + oy * oy + oz * oz);
-                    const float inv = 1.f / (dis + 1e-8f);
-                    const float heat = (p.kernel_size - dis) / p.kernel_size;
+                    const float d2 = ox * ox + oy * oy + oz * oz;
+                    const float dis = d2 * rsqrtf(fmaxf(d2, 1e-30f));       // bf16 operand: approximate sqrt / divide are ample
+                    const float inv = __fdividef(1.f, dis + 1e-8f);
+                    const float heat = (p.kernel_size - dis) * inv_ks;
                     const float msk = (heat >= 0.f && pz < 0.99f) ? 1.f : 0.f;
                     buf[3 * j] = ox * inv * msk;
                     buf[3 * j + 1] = oy * inv * msk;
@@ -171,6 +183,7 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
 #pragma unroll
             for (int c = 0; c < 12; ++c) sA1[(20 + c) * 128 + tid] = pack8_bf16(buf + 8 * c);
         }
+        stamp();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -185,32 +198,49 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
         }
         w_ready = true;
         // ---- softmax numerators over this tile's points while the MMAs run: per joint max / exp / sum across 128 threads
+        // transposed through shared memory: 4 threads per joint row reduce 128 points (instead of 2 x 32 x 5 warp shuffles)
         float pj[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float m = warp_max(j < J ? wraw[j] : -INFINITY);
-            if (lane == 0) sRed[warp * 32 + j] = m;
+        for (int j = 0; j < 21; ++j)
+            if (j < J) sT[j * 129 + tid] = wraw[j];
+        __syncthreads();
+        const int rj = tid >> 2, rs = tid & 3;   // joint row, quarter
+        {
+            float m = -INFINITY;
+            if (rj < J) {
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) m = fmaxf(m, sT[rj * 129 + rs + 4 * i]);
+            }
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            if (rs == 0 && rj < J) sRed[rj] = m;
         }
         __syncthreads();
-        float mt[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            mt[j] = fmaxf(fmaxf(sRed[j], sRed[32 + j]), fmaxf(sRed[64 + j], sRed[96 + j]));
-            pj[j] = j < J ? __bfloat162float(__float2bfloat16_rn(__expf(wraw[j] - mt[j]))) : 0.f;
-        }
         float* ms = p.part_ms + ((size_t)b * T + t) * 64;
-        if (tid < 32) ms[tid] = fmaxf(fmaxf(sRed[tid], sRed[32 + tid]), fmaxf(sRed[64 + tid], sRed[96 + tid]));
-        __syncthreads();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const float s = warp_sum(pj[j]);
-            if (lane == 0) sRed[warp * 32 + j] = s;
+            pj[j] = (j < J && j < 21) ? __bfloat162float(__float2bfloat16_rn(__expf(wraw[j < 21 ? j : 0] - sRed[j < 21 ? j : 0]))) : 0.f;
         }
+        if (tid < 32) ms[tid] = tid < J ? sRed[tid] : -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 21; ++j)
+            if (j < J) sT[j * 129 + tid] = pj[j];
         __syncthreads();
-        if (tid < 32) ms[32 + tid] = sRed[tid] + sRed[32 + tid] + sRed[64 + tid] + sRed[96 + tid];
+        {
+            float sm_ = 0.f;
+            if (rj < J) {
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) sm_ += sT[rj * 129 + rs + 4 * i];
+            }
+            sm_ += __shfl_xor_sync(0xffffffffu, sm_, 1);
+            sm_ += __shfl_xor_sync(0xffffffffu, sm_, 2);
+            if (rs == 0 && rj < 32) ms[32 + rj] = rj < J ? sm_ : 0.f;
+        }
+        stamp();
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
+        stamp();
         // ---- epilogue: e = relu(relu(acc1 + b1) + acc2 + b2) -> global (bf16) and MN-major A operand (sA2 region)
         __nv_bfloat16* eo = p.e_out + pn * 128;
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -226,6 +256,7 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
                 sA2[(tid >> 3) * 128 + (c0 / 8 + c) * 8 + (tid & 7)] = v;  // e^T: M = channel contiguous
             }
         }
+        stamp();
         // p as MN-major B operand [K = 128 points][N = 32 joints] over the (dead) head of sA1
 #pragma unroll
         for (int c = 0; c < 4; ++c) sA1[(tid >> 3) * 32 + c * 8 + (tid & 7)] = pack8_bf16(pj + 8 * c);
@@ -248,12 +279,13 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
             for (int i = 0; i < 8; ++i) o[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
         }
         tc_fence_before();
+        stamp();
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem0, 512);
 }
 
-constexpr size_t PE_SMEM = (size_t)(3 * 2048 + 4096 + 2048) * 16 + (128 + 128 + 256) * 4;
+constexpr size_t PE_SMEM = (size_t)(3 * 2048 + 4096 + 2048) * 16 + (128 + 128 + 256 + 21 * 129 + 3) * 4;
 
 }  // namespace kpf
 
@@ -277,7 +309,7 @@ extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const voi
 
 extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
                                const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out,
-                               float* part_acc, float* part_ms, int num_sms, cudaStream_t stream) {
+                               float* part_acc, float* part_ms, int num_sms, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && J >= 1 && J <= 21 && HW >= 1 && num_sms >= 1);
     KPF_REQUIRE(((uintptr_t)featT % 16) == 0 && ((uintptr_t)wmat % 16) == 0 && ((uintptr_t)idx % 16) == 0 && ((uintptr_t)clos % 16) == 0);
@@ -286,6 +318,7 @@ extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const floa
     p.featT = (const uint4*)featT; p.idx = idx; p.clos = clos; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat; p.wvec = wvec;
     p.e_out = (__nv_bfloat16*)e_out; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
     p.kernel_size = kernel_size;
+    p.dbg = dbg;
     cudaError_t e = cudaFuncSetAttribute(point_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PE_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int tiles = B * (N / 128);

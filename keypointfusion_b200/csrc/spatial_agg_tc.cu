@@ -25,10 +25,21 @@ struct SpatialParams {
     float *sw_out, *feat_j_out;
     int B, J, fs;
     float img_size, flip, hm_std, hm_sigma, gamma;
+    long long* dbg;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+// uvd -> xyz with approximate division: this kernel only feeds bf16 tensor-core operands (GAM), unlike K2 it produces no indices
+__device__ __forceinline__ float3 uvd2xyz_fast(const CamF& c, float un, float vn, float dn) {
+    const float u = (un + 1.0f) * c.hs, v = (vn + 1.0f) * c.hs, d = dn * c.hz + c.cz;
+    const float xw = c.mi[0] * u + c.mi[1] * v + c.mi[2], yw = c.mi[3] * u + c.mi[4] * v + c.mi[5];
+    float3 o;
+    o.x = __fdividef(__fdividef((xw - c.fu) * d, c.fx) - c.cx, c.hx);
+    o.y = __fdividef(__fdividef(c.flip * (yw - c.fv) * d, c.fy) - c.cy, c.hy);
+    o.z = dn;
+    return o;
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -40,6 +51,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
     uint4* sG = sHm + 512;                           // [16][4][8] G, MN-major B operand [K = 128 cells][N = 32]
     uint4* sWa = sG + 512;                           // [16][32] + [4][32]
     float* sJ = reinterpret_cast<float*>(sWa + 640); // [32][8]: hm centre (x,y), xyz
+    float* sBa = sJ + 256;                           // [32] atten_spatial bias
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ CamF cam;
@@ -47,6 +59,12 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
     const int b = blockIdx.x, J = p.J, fs = p.fs, HW = fs * fs, T = HW / 128;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const uint32_t ACC1 = 0, ACC2 = 32;
+    int n_stamp = 0;
+    auto stamp = [&]() {
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 64) p.dbg[n_stamp] = clock64();
+        ++n_stamp;
+    };
+    stamp();
 
     if (warp == 0) tmem_alloc(&tmem_slot, 64);
     if (tid == 0) {
@@ -55,6 +73,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         load_cam(cam, b, p.center, p.M, p.cube, p.cam, p.img_size, p.flip);
     }
     for (int i = tid; i < 640; i += 128) sWa[i] = p.wa[i];
+    if (tid < 32) sBa[tid] = tid < J ? p.ba[tid] : 0.f;
     const __nv_bfloat16* fb = p.feat + (size_t)b * 128 * HW;
     // tile loader: thread -> (c%8 = tid%8, hw8 = tid/8); 16 passes over c/8
     auto load_tile = [&](int t, uint4* dst) {
@@ -80,18 +99,20 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
     uint32_t phase = 0;
     const float sg = 1.f / (1.f + __expf(-p.weight_dis[0]));
     const float inv2s2 = 1.f / (2.f * p.hm_sigma * p.hm_sigma * p.hm_std * p.hm_std);
-    const float ffs = (float)fs;
+    const float inv_fs = 1.f / (float)fs;
     __syncthreads();
 
+    stamp();
     for (int t = 0; t < T; ++t) {
         uint4* cur = sF + (t & 1) * 2048;
         cp_async_wait_all();   // this thread's part of tile t has landed ...
         __syncthreads();       // ... and everybody's; the other buffer's readers (tile t-1) are done
         if (t + 1 < T) load_tile(t + 1, sF + ((t + 1) & 1) * 2048);  // overlaps the whole iteration
+        if (t == 1) stamp();
         // ---- per-cell geometry (thread = cell): heat-map row (A operand) and GAM (registers)
         const int m = t * 128 + tid, r = m / fs, col = m - r * fs;
         const float d = __ldg(p.depth + (size_t)b * p.depth_bs + (size_t)r * p.depth_rs + (size_t)col * p.depth_cs);
-        const float3 q = uvd2xyz(cam, cell_coord(col, ffs), cell_coord(r, ffs), d);
+        const float3 q = uvd2xyz_fast(cam, (2.f * col + 1.f) * inv_fs - 1.f, (2.f * r + 1.f) * inv_fs - 1.f, d);
         float gam[32], hm[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -99,7 +120,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
                 const float dx = (float)col + 0.5f - sJ[8 * j], dy = (float)r + 0.5f - sJ[8 * j + 1];
                 hm[j] = __expf(-(dx * dx + dy * dy) * inv2s2);
                 const float ex = q.x - sJ[8 * j + 2], ey = q.y - sJ[8 * j + 3], ez = q.z - sJ[8 * j + 4];
-                gam[j] = 1.f / (p.gamma * (ex * ex + ey * ey + ez * ez) + 1.f);
+                gam[j] = __fdividef(1.f, p.gamma * (ex * ex + ey * ey + ez * ez) + 1.f);
             } else {
                 hm[j] = 0.f;
                 gam[j] = 0.f;
@@ -107,6 +128,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) sHm[c * 128 + tid] = pack8_bf16(hm + 8 * c);
+        if (t == 1) stamp();
         // relu copy for GEMM B (same layout)
         for (int i = tid; i < 2048; i += 128) {
             uint4 v = cur[i];
@@ -116,6 +138,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
             for (int k = 0; k < 4; ++k) h[k] = __hmax2(h[k], z);
             sFr[i] = v;
         }
+        if (t == 1) stamp();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -129,6 +152,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (t == 1) stamp();
         {
             float s1[32];
             tmem_ld32(tmem + ACC1, s1);
@@ -136,7 +160,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (j < J) {
-                    const float swv = 1.f / (1.f + __expf(-(s1[j] + __ldg(p.ba + j))));
+                    const float swv = __fdividef(1.f, 1.f + __expf(-(s1[j] + sBa[j])));
                     p.sw_out[((size_t)b * J + j) * HW + m] = swv;
                     s1[j] = fw * (sg * gam[j] + (1.f - sg) * swv);  // model.py:337-338 and fc_spatial2joint_feature's weight
                 } else {
@@ -146,6 +170,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
 #pragma unroll
             for (int c = 0; c < 4; ++c) sG[(tid >> 3) * 32 + c * 8 + (tid & 7)] = pack8_bf16(s1 + 8 * c);
         }
+        if (t == 1) stamp();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -158,7 +183,9 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         mbar_wait(&mma_bar, phase);  // sFr / sG / sHm are rewritten by the next tile
         phase ^= 1;
         tc_fence_after();
+        if (t == 1) stamp();
     }
+    stamp();
     {
         float o[32];
         tmem_ld32(tmem + ACC2, o);  // thread = channel c
@@ -184,7 +211,7 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joint
                                         int depth_cs, const float* center, const float* M, const float* cube, const float* cam,
                                         const void* wa_packed, const float* ba, const float* weight_dis, const float* fc_w,
                                         const float* fc_b, const float* prev, int B, int C, int J, int fs, float img_size, float flip,
-                                        float hm_std, float hm_sigma, float gamma, float* sw_out, float* feat_j_out, cudaStream_t stream) {
+                                        float hm_std, float hm_sigma, float gamma, float* sw_out, float* feat_j_out, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && C == 128 && J >= 1 && J <= 32 && fs >= 1 && (fs * fs) % 128 == 0);
     KPF_REQUIRE(((uintptr_t)feat_rgb % 16) == 0 && ((uintptr_t)wa_packed % 16) == 0);
@@ -193,8 +220,9 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joint
     p.feat = (const __nv_bfloat16*)feat_rgb; p.joints = joints; p.depth = depth; p.depth_bs = depth_bs; p.depth_rs = depth_rs;
     p.depth_cs = depth_cs; p.center = center; p.M = M; p.cube = cube; p.cam = cam; p.wa = (const uint4*)wa_packed; p.ba = ba;
     p.weight_dis = weight_dis; p.fc_w = fc_w; p.fc_b = fc_b; p.prev = prev; p.sw_out = sw_out; p.feat_j_out = feat_j_out;
+    p.dbg = dbg;
     p.B = B; p.J = J; p.fs = fs; p.img_size = img_size; p.flip = flip; p.hm_std = hm_std; p.hm_sigma = hm_sigma; p.gamma = gamma;
-    const size_t smem = (size_t)(4096 + 2048 + 512 + 512 + 640) * 16 + 32 * 8 * 4;
+    const size_t smem = (size_t)(4096 + 2048 + 512 + 512 + 640) * 16 + 32 * 8 * 4 + 32 * 4;
     cudaError_t e = cudaFuncSetAttribute(spatial_aggregate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     spatial_aggregate_tc_kernel<<<B, 128, smem, stream>>>(p);

@@ -38,6 +38,7 @@ struct TokParams {
     float* out_jc;         // cross only: element (b,t,c) at out_jc[(b*J+t)*stride + c0 + c] or null
     int out_jc_stride, out_jc_c0;
     int B, J, D, L, F, pre, cross, Fc, G;
+    long long* dbg;        // optional: clock64 stamps of CTA 0 (profiling aid)
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
@@ -148,7 +149,12 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
         for (int c = 0; c < 4; ++c) buf[(kc0 + c) * 128 + row] = pack8_bf16(v + 8 * c);
     };
 
-    int g = 0;
+    int g = 0, n_stamp = 0;
+    auto stamp = [&]() {
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 64) p.dbg[n_stamp] = clock64();
+        ++n_stamp;
+    };
+    stamp();
     const float* vec = p.wvec;
     float head_x[3] = {0.f, 0.f, 0.f};  // this thread's share of residual(x) of the regression head (fp32)
     const float qscale = rsqrtf((float)(C / 4));  // head_dim^-0.5, 4 heads
@@ -184,6 +190,7 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
 #pragma unroll
             for (int c = 0; c < 4; ++c) bufV[(row >> 3) * 128 + (c0 / 8 + c) * 8 + (row & 7)] = pack8_bf16(a + 8 * c);
         }
+        stamp();
         // ---- attention.  Warpgroup `half` owns heads 2*half and 2*half+1 (= its 64 output columns).  Round pr handles head pr
         //      (group 0, S in ACC0) and head 2+pr (group 1, S in ACC1) concurrently; the P V MMAs take turns on bufA.
         float inv_sum[2];
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
                 wait_mma();  // bufA is rewritten next
             }
         }
+        stamp();
         // ---- O -> bf16 A operand: thread drains heads 2*half (+0, +1) = columns [cb, cb+64), scaling by its softmax sums
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
@@ -283,6 +291,7 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
         };
         run_gemm(g++, bufA, C, C, ACC0, false, false);
         resid_ln(ACC0, bo, g1, be1, nullptr);
+        stamp();
         // ---- FFN
         run_gemm(g++, bufA, F, C, ACC2, false, false);
         for (int c0 = cb; c0 < cb + 64 && c0 < F; c0 += 32) {
@@ -306,6 +315,7 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
         }
         run_gemm(g++, bufQ, C, F, ACC0, false, false);
         resid_ln(ACC0, b2, g2, be2, Wres_feat);
+        stamp();
     };
 
     // =========================== cross-attention layer (crossTR) ===========================
@@ -432,6 +442,7 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
             store_row_chunks(bufA, c0 / 8, a);
         }
         vec = bcls + 4;
+        stamp();
         for (int l = 0; l < p.L; ++l) {
             load_vecs(vec, 10 * C);
             vec += 10 * C;
@@ -468,6 +479,7 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
             o[2] = pr3[2] + sRed[row * 3 + 2] + bres[2] + bcls[2];
         }
     }
+    stamp();
     tc_fence_before();
     __syncthreads();
     if (tid < 32) tmem_dealloc(tmem0, 512);
@@ -480,7 +492,7 @@ constexpr size_t TS_SMEM = (size_t)(2 * TS_SLOT + 256 + 2048 + 256 + 3 * 2048) *
 extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d, const float* desa, const float* jf, const void* wmat,
                                const void* wseq, const float* wvec, int n_weights, int cross, int pre, int B, int J, int D, int L, int F,
                                int Fc, float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride, int out_jc_c0,
-                               cudaStream_t stream) {
+                               long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && J >= 1 && J <= 32 && L >= 0 && (cross || L > 0));
     KPF_REQUIRE(L == 0 || F == 16 || F == 32 || F == 64 || F == 128);
@@ -494,7 +506,7 @@ extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d,
     TokParams p;
     p.x = x; p.y = y; p.r3d = r3d; p.desa = desa; p.jf = jf; p.wmat = (const uint4*)wmat; p.wseq = (const int2*)wseq; p.wvec = wvec;
     p.tokens_out = tokens_out; p.pred_out = pred_out; p.out_cj = out_cj; p.out_jc = out_jc; p.out_jc_stride = out_jc_stride;
-    p.out_jc_c0 = out_jc_c0; p.B = B; p.J = J; p.D = D; p.L = L; p.F = F; p.pre = pre; p.cross = cross; p.Fc = Fc; p.G = n_weights;
+    p.out_jc_c0 = out_jc_c0; p.B = B; p.J = J; p.D = D; p.L = L; p.F = F; p.pre = pre; p.cross = cross; p.Fc = Fc; p.G = n_weights; p.dbg = dbg;
     cudaError_t e = cudaFuncSetAttribute(token_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM);
     if (e != cudaSuccess) return (int)e;
     token_stack_kernel<<<(B + 3) / 4, 256, TS_SMEM, stream>>>(p);

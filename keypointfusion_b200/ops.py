@@ -402,7 +402,7 @@ def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
                         torch.cat([v.reshape(-1) for v in vecs]).contiguous(), int(cross is not None), int(fusion is not None), D, L, F_, Fc, J)
 
 
-def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=True, out_jc=None, out_jc_c0=0, want_cj=False):
+def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=True, out_jc=None, out_jc_c0=0, want_cj=False, dbg=None):
     """Run one packed token program.  Returns (tokens [B,J,128] | None, pred [B,J,3] | None, out_cj [B,128,J] | None)."""
     ref = x if x is not None else desa
     dev = ref.device
@@ -418,7 +418,7 @@ def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=Tr
     out_cj = torch.empty(B, 128, J, device=dev, dtype=torch.float32) if (want_cj and pk.L == 0) else None
     stride = out_jc.shape[-1] if out_jc is not None else 0
     _call("kpf_token_stack", _p(x), _p(y), _p(r3d), _p(desa), _p(jf), _p(pk.wmat), _p(pk.wseq), _p(pk.wvec), pk.n_weights, pk.cross, pk.pre,
-          B, J, pk.D, pk.L, pk.F, pk.Fc, _p(tokens), _p(pred), _p(out_cj), _p(out_jc), stride, out_jc_c0)
+          B, J, pk.D, pk.L, pk.F, pk.Fc, _p(tokens), _p(pred), _p(out_cj), _p(out_jc), stride, out_jc_c0, _p(dbg))
     return tokens, pred, out_cj
 
 
@@ -463,7 +463,7 @@ def pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, J):
     return wmat, wvec
 
 
-def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8):
+def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg=None):
     """-> e [B,N,128] bf16, part_acc [B,T,128,32] f32, part_ms [B,T,2,32] f32  (T = N/128)."""
     _need_cuda(featT, idx32, clos, pcl, joint)
     pcl, joint, clos = _f32(pcl), _f32(joint), _f32(clos)
@@ -477,7 +477,7 @@ def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8):
     acc = torch.empty(B, T, 128, 32, device=dev, dtype=torch.float32)
     ms = torch.empty(B, T, 2, 32, device=dev, dtype=torch.float32)
     _call("kpf_point_embed", _p(featT), _p(idx32), _p(clos), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, HW, float(kernel_size), _p(e),
-          _p(acc), _p(ms), sm_count(dev))
+          _p(acc), _p(ms), sm_count(dev), _p(dbg))
     return e, acc, ms
 
 
@@ -507,7 +507,7 @@ def pack_desa(Wj, bj, Wjx, bjx, scales):
     return torch.cat(mats).contiguous(), torch.cat(vecs).contiguous()
 
 
-def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample):
+def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, dbg=None):
     pcl, joint = _f32(pcl), _f32(joint)
     B, N, _ = pcl.shape
     J = joint.shape[1]
@@ -516,7 +516,7 @@ def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample):
     part = torch.empty(B, S, J, 128, device=pcl.device, dtype=torch.float32)
     jf = torch.empty(B, J, 128, device=pcl.device, dtype=torch.float32)
     _call("kpf_desa_fused", _p(e), _p(part_acc), _p(part_ms), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, S, nsample, float(r[0]),
-          float(r[1]), float(r[2]), float(r[3]), _p(part), _p(jf))
+          float(r[1]), float(r[2]), float(r[3]), _p(part), _p(jf), _p(dbg))
     return part, jf
 
 
@@ -532,7 +532,7 @@ def pack_spatial_wa(Wa, J, C=128):
 
 
 def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed, ba, weight_dis, fc_w, fc_b, prev=None, img_size=128,
-                         flip=1.0, hm_std=0.8, hm_sigma=1.0, gamma=10.0):
+                         flip=1.0, hm_std=0.8, hm_sigma=1.0, gamma=10.0, dbg=None):
     _need_cuda(feat_rgb)
     assert feat_rgb.dtype == torch.bfloat16
     feat_rgb = feat_rgb.contiguous()
@@ -546,5 +546,5 @@ def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed,
     fj = torch.empty(B, J, C, device=feat_rgb.device, dtype=torch.float32)
     _call("kpf_spatial_aggregate_tc", _p(feat_rgb), _p(joints), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam), _p(wa_packed),
           _p(ba), _p(weight_dis), _p(fc_w), _p(fc_b), _p(prev), B, C, J, fs, float(img_size), float(flip), float(hm_std), float(hm_sigma),
-          float(gamma), _p(sw), _p(fj))
+          float(gamma), _p(sw), _p(fj), _p(dbg))
     return sw, fj
