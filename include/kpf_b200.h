@@ -171,12 +171,14 @@ int kpf_desa_fused(const void* e, const float* part_acc, const float* part_ms, c
                    float* jf_out, long long* dbg, cudaStream_t stream);
 
 /* ---- a12 on tensor cores (csrc/spatial_agg_tc.cu): same contract as kpf_spatial_aggregate for bf16 feat_rgb [B,128,fs,fs]
- * with fs*fs % 128 == 0; wa_packed from ops.pack_spatial_wa (atten_spatial.weight in canonical bf16 operand layout). */
+ * with fs*fs % 128 == 0; wa_packed from ops.pack_spatial_wa (atten_spatial.weight in canonical bf16 operand layout).
+ * split > 1: each sample's cell tiles are spread over `split` CTAs; caller workspace scratch [B,split,128,32] f32 and
+ * counters [B] i32 (ZERO on entry; the kernel leaves them zero again), reduction order fixed (deterministic). */
 int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joints, const float* depth, long long depth_bs, int depth_rs, int depth_cs,
                              const float* center, const float* M, const float* cube, const float* cam, const void* wa_packed,
                              const float* ba, const float* weight_dis, const float* fc_w, const float* fc_b, const float* prev, int B, int C,
                              int J, int fs, float img_size, float flip, float hm_std, float hm_sigma, float gamma, float* sw_out,
-                             float* feat_j_out, long long* dbg, cudaStream_t stream);
+                             float* feat_j_out, float* scratch, int* counters, int split, long long* dbg, cudaStream_t stream);
 
 /* ---- bring-up self-test of the tcgen05 primitives (csrc/umma.cuh): D[128,N] f32 = A * B^T with bf16 operands.
  * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);

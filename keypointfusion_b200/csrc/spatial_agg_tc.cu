@@ -26,6 +26,9 @@ struct SpatialParams {
     int B, J, fs;
     float img_size, flip, hm_std, hm_sigma, gamma;
     long long* dbg;
+    float* scratch;   // [B][split][128][32] partial out[c][j]
+    int* counters;    // [B], zero on entry, zero again on exit
+    int split;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -56,7 +59,9 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
     __shared__ uint32_t tmem_slot;
     __shared__ CamF cam;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int b = blockIdx.x, J = p.J, fs = p.fs, HW = fs * fs, T = HW / 128;
+    const int b = blockIdx.x / p.split, sp = blockIdx.x - b * p.split, J = p.J, fs = p.fs, HW = fs * fs, T = HW / 128;
+    const int t_begin = sp * (T / p.split), t_end = t_begin + T / p.split;
+    __shared__ int s_last;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const uint32_t ACC1 = 0, ACC2 = 32;
     int n_stamp = 0;
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         for (int cg = 0; cg < 16; ++cg)
             cp_async16(dst + cg * 128 + hw8 * 8 + c8, fb + (size_t)(cg * 8 + c8) * HW + t * 128 + hw8 * 8);
     };
-    load_tile(0, sF);
+    load_tile(t_begin, sF);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -103,12 +108,12 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
     __syncthreads();
 
     stamp();
-    for (int t = 0; t < T; ++t) {
-        uint4* cur = sF + (t & 1) * 2048;
+    for (int t = t_begin; t < t_end; ++t) {
+        uint4* cur = sF + ((t - t_begin) & 1) * 2048;
         cp_async_wait_all();   // this thread's part of tile t has landed ...
         __syncthreads();       // ... and everybody's; the other buffer's readers (tile t-1) are done
-        if (t + 1 < T) load_tile(t + 1, sF + ((t + 1) & 1) * 2048);  // overlaps the whole iteration
-        if (t == 1) stamp();
+        if (t + 1 < t_end) load_tile(t + 1, sF + ((t + 1 - t_begin) & 1) * 2048);  // overlaps the whole iteration
+        if (t == t_begin + 1) stamp();
         // ---- per-cell geometry (thread = cell): heat-map row (A operand) and GAM (registers)
         const int m = t * 128 + tid, r = m / fs, col = m - r * fs;
         const float d = __ldg(p.depth + (size_t)b * p.depth_bs + (size_t)r * p.depth_rs + (size_t)col * p.depth_cs);
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) sHm[c * 128 + tid] = pack8_bf16(hm + 8 * c);
-        if (t == 1) stamp();
+        if (t == t_begin + 1) stamp();
         // relu copy for GEMM B (same layout)
         for (int i = tid; i < 2048; i += 128) {
             uint4 v = cur[i];
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
             for (int k = 0; k < 4; ++k) h[k] = __hmax2(h[k], z);
             sFr[i] = v;
         }
-        if (t == 1) stamp();
+        if (t == t_begin + 1) stamp();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
-        if (t == 1) stamp();
+        if (t == t_begin + 1) stamp();
         {
             float s1[32];
             tmem_ld32(tmem + ACC1, s1);
@@ -170,33 +175,62 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
 #pragma unroll
             for (int c = 0; c < 4; ++c) sG[(tid >> 3) * 32 + c * 8 + (tid & 7)] = pack8_bf16(s1 + 8 * c);
         }
-        if (t == 1) stamp();
+        if (t == t_begin + 1) stamp();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
             // GEMM B: A = relu(F) tile read K-major (K = cells): LBO 128 between cell groups, SBO 2048 between channel groups
-            umma_gemm(tmem0 + ACC2, smem_u32(sFr), 128, 2048, smem_u32(sG), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, t > 0);
+            umma_gemm(tmem0 + ACC2, smem_u32(sFr), 128, 2048, smem_u32(sG), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, t > t_begin);
             umma_commit(&mma_bar);
         }
         mbar_wait(&mma_bar, phase);  // sFr / sG / sHm are rewritten by the next tile
         phase ^= 1;
         tc_fence_after();
-        if (t == 1) stamp();
+        if (t == t_begin + 1) stamp();
     }
     stamp();
     {
         float o[32];
-        tmem_ld32(tmem + ACC2, o);  // thread = channel c
-        const float fb0 = p.fc_b[0];
+        tmem_ld32(tmem + ACC2, o);  // thread = channel c: this CTA's partial out[c][0..31]
+        if (p.split > 1) {
+            // deterministic cross-CTA reduction: publish the partial, the last CTA of the sample sums them in split order
+            float4* dst = reinterpret_cast<float4*>(p.scratch + (((size_t)b * p.split + sp) * 128 + tid) * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < J) {
-                float v = o[j] + fb0;
-                const size_t idx = ((size_t)b * J + j) * 128 + tid;
-                if (p.prev) v = fmaxf((v + p.prev[idx]) * 0.5f, 0.f);  // model.py:343-344
-                p.feat_j_out[idx] = v;
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = (atomicAdd(p.counters + b, 1) == p.split - 1);
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = 0.f;
+                for (int q = 0; q < p.split; ++q) {
+                    const float4* src = reinterpret_cast<const float4*>(p.scratch + (((size_t)b * p.split + q) * 128 + tid) * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 v = __ldcg(src + i);
+                        o[4 * i] += v.x;
+                        o[4 * i + 1] += v.y;
+                        o[4 * i + 2] += v.z;
+                        o[4 * i + 3] += v.w;
+                    }
+                }
+                if (tid == 0) p.counters[b] = 0;  // ready for the next launch / graph replay
+            }
+        }
+        if (p.split == 1 || s_last) {
+            const float fb0 = p.fc_b[0];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < J) {
+                    float v = o[j] + fb0;
+                    const size_t idx = ((size_t)b * J + j) * 128 + tid;
+                    if (p.prev) v = fmaxf((v + p.prev[idx]) * 0.5f, 0.f);  // model.py:343-344
+                    p.feat_j_out[idx] = v;
+                }
             }
         }
     }
@@ -211,21 +245,23 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joint
                                         int depth_cs, const float* center, const float* M, const float* cube, const float* cam,
                                         const void* wa_packed, const float* ba, const float* weight_dis, const float* fc_w,
                                         const float* fc_b, const float* prev, int B, int C, int J, int fs, float img_size, float flip,
-                                        float hm_std, float hm_sigma, float gamma, float* sw_out, float* feat_j_out, long long* dbg, cudaStream_t stream) {
+                                        float hm_std, float hm_sigma, float gamma, float* sw_out, float* feat_j_out, float* scratch, int* counters, int split, long long* dbg,
+                                        cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && C == 128 && J >= 1 && J <= 32 && fs >= 1 && (fs * fs) % 128 == 0);
     KPF_REQUIRE(((uintptr_t)feat_rgb % 16) == 0 && ((uintptr_t)wa_packed % 16) == 0);
+    KPF_REQUIRE(split >= 1 && ((fs * fs) / 128) % split == 0 && (split == 1 || (scratch != nullptr && counters != nullptr)));
     if (B == 0) return 0;
     SpatialParams p;
     p.feat = (const __nv_bfloat16*)feat_rgb; p.joints = joints; p.depth = depth; p.depth_bs = depth_bs; p.depth_rs = depth_rs;
     p.depth_cs = depth_cs; p.center = center; p.M = M; p.cube = cube; p.cam = cam; p.wa = (const uint4*)wa_packed; p.ba = ba;
     p.weight_dis = weight_dis; p.fc_w = fc_w; p.fc_b = fc_b; p.prev = prev; p.sw_out = sw_out; p.feat_j_out = feat_j_out;
-    p.dbg = dbg;
+    p.dbg = dbg; p.scratch = scratch; p.counters = counters; p.split = split;
     p.B = B; p.J = J; p.fs = fs; p.img_size = img_size; p.flip = flip; p.hm_std = hm_std; p.hm_sigma = hm_sigma; p.gamma = gamma;
     const size_t smem = (size_t)(4096 + 2048 + 512 + 512 + 640) * 16 + 32 * 8 * 4 + 32 * 4;
     cudaError_t e = cudaFuncSetAttribute(spatial_aggregate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    spatial_aggregate_tc_kernel<<<B, 128, smem, stream>>>(p);
+    spatial_aggregate_tc_kernel<<<B * split, 128, smem, stream>>>(p);
     KPF_CHECK_LAUNCH();
     return 0;
 }

@@ -55,7 +55,35 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf-GELU with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): the exact erff costs ~2k cycles per 16-wide FFN epilogue
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.f, 1.f + 0.3275911f * z);
+    const float poly = ((((1.061405429f * t - 1.453152027f) * t + 1.421413741f) * t - 0.284496736f) * t + 0.254829592f) * t;
+    const float erf_abs = 1.f - poly * __expf(-z * z);
+    return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
+// 32 consecutive floats of a row; 128-bit loads when the row is 16-byte aligned (it is, except for D = 131 inputs)
+__device__ __forceinline__ void load_row32(const float* __restrict__ src, float* v, bool valid) {
+    if (!valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    } else if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(s4 + i);
+            v[4 * i] = t.x;
+            v[4 * i + 1] = t.y;
+            v[4 * i + 2] = t.z;
+            v[4 * i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __ldg(src + i);
+    }
+}
 
 __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) {
     extern __shared__ __align__(128) unsigned char ts_smem[];
@@ -166,29 +194,31 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
                     *b1 = sVec + 6 * C, *b2 = sVec + 7 * C, *g2 = sVec + 8 * C, *be2 = sVec + 9 * C;
         // ---- Q, K, V projections (three weight tiles); each thread drains its 64 columns
         run_gemm(g++, bufA, C, C, ACC0, false, false);
-        for (int c0 = cb; c0 < cb + 64; c0 += 32) {
-            float a[32];
-            tmem_ld32(tmem + ACC0 + c0, a);
+        {
+            float a[64];
+            tmem_ld64(tmem + ACC0 + cb, a);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = (a[i] + bq[c0 + i]) * qscale;
-            store_row_chunks(bufQ, c0 / 8, a);
+            for (int i = 0; i < 64; ++i) a[i] = (a[i] + bq[cb + i]) * qscale;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bufQ[(cb / 8 + c) * 128 + row] = pack8_bf16(a + 8 * c);
         }
         run_gemm(g++, kv_src, C, C, ACC1, false, false);
-        for (int c0 = cb; c0 < cb + 64; c0 += 32) {
-            float a[32];
-            tmem_ld32(tmem + ACC1 + c0, a);
+        {
+            float a[64];
+            tmem_ld64(tmem + ACC1 + cb, a);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] += bk[c0 + i];
-            store_row_chunks(bufK, c0 / 8, a);
+            for (int i = 0; i < 64; ++i) a[i] += bk[cb + i];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bufK[(cb / 8 + c) * 128 + row] = pack8_bf16(a + 8 * c);
         }
         run_gemm(g++, kv_src, C, C, ACC2, false, false);
-        for (int c0 = cb; c0 < cb + 64; c0 += 32) {  // V: MN-major B operand for P V ([token][dim], dim contiguous)
-            float a[32];
-            tmem_ld32(tmem + ACC2 + c0, a);
+        {   // V: MN-major B operand for P V ([token][dim], dim contiguous)
+            float a[64];
+            tmem_ld64(tmem + ACC2 + cb, a);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] += bv[c0 + i];
+            for (int i = 0; i < 64; ++i) a[i] += bv[cb + i];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) bufV[(row >> 3) * 128 + (c0 / 8 + c) * 8 + (row & 7)] = pack8_bf16(a + 8 * c);
+            for (int c = 0; c < 8; ++c) bufV[(row >> 3) * 128 + (cb / 8 + c) * 8 + (row & 7)] = pack8_bf16(a + 8 * c);
         }
         stamp();
         // ---- attention.  Warpgroup `half` owns heads 2*half and 2*half+1 (= its 64 output columns).  Round pr handles head pr
@@ -222,9 +252,12 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
             inv_sum[pr] = valid ? 1.f / sum : 0.f;  // P stays un-normalised; O_h is scaled when it is read out
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                if (half == hh) {  // this warpgroup's P -> bufA, zeros outside the row's 32-column block
+                if (half == hh) {  // this warpgroup's P -> bufA; zeros outside the row's 32-column block are laid down once per
+                                   // layer (first head): later heads overwrite the same 4 chunks and nothing else
+                    if (pr == 0 && hh == 0) {
 #pragma unroll
-                    for (int kc = 0; kc < 16; ++kc) bufA[kc * 128 + row] = make_uint4(0, 0, 0, 0);
+                        for (int kc = 0; kc < 16; ++kc) bufA[kc * 128 + row] = make_uint4(0, 0, 0, 0);
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) bufA[(4 * wq + c) * 128 + row] = pack8_bf16(pv + 8 * c);
                 }
@@ -241,28 +274,31 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
         }
         stamp();
         // ---- O -> bf16 A operand: thread drains heads 2*half (+0, +1) = columns [cb, cb+64), scaling by its softmax sums
+        {
+            float a[64];
+            tmem_ld64(tmem + ACC2 + cb, a);
 #pragma unroll
-        for (int pr = 0; pr < 2; ++pr) {
-            float a[32];
-            tmem_ld32(tmem + ACC2 + cb + 32 * pr, a);
+            for (int i = 0; i < 32; ++i) {
+                a[i] *= inv_sum[0];
+                a[32 + i] *= inv_sum[1];
+            }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] *= inv_sum[pr];
-            store_row_chunks(bufA, (cb + 32 * pr) / 8, a);
+            for (int c = 0; c < 8; ++c) bufA[(cb / 8 + c) * 128 + row] = pack8_bf16(a + 8 * c);
         }
         // ---- residual + LayerNorm on a 128-wide accumulator; the two threads of a row exchange partial statistics
         auto resid_ln = [&](uint32_t acc, const float* bias, const float* gam, const float* bet, const float* Wrf) {
+            float y[64];
             float sum = 0.f, sq = 0.f;
-            for (int c0 = cb; c0 < cb + 64; c0 += 32) {
-                float a[32], r[32];
-                tmem_ld32(tmem + acc + c0, a);
-                tmem_ld32(tmem + RESID + c0, r);
+            {
+                float r[64];
+                tmem_ld64(tmem + acc + cb, y);
+                tmem_ld64(tmem + RESID + cb, r);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    a[i] += bias[c0 + i] + r[i];
-                    sum += a[i];
-                    sq += a[i] * a[i];
+                for (int i = 0; i < 64; ++i) {
+                    y[i] += bias[cb + i] + r[i];
+                    sum += y[i];
+                    sq += y[i] * y[i];
                 }
-                tmem_st32(tmem + RESID + c0, a);
             }
             sRed[(half * 128 + row) * 2] = sum;
             sRed[(half * 128 + row) * 2 + 1] = sq;
@@ -272,20 +308,18 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
             __syncthreads();
             const float mean = sum * (1.f / C);
             const float rstd = rsqrtf(fmaxf(sq * (1.f / C) - mean * mean, 0.f) + eps);
-            for (int c0 = cb; c0 < cb + 64; c0 += 32) {
-                float a[32];
-                tmem_ld32(tmem + RESID + c0, a);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) a[i] = valid ? (a[i] - mean) * rstd * gam[c0 + i] + bet[c0 + i] : 0.f;
-                tmem_st32(tmem + RESID + c0, a);
-                store_row_chunks(bufA, c0 / 8, a);
-                if (Wrf) {
+            for (int i = 0; i < 64; ++i) y[i] = valid ? (y[i] - mean) * rstd * gam[cb + i] + bet[cb + i] : 0.f;
+            tmem_st32(tmem + RESID + cb, y);
+            tmem_st32(tmem + RESID + cb + 32, y + 32);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        head_x[0] += a[i] * __ldg(Wrf + c0 + i);
-                        head_x[1] += a[i] * __ldg(Wrf + p.D + c0 + i);
-                        head_x[2] += a[i] * __ldg(Wrf + 2 * p.D + c0 + i);
-                    }
+            for (int c = 0; c < 8; ++c) bufA[(cb / 8 + c) * 128 + row] = pack8_bf16(y + 8 * c);
+            if (Wrf) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    head_x[0] += y[i] * __ldg(Wrf + cb + i);
+                    head_x[1] += y[i] * __ldg(Wrf + p.D + cb + i);
+                    head_x[2] += y[i] * __ldg(Wrf + 2 * p.D + cb + i);
                 }
             }
         };
@@ -325,16 +359,17 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
         const float* ar = p.x + ((size_t)b * J + tok) * C;
         const float* yr = p.y + ((size_t)b * J + tok) * C;
         for (int c0 = cb; c0 < cb + 64; c0 += 32) {
-            float a[32], q[32];
+            float a[32], q[32], e[32];
+            load_row32(ar + c0, a, valid);
+            load_row32(qpos + tok * C + c0, e, valid);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                a[i] = valid ? __ldg(ar + c0 + i) : 0.f;
-                q[i] = valid ? a[i] + __ldg(qpos + tok * C + c0 + i) : 0.f;
-            }
+            for (int i = 0; i < 32; ++i) q[i] = a[i] + e[i];
             tmem_st32(tmem + RESID + c0, a);           // residual = anchor (transfusion_head.py:164)
             store_row_chunks(bufA, c0 / 8, q);
+            load_row32(yr + c0, q, valid);
+            load_row32(kpos + tok * C + c0, e, valid);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) q[i] = valid ? __ldg(yr + c0 + i) + __ldg(kpos + tok * C + c0 + i) : 0.f;
+            for (int i = 0; i < 32; ++i) q[i] += e[i];
             store_row_chunks(bufV, c0 / 8, q);         // bufV temporarily holds k_in as a K-major operand
         }
         vec = kpos + J * C;
@@ -371,8 +406,7 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
                 const float* src = s < 3 ? p.desa + (((size_t)b * 3 + s) * J + tok) * C : p.jf + ((size_t)b * J + tok) * C;
                 for (int c0 = cb; c0 < cb + 64; c0 += 32) {
                     float a[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) a[i] = valid ? __ldg(src + c0 + i) : 0.f;
+                    load_row32(src + c0, a, valid);
                     store_row_chunks(dst, c0 / 8, a);
                 }
             }
@@ -404,8 +438,7 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
             const float* xr = p.x + ((size_t)b * J + tok) * D;
             for (int c0 = cb; c0 < cb + 64; c0 += 32) {
                 float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = valid ? __ldg(xr + shift + c0 + i) : 0.f;
+                load_row32(xr + shift + c0, v, valid);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     head_x[0] += v[i] * __ldg(Wres + shift + c0 + i);
@@ -434,10 +467,11 @@ __global__ void __launch_bounds__(256, 1) token_stack_kernel(const TokParams p) 
         // ---- embedding: h = pos_emb[tok] + x W_emb^T + b_emb      (model.py:56, :88-89)
         run_gemm(g++, bufA, C, C, ACC0, shift > 0, false);
         for (int c0 = cb; c0 < cb + 64; c0 += 32) {
-            float a[32];
+            float a[32], e[32];
             tmem_ld32(tmem + ACC0 + c0, a);
+            load_row32(pos + tok * C + c0, e, valid);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = valid ? a[i] + __ldg(bemb + c0 + i) + __ldg(pos + tok * C + c0 + i) : 0.f;
+            for (int i = 0; i < 32; ++i) a[i] = valid ? a[i] + __ldg(bemb + c0 + i) + e[i] : 0.f;
             tmem_st32(tmem + RESID + c0, a);
             store_row_chunks(bufA, c0 / 8, a);
         }

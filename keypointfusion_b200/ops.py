@@ -521,6 +521,18 @@ def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, db
 
 
 # ------------------------------------------------------------------------------------------------ a12 on tensor cores
+_counter_cache = {}
+
+
+def _zero_counters(n, device):
+    """Persistent zeroed int32 workspace per (device, size, stream): kernels that use it leave it zero again."""
+    key = (str(device), n, torch.cuda.current_stream(device).cuda_stream)
+    c = _counter_cache.get(key)
+    if c is None:
+        c = _counter_cache[key] = torch.zeros(n, device=device, dtype=torch.int32)
+    return c
+
+
 def pack_spatial_wa(Wa, J, C=128):
     """atten_spatial.weight [J, C+J(,1,1)] -> canonical bf16 B operands: Wa[:, :C] as [16][32][8], Wa[:, C:] as [4][32][8]."""
     Wa = Wa.detach().float().reshape(J, C + J)
@@ -544,7 +556,11 @@ def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed,
     prev = _f32(prev) if prev is not None else None
     sw = torch.empty(B, J, fs, fs, device=feat_rgb.device, dtype=torch.float32)
     fj = torch.empty(B, J, C, device=feat_rgb.device, dtype=torch.float32)
+    T = fs * fs // 128
+    split = 4 if T % 4 == 0 else (2 if T % 2 == 0 else 1)
+    scratch = torch.empty(B, split, 128, 32, device=feat_rgb.device, dtype=torch.float32) if split > 1 else None
+    counters = _zero_counters(B, feat_rgb.device) if split > 1 else None
     _call("kpf_spatial_aggregate_tc", _p(feat_rgb), _p(joints), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam), _p(wa_packed),
           _p(ba), _p(weight_dis), _p(fc_w), _p(fc_b), _p(prev), B, C, J, fs, float(img_size), float(flip), float(hm_std), float(hm_sigma),
-          float(gamma), _p(sw), _p(fj), _p(dbg))
+          float(gamma), _p(sw), _p(fj), _p(scratch), _p(counters), split, _p(dbg))
     return sw, fj
