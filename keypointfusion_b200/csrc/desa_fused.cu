@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
         float agg[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) agg[j] = 0.f;
+#pragma unroll 4
         for (int t = 0; t < T; ++t) {
             const float4* a = reinterpret_cast<const float4*>(p.part_acc + (((size_t)b * T + t) * 128 + tid) * 32);
 #pragma unroll
@@ -153,64 +154,102 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     // Phase 2: one warp per centre compacts the set bits in index order with ballots (no arithmetic in the serial loop).
     {
         const float r2 = xmul(radius, radius);
-        for (int n = tid; n < N + J; n += 128) {
-            const float4 q = sPcl[n];
-            uint32_t m = 0;
-#pragma unroll 7
+        // rounds of 8 points per thread held in registers; centres stream through (one LDS.128 per centre per round)
+        for (int base = 0; base < N + J; base += 128 * 8) {
+            float4 q[8];
+            uint32_t m[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int n = base + u * 128 + tid;
+                q[u] = n < N + J ? sPcl[n] : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+                m[u] = 0;
+            }
             for (int j = 0; j < J; ++j) {
                 const float4 c = sPcl[N + j];
-                const float dx = xsub(c.x, q.x), dy = xsub(c.y, q.y), dz = xsub(c.z, q.z);
-                m |= (xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz)) < r2 ? 1u : 0u) << j;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float dx = xsub(c.x, q[u].x), dy = xsub(c.y, q[u].y), dz = xsub(c.z, q[u].z);
+                    m[u] |= (xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz)) < r2 ? 1u : 0u) << j;
+                }
             }
-            sMask[n] = m;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int n = base + u * 128 + tid;
+                if (n < N + J) sMask[n] = m[u];
+            }
         }
         __syncthreads();
+        stamp();
         for (int j = warp; j < J; j += 4) {
             int cnt = 0, first = 0;
-            for (int base = 0; base < N + J && cnt < NS; base += 32) {
-                const int n = base + lane;
-                const bool hit = n < N + J && ((sMask[n] >> j) & 1u);
-                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                if (bal) {
-                    if (cnt == 0) first = base + __ffs(bal) - 1;
-                    const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
-                    if (hit && slot < NS) sIdx[j * NS + slot] = (uint16_t)n;
-                    cnt += __popc(bal);
+            // 128 points (4 ballots) per iteration: the serial dependency is one prefix count per 128 points, not per 32
+            for (int base = 0; base < N + J && cnt < NS; base += 128) {
+                bool hit[4];
+                uint32_t bal[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = base + 32 * u + lane;
+                    hit[u] = n < N + J && ((sMask[n] >> j) & 1u);
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bal[u] = __ballot_sync(0xffffffffu, hit[u]);
+                int off = cnt;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (bal[u]) {
+                        if (off == 0) first = base + 32 * u + __ffs(bal[u]) - 1;
+                        const int slot = off + __popc(bal[u] & ((1u << lane) - 1u));
+                        if (hit[u] && slot < NS) sIdx[j * NS + slot] = (uint16_t)(base + 32 * u + lane);
+                        off += __popc(bal[u]);
+                    }
+                }
+                cnt = off;
             }
             if (cnt > NS) cnt = NS;
             for (int s2 = cnt + lane; s2 < NS; s2 += 32) sIdx[j * NS + s2] = (uint16_t)first;
         }
     }
+    stamp();
     const float b1 = p.wvec[128 + 512 + sc * 256 + tid], b2 = p.wvec[128 + 512 + sc * 256 + 128 + tid];
     const float inv_r = 1.f / radius;
     __syncthreads();  // sJF, sIdx ready; the joint-embedding MMA (reader of sX, sH) has completed
+    stamp();
     if (tid == 0) mbar_wait(&wbar[1], 0);
 
     const int JPT = 128 / NS;  // joints per tile (2 for nsample = 64)
     stamp();
+    // point-feature row of this thread's grouped point for tile j0 (16 x 16 B, all in flight); rows >= N are joints (smem)
+    auto row_index = [&](int j0_) {
+        const int jj_ = j0_ + tid / NS;
+        return jj_ < J ? (int)sIdx[jj_ * NS + (tid % NS)] : 0;
+    };
+    uint4 pre[16];
+    {
+        const int i0 = row_index(0);
+        const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + (i0 < N ? i0 : 0)) * 128);
+#pragma unroll
+        for (int kc = 0; kc < 16; ++kc) pre[kc] = __ldg(src + kc);
+    }
     for (int j0 = 0; j0 < J; j0 += JPT) {
-        // ---- gather: row r = tid -> (joint j0 + r/NS, slot r%NS)
+        // ---- gather: row r = tid -> (joint j0 + r/NS, slot r%NS); the global rows were prefetched during the previous tile
         {
             const int jj = j0 + tid / NS;
             const bool ok = jj < J;
             const int ii = ok ? sIdx[jj * NS + (tid % NS)] : 0;
             const float* cf = sJF + (ok ? jj : 0) * 128;
             if (ii < N) {
-                const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + ii) * 128);
-                uint4 vv[16];
-#pragma unroll
-                for (int kc = 0; kc < 16; ++kc) vv[kc] = __ldg(src + kc);   // the whole 256-byte row in flight
 #pragma unroll
                 for (int kc = 0; kc < 16; ++kc) {
-                    const uint4 v = vv[kc];
+                    const uint4 v = pre[kc];
                     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
                     float f[8];
+                    const float4 c0 = *reinterpret_cast<const float4*>(cf + kc * 8), c1 = *reinterpret_cast<const float4*>(cf + kc * 8 + 4);
+                    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float2 t2 = __bfloat1622float2(h[i]);
-                        f[2 * i] = ok ? t2.x - cf[kc * 8 + 2 * i] : 0.f;
-                        f[2 * i + 1] = ok ? t2.y - cf[kc * 8 + 2 * i + 1] : 0.f;
+                        f[2 * i] = ok ? t2.x - cc[2 * i] : 0.f;
+                        f[2 * i + 1] = ok ? t2.y - cc[2 * i + 1] : 0.f;
                     }
                     sX[kc * 128 + tid] = pack8_bf16(f);
                 }
@@ -223,6 +262,12 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
                     for (int i = 0; i < 8; ++i) f[i] = ok ? sf[kc * 8 + i] - cf[kc * 8 + i] : 0.f;
                     sX[kc * 128 + tid] = pack8_bf16(f);
                 }
+            }
+            if (j0 + JPT < J) {  // prefetch the next tile's rows; they land while this tile's MMAs / epilogues run
+                const int i1 = row_index(j0 + JPT);
+                const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + (i1 < N ? i1 : 0)) * 128);
+#pragma unroll
+                for (int kc = 0; kc < 16; ++kc) pre[kc] = __ldg(src + kc);
             }
             const float4 q = sPcl[ii], c = sPcl[N + (ok ? jj : 0)];
             float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

@@ -85,25 +85,44 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
         bd[k] = INFINITY;
         bi[k] = 0;
     }
-    for (int m = 0; m < HW; ++m) {
-        const float4 q = cells[m];
-        const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
-        const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));  // loader.py:956
-        if (d2 < bd[K - 1]) {
-            float cd = d2;
-            int ci = m;
+    // four cells per iteration: the distance arithmetic of a group is branch-free; the (rare, after warm-up) insertions stay in
+    // ascending cell order so ties still resolve to the lower index
+    auto insert = [&](float d2, int m) {
+        float cd = d2;
+        int ci = m;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if (cd < bd[k]) {
-                    const float td = bd[k];
-                    const int ti = bi[k];
-                    bd[k] = cd;
-                    bi[k] = ci;
-                    cd = td;
-                    ci = ti;
-                }
+        for (int k = 0; k < K; ++k) {
+            if (cd < bd[k]) {
+                const float td = bd[k];
+                const int ti = bi[k];
+                bd[k] = cd;
+                bi[k] = ci;
+                cd = td;
+                ci = ti;
             }
         }
+    };
+    int m = 0;
+    for (; m + 4 <= HW; m += 4) {
+        float d2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 q = cells[m + u];
+            const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
+            d2[u] = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));  // loader.py:956
+        }
+        const float mn = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
+        if (mn < bd[K - 1]) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (d2[u] < bd[K - 1]) insert(d2[u], m + u);
+        }
+    }
+    for (; m < HW; ++m) {
+        const float4 q = cells[m];
+        const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
+        const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+        if (d2 < bd[K - 1]) insert(d2, m);
     }
     float cv[K];
     float s = 0.f;

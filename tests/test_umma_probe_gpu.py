@@ -82,5 +82,5 @@ def test_block_kernel_phase_clocks(path_params, capsys):
     torch.cuda.synchronize()
     show("point_embed (per tile: setup, gather, offsets, issue+softmax, wait, epilogue, agg-mma+store)", d1,
          ["setup", "gather", "offsets", "stage->issue", "softmax", "mma wait", "epilogue", "agg"] * 5)
-    show("desa_fused", d2, ["stage", "partials+emb", "ballquery", "pre-loop", "gather0", "L1 mma0", "L1 epi0", "L2 mma0+", "tile0 end", "rest tiles"])
+    show("desa_fused", d2, ["stage", "partials+emb", "bq phase1", "bq phase2 (warp 0)", "bias loads+sync", "weights wait", "gather0", "L1 mma0", "L1 epi0+L2 mma", "L2 epi0", "rest tiles"])
     show("spatial_aggregate_tc", d3, ["setup", "tile0", "t1 wait+prefetch", "t1 geometry", "t1 relu copy", "t1 gemmA", "t1 epiA", "t1 gemmB", "rest"])
