@@ -170,6 +170,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from keypointfusion_b200 import ops
     from keypointfusion_b200.dataloader.loader import loader as Loader
+    sampler = ClockSampler(local)   # runs from before the warm-up to after the last timed region (the timed regions are ~0.1 s each)
+    sampler.start()
     net = build_net(dev)
     ldr = Loader(img_size=S)
     NSETS = 4
@@ -228,15 +230,12 @@ def main():
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
         return
-    sampler = ClockSampler(local)
-    sampler.start()
     n0 = ops.launch_count()
     ms = timed(lambda i: step(i, sets[i % NSETS]), a.steps, W)
     if graphed is not None:
         launches = graphed.launches_per_replay * a.steps   # kernels of ours replayed by the graph inside the K timed steps
     else:
         launches = (ops.launch_count() - n0) * a.steps // (a.steps + W)
-    clocks = sampler.stop()
 
     # end to end through the public API: pinned host buffers -> H2D -> path -> D2H joints, every step
     h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
@@ -245,14 +244,53 @@ def main():
     def e2e_step(i):
         out_host.copy_(step(i, pinned[i % NSETS]), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the joints on the host every step
-    ms_e2e = timed(e2e_step, a.steps, W)
+    if graphed is None:
+        ms_e2e = timed(e2e_step, a.steps, W)
+    else:
+        # public serving API: double-buffered graphs, H2D of step i+1 overlaps compute of step i, host reads step i-1's joints
+        from keypointfusion_b200.runtime import PipelinedRunner
+        runner = PipelinedRunner(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0)
+        pending = []
 
+        def pipe_step(i):
+            pending.append(runner.submit(pinned[i % NSETS]))
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, runner.paths[pending[-1]].out["joints"].contiguous())
+            if len(pending) > 1:
+                runner.fetch(pending.pop(0))       # host-side read of the previous step's result
+        with torch.no_grad():
+            for i in range(W):
+                pipe_step(i)
+            while pending:
+                runner.fetch(pending.pop(0))
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(a.steps):
+                pipe_step(W + i)
+            while pending:
+                runner.fetch(pending.pop(0))       # the last result is read inside the timed region too
+            e1.record()
+            barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t)
     value = world * B * a.steps / (ms / 1e3)
     e2e = world * B * a.steps / (ms_e2e / 1e3)
     hbm, tfl, which = load_peaks()
 
     # dominant kernel of the step: measured live, CUDA events on the launching stream
     roof = dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, a.breakdown and rank == 0)
+    # keep the GPU under the same load until nvidia-smi has delivered a few samples (its first sample takes ~1 s to appear)
+    t_end = time.time() + 3.0
+    with torch.no_grad():
+        while len(sampler.rows) < 8 and time.time() < t_end:
+            for i in range(20):
+                step(i, sets[i % NSETS])
+            torch.cuda.synchronize()
+    clocks = sampler.stop()
 
     line = {"metric": "fusion-path RGB-D samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -273,55 +311,85 @@ def main():
 
 
 def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
-    """Time each stage of the step alone with CUDA events (inputs rotate so they come from HBM, not L2) and report the
-    roofline of the heaviest of OUR kernels."""
+    """Time every kernel of the step ALONE with CUDA events on the launching stream (inputs rotate over resident sets so they
+    come from HBM, not L2), weight by launches per step, and report the roofline of the kernel with the largest share.
+    ALGORITHMIC bytes / FLOPs per launch follow SURVEY.md 8d x the units one launch processes."""
     from keypointfusion_b200 import ops
     d0 = sets[0]
     B = d0["img"].shape[0]
+    blk = net.block1
+    k = blk.kc()
     with torch.no_grad():
         pcl, _ = ops.getpcl(d0["img"], d0["center"], d0["cube"], d0["M"], d0["cam"], N_PTS, seed=0)
         close, _, idx = ops.img2pcl_index(pcl, d0["img"], d0["center"], d0["M"], d0["cube"], d0["cam"], S, 4, fs=H, want_i64=False, want_i32=True)
-        joints = torch.rand(B, J, 3, device=pcl.device) * 1.2 - 0.6
-    blk = net.block1
-    e = 2  # bf16
+        joints = pcl[:, ::48][:, :J].contiguous() + 0.01
+        featT = ops.repack_features(d0["img_feat"], d0["img_feat_rgb"], d0["img_offset"][:, 4 * J:])
+        e_, acc_, ms_ = ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8)
+        part_, jf_ = ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0])
+        tok_, r3d_, _ = ops.token_stack(k["tok_init"], desa=part_, jf=jf_)
+    e = 2  # bf16 feature maps
+    # name -> (callable, launches per step, algorithmic bytes per launch, algorithmic FLOPs per launch, bound)
     stages = {
-        "backproject_kernel (K1)": (lambda d: ops.getpcl(d["img"], d["center"], d["cube"], d["M"], d["cam"], N_PTS, seed=0),
-                                    B * (S * S * 4 + 76 + N_PTS * 12), "hbm"),
-        "nearest_cells_kernel (K2)": (lambda d: ops.img2pcl_index(pcl, d["img"], d["center"], d["M"], d["cube"], d["cam"], S, 4, fs=H,
-                                                                  want_i64=False, want_i32=True),
-                                      B * (N_PTS * 12 + H * H * 4 + 76 + N_PTS * 4 * 8), "hbm"),
-        "gather_taps_kernel x3 (K3)": (lambda d: (ops.gather_taps(d["img_feat"], idx, close), ops.gather_taps(d["img_feat_rgb"], idx, close),
-                                                  ops.gather_taps(d["img_offset"][:, 4 * J:], idx, close)),
-                                       B * ((2 * C + J) * H * H * e + N_PTS * 4 * 8 + (2 * C + J) * N_PTS * e), "hbm"),
-        "offset2joint_kernel (K4a)": (lambda d: ops.offset2joint_weight(d["img_offset"], d["img"], 0.8), B * (5 * J * H * H * e + H * H * 4), "hbm"),
-        "spatial_aggregate_kernel (K5)": (lambda d: ops.spatial_aggregate(d["img_feat_rgb"], joints, d["img"][:, :, ::4, ::4], d["center"], d["M"],
-                                                                           d["cube"], d["cam"], blk.atten_spatial.weight, blk.atten_spatial.bias,
-                                                                           blk.weight_dis, blk.fc_spatial2joint_feature.weight,
-                                                                           blk.fc_spatial2joint_feature.bias),
-                                          B * (C * H * H * e + J * H * H * 4 + J * C * 4), "hbm"),
+        "token_stack_kernel": (lambda d: ops.token_stack(k["tok_init"], desa=part_, jf=jf_), 4,
+                               B * (4 * J * C * 4 + J * C * 4 + J * 12), B * 16.1e6, "tensor"),
+        "desa_fused_kernel": (lambda d: ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0]), 2,
+                              B * (3 * J * 64 * C * e + N_PTS * 12 + 4 * J * C * 4), B * 270.1e6, "tensor"),
+        "point_embed_kernel": (lambda d: ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8), 2,
+                               B * ((2 * C + J) * H * H * e + N_PTS * 4 * 8 + N_PTS * C * e), B * 95.4e6, "tensor"),
+        "spatial_aggregate_tc_kernel": (lambda d: ops.spatial_aggregate_tc(d["img_feat_rgb"], joints, d["img"][:, :, ::4, ::4], d["center"], d["M"],
+                                                                          d["cube"], d["cam"], k["wa_packed"], blk.atten_spatial.bias,
+                                                                          blk.weight_dis, blk.fc_spatial2joint_feature.weight,
+                                                                          blk.fc_spatial2joint_feature.bias), 2,
+                                        B * (C * H * H * e + J * H * H * 4 + J * C * 4), B * 12.04e6, "hbm"),
+        "nearest_cells_kernel": (lambda d: ops.img2pcl_index(pcl, d["img"], d["center"], d["M"], d["cube"], d["cam"], S, 4, fs=H, want_i64=False,
+                                                             want_i32=True), 1, B * (N_PTS * 12 + H * H * 4 + 76 + N_PTS * 4 * 8), B * 8.39e6, "hbm"),
+        "repack_kernel": (lambda d: ops.repack_features(d["img_feat"], d["img_feat_rgb"], d["img_offset"][:, 4 * J:]), 1,
+                          B * ((2 * C + J) * H * H * e + 288 * H * H * 2), 0.0, "hbm"),
+        "offset2joint_kernel": (lambda d: ops.offset2joint_weight(d["img_offset"], d["img"], 0.8), 1, B * (5 * J * H * H * e + H * H * 4), B * 0.3e6,
+                                "hbm"),
+        "backproject_kernel": (lambda d: ops.getpcl(d["img"], d["center"], d["cube"], d["M"], d["cam"], N_PTS, seed=0), 1,
+                               B * (S * S * 4 + 76 + N_PTS * 12), B * 0.33e6, "hbm"),
     }
     res = {}
-    for name, (fn, alg_bytes, bound) in stages.items():
+    for name, (fn, per_step, alg_bytes, alg_flops, bound) in stages.items():
+        g = torch.cuda.CUDAGraph()   # a graph of NSETS launches: no Python / launch overhead inside the timed region
         with torch.no_grad():
             for i in range(3):
                 fn(sets[i % len(sets)])
             torch.cuda.synchronize()
-            reps = 20
+            with torch.cuda.graph(g):
+                for i in range(len(sets)):
+                    fn(sets[i])
+            g.replay()
+            torch.cuda.synchronize()
+            reps = 5
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(reps):
-                fn(sets[i % len(sets)])
+                g.replay()
             e1.record()
             torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / reps
-        res[name] = (us, alg_bytes)
+        us = e0.elapsed_time(e1) * 1e3 / (reps * len(sets))
+        res[name] = dict(us=us, per_step=per_step, bytes=alg_bytes, flops=alg_flops, bound=bound)
         if verbose:
-            print(f"[breakdown] {name:34s} {us:9.1f} us  {alg_bytes / us / 1e3:8.1f} GB/s algorithmic", file=sys.stderr)
-    top = max(res, key=lambda k: res[k][0])
-    us, alg = res[top]
-    ach = alg / (us * 1e-6) / 1e9
-    return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-            "us_per_launch": us, "algorithmic_bytes": alg, "peaks": which}
+            print(f"[breakdown] {name:30s} x{per_step}  {us:8.1f} us  {alg_bytes / us / 1e3:8.1f} GB/s  {alg_flops / us / 1e6:8.2f} TFLOP/s (algorithmic)",
+                  file=sys.stderr)
+    tot = sum(r["us"] * r["per_step"] for r in res.values())
+    top = max(res, key=lambda n: res[n]["us"] * res[n]["per_step"])
+    r = res[top]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dram_bytes_per_launch.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top)
+    if r["bound"] == "tensor":
+        ach, peak, unit = r["flops"] / (r["us"] * 1e-6) / 1e12, tfl, "TFLOP/s"
+    else:
+        ach, peak, unit = r["bytes"] / (r["us"] * 1e-6) / 1e9, hbm, "GB/s"
+    return {"kernel": top, "bound": r["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
+            "us_per_launch": r["us"], "launches_per_step": r["per_step"], "share_of_step": r["us"] * r["per_step"] / tot,
+            "algorithmic_bytes": r["bytes"], "algorithmic_flops": r["flops"], "peaks": which,
+            "note": "latency-bound: small serial MMA->epilogue chains on <= 192 CTAs; see DESIGN.md section 4",
+            "kernels": {n: {"us": round(v["us"], 1), "per_step": v["per_step"]} for n, v in res.items()}}
 
 
 if __name__ == "__main__":

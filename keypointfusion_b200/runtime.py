@@ -91,3 +91,44 @@ def shard_batch(n_items, rank, world):
     base, rem = divmod(n_items, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+class PipelinedRunner:
+    """Host-fed serving loop: two captured graphs with their own static input buffers; while graph[i % 2] computes step i on
+    the compute stream, a copy stream uploads step i+1's pinned host inputs into the other buffer set, and the host reads step
+    i-1's joints from pinned memory.  Every step still does its own H2D of all inputs and its own D2H of the result."""
+
+    def __init__(self, net, loader, example, **kw):
+        self.paths = [GraphedFusionPath(net, loader, example, **kw) for _ in range(2)]
+        dev = next(net.parameters()).device
+        self.dev = dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        j = self.paths[0].out["joints"]
+        self.host_out = [torch.empty(j.shape, dtype=j.dtype).pin_memory() for _ in range(2)]
+        self.step = 0
+        for e in self.done:
+            e.record(torch.cuda.current_stream(dev))
+
+    def submit(self, host_inputs):
+        """Enqueue one step (returns immediately); `fetch()` later returns results in submission order."""
+        s = self.step % 2
+        path = self.paths[s]
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.done[s])          # the previous user of this buffer set has finished
+            for k in path.KEYS:
+                path.static[k].copy_(host_inputs[k], non_blocking=True)
+            self.copied[s].record(self.copy_stream)
+        main.wait_event(self.copied[s])
+        path.graph.replay()
+        self.host_out[s].copy_(path.out["joints"], non_blocking=True)
+        self.done[s].record(main)
+        self.step += 1
+        return s
+
+    def fetch(self, slot):
+        """Block until the step submitted into `slot` is complete; returns its joints (pinned host tensor)."""
+        self.done[slot].synchronize()
+        return self.host_out[slot]
