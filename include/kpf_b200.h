@@ -180,6 +180,19 @@ int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joints, const fl
                              int J, int fs, float img_size, float flip, float hm_std, float hm_sigma, float gamma, float* sw_out,
                              float* feat_j_out, float* scratch, int* counters, int split, long long* dbg, cudaStream_t stream);
 
+/* ---- 8f-3 crop + normalise front end for in-the-wild frames (demo_RGBD.py:253-276, :378-385, :410-569) ------------------
+ * depth_u16 [B,Hf,Wf] uint16 (mm), rgb_u8 [B,Hf,Wf,3] uint8 (BGR as cv2 reads it); bbox [B,4] f64 (x,y,w,h);
+ * center [B,3] f64 (u,v,d_mm); cube [B,3] f32 (mm); cam [B,4] f64 (fx,fy,fu,fv) -- f64 because the reference computes its
+ * integer crop bounds from Python floats.  Integer work is bit-exact vs the reference (cv2 INTER_NEAREST rule included).
+ * kpf_center_from_bbox -> center_out [B,3] f64;  kpf_crop_depth -> img_out [B,1,dsize,dsize] f32 (normalised, background 1),
+ * M_out [B,3,3] f32 (frame px -> crop px), com3d_out [B,3] f32;  kpf_crop_rgb -> out [B,3,dsize,dsize] f32 in [0,1]. */
+int kpf_center_from_bbox(const void* depth_u16, const double* bbox, int B, int Hf, int Wf, int upper, int lower, double* center_out,
+                         cudaStream_t stream);
+int kpf_crop_depth(const void* depth_u16, const double* center, const float* cube, const double* cam, int B, int Hf, int Wf, int dsize,
+                   float* img_out, float* M_out, float* com3d_out, cudaStream_t stream);
+int kpf_crop_rgb(const void* rgb_u8, const double* center, const float* cube, const double* cam, int B, int Hf, int Wf, int dsize,
+                 float* out, cudaStream_t stream);
+
 /* ---- bring-up self-test of the tcgen05 primitives (csrc/umma.cuh): D[128,N] f32 = A * B^T with bf16 operands.
  * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);
  * b_mn == 0: B is [N,K] row-major, else B is given as [K,N]. */

@@ -564,3 +564,51 @@ def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed,
           _p(ba), _p(weight_dis), _p(fc_w), _p(fc_b), _p(prev), B, C, J, fs, float(img_size), float(flip), float(hm_std), float(hm_sigma),
           float(gamma), _p(sw), _p(fj), _p(scratch), _p(counters), split, _p(dbg))
     return sw, fj
+
+
+# ------------------------------------------------------------------------------------------------ 8f-3 crop front end
+def _u16(t):
+    _need_cuda(t)
+    if t.dtype == torch.uint16:
+        return t.contiguous()
+    if t.dtype == torch.int16:
+        return t.contiguous()          # same bits
+    return t.to(torch.int32).clamp_(0, 65535).to(torch.uint16).contiguous()
+
+
+def _f64(t, device):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t, dtype=torch.float64)
+    return t.to(device=device, dtype=torch.float64).contiguous()
+
+
+def center_from_bbox(depth_u16, bbox, upper=1500, lower=171):
+    d = _u16(depth_u16)
+    B, Hf, Wf = d.shape
+    bbox = _f64(bbox, d.device).reshape(B, 4)
+    out = torch.empty(B, 3, device=d.device, dtype=torch.float64)
+    _call("kpf_center_from_bbox", _p(d), _p(bbox), B, Hf, Wf, int(upper), int(lower), _p(out))
+    return out
+
+
+def crop_depth(depth_u16, center, cube, cam, dsize=128):
+    d = _u16(depth_u16)
+    B, Hf, Wf = d.shape
+    center, cam = _f64(center, d.device).reshape(B, 3), _f64(cam, d.device).reshape(-1, 4).expand(B, 4).contiguous()
+    cube = torch.as_tensor(cube, dtype=torch.float32).to(d.device).reshape(-1, 3).expand(B, 3).contiguous()
+    img = torch.empty(B, 1, dsize, dsize, device=d.device, dtype=torch.float32)
+    M = torch.empty(B, 3, 3, device=d.device, dtype=torch.float32)
+    com3d = torch.empty(B, 3, device=d.device, dtype=torch.float32)
+    _call("kpf_crop_depth", _p(d), _p(center), _p(cube), _p(cam), B, Hf, Wf, dsize, _p(img), _p(M), _p(com3d))
+    return img, M, com3d, cube
+
+
+def crop_rgb(rgb_u8, center, cube, cam, dsize=128):
+    _need_cuda(rgb_u8)
+    r = rgb_u8.to(torch.uint8).contiguous()
+    B, Hf, Wf, _ = r.shape
+    center, cam = _f64(center, r.device).reshape(B, 3), _f64(cam, r.device).reshape(-1, 4).expand(B, 4).contiguous()
+    cube = torch.as_tensor(cube, dtype=torch.float32).to(r.device).reshape(-1, 3).expand(B, 3).contiguous()
+    out = torch.empty(B, 3, dsize, dsize, device=r.device, dtype=torch.float32)
+    _call("kpf_crop_rgb", _p(r), _p(center), _p(cube), _p(cam), B, Hf, Wf, dsize, _p(out))
+    return out

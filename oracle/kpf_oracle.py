@@ -634,3 +634,108 @@ def fusion_path(p, img, pcl, img_offset, img_feat, img_feat_rgb, center, M, cube
         sws.append(sw)
         joint_xyz = r2d                                                                  # :424
     return res, sws, extras
+
+
+# ----------------------------------------------------------------------------------------------
+# crop + normalise front end of demo_RGBD.py (in-the-wild frames, BASELINE config 5)
+#   get_center_from_bbx :253-276, comToBounds :519-529, getCrop :531-569, Crop_Image_deep_pp :410-462,
+#   Crop_Image_deep_pp_RGB :464-517, normalize_img :378-385, jointImgTo3D :387-.  numpy only (cv2's INTER_NEAREST restated).
+# ----------------------------------------------------------------------------------------------
+def center_from_bbox(depth, bbx, upper=1500, lower=171):
+    """depth [Hf,Wf] uint16, bbx (x,y,w,h) -> centre (u, v, d_mm) float64.  demo_RGBD.py:253-276."""
+    c = np.array([0.0, 0.0, 300.0])
+    x0, x1, y0, y1 = int(bbx[0]), int(bbx[0] + bbx[2]), int(bbx[1]), int(bbx[1] + bbx[3])
+    img = depth[y0:y1, x0:x1]
+    flag = np.logical_and(img <= upper, img >= lower)
+    if flag.any():
+        h, w = img.shape
+        xs = np.linspace(0, w, w)
+        ys = np.linspace(0, h, h)
+        rr, cc = np.nonzero(flag)
+        c[0] = xs[cc].mean()
+        c[1] = ys[rr].mean()
+        c[2] = img[flag].mean()
+        if c[2] <= 0:
+            c[2] = 300.0
+    else:
+        c[:] = (0, 0, 300.0)
+    c[0] += bbx[0]
+    c[1] += bbx[1]
+    return c
+
+
+def com_to_bounds(com, size, cam):
+    """demo_RGBD.py:519-529 (float64, then floor)."""
+    fx, fy, fu, fv = [float(t) for t in cam]
+    zs, ze = com[2] - size[2] / 2., com[2] + size[2] / 2.
+    xs = int(np.floor((com[0] * com[2] / fx - size[0] / 2.) / com[2] * fx + 0.5))
+    xe = int(np.floor((com[0] * com[2] / fx + size[0] / 2.) / com[2] * fx + 0.5))
+    ys = int(np.floor((com[1] * com[2] / fy - size[1] / 2.) / com[2] * fy + 0.5))
+    ye = int(np.floor((com[1] * com[2] / fy + size[1] / 2.) / com[2] * fy + 0.5))
+    return xs, xe, ys, ye, zs, ze
+
+
+def _nearest_map(dst, src):
+    """cv2.resize INTER_NEAREST source index: min(floor(x * (1 / (dst/src))), src-1) in double."""
+    ifx = 1.0 / (float(dst) / float(src))
+    return np.minimum(np.floor(np.arange(dst) * ifx).astype(np.int64), src - 1)
+
+
+def crop_geometry(com, size, cam, dsize):
+    """Bounds, resized size, paste offset and the 3x3 transform of Crop_Image_deep_pp (demo_RGBD.py:410-462)."""
+    xs, xe, ys, ye, zs, ze = com_to_bounds(com, size, cam)
+    wb, hb = xe - xs, ye - ys
+    sz = (dsize, int(hb * dsize / wb)) if wb > hb else (int(wb * dsize / hb), dsize)   # (width, height)
+    ch, cw = hb, wb                                                                    # cropped.shape after padding
+    sc = sz[1] / float(ch) if ch > cw else sz[0] / float(cw)
+    px = int(np.floor(dsize / 2. - sz[0] / 2.))
+    py = int(np.floor(dsize / 2. - sz[1] / 2.))
+    trans = np.eye(3)
+    trans[0, 2], trans[1, 2] = -xs, -ys
+    scale = np.eye(3) * sc
+    scale[2, 2] = 1
+    off = np.eye(3)
+    off[0, 2], off[1, 2] = px, py
+    return dict(xs=xs, xe=xe, ys=ys, ye=ye, zs=zs, ze=ze, sz=sz, px=px, py=py, M=off @ scale @ trans)
+
+
+def crop_depth(depth, com, size, cam, dsize=128):
+    """uint16 frame -> (normalised crop [dsize,dsize] f32, M [3,3] f64, com3D [3] f64).  process_depth demo_RGBD.py:305-316:
+    Crop_Image_deep_pp on the uint16 frame (z-threshold writes are cast to uint16, like numpy does), nearest resize,
+    centred paste into zeros, normalize_img (premax = crop max)."""
+    g = crop_geometry(com, size, cam, dsize)
+    Hf, Wf = depth.shape
+    sx = _nearest_map(g["sz"][0], g["xe"] - g["xs"]) + g["xs"]       # source columns in the full frame
+    sy = _nearest_map(g["sz"][1], g["ye"] - g["ys"]) + g["ys"]
+    inside = ((sy >= 0) & (sy < Hf))[:, None] & ((sx >= 0) & (sx < Wf))[None, :]
+    vals = np.where(inside, depth[np.clip(sy, 0, Hf - 1)][:, np.clip(sx, 0, Wf - 1)], 0).astype(depth.dtype)
+    nz = vals != 0
+    zs_cast = np.array(g["zs"]).astype(depth.dtype)                  # cropped[msk1] = zstart on a uint16 array
+    vals = np.where(nz & (vals < g["zs"]), zs_cast, vals)
+    vals = np.where(nz & (vals > g["ze"]), 0, vals).astype(depth.dtype)
+    ret = np.zeros((dsize, dsize), np.float32)
+    ret[g["py"]:g["py"] + g["sz"][1], g["px"]:g["px"] + g["sz"][0]] = vals
+    hi, lo = com[2] + size[2] / 2., com[2] - size[2] / 2.
+    premax = ret.max()
+    ret[ret == premax] = hi
+    ret[ret == 0] = hi
+    ret[ret >= hi] = hi
+    ret[ret <= lo] = lo
+    ret -= com[2]
+    ret /= (size[2] / 2.)
+    fx, fy, fu, fv = [float(t) for t in cam]
+    com3d = np.array([(com[0] - fu) * com[2] / fx, (com[1] - fv) * com[2] / fy, com[2]]).astype(np.float32)  # jointImgTo3D returns f32
+    return ret, g["M"], com3d
+
+
+def crop_rgb(rgb, com, size, cam, dsize=128):
+    """uint8 HWC (BGR as cv2 gives it) -> [3,dsize,dsize] f32 in [0,1].  Crop_Image_deep_pp_RGB :464-517 + ToTensor()/255 (:87)."""
+    g = crop_geometry(com, size, cam, dsize)
+    Hf, Wf = rgb.shape[:2]
+    sx = _nearest_map(g["sz"][0], g["xe"] - g["xs"]) + g["xs"]
+    sy = _nearest_map(g["sz"][1], g["ye"] - g["ys"]) + g["ys"]
+    inside = ((sy >= 0) & (sy < Hf))[:, None] & ((sx >= 0) & (sx < Wf))[None, :]
+    vals = np.where(inside[..., None], rgb[np.clip(sy, 0, Hf - 1)][:, np.clip(sx, 0, Wf - 1)], 0)
+    ret = np.zeros((dsize, dsize, 3), np.float32)
+    ret[g["py"]:g["py"] + g["sz"][1], g["px"]:g["px"] + g["sz"][0]] = vals
+    return (ret.transpose(2, 0, 1) / np.float32(255.)).astype(np.float32)

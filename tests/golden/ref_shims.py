@@ -16,8 +16,17 @@ import torch.nn as nn
 REF = os.environ.get("KPF_REFERENCE", "/root/reference")
 
 
+class _Permissive(types.ModuleType):
+    """Stub module: any missing attribute resolves to a do-nothing placeholder (import-time glue only)."""
+
+    def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
+        return lambda *a, **k: None
+
+
 def _stub(name, **attrs):
-    m = types.ModuleType(name)
+    m = _Permissive(name)
     m.__dict__.update(attrs)
     sys.modules[name] = m
     return m
@@ -89,7 +98,7 @@ def install():
     _stub("timm.models.registry", register_model=lambda f: f)
     for name in ["pycocotools", "pycocotools.coco", "matplotlib", "matplotlib.pyplot", "trimesh", "pytorch3d",
                  "pytorch3d.transforms", "tensorboardX", "chumpy", "mpl_toolkits", "mpl_toolkits.mplot3d",
-                 "sklearn.decomposition"]:
+                 "sklearn.decomposition", "dataloader.webuser", "dataloader.webuser.smpl_handpca_wrapper_HAND_only"]:
         if name not in sys.modules:
             try:
                 __import__(name)
@@ -97,7 +106,8 @@ def install():
                 _stub(name)
     sys.modules["pycocotools.coco"].__dict__.setdefault("COCO", object)
     mpl = sys.modules["matplotlib"]
-    if not hasattr(mpl, "cm"):
+    if isinstance(mpl, _Permissive):
+        mpl.__path__ = []            # make the stub a package so `import matplotlib.colors` resolves to the stubs below
         mpl.cm = _stub("matplotlib.cm")
         mpl.colors = _stub("matplotlib.colors")
     sys.modules["tensorboardX"].__dict__.setdefault("SummaryWriter", object)
