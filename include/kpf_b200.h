@@ -193,6 +193,11 @@ int kpf_crop_depth(const void* depth_u16, const double* center, const float* cub
 int kpf_crop_rgb(const void* rgb_u8, const double* center, const float* cube, const double* cam, int B, int Hf, int Wf, int dsize,
                  float* out, cudaStream_t stream);
 
+/* ---- 8f-4 evaluation tail (train.py:330-386, :470-488; util/generateFeature.py:681-703) -----------------------------------
+ * pred, gt [B,J,3] f32 normalised xyz, cube [B,3] -> err [B,J] f32 (mm) and, if pa_err != NULL, pa_err [B,J] f32: the error
+ * after GFM.rigid_align (similarity Procrustes, 3x3 SVD per sample in fp64 on the device). */
+int kpf_eval_errors(const float* pred, const float* gt, const float* cube, int B, int J, float* err, float* pa_err, cudaStream_t stream);
+
 /* ---- bring-up self-test of the tcgen05 primitives (csrc/umma.cuh): D[128,N] f32 = A * B^T with bf16 operands.
  * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);
  * b_mn == 0: B is [N,K] row-major, else B is given as [K,N]. */

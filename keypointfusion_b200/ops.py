@@ -612,3 +612,14 @@ def crop_rgb(rgb_u8, center, cube, cam, dsize=128):
     out = torch.empty(B, 3, dsize, dsize, device=r.device, dtype=torch.float32)
     _call("kpf_crop_rgb", _p(r), _p(center), _p(cube), _p(cam), B, Hf, Wf, dsize, _p(out))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ 8f-4 evaluation tail
+def eval_errors(pred, gt, cube, aligned=True):
+    """-> (err [B,J] mm, pa_err [B,J] mm | None): Trainer.xyz2error and the rigid_align'ed error of train.py:330-386."""
+    pred, gt, cube = _f32(pred), _f32(gt), _f32(cube)
+    B, J, _ = pred.shape
+    err = torch.empty(B, J, device=pred.device, dtype=torch.float32)
+    pa = torch.empty(B, J, device=pred.device, dtype=torch.float32) if aligned else None
+    _call("kpf_eval_errors", _p(pred), _p(gt), _p(cube), B, J, _p(err), _p(pa))
+    return err, pa

@@ -739,3 +739,31 @@ def crop_rgb(rgb, com, size, cam, dsize=128):
     ret = np.zeros((dsize, dsize, 3), np.float32)
     ret[g["py"]:g["py"] + g["sz"][1], g["px"]:g["px"] + g["sz"][0]] = vals
     return (ret.transpose(2, 0, 1) / np.float32(255.)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# SURVEY 8f-4: evaluation tail (train.py:470-488 xyz2error; util/generateFeature.py:681-703 rigid_align)
+# ----------------------------------------------------------------------------------------------
+def xyz2error(output, joint, center, cube):
+    """[B,J,3] normalised -> per-joint error in mm [B,J].  train.py:470-488."""
+    output, joint = np.asarray(output, f64), np.asarray(joint, f64)
+    c = np.asarray(center, f64)[:, None, :]
+    h = np.asarray(cube, f64)[:, None, :] / 2
+    d = (output * h + c) - (joint * h + c)
+    return np.sqrt((d * d).sum(-1))
+
+
+def rigid_align(A, B):
+    """Similarity (Umeyama) alignment of A onto B, both [J,3].  generateFeature.py:681-703."""
+    n = A.shape[0]
+    ca, cb = A.mean(0), B.mean(0)
+    H = (A - ca).T @ (B - cb) / n
+    U, s, V = np.linalg.svd(H)
+    R = V.T @ U.T
+    if np.linalg.det(R) < 0:
+        s[-1] = -s[-1]
+        V[2] = -V[2]
+        R = V.T @ U.T
+    c = 1 / np.var(A, axis=0).sum() * np.sum(s)
+    t = -(c * R) @ ca + cb
+    return (c * R @ A.T).T + t

@@ -200,3 +200,24 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def add_eval_tail_golden():
+    """GFM.rigid_align of the reference on seeded joint sets incl. a reflection (det(R) < 0 branch); appended to
+    golden_path.npz as f4_A / f4_B / f4_aligned."""
+    g = GFM()
+    rs = np.random.RandomState(11)
+    A = rs.uniform(-0.8, 0.8, (6, 21, 3)).astype(np.float32)
+    Rm = np.linalg.qr(rs.standard_normal((3, 3)))[0]
+    B2 = (1.3 * (A @ Rm.T) + 0.1 + 0.02 * rs.standard_normal(A.shape)).astype(np.float32)
+    B2[1] = (A[1] * np.array([1, 1, -1], np.float32)) + 0.01 * rs.standard_normal((21, 3)).astype(np.float32)
+    B2[2] = A[2] + 0.05 * rs.standard_normal((21, 3)).astype(np.float32)
+    out = np.stack([g.rigid_align(A[i], B2[i]) for i in range(6)])
+    path = os.path.join(HERE, "golden_path.npz")
+    d = dict(np.load(path))
+    d.update(f4_A=A, f4_B=B2, f4_aligned=out.astype(np.float64))
+    np.savez_compressed(path, **d)
+
+
+if __name__ == "__main__":
+    add_eval_tail_golden()

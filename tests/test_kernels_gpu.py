@@ -268,3 +268,16 @@ def test_fusion_layers(ops, golden, golden_meta, dtype):
     close(out, O.fsp(p, gdd.float(), mn.float()), **tol)
     if dtype == torch.float32:
         close(out, golden["a15_fsp_out"], **tol)
+
+
+# ------------------------------------------------------------------------------------------------ 8f-4 evaluation tail
+def test_eval_errors(ops, golden):
+    A, Bt = golden["f4_A"], golden["f4_B"]
+    n = A.shape[0]
+    cube = np.full((n, 3), 250.0, np.float32)
+    center = np.zeros((n, 3), np.float32)
+    err, pa = ops.eval_errors(cu(A), cu(Bt), cu(cube))
+    close(err, O.xyz2error(A, Bt, center, cube), rtol=1e-5, atol=1e-4)
+    ref_pa = O.xyz2error(golden["f4_aligned"], Bt, center, cube)       # the reference's own aligned joints
+    close(pa, ref_pa, rtol=1e-4, atol=1e-3)
+    assert float(pa[1].mean()) > 1.0                                    # the reflected sample cannot be aligned by a rotation

@@ -202,3 +202,10 @@ def test_whole_path(golden, golden_inputs, path_params):
                                  i["M"].numpy(), i["cube"].numpy(), i["cam"].numpy())
     mm = np.linalg.norm((res[3].numpy() - golden["b2_r2d"]) * 125.0, axis=-1).mean()
     assert mm <= 0.05, mm
+
+
+def test_eval_tail_rigid_align(golden):
+    """oracle rigid_align vs the reference's GFM.rigid_align (incl. the reflection branch)."""
+    for i in range(golden["f4_A"].shape[0]):
+        a2 = O.rigid_align(golden["f4_A"][i].astype(np.float64), golden["f4_B"][i].astype(np.float64))
+        close(a2, golden["f4_aligned"][i], rtol=1e-5, atol=1e-6)   # the reference ran on float32 joints
