@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     float* sJF = reinterpret_cast<float*>(sPcl + (p.N + p.J + 3) / 4 * 4);  // [J][128] fp32 joint features
     float* sOut = sJF + p.J * 128;                     // [J][128]
     float* sMS = sOut + p.J * 128;                     // [T][2][32] partial max/sum, then [T][32] scale factors + den[32]
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sMS + p.T * 64 + 64);  // [N + J] ball-query hit bits (one per centre)
-    uint16_t* sIdx = reinterpret_cast<uint16_t*>(sMask + ((p.N + p.J + 3) / 4 * 4));  // [J][nsample]
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sMS + p.T * 64 + 64);  // [J][(N+J+31)/32] ball-query hit words (bit = point)
+    uint16_t* sIdx = reinterpret_cast<uint16_t*>(sMask + ((p.J * ((p.N + p.J + 31) / 32) + 3) / 4 * 4));  // [J][nsample]
     __shared__ __align__(8) uint64_t wbar[2], mma_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -154,58 +154,62 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     // Phase 2: one warp per centre compacts the set bits in index order with ballots (no arithmetic in the serial loop).
     {
         const float r2 = xmul(radius, radius);
-        // rounds of 8 points per thread held in registers; centres stream through (one LDS.128 per centre per round)
+        const int NW = (N + J + 31) / 32;   // hit words per centre
+        // Phase 1: rounds of 8 points per thread held in registers; centres stream through (one LDS.128 per centre per round).
+        // A warp's 32 lanes hold 32 CONSECUTIVE points, so one ballot per (centre, point group) IS the transposed hit word.
         for (int base = 0; base < N + J; base += 128 * 8) {
             float4 q[8];
-            uint32_t m[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int n = base + u * 128 + tid;
                 q[u] = n < N + J ? sPcl[n] : make_float4(1e30f, 1e30f, 1e30f, 0.f);
-                m[u] = 0;
             }
             for (int j = 0; j < J; ++j) {
                 const float4 c = sPcl[N + j];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const float dx = xsub(c.x, q[u].x), dy = xsub(c.y, q[u].y), dz = xsub(c.z, q[u].z);
-                    m[u] |= (xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz)) < r2 ? 1u : 0u) << j;
+                    const bool hit = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz)) < r2;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                    const int wi = (base + u * 128) / 32 + warp;
+                    if (lane == 0 && wi < NW) sMask[j * NW + wi] = bal;
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int n = base + u * 128 + tid;
-                if (n < N + J) sMask[n] = m[u];
             }
         }
         __syncthreads();
         stamp();
+        // Phase 2: one warp per centre: popcount prefix over its hit words, then every lane expands the set bits of its word(s)
+        // into their slots; first NS hits in index order, the rest padded with the first hit (pointnet2_ops semantics).
         for (int j = warp; j < J; j += 4) {
-            int cnt = 0, first = 0;
-            // 128 points (4 ballots) per iteration: the serial dependency is one prefix count per 128 points, not per 32
-            for (int base = 0; base < N + J && cnt < NS; base += 128) {
-                bool hit[4];
-                uint32_t bal[4];
+            const uint32_t* wj = sMask + j * NW;
+            int carry = 0, first = -1;
+            for (int w0 = 0; w0 < NW && carry < NS; w0 += 32) {
+                const int wi = w0 + lane;
+                uint32_t word = wi < NW ? wj[wi] : 0u;
+                const int cntw = __popc(word);
+                int incl = cntw;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int n = base + 32 * u + lane;
-                    hit[u] = n < N + J && ((sMask[n] >> j) & 1u);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) bal[u] = __ballot_sync(0xffffffffu, hit[u]);
-                int off = cnt;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (bal[u]) {
-                        if (off == 0) first = base + 32 * u + __ffs(bal[u]) - 1;
-                        const int slot = off + __popc(bal[u] & ((1u << lane) - 1u));
-                        if (hit[u] && slot < NS) sIdx[j * NS + slot] = (uint16_t)(base + 32 * u + lane);
-                        off += __popc(bal[u]);
-                    }
+                int slot = carry + incl - cntw;
+                const uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
+                if (first < 0 && nz) {
+                    const int fl = __ffs(nz) - 1;
+                    const uint32_t fw = __shfl_sync(0xffffffffu, word, fl);
+                    first = (w0 + fl) * 32 + __ffs(fw) - 1;
                 }
-                cnt = off;
+                while (word && slot < NS) {
+                    const int bit = __ffs(word) - 1;
+                    sIdx[j * NS + slot] = (uint16_t)(wi * 32 + bit);
+                    word &= word - 1;
+                    ++slot;
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-            if (cnt > NS) cnt = NS;
+            if (first < 0) first = 0;
+            const int cnt = carry < NS ? carry : NS;
             for (int s2 = cnt + lane; s2 < NS; s2 += 32) sIdx[j * NS + s2] = (uint16_t)first;
         }
     }
@@ -352,7 +356,7 @@ extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float*
     p.dbg = dbg;
     p.radius[0] = r0; p.radius[1] = r1; p.radius[2] = r2; p.radius[3] = r3;
     const size_t smem = (size_t)(2048 + 256 + 2048 + 2048 + 256 + 2048) * 16 + (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * 128 * 4 * 2 +
-                        (size_t)(p.T * 64 + 64) * 4 + (size_t)((N + J + 3) / 4 * 4) * 4 + (size_t)J * nsample * 2 + 64;
+                        (size_t)(p.T * 64 + 64) * 4 + (size_t)((J * ((N + J + 31) / 32) + 3) / 4 * 4) * 4 + (size_t)J * nsample * 2 + 64;
     KPF_REQUIRE(smem <= 227 * 1024);
     cudaError_t err = cudaFuncSetAttribute(desa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
