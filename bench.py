@@ -230,6 +230,27 @@ def main():
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
         return
+    if os.environ.get("KPF_TRACE"):  # CUPTI timeline of warm graph replays: in-step kernel durations and the gaps between them
+        from torch.profiler import profile, ProfilerActivity
+        with torch.no_grad():
+            for i in range(4):
+                step(i, sets[i % NSETS])
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for i in range(4):
+                    step(i, sets[i % NSETS])
+                torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                     key=lambda e: e.time_range.start)
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.environ["KPF_TRACE"], "w") as f:
+            prev_end = None
+            for e in evs:
+                s, t = e.time_range.start, e.time_range.end
+                gap = 0.0 if prev_end is None else s - prev_end
+                f.write(f"{s - evs[0].time_range.start:10.1f} us  dur {t - s:8.1f}  gap {gap:7.1f}  {e.name[:70]}\n")
+                prev_end = t
+        return
     n0 = ops.launch_count()
     ms = timed(lambda i: step(i, sets[i % NSETS]), a.steps, W)
     if graphed is not None:

@@ -224,7 +224,7 @@ extern "C" int kpf_getpcl(const float* img, const float* com3D, const float* cub
     KPF_REQUIRE(B >= 0 && S >= 1 && S <= 256 && sample_num >= 1);
     if (B == 0) return 0;
     const size_t smem = k1_smem_bytes(S);
-    cudaError_t e = cudaFuncSetAttribute(backproject_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kpf::set_smem(backproject_kernel<0>, smem);
     if (e != cudaSuccess) return (int)e;
     backproject_kernel<0><<<B, K1_THREADS, smem, stream>>>(img, com3D, cube, M, cam, S, sample_num, ranks, seed, clamp, flip,
                                                           pcl_out, nullptr, count_out);
@@ -239,7 +239,7 @@ extern "C" int kpf_backproject_all(const float* img, const float* com3D, const f
     KPF_REQUIRE(B >= 0 && S >= 1 && S <= 256);
     if (B == 0) return 0;
     const size_t smem = k1_smem_bytes(S);
-    cudaError_t e = cudaFuncSetAttribute(backproject_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kpf::set_smem(backproject_kernel<1>, smem);
     if (e != cudaSuccess) return (int)e;
     backproject_kernel<1><<<B, K1_THREADS, smem, stream>>>(img, com3D, cube, M, cam, S, 0, nullptr, 0u, 0, flip, xyz_out, pix_out,
                                                           count_out);

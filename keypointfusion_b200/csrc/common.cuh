@@ -12,6 +12,17 @@
         if (e__ != cudaSuccess) return (int)e__;   \
     } while (0)
 
+namespace kpf {
+// Opt a kernel into `smem` bytes of dynamic shared memory and pin the L1/shared split at "max shared" so that
+// back-to-back kernels of one step never ask the SM to re-partition its unified L1 between launches.
+template <typename K>
+inline cudaError_t set_smem(K* kernel, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+}  // namespace kpf
+
 #define KPF_REQUIRE(cond)                          \
     do {                                           \
         if (!(cond)) return KPF_ERR_BAD_ARGUMENT;  \

@@ -202,7 +202,7 @@ extern "C" int kpf_crop_depth(const void* depth_u16, const double* center, const
     KPF_REQUIRE(B >= 0 && Hf >= 1 && Wf >= 1 && dsize >= 8 && dsize <= 224);
     if (B == 0) return 0;
     const size_t smem = (size_t)dsize * dsize * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(crop_depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kpf::set_smem(crop_depth_kernel, smem);
     if (e != cudaSuccess) return (int)e;
     crop_depth_kernel<<<B, 256, smem, stream>>>((const uint16_t*)depth_u16, center, cube, cam, Hf, Wf, dsize, img_out, M_out, com3d_out);
     KPF_CHECK_LAUNCH();

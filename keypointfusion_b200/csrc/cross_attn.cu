@@ -160,7 +160,7 @@ extern "C" int kpf_cross_decoder_layer(const float* anchor, const float* tokens,
     if (B == 0) return 0;
     const int mx = C > F ? C : F;
     const size_t smem = ((size_t)J * C * 3 + (size_t)J * mx + (size_t)J * 2 * C + (size_t)heads * J * J) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(cross_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kpf::set_smem(cross_decoder_kernel, smem);
     if (e != cudaSuccess) return (int)e;
     cross_decoder_kernel<<<B, 256, smem, stream>>>(anchor, tokens, wpack, J, C, F, heads, out_cj, out_jc, out_jc_stride, out_jc_c0);
     KPF_CHECK_LAUNCH();

@@ -358,7 +358,7 @@ extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float*
     const size_t smem = (size_t)(2048 + 256 + 2048 + 2048 + 256 + 2048) * 16 + (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * 128 * 4 * 2 +
                         (size_t)(p.T * 64 + 64) * 4 + (size_t)((J * ((N + J + 31) / 32) + 3) / 4 * 4) * 4 + (size_t)J * nsample * 2 + 64;
     KPF_REQUIRE(smem <= 227 * 1024);
-    cudaError_t err = cudaFuncSetAttribute(desa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = kpf::set_smem(desa_fused_kernel, smem);
     if (err != cudaSuccess) return (int)err;
     desa_fused_kernel<<<B * S, 128, smem, stream>>>(p);
     KPF_CHECK_LAUNCH();

@@ -56,7 +56,7 @@ static int launch_gather(const T* feat, long long feat_bs, int B, int C, int HW,
 #define KPF_GATHER(CTV)                                                                                                      \
     {                                                                                                                        \
         const size_t smem = row * CTV;                                                                                       \
-        cudaError_t e = cudaFuncSetAttribute(gather_taps_kernel<T, I, CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = kpf::set_smem(gather_taps_kernel<T, I, CTV>, smem); \
         if (e != cudaSuccess) return (int)e;                                                                                 \
         dim3 grid((C + CTV - 1) / CTV, B);                                                                                   \
         gather_taps_kernel<T, I, CTV><<<grid, 256, smem, stream>>>(feat, feat_bs, C, HW, index, closeness, N, K, out, out_stride, out_c0); \

@@ -339,7 +339,7 @@ extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long
     const size_t smem = (size_t)fs * fs * sizeof(float4);
 #define KPF_LAUNCH_K2(KK)                                                                                                    \
     case KK: {                                                                                                               \
-        cudaError_t e = cudaFuncSetAttribute(nearest_cells_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = kpf::set_smem(nearest_cells_kernel<KK>, smem); \
         if (e != cudaSuccess) return (int)e;                                                                                 \
         nearest_cells_kernel<KK><<<grid, 256, smem, stream>>>(pcl, depth, depth_bs, depth_rs, depth_cs, center, M, cube, cam, N, \
                                                              fs, img_size, flip, closeness, index64, index32);               \
@@ -368,12 +368,15 @@ extern "C" int kpf_offset2joint_weight(const void* offset, int dtype, const floa
     KPF_REQUIRE(B >= 0 && J >= 1 && fs >= 1 && S >= fs);
     if (B == 0) return 0;
     dim3 grid(J, B);
-    if (dtype == KPF_F32)
+    if (dtype == KPF_F32) {
+        kpf::set_smem(offset2joint_kernel<float>, 0);
         offset2joint_kernel<float><<<grid, 256, 0, stream>>>((const float*)offset, depth, S, J, fs, kernel_vec, joint_out);
-    else if (dtype == KPF_BF16)
+    } else if (dtype == KPF_BF16) {
+        kpf::set_smem(offset2joint_kernel<__nv_bfloat16>, 0);
         offset2joint_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)offset, depth, S, J, fs, kernel_vec, joint_out);
-    else
+    } else {
         return KPF_ERR_UNSUPPORTED;
+    }
     KPF_CHECK_LAUNCH();
     return 0;
 }

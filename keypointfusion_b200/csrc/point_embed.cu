@@ -295,14 +295,17 @@ extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const voi
     KPF_REQUIRE(B >= 0 && C == 128 && J >= 1 && J <= 32 && HW >= 1);
     if (B == 0) return 0;
     dim3 grid((HW + 31) / 32, PE_CP / 32, B);
-    if (dtype == KPF_F32)
+    if (dtype == KPF_F32) {
+        kpf::set_smem(repack_kernel<float>, 0);
         repack_kernel<float><<<grid, 256, 0, stream>>>((const float*)f_d, (const float*)f_rgb, (const float*)f_w, w_batch_stride, C, J, HW,
                                                       (__nv_bfloat16*)out);
-    else if (dtype == KPF_BF16)
+    } else if (dtype == KPF_BF16) {
+        kpf::set_smem(repack_kernel<__nv_bfloat16>, 0);
         repack_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)f_d, (const __nv_bfloat16*)f_rgb,
                                                               (const __nv_bfloat16*)f_w, w_batch_stride, C, J, HW, (__nv_bfloat16*)out);
-    else
+    } else {
         return KPF_ERR_UNSUPPORTED;
+    }
     KPF_CHECK_LAUNCH();
     return 0;
 }
@@ -319,7 +322,7 @@ extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const floa
     p.e_out = (__nv_bfloat16*)e_out; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
     p.kernel_size = kernel_size;
     p.dbg = dbg;
-    cudaError_t e = cudaFuncSetAttribute(point_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PE_SMEM);
+    cudaError_t e = kpf::set_smem(point_embed_kernel, PE_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int tiles = B * (N / 128);
     point_embed_kernel<<<tiles < num_sms ? tiles : num_sms, 128, PE_SMEM, stream>>>(p);

@@ -163,7 +163,7 @@ extern "C" int kpf_spatial_aggregate(const void* feat_rgb, int dtype, const floa
     if (B == 0) return 0;
     const size_t smem = ((size_t)C * K5_LD + (size_t)J * (C + J) + 2 * (size_t)J * K5_TH + (size_t)J * 8) * sizeof(float);
     if (dtype == KPF_F32) {
-        cudaError_t e = cudaFuncSetAttribute(spatial_aggregate_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = kpf::set_smem(spatial_aggregate_kernel<float>, smem);
         if (e != cudaSuccess) return (int)e;
         spatial_aggregate_kernel<float><<<B, 256, smem, stream>>>((const float*)feat_rgb, joints, depth, depth_bs, depth_rs, depth_cs,
                                                                  center, M, cube, cam, Wa, ba, weight_dis, fc_w, fc_b, prev, C, J, fs,
@@ -171,7 +171,7 @@ extern "C" int kpf_spatial_aggregate(const void* feat_rgb, int dtype, const floa
                                                                  gam_out);
     } else if (dtype == KPF_BF16) {
         cudaError_t e =
-            cudaFuncSetAttribute(spatial_aggregate_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kpf::set_smem(spatial_aggregate_kernel<__nv_bfloat16>, smem);
         if (e != cudaSuccess) return (int)e;
         spatial_aggregate_kernel<__nv_bfloat16><<<B, 256, smem, stream>>>(
             (const __nv_bfloat16*)feat_rgb, joints, depth, depth_bs, depth_rs, depth_cs, center, M, cube, cam, Wa, ba, weight_dis, fc_w,

@@ -259,7 +259,7 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joint
     p.dbg = dbg; p.scratch = scratch; p.counters = counters; p.split = split;
     p.B = B; p.J = J; p.fs = fs; p.img_size = img_size; p.flip = flip; p.hm_std = hm_std; p.hm_sigma = hm_sigma; p.gamma = gamma;
     const size_t smem = (size_t)(4096 + 2048 + 512 + 512 + 640) * 16 + 32 * 8 * 4 + 32 * 4;
-    cudaError_t e = cudaFuncSetAttribute(spatial_aggregate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kpf::set_smem(spatial_aggregate_tc_kernel, smem);
     if (e != cudaSuccess) return (int)e;
     spatial_aggregate_tc_kernel<<<B * split, 128, smem, stream>>>(p);
     KPF_CHECK_LAUNCH();

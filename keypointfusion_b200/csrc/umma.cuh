@@ -36,14 +36,37 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
-// D[128 x N] (+)= A[128 x K] * B[N x K]^T ; K % 16 == 0.  Issued by ONE thread.
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T ; K % 16 == 0.  Issued by ONE thread.  A rolled loop on purpose: the issue
+// rate of the tensor pipe (~80 cycles per MMA here), not this loop, bounds it, and the unrolled form costs ~15 SASS
+// instructions of descriptor arithmetic per MMA in kernels that are already instruction-fetch bound.
 __device__ __forceinline__ void umma_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_addr,
                                           uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int K, bool accumulate) {
+    uint64_t ad = umma_smem_desc(a_addr, a_lbo, a_sbo), bd = umma_smem_desc(b_addr, b_lbo, b_sbo);
+    const uint64_t a_step = (uint64_t)((2 * a_lbo) >> 4), b_step = (uint64_t)((2 * b_lbo) >> 4);  // start-address field, 16-byte units
+#pragma unroll 1
     for (int ks = 0; ks < K / 16; ++ks) {
-        umma_bf16(tmem_d, umma_smem_desc(a_addr + ks * 2 * a_lbo, a_lbo, a_sbo), umma_smem_desc(b_addr + ks * 2 * b_lbo, b_lbo, b_sbo),
-                  idesc, accumulate || ks > 0);
+        umma_bf16(tmem_d, ad, bd, idesc, accumulate || ks > 0);
+        ad += a_step;
+        bd += b_step;
     }
 }
+
+// One lane of a CONVERGENT warp.  MMA / TMA issue code belongs in `if (warp_u == 0) { if (elect_one()) {...} __syncwarp(); }` with
+// warp_u = warp_index_uniform(): inside a branch ptxas can prove warp-uniform the descriptors stay in uniform registers and each
+// tcgen05.mma is one UTCHMMA; under a divergent `if (tid == 0)` every MMA is wrapped in a ~15-instruction
+// ELECT / R2UR.BROADCAST waterfall loop (~100 cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int warp_index_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

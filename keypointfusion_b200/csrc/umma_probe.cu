@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(long long* out, int N, 
 extern "C" int kpf_umma_probe(long long* out, int N, int K, int reps, cudaStream_t stream) {
     using namespace kpf;
     const size_t smem = (size_t)(128 + N) * K * 2;
-    cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kpf::set_smem(umma_probe_kernel, smem);
     if (e != cudaSuccess) return (int)e;
     umma_probe_kernel<<<1, 128, smem, stream>>>(out, N, K, reps);
     KPF_CHECK_LAUNCH();

@@ -72,7 +72,7 @@ extern "C" int kpf_umma_selftest(const void* A, const void* B, float* D, int N, 
     KPF_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0);
     const size_t smem = (size_t)(128 + N) * K * 2;
     KPF_REQUIRE(smem <= 200 * 1024);
-    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kpf::set_smem(umma_selftest_kernel, smem);
     if (e != cudaSuccess) return (int)e;
     umma_selftest_kernel<<<1, 128, smem, stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, N, K, a_mn, b_mn);
     KPF_CHECK_LAUNCH();

@@ -385,8 +385,11 @@ def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
             T = Wemb.new_zeros(C, 16)
             T[:, :shift] = Wemb[:, :shift]
             add(_canon(T), in_seq=False)   # K-tail sits right behind the main part
-        vecs += [g("bert.position_embeddings.weight")[:J].reshape(-1), g("bert.img_embedding.bias"), g("residual.weight").reshape(-1),
-                 _pad(g("residual.bias"), 4), g("cls_head.weight").reshape(-1), _pad(g("cls_head.bias"), 4)]
+        Wres = g("residual.weight")                       # [3, D] -> 16-byte aligned rows: [3][16] lead (zero padded) | [3][128] features
+        lead = Wres.new_zeros(3, 16)
+        lead[:, :shift] = Wres[:, :shift]
+        vecs += [g("bert.position_embeddings.weight")[:J].reshape(-1), g("bert.img_embedding.bias"), lead.reshape(-1),
+                 Wres[:, shift:].reshape(-1), _pad(g("residual.bias"), 4), g("cls_head.weight").reshape(-1), _pad(g("cls_head.bias"), 4)]
         while f"{pf}bert.encoder.layer.{L}.attention.self.query.weight" in sd:
             lp = f"bert.encoder.layer.{L}."
             F_ = g(lp + "intermediate.dense.weight").shape[0]

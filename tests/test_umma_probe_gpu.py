@@ -35,7 +35,7 @@ def test_token_stack_phase_clocks(path_params, capsys):
     for _ in range(3):
         ops.token_stack(pk, desa=part, jf=jf, dbg=dbg)
     torch.cuda.synchronize()
-    t = dbg.cpu().numpy()
+    t = dbg.cpu().numpy()[:32]
     n = int((t > 0).sum())
     d = np.diff(t[:n])
     with capsys.disabled():
@@ -44,6 +44,9 @@ def test_token_stack_phase_clocks(path_params, capsys):
         for l in range(4):
             print("   layer", l, [int(x) for x in d[1 + 4 * l: 5 + 4 * l]])
         print("   tail", [int(x) for x in d[17:]])
+        f = dbg.cpu().numpy()[32:]
+        nf = int((f > 0).sum())
+        print("   fine stamps inside encoder layer 0 (deltas):", [int(x) for x in np.diff(f[:nf])])
 
 
 def test_block_kernel_phase_clocks(path_params, capsys):
