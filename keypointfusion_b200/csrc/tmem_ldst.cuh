@@ -9,6 +9,10 @@ namespace kpf {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld1_nw(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld2_nw(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
@@ -73,8 +77,9 @@ __device__ __forceinline__ void tmem_st32_nw(uint32_t taddr, const float* v) {
 
 template <int N>
 __device__ __forceinline__ void tmem_ld_nw(uint32_t taddr, float* v) {
-    static_assert(N == 2 || N == 4 || N == 8 || N == 16 || N == 32 || N == 64, "unsupported width");
-    if constexpr (N == 2) tmem_ld2_nw(taddr, v);
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16 || N == 32 || N == 64, "unsupported width");
+    if constexpr (N == 1) tmem_ld1_nw(taddr, v);
+    else if constexpr (N == 2) tmem_ld2_nw(taddr, v);
     else if constexpr (N == 4) tmem_ld4_nw(taddr, v);
     else if constexpr (N == 8) tmem_ld8_nw(taddr, v);
     else if constexpr (N == 16) tmem_ld16_nw(taddr, v);

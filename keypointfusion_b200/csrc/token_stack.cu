@@ -7,30 +7,31 @@
 //             Q from anchor + self_posembed, K = V from tokens + cross_posembed, +res(anchor), LN2, FFN(relu), +res, LN3
 //   cross + encoder fused: crossTR followed by final_TR on cat([r3d, cross_out]) (model.py:347-349) without leaving the SM.
 //
-// Tile = 4 samples x 32 rows (J <= 32 joint tokens per sample, zero padded): warp q of each warpgroup owns sample q, so the
-// 32 x 32 key block of a row is ONE 32-column TMEM chunk at a warp-uniform address.  TS_NT threads: TS_CG threads per row
-// (tid, tid+128, ...) split every epilogue's columns; the softmax of the two heads of a round runs in column groups 0 / 1.
-// Projections / FFNs are [128 x K] x [K x N] MMAs against weights streamed by the TMA engine (cp.async.bulk, 2-slot ring).
-// Per head S = Q_h K_h^T is a 128 x 128 x 32 MMA of which the block diagonal is kept (softmax in registers), P is written
-// with zeros elsewhere, and O_h = P V_h is a 128 x 32 x 128 MMA with V as an MN-major B operand.  The fp32 residual stream
-// lives in TMEM columns [384,512).  Thread 0 issues MMAs and TMA copies.
+// These stacks are latency chains (tiny GEMMs, long dependent sequences), so the design minimises the chain of ONE sample and
+// spreads samples over SMs: one CTA = one sample, 512 threads.
+//   * The M = 128 MMA tile holds the sample's J <= 32 token rows FOUR times (rows 32r + t, r = 0..3).  A warp may only touch the
+//     32 TMEM lanes of its quarter (warp % 4), so replication is what lets all 16 warps work on the same 32 tokens: thread
+//     (quarter q, column group c, token t) owns columns [32q + 8c, +8) of every 128-wide epilogue = ONE 16-byte operand chunk.
+//   * Attention for all four heads is two MMA pairs.  Q is written "head major" (row 32h + t = head h of token t, K = 32), K
+//     likewise as the B operand, so ONE 128x128x32 MMA pair yields S_h in lanes/columns [32h, 32h+32) - the block diagonal.
+//     P_h goes back to rows 32h + t (K = 32 keys), V is an MN-major [128 dims x 32 keys] B operand, and ONE 128x128x32 MMA
+//     pair yields O_h in the same diagonal blocks, which are exactly the columns each quarter owns.
+//   * Q and K|V (one N = 256 tile) are issued back to back; weights stream through three 32 KB slots by cp.async.bulk, each
+//     transfer gated on the GEMM that last used its slot (table from ops.pack_token_program); per-layer vectors are
+//     double-buffered the same way.  The fp32 residual stream lives in TMEM columns [384, 512).
+// One elected lane of warp 0 issues MMAs and TMA copies from warp-uniform code (umma.cuh: elect_one).
 #include "tmem_ldst.cuh"
 
 namespace kpf {
 
 constexpr int TS_C = 128;              // hidden size
-constexpr int TS_SLOT = 2048;          // uint4 per weight slot (32 KB)
-constexpr uint32_t TS_LBO = 128 * 16;  // K-major operand with 128 rows: bytes between 8-k groups
+constexpr int TS_NT = 512;             // 16 warps = 4 lane quarters x 4 column groups
+constexpr int TS_SLOT = 2048;          // uint4 per weight slot (32 KB), three slots
 constexpr int TS_MAXG = 64;            // weight tiles per program
+constexpr int TS_NB = 8;               // weight-arrival barriers (transfer g uses g % TS_NB)
+constexpr int TS_VEC = 10 * TS_C;      // floats of per-layer vectors
+constexpr uint32_t TS_LBO = 128 * 16;  // K-major operand with 128 rows: bytes between 8-k groups
 constexpr uint32_t ACC0 = 0, ACC1 = 128, ACC2 = 256, RESID = 384;
-// Threads per CTA.  128 rows x TS_CG threads per row: every 128-wide epilogue is split into TS_CW-column pieces, so the
-// serial instruction stream of a thread (and the SASS the SM has to fetch) shrinks with TS_CG while the warps per
-// scheduler that hide TMEM / shared-memory latency grow with it.
-constexpr int TS_NT = 512;
-constexpr int TS_CG = TS_NT / 128;
-constexpr int TS_CW = 128 / TS_CG;
-constexpr int TS_CH = TS_CW < 32 ? TS_CW : 32;  // columns per prologue piece
-constexpr int TS_FU = TS_CG >= 8 ? 2 : (TS_CG == 4 ? 4 : 8);  // FFN hidden columns per thread per pass
 
 struct TokParams {
     const float* x;        // encoder input [B,J,D] (no prologue) | cross: anchor [B,J,C]
@@ -39,7 +40,7 @@ struct TokParams {
     const float* desa;     // prologue: [B,3,J,C]
     const float* jf;       // prologue: [B,J,C]
     const uint4* wmat;     // bf16 canonical matrices
-    const int2* wseq;      // (offset, count) in uint4 of weight g of the consumption sequence
+    const int4* wseq;      // per weight tile g: (source offset, count, slot offset) in uint4, GEMM whose completion frees the slot
     const float* wvec;     // fp32 vectors
     float* tokens_out;     // [B,J,C] or null (final hidden states)
     float* pred_out;       // [B,J,3] or null
@@ -59,25 +60,19 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
 
-// N consecutive floats of a row.  ALIGNED: the row start is 16-byte aligned (everything except the D = 131 inputs).
-template <int N, bool ALIGNED>
-__device__ __forceinline__ void load_row(const float* __restrict__ src, float* v, bool valid) {
+// 8 consecutive floats of a row.  ALIGNED: 16-byte aligned (everything except the D = 131 inputs).
+template <bool ALIGNED>
+__device__ __forceinline__ void load8(const float* __restrict__ src, float* v, bool valid) {
     if (!valid) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = 0.f;
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
     } else if (ALIGNED) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-        for (int i = 0; i < N / 4; ++i) {
-            const float4 t = __ldg(s4 + i);
-            v[4 * i] = t.x;
-            v[4 * i + 1] = t.y;
-            v[4 * i + 2] = t.z;
-            v[4 * i + 3] = t.w;
-        }
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = __ldg(src + i);
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(src + i);
     }
 }
 
@@ -96,37 +91,40 @@ __device__ __forceinline__ void head_acc(float* acc, const float* v, const float
 }
 
 __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p) {
-    constexpr int CG = TS_CG, CW = TS_CW, CH = TS_CH, NCH = TS_CW / 8;
     extern __shared__ __align__(128) unsigned char ts_smem[];
-    uint4* wslot = reinterpret_cast<uint4*>(ts_smem);             // [2][2048]
-    uint4* wtail = wslot + 2 * TS_SLOT;                           // [256]
-    uint4* bufA = wtail + 256;                                    // [16][128]  K-major A operand (h / P / O / LN out)
-    uint4* bufAt = bufA + 2048;                                   // [2][128]   K-tail of the embedding input
-    uint4* bufQ = bufAt + 256;                                    // [16][128]
-    uint4* bufK = bufQ + 2048;                                    // [16][128]
-    uint4* bufV = bufK + 2048;                                    // MN-major [16][16][8]
-    float* sVec = reinterpret_cast<float*>(bufV + 2048);          // [10][128] per-layer vectors
-    float* sInv = sVec + 10 * TS_C;                               // [4][128] 1 / softmax sum of (head, row)
-    float* sRed = sInv + 4 * TS_C;                                // [2][CG][128][2] LayerNorm partials (double buffered)
-    __shared__ __align__(8) uint64_t full[2], mma_bar, tail_bar;
+    uint4* wslot = reinterpret_cast<uint4*>(ts_smem);             // [3][2048]  weight slots
+    uint4* bufA = wslot + 3 * TS_SLOT;                            // [16][128]  K-major A operand, rows replicated x4 (h / O / LN out)
+    uint4* bufB = bufA + 2048;                                    // [16][128]  second full operand: prologue source, cross k_in, FFN hidden
+    uint4* bufQ = bufB + 2048;                                    // [4][128]   Q head-major (row 32h+t, K = 32)
+    uint4* bufK = bufQ + 512;                                     // [4][128]   K head-major (B operand of S)
+    uint4* bufV = bufK + 512;                                     // [4][16][8] V MN-major (B operand of P V): 128 dims x 32 keys
+    uint4* bufP = bufV + 512;                                     // [4][128]   P (row 32h+t, K = 32 keys)
+    uint4* bufAt = bufP + 512;                                    // [2][128]   K-tail of the embedding input
+    uint4* wtail = bufAt + 256;                                   // [256]      K-tail of the embedding weight
+    float* sVec = reinterpret_cast<float*>(wtail + 256);          // [2][10][128] per-layer vectors (double buffered)
+    float2* sRed = reinterpret_cast<float2*>(sVec + 2 * TS_VEC);  // [2][16][32] LayerNorm partials (double buffered)
+    float* sSum = reinterpret_cast<float*>(sRed + 2 * 16 * 32);   // [4][128]   softmax partial sums of (column group, row)
+    __shared__ __align__(8) uint64_t full[TS_NB], vec_bar[2], mma_bar, aux_bar, tail_bar;
     __shared__ uint32_t tmem_slot;
-    __shared__ int2 sSeq[TS_MAXG];   // the weight sequence table: the issuing lane must not sit behind a global load per GEMM
+    __shared__ int4 sSeq[TS_MAXG];
 
-    const int tid = threadIdx.x, row = tid & 127, cg = tid >> 7, wq = (tid >> 5) & 3;
-    const int J = p.J, C = TS_C;
-    const int tok = row & 31;
-    const int b = blockIdx.x * 4 + wq;                   // warp-uniform sample
-    const bool valid = tok < J && b < p.B;
-    const int cb = cg * CW;                              // this thread's columns of every 128-wide epilogue
-    const int G = p.G;
-    const int warp_u = warp_index_uniform();             // MMA / TMA issue: one elected lane of warp 0
+    const int tid = threadIdx.x, t = tid & 31, w = tid >> 5, q = w & 3, c = w >> 2;
+    const int row = 32 * q + t;   // this thread's TMEM lane = operand row of its quarter's replica
+    const int col0 = 32 * q + 8 * c;  // its 8 columns of every 128-wide epilogue
+    const int ck = 4 * q + c;         // = col0 / 8: its 16-byte chunk of a K-major row
+    const int J = p.J, C = TS_C, G = p.G;
+    const int b = blockIdx.x;
+    const bool valid = t < J;
+    const int warp_u = warp_index_uniform();
 
     if (tid < 32) tmem_alloc(&tmem_slot, 512);
     if (tid >= 32 && tid < 32 + G) sSeq[tid - 32] = p.wseq[tid - 32];
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int i = 0; i < TS_NB; ++i) mbar_init(&full[i], 1);
+        mbar_init(&vec_bar[0], 1);
+        mbar_init(&vec_bar[1], 1);
         mbar_init(&mma_bar, 1);
+        mbar_init(&aux_bar, 1);
         mbar_init(&tail_bar, 1);
         fence_mbar_init();
     }
@@ -134,34 +132,77 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem0 = tmem_slot;
-    const uint32_t tmem = tmem0 + ((uint32_t)(wq * 32) << 16);  // this thread's lane window
-    uint32_t mma_phase = 0;
-    int n_fine = 0;
-    bool fine_on = false;
-    auto fine = [&]() {   // second stamp series (dbg[32..63]): inside the first encoder layer
-        if (p.dbg && fine_on && blockIdx.x == 0 && tid == 0 && n_fine < 32) p.dbg[32 + n_fine++] = clock64();
-    };
-    // sequence index of the embedding GEMM that owns the K-tail (its tail weights follow its main part in wmat)
-    const int tail_g = (p.L > 0 && p.D > C) ? (p.cross ? 6 : 0) + (p.pre ? 4 : 0) : -1;
+    const uint32_t tmem = tmem0 + ((uint32_t)(32 * q) << 16);  // this thread's lane window
+    uint32_t mma_phase = 0, aux_phase = 0;
 
-    auto load_w = [&](int gi) {  // one elected lane of warp 0
-        const int2 s = sSeq[gi];
-        mbar_expect_tx(&full[gi & 1], (uint32_t)s.y * 16);
-        tma_bulk_g2s(wslot + (gi & 1) * TS_SLOT, p.wmat + s.x, (uint32_t)s.y * 16, &full[gi & 1]);
+    // ---- layout of the fp32 vector blob (ops.pack_token_program)
+    const int D = p.D, shift = p.L > 0 ? D - C : 0;
+    const float* vp = p.wvec;
+    const float *qpos = nullptr, *kpos = nullptr, *cross_vec = nullptr, *bfu = nullptr, *pos = nullptr, *bemb = nullptr,
+                *Wres_lead = nullptr, *Wres_feat = nullptr, *bres = nullptr, *Wcls = nullptr, *bcls = nullptr, *enc_vec = nullptr;
+    if (p.cross) {
+        qpos = vp;
+        kpos = qpos + J * C;
+        cross_vec = kpos + J * C;
+        vp = cross_vec + TS_VEC;
+    }
+    if (p.pre) {
+        bfu = vp;
+        vp += C;
+    }
+    if (p.L > 0) {
+        pos = vp;                        // [J][128]
+        bemb = pos + J * C;              // [128]
+        Wres_lead = bemb + C;            // [3][16]  residual.weight columns of the leading D-128 inputs (zero padded)
+        Wres_feat = Wres_lead + 48;      // [3][128] residual.weight columns of the 128 features
+        bres = Wres_feat + 3 * C;        // [3] (+1 pad)
+        Wcls = bres + 4;                 // [3][128]
+        bcls = Wcls + 3 * C;             // [3] (+1 pad)
+        enc_vec = bcls + 4;              // [L][10][128]
+    }
+    const int n_layers = (p.cross ? 1 : 0) + p.L;
+    auto layer_vec = [&](int it) { return (p.cross && it == 0) ? cross_vec : enc_vec + (size_t)(it - (p.cross ? 1 : 0)) * TS_VEC; };
+    // sequence index of the embedding GEMM that owns the K-tail (its tail weights follow its main part in wmat)
+    const int tail_g = (p.L > 0 && D > C) ? (p.cross ? 5 : 0) + (p.pre ? 4 : 0) : -1;
+
+    // ---- weight streaming (elected lane of warp 0)
+    int nxt = 0;  // next transfer to issue
+    auto load_w = [&](int gi) {
+        const int4 s = sSeq[gi];
+        mbar_expect_tx(&full[gi % TS_NB], (uint32_t)s.y * 16);
+        tma_bulk_g2s(wslot + s.z, p.wmat + s.x, (uint32_t)s.y * 16, &full[gi % TS_NB]);
     };
+    // GEMM `done` has completed: start every transfer whose slot it (or an earlier GEMM) released
+    auto after_gemm = [&](int done) {
+        if (warp_u == 0) {
+            const bool lead = elect_one();
+            while (nxt < G && sSeq[nxt].w <= done) {
+                if (lead) load_w(nxt);
+                ++nxt;
+            }
+            __syncwarp();
+        }
+    };
+    auto load_vec = [&](int it) {  // elected lane
+        mbar_expect_tx(&vec_bar[it & 1], TS_VEC * 4);
+        tma_bulk_g2s(sVec + (it & 1) * TS_VEC, layer_vec(it), TS_VEC * 4, &vec_bar[it & 1]);
+    };
+    auto wait_w = [&](int gi) { mbar_wait(&full[gi % TS_NB], (gi / TS_NB) & 1); };
+    auto wslot_of = [&](int gi) { return smem_u32(wslot + sSeq[gi].z); };
     if (warp_u == 0) {
         if (elect_one()) {
-            load_w(0);
-            if (G > 1) load_w(1);
+            if (n_layers > 0) load_vec(0);
             if (tail_g >= 0) {
-                const int2 s = sSeq[tail_g];
+                const int4 s = sSeq[tail_g];
                 mbar_expect_tx(&tail_bar, 256 * 16);
                 tma_bulk_g2s(wtail, p.wmat + s.x + s.y, 256 * 16, &tail_bar);
             }
         }
         __syncwarp();
     }
-    // operand writes -> async proxy, everybody's TMEM reads done, then one elected thread issues
+    after_gemm(-1);
+
+    // operand writes -> async proxy, everybody's TMEM reads done, then the elected lane issues
     auto sync_for_mma = [&]() {
         fence_proxy_async();
         tc_fence_before();
@@ -172,391 +213,398 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         mma_phase ^= 1;
         tc_fence_after();
     };
-    // GEMM gi of the sequence: acc[128 x N] (+)= A[128 x K] * W^T.  All threads call; returns once the MMAs have completed.
-    auto run_gemm = [&](int gi, const uint4* a_buf, int N, int K, uint32_t acc_col, bool with_tail, bool accumulate) {
-        sync_for_mma();
-        fine();
-        if (warp_u == 0) {
-            tc_fence_after();
-            mbar_wait(&full[gi & 1], (gi >> 1) & 1);
-            if (with_tail) mbar_wait(&tail_bar, 0);
-            fine();
-            if (elect_one()) {
-                const uint32_t idesc = umma_idesc_bf16(128, N, false, false);
-                umma_gemm(tmem0 + acc_col, smem_u32(a_buf), TS_LBO, 128, smem_u32(wslot + (gi & 1) * TS_SLOT), (uint32_t)N * 16, 128, idesc,
-                          K, accumulate);
-                if (with_tail) umma_gemm(tmem0 + acc_col, smem_u32(bufAt), TS_LBO, 128, smem_u32(wtail), (uint32_t)N * 16, 128, idesc, 16, true);
-                umma_commit(&mma_bar);
-            }
-            __syncwarp();
-            fine();
-        }
-        wait_mma();
-        fine();
-        if (warp_u == 0 && gi + 2 < G) {  // slot gi&1 is free again
-            if (elect_one()) load_w(gi + 2);
-            __syncwarp();
-        }
+    auto wait_aux = [&]() {
+        mbar_wait(&aux_bar, aux_phase);
+        aux_phase ^= 1;
+        tc_fence_after();
     };
-    auto load_vecs = [&](const float* src, int n) {
-        __syncthreads();
-        for (int i = tid; i < n / 4; i += TS_NT) reinterpret_cast<float4*>(sVec)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        __syncthreads();
-    };
-    // N fp32 of this row starting at column c0 -> K-major bf16 chunks
-    auto store_chunks = [&](uint4* buf, int c0, const float* v, int n) {
+    // this thread's chunk of a 128-wide K-major row, written to the four row replicas
+    auto store_rep = [&](uint4* buf, int chunk, const uint4 v) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < n / 8) buf[(c0 / 8 + c) * 128 + row] = pack8_bf16(v + 8 * c);
-    };
-    // acc[:, cb .. cb+CW) + bias (* scale) -> bf16 chunks of a K-major buffer
-    auto drain_kmajor = [&](uint32_t acc, const float* bias, float scale, uint4* dst) {
-        float a[CW];
-        tmem_ld<CW>(tmem + acc + cb, a);
-#pragma unroll
-        for (int i = 0; i < CW; ++i) a[i] = (a[i] + bias[cb + i]) * scale;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) dst[(cb / 8 + c) * 128 + row] = pack8_bf16(a + 8 * c);
+        for (int r = 0; r < 4; ++r) buf[chunk * 128 + 32 * r + t] = v;
     };
 
     int g = 0, n_stamp = 0, red_par = 0;
     auto stamp = [&]() {
-        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 32) p.dbg[n_stamp] = clock64();
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 64) p.dbg[n_stamp] = clock64();
         ++n_stamp;
     };
     stamp();
-    const float* vec = p.wvec;
     float head_x[3] = {0.f, 0.f, 0.f};  // this thread's share of residual(x) of the regression head (fp32)
     const float qscale = rsqrtf((float)(C / 4));  // head_dim^-0.5, 4 heads
-    const int D = p.D, shift = p.L > 0 ? D - C : 0;
-    const float *pos = nullptr, *bemb = nullptr, *Wres_lead = nullptr, *Wres_feat = nullptr, *bres = nullptr, *Wcls = nullptr,
-                *bcls = nullptr;
 
     // =========================== cross-attention inputs (crossTR) ===========================
     if (p.cross) {
-        const float* qpos = vec;
-        const float* kpos = qpos + J * C;
-        const float* ar = p.x + ((size_t)b * J + tok) * C;
-        const float* yr = p.y + ((size_t)b * J + tok) * C;
-        for (int c0 = cb; c0 < cb + CW; c0 += CH) {
-            float a[CH], q[CH], e[CH];
-            load_row<CH, true>(ar + c0, a, valid);
-            load_row<CH, true>(qpos + tok * C + c0, e, valid);
+        float a[8], e[8], kin[8];
+        load8<true>(p.x + ((size_t)b * J + t) * C + col0, a, valid);
+        load8<true>(qpos + t * C + col0, e, valid);
+        load8<true>(p.y + ((size_t)b * J + t) * C + col0, kin, valid);
+        tmem_st_nw<8>(tmem + RESID + col0, a);           // residual = anchor (transfusion_head.py:164)
 #pragma unroll
-            for (int i = 0; i < CH; ++i) q[i] = a[i] + e[i];
-            tmem_st<CH>(tmem + RESID + c0, a);           // residual = anchor (transfusion_head.py:164)
-            store_chunks(bufA, c0, q, CH);
-            load_row<CH, true>(yr + c0, q, valid);
-            load_row<CH, true>(kpos + tok * C + c0, e, valid);
+        for (int i = 0; i < 8; ++i) e[i] += a[i];
+        store_rep(bufA, ck, pack8_bf16(e));              // q_in = anchor + self_posembed
+        load8<true>(kpos + t * C + col0, e, valid);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) q[i] += e[i];
-            store_chunks(bufV, c0, q, CH);               // bufV temporarily holds k_in as a K-major operand
-        }
-        vec = kpos + J * C;
+        for (int i = 0; i < 8; ++i) kin[i] += e[i];
+        store_rep(bufB, ck, pack8_bf16(kin));            // k_in = tokens + cross_posembed
+        tmem_wait_st();
     }
 
-    // One loop over every transformer layer of the program: iteration 0 is the cross layer when there is one, the encoder's
-    // input stage runs in front of its first layer.  (One instance of the layer body keeps the kernel's SASS small.)
-    const int n_layers = (p.cross ? 1 : 0) + p.L;
+    // One loop over every transformer layer of the program: iteration 0 is the cross layer when there is one; the encoder's
+    // input stage runs in front of its first layer.
     for (int it = 0; it < n_layers; ++it) {
         const bool is_cross = p.cross && it == 0;
         if (it == (p.cross ? 1 : 0) && p.L > 0) {
             // =========================== encoder input stage (KP_Interaction_TR) ===========================
             if (p.pre) {
-                // ---- DESA fusion conv: x = relu(W_fu [desa_0 | desa_1 | desa_2 | jf] + b_fu), four accumulating K = 128 steps
-                const float* bfu = vec;
-                vec += C;
-#pragma unroll 1
-                for (int s = 0; s < 4; ++s) {
-                    uint4* dst = s == 0 ? bufA : (s == 1 ? bufQ : (s == 2 ? bufK : bufV));
-                    const float* src = s < 3 ? p.desa + (((size_t)b * 3 + s) * J + tok) * C : p.jf + ((size_t)b * J + tok) * C;
-                    for (int c0 = cb; c0 < cb + CW; c0 += CH) {
-                        float a[CH];
-                        load_row<CH, true>(src + c0, a, valid);
-                        store_chunks(dst, c0, a, CH);
-                    }
-                }
-                run_gemm(g++, bufA, C, C, ACC0, false, false);
-                run_gemm(g++, bufQ, C, C, ACC0, false, true);
-                run_gemm(g++, bufK, C, C, ACC0, false, true);
-                run_gemm(g++, bufV, C, C, ACC0, false, true);
-                const float* Wrf0 = vec + (size_t)J * C + C + 48;
-                for (int c0 = cb; c0 < cb + CW; c0 += CH) {
-                    float a[CH], bb[CH];
-                    tmem_ld_nw<CH>(tmem + ACC0 + c0, a);
-                    load_row<CH, true>(bfu + c0, bb, true);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < CH; ++i) a[i] = valid ? fmaxf(a[i] + bb[i], 0.f) : 0.f;
-                    head_acc<CH>(head_x, a, Wrf0 + c0, C);
-                    store_chunks(bufA, c0, a, CH);
-                }
-            }
-            pos = vec;                       // [J][128]
-            bemb = pos + J * C;              // [128]
-            Wres_lead = bemb + C;            // [3][16]  residual.weight columns of the leading D-128 inputs (zero padded)
-            Wres_feat = Wres_lead + 48;      // [3][128] residual.weight columns of the 128 features
-            bres = Wres_feat + 3 * C;        // [3] (+1 pad)
-            Wcls = bres + 4;                 // [3][128]
-            bcls = Wcls + 3 * C;             // [3] (+1 pad)
-            if (!p.pre && !p.cross) {
-                const float* xr = p.x + ((size_t)b * J + tok) * D;
-                const bool al = (D & 3) == 0 && shift == 0;
-                for (int c0 = cb; c0 < cb + CW; c0 += CH) {
-                    float v[CH];
-                    if (al)
-                        load_row<CH, true>(xr + shift + c0, v, valid);
-                    else
-                        load_row<CH, false>(xr + shift + c0, v, valid);
-                    head_acc<CH>(head_x, v, Wres_feat + c0, C);
-                    store_chunks(bufA, c0, v, CH);
-                }
-            }
-            if (shift > 0 && cg == 0) {  // leading (D - 128) inputs: joint coordinates
-                const float* lead = p.cross ? p.r3d + ((size_t)b * J + tok) * shift : p.x + ((size_t)b * J + tok) * D;
-                float t[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) t[i] = (valid && i < shift) ? __ldg(lead + i) : 0.f;
-                head_acc<16>(head_x, t, Wres_lead, 16);
-                bufAt[row] = pack8_bf16(t);
-                bufAt[128 + row] = pack8_bf16(t + 8);
-            }
-            // ---- embedding: h = pos_emb[tok] + x W_emb^T + b_emb      (model.py:56, :88-89)
-            run_gemm(g++, bufA, C, C, ACC0, shift > 0, false);
-            for (int c0 = cb; c0 < cb + CW; c0 += CH) {
-                float a[CH], e[CH], bb[CH];
-                tmem_ld_nw<CH>(tmem + ACC0 + c0, a);
-                load_row<CH, true>(pos + tok * C + c0, e, valid);
-                load_row<CH, true>(bemb + c0, bb, true);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < CH; ++i) a[i] = valid ? a[i] + bb[i] + e[i] : 0.f;
-                tmem_st<CH>(tmem + RESID + c0, a);
-                store_chunks(bufA, c0, a, CH);
-            }
-            vec = bcls + 4;
-            stamp();
-        }
-
-        fine_on = (it == (p.cross ? 1 : 0));
-        fine();
-        load_vecs(vec, 10 * C);
-        fine();
-        vec += 10 * C;
-        const uint4* kv_src = is_cross ? bufV : bufA;     // K-major operand the K / V projections read
-        const int F = is_cross ? p.Fc : p.F;
-        const int act = is_cross ? 0 : 1;                 // relu | erf-gelu
-        const float eps = is_cross ? 1e-5f : 1e-12f;
-        // the fused encoder's residual() head accumulates over the cross layer's output (cross -> final_TR fusion);
-        // its feature columns sit behind [pos | bemb | lead] of the encoder block that follows this layer's vectors
-        const float* Wrf = (is_cross && p.L > 0) ? vec + (size_t)J * C + C + 48 : nullptr;
-
-        const float *bq = sVec, *bk = sVec + C, *bv = sVec + 2 * C, *bo = sVec + 3 * C, *g1 = sVec + 4 * C, *be1 = sVec + 5 * C,
-                    *b1 = sVec + 6 * C, *b2 = sVec + 7 * C, *g2 = sVec + 8 * C, *be2 = sVec + 9 * C;
-        // ---- Q, K, V projections (three weight tiles); each thread drains its CW columns
-        run_gemm(g++, bufA, C, C, ACC0, false, false);
-        drain_kmajor(ACC0, bq, qscale, bufQ);
-        run_gemm(g++, kv_src, C, C, ACC1, false, false);
-        drain_kmajor(ACC1, bk, 1.f, bufK);
-        run_gemm(g++, kv_src, C, C, ACC2, false, false);
-        {   // V: MN-major B operand for P V ([token][dim], dim contiguous)
-            float a[CW];
-            tmem_ld<CW>(tmem + ACC2 + cb, a);
-#pragma unroll
-            for (int i = 0; i < CW; ++i) a[i] += bv[cb + i];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) bufV[(row >> 3) * 128 + (cb / 8 + c) * 8 + (row & 7)] = pack8_bf16(a + 8 * c);
-            // P is block diagonal: zero the 12 chunks of this row outside its own 32-key block once per layer (the row's own
-            // block is overwritten by every head's P); bufA is free, its last readers were the projections above
-            for (int kc = cg; kc < 16; kc += CG)
-                if ((kc >> 2) != wq) bufA[kc * 128 + row] = make_uint4(0, 0, 0, 0);
-        }
-        stamp();
-        // ---- attention.  Column groups 0 / 1 own the softmax of heads pr / 2+pr of round pr (S in ACC0 / ACC1); the P V
-        //      MMAs take turns on bufA.
-#pragma unroll 1
-        for (int pr = 0; pr < 2; ++pr) {
-            sync_for_mma();
-            if (warp_u == 0) {
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t idS = umma_idesc_bf16(128, 128, false, false);
-                    umma_gemm(tmem0 + ACC0, smem_u32(bufQ) + pr * 4 * TS_LBO, TS_LBO, 128, smem_u32(bufK) + pr * 4 * TS_LBO, TS_LBO, 128, idS,
-                              32, false);
-                    umma_gemm(tmem0 + ACC1, smem_u32(bufQ) + (2 + pr) * 4 * TS_LBO, TS_LBO, 128, smem_u32(bufK) + (2 + pr) * 4 * TS_LBO,
-                              TS_LBO, 128, idS, 32, false);
-                    umma_commit(&mma_bar);
-                }
-                __syncwarp();
-            }
-            wait_mma();
-            fine();
-            // block-diagonal softmax: this row's keys are columns [32*wq, 32*wq + J) of its head's S
-            float pv[32];
-            if (cg < 2) {  // warp-uniform
-                tmem_ld<32>(tmem + (cg ? ACC1 : ACC0) + 32 * wq, pv);
-                float mx = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < J ? pv[i] : -INFINITY);
-                float sum = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    pv[i] = (valid && i < J) ? __expf(pv[i] - mx) : 0.f;
-                    sum += pv[i];
-                }
-                // P stays un-normalised; O_h is scaled when it is read out
-                sInv[(2 * cg + pr) * 128 + row] = valid ? 1.f / sum : 0.f;
-            }
-#pragma unroll 1
-            for (int hh = 0; hh < 2; ++hh) {
-                if (cg == hh) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) bufA[(4 * wq + c) * 128 + row] = pack8_bf16(pv + 8 * c);
-                }
+                // ---- DESA fusion conv: x = relu(W_fu [desa_0 | desa_1 | desa_2 | jf] + b_fu): four accumulating K = 128 GEMMs,
+                //      two operand buffers, two in flight
+                float v0[8], v1[8], v2[8], v3[8];
+                const float* dsrc = p.desa + ((size_t)b * 3 * J + t) * C + col0;
+                load8<true>(dsrc, v0, valid);
+                load8<true>(dsrc + (size_t)J * C, v1, valid);
+                load8<true>(dsrc + (size_t)2 * J * C, v2, valid);
+                load8<true>(p.jf + ((size_t)b * J + t) * C + col0, v3, valid);
+                store_rep(bufA, ck, pack8_bf16(v0));
+                store_rep(bufB, ck, pack8_bf16(v1));
                 sync_for_mma();
                 if (warp_u == 0) {
                     tc_fence_after();
+                    wait_w(g);
+                    wait_w(g + 1);
                     if (elect_one()) {
-                        const int h = 2 * hh + pr;  // O_h[128 x 32] = P V_h, V_h = N-slice [32h, 32h+32) of the MN-major buffer
-                        umma_gemm(tmem0 + ACC2 + 32 * h, smem_u32(bufA), TS_LBO, 128, smem_u32(bufV) + h * 4 * 128, 16 * 128, 128,
-                                  umma_idesc_bf16(128, 32, false, true), 128, false);
+                        const uint32_t id = umma_idesc_bf16(128, 128, false, false);
+                        umma_gemm(tmem0 + ACC0, smem_u32(bufA), TS_LBO, 128, wslot_of(g), TS_LBO, 128, id, C, false);
+                        umma_commit(&aux_bar);
+                        umma_gemm(tmem0 + ACC0, smem_u32(bufB), TS_LBO, 128, wslot_of(g + 1), TS_LBO, 128, id, C, true);
                         umma_commit(&mma_bar);
                     }
                     __syncwarp();
                 }
-                wait_mma();  // bufA is rewritten next
-                fine();
+                wait_aux();
+                after_gemm(g);
+                store_rep(bufA, ck, pack8_bf16(v2));
+                wait_mma();
+                after_gemm(g + 1);
+                store_rep(bufB, ck, pack8_bf16(v3));
+                sync_for_mma();
+                if (warp_u == 0) {
+                    tc_fence_after();
+                    wait_w(g + 2);
+                    wait_w(g + 3);
+                    if (elect_one()) {
+                        const uint32_t id = umma_idesc_bf16(128, 128, false, false);
+                        umma_gemm(tmem0 + ACC0, smem_u32(bufA), TS_LBO, 128, wslot_of(g + 2), TS_LBO, 128, id, C, true);
+                        umma_gemm(tmem0 + ACC0, smem_u32(bufB), TS_LBO, 128, wslot_of(g + 3), TS_LBO, 128, id, C, true);
+                        umma_commit(&mma_bar);
+                    }
+                    __syncwarp();
+                }
+                float bb[8];
+                load8<true>(bfu + col0, bb, true);
+                wait_mma();
+                after_gemm(g + 3);
+                g += 4;
+                float a[8];
+                tmem_ld<8>(tmem + ACC0 + col0, a);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = valid ? fmaxf(a[i] + bb[i], 0.f) : 0.f;
+                head_acc<8>(head_x, a, Wres_feat + col0, C);
+                store_rep(bufA, ck, pack8_bf16(a));
             }
-        }
-        stamp();
-        // ---- O -> bf16 A operand, scaled by the softmax sums of the head each column belongs to
-        {
-            float a[CW];
-            tmem_ld<CW>(tmem + ACC2 + cb, a);
-            constexpr int HS = CW < 32 ? CW : 32;
-#pragma unroll
-            for (int s0 = 0; s0 < CW; s0 += HS) {
-                const float inv = sInv[((cb + s0) >> 5) * 128 + row];
-#pragma unroll
-                for (int i = 0; i < HS; ++i) a[s0 + i] *= inv;
+            if (!p.pre && !p.cross) {
+                const float* xr = p.x + ((size_t)b * J + t) * D + shift + col0;
+                float v[8];
+                if ((D & 3) == 0 && shift == 0)
+                    load8<true>(xr, v, valid);
+                else
+                    load8<false>(xr, v, valid);
+                head_acc<8>(head_x, v, Wres_feat + col0, C);
+                store_rep(bufA, ck, pack8_bf16(v));
             }
+            if (shift > 0 && ck == 0) {  // leading (D - 128) inputs: joint coordinates (one thread per token)
+                const float* lead = p.cross ? p.r3d + ((size_t)b * J + t) * shift : p.x + ((size_t)b * J + t) * D;
+                float tl[16];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) bufA[(cb / 8 + c) * 128 + row] = pack8_bf16(a + 8 * c);
-        }
-        // ---- residual + LayerNorm on a 128-wide accumulator; the CG threads of a row exchange partial statistics
-        auto resid_ln = [&](uint32_t acc, const float* bias, const float* gam, const float* bet, const float* Wr) {
-            float y[CW];
-            float sum = 0.f, sq = 0.f;
-            {
-                float r[CW];
-                tmem_ld_nw<CW>(tmem + acc + cb, y);
-                tmem_ld_nw<CW>(tmem + RESID + cb, r);
-                tmem_wait_ld();
-                fine();
+                for (int i = 0; i < 16; ++i) tl[i] = (valid && i < shift) ? __ldg(lead + i) : 0.f;
+                head_acc<16>(head_x, tl, Wres_lead, 16);
+                const uint4 lo = pack8_bf16(tl), hi = pack8_bf16(tl + 8);
 #pragma unroll
-                for (int i = 0; i < CW; ++i) {
-                    y[i] += bias[cb + i] + r[i];
-                    sum += y[i];
-                    sq += y[i] * y[i];
+                for (int r = 0; r < 4; ++r) {
+                    bufAt[32 * r + t] = lo;
+                    bufAt[128 + 32 * r + t] = hi;
                 }
             }
-            float2* red = reinterpret_cast<float2*>(sRed) + red_par * (CG * 128);
+            // ---- embedding: h = pos_emb[tok] + x W_emb^T + b_emb      (model.py:56, :88-89)
+            sync_for_mma();
+            if (warp_u == 0) {
+                tc_fence_after();
+                wait_w(g);
+                if (shift > 0) mbar_wait(&tail_bar, 0);
+                if (elect_one()) {
+                    const uint32_t id = umma_idesc_bf16(128, 128, false, false);
+                    umma_gemm(tmem0 + ACC0, smem_u32(bufA), TS_LBO, 128, wslot_of(g), TS_LBO, 128, id, C, false);
+                    if (shift > 0) umma_gemm(tmem0 + ACC0, smem_u32(bufAt), TS_LBO, 128, smem_u32(wtail), TS_LBO, 128, id, 16, true);
+                    umma_commit(&mma_bar);
+                }
+                __syncwarp();
+            }
+            float e[8], bb[8];
+            load8<true>(pos + t * C + col0, e, valid);
+            load8<true>(bemb + col0, bb, true);
+            wait_mma();
+            after_gemm(g);
+            ++g;
+            float a[8];
+            tmem_ld<8>(tmem + ACC0 + col0, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = valid ? a[i] + bb[i] + e[i] : 0.f;
+            tmem_st_nw<8>(tmem + RESID + col0, a);
+            store_rep(bufA, ck, pack8_bf16(a));
+            tmem_wait_st();
+            stamp();
+        }
+
+        const float* sv = sVec + (it & 1) * TS_VEC;
+        const float *bq = sv, *bk = sv + C, *bv = sv + 2 * C, *bo = sv + 3 * C, *g1 = sv + 4 * C, *be1 = sv + 5 * C, *b1 = sv + 6 * C,
+                    *b2 = sv + 7 * C, *g2 = sv + 8 * C, *be2 = sv + 9 * C;
+        const uint4* kv_src = is_cross ? bufB : bufA;     // K-major operand the K / V projections read
+        const int F = is_cross ? p.Fc : p.F;
+        const int act = is_cross ? 0 : 1;                 // relu | erf-gelu
+        const float eps = is_cross ? 1e-5f : 1e-12f;
+        // the fused encoder's residual() head accumulates over the cross layer's output (cross -> final_TR fusion)
+        const float* Wrf = (is_cross && p.L > 0) ? Wres_feat : nullptr;
+
+        // ---- Q and K|V projections, issued back to back (weights g, g+1 = one N = 256 tile)
+        sync_for_mma();
+        if (warp_u == 0) {
+            tc_fence_after();
+            wait_w(g);
+            wait_w(g + 1);
+            if (elect_one()) {
+                if (it + 1 < n_layers) load_vec(it + 1);   // the other vector buffer was last read before the barrier above
+                umma_gemm(tmem0 + ACC0, smem_u32(bufA), TS_LBO, 128, wslot_of(g), TS_LBO, 128, umma_idesc_bf16(128, 128, false, false), C,
+                          false);
+                umma_commit(&aux_bar);
+                umma_gemm(tmem0 + ACC1, smem_u32(kv_src), TS_LBO, 128, wslot_of(g + 1), 256 * 16, 128, umma_idesc_bf16(128, 256, false, false),
+                          C, false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&vec_bar[it & 1], (it >> 1) & 1);       // this layer's vectors have landed
+        wait_aux();
+        after_gemm(g);
+        {   // Q -> head-major A operand of S: row 32q+t = head q of token t, chunk c = its dims [8c, 8c+8)
+            float a[8];
+            tmem_ld<8>(tmem + ACC0 + col0, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = (a[i] + bq[col0 + i]) * qscale;
+            bufQ[c * 128 + row] = pack8_bf16(a);
+        }
+        wait_mma();
+        after_gemm(g + 1);
+        float kv[16];
+        tmem_ld_nw<8>(tmem + ACC1 + col0, kv);
+        tmem_ld_nw<8>(tmem + ACC2 + col0, kv + 8);
+        tmem_wait_ld();
+        {   // K likewise, as the B operand of S
+#pragma unroll
+            for (int i = 0; i < 8; ++i) kv[i] += bk[col0 + i];
+            bufK[c * 128 + row] = pack8_bf16(kv);
+        }
+        stamp();
+        // ---- S for all four heads: D[32h+t][32h'+k] = Q_h[t] . K_h'[k]; the diagonal blocks h = h' are the scores
+        sync_for_mma();
+        if (warp_u == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                umma_gemm(tmem0 + ACC0, smem_u32(bufQ), TS_LBO, 128, smem_u32(bufK), TS_LBO, 128, umma_idesc_bf16(128, 128, false, false), 32,
+                          false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
+        }
+        {   // V -> MN-major B operand of P V (dims contiguous): key t, dims [32q+8c, +8); overlaps the S MMAs
+#pragma unroll
+            for (int i = 0; i < 8; ++i) kv[8 + i] += bv[col0 + i];
+            bufV[(t >> 3) * 128 + ck * 8 + (t & 7)] = pack8_bf16(kv + 8);
+        }
+        wait_mma();
+        {   // softmax of row t of head q: every column group takes the row maximum over all keys and exponentiates its 8 keys;
+            // P stays un-normalised, the partial sums meet when O is read out
+            float sa[32], own[8];
+            tmem_ld_nw<32>(tmem + ACC0 + 32 * q, sa);
+            tmem_ld_nw<8>(tmem + ACC0 + col0, own);
+            tmem_wait_ld();
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < J ? sa[i] : -INFINITY);
+            float psum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                own[i] = (valid && 8 * c + i < J) ? __expf(own[i] - mx) : 0.f;
+                psum += own[i];
+            }
+            sSum[c * 128 + row] = psum;
+            bufP[c * 128 + row] = pack8_bf16(own);
+        }
+        // ---- O for all four heads: D[32h+t][n] = P_h[t] . V[:, n]; columns [32h, 32h+32) are head h's output
+        sync_for_mma();
+        if (warp_u == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                umma_gemm(tmem0 + ACC1, smem_u32(bufP), TS_LBO, 128, smem_u32(bufV), 16 * 128, 128, umma_idesc_bf16(128, 128, false, true), 32,
+                          false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
+        }
+        float inv;
+        {
+            const float ssum = sSum[row] + sSum[128 + row] + sSum[256 + row] + sSum[384 + row];
+            inv = valid ? 1.f / ssum : 0.f;
+        }
+        wait_mma();
+        stamp();
+        {   // O -> replicated A operand of the output projection
+            float a[8];
+            tmem_ld<8>(tmem + ACC1 + col0, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] *= inv;
+            store_rep(bufA, ck, pack8_bf16(a));
+        }
+        // ---- residual + LayerNorm on a 128-wide accumulator; the 16 threads of a token exchange partial statistics
+        auto resid_ln = [&](uint32_t acc, const float* bias, const float* gam, const float* bet, const float* Wr) {
+            float y[8], r[8];
+            tmem_ld_nw<8>(tmem + acc + col0, y);
+            tmem_ld_nw<8>(tmem + RESID + col0, r);
+            tmem_wait_ld();
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                y[i] += bias[col0 + i] + r[i];
+                sum += y[i];
+                sq += y[i] * y[i];
+            }
+            float2* red = sRed + red_par * (16 * 32);
             red_par ^= 1;
-            red[cg * 128 + row] = make_float2(sum, sq);
-            fine();
+            red[ck * 32 + t] = make_float2(sum, sq);
             __syncthreads();
-            fine();
             sum = 0.f;
             sq = 0.f;
 #pragma unroll
-            for (int k = 0; k < CG; ++k) {   // same order in every thread of the row: identical statistics
-                const float2 t = red[k * 128 + row];
-                sum += t.x;
-                sq += t.y;
+            for (int k = 0; k < 16; ++k) {   // same order in every thread of the token: identical statistics in all replicas
+                const float2 u = red[k * 32 + t];
+                sum += u.x;
+                sq += u.y;
             }
             const float mean = sum * (1.f / C);
             const float rstd = rsqrtf(fmaxf(sq * (1.f / C) - mean * mean, 0.f) + eps);
 #pragma unroll
-            for (int i = 0; i < CW; ++i) y[i] = valid ? (y[i] - mean) * rstd * gam[cb + i] + bet[cb + i] : 0.f;
-            fine();
-            tmem_st_nw<CW>(tmem + RESID + cb, y);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) bufA[(cb / 8 + c) * 128 + row] = pack8_bf16(y + 8 * c);
-            if (Wr) head_acc<CW>(head_x, y, Wr + cb, C);
+            for (int i = 0; i < 8; ++i) y[i] = valid ? (y[i] - mean) * rstd * gam[col0 + i] + bet[col0 + i] : 0.f;
+            tmem_st_nw<8>(tmem + RESID + col0, y);
+            store_rep(bufA, ck, pack8_bf16(y));
+            if (Wr) head_acc<8>(head_x, y, Wr + col0, C);
             tmem_wait_st();
-            fine();
         };
-        run_gemm(g++, bufA, C, C, ACC0, false, false);
+        sync_for_mma();
+        if (warp_u == 0) {
+            tc_fence_after();
+            wait_w(g + 2);
+            if (elect_one()) {
+                umma_gemm(tmem0 + ACC0, smem_u32(bufA), TS_LBO, 128, wslot_of(g + 2), TS_LBO, 128, umma_idesc_bf16(128, 128, false, false), C,
+                          false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
+        }
+        wait_mma();
+        after_gemm(g + 2);
         resid_ln(ACC0, bo, g1, be1, nullptr);
         stamp();
-        // ---- FFN: hidden columns in TS_FU-wide pieces spread over the column groups
-        run_gemm(g++, bufA, F, C, ACC2, false, false);
-#pragma unroll 1
-        for (int c0 = TS_FU * cg; c0 < F; c0 += TS_FU * CG) {
-            float a[TS_FU];
-            tmem_ld<TS_FU>(tmem + ACC2 + c0, a);
-#pragma unroll
-            for (int i = 0; i < TS_FU; ++i) {
-                const float t = a[i] + b1[c0 + i];
-                a[i] = act == 1 ? gelu_erf(t) : fmaxf(t, 0.f);
+        // ---- FFN: hidden column(s) ck * F/16 ... of the token, written to the four row replicas of the hidden operand
+        sync_for_mma();
+        if (warp_u == 0) {
+            tc_fence_after();
+            wait_w(g + 3);
+            if (elect_one()) {
+                umma_gemm(tmem0 + ACC2, smem_u32(bufA), TS_LBO, 128, wslot_of(g + 3), (uint32_t)F * 16, 128, umma_idesc_bf16(128, F, false, false),
+                          C, false);
+                umma_commit(&mma_bar);
             }
-            unsigned char* dst = reinterpret_cast<unsigned char*>(bufQ + (c0 >> 3) * 128 + row) + (c0 & 7) * 2;
-            if constexpr (TS_FU == 8) {
-                *reinterpret_cast<uint4*>(dst) = pack8_bf16(a);
-            } else {
+            __syncwarp();
+        }
+        wait_mma();
+        after_gemm(g + 3);
+        {
+            const int fp = F >> 4;
+#pragma unroll 1
+            for (int i = 0; i < fp; ++i) {
+                const int col = ck * fp + i;
+                float a1[2];
+                tmem_ld<1>(tmem + ACC2 + col, a1);
+                const float u = a1[0] + b1[col];
+                const __nv_bfloat16 hv = __float2bfloat16(act == 1 ? gelu_erf(u) : fmaxf(u, 0.f));
 #pragma unroll
-                for (int i = 0; i < TS_FU; i += 2) {
-                    const __nv_bfloat162 t2 = __floats2bfloat162_rn(a[i], a[i + 1]);
-                    *reinterpret_cast<uint32_t*>(dst + 2 * i) = *reinterpret_cast<const uint32_t*>(&t2);
-                }
+                for (int r = 0; r < 4; ++r) reinterpret_cast<__nv_bfloat16*>(bufB + (col >> 3) * 128 + 32 * r + t)[col & 7] = hv;
             }
         }
-        run_gemm(g++, bufQ, C, F, ACC0, false, false);
+        sync_for_mma();
+        if (warp_u == 0) {
+            tc_fence_after();
+            wait_w(g + 4);
+            if (elect_one()) {
+                umma_gemm(tmem0 + ACC0, smem_u32(bufB), TS_LBO, 128, wslot_of(g + 4), TS_LBO, 128, umma_idesc_bf16(128, 128, false, false), F,
+                          false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
+        }
+        wait_mma();
+        after_gemm(g + 4);
         resid_ln(ACC0, b2, g2, be2, Wrf);
+        g += 5;
         stamp();
     }
 
     if (p.cross && p.L == 0) {
-        for (int c0 = cb; c0 < cb + CW; c0 += CH) {
-            float a[CH];
-            tmem_ld<CH>(tmem + RESID + c0, a);
-            if (valid) {
+        float a[8];
+        tmem_ld<8>(tmem + RESID + col0, a);
+        if (valid) {
 #pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    if (p.out_cj) p.out_cj[((size_t)b * C + c0 + i) * J + tok] = a[i];
-                    if (p.out_jc) p.out_jc[((size_t)b * J + tok) * p.out_jc_stride + p.out_jc_c0 + c0 + i] = a[i];
-                }
+            for (int i = 0; i < 8; ++i) {
+                if (p.out_cj) p.out_cj[((size_t)b * C + col0 + i) * J + t] = a[i];
+                if (p.out_jc) p.out_jc[((size_t)b * J + t) * p.out_jc_stride + p.out_jc_c0 + col0 + i] = a[i];
             }
         }
     }
     if (p.L > 0) {
-        // ---- regression head: pred = cls_head(h) + residual(x)   (model.py:122-124), fp32, CG threads per row
+        // ---- regression head: pred = cls_head(h) + residual(x)   (model.py:122-124), fp32, 16 threads per token
         float pr3[3] = {head_x[0], head_x[1], head_x[2]};
-        for (int c0 = cb; c0 < cb + CW; c0 += CH) {
-            float a[CH];
-            tmem_ld<CH>(tmem + RESID + c0, a);
-            head_acc<CH>(pr3, a, Wcls + c0, C);
-            if (valid && p.tokens_out) {
-                float4* o = reinterpret_cast<float4*>(p.tokens_out + ((size_t)b * J + tok) * C + c0);
-#pragma unroll
-                for (int i = 0; i < CH / 4; ++i) o[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-            }
+        float a[8];
+        tmem_ld<8>(tmem + RESID + col0, a);
+        head_acc<8>(pr3, a, Wcls + col0, C);
+        if (valid && p.tokens_out) {
+            float4* o = reinterpret_cast<float4*>(p.tokens_out + ((size_t)b * J + t) * C + col0);
+            o[0] = make_float4(a[0], a[1], a[2], a[3]);
+            o[1] = make_float4(a[4], a[5], a[6], a[7]);
         }
         __syncthreads();
-        float* red3 = sRed;   // [CG][128][3]
-        red3[(cg * 128 + row) * 3] = pr3[0];
-        red3[(cg * 128 + row) * 3 + 1] = pr3[1];
-        red3[(cg * 128 + row) * 3 + 2] = pr3[2];
+        float* red3 = reinterpret_cast<float*>(sRed);   // [16][32][3]
+        red3[(ck * 32 + t) * 3] = pr3[0];
+        red3[(ck * 32 + t) * 3 + 1] = pr3[1];
+        red3[(ck * 32 + t) * 3 + 2] = pr3[2];
         __syncthreads();
-        if (cg == 0 && valid && p.pred_out) {
+        if (ck == 0 && valid && p.pred_out) {
             float o3[3] = {bres[0] + bcls[0], bres[1] + bcls[1], bres[2] + bcls[2]};
 #pragma unroll
-            for (int k = 0; k < CG; ++k) {
-                o3[0] += red3[(k * 128 + row) * 3];
-                o3[1] += red3[(k * 128 + row) * 3 + 1];
-                o3[2] += red3[(k * 128 + row) * 3 + 2];
+            for (int k = 0; k < 16; ++k) {
+                o3[0] += red3[(k * 32 + t) * 3];
+                o3[1] += red3[(k * 32 + t) * 3 + 1];
+                o3[2] += red3[(k * 32 + t) * 3 + 2];
             }
-            float* o = p.pred_out + ((size_t)b * J + tok) * 3;
+            float* o = p.pred_out + ((size_t)b * J + t) * 3;
             o[0] = o3[0];
             o[1] = o3[1];
             o[2] = o3[2];
@@ -568,8 +616,8 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
     if (tid < 32) tmem_dealloc(tmem0, 512);
 }
 
-constexpr size_t TS_SMEM = (size_t)(2 * TS_SLOT + 256 + 2048 + 256 + 3 * 2048) * 16 + (10 * TS_C + 4 * TS_C + 2 * TS_CG * 128 * 2) * 4;
-static_assert(2 * TS_CG * 128 * 2 >= TS_CG * 128 * 3, "head reduction reuses the LayerNorm exchange buffer");
+constexpr size_t TS_SMEM = (size_t)(3 * TS_SLOT + 2 * 2048 + 4 * 512 + 2 * 256) * 16 + (size_t)(2 * TS_VEC) * 4 + 2 * 16 * 32 * 8 + 4 * 128 * 4;
+static_assert(2 * 16 * 32 * 8 >= 16 * 32 * 3 * 4, "head reduction reuses the LayerNorm exchange buffer");
 
 }  // namespace kpf
 
@@ -585,16 +633,16 @@ extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d,
     KPF_REQUIRE(!pre || (desa != nullptr && jf != nullptr && !cross && D == TS_C));
     KPF_REQUIRE(!(cross && L > 0) || (r3d != nullptr && D > TS_C));
     KPF_REQUIRE(n_weights <= TS_MAXG);
-    KPF_REQUIRE(n_weights == (cross ? 6 : 0) + (pre ? 4 : 0) + (L > 0 ? 1 + 6 * L : 0));
-    KPF_REQUIRE(((uintptr_t)wmat % 16) == 0 && ((uintptr_t)wseq % 8) == 0);
+    KPF_REQUIRE(n_weights == (cross ? 5 : 0) + (pre ? 4 : 0) + (L > 0 ? 1 + 5 * L : 0));
+    KPF_REQUIRE(((uintptr_t)wmat % 16) == 0 && ((uintptr_t)wseq % 16) == 0);
     if (B == 0) return 0;
     TokParams p;
-    p.x = x; p.y = y; p.r3d = r3d; p.desa = desa; p.jf = jf; p.wmat = (const uint4*)wmat; p.wseq = (const int2*)wseq; p.wvec = wvec;
+    p.x = x; p.y = y; p.r3d = r3d; p.desa = desa; p.jf = jf; p.wmat = (const uint4*)wmat; p.wseq = (const int4*)wseq; p.wvec = wvec;
     p.tokens_out = tokens_out; p.pred_out = pred_out; p.out_cj = out_cj; p.out_jc = out_jc; p.out_jc_stride = out_jc_stride;
     p.out_jc_c0 = out_jc_c0; p.B = B; p.J = J; p.D = D; p.L = L; p.F = F; p.pre = pre; p.cross = cross; p.Fc = Fc; p.G = n_weights; p.dbg = dbg;
     cudaError_t e = kpf::set_smem(token_stack_kernel, TS_SMEM);
     if (e != cudaSuccess) return (int)e;
-    token_stack_kernel<<<(B + 3) / 4, TS_NT, TS_SMEM, stream>>>(p);
+    token_stack_kernel<<<B, TS_NT, TS_SMEM, stream>>>(p);
     KPF_CHECK_LAUNCH();
     return 0;
 }

@@ -348,31 +348,46 @@ class TokenProgram:
 
 def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
     """enc = (state_dict, prefix) of a KP_Interaction_TR; cross = (state_dict, prefix) of one TransformerDecoderLayer;
-    fusion = (W [128,512], b [128]) BN-folded DESA fusion conv.  Weight order = consumption order of csrc/token_stack.cu."""
-    mats, seq, vecs, off = [], [], [], 0
+    fusion = (W [128,512], b [128]) BN-folded DESA fusion conv.  Weight order = consumption order of csrc/token_stack.cu.
 
-    def add(m, in_seq=True):
+    wseq row g = (source offset, count, destination offset inside the three 32 KB shared-memory slots) in 16-byte units and
+    the index of the GEMM whose completion frees that destination (-1: free from the start)."""
+    SLOT = 2048
+    mats, seq, vecs, off = [], [], [], 0
+    last_user = [-1, -1, -1]
+
+    def add(m, slots=None):
         nonlocal off
         n = m.numel() // 8
-        if in_seq:
-            seq.append((off, n))
+        if slots is not None:
+            assert n <= SLOT * len(slots)
+            g_ = len(seq)
+            seq.append((off, n, slots[0] * SLOT, max(last_user[s_] for s_ in slots)))
+            for s_ in slots:
+                last_user[s_] = g_
         mats.append(m)
         off += n
+
+    def add_layer(Wq, Wk, Wv, Wo, W1, W2):
+        add(_canon(Wq), (0,))
+        add(_canon(torch.cat([Wk, Wv], 0)), (1, 2))     # one N = 256 tile
+        add(_canon(Wo), (0,))
+        add(_canon(W1), (1,))
+        add(_canon(W2), (2,))
     Fc = D = L = F_ = 0
     if cross is not None:
         sd, pf = cross
         g = lambda k: sd[pf + k].detach().float()
         Wi, bi = g("multihead_attn.in_proj_weight"), g("multihead_attn.in_proj_bias")
         Fc = g("linear1.weight").shape[0]
-        for m in (Wi[:C], Wi[C:2 * C], Wi[2 * C:], g("multihead_attn.out_proj.weight"), g("linear1.weight"), g("linear2.weight")):
-            add(_canon(m))
+        add_layer(Wi[:C], Wi[C:2 * C], Wi[2 * C:], g("multihead_attn.out_proj.weight"), g("linear1.weight"), g("linear2.weight"))
         vecs += [g("self_posembed.weight")[:J].reshape(-1), g("cross_posembed.weight")[:J].reshape(-1), bi[:C], bi[C:2 * C], bi[2 * C:],
                  g("multihead_attn.out_proj.bias"), g("norm2.weight"), g("norm2.bias"), _pad(g("linear1.bias"), C), g("linear2.bias"),
                  g("norm3.weight"), g("norm3.bias")]
     if fusion is not None:
         Wfu, bfu = fusion
         for s_ in range(4):
-            add(_canon(Wfu.detach().float()[:, C * s_:C * (s_ + 1)]))
+            add(_canon(Wfu.detach().float()[:, C * s_:C * (s_ + 1)]), (s_ % 3,))
         vecs.append(bfu.detach().float())
     if enc is not None:
         sd, pf = enc
@@ -380,11 +395,11 @@ def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
         Wemb = g("bert.img_embedding.weight")
         D = Wemb.shape[1]
         shift = D - C
-        add(_canon(Wemb[:, shift:]))
+        add(_canon(Wemb[:, shift:]), (1,))
         if shift > 0:
             T = Wemb.new_zeros(C, 16)
             T[:, :shift] = Wemb[:, :shift]
-            add(_canon(T), in_seq=False)   # K-tail sits right behind the main part
+            add(_canon(T))   # K-tail sits right behind the main part, outside the sequence
         Wres = g("residual.weight")                       # [3, D] -> 16-byte aligned rows: [3][16] lead (zero padded) | [3][128] features
         lead = Wres.new_zeros(3, 16)
         lead[:, :shift] = Wres[:, :shift]
@@ -393,9 +408,8 @@ def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
         while f"{pf}bert.encoder.layer.{L}.attention.self.query.weight" in sd:
             lp = f"bert.encoder.layer.{L}."
             F_ = g(lp + "intermediate.dense.weight").shape[0]
-            for k_ in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense",
-                       "intermediate.dense", "output.dense"):
-                add(_canon(g(lp + k_ + ".weight")))
+            add_layer(*(g(lp + k_ + ".weight") for k_ in ("attention.self.query", "attention.self.key", "attention.self.value",
+                                                          "attention.output.dense", "intermediate.dense", "output.dense")))
             vecs += [g(lp + "attention.self.query.bias"), g(lp + "attention.self.key.bias"), g(lp + "attention.self.value.bias"),
                      g(lp + "attention.output.dense.bias"), g(lp + "attention.output.LayerNorm.weight"),
                      g(lp + "attention.output.LayerNorm.bias"), _pad(g(lp + "intermediate.dense.bias"), C), g(lp + "output.dense.bias"),
