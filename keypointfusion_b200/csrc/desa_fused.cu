@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp_u = warp_index_uniform();  // MMA issue: one elected lane of warp 0 from warp-uniform code (umma.cuh)
     const int b = blockIdx.x / p.S, sc = blockIdx.x - b * p.S;
     const int J = p.J, N = p.N, T = p.T, NS = p.nsample;
     const float radius = p.radius[sc];
@@ -124,11 +125,14 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {
         tc_fence_after();
         mbar_wait(&wbar[0], 0);
-        umma_gemm(tmem0 + ACCE, smem_u32(sX), 2048, 128, smem_u32(sH), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, false);
-        umma_commit(&mma_bar);
+        if (elect_one()) {
+            umma_gemm(tmem0 + ACCE, smem_u32(sX), 2048, 128, smem_u32(sH), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, false);
+            umma_commit(&mma_bar);
+        }
+        __syncwarp();
     }
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
     const float inv_r = 1.f / radius;
     __syncthreads();  // sJF, sIdx ready; the joint-embedding MMA (reader of sX, sH) has completed
     stamp();
-    if (tid == 0) mbar_wait(&wbar[1], 0);
+    if (warp_u == 0) mbar_wait(&wbar[1], 0);
 
     const int JPT = 128 / NS;  // joints per tile (2 for nsample = 64)
     stamp();
@@ -288,11 +292,14 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
         tc_fence_before();
         __syncthreads();
         const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
-            umma_gemm(tmem0 + ACC1, smem_u32(sW1), 2048, 128, smem_u32(sX), 2048, 128, id128, 128, false);
-            umma_gemm(tmem0 + ACC1, smem_u32(sW1t), 2048, 128, smem_u32(sXt), 2048, 128, id128, 16, true);
-            umma_commit(&mma_bar);
+            if (elect_one()) {
+                umma_gemm(tmem0 + ACC1, smem_u32(sW1), 2048, 128, smem_u32(sX), 2048, 128, id128, 128, false);
+                umma_gemm(tmem0 + ACC1, smem_u32(sW1t), 2048, 128, smem_u32(sXt), 2048, 128, id128, 16, true);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
@@ -310,10 +317,13 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
-            umma_gemm(tmem0 + ACC2, smem_u32(sW2), 2048, 128, smem_u32(sH), 2048, 128, umma_idesc_bf16(128, 128, false, true), 128, false);
-            umma_commit(&mma_bar);
+            if (elect_one()) {
+                umma_gemm(tmem0 + ACC2, smem_u32(sW2), 2048, 128, smem_u32(sH), 2048, 128, umma_idesc_bf16(128, 128, false, true), 128, false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(&mma_bar, phase);
         phase ^= 1;

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
     __shared__ __align__(8) uint64_t wbar, mma_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp_u = warp_index_uniform();  // MMA issue: one elected lane of warp 0 from warp-uniform code (umma.cuh)
     const int J = p.J, N = p.N, T = N / 128;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
@@ -187,14 +188,17 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
             if (!w_ready) mbar_wait(&wbar, 0);
-            const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
-            umma_gemm(tmem0 + ACC1, smem_u32(sA1), 2048, 128, smem_u32(sW), 2048, 128, id128, 128, false);
-            umma_gemm(tmem0 + ACC1, smem_u32(sA1 + 2048), 2048, 128, smem_u32(sW + 2048), 2048, 128, id128, 128, true);
-            umma_gemm(tmem0 + ACC2, smem_u32(sA2), 2048, 128, smem_u32(sW + 4096), 2048, 128, id128, 128, false);
-            umma_commit(&mma_bar);
+            if (elect_one()) {
+                const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
+                umma_gemm(tmem0 + ACC1, smem_u32(sA1), 2048, 128, smem_u32(sW), 2048, 128, id128, 128, false);
+                umma_gemm(tmem0 + ACC1, smem_u32(sA1 + 2048), 2048, 128, smem_u32(sW + 2048), 2048, 128, id128, 128, true);
+                umma_gemm(tmem0 + ACC2, smem_u32(sA2), 2048, 128, smem_u32(sW + 4096), 2048, 128, id128, 128, false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
         }
         w_ready = true;
         // ---- softmax numerators over this tile's points while the MMAs run: per joint max / exp / sum across 128 threads
@@ -263,10 +267,13 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
-            umma_gemm(tmem0 + ACC3, smem_u32(sA2), 2048, 128, smem_u32(sA1), 512, 128, umma_idesc_bf16(128, 32, true, true), 128, false);
-            umma_commit(&mma_bar);
+            if (elect_one()) {
+                umma_gemm(tmem0 + ACC3, smem_u32(sA2), 2048, 128, smem_u32(sA1), 512, 128, umma_idesc_bf16(128, 32, true, true), 128, false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(&mma_bar, phase);
         phase ^= 1;

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
     __shared__ uint32_t tmem_slot;
     __shared__ CamF cam;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int warp_u = warp_index_uniform();  // MMA issue: one elected lane of warp 0 from warp-uniform code (umma.cuh)
     const int b = blockIdx.x / p.split, sp = blockIdx.x - b * p.split, J = p.J, fs = p.fs, HW = fs * fs, T = HW / 128;
     const int t_begin = sp * (T / p.split), t_end = t_begin + T / p.split;
     __shared__ int s_last;
@@ -147,12 +148,16 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
-            // GEMM A: A = F tile MN-major (LBO 2048 between channel groups, SBO 128 between cell groups)
-            umma_gemm(tmem0 + ACC1, smem_u32(cur), 2048, 128, smem_u32(sWa), 512, 128, umma_idesc_bf16(128, 32, true, false), 128, false);
-            umma_gemm(tmem0 + ACC1, smem_u32(sHm), 2048, 128, smem_u32(sWa + 512), 512, 128, umma_idesc_bf16(128, 32, false, false), 32, true);
-            umma_commit(&mma_bar);
+            if (elect_one()) {
+                // GEMM A: A = F tile MN-major (LBO 2048 between channel groups, SBO 128 between cell groups)
+                umma_gemm(tmem0 + ACC1, smem_u32(cur), 2048, 128, smem_u32(sWa), 512, 128, umma_idesc_bf16(128, 32, true, false), 128, false);
+                umma_gemm(tmem0 + ACC1, smem_u32(sHm), 2048, 128, smem_u32(sWa + 512), 512, 128, umma_idesc_bf16(128, 32, false, false), 32,
+                          true);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
@@ -179,11 +184,15 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
-            // GEMM B: A = relu(F) tile read K-major (K = cells): LBO 128 between cell groups, SBO 2048 between channel groups
-            umma_gemm(tmem0 + ACC2, smem_u32(sFr), 128, 2048, smem_u32(sG), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, t > t_begin);
-            umma_commit(&mma_bar);
+            if (elect_one()) {
+                // GEMM B: A = relu(F) tile read K-major (K = cells): LBO 128 between cell groups, SBO 2048 between channel groups
+                umma_gemm(tmem0 + ACC2, smem_u32(sFr), 128, 2048, smem_u32(sG), 512, 128, umma_idesc_bf16(128, 32, false, true), 128,
+                          t > t_begin);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(&mma_bar, phase);  // sFr / sG / sHm are rewritten by the next tile
         phase ^= 1;
