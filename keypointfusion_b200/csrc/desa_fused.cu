@@ -1,15 +1,20 @@
-// DESA on tensor cores (model/model.py:129-204 + the joint embeddings :323-325), SURVEY.md 8f-1.
-// One CTA per (sample, scale); thread c owns OUTPUT CHANNEL c (TMEM lane c), so every GEMM is computed transposed --
-// D[c][row] = sum_k W[c][k] X[row][k] with the (BatchNorm-folded) weight as the M=128 A operand and the activations as the
-// N operand -- which turns DESA's max-pool over the 64 grouped points of a joint into a per-thread register reduction.
+// DESA on tensor cores (model/model.py:129-204 + the joint embeddings :323-325), SURVEY.md 8f-1.  Two kernels:
 //
-//   prologue  combine the point stage's softmax partials (flash-style) -> joint_agg[J][128]
+// desa_prep_kernel   one CTA per sample, 512 threads:
+//             combine the point stage's softmax partials (flash-style) -> joint_agg[J][128]
 //             jf = relu(Wj [joint_agg | joint_xyz] + b)                     (model.py:323-325)   tcgen05 + fp32 xyz term
-//             ball query (pointnet2_ops semantics) of the J joints over the N points + the J joints themselves
-//   per tile  (2 joints x 64 grouped points = 128 rows):
-//             X = [feat[idx] - jf[j] | (xyz[idx] - c_j)/r]  ->  h = relu(W1 X + b1)  ->  relu(W2 h + b2)  -> max over 64
-//   output    desa_part[b][scale][j][:]  (+ jf[b][j][:] from the scale-0 CTA); the 512->128 fusion conv follows.
-#include "umma.cuh"
+//             ball query (pointnet2_ops semantics) of the J joints over the N points + the J joints themselves, all S radii in
+//             one pass over the distances -> idx[b][scale][j][nsample]
+// desa_tile_kernel   persistent, one CTA per SM, 512 threads.  Work item = (scale, sample, tile of 128/nsample joints); every
+//             CTA takes a contiguous, scale-major range so the scale's weights stay resident:
+//             X = [feat[idx] - jf[j] | (xyz[idx] - c_j)/r]  ->  h = relu(W1 X + b1)  ->  relu(W2 h + b2)  -> max over nsample
+//             Both GEMMs are computed transposed -- D[c][row] = sum_k W[c][k] X[row][k], weight = M=128 A operand, activations =
+//             N operand -- so thread (lane quarter, column group) owns OUTPUT CHANNEL c and DESA's max-pool over the grouped
+//             points of a joint is a per-thread register reduction.  Software pipeline per iteration s: GEMM2(s) and GEMM1(s+1)
+//             are issued together; while they run the threads write X(s+2) (rows prefetched one iteration earlier, indices two);
+//             then epilogue 2 of s and epilogue 1 of s+1.  One __syncthreads per tile.
+//   output    desa_part[b][scale][j][:], jf[b][j][:]; the 512->128 fusion conv follows in kpf_token_stack.
+#include "tmem_ldst.cuh"
 
 namespace kpf {
 
@@ -23,69 +28,56 @@ struct DesaParams {
     const float* wvec;        // bj[128], Wjx[128][4] ; per scale: b1[128], b2[128]
     float* desa_part;         // [B,S,J,128]
     float* jf_out;            // [B,J,128]
+    float* ctx;               // scratch [B][J*128 + 128]: jf (fp32) | joint xyz padded to [32][4]
+    uint16_t* idx;            // scratch [B,S,J,nsample] ball-query indices (>= N: one of the joints)
     int B, N, J, T, S, nsample;
     float radius[4];
     long long* dbg;
 };
 
+constexpr int DS_NT = 512;
 constexpr int DS_MAT_PER_SCALE = 2048 + 256 + 2048;
+constexpr int DS_XBUF = 2048 + 256;   // uint4 per activation buffer (main + K tail)
 
-__global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) {
+// ================================================================================================ prep
+__global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p) {
     extern __shared__ __align__(128) unsigned char ds_smem[];
-    uint4* sW1 = reinterpret_cast<uint4*>(ds_smem);   // [16][128] + tail [2][128]
-    uint4* sW1t = sW1 + 2048;
-    uint4* sW2 = sW1t + 256;                           // [16][128]
-    uint4* sX = sW2 + 2048;                            // [16][128] K-major activations; prologue: Wj
-    uint4* sXt = sX + 2048;                            // [2][128]
-    uint4* sH = sXt + 256;                             // MN-major [16][16][8]; prologue: joint_agg operand [16][4][8]
-    float4* sPcl = reinterpret_cast<float4*>(sH + 2048);   // [N + J] xyz
-    float* sJF = reinterpret_cast<float*>(sPcl + (p.N + p.J + 3) / 4 * 4);  // [J][128] fp32 joint features
-    float* sOut = sJF + p.J * 128;                     // [J][128]
-    float* sMS = sOut + p.J * 128;                     // [T][2][32] partial max/sum, then [T][32] scale factors + den[32]
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sMS + p.T * 64 + 64);  // [J][(N+J+31)/32] ball-query hit words (bit = point)
-    uint16_t* sIdx = reinterpret_cast<uint16_t*>(sMask + ((p.J * ((p.N + p.J + 31) / 32) + 3) / 4 * 4));  // [J][nsample]
-    __shared__ __align__(8) uint64_t wbar[2], mma_bar;
+    uint4* sWj = reinterpret_cast<uint4*>(ds_smem);             // [16][128] K-major A operand
+    uint4* sAgg = sWj + 2048;                                    // MN-major B operand [16][4][8]: joint_agg[channel][joint]
+    float4* sPcl = reinterpret_cast<float4*>(sAgg + 512);        // [N + J] xyz
+    float* sMS = reinterpret_cast<float*>(sPcl + (p.N + p.J + 3) / 4 * 4);  // [T][2][32] partial max/sum -> [T][32] factors + den[32]
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sMS + p.T * 64 + 64);    // [S][J][NW] ball-query hit words (bit = point)
+    __shared__ __align__(8) uint64_t wbar, mma_bar;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int warp_u = warp_index_uniform();  // MMA issue: one elected lane of warp 0 from warp-uniform code (umma.cuh)
-    const int b = blockIdx.x / p.S, sc = blockIdx.x - b * p.S;
-    const int J = p.J, N = p.N, T = p.T, NS = p.nsample;
-    const float radius = p.radius[sc];
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const uint32_t ACCE = 0, ACC1 = 128, ACC2 = 256;
+    const int warp_u = warp_index_uniform();
+    const int b = blockIdx.x;
+    const int J = p.J, N = p.N, T = p.T, NS = p.nsample, S = p.S;
     int n_stamp = 0;
     auto stamp = [&]() {
-        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 64) p.dbg[n_stamp] = clock64();
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 16) p.dbg[n_stamp] = clock64();
         ++n_stamp;
     };
     stamp();
-
-    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (warp == 0) tmem_alloc(&tmem_slot, 32);
     if (tid == 0) {
-        mbar_init(&wbar[0], 1);
-        mbar_init(&wbar[1], 1);
+        mbar_init(&wbar, 1);
         mbar_init(&mma_bar, 1);
         fence_mbar_init();
-        mbar_expect_tx(&wbar[0], 2048 * 16);                      // Wj -> sX
-        tma_bulk_g2s(sX, p.wmat, 2048 * 16, &wbar[0]);
-        const uint4* ws = p.wmat + 2048 + (size_t)sc * DS_MAT_PER_SCALE;
-        mbar_expect_tx(&wbar[1], DS_MAT_PER_SCALE * 16);          // W1 (+tail), W2 of this scale
-        tma_bulk_g2s(sW1, ws, (2048 + 256) * 16, &wbar[1]);
-        tma_bulk_g2s(sW2, ws + 2048 + 256, 2048 * 16, &wbar[1]);
+        mbar_expect_tx(&wbar, 2048 * 16);
+        tma_bulk_g2s(sWj, p.wmat, 2048 * 16, &wbar);
     }
     // ---- stage xyz of the point set (N points + J joints) and the partial (max, sum) table
-    for (int i = tid; i < N + J; i += 128) {
+    for (int i = tid; i < N + J; i += DS_NT) {
         const float* s = i < N ? p.pcl + ((size_t)b * N + i) * 3 : p.joint + ((size_t)b * J + (i - N)) * 3;
         sPcl[i] = make_float4(s[0], s[1], s[2], 0.f);
     }
-    for (int i = tid; i < T * 64; i += 128) sMS[i] = p.part_ms[(size_t)b * T * 64 + i];
+    for (int i = tid; i < T * 64; i += DS_NT) sMS[i] = p.part_ms[(size_t)b * T * 64 + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem0 = tmem_slot, tmem = tmem0 + lane_off;
-    uint32_t phase = 0;
-    stamp();
+    const uint32_t tmem0 = tmem_slot;
     // scale factors exp(m_t - m) and the softmax denominator, per joint
     if (tid < 32) {
         float m = -INFINITY;
@@ -99,278 +91,415 @@ __global__ void __launch_bounds__(128, 1) desa_fused_kernel(const DesaParams p) 
         sMS[T * 64 + tid] = den;
     }
     __syncthreads();
-    // ---- joint_agg[c = tid][j] (softmax over all N points of the gathered weight map, model.py:319-320)
+    stamp();
+    // ---- joint_agg[c][j] (softmax over all N points of the gathered weight map, model.py:319-320): thread = (channel, 8 joints)
     {
-        float agg[32];
+        const int ch = tid & 127, jg = tid >> 7;
+        float agg[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) agg[j] = 0.f;
+        for (int j = 0; j < 8; ++j) agg[j] = 0.f;
 #pragma unroll 4
         for (int t = 0; t < T; ++t) {
-            const float4* a = reinterpret_cast<const float4*>(p.part_acc + (((size_t)b * T + t) * 128 + tid) * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 v = __ldg(a + q);
-                agg[4 * q] += v.x * sMS[t * 64 + 4 * q];
-                agg[4 * q + 1] += v.y * sMS[t * 64 + 4 * q + 1];
-                agg[4 * q + 2] += v.z * sMS[t * 64 + 4 * q + 2];
-                agg[4 * q + 3] += v.w * sMS[t * 64 + 4 * q + 3];
-            }
+            const float4* a = reinterpret_cast<const float4*>(p.part_acc + (((size_t)b * T + t) * 128 + ch) * 32 + 8 * jg);
+            const float4 v0 = __ldg(a), v1 = __ldg(a + 1);
+            const float* f = sMS + t * 64 + 8 * jg;
+            agg[0] += v0.x * f[0];
+            agg[1] += v0.y * f[1];
+            agg[2] += v0.z * f[2];
+            agg[3] += v0.w * f[3];
+            agg[4] += v1.x * f[4];
+            agg[5] += v1.y * f[5];
+            agg[6] += v1.z * f[6];
+            agg[7] += v1.w * f[7];
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) agg[j] = j < J ? agg[j] / sMS[T * 64 + j] : 0.f;
-        // B operand, MN-major [K = 128 channels][N = 32 joints]: thread k = tid writes its 32 joints
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sH[(tid >> 3) * 32 + c * 8 + (tid & 7)] = pack8_bf16(agg + 8 * c);
+        for (int j = 0; j < 8; ++j) agg[j] = (8 * jg + j) < J ? agg[j] / sMS[T * 64 + 8 * jg + j] : 0.f;
+        sAgg[(ch >> 3) * 32 + jg * 8 + (ch & 7)] = pack8_bf16(agg);   // (k = channel, n = joint), n contiguous
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (warp_u == 0) {
         tc_fence_after();
-        mbar_wait(&wbar[0], 0);
+        mbar_wait(&wbar, 0);
         if (elect_one()) {
-            umma_gemm(tmem0 + ACCE, smem_u32(sX), 2048, 128, smem_u32(sH), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, false);
+            umma_gemm(tmem0, smem_u32(sWj), 2048, 128, smem_u32(sAgg), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, false);
             umma_commit(&mma_bar);
         }
         __syncwarp();
     }
-    mbar_wait(&mma_bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    {
-        float d[32];
-        tmem_ld32(tmem + ACCE, d);
-        const float bj = p.wvec[tid];
-        const float4 wx = *reinterpret_cast<const float4*>(p.wvec + 128 + 4 * tid);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < J) {
-                const float4 q = sPcl[N + j];
-                const float v = fmaxf(d[j] + bj + wx.x * q.x + wx.y * q.y + wx.z * q.z, 0.f);
-                sJF[j * 128 + tid] = v;
-                if (sc == 0 && p.jf_out) p.jf_out[((size_t)b * J + j) * 128 + tid] = v;
-            }
-        }
-    }
     stamp();
-    // ---- ball query (pointnet2_ops: first NS hits in index order, pad with the first hit).
-    // Phase 1: one thread per point tests all J centres (exact fp32 op order) -> hit bit mask per point.
-    // Phase 2: one warp per centre compacts the set bits in index order with ballots (no arithmetic in the serial loop).
+    // ---- ball query phase 1 (overlaps the MMA): one thread per point tests all J centres (exact fp32 op order) against the S
+    // radii.  A warp's 32 lanes hold 32 CONSECUTIVE points, so one ballot per (scale, centre, point group) IS the hit word.
+    const int NW = (N + J + 31) / 32;
     {
-        const float r2 = xmul(radius, radius);
-        const int NW = (N + J + 31) / 32;   // hit words per centre
-        // Phase 1: rounds of 8 points per thread held in registers; centres stream through (one LDS.128 per centre per round).
-        // A warp's 32 lanes hold 32 CONSECUTIVE points, so one ballot per (centre, point group) IS the transposed hit word.
-        for (int base = 0; base < N + J; base += 128 * 8) {
-            float4 q[8];
+        float r2[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int n = base + u * 128 + tid;
-                q[u] = n < N + J ? sPcl[n] : make_float4(1e30f, 1e30f, 1e30f, 0.f);
-            }
+        for (int s = 0; s < 4; ++s) r2[s] = xmul(p.radius[s], p.radius[s]);
+        for (int base = 0; base < N + J; base += DS_NT) {
+            const int n = base + tid;
+            const float4 q = n < N + J ? sPcl[n] : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+            const int wi = (base >> 5) + warp;
             for (int j = 0; j < J; ++j) {
                 const float4 c = sPcl[N + j];
+                const float dx = xsub(c.x, q.x), dy = xsub(c.y, q.y), dz = xsub(c.z, q.z);
+                const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const float dx = xsub(c.x, q[u].x), dy = xsub(c.y, q[u].y), dz = xsub(c.z, q[u].z);
-                    const bool hit = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz)) < r2;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                    const int wi = (base + u * 128) / 32 + warp;
-                    if (lane == 0 && wi < NW) sMask[j * NW + wi] = bal;
-                }
-            }
-        }
-        __syncthreads();
-        stamp();
-        // Phase 2: one warp per centre: popcount prefix over its hit words, then every lane expands the set bits of its word(s)
-        // into their slots; first NS hits in index order, the rest padded with the first hit (pointnet2_ops semantics).
-        for (int j = warp; j < J; j += 4) {
-            const uint32_t* wj = sMask + j * NW;
-            int carry = 0, first = -1;
-            for (int w0 = 0; w0 < NW && carry < NS; w0 += 32) {
-                const int wi = w0 + lane;
-                uint32_t word = wi < NW ? wj[wi] : 0u;
-                const int cntw = __popc(word);
-                int incl = cntw;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                int slot = carry + incl - cntw;
-                const uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
-                if (first < 0 && nz) {
-                    const int fl = __ffs(nz) - 1;
-                    const uint32_t fw = __shfl_sync(0xffffffffu, word, fl);
-                    first = (w0 + fl) * 32 + __ffs(fw) - 1;
-                }
-                while (word && slot < NS) {
-                    const int bit = __ffs(word) - 1;
-                    sIdx[j * NS + slot] = (uint16_t)(wi * 32 + bit);
-                    word &= word - 1;
-                    ++slot;
-                }
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (first < 0) first = 0;
-            const int cnt = carry < NS ? carry : NS;
-            for (int s2 = cnt + lane; s2 < NS; s2 += 32) sIdx[j * NS + s2] = (uint16_t)first;
-        }
-    }
-    stamp();
-    const float b1 = p.wvec[128 + 512 + sc * 256 + tid], b2 = p.wvec[128 + 512 + sc * 256 + 128 + tid];
-    const float inv_r = 1.f / radius;
-    __syncthreads();  // sJF, sIdx ready; the joint-embedding MMA (reader of sX, sH) has completed
-    stamp();
-    if (warp_u == 0) mbar_wait(&wbar[1], 0);
-
-    const int JPT = 128 / NS;  // joints per tile (2 for nsample = 64)
-    stamp();
-    // point-feature row of this thread's grouped point for tile j0 (16 x 16 B, all in flight); rows >= N are joints (smem)
-    auto row_index = [&](int j0_) {
-        const int jj_ = j0_ + tid / NS;
-        return jj_ < J ? (int)sIdx[jj_ * NS + (tid % NS)] : 0;
-    };
-    uint4 pre[16];
-    {
-        const int i0 = row_index(0);
-        const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + (i0 < N ? i0 : 0)) * 128);
-#pragma unroll
-        for (int kc = 0; kc < 16; ++kc) pre[kc] = __ldg(src + kc);
-    }
-    for (int j0 = 0; j0 < J; j0 += JPT) {
-        // ---- gather: row r = tid -> (joint j0 + r/NS, slot r%NS); the global rows were prefetched during the previous tile
-        {
-            const int jj = j0 + tid / NS;
-            const bool ok = jj < J;
-            const int ii = ok ? sIdx[jj * NS + (tid % NS)] : 0;
-            const float* cf = sJF + (ok ? jj : 0) * 128;
-            if (ii < N) {
-#pragma unroll
-                for (int kc = 0; kc < 16; ++kc) {
-                    const uint4 v = pre[kc];
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-                    float f[8];
-                    const float4 c0 = *reinterpret_cast<const float4*>(cf + kc * 8), c1 = *reinterpret_cast<const float4*>(cf + kc * 8 + 4);
-                    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 t2 = __bfloat1622float2(h[i]);
-                        f[2 * i] = ok ? t2.x - cc[2 * i] : 0.f;
-                        f[2 * i + 1] = ok ? t2.y - cc[2 * i + 1] : 0.f;
+                for (int s = 0; s < 4; ++s) {
+                    if (s < S) {
+                        const uint32_t bal = __ballot_sync(0xffffffffu, d2 < r2[s]);
+                        if (lane == 0 && wi < NW) sMask[(s * J + j) * NW + wi] = bal;
                     }
-                    sX[kc * 128 + tid] = pack8_bf16(f);
-                }
-            } else {  // one of the J joints appended to the point set (model.py:168-169)
-                const float* sf = sJF + (ii - N) * 128;
-#pragma unroll 4
-                for (int kc = 0; kc < 16; ++kc) {
-                    float f[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = ok ? sf[kc * 8 + i] - cf[kc * 8 + i] : 0.f;
-                    sX[kc * 128 + tid] = pack8_bf16(f);
                 }
             }
-            if (j0 + JPT < J) {  // prefetch the next tile's rows; they land while this tile's MMAs / epilogues run
-                const int i1 = row_index(j0 + JPT);
-                const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + (i1 < N ? i1 : 0)) * 128);
+        }
+    }
+    stamp();
+    mbar_wait(&mma_bar, 0);
+    tc_fence_after();
+    {   // jf[j][ch]: thread (lane quarter q, column group cg) -> channel 32q + lane, joints [8cg, 8cg + 8)
+        const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;
+        float d[8];
+        tmem_ld<8>(tmem0 + ((uint32_t)(32 * q) << 16) + 8 * cg, d);
+        const float bj = p.wvec[ch];
+        const float4 wx = *reinterpret_cast<const float4*>(p.wvec + 128 + 4 * ch);
+        float* ctx = p.ctx + (size_t)b * (J * 128 + 128);
 #pragma unroll
-                for (int kc = 0; kc < 16; ++kc) pre[kc] = __ldg(src + kc);
+        for (int i = 0; i < 8; ++i) {
+            const int j = 8 * cg + i;
+            if (j < J) {
+                const float4 c = sPcl[N + j];
+                const float v = fmaxf(d[i] + bj + wx.x * c.x + wx.y * c.y + wx.z * c.z, 0.f);
+                ctx[j * 128 + ch] = v;
+                if (p.jf_out) p.jf_out[((size_t)b * J + j) * 128 + ch] = v;
             }
-            const float4 q = sPcl[ii], c = sPcl[N + (ok ? jj : 0)];
+        }
+        if (tid < 32) {
+            const float4 c = tid < J ? sPcl[N + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+            reinterpret_cast<float4*>(ctx + J * 128)[tid] = c;
+        }
+    }
+    __syncthreads();   // sMask complete
+    stamp();
+    // ---- phase 2: one warp per (scale, centre): popcount prefix over its hit words, then every lane expands the set bits of
+    // its word(s) into their slots; first NS hits in index order, the rest padded with the first hit (pointnet2_ops semantics).
+    for (int pi = warp; pi < S * J; pi += DS_NT / 32) {
+        const uint32_t* wj = sMask + pi * NW;
+        uint16_t* out = p.idx + ((size_t)b * S * J + pi) * NS;
+        int carry = 0, first = -1;
+        for (int w0 = 0; w0 < NW && carry < NS; w0 += 32) {
+            const int wi = w0 + lane;
+            uint32_t word = wi < NW ? wj[wi] : 0u;
+            const int cntw = __popc(word);
+            int incl = cntw;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int slot = carry + incl - cntw;
+            const uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
+            if (first < 0 && nz) {
+                const int fl = __ffs(nz) - 1;
+                const uint32_t fw = __shfl_sync(0xffffffffu, word, fl);
+                first = (w0 + fl) * 32 + __ffs(fw) - 1;
+            }
+            while (word && slot < NS) {
+                const int bit = __ffs(word) - 1;
+                out[slot] = (uint16_t)(wi * 32 + bit);
+                word &= word - 1;
+                ++slot;
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (first < 0) first = 0;
+        const int cnt = carry < NS ? carry : NS;
+        for (int s2 = cnt + lane; s2 < NS; s2 += 32) out[s2] = (uint16_t)first;
+    }
+    stamp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, 32);
+}
+
+// ================================================================================================ tiles
+__global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p) {
+    extern __shared__ __align__(128) unsigned char ds_smem[];
+    uint4* sW1 = reinterpret_cast<uint4*>(ds_smem);   // [16][128] + tail [2][128]
+    uint4* sW2 = sW1 + 2048 + 256;                     // [16][128]
+    uint4* sX = sW2 + 2048;                            // [2] x ([16][128] K-major activations + tail [2][128])
+    uint4* sH = sX + 2 * DS_XBUF;                      // MN-major [16][16][8]
+    float* sCtx = reinterpret_cast<float*>(sH + 2048); // [2][J*128 + 128] jf | joint xyz of the sample(s) in flight
+    const int ctx_n = p.J * 128 + 128;
+    float* sPart = sCtx + 2 * ctx_n;                   // [2][4][128] per-column-group maxima
+    __shared__ __align__(8) uint64_t wbar, g1_bar, g2_bar, ctx_bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp_u = warp_index_uniform();
+    const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;   // epilogues: channel ch, tile rows [32cg, 32cg + 32)
+    const int r = tid & 127, kq = tid >> 7;                       // gather: tile row r, channel chunks [4kq, 4kq + 4)
+    const int J = p.J, N = p.N, NS = p.nsample, S = p.S, B = p.B;
+    const int JPT = 128 / NS, TPS = (J + JPT - 1) / JPT;          // joints per tile, tiles per (sample, scale)
+    const int total = S * B * TPS;
+    const int it0 = (int)((long long)total * blockIdx.x / gridDim.x), it1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+    const uint32_t ACC1 = 0, ACC2 = 128;
+    int n_stamp = 0;
+    auto stamp = [&]() {
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 48) p.dbg[16 + n_stamp] = clock64();
+        ++n_stamp;
+    };
+    stamp();
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (tid == 0) {
+        mbar_init(&wbar, 1);
+        mbar_init(&g1_bar, 1);
+        mbar_init(&g2_bar, 1);
+        mbar_init(&ctx_bar[0], 1);
+        mbar_init(&ctx_bar[1], 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = tmem_slot, tmem = tmem0 + ((uint32_t)(32 * q) << 16);
+    uint32_t g1_phase = 0, g2_phase = 0, w_phase = 0;
+
+    auto decode = [&](int item, int& sc, int& b, int& j0) {
+        sc = item / (B * TPS);
+        const int rem = item - sc * (B * TPS);
+        b = rem / TPS;
+        j0 = (rem - b * TPS) * JPT;
+    };
+    // ---- gather-side register pipeline
+    int ii_n = 0;            // ball-query index of this thread's row for the item whose rows are fetched next
+    int ii_r = 0;            // ... for the item whose rows are in `pre`
+    uint4 pre[4];            // 4 x 16 B of the point-feature row (channels [32kq, 32kq + 32))
+    float3 pxyz = make_float3(0.f, 0.f, 0.f);
+    int ctx_loads = 0;       // sample contexts requested so far (slot = count & 1)
+    int ctx_b_load = -1;     // sample of the most recent request
+    int ctx_k = -1;          // index of the context the store stage uses
+    int ctx_b_store = -1;
+
+    auto fetch_idx = [&](int item) {
+        int sc, b, j0;
+        decode(item, sc, b, j0);
+        const int jj = j0 + r / NS;
+        ii_n = jj < J ? (int)__ldg(p.idx + (((size_t)b * S + sc) * J + j0) * NS + r) : 0;
+    };
+    auto fetch_rows = [&](int item) {   // uses ii_n
+        int sc, b, j0;
+        decode(item, sc, b, j0);
+        ii_r = ii_n;
+        const int i0 = ii_r < N ? ii_r : 0;
+        const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + i0) * 128) + 4 * kq;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pre[k] = __ldg(src + k);
+        if (kq == 0) {
+            const float* s = p.pcl + ((size_t)b * N + i0) * 3;
+            pxyz = make_float3(__ldg(s), __ldg(s + 1), __ldg(s + 2));
+        }
+        if (b != ctx_b_load) {   // first item of a sample on the gather side: request its context (block-uniform branch)
+            if (warp_u == 0) {
+                if (elect_one()) {
+                    mbar_expect_tx(&ctx_bar[ctx_loads & 1], (uint32_t)ctx_n * 4);
+                    tma_bulk_g2s(sCtx + (ctx_loads & 1) * ctx_n, p.ctx + (size_t)b * ctx_n, (uint32_t)ctx_n * 4, &ctx_bar[ctx_loads & 1]);
+                }
+                __syncwarp();
+            }
+            ctx_b_load = b;
+            ++ctx_loads;
+        }
+    };
+    auto store_x = [&](int item) {      // uses pre / ii_r / pxyz
+        int sc, b, j0;
+        decode(item, sc, b, j0);
+        if (b != ctx_b_store) {
+            ctx_b_store = b;
+            ++ctx_k;
+        }
+        mbar_wait(&ctx_bar[ctx_k & 1], (ctx_k >> 1) & 1);
+        const float* cx = sCtx + (ctx_k & 1) * ctx_n;
+        uint4* X = sX + (item & 1) * DS_XBUF;
+        const int jj = j0 + r / NS;
+        const bool ok = jj < J;
+        const float* cf = cx + (ok ? jj : 0) * 128 + 32 * kq;
+        const float inv_r = 1.f / p.radius[sc];
+        if (ii_r < N) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pre[k]);
+                const float4 c0 = *reinterpret_cast<const float4*>(cf + k * 8), c1 = *reinterpret_cast<const float4*>(cf + k * 8 + 4);
+                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 t2 = __bfloat1622float2(h[i]);
+                    f[2 * i] = ok ? t2.x - cc[2 * i] : 0.f;
+                    f[2 * i + 1] = ok ? t2.y - cc[2 * i + 1] : 0.f;
+                }
+                X[(4 * kq + k) * 128 + r] = pack8_bf16(f);
+            }
+        } else {  // one of the J joints appended to the point set (model.py:168-169)
+            const float* sf = cx + (ii_r - N) * 128 + 32 * kq;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = ok ? sf[k * 8 + i] - cf[k * 8 + i] : 0.f;
+                X[(4 * kq + k) * 128 + r] = pack8_bf16(f);
+            }
+        }
+        if (kq == 0) {
+            const float4* cxyz = reinterpret_cast<const float4*>(cx + J * 128);
+            const float4 c = cxyz[ok ? jj : 0];
+            float3 pq = pxyz;
+            if (ii_r >= N) {
+                const float4 t4 = cxyz[ii_r - N];
+                pq = make_float3(t4.x, t4.y, t4.z);
+            }
             float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (ok) {
-                t8[0] = (q.x - c.x) * inv_r;   // group_xyz_norm = (xyz[idx] - centre) / radius   model.py:177
-                t8[1] = (q.y - c.y) * inv_r;
-                t8[2] = (q.z - c.z) * inv_r;
+                t8[0] = (pq.x - c.x) * inv_r;   // group_xyz_norm = (xyz[idx] - centre) / radius   model.py:177
+                t8[1] = (pq.y - c.y) * inv_r;
+                t8[2] = (pq.z - c.z) * inv_r;
             }
-            sXt[tid] = pack8_bf16(t8);
-            sXt[128 + tid] = make_uint4(0, 0, 0, 0);
+            X[2048 + r] = pack8_bf16(t8);
+            X[2048 + 128 + r] = make_uint4(0, 0, 0, 0);
         }
-        if (j0 == 0) stamp();
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
+    };
+    // maxima of a finished tile: combine the column groups of each joint, store
+    auto store_max = [&](int item) {
+        if (tid < JPT * 128) {
+            int sc, b, j0;
+            decode(item, sc, b, j0);
+            const int g = tid >> 7, c = tid & 127, nc = NS / 32;
+            const float* pp = sPart + (item & 1) * 512 + (g * nc) * 128 + c;
+            float m = pp[0];
+            for (int k = 1; k < nc; ++k) m = fmaxf(m, pp[k * 128]);
+            if (j0 + g < J) p.desa_part[(((size_t)b * S + sc) * J + j0 + g) * 128 + c] = m;
+        }
+    };
+
+    // ---- runs of items that share a scale (= weights)
+    for (int i0 = it0; i0 < it1;) {
+        int sc0, b0, j00;
+        decode(i0, sc0, b0, j00);
+        const int run_end = (sc0 + 1) * B * TPS;
+        const int i1 = it1 < run_end ? it1 : run_end;
+        // every MMA of the previous run has completed (its epilogues ran), so the weight buffers are free
         if (warp_u == 0) {
-            tc_fence_after();
             if (elect_one()) {
-                umma_gemm(tmem0 + ACC1, smem_u32(sW1), 2048, 128, smem_u32(sX), 2048, 128, id128, 128, false);
-                umma_gemm(tmem0 + ACC1, smem_u32(sW1t), 2048, 128, smem_u32(sXt), 2048, 128, id128, 16, true);
-                umma_commit(&mma_bar);
+                const uint4* ws = p.wmat + 2048 + (size_t)sc0 * DS_MAT_PER_SCALE;
+                mbar_expect_tx(&wbar, DS_MAT_PER_SCALE * 16);
+                tma_bulk_g2s(sW1, ws, DS_MAT_PER_SCALE * 16, &wbar);   // W1 | W1 tail | W2 are contiguous on both sides
             }
             __syncwarp();
         }
-        mbar_wait(&mma_bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        if (j0 == 0) stamp();
-        // ---- layer-1 epilogue: h[c][r] = relu(D1 + b1) -> MN-major B operand [K = channel][N = row]
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-            float a[32];
-            tmem_ld32(tmem + ACC1 + c0, a);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + b1, 0.f);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) sH[(tid >> 3) * 128 + (c0 / 8 + c) * 8 + (tid & 7)] = pack8_bf16(a + 8 * c);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (warp_u == 0) {
-            tc_fence_after();
-            if (elect_one()) {
-                umma_gemm(tmem0 + ACC2, smem_u32(sW2), 2048, 128, smem_u32(sH), 2048, 128, umma_idesc_bf16(128, 128, false, true), 128, false);
-                umma_commit(&mma_bar);
+        const float b1 = p.wvec[128 + 512 + sc0 * 256 + ch], b2 = p.wvec[128 + 512 + sc0 * 256 + 128 + ch];
+        bool w_ready = false;
+        // fill: indices of i0, rows of i0, indices of i0 + 1
+        fetch_idx(i0);
+        fetch_rows(i0);
+        if (i0 + 1 < i1) fetch_idx(i0 + 1);
+        for (int s = i0 - 2; s < i1; ++s) {
+            if (s >= i0 - 1) {
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                if (warp_u == 0) {
+                    tc_fence_after();
+                    if (!w_ready) mbar_wait(&wbar, w_phase);
+                    if (elect_one()) {
+                        if (s >= i0) {   // layer 2 of tile s: D2[c][row] = W2 h
+                            umma_gemm(tmem0 + ACC2, smem_u32(sW2), 2048, 128, smem_u32(sH), 2048, 128, umma_idesc_bf16(128, 128, false, true),
+                                      128, false);
+                            umma_commit(&g2_bar);
+                        }
+                        if (s + 1 < i1) {   // layer 1 of tile s + 1: D1[c][row] = W1 [feat - jf | xyz]
+                            const uint4* X = sX + ((s + 1) & 1) * DS_XBUF;
+                            const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
+                            umma_gemm(tmem0 + ACC1, smem_u32(sW1), 2048, 128, smem_u32(X), 2048, 128, id128, 128, false);
+                            umma_gemm(tmem0 + ACC1, smem_u32(sW1 + 2048), 2048, 128, smem_u32(X + 2048), 2048, 128, id128, 16, true);
+                            umma_commit(&g1_bar);
+                        }
+                    }
+                    __syncwarp();
+                }
+                w_ready = true;
+                if (s - 1 >= i0) store_max(s - 1);   // written before the barrier above
             }
-            __syncwarp();
-        }
-        mbar_wait(&mma_bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        if (j0 == 0) stamp();
-        // ---- layer-2 epilogue: max over the NS grouped points of each joint  (model.py:197-198)
-        for (int g = 0; g < JPT; ++g) {
-            float mx = 0.f;  // relu output >= 0
-            for (int c0 = g * NS; c0 < (g + 1) * NS; c0 += 32) {
+            // gather side, two / three / four tiles ahead
+            if (s + 2 < i1) store_x(s + 2);
+            if (s + 3 < i1) fetch_rows(s + 3);
+            if (s + 4 < i1) fetch_idx(s + 4);
+            if (s >= i0) {   // layer-2 epilogue of tile s: max over this thread's 32 grouped points  (model.py:197-198)
+                mbar_wait(&g2_bar, g2_phase);
+                g2_phase ^= 1;
+                tc_fence_after();
                 float a[32];
-                tmem_ld32(tmem + ACC2 + c0, a);
+                tmem_ld<32>(tmem + ACC2 + 32 * cg, a);
+                float mx = 0.f;  // relu output >= 0
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mx = fmaxf(mx, a[i] + b2);
+                sPart[(s & 1) * 512 + cg * 128 + ch] = mx;
+                tc_fence_before();
             }
-            if (j0 + g < J) sOut[(j0 + g) * 128 + tid] = mx;
+            if (s >= i0 - 1 && s + 1 < i1) {   // layer-1 epilogue of tile s + 1: h[c][row] = relu(D1 + b1) -> MN-major B operand
+                mbar_wait(&g1_bar, g1_phase);
+                g1_phase ^= 1;
+                tc_fence_after();
+                float a[32];
+                tmem_ld<32>(tmem + ACC1 + 32 * cg, a);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + b1, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sH[(ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = pack8_bf16(a + 8 * c);
+            }
+            if (s <= i0 + 2) stamp();
         }
-        tc_fence_before();
-        if (j0 == 0) stamp();
+        __syncthreads();
+        store_max(i1 - 1);
+        w_phase ^= 1;
+        i0 = i1;
+        stamp();
     }
-    stamp();
+    tc_fence_before();
     __syncthreads();
-    for (int i = tid; i < J * 128; i += 128) p.desa_part[(((size_t)b * p.S + sc) * J) * 128 + i] = sOut[i];
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem0, 512);
+    if (warp == 0) tmem_dealloc(tmem0, 256);
 }
 
 }  // namespace kpf
 
 extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
                               const void* wmat, const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2,
-                              float r3, float* desa_part, float* jf_out, long long* dbg, cudaStream_t stream) {
+                              float r3, float* desa_part, float* jf_out, void* scratch, int num_sms, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && N + J <= 65535 && J >= 1 && J <= 32 && S >= 1 && S <= 4);
     KPF_REQUIRE(nsample == 32 || nsample == 64 || nsample == 128);
     KPF_REQUIRE(((uintptr_t)wmat % 16) == 0 && ((uintptr_t)e % 16) == 0 && ((uintptr_t)part_acc % 16) == 0 && ((uintptr_t)wvec % 16) == 0);
+    KPF_REQUIRE(scratch != nullptr && ((uintptr_t)scratch % 16) == 0 && num_sms >= 1);
     if (B == 0) return 0;
     DesaParams p;
     p.e = (const __nv_bfloat16*)e; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;
     p.wvec = wvec; p.desa_part = desa_part; p.jf_out = jf_out; p.B = B; p.N = N; p.J = J; p.T = N / 128; p.S = S; p.nsample = nsample;
     p.dbg = dbg;
     p.radius[0] = r0; p.radius[1] = r1; p.radius[2] = r2; p.radius[3] = r3;
-    const size_t smem = (size_t)(2048 + 256 + 2048 + 2048 + 256 + 2048) * 16 + (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * 128 * 4 * 2 +
-                        (size_t)(p.T * 64 + 64) * 4 + (size_t)((J * ((N + J + 31) / 32) + 3) / 4 * 4) * 4 + (size_t)J * nsample * 2 + 64;
-    KPF_REQUIRE(smem <= 227 * 1024);
-    cudaError_t err = kpf::set_smem(desa_fused_kernel, smem);
+    const size_t ctx_n = (size_t)J * 128 + 128;
+    p.ctx = (float*)scratch;
+    p.idx = (uint16_t*)((char*)scratch + (size_t)B * ctx_n * 4);
+    const int NW = (N + J + 31) / 32;
+    const size_t smem_a = (size_t)(2048 + 512) * 16 + (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)(p.T * 64 + 64) * 4 + (size_t)S * J * NW * 4 + 64;
+    const size_t smem_b = (size_t)(DS_MAT_PER_SCALE + 2 * DS_XBUF + 2048) * 16 + 2 * ctx_n * 4 + 2 * 512 * 4 + 64;
+    KPF_REQUIRE(smem_a <= 227 * 1024 && smem_b <= 227 * 1024);
+    cudaError_t err = kpf::set_smem(desa_prep_kernel, smem_a);
     if (err != cudaSuccess) return (int)err;
-    desa_fused_kernel<<<B * S, 128, smem, stream>>>(p);
+    err = kpf::set_smem(desa_tile_kernel, smem_b);
+    if (err != cudaSuccess) return (int)err;
+    desa_prep_kernel<<<B, DS_NT, smem_a, stream>>>(p);
+    KPF_CHECK_LAUNCH();
+    const int JPT = 128 / nsample, total = S * B * ((J + JPT - 1) / JPT);
+    desa_tile_kernel<<<total < num_sms ? total : num_sms, DS_NT, smem_b, stream>>>(p);
     KPF_CHECK_LAUNCH();
     return 0;
 }

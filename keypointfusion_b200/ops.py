@@ -49,11 +49,14 @@ def launch_count():
     return _launches
 
 
+_KERNELS_PER_CALL = {"kpf_desa_fused": 2}   # entry points that launch more than one kernel
+
+
 def _call(name, *args):
     global _launches
     rc = getattr(_lib.lib(), name)(*args, _stream())
     _lib.check(rc, name)
-    _launches += 1
+    _launches += _KERNELS_PER_CALL.get(name, 1)
 
 
 _kvec_cache = {}
@@ -532,8 +535,10 @@ def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, db
     r = list(radius) + [0.0] * (4 - S)
     part = torch.empty(B, S, J, 128, device=pcl.device, dtype=torch.float32)
     jf = torch.empty(B, J, 128, device=pcl.device, dtype=torch.float32)
+    # workspace between the two kernels: per sample [jf | joint xyz] fp32, then the ball-query indices u16
+    scratch = torch.empty(B * (J * 128 + 128) * 4 + B * S * J * nsample * 2, device=pcl.device, dtype=torch.uint8)
     _call("kpf_desa_fused", _p(e), _p(part_acc), _p(part_ms), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, S, nsample, float(r[0]),
-          float(r[1]), float(r[2]), float(r[3]), _p(part), _p(jf), _p(dbg))
+          float(r[1]), float(r[2]), float(r[3]), _p(part), _p(jf), _p(scratch), sm_count(pcl.device), _p(dbg))
     return part, jf
 
 

@@ -85,5 +85,13 @@ def test_block_kernel_phase_clocks(path_params, capsys):
     torch.cuda.synchronize()
     show("point_embed (per tile: setup, gather, offsets, issue+softmax, wait, epilogue, agg-mma+store)", d1,
          ["setup", "gather", "offsets", "stage->issue", "softmax", "mma wait", "epilogue", "agg"] * 5)
-    show("desa_fused", d2, ["stage", "partials+emb", "bq phase1", "bq phase2 (warp 0)", "bias loads+sync", "weights wait", "gather0", "L1 mma0", "L1 epi0+L2 mma", "L2 epi0", "rest tiles"])
+    t2 = d2.cpu().numpy()
+    with capsys.disabled():
+        a = t2[:16]
+        na = int((a > 0).sum())
+        print(f"\n[desa prep] total cycles {int(a[na - 1] - a[0])}:",
+              list(zip(["stage", "partials", "agg+issue", "bq phase1", "jf drain", "bq phase2"], [int(x) for x in np.diff(a[:na])])))
+        bb = t2[16:]
+        nb = int((bb > 0).sum())
+        print(f"[desa tiles] total cycles {int(bb[nb - 1] - bb[0])} (CTA 0), stamp deltas:", [int(x) for x in np.diff(bb[:nb])])
     show("spatial_aggregate_tc", d3, ["setup", "tile0", "t1 wait+prefetch", "t1 geometry", "t1 relu copy", "t1 gemmA", "t1 epiA", "t1 gemmB", "rest"])
