@@ -5,15 +5,15 @@
 //
 //   kpf_repack_features : NCHW (img_feat | img_feat_rgb | img_offset[4J:]) -> channels-last bf16 rows [B,HW,288]
 //                         so that one tap of a point is ONE contiguous 576-byte row.
-//   kpf_point_embed     : per 128-point tile (thread = point):
-//       A1[128 x 256] = [gather(img_feat) | gather(weight map) | unit offsets, closeness, xyz]   (bf16, smem)
+//   kpf_point_embed     : per 128-point tile (512 threads: 4 per point in the gather, 4 column groups per row in the epilogues):
+//       A1[128 x 256] = [gather(img_feat) | gather(weight map) | (unit offset xyz, closeness) per joint, xyz]   (bf16, smem)
 //       A2[128 x 128] =  gather(img_feat_rgb)
 //       e  = relu( relu(A1 W1^T + b1) + A2 W2^T + b2 )                     tcgen05, fp32 accumulators in TMEM
 //       p  = exp(w - max_tile w)  (softmax numerators of the gathered weight map, per joint)
 //       D[c][j] = sum_n e[n][c] p[n][j]                                    tcgen05 with MN-major operands
 //     outputs: e [B,N,128] bf16, and per tile (D, max, sum) partials that the DESA kernel combines flash-style.
 //   Weights (96 KB bf16) stay resident in shared memory; CTAs are persistent over tiles.
-#include "umma.cuh"
+#include "tmem_ldst.cuh"
 
 namespace kpf {
 
@@ -70,21 +70,27 @@ __device__ __forceinline__ void bf16x8_fma(float* acc, const uint4& v, float w) 
     }
 }
 
-__global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p) {
+constexpr int PE_NT = 512;   // gather: warp = 8 points x 4 chunk lanes; epilogues: 4 lane quarters x 4 column groups
+
+__global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams p) {
     extern __shared__ __align__(128) unsigned char pe_smem[];
     uint4* sW = reinterpret_cast<uint4*>(pe_smem);   // [3][2048]
-    uint4* sA1 = sW + 3 * 2048;                       // [32][128]  (K = 256); after the MMAs: sP [16][4][8]
-    uint4* sA2 = sA1 + 4096;                          // [16][128]  (K = 128); after the MMAs: sE MN-major [16][16][8]
+    uint4* sA1 = sW + 3 * 2048;                       // K-major [16 row groups][32 k-chunks][8 rows] (K = 256); after the MMAs: sP [16][4][8]
+    uint4* sA2 = sA1 + 4096;                          // K-major [16][16][8] (K = 128) = e^T MN-major [16][16][8] after the MMAs
     float* sJ = reinterpret_cast<float*>(sA2 + 2048); // [32][4] joints of the current sample
-    float* sRed = sJ + 128;                           // [4][32] cross-warp reductions
+    float* sRed = sJ + 128;                           // [32] per-joint tile maxima
     float* sB = sRed + 128;                           // b1[128], b2[128]
     float* sT = sB + 256;                             // [21][129] transposed softmax scratch
     __shared__ __align__(8) uint64_t wbar, mma_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = warp_index_uniform();  // MMA issue: one elected lane of warp 0 from warp-uniform code (umma.cuh)
+    // gather / offsets: a warp takes 8 points; lane = (point p8, sub): the 4 `sub` lanes of a point read 64 contiguous bytes of a
+    // tap row per load (8 L1 wavefronts per warp load instead of 32 with one lane per row) and the 8 points of a warp fill the
+    // 8 rows x 16 B core matrices of the operand, so the stores are conflict free
+    const int r = 8 * warp + (lane & 7), sub = lane >> 3;
+    const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane; // epilogues: TMEM lane `row`, columns [32cg, 32cg + 32)
     const int J = p.J, N = p.N, T = N / 128;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
@@ -92,13 +98,13 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
         mbar_init(&mma_bar, 1);
         fence_mbar_init();
         mbar_expect_tx(&wbar, 3 * 2048 * 16);
-        for (int i = 0; i < 3; ++i) tma_bulk_g2s(sW + i * 2048, p.wmat + i * 2048, 2048 * 16, &wbar);
+        tma_bulk_g2s(sW, p.wmat, 3 * 2048 * 16, &wbar);
     }
-    for (int i = tid; i < 256; i += 128) sB[i] = p.wvec[i];
+    for (int i = tid; i < 256; i += PE_NT) sB[i] = p.wvec[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem0 = tmem_slot, tmem = tmem0 + lane_off;
+    const uint32_t tmem0 = tmem_slot, tmem = tmem0 + ((uint32_t)(32 * q) << 16);
     const uint32_t ACC1 = 0, ACC2 = 128, ACC3 = 256;
     uint32_t phase = 0;
     bool w_ready = false;
@@ -110,61 +116,83 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
     };
     stamp();
 
+    // per-point inputs of the tile about to be gathered (prefetched during the previous tile's MMAs)
+    int4 id = make_int4(0, 0, 0, 0);
+    float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
+    float px = 0.f, py = 0.f, pz = 0.f;
+    auto fetch_point = [&](int tile) {
+        const int b = tile / T, t = tile - b * T;
+        const size_t pn = (size_t)b * N + t * 128 + r;
+        id = __ldg(reinterpret_cast<const int4*>(p.idx + pn * 4));
+        cw = __ldg(reinterpret_cast<const float4*>(p.clos + pn * 4));
+        px = __ldg(p.pcl + pn * 3);
+        py = __ldg(p.pcl + pn * 3 + 1);
+        pz = __ldg(p.pcl + pn * 3 + 2);
+    };
+    if ((int)blockIdx.x < p.B * T) fetch_point(blockIdx.x);
+
     for (int tile = blockIdx.x; tile < p.B * T; tile += gridDim.x) {
-        const int b = tile / T, t = tile - b * T, n = t * 128 + tid;
-        __syncthreads();  // previous tile's readers of sJ / sRed / sA* are done
+        const int b = tile / T, t = tile - b * T;
+        __syncthreads();  // previous tile's readers of sJ / sRed / sT are done (its MMAs were waited for)
         if (tid < J) {
             sJ[4 * tid] = p.joint[((size_t)b * J + tid) * 3];
             sJ[4 * tid + 1] = p.joint[((size_t)b * J + tid) * 3 + 1];
             sJ[4 * tid + 2] = p.joint[((size_t)b * J + tid) * 3 + 2];
         }
-        const size_t pn = (size_t)b * N + n;
-        const int4 id = *reinterpret_cast<const int4*>(p.idx + pn * 4);
-        const float4 cw = *reinterpret_cast<const float4*>(p.clos + pn * 4);
-        const float px = p.pcl[pn * 3], py = p.pcl[pn * 3 + 1], pz = p.pcl[pn * 3 + 2];
         const uint4* r0 = p.featT + ((size_t)b * p.HW + id.x) * PE_CH;
         const uint4* r1 = p.featT + ((size_t)b * p.HW + id.y) * PE_CH;
         const uint4* r2 = p.featT + ((size_t)b * p.HW + id.z) * PE_CH;
         const uint4* r3 = p.featT + ((size_t)b * p.HW + id.w) * PE_CH;
         stamp();
-        // ---- K3: 4-tap gathers, 8 channels (one 16-byte chunk) at a time, 4 chunks in flight
-        float wraw[32];
+        // ---- K3: 4-tap gathers: chunk 4i + sub of the 36-chunk row in iteration i (depth 0-15 -> A1, rgb 16-31 -> A2, weight map
+        //      32-35 -> A1 chunks 16-19 and the softmax), three iterations (12 x 16 B) in flight
+        float wraw[8];   // gathered weight-map channels [8 sub, 8 sub + 8) of this point
+        uint4* a1r = sA1 + (r >> 3) * 256 + (r & 7);
+        uint4* a2r = sA2 + (r >> 3) * 128 + (r & 7);
 #pragma unroll
-        for (int c = 0; c < PE_CH; c += 6) {
-            uint4 v[6][4];
+        for (int i0 = 0; i0 < 9; i0 += 3) {
+            uint4 v[3][4];
 #pragma unroll
-            for (int u = 0; u < 6; ++u) {
-                v[u][0] = __ldg(r0 + c + u);
-                v[u][1] = __ldg(r1 + c + u);
-                v[u][2] = __ldg(r2 + c + u);
-                v[u][3] = __ldg(r3 + c + u);
+            for (int u = 0; u < 3; ++u) {
+                const int cc = 4 * (i0 + u) + sub;
+                v[u][0] = __ldg(r0 + cc);
+                v[u][1] = __ldg(r1 + cc);
+                v[u][2] = __ldg(r2 + cc);
+                v[u][3] = __ldg(r3 + cc);
             }
 #pragma unroll
-            for (int u = 0; u < 6; ++u) {
+            for (int u = 0; u < 3; ++u) {
                 float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 bf16x8_fma(acc, v[u][0], cw.x);
                 bf16x8_fma(acc, v[u][1], cw.y);
                 bf16x8_fma(acc, v[u][2], cw.z);
                 bf16x8_fma(acc, v[u][3], cw.w);
-                const int cc = c + u;
-                if (cc < 16) sA1[cc * 128 + tid] = pack8_bf16(acc);             // depth-branch features
-                else if (cc < 32) sA2[(cc - 16) * 128 + tid] = pack8_bf16(acc);  // rgb-branch features
-                else {                                                           // weight map (J channels, zero padded)
-                    sA1[(16 + cc - 32) * 128 + tid] = pack8_bf16(acc);
+                const int i = i0 + u;   // compile-time after unrolling
+                if (i < 4) {
+                    a1r[(4 * i + sub) * 8] = pack8_bf16(acc);
+                } else if (i < 8) {
+                    a2r[(4 * (i - 4) + sub) * 8] = pack8_bf16(acc);
+                } else {
+                    a1r[(16 + sub) * 8] = pack8_bf16(acc);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) wraw[(cc - 32) * 8 + i] = acc[i];
+                    for (int k = 0; k < 8; ++k) wraw[k] = acc[k];
                 }
             }
         }
+        // softmax over the tile's points, step 1: the gathered weights, transposed, for the per-joint maxima
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (8 * sub + k < J) sT[(8 * sub + k) * 129 + r] = wraw[k];
         stamp();
-        __syncthreads();  // sJ visible
-        // ---- K4b: unit offsets (joint-major xyz), closeness, then xyz; 96 values -> chunks 20..31 of A1
+        __syncthreads();  // sJ, sT visible
+        // ---- K4b: [unit offset xyz, closeness] of joints [6sub, 6sub + 6), then xyz -> chunks 20 + 3sub .. of A1 (ops.pack_point_embed
+        //      orders W1's columns to match)
         {
-            float buf[96];
+            float buf[24];
 #pragma unroll
-            for (int i = 0; i < 96; ++i) buf[i] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 21; ++j) {
+            for (int jj = 0; jj < 6; ++jj) {
+                const int j = 6 * sub + jj;
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
                 if (j < J) {
                     const float ox = sJ[4 * j] - px, oy = sJ[4 * j + 1] - py, oz = sJ[4 * j + 2] - pz;
                     const float d2 = ox * ox + oy * oy + oz * oz;
@@ -172,17 +200,34 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
                     const float inv = __fdividef(1.f, dis + 1e-8f);
                     const float heat = (p.kernel_size - dis) * inv_ks;
                     const float msk = (heat >= 0.f && pz < 0.99f) ? 1.f : 0.f;
-                    buf[3 * j] = ox * inv * msk;
-                    buf[3 * j + 1] = oy * inv * msk;
-                    buf[3 * j + 2] = oz * inv * msk;
-                    buf[63 + j] = heat * msk;
+                    o0 = ox * inv * msk;
+                    o1 = oy * inv * msk;
+                    o2 = oz * inv * msk;
+                    o3 = heat * msk;
+                } else if (j == J) {
+                    o0 = px;
+                    o1 = py;
+                    o2 = pz;
                 }
+                buf[4 * jj] = o0;
+                buf[4 * jj + 1] = o1;
+                buf[4 * jj + 2] = o2;
+                buf[4 * jj + 3] = o3;
             }
-            buf[84] = px;
-            buf[85] = py;
-            buf[86] = pz;
 #pragma unroll
-            for (int c = 0; c < 12; ++c) sA1[(20 + c) * 128 + tid] = pack8_bf16(buf + 8 * c);
+            for (int c = 0; c < 3; ++c) a1r[(20 + 3 * sub + c) * 8] = pack8_bf16(buf + 8 * c);
+        }
+        // softmax step 1b: per-joint maximum, 16 threads per joint
+        {
+            const int rj = tid >> 4, rs = tid & 15;
+            float m = -INFINITY;
+            if (rj < J) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m = fmaxf(m, sT[rj * 129 + rs + 16 * i]);
+            }
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (rs == 0 && rj < 32) sRed[rj] = rj < J ? m : -INFINITY;
         }
         stamp();
         fence_proxy_async();
@@ -193,51 +238,37 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
             if (!w_ready) mbar_wait(&wbar, 0);
             if (elect_one()) {
                 const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
-                umma_gemm(tmem0 + ACC1, smem_u32(sA1), 2048, 128, smem_u32(sW), 2048, 128, id128, 128, false);
-                umma_gemm(tmem0 + ACC1, smem_u32(sA1 + 2048), 2048, 128, smem_u32(sW + 2048), 2048, 128, id128, 128, true);
-                umma_gemm(tmem0 + ACC2, smem_u32(sA2), 2048, 128, smem_u32(sW + 4096), 2048, 128, id128, 128, false);
+                // A operands: 128 B between k-chunks, 4096 / 2048 B between 8-row groups
+                umma_gemm(tmem0 + ACC1, smem_u32(sA1), 128, 4096, smem_u32(sW), 2048, 128, id128, 128, false);
+                umma_gemm(tmem0 + ACC1, smem_u32(sA1 + 128), 128, 4096, smem_u32(sW + 2048), 2048, 128, id128, 128, true);
+                umma_gemm(tmem0 + ACC2, smem_u32(sA2), 128, 2048, smem_u32(sW + 4096), 2048, 128, id128, 128, false);
                 umma_commit(&mma_bar);
             }
             __syncwarp();
         }
         w_ready = true;
-        // ---- softmax numerators over this tile's points while the MMAs run: per joint max / exp / sum across 128 threads
-        // transposed through shared memory: 4 threads per joint row reduce 128 points (instead of 2 x 32 x 5 warp shuffles)
-        float pj[32];
-#pragma unroll
-        for (int j = 0; j < 21; ++j)
-            if (j < J) sT[j * 129 + tid] = wraw[j];
-        __syncthreads();
-        const int rj = tid >> 2, rs = tid & 3;   // joint row, quarter
-        {
-            float m = -INFINITY;
-            if (rj < J) {
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) m = fmaxf(m, sT[rj * 129 + rs + 4 * i]);
-            }
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-            if (rs == 0 && rj < J) sRed[rj] = m;
-        }
-        __syncthreads();
+        // ---- while the MMAs run: next tile's point inputs, and the softmax numerators p = exp(w - max) (bf16-rounded, as the MMA
+        //      will see them) with their per-joint sums
+        if (tile + (int)gridDim.x < p.B * T) fetch_point(tile + gridDim.x);
         float* ms = p.part_ms + ((size_t)b * T + t) * 64;
+        float pj[8];   // joints [8 sub, 8 sub + 8) of this point
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            pj[j] = (j < J && j < 21) ? __bfloat162float(__float2bfloat16_rn(__expf(wraw[j < 21 ? j : 0] - sRed[j < 21 ? j : 0]))) : 0.f;
+        for (int k = 0; k < 8; ++k) {
+            const int j = 8 * sub + k;
+            pj[k] = j < J ? __bfloat162float(__float2bfloat16_rn(__expf(wraw[k] - sRed[j]))) : 0.f;
+            if (j < J) sT[j * 129 + r] = pj[k];
         }
-        if (tid < 32) ms[tid] = tid < J ? sRed[tid] : -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 21; ++j)
-            if (j < J) sT[j * 129 + tid] = pj[j];
+        if (tid < 32) ms[tid] = sRed[tid];
         __syncthreads();
         {
+            const int rj = tid >> 4, rs = tid & 15;
             float sm_ = 0.f;
             if (rj < J) {
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) sm_ += sT[rj * 129 + rs + 4 * i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sm_ += sT[rj * 129 + rs + 16 * i];
             }
-            sm_ += __shfl_xor_sync(0xffffffffu, sm_, 1);
-            sm_ += __shfl_xor_sync(0xffffffffu, sm_, 2);
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) sm_ += __shfl_xor_sync(0xffffffffu, sm_, o);
             if (rs == 0 && rj < 32) ms[32 + rj] = rj < J ? sm_ : 0.f;
         }
         stamp();
@@ -246,24 +277,24 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
         tc_fence_after();
         stamp();
         // ---- epilogue: e = relu(relu(acc1 + b1) + acc2 + b2) -> global (bf16) and MN-major A operand (sA2 region)
-        __nv_bfloat16* eo = p.e_out + pn * 128;
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-            float a[32], r[32];
-            tmem_ld32(tmem + ACC1 + c0, a);
-            tmem_ld32(tmem + ACC2 + c0, r);
+        {
+            __nv_bfloat16* eo = p.e_out + ((size_t)b * N + t * 128 + row) * 128 + 32 * cg;
+            float a[32], rr[32];
+            tmem_ld_nw<32>(tmem + ACC1 + 32 * cg, a);
+            tmem_ld_nw<32>(tmem + ACC2 + 32 * cg, rr);
+            tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = fmaxf(fmaxf(a[i] + sB[c0 + i], 0.f) + r[i] + sB[128 + c0 + i], 0.f);
+            for (int i = 0; i < 32; ++i) a[i] = fmaxf(fmaxf(a[i] + sB[32 * cg + i], 0.f) + rr[i] + sB[128 + 32 * cg + i], 0.f);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const uint4 v = pack8_bf16(a + 8 * c);
-                *reinterpret_cast<uint4*>(eo + c0 + 8 * c) = v;
-                sA2[(tid >> 3) * 128 + (c0 / 8 + c) * 8 + (tid & 7)] = v;  // e^T: M = channel contiguous
+                *reinterpret_cast<uint4*>(eo + 8 * c) = v;
+                sA2[(row >> 3) * 128 + (4 * cg + c) * 8 + (row & 7)] = v;  // e^T: M = channel contiguous
             }
         }
-        stamp();
         // p as MN-major B operand [K = 128 points][N = 32 joints] over the (dead) head of sA1
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sA1[(tid >> 3) * 32 + c * 8 + (tid & 7)] = pack8_bf16(pj + 8 * c);
+        sA1[(r >> 3) * 32 + sub * 8 + (r & 7)] = pack8_bf16(pj);
+        stamp();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -278,12 +309,12 @@ __global__ void __launch_bounds__(128, 1) point_embed_kernel(const PointParams p
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
-        {
-            float a[32];
-            tmem_ld32(tmem + ACC3, a);  // thread = channel c: D[c][0..31]
-            float4* o = reinterpret_cast<float4*>(p.part_acc + (((size_t)b * T + t) * 128 + tid) * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+        {   // D[channel = row][joints 8cg .. 8cg + 8)
+            float a[8];
+            tmem_ld<8>(tmem + ACC3 + 8 * cg, a);
+            float4* o = reinterpret_cast<float4*>(p.part_acc + (((size_t)b * T + t) * 128 + row) * 32 + 8 * cg);
+            o[0] = make_float4(a[0], a[1], a[2], a[3]);
+            o[1] = make_float4(a[4], a[5], a[6], a[7]);
         }
         tc_fence_before();
         stamp();
@@ -332,7 +363,7 @@ extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const floa
     cudaError_t e = kpf::set_smem(point_embed_kernel, PE_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int tiles = B * (N / 128);
-    point_embed_kernel<<<tiles < num_sms ? tiles : num_sms, 128, PE_SMEM, stream>>>(p);
+    point_embed_kernel<<<tiles < num_sms ? tiles : num_sms, PE_NT, PE_SMEM, stream>>>(p);
     KPF_CHECK_LAUNCH();
     return 0;
 }

@@ -471,12 +471,15 @@ def repack_features(img_feat, img_feat_rgb, weight_map):
 
 def pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, J):
     """BN-folded point-embedding weights (pcl_feat_emb, pcl_xyz_emb, pcl_pose_emb, pcl_feat_emb_RGB) -> (wmat bf16, wvec f32).
-    A1 column order: [depth feats 128 | weight map J (+pad to 32) | unit offsets 3J, closeness J, xyz 3 (+pad to 96)]."""
+    A1 column order: [depth feats 128 | weight map J (+pad to 32) | (unit offset xyz, closeness) per joint, xyz 3 (+pad to 96)]
+    (the reference's pcl_pose_emb input is [weight J | unit offsets 3J joint-major | closeness J], model.py:312-317)."""
     C = Wf.shape[0]
     W1 = Wf.new_zeros(C, 256)
     W1[:, :128] = Wf
     W1[:, 128:128 + J] = Wp[:, :J]
-    W1[:, 160:160 + 4 * J] = Wp[:, J:5 * J]
+    for j in range(J):
+        W1[:, 160 + 4 * j:160 + 4 * j + 3] = Wp[:, J + 3 * j:J + 3 * j + 3]
+        W1[:, 160 + 4 * j + 3] = Wp[:, 4 * J + j]
     W1[:, 160 + 4 * J:160 + 4 * J + 3] = Wx
     wmat = torch.cat([_canon(W1[:, :128]), _canon(W1[:, 128:]), _canon(Wr)]).contiguous()
     wvec = torch.cat([(bf + bx + bp).float(), br.float()]).contiguous()
