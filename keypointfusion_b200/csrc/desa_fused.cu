@@ -1,10 +1,10 @@
 // DESA on tensor cores (model/model.py:129-204 + the joint embeddings :323-325), SURVEY.md 8f-1.  Two kernels:
 //
-// desa_prep_kernel   one CTA per sample, 512 threads:
-//             combine the point stage's softmax partials (flash-style) -> joint_agg[J][128]
-//             jf = relu(Wj [joint_agg | joint_xyz] + b)                     (model.py:323-325)   tcgen05 + fp32 xyz term
-//             ball query (pointnet2_ops semantics) of the J joints over the N points + the J joints themselves, all S radii in
-//             one pass over the distances -> idx[b][scale][j][nsample]
+// desa_prep_kernel   512 threads, two independent roles side by side in one launch:
+//             CTA per sample:  combine the point stage's softmax partials (flash-style) -> joint_agg[J][128]
+//                              jf = relu(Wj [joint_agg | joint_xyz] + b)    (model.py:323-325)   tcgen05 + fp32 xyz term
+//             CTA per (sample, scale): ball query (pointnet2_ops semantics) of the J joints over the N points + the J joints
+//                              themselves -> idx[b][scale][j][nsample]
 // desa_tile_kernel   persistent, one CTA per SM, 512 threads.  Work item = (scale, sample, tile of 128/nsample joints); every
 //             CTA takes a contiguous, scale-major range so the scale's weights stay resident:
 //             X = [feat[idx] - jf[j] | (xyz[idx] - c_j)/r]  ->  h = relu(W1 X + b1)  ->  relu(W2 h + b2)  -> max over nsample
@@ -40,26 +40,97 @@ constexpr int DS_MAT_PER_SCALE = 2048 + 256 + 2048;
 constexpr int DS_XBUF = 2048 + 256;   // uint4 per activation buffer (main + K tail)
 
 // ================================================================================================ prep
+// Two roles in one launch: CTAs [0, B) embed the joints of one sample (softmax-partial combine + tcgen05 GEMM); CTAs
+// [B, B + B*S) run the ball query of one (sample, scale).  The roles are independent and run side by side on different SMs.
 __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p) {
     extern __shared__ __align__(128) unsigned char ds_smem[];
-    uint4* sWj = reinterpret_cast<uint4*>(ds_smem);             // [16][128] K-major A operand
-    uint4* sAgg = sWj + 2048;                                    // MN-major B operand [16][4][8]: joint_agg[channel][joint]
-    float4* sPcl = reinterpret_cast<float4*>(sAgg + 512);        // [N + J] xyz
-    float* sMS = reinterpret_cast<float*>(sPcl + (p.N + p.J + 3) / 4 * 4);  // [T][2][32] partial max/sum -> [T][32] factors + den[32]
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sMS + p.T * 64 + 64);    // [S][J][NW] ball-query hit words (bit = point)
-    __shared__ __align__(8) uint64_t wbar, mma_bar;
-    __shared__ uint32_t tmem_slot;
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int warp_u = warp_index_uniform();
-    const int b = blockIdx.x;
     const int J = p.J, N = p.N, T = p.T, NS = p.nsample, S = p.S;
     int n_stamp = 0;
     auto stamp = [&]() {
-        if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 16) p.dbg[n_stamp] = clock64();
+        if (p.dbg && (blockIdx.x == 0 || (int)blockIdx.x == p.B) && tid == 0 && n_stamp < 8) p.dbg[(blockIdx.x == 0 ? 0 : 8) + n_stamp] = clock64();
         ++n_stamp;
     };
     stamp();
+
+    if ((int)blockIdx.x >= p.B) {
+        // ================= ball query (pointnet2_ops: first NS hits in index order, padded with the first hit) =================
+        const int pi = blockIdx.x - p.B, b = pi / S, sc = pi - b * S;
+        float4* sPcl = reinterpret_cast<float4*>(ds_smem);                          // [N + J] xyz
+        uint32_t* sMask = reinterpret_cast<uint32_t*>(sPcl + (N + J + 3) / 4 * 4);   // [J][NW] hit words (bit = point)
+        for (int i = tid; i < N + J; i += DS_NT) {
+            const float* s = i < N ? p.pcl + ((size_t)b * N + i) * 3 : p.joint + ((size_t)b * J + (i - N)) * 3;
+            sPcl[i] = make_float4(s[0], s[1], s[2], 0.f);
+        }
+        __syncthreads();
+        stamp();
+        // Phase 1: one thread per point tests all J centres (exact fp32 op order).  A warp's 32 lanes hold 32 CONSECUTIVE
+        // points, so one ballot per (centre, point group) IS the hit word.
+        const int NW = (N + J + 31) / 32;
+        const float r2 = xmul(p.radius[sc], p.radius[sc]);
+        for (int base = 0; base + 32 * warp < N + J; base += DS_NT) {   // warp-uniform: warps without points skip the round
+            const int n = base + tid;
+            const float4 q = n < N + J ? sPcl[n] : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+            const int wi = (base >> 5) + warp;
+#pragma unroll 3
+            for (int j = 0; j < J; ++j) {
+                const float4 c = sPcl[N + j];
+                const float dx = xsub(c.x, q.x), dy = xsub(c.y, q.y), dz = xsub(c.z, q.z);
+                const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+                const uint32_t bal = __ballot_sync(0xffffffffu, d2 < r2);
+                if (lane == 0) sMask[j * NW + wi] = bal;
+            }
+        }
+        __syncthreads();
+        stamp();
+        // Phase 2: one warp per centre: popcount prefix over its hit words, then every lane expands the set bits of its word(s)
+        // into their slots
+        for (int j = warp; j < J; j += DS_NT / 32) {
+            const uint32_t* wj = sMask + j * NW;
+            uint16_t* out = p.idx + (((size_t)b * S + sc) * J + j) * NS;
+            int carry = 0, first = -1;
+            for (int w0 = 0; w0 < NW && carry < NS; w0 += 32) {
+                const int wi = w0 + lane;
+                uint32_t word = wi < NW ? wj[wi] : 0u;
+                const int cntw = __popc(word);
+                int incl = cntw;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int slot = carry + incl - cntw;
+                const uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
+                if (first < 0 && nz) {
+                    const int fl = __ffs(nz) - 1;
+                    const uint32_t fw = __shfl_sync(0xffffffffu, word, fl);
+                    first = (w0 + fl) * 32 + __ffs(fw) - 1;
+                }
+                while (word && slot < NS) {
+                    const int bit = __ffs(word) - 1;
+                    out[slot] = (uint16_t)(wi * 32 + bit);
+                    word &= word - 1;
+                    ++slot;
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (first < 0) first = 0;
+            const int cnt = carry < NS ? carry : NS;
+            for (int s2 = cnt + lane; s2 < NS; s2 += 32) out[s2] = (uint16_t)first;
+        }
+        stamp();
+        return;
+    }
+
+    // ================= joint embedding: jf = relu(Wj [joint_agg | joint_xyz] + b)  (model.py:319-325) =================
+    uint4* sWj = reinterpret_cast<uint4*>(ds_smem);             // [16][128] K-major A operand
+    uint4* sAgg = sWj + 2048;                                    // MN-major B operand [16][4][8]: joint_agg[channel][joint]
+    float* sMS = reinterpret_cast<float*>(sAgg + 512);           // [T][2][32] partial max/sum -> [T][32] factors + den[32]
+    float4* sJ = reinterpret_cast<float4*>(sMS + T * 64 + 64);   // [32] joint xyz
+    __shared__ __align__(8) uint64_t wbar, mma_bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp_u = warp_index_uniform();
+    const int b = blockIdx.x;
     if (warp == 0) tmem_alloc(&tmem_slot, 32);
     if (tid == 0) {
         mbar_init(&wbar, 1);
@@ -68,10 +139,9 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         mbar_expect_tx(&wbar, 2048 * 16);
         tma_bulk_g2s(sWj, p.wmat, 2048 * 16, &wbar);
     }
-    // ---- stage xyz of the point set (N points + J joints) and the partial (max, sum) table
-    for (int i = tid; i < N + J; i += DS_NT) {
-        const float* s = i < N ? p.pcl + ((size_t)b * N + i) * 3 : p.joint + ((size_t)b * J + (i - N)) * 3;
-        sPcl[i] = make_float4(s[0], s[1], s[2], 0.f);
+    if (tid < 32) {
+        const float* s = p.joint + ((size_t)b * J + (tid < J ? tid : 0)) * 3;
+        sJ[tid] = tid < J ? make_float4(s[0], s[1], s[2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int i = tid; i < T * 64; i += DS_NT) sMS[i] = p.part_ms[(size_t)b * T * 64 + i];
     tc_fence_before();
@@ -92,29 +162,32 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
     }
     __syncthreads();
     stamp();
-    // ---- joint_agg[c][j] (softmax over all N points of the gathered weight map, model.py:319-320): thread = (channel, 8 joints)
+    // ---- joint_agg[c][j] (softmax over all N points of the gathered weight map): 8 lanes read one channel's 128-byte row of
+    //      a partial per load (4 L1 wavefronts per warp load); thread = (channel, 4 joints), two channel halves
     {
-        const int ch = tid & 127, jg = tid >> 7;
-        float agg[8];
+        const int jq = lane & 7;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) agg[j] = 0.f;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t) {
-            const float4* a = reinterpret_cast<const float4*>(p.part_acc + (((size_t)b * T + t) * 128 + ch) * 32 + 8 * jg);
-            const float4 v0 = __ldg(a), v1 = __ldg(a + 1);
-            const float* f = sMS + t * 64 + 8 * jg;
-            agg[0] += v0.x * f[0];
-            agg[1] += v0.y * f[1];
-            agg[2] += v0.z * f[2];
-            agg[3] += v0.w * f[3];
-            agg[4] += v1.x * f[4];
-            agg[5] += v1.y * f[5];
-            agg[6] += v1.z * f[6];
-            agg[7] += v1.w * f[7];
+        for (int half = 0; half < 2; ++half) {
+            const int ch = 64 * half + 4 * warp + (lane >> 3);
+            float agg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int t = 0; t < T; ++t) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p.part_acc + (((size_t)b * T + t) * 128 + ch) * 32) + jq);
+                const float* f = sMS + t * 64 + 4 * jq;
+                agg[0] += v.x * f[0];
+                agg[1] += v.y * f[1];
+                agg[2] += v.z * f[2];
+                agg[3] += v.w * f[3];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) agg[j] = (4 * jq + j) < J ? agg[j] / sMS[T * 64 + 4 * jq + j] : 0.f;
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(agg[0], agg[1]), hi = __floats2bfloat162_rn(agg[2], agg[3]);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&lo);
+            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            // (k = channel, n = joint), n contiguous: chunk jq / 2 of the row, half jq & 1
+            reinterpret_cast<uint2*>(sAgg + (ch >> 3) * 32 + (jq >> 1) * 8 + (ch & 7))[jq & 1] = o;
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) agg[j] = (8 * jg + j) < J ? agg[j] / sMS[T * 64 + 8 * jg + j] : 0.f;
-        sAgg[(ch >> 3) * 32 + jg * 8 + (ch & 7)] = pack8_bf16(agg);   // (k = channel, n = joint), n contiguous
     }
     fence_proxy_async();
     tc_fence_before();
@@ -127,32 +200,6 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
             umma_commit(&mma_bar);
         }
         __syncwarp();
-    }
-    stamp();
-    // ---- ball query phase 1 (overlaps the MMA): one thread per point tests all J centres (exact fp32 op order) against the S
-    // radii.  A warp's 32 lanes hold 32 CONSECUTIVE points, so one ballot per (scale, centre, point group) IS the hit word.
-    const int NW = (N + J + 31) / 32;
-    {
-        float r2[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) r2[s] = xmul(p.radius[s], p.radius[s]);
-        for (int base = 0; base < N + J; base += DS_NT) {
-            const int n = base + tid;
-            const float4 q = n < N + J ? sPcl[n] : make_float4(1e30f, 1e30f, 1e30f, 0.f);
-            const int wi = (base >> 5) + warp;
-            for (int j = 0; j < J; ++j) {
-                const float4 c = sPcl[N + j];
-                const float dx = xsub(c.x, q.x), dy = xsub(c.y, q.y), dz = xsub(c.z, q.z);
-                const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    if (s < S) {
-                        const uint32_t bal = __ballot_sync(0xffffffffu, d2 < r2[s]);
-                        if (lane == 0 && wi < NW) sMask[(s * J + j) * NW + wi] = bal;
-                    }
-                }
-            }
-        }
     }
     stamp();
     mbar_wait(&mma_bar, 0);
@@ -168,53 +215,13 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         for (int i = 0; i < 8; ++i) {
             const int j = 8 * cg + i;
             if (j < J) {
-                const float4 c = sPcl[N + j];
+                const float4 c = sJ[j];
                 const float v = fmaxf(d[i] + bj + wx.x * c.x + wx.y * c.y + wx.z * c.z, 0.f);
                 ctx[j * 128 + ch] = v;
                 if (p.jf_out) p.jf_out[((size_t)b * J + j) * 128 + ch] = v;
             }
         }
-        if (tid < 32) {
-            const float4 c = tid < J ? sPcl[N + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
-            reinterpret_cast<float4*>(ctx + J * 128)[tid] = c;
-        }
-    }
-    __syncthreads();   // sMask complete
-    stamp();
-    // ---- phase 2: one warp per (scale, centre): popcount prefix over its hit words, then every lane expands the set bits of
-    // its word(s) into their slots; first NS hits in index order, the rest padded with the first hit (pointnet2_ops semantics).
-    for (int pi = warp; pi < S * J; pi += DS_NT / 32) {
-        const uint32_t* wj = sMask + pi * NW;
-        uint16_t* out = p.idx + ((size_t)b * S * J + pi) * NS;
-        int carry = 0, first = -1;
-        for (int w0 = 0; w0 < NW && carry < NS; w0 += 32) {
-            const int wi = w0 + lane;
-            uint32_t word = wi < NW ? wj[wi] : 0u;
-            const int cntw = __popc(word);
-            int incl = cntw;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            int slot = carry + incl - cntw;
-            const uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
-            if (first < 0 && nz) {
-                const int fl = __ffs(nz) - 1;
-                const uint32_t fw = __shfl_sync(0xffffffffu, word, fl);
-                first = (w0 + fl) * 32 + __ffs(fw) - 1;
-            }
-            while (word && slot < NS) {
-                const int bit = __ffs(word) - 1;
-                out[slot] = (uint16_t)(wi * 32 + bit);
-                word &= word - 1;
-                ++slot;
-            }
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (first < 0) first = 0;
-        const int cnt = carry < NS ? carry : NS;
-        for (int s2 = cnt + lane; s2 < NS; s2 += 32) out[s2] = (uint16_t)first;
+        if (tid < 32) reinterpret_cast<float4*>(ctx + J * 128)[tid] = sJ[tid];
     }
     stamp();
     tc_fence_before();
@@ -223,7 +230,13 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
 }
 
 // ================================================================================================ tiles
-__global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p) {
+constexpr int DS_TILE_NT = DS_NT + 32;   // 16 worker warps + one warp that only issues MMAs / TMA copies
+
+struct DesaItem {   // (scale, sample, first joint) of a work item, advanced incrementally (no divisions in the loop)
+    int sc, b, j0;
+};
+
+__global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaParams p) {
     extern __shared__ __align__(128) unsigned char ds_smem[];
     uint4* sW1 = reinterpret_cast<uint4*>(ds_smem);   // [16][128] + tail [2][128]
     uint4* sW2 = sW1 + 2048 + 256;                     // [16][128]
@@ -237,8 +250,9 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = warp_index_uniform();
-    const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;   // epilogues: channel ch, tile rows [32cg, 32cg + 32)
-    const int r = tid & 127, kq = tid >> 7;                       // gather: tile row r, channel chunks [4kq, 4kq + 4)
+    const bool issuer = warp_u == DS_NT / 32;                     // warp 16: MMA / TMA issue only
+    const int q = warp & 3, cg = (warp >> 2) & 3, ch = 32 * q + lane;   // epilogues: channel ch, tile rows [32cg, 32cg + 32)
+    const int r = tid & 127, kq = (tid >> 7) & 3;                 // gather: tile row r, channel chunks [4kq, 4kq + 4)
     const int J = p.J, N = p.N, NS = p.nsample, S = p.S, B = p.B;
     const int JPT = 128 / NS, TPS = (J + JPT - 1) / JPT;          // joints per tile, tiles per (sample, scale)
     const int total = S * B * TPS;
@@ -265,13 +279,26 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
     const uint32_t tmem0 = tmem_slot, tmem = tmem0 + ((uint32_t)(32 * q) << 16);
     uint32_t g1_phase = 0, g2_phase = 0, w_phase = 0;
 
-    auto decode = [&](int item, int& sc, int& b, int& j0) {
-        sc = item / (B * TPS);
-        const int rem = item - sc * (B * TPS);
-        b = rem / TPS;
-        j0 = (rem - b * TPS) * JPT;
+    auto decode = [&](int item) {
+        DesaItem it;
+        it.sc = item / (B * TPS);
+        const int rem = item - it.sc * (B * TPS);
+        it.b = rem / TPS;
+        it.j0 = (rem - it.b * TPS) * JPT;
+        return it;
     };
-    // ---- gather-side register pipeline
+    auto advance = [&](DesaItem& it) {
+        it.j0 += JPT;
+        if (it.j0 >= J) {
+            it.j0 = 0;
+            if (++it.b == B) {
+                it.b = 0;
+                ++it.sc;
+            }
+        }
+    };
+    // ---- gather-side register pipeline (worker warps); every stage walks the items with its own cursor
+    DesaItem c_idx, c_rows, c_store, c_max;
     int ii_n = 0;            // ball-query index of this thread's row for the item whose rows are fetched next
     int ii_r = 0;            // ... for the item whose rows are in `pre`
     uint4 pre[4];            // 4 x 16 B of the point-feature row (channels [32kq, 32kq + 32))
@@ -281,26 +308,15 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
     int ctx_k = -1;          // index of the context the store stage uses
     int ctx_b_store = -1;
 
-    auto fetch_idx = [&](int item) {
-        int sc, b, j0;
-        decode(item, sc, b, j0);
-        const int jj = j0 + r / NS;
-        ii_n = jj < J ? (int)__ldg(p.idx + (((size_t)b * S + sc) * J + j0) * NS + r) : 0;
+    auto fetch_idx = [&]() {
+        const int jj = c_idx.j0 + r / NS;
+        ii_n = jj < J ? (int)__ldg(p.idx + (((size_t)c_idx.b * S + c_idx.sc) * J + c_idx.j0) * NS + r) : 0;
+        advance(c_idx);
     };
-    auto fetch_rows = [&](int item) {   // uses ii_n
-        int sc, b, j0;
-        decode(item, sc, b, j0);
-        ii_r = ii_n;
-        const int i0 = ii_r < N ? ii_r : 0;
-        const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + i0) * 128) + 4 * kq;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pre[k] = __ldg(src + k);
-        if (kq == 0) {
-            const float* s = p.pcl + ((size_t)b * N + i0) * 3;
-            pxyz = make_float3(__ldg(s), __ldg(s + 1), __ldg(s + 2));
-        }
-        if (b != ctx_b_load) {   // first item of a sample on the gather side: request its context (block-uniform branch)
-            if (warp_u == 0) {
+    auto fetch_rows = [&]() {   // uses ii_n; all warps track the context requests, the issuer warp makes them
+        const int b = c_rows.b;
+        if (b != ctx_b_load) {   // first item of a sample on the gather side (block-uniform branch)
+            if (issuer) {
                 if (elect_one()) {
                     mbar_expect_tx(&ctx_bar[ctx_loads & 1], (uint32_t)ctx_n * 4);
                     tma_bulk_g2s(sCtx + (ctx_loads & 1) * ctx_n, p.ctx + (size_t)b * ctx_n, (uint32_t)ctx_n * 4, &ctx_bar[ctx_loads & 1]);
@@ -310,22 +326,35 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
             ctx_b_load = b;
             ++ctx_loads;
         }
+        advance(c_rows);
+        if (issuer) return;
+        ii_r = ii_n;
+        const int i0 = ii_r < N ? ii_r : 0;
+        const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + i0) * 128) + 4 * kq;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pre[k] = __ldg(src + k);
+        if (kq == 0) {
+            const float* s = p.pcl + ((size_t)b * N + i0) * 3;
+            pxyz = make_float3(__ldg(s), __ldg(s + 1), __ldg(s + 2));
+        }
     };
     auto store_x = [&](int item) {      // uses pre / ii_r / pxyz
-        int sc, b, j0;
-        decode(item, sc, b, j0);
-        if (b != ctx_b_store) {
-            ctx_b_store = b;
+        const DesaItem it = c_store;
+        advance(c_store);
+        if (it.b != ctx_b_store) {
+            ctx_b_store = it.b;
             ++ctx_k;
         }
         mbar_wait(&ctx_bar[ctx_k & 1], (ctx_k >> 1) & 1);
         const float* cx = sCtx + (ctx_k & 1) * ctx_n;
         uint4* X = sX + (item & 1) * DS_XBUF;
-        const int jj = j0 + r / NS;
+        const int jj = it.j0 + r / NS;
         const bool ok = jj < J;
         const float* cf = cx + (ok ? jj : 0) * 128 + 32 * kq;
-        const float inv_r = 1.f / p.radius[sc];
-        if (ii_r < N) {
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) X[(4 * kq + k) * 128 + r] = make_uint4(0, 0, 0, 0);
+        } else if (ii_r < N) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pre[k]);
@@ -335,8 +364,8 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 t2 = __bfloat1622float2(h[i]);
-                    f[2 * i] = ok ? t2.x - cc[2 * i] : 0.f;
-                    f[2 * i + 1] = ok ? t2.y - cc[2 * i + 1] : 0.f;
+                    f[2 * i] = t2.x - cc[2 * i];
+                    f[2 * i + 1] = t2.y - cc[2 * i + 1];
                 }
                 X[(4 * kq + k) * 128 + r] = pack8_bf16(f);
             }
@@ -346,7 +375,7 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
             for (int k = 0; k < 4; ++k) {
                 float f[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = ok ? sf[k * 8 + i] - cf[k * 8 + i] : 0.f;
+                for (int i = 0; i < 8; ++i) f[i] = sf[k * 8 + i] - cf[k * 8 + i];
                 X[(4 * kq + k) * 128 + r] = pack8_bf16(f);
             }
         }
@@ -358,6 +387,7 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
                 const float4 t4 = cxyz[ii_r - N];
                 pq = make_float3(t4.x, t4.y, t4.z);
             }
+            const float inv_r = 1.f / p.radius[it.sc];
             float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (ok) {
                 t8[0] = (pq.x - c.x) * inv_r;   // group_xyz_norm = (xyz[idx] - centre) / radius   model.py:177
@@ -370,25 +400,26 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
     };
     // maxima of a finished tile: combine the column groups of each joint, store
     auto store_max = [&](int item) {
+        const DesaItem it = c_max;
+        advance(c_max);
         if (tid < JPT * 128) {
-            int sc, b, j0;
-            decode(item, sc, b, j0);
             const int g = tid >> 7, c = tid & 127, nc = NS / 32;
             const float* pp = sPart + (item & 1) * 512 + (g * nc) * 128 + c;
             float m = pp[0];
             for (int k = 1; k < nc; ++k) m = fmaxf(m, pp[k * 128]);
-            if (j0 + g < J) p.desa_part[(((size_t)b * S + sc) * J + j0 + g) * 128 + c] = m;
+            if (it.j0 + g < J) p.desa_part[(((size_t)it.b * S + it.sc) * J + it.j0 + g) * 128 + c] = m;
         }
     };
 
     // ---- runs of items that share a scale (= weights)
     for (int i0 = it0; i0 < it1;) {
-        int sc0, b0, j00;
-        decode(i0, sc0, b0, j00);
+        const DesaItem first = decode(i0);
+        const int sc0 = first.sc;
         const int run_end = (sc0 + 1) * B * TPS;
         const int i1 = it1 < run_end ? it1 : run_end;
+        c_idx = c_rows = c_store = c_max = first;
         // every MMA of the previous run has completed (its epilogues ran), so the weight buffers are free
-        if (warp_u == 0) {
+        if (issuer) {
             if (elect_one()) {
                 const uint4* ws = p.wmat + 2048 + (size_t)sc0 * DS_MAT_PER_SCALE;
                 mbar_expect_tx(&wbar, DS_MAT_PER_SCALE * 16);
@@ -399,15 +430,15 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
         const float b1 = p.wvec[128 + 512 + sc0 * 256 + ch], b2 = p.wvec[128 + 512 + sc0 * 256 + 128 + ch];
         bool w_ready = false;
         // fill: indices of i0, rows of i0, indices of i0 + 1
-        fetch_idx(i0);
-        fetch_rows(i0);
-        if (i0 + 1 < i1) fetch_idx(i0 + 1);
+        if (!issuer) fetch_idx();
+        fetch_rows();
+        if (!issuer && i0 + 1 < i1) fetch_idx();
         for (int s = i0 - 2; s < i1; ++s) {
             if (s >= i0 - 1) {
                 fence_proxy_async();
                 tc_fence_before();
                 __syncthreads();
-                if (warp_u == 0) {
+                if (issuer) {
                     tc_fence_after();
                     if (!w_ready) mbar_wait(&wbar, w_phase);
                     if (elect_one()) {
@@ -430,33 +461,35 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_tile_kernel(const DesaParams p)
                 if (s - 1 >= i0) store_max(s - 1);   // written before the barrier above
             }
             // gather side, two / three / four tiles ahead
-            if (s + 2 < i1) store_x(s + 2);
-            if (s + 3 < i1) fetch_rows(s + 3);
-            if (s + 4 < i1) fetch_idx(s + 4);
-            if (s >= i0) {   // layer-2 epilogue of tile s: max over this thread's 32 grouped points  (model.py:197-198)
-                mbar_wait(&g2_bar, g2_phase);
-                g2_phase ^= 1;
-                tc_fence_after();
-                float a[32];
-                tmem_ld<32>(tmem + ACC2 + 32 * cg, a);
-                float mx = 0.f;  // relu output >= 0
+            if (!issuer && s + 2 < i1) store_x(s + 2);
+            if (s + 3 < i1) fetch_rows();
+            if (!issuer) {
+                if (s + 4 < i1) fetch_idx();
+                if (s >= i0) {   // layer-2 epilogue of tile s: max over this thread's 32 grouped points  (model.py:197-198)
+                    mbar_wait(&g2_bar, g2_phase);
+                    g2_phase ^= 1;
+                    tc_fence_after();
+                    float a[32];
+                    tmem_ld<32>(tmem + ACC2 + 32 * cg, a);
+                    float mx = a[0];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, a[i] + b2);
-                sPart[(s & 1) * 512 + cg * 128 + ch] = mx;
-                tc_fence_before();
+                    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, a[i]);
+                    sPart[(s & 1) * 512 + cg * 128 + ch] = fmaxf(mx + b2, 0.f);   // max_i relu(a_i + b2)
+                    tc_fence_before();
+                }
+                if (s >= i0 - 1 && s + 1 < i1) {   // layer-1 epilogue of tile s + 1: h[c][row] = relu(D1 + b1) -> MN-major B operand
+                    mbar_wait(&g1_bar, g1_phase);
+                    g1_phase ^= 1;
+                    tc_fence_after();
+                    float a[32];
+                    tmem_ld<32>(tmem + ACC1 + 32 * cg, a);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + b1, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) sH[(ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = pack8_bf16(a + 8 * c);
+                }
             }
-            if (s >= i0 - 1 && s + 1 < i1) {   // layer-1 epilogue of tile s + 1: h[c][row] = relu(D1 + b1) -> MN-major B operand
-                mbar_wait(&g1_bar, g1_phase);
-                g1_phase ^= 1;
-                tc_fence_after();
-                float a[32];
-                tmem_ld<32>(tmem + ACC1 + 32 * cg, a);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + b1, 0.f);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) sH[(ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = pack8_bf16(a + 8 * c);
-            }
-            if (s <= i0 + 2) stamp();
+            if (s <= i0 + 3) stamp();
         }
         __syncthreads();
         store_max(i1 - 1);
@@ -489,17 +522,19 @@ extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float*
     p.ctx = (float*)scratch;
     p.idx = (uint16_t*)((char*)scratch + (size_t)B * ctx_n * 4);
     const int NW = (N + J + 31) / 32;
-    const size_t smem_a = (size_t)(2048 + 512) * 16 + (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)(p.T * 64 + 64) * 4 + (size_t)S * J * NW * 4 + 64;
+    const size_t smem_jf = (size_t)(2048 + 512) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
+    const size_t smem_bq = (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * NW * 4 + 64;
+    const size_t smem_a = smem_jf > smem_bq ? smem_jf : smem_bq;
     const size_t smem_b = (size_t)(DS_MAT_PER_SCALE + 2 * DS_XBUF + 2048) * 16 + 2 * ctx_n * 4 + 2 * 512 * 4 + 64;
     KPF_REQUIRE(smem_a <= 227 * 1024 && smem_b <= 227 * 1024);
     cudaError_t err = kpf::set_smem(desa_prep_kernel, smem_a);
     if (err != cudaSuccess) return (int)err;
     err = kpf::set_smem(desa_tile_kernel, smem_b);
     if (err != cudaSuccess) return (int)err;
-    desa_prep_kernel<<<B, DS_NT, smem_a, stream>>>(p);
+    desa_prep_kernel<<<B + B * S, DS_NT, smem_a, stream>>>(p);
     KPF_CHECK_LAUNCH();
     const int JPT = 128 / nsample, total = S * B * ((J + JPT - 1) / JPT);
-    desa_tile_kernel<<<total < num_sms ? total : num_sms, DS_NT, smem_b, stream>>>(p);
+    desa_tile_kernel<<<total < num_sms ? total : num_sms, DS_TILE_NT, smem_b, stream>>>(p);
     KPF_CHECK_LAUNCH();
     return 0;
 }

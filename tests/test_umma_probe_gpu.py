@@ -87,10 +87,9 @@ def test_block_kernel_phase_clocks(path_params, capsys):
          ["setup", "gather", "offsets", "stage->issue", "softmax", "mma wait", "epilogue", "agg"] * 5)
     t2 = d2.cpu().numpy()
     with capsys.disabled():
-        a = t2[:16]
-        na = int((a > 0).sum())
-        print(f"\n[desa prep] total cycles {int(a[na - 1] - a[0])}:",
-              list(zip(["stage", "partials", "agg+issue", "bq phase1", "jf drain", "bq phase2"], [int(x) for x in np.diff(a[:na])])))
+        for nm, a, lab in (("jf role", t2[:8], ["stage", "agg", "mma issue", "mma + drain"]), ("ball-query role", t2[8:16], ["stage", "phase 1", "phase 2"])):
+            na = int((a > 0).sum())
+            print(f"\n[desa prep / {nm}] total cycles {int(a[na - 1] - a[0])}:", list(zip(lab, [int(x) for x in np.diff(a[:na])])))
         bb = t2[16:]
         nb = int((bb > 0).sum())
         print(f"[desa tiles] total cycles {int(bb[nb - 1] - bb[0])} (CTA 0), stamp deltas:", [int(x) for x in np.diff(bb[:nb])])
