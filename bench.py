@@ -83,8 +83,11 @@ def build_net(device):
     return net.to(device).eval()
 
 
+DEPTH_NOISE = float(os.environ.get("KPF_DEPTH_NOISE", "0.35"))   # synthetic depth noise (normalised; x125 mm), see utils/synth.py
+
+
 def host_inputs(B, seed):
-    inp = synth.make_inputs(B, S, J, C, seed=seed)
+    inp = synth.make_inputs(B, S, J, C, seed=seed, depth_noise=DEPTH_NOISE)
     for k in ("img_feat", "img_feat_rgb", "img_offset"):
         inp[k] = inp[k].bfloat16()
     inp.pop("img_rgb")
@@ -347,10 +350,12 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
     k = blk.kc()
     with torch.no_grad():
         pcl, _ = ops.getpcl(d0["img"], d0["center"], d0["cube"], d0["M"], d0["cam"], N_PTS, seed=0)
-        close, _, idx = ops.img2pcl_index(pcl, d0["img"], d0["center"], d0["M"], d0["cube"], d0["cam"], S, 4, fs=H, want_i64=False, want_i32=True)
+        order = ops.spatial_order(pcl, d0["center"], d0["M"], d0["cube"], d0["cam"], S, H)
+        close, _, idx = ops.img2pcl_index(pcl, d0["img"], d0["center"], d0["M"], d0["cube"], d0["cam"], S, 4, fs=H, want_i64=False, want_i32=True,
+                                          order=order)
         joints = pcl[:, ::48][:, :J].contiguous() + 0.01
         featT = ops.repack_features(d0["img_feat"], d0["img_feat_rgb"], d0["img_offset"][:, 4 * J:])
-        e_, acc_, ms_ = ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8)
+        e_, acc_, ms_ = ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order)
         part_, jf_ = ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0])
         tok_, r3d_, _ = ops.token_stack(k["tok_init"], desa=part_, jf=jf_)
     e = 2  # bf16 feature maps
@@ -360,7 +365,7 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
                                B * (4 * J * C * 4 + J * C * 4 + J * 12), B * 16.1e6, "tensor"),
         "desa_fused_kernel": (lambda d: ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0]), 2,
                               B * (3 * J * 64 * C * e + N_PTS * 12 + 4 * J * C * 4), B * 270.1e6, "tensor"),
-        "point_embed_kernel": (lambda d: ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8), 2,
+        "point_embed_kernel": (lambda d: ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order), 2,
                                B * ((2 * C + J) * H * H * e + N_PTS * 4 * 8 + N_PTS * C * e), B * 95.4e6, "tensor"),
         "spatial_aggregate_tc_kernel": (lambda d: ops.spatial_aggregate_tc(d["img_feat_rgb"], joints, d["img"][:, :, ::4, ::4], d["center"], d["M"],
                                                                           d["cube"], d["cam"], k["wa_packed"], blk.atten_spatial.bias,
@@ -368,7 +373,7 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
                                                                           blk.fc_spatial2joint_feature.bias), 2,
                                         B * (C * H * H * e + J * H * H * 4 + J * C * 4), B * 12.04e6, "hbm"),
         "nearest_cells_kernel": (lambda d: ops.img2pcl_index(pcl, d["img"], d["center"], d["M"], d["cube"], d["cam"], S, 4, fs=H, want_i64=False,
-                                                             want_i32=True), 1, B * (N_PTS * 12 + H * H * 4 + 76 + N_PTS * 4 * 8), B * 8.39e6, "hbm"),
+                                                             want_i32=True, order=order), 1, B * (N_PTS * 12 + H * H * 4 + 76 + N_PTS * 4 * 8), B * 8.39e6, "hbm"),
         "repack_kernel": (lambda d: ops.repack_features(d["img_feat"], d["img_feat_rgb"], d["img_offset"][:, 4 * J:]), 1,
                           B * ((2 * C + J) * H * H * e + 288 * H * H * 2), 0.0, "hbm"),
         "offset2joint_kernel": (lambda d: ops.offset2joint_weight(d["img_offset"], d["img"], 0.8), 1, B * (5 * J * H * H * e + H * H * 4), B * 0.3e6,

@@ -55,10 +55,18 @@ int kpf_xyz2uvd(const float* xyz, const float* center, const float* M, const flo
 /* ---- a6  dataloader/loader.py:936-967 img2pcl_index ---------------------------------------------------------------
  * pcl [B,N,3]; depth element (b,r,c) at depth[b*depth_bs + r*depth_rs + c*depth_cs], r,c < fs.
  * closeness [B,N,K] f32; index64 [B,N,K] i64 and/or index32 [B,N,K] i32 (either may be NULL): flat cell index
- * row*fs+col of the K nearest cells in normalised 3-D space, ascending distance, ties -> lower index. K in 1..9 or 16. */
+ * row*fs+col of the K nearest cells in normalised 3-D space, ascending distance, ties -> lower index. K in 1..9 or 16.
+ * order: NULL, or [B,N] i32 from kpf_spatial_order -- the order in which threads take the points (results identical). */
 int kpf_img2pcl_index(const float* pcl, const float* depth, long long depth_bs, int depth_rs, int depth_cs, const float* center,
                       const float* M, const float* cube, const float* cam, int B, int N, int fs, float img_size, float flip, int K,
-                      float* closeness, long long* index64, int32_t* index32, cudaStream_t stream);
+                      const int32_t* order, float* closeness, long long* index64, int32_t* index32, cudaStream_t stream);
+
+/* ---- scheduling helper (no reference counterpart): order [B,N] i32 = the permutation that sorts each sample's points by the
+ * fs x fs feature-map cell they project to (row-major cell, point id as tie break).  kpf_img2pcl_index and kpf_point_embed
+ * accept it so that neighbouring threads / 128-point tiles touch neighbouring cells; outputs do not depend on it except
+ * for the partition of kpf_point_embed's per-tile partial sums.  N <= 8192. */
+int kpf_spatial_order(const float* pcl, const float* center, const float* M, const float* cube, const float* cam, int B, int N, int fs,
+                      float img_size, float flip, int32_t* order, cudaStream_t stream);
 
 /* ---- a4  model/model.py:466-500 offset2joint_weight (== util/generateFeature.py:166-195) ------------------------
  * offset [B,5J,fs,fs] (dtype), depth [B,1,S,S] f32 (nearest down-sampled to fs inside), kernel_vec [J] f32.
@@ -153,13 +161,14 @@ int kpf_token_stack(const float* x, const float* y, const float* r3d, const floa
  * kpf_repack_features: f_d, f_rgb [B,128,HW], f_w [B,J,HW] (batch stride w_batch_stride elements; = img_offset[:,4J:])
  *   -> out [B,HW,288] bf16 channels-last rows (128 | 128 | J zero-padded to 32).
  * kpf_point_embed: featT from above; idx [B,N,4] i32 / clos [B,N,4] f32 from kpf_img2pcl_index (K = 4); pcl [B,N,3];
- *   joint [B,J,3] (J <= 21); wmat/wvec from ops.pack_point_embed -> e_out [B,N,128] bf16 (point features after the four
+ *   joint [B,J,3] (J <= 21); order NULL or [B,N] i32 (kpf_spatial_order: tile t = points order[128t .. 128t+128));
+ *   wmat/wvec from ops.pack_point_embed -> e_out [B,N,128] bf16 (point features after the four
  *   folded Conv1d+BN embeddings and both relus), part_acc [B,N/128,128,32] f32 and part_ms [B,N/128,2,32] f32: per
  *   128-point tile the softmax-aggregation numerators sum_n e[n][c]*exp(w[n][j]-max_tile) and (max_tile, sum_tile). */
 int kpf_repack_features(const void* f_d, const void* f_rgb, const void* f_w, long long w_batch_stride, int dtype, int B, int C, int J,
                         int HW, void* out, cudaStream_t stream);
-int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint, const void* wmat,
-                    const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out, float* part_acc, float* part_ms,
+int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
+                    const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out, float* part_acc, float* part_ms,
                     int num_sms, long long* dbg, cudaStream_t stream);
 
 /* ---- 8f-1 DESA on tensor cores (csrc/desa_fused.cu), model/model.py:129-204 + joint embeddings :323-325 ---------------

@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     const int r = tid & 127, kq = (tid >> 7) & 3;                 // gather: tile row r, channel chunks [4kq, 4kq + 4)
     const int J = p.J, N = p.N, NS = p.nsample, S = p.S, B = p.B;
     const int JPT = 128 / NS, TPS = (J + JPT - 1) / JPT;          // joints per tile, tiles per (sample, scale)
+    const int jrow = r >> (31 - __clz(NS));                       // r / NS (NS is a power of two): joint of this gather row within the tile
     const int total = S * B * TPS;
     const int it0 = (int)((long long)total * blockIdx.x / gridDim.x), it1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
     const uint32_t ACC1 = 0, ACC2 = 128;
@@ -307,9 +308,10 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     int ctx_b_load = -1;     // sample of the most recent request
     int ctx_k = -1;          // index of the context the store stage uses
     int ctx_b_store = -1;
+    float inv_r = 1.f;       // 1 / radius of the run's scale
 
     auto fetch_idx = [&]() {
-        const int jj = c_idx.j0 + r / NS;
+        const int jj = c_idx.j0 + jrow;
         ii_n = jj < J ? (int)__ldg(p.idx + (((size_t)c_idx.b * S + c_idx.sc) * J + c_idx.j0) * NS + r) : 0;
         advance(c_idx);
     };
@@ -341,14 +343,14 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     auto store_x = [&](int item) {      // uses pre / ii_r / pxyz
         const DesaItem it = c_store;
         advance(c_store);
-        if (it.b != ctx_b_store) {
+        if (it.b != ctx_b_store) {   // first tile of a sample on the store side: its context must have landed
             ctx_b_store = it.b;
             ++ctx_k;
+            mbar_wait(&ctx_bar[ctx_k & 1], (ctx_k >> 1) & 1);
         }
-        mbar_wait(&ctx_bar[ctx_k & 1], (ctx_k >> 1) & 1);
         const float* cx = sCtx + (ctx_k & 1) * ctx_n;
         uint4* X = sX + (item & 1) * DS_XBUF;
-        const int jj = it.j0 + r / NS;
+        const int jj = it.j0 + jrow;
         const bool ok = jj < J;
         const float* cf = cx + (ok ? jj : 0) * 128 + 32 * kq;
         if (!ok) {
@@ -387,7 +389,6 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                 const float4 t4 = cxyz[ii_r - N];
                 pq = make_float3(t4.x, t4.y, t4.z);
             }
-            const float inv_r = 1.f / p.radius[it.sc];
             float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (ok) {
                 t8[0] = (pq.x - c.x) * inv_r;   // group_xyz_norm = (xyz[idx] - centre) / radius   model.py:177
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
             __syncwarp();
         }
         const float b1 = p.wvec[128 + 512 + sc0 * 256 + ch], b2 = p.wvec[128 + 512 + sc0 * 256 + 128 + ch];
+        inv_r = 1.f / p.radius[sc0];
         bool w_ready = false;
         // fill: indices of i0, rows of i0, indices of i0 + 1
         if (!issuer) fetch_idx();
@@ -469,19 +471,19 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                     mbar_wait(&g2_bar, g2_phase);
                     g2_phase ^= 1;
                     tc_fence_after();
-                    float a[32];
+                        float a[32];
                     tmem_ld<32>(tmem + ACC2 + 32 * cg, a);
                     float mx = a[0];
 #pragma unroll
                     for (int i = 1; i < 32; ++i) mx = fmaxf(mx, a[i]);
                     sPart[(s & 1) * 512 + cg * 128 + ch] = fmaxf(mx + b2, 0.f);   // max_i relu(a_i + b2)
                     tc_fence_before();
-                }
+                    }
                 if (s >= i0 - 1 && s + 1 < i1) {   // layer-1 epilogue of tile s + 1: h[c][row] = relu(D1 + b1) -> MN-major B operand
                     mbar_wait(&g1_bar, g1_phase);
                     g1_phase ^= 1;
                     tc_fence_after();
-                    float a[32];
+                        float a[32];
                     tmem_ld<32>(tmem + ACC1 + 32 * cg, a);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + b1, 0.f);

@@ -51,16 +51,67 @@ __global__ void xyz2uvd_kernel(const float* __restrict__ xyz, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Spatial processing order of a sample's points: the permutation that sorts them by the feature-map cell they project to
+// (row-major cell index, point id as tie break -> deterministic).  Not part of the reference; kpf_img2pcl_index and
+// kpf_point_embed use it to make neighbouring threads / tiles touch neighbouring cells.  One CTA per sample, bitonic sort of
+// (cell << 13 | id) keys in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+spatial_order_kernel(const float* __restrict__ pcl, const float* __restrict__ center, const float* __restrict__ M,
+                     const float* __restrict__ cube, const float* __restrict__ cam, int N, int npow2, int fs, float img_size, float flip,
+                     int32_t* __restrict__ order) {
+    extern __shared__ uint32_t so_keys[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* m9 = M + 9 * b;
+    const float cx = center[3 * b], cy = center[3 * b + 1], cz = center[3 * b + 2];
+    const float hx = cube[3 * b] * 0.5f, hy = cube[3 * b + 1] * 0.5f, hz = cube[3 * b + 2] * 0.5f;
+    const float fx = cam[4 * b], fy = cam[4 * b + 1], fu = cam[4 * b + 2], fv = cam[4 * b + 3];
+    const float sc = (float)fs / img_size;
+    for (int i = tid; i < npow2; i += blockDim.x) {
+        uint32_t key = 0xFFFFFFFFu;
+        if (i < N) {
+            const float* s = pcl + ((size_t)b * N + i) * 3;
+            const float X = s[0] * hx + cx, Y = s[1] * hy + cy, Z = s[2] * hz + cz;   // loader.py:828
+            const float pu = X * fx / (Z + 1e-8f) + fu, pv = flip * Y * fy / Z + fv;  // loader.py:281-286
+            const float tu = m9[0] * pu + m9[1] * pv + m9[2], tv = m9[3] * pu + m9[4] * pv + m9[5];
+            int cp = (int)(tu * sc), rp = (int)(tv * sc);
+            cp = min(max(cp, 0), fs - 1);
+            rp = min(max(rp, 0), fs - 1);
+            key = ((uint32_t)(rp * fs + cp) << 13) | (uint32_t)i;
+        }
+        so_keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = so_keys[i], c = so_keys[ixj];
+                    if ((a > c) == ((i & k) == 0)) {
+                        so_keys[i] = c;
+                        so_keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < N; i += blockDim.x) order[(size_t)b * N + i] = (int32_t)(so_keys[i] & 0x1FFFu);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2 / a6: img2pcl_index   dataloader/loader.py:936-967
 //   cell cloud of the sample (H*W x float4) lives in shared memory; one thread per point keeps a sorted
-//   top-K in registers; ties -> lower cell index (strict '<' while scanning cells in ascending order).
+//   top-K in registers; ties -> lower cell index (lexicographic (d2, index) order, = the reference's stable ascending scan).
 // ------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(256)
 nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ depth, long long depth_bs, int depth_rs,
                      int depth_cs, const float* __restrict__ center, const float* __restrict__ M,
                      const float* __restrict__ cube, const float* __restrict__ cam, int N, int fs, float img_size, float flip,
-                     float* __restrict__ closeness, long long* __restrict__ index64, int32_t* __restrict__ index32) {
+                     const int32_t* __restrict__ order, float* __restrict__ closeness, long long* __restrict__ index64,
+                     int32_t* __restrict__ index32) {
     extern __shared__ __align__(16) float4 cells[];
     __shared__ CamF c;
     const int b = blockIdx.y, HW = fs * fs;
@@ -74,8 +125,11 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
         cells[m] = make_float4(q.x, q.y, q.z, 0.f);
     }
     __syncthreads();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= N) return;
+    // optional processing order (kpf_spatial_order): neighbouring threads then hold neighbouring points, so a warp's lanes take
+    // the insertion path at the same cells; the outputs are indexed by the point id either way
+    const int n = order ? order[(size_t)b * N + slot] : slot;
     const float* pp = pcl + ((size_t)b * N + n) * 3;
     const float px = pp[0], py = pp[1], pz = pp[2];
     float bd[K];
@@ -85,14 +139,16 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
         bd[k] = INFINITY;
         bi[k] = 0;
     }
-    // four cells per iteration: the distance arithmetic of a group is branch-free; the (rare, after warm-up) insertions stay in
-    // ascending cell order so ties still resolve to the lower index
+    // The result is the K smallest (d2, cell index) pairs in lexicographic order -- exactly what the reference's stable
+    // ascending scan with a strict '<' yields -- so cells may be visited in any order.  Seed the list from a 3 x 8 window of
+    // cells around the point's own (approximately projected) cell: the K-th best distance is then already tight and the full
+    // scan below almost never takes the (divergent, ~25-instruction) insertion path.
     auto insert = [&](float d2, int m) {
         float cd = d2;
         int ci = m;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            if (cd < bd[k]) {
+            if (cd < bd[k] || (cd == bd[k] && ci < bi[k])) {
                 const float td = bd[k];
                 const int ti = bi[k];
                 bd[k] = cd;
@@ -102,27 +158,52 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
             }
         }
     };
-    int m = 0;
+    auto dist2 = [&](const float4 q) {
+        const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
+        return xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));  // loader.py:956
+    };
+    const bool windowed = (fs & 3) == 0 && fs >= 8;
+    int wr0 = -64, wc0 = -64;   // window origin (rows wr0..wr0+2, columns wc0..wc0+7); far away = no window
+    if (windowed) {
+        // fast-math projection of the point into the crop (loader.py:281-286, :828-831); only seeds the window
+        const float* m9 = M + 9 * b;
+        const float X = px * c.hx + c.cx, Y = py * c.hy + c.cy, Z = pz * c.hz + c.cz;
+        const float pu = X * c.fx / (Z + 1e-8f) + c.fu, pv = c.flip * Y * c.fy / Z + c.fv;
+        const float tu = m9[0] * pu + m9[1] * pv + m9[2], tv = m9[3] * pu + m9[4] * pv + m9[5];
+        const float sc = ffs / img_size;
+        int cp = (int)(tu * sc), rp = (int)(tv * sc);   // NaN / out of range -> clamped: any window is valid
+        cp = min(max(cp, 0), fs - 1);
+        rp = min(max(rp, 0), fs - 1);
+        wr0 = min(max(rp - 1, 0), fs - 3);
+        wc0 = min(max((((cp + 2) >> 2) << 2) - 4, 0), fs - 8);   // multiple of 4: a 4-cell group is inside or outside as a whole
+        for (int rr = 0; rr < 3; ++rr) {
+            const int m0 = (wr0 + rr) * fs + wc0;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) insert(dist2(cells[m0 + cc]), m0 + cc);
+        }
+    }
+    // full scan, four cells per iteration: the distance arithmetic of a group is branch-free
+    int m = 0, row = 0, col = 0;
     for (; m + 4 <= HW; m += 4) {
         float d2[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float4 q = cells[m + u];
-            const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
-            d2[u] = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));  // loader.py:956
-        }
+        for (int u = 0; u < 4; ++u) d2[u] = dist2(cells[m + u]);
         const float mn = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
-        if (mn < bd[K - 1]) {
+        const bool inwin = (unsigned)(row - wr0) < 3u && (unsigned)(col - wc0) < 8u;   // already inserted
+        if (!inwin && mn <= bd[K - 1]) {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (d2[u] < bd[K - 1]) insert(d2[u], m + u);
+                if (d2[u] <= bd[K - 1]) insert(d2[u], m + u);
+        }
+        col += 4;
+        if (col >= fs) {   // only meaningful when fs % 4 == 0 (the windowed case)
+            col = 0;
+            ++row;
         }
     }
     for (; m < HW; ++m) {
-        const float4 q = cells[m];
-        const float dx = xsub(px, q.x), dy = xsub(py, q.y), dz = xsub(pz, q.z);
-        const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-        if (d2 < bd[K - 1]) insert(d2, m);
+        const float d2 = dist2(cells[m]);
+        if (d2 <= bd[K - 1]) insert(d2, m);
     }
     float cv[K];
     float s = 0.f;
@@ -329,10 +410,21 @@ extern "C" int kpf_xyz2uvd(const float* xyz, const float* center, const float* M
     return 0;
 }
 
+extern "C" int kpf_spatial_order(const float* pcl, const float* center, const float* M, const float* cube, const float* cam, int B, int N,
+                                 int fs, float img_size, float flip, int32_t* order, cudaStream_t stream) {
+    KPF_REQUIRE(B >= 0 && N >= 1 && N <= 8192 && fs >= 1 && fs * fs <= (1 << 19));
+    if (B == 0) return 0;
+    int npow2 = 1;
+    while (npow2 < N) npow2 <<= 1;
+    kpf::spatial_order_kernel<<<B, 1024, (size_t)npow2 * 4, stream>>>(pcl, center, M, cube, cam, N, npow2, fs, img_size, flip, order);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long depth_bs, int depth_rs, int depth_cs,
                                  const float* center, const float* M, const float* cube, const float* cam, int B, int N, int fs,
-                                 float img_size, float flip, int K, float* closeness, long long* index64, int32_t* index32,
-                                 cudaStream_t stream) {
+                                 float img_size, float flip, int K, const int32_t* order, float* closeness, long long* index64,
+                                 int32_t* index32, cudaStream_t stream) {
     KPF_REQUIRE(B >= 0 && N >= 0 && fs >= 1 && fs * fs <= 8192 && K >= 1 && K <= fs * fs);
     if (B == 0 || N == 0) return 0;
     dim3 grid((N + 255) / 256, B);
@@ -342,7 +434,7 @@ extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long
         cudaError_t e = kpf::set_smem(nearest_cells_kernel<KK>, smem); \
         if (e != cudaSuccess) return (int)e;                                                                                 \
         nearest_cells_kernel<KK><<<grid, 256, smem, stream>>>(pcl, depth, depth_bs, depth_rs, depth_cs, center, M, cube, cam, N, \
-                                                             fs, img_size, flip, closeness, index64, index32);               \
+                                                             fs, img_size, flip, order, closeness, index64, index32);        \
     } break;
     switch (K) {
         KPF_LAUNCH_K2(1)

@@ -44,12 +44,52 @@ repack_kernel(const T* __restrict__ f_d, const T* __restrict__ f_rgb, const T* _
     }
 }
 
+// bf16 fast path of the repack (C = 128, HW % 128 == 0): a CTA transposes a [64 channels x 128 cells] block through shared memory
+// with 16-byte global accesses on both sides (8 cells of a channel in, 8 channels of a cell out) -- the generic kernel above
+// moves 2 bytes per lane.  Channel blocks 0,1 = depth branch, 2,3 = rgb branch, 4 = the J weight channels zero-padded to 32.
+constexpr int RP_LD = 128 + 2;   // bf16 elements per staged channel row (+2: consecutive channels land in consecutive banks)
+__global__ void __launch_bounds__(256)
+repack_bf16_kernel(const __nv_bfloat16* __restrict__ f_d, const __nv_bfloat16* __restrict__ f_rgb, const __nv_bfloat16* __restrict__ f_w,
+                   long long w_bs, int J, int HW, __nv_bfloat16* __restrict__ out) {
+    __shared__ __align__(16) __nv_bfloat16 tile[64 * RP_LD];
+    const int b = blockIdx.z, cb = blockIdx.y, h0 = blockIdx.x * 128, tid = threadIdx.x;
+    const int nch = cb < 4 ? 64 : 32;
+    // load: thread -> (channel, 8 consecutive cells); a warp reads 2 channels x 256 B
+    for (int i = tid; i < nch * 16; i += 256) {
+        const int ch = i >> 4, seg = i & 15;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (cb < 2) v = __ldg(reinterpret_cast<const uint4*>(f_d + ((size_t)b * 128 + cb * 64 + ch) * HW + h0) + seg);
+        else if (cb < 4) v = __ldg(reinterpret_cast<const uint4*>(f_rgb + ((size_t)b * 128 + (cb - 2) * 64 + ch) * HW + h0) + seg);
+        else if (ch < J) v = __ldg(reinterpret_cast<const uint4*>(f_w + (size_t)b * w_bs + (size_t)ch * HW + h0) + seg);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tile + ch * RP_LD + seg * 8);   // 4-byte aligned (RP_LD even)
+        dst[0] = v.x;
+        dst[1] = v.y;
+        dst[2] = v.z;
+        dst[3] = v.w;
+    }
+    __syncthreads();
+    // store: thread -> (cell, 8 consecutive channels); a warp writes 128 contiguous bytes of each of 4 (or 8) cell rows
+    const int gs = cb < 4 ? 3 : 2, ngrp = 1 << gs;   // 8-channel groups per cell
+    for (int i = tid; i < 128 * ngrp; i += 256) {
+        const int g = i & (ngrp - 1), cell = i >> gs;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint16_t lo = *reinterpret_cast<const uint16_t*>(tile + (8 * g + 2 * k) * RP_LD + cell);
+            const uint16_t hi = *reinterpret_cast<const uint16_t*>(tile + (8 * g + 2 * k + 1) * RP_LD + cell);
+            w[k] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+        *reinterpret_cast<uint4*>(out + ((size_t)b * HW + h0 + cell) * PE_CP + cb * 64 + 8 * g) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 struct PointParams {
     const uint4* featT;      // [B,HW,36] uint4 (288 bf16)
     const int32_t* idx;      // [B,N,4]
     const float* clos;       // [B,N,4]
     const float* pcl;        // [B,N,3]
     const float* joint;      // [B,J,3]
+    const int32_t* order;    // [B,N] processing order of the points (kpf_spatial_order) or null = identity
     const uint4* wmat;       // W1a, W1b, W2: 3 x [16][128] uint4
     const float* wvec;       // b1[128], b2[128]
     __nv_bfloat16* e_out;    // [B,N,128]
@@ -81,6 +121,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
     float* sRed = sJ + 128;                           // [32] per-joint tile maxima
     float* sB = sRed + 128;                           // b1[128], b2[128]
     float* sT = sB + 256;                             // [21][129] transposed softmax scratch
+    int* sN = reinterpret_cast<int*>(sT + 21 * 129 + 3);  // [2][128] point ids of the tile in flight / being prefetched
     __shared__ __align__(8) uint64_t wbar, mma_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -120,16 +161,19 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
     int4 id = make_int4(0, 0, 0, 0);
     float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
     float px = 0.f, py = 0.f, pz = 0.f;
-    auto fetch_point = [&](int tile) {
+    int n_id = 0, tile_par = 0;
+    auto fetch_point = [&](int tile, int par) {
         const int b = tile / T, t = tile - b * T;
-        const size_t pn = (size_t)b * N + t * 128 + r;
+        n_id = p.order ? __ldg(p.order + (size_t)b * N + t * 128 + r) : t * 128 + r;   // tile = 128 consecutive points of the order
+        if (sub == 0) sN[par * 128 + r] = n_id;
+        const size_t pn = (size_t)b * N + n_id;
         id = __ldg(reinterpret_cast<const int4*>(p.idx + pn * 4));
         cw = __ldg(reinterpret_cast<const float4*>(p.clos + pn * 4));
         px = __ldg(p.pcl + pn * 3);
         py = __ldg(p.pcl + pn * 3 + 1);
         pz = __ldg(p.pcl + pn * 3 + 2);
     };
-    if ((int)blockIdx.x < p.B * T) fetch_point(blockIdx.x);
+    if ((int)blockIdx.x < p.B * T) fetch_point(blockIdx.x, 0);
 
     for (int tile = blockIdx.x; tile < p.B * T; tile += gridDim.x) {
         const int b = tile / T, t = tile - b * T;
@@ -249,7 +293,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         w_ready = true;
         // ---- while the MMAs run: next tile's point inputs, and the softmax numerators p = exp(w - max) (bf16-rounded, as the MMA
         //      will see them) with their per-joint sums
-        if (tile + (int)gridDim.x < p.B * T) fetch_point(tile + gridDim.x);
+        if (tile + (int)gridDim.x < p.B * T) fetch_point(tile + gridDim.x, tile_par ^ 1);
         float* ms = p.part_ms + ((size_t)b * T + t) * 64;
         float pj[8];   // joints [8 sub, 8 sub + 8) of this point
 #pragma unroll
@@ -278,7 +322,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         stamp();
         // ---- epilogue: e = relu(relu(acc1 + b1) + acc2 + b2) -> global (bf16) and MN-major A operand (sA2 region)
         {
-            __nv_bfloat16* eo = p.e_out + ((size_t)b * N + t * 128 + row) * 128 + 32 * cg;
+            __nv_bfloat16* eo = p.e_out + ((size_t)b * N + sN[tile_par * 128 + row]) * 128 + 32 * cg;
             float a[32], rr[32];
             tmem_ld_nw<32>(tmem + ACC1 + 32 * cg, a);
             tmem_ld_nw<32>(tmem + ACC2 + 32 * cg, rr);
@@ -317,13 +361,14 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
             o[1] = make_float4(a[4], a[5], a[6], a[7]);
         }
         tc_fence_before();
+        tile_par ^= 1;
         stamp();
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem0, 512);
 }
 
-constexpr size_t PE_SMEM = (size_t)(3 * 2048 + 4096 + 2048) * 16 + (128 + 128 + 256 + 21 * 129 + 3) * 4;
+constexpr size_t PE_SMEM = (size_t)(3 * 2048 + 4096 + 2048) * 16 + (128 + 128 + 256 + 21 * 129 + 3 + 256) * 4;
 
 }  // namespace kpf
 
@@ -337,6 +382,11 @@ extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const voi
         kpf::set_smem(repack_kernel<float>, 0);
         repack_kernel<float><<<grid, 256, 0, stream>>>((const float*)f_d, (const float*)f_rgb, (const float*)f_w, w_batch_stride, C, J, HW,
                                                       (__nv_bfloat16*)out);
+    } else if (dtype == KPF_BF16 && HW % 128 == 0 && ((uintptr_t)f_d % 16) == 0 && ((uintptr_t)f_rgb % 16) == 0 && ((uintptr_t)f_w % 16) == 0 &&
+               w_batch_stride % 8 == 0) {
+        kpf::set_smem(repack_bf16_kernel, 0);
+        repack_bf16_kernel<<<dim3(HW / 128, 5, B), 256, 0, stream>>>((const __nv_bfloat16*)f_d, (const __nv_bfloat16*)f_rgb,
+                                                                    (const __nv_bfloat16*)f_w, w_batch_stride, J, HW, (__nv_bfloat16*)out);
     } else if (dtype == KPF_BF16) {
         kpf::set_smem(repack_kernel<__nv_bfloat16>, 0);
         repack_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)f_d, (const __nv_bfloat16*)f_rgb,
@@ -349,14 +399,14 @@ extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const voi
 }
 
 extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
-                               const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out,
+                               const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out,
                                float* part_acc, float* part_ms, int num_sms, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && J >= 1 && J <= 21 && HW >= 1 && num_sms >= 1);
     KPF_REQUIRE(((uintptr_t)featT % 16) == 0 && ((uintptr_t)wmat % 16) == 0 && ((uintptr_t)idx % 16) == 0 && ((uintptr_t)clos % 16) == 0);
     if (B == 0) return 0;
     PointParams p;
-    p.featT = (const uint4*)featT; p.idx = idx; p.clos = clos; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat; p.wvec = wvec;
+    p.featT = (const uint4*)featT; p.idx = idx; p.clos = clos; p.pcl = pcl; p.joint = joint; p.order = order; p.wmat = (const uint4*)wmat; p.wvec = wvec;
     p.e_out = (__nv_bfloat16*)e_out; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
     p.kernel_size = kernel_size;
     p.dbg = dbg;

@@ -355,7 +355,7 @@ class Block_KPFusion(_KernelCache, nn.Module):
                     W_joint=torch.cat([Wj, Wjx], 1).contiguous(), b_joint=(bj + bjx).contiguous(), pe_wmat=pe_wmat, pe_wvec=pe_wvec)
 
     def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
-                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None):
+                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None, point_order=None):
         k = self.kc()
         B, N, _ = pcl.shape
         C, H = img_feat.shape[1], img_feat.shape[2]
@@ -370,7 +370,8 @@ class Block_KPFusion(_KernelCache, nn.Module):
             #   point stage (K4b + K3 + embeddings + softmax partials) -> DESA -> [fusion conv + init_TR] -> K5 -> [crossTR + final_TR]
             if featT is None:
                 featT = ops.repack_features(img_feat, img_feature_rgb, img_offset[:, J * 4:])
-            e, p_acc, p_ms = ops.point_embed(featT, pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8)
+            e, p_acc, p_ms = ops.point_embed(featT, pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8,
+                                             order=point_order)
             part, jf = ops.desa_fused(e, p_acc, p_ms, pcl, joint_xyz, k["ds_wmat"], k["ds_wvec"], self.FA.radius, self.FA.S[0])
             outfeature_init_TR, refined_3d_joints, _ = ops.token_stack(k["tok_init"], desa=part, jf=jf)        # model.py:203, :330
             spatial_weight_loss, img_feat_j = ops.spatial_aggregate_tc(
@@ -448,8 +449,11 @@ class KPFusion(nn.Module):
         joint_xyz = ops.uvd2xyz(joint_uvd, center, M, cube, cam_para, loader.img_size, loader.flip)      # :410
         # (measured: forking K2 and the K4a + repack branch onto parallel streams inside the graph is SLOWER than this serial
         #  order on B200 -- 1.283 vs 1.240 ms per step -- so the chain stays single-stream)
+        # processing order of the points by feature-map cell: warps / point tiles then touch neighbouring cells (K2's insertions
+        # coincide, the point stage's gathers hit the same lines); the results do not depend on it
+        order = ops.spatial_order(pcl, center, M, cube, cam_para, loader.img_size, H, loader.flip) if pcl.shape[1] <= 8192 else None
         pcl_closeness, _, pcl_index = ops.img2pcl_index(pcl, img_down, center, M, cube, cam_para, loader.img_size, 4, loader.flip,
-                                                        want_i64=False, want_i32=True)                  # :411
+                                                        want_i64=False, want_i32=True, order=order)     # :411
         updated_2d_feature = [None] * (self.num_stages + 1)
         spatial_weight = [None] * self.num_stages
         featT = None
@@ -459,7 +463,7 @@ class KPFusion(nn.Module):
             block = getattr(self, f"block{i + 1}")
             r3d, r2d, updated_2d_feature[i + 1], spatial_weight[i], _ = block(
                 img_feat, img_feat_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature[i], loader, img_down,
-                center, M, cube, cam_para, writer, ii, featT=featT)
+                center, M, cube, cam_para, writer, ii, featT=featT, point_order=order)
             result.append(r3d)
             result.append(r2d)
             joint_xyz = r2d

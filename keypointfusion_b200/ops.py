@@ -131,7 +131,17 @@ def xyz2uvd(xyz, center, M, cube, cam, img_size, flip=1.0):
 
 
 # ------------------------------------------------------------------------------------------------ a6
-def img2pcl_index(pcl, img, center, M, cube, cam, img_size, select_num=9, flip=1.0, fs=None, want_i64=True, want_i32=False):
+def spatial_order(pcl, center, M, cube, cam, img_size, fs, flip=1.0):
+    """[B,N] i32 permutation sorting each sample's points by the fs x fs cell they project to (scheduling aid for
+    img2pcl_index / point_embed; results do not depend on it)."""
+    pcl, center, M, cube, cam = _f32(pcl), _f32(center), _f32(M), _f32(cube), _f32(cam)
+    B, N, _ = pcl.shape
+    order = torch.empty(B, N, device=pcl.device, dtype=torch.int32)
+    _call("kpf_spatial_order", _p(pcl), _p(center), _p(M), _p(cube), _p(cam), B, N, int(fs), float(img_size), float(flip), _p(order))
+    return order
+
+
+def img2pcl_index(pcl, img, center, M, cube, cam, img_size, select_num=9, flip=1.0, fs=None, want_i64=True, want_i32=False, order=None):
     pcl, center, M, cube, cam = _f32(pcl), _f32(center), _f32(M), _f32(cube), _f32(cam)
     d, bs, rs, cs, fs = _depth_view(img, fs)
     B, N, _ = pcl.shape
@@ -139,7 +149,7 @@ def img2pcl_index(pcl, img, center, M, cube, cam, img_size, select_num=9, flip=1
     i64 = torch.empty(B, N, select_num, device=pcl.device, dtype=torch.int64) if want_i64 else None
     i32 = torch.empty(B, N, select_num, device=pcl.device, dtype=torch.int32) if want_i32 else None
     _call("kpf_img2pcl_index", _p(pcl), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam), B, N, fs, float(img_size),
-          float(flip), select_num, _p(close), _p(i64), _p(i32))
+          float(flip), select_num, _p(order), _p(close), _p(i64), _p(i32))
     return close, i64, i32
 
 
@@ -486,7 +496,7 @@ def pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, J):
     return wmat, wvec
 
 
-def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg=None):
+def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg=None, order=None):
     """-> e [B,N,128] bf16, part_acc [B,T,128,32] f32, part_ms [B,T,2,32] f32  (T = N/128)."""
     _need_cuda(featT, idx32, clos, pcl, joint)
     pcl, joint, clos = _f32(pcl), _f32(joint), _f32(clos)
@@ -499,7 +509,8 @@ def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg
     e = torch.empty(B, N, 128, device=dev, dtype=torch.bfloat16)
     acc = torch.empty(B, T, 128, 32, device=dev, dtype=torch.float32)
     ms = torch.empty(B, T, 2, 32, device=dev, dtype=torch.float32)
-    _call("kpf_point_embed", _p(featT), _p(idx32), _p(clos), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, HW, float(kernel_size), _p(e),
+    _call("kpf_point_embed", _p(featT), _p(idx32), _p(clos), _p(pcl), _p(joint), _p(order), _p(wmat), _p(wvec), B, N, J, HW,
+          float(kernel_size), _p(e),
           _p(acc), _p(ms), sm_count(dev), _p(dbg))
     return e, acc, ms
 

@@ -9,9 +9,11 @@ import numpy as np
 import torch
 
 
-def make_depth_crops(B, S=128, seed=0):
-    """`img [B,1,S,S]` f32: background exactly 1.0, hand = disc of radius 0.3125*S with values U(-0.6,0.6),
-    plus planted edge cases (isclose band, 0.99 threshold, exact-zero depth)."""
+def make_depth_crops(B, S=128, seed=0, noise=0.35):
+    """`img [B,1,S,S]` f32: background exactly 1.0, hand = disc of radius ~0.3125*S holding a smooth surface plus U(-noise, noise)
+    per-pixel noise (normalised depth: 1.0 = half the crop cube, 125 mm), plus planted edge cases (isclose band, 0.99 threshold).
+    noise = 0.35 (+-44 mm, the default the parity tests use) scatters a point's 3-D nearest cells over many feature-map cells --
+    a worst case for every locality heuristic; a depth sensor is closer to noise = 0.02 (+-2.5 mm)."""
     rs = np.random.RandomState(seed)
     img = np.ones((B, 1, S, S), np.float32)
     yy, xx = np.mgrid[0:S, 0:S]
@@ -22,7 +24,7 @@ def make_depth_crops(B, S=128, seed=0):
         disc = (xx + 0.5 - cx) ** 2 + (yy + 0.5 - cy) ** 2 <= rad ** 2
         # smooth-ish surface + noise so neighbouring cells are close in 3-D, like a real hand
         base = 0.25 * np.sin((xx + 3 * b) / S * 5.0) * np.cos(yy / S * 4.0)
-        vals = (base + rs.uniform(-0.35, 0.35, size=(S, S))).astype(np.float32)
+        vals = (base + rs.uniform(-noise, noise, size=(S, S))).astype(np.float32)
         img[b, 0][disc] = vals[disc]
         # planted edge cases inside the disc
         c = S // 2
@@ -61,10 +63,10 @@ def make_feature_maps(B, J=21, C=128, H=32, seed=0):
     return img_feat, img_feat_rgb, img_offset
 
 
-def make_inputs(B, S=128, J=21, C=128, seed=0, as_torch=True, bf16_round=False):
+def make_inputs(B, S=128, J=21, C=128, seed=0, as_torch=True, bf16_round=False, depth_noise=0.35):
     """Everything the fusion path consumes (fusion-path-only configs feed feature maps directly)."""
     H = S // 4
-    img = make_depth_crops(B, S, seed)
+    img = make_depth_crops(B, S, seed, depth_noise)
     center, M, cube, cam = make_camera(B, S, seed)
     img_feat, img_feat_rgb, img_offset = make_feature_maps(B, J, C, H, seed)
     rs = np.random.RandomState(seed + 3000)

@@ -54,6 +54,16 @@ def test_point_embed(golden, golden_inputs, path_params, B):
     ragg = torch.softmax(pw.permute(0, 2, 1), -1) @ ee
     assert rms_rel(e, ee) < 1e-2, rms_rel(e, ee)
     assert rms_rel(agg, ragg) < 1e-2, rms_rel(agg, ragg)
+    # spatial processing order (scheduling aid): K2 and the point features are bit-identical, the aggregation only regroups
+    order = ops.spatial_order(pcl, c["center"], c["M"], c["cube"], c["cam"], 128, 32)
+    assert torch.equal(torch.sort(order.long(), dim=1)[0].cpu(), torch.arange(pcl.shape[1]).expand(B, -1))
+    close2, _, idx2 = ops.img2pcl_index(pcl, c["img"], c["center"], c["M"], c["cube"], c["cam"], 128, 4, fs=32, want_i64=False, want_i32=True,
+                                        order=order)
+    assert torch.equal(idx2, idx) and torch.equal(close2, close)
+    e2, acc2, ms2 = ops.point_embed(featT, idx, close, pcl, joint.to(DEV), k["pe_wmat"], k["pe_wvec"], 0.8, order=order)
+    assert torch.equal(e2, e)
+    agg2 = ops.combine_point_partials(acc2, ms2, 21)
+    assert rms_rel(agg2, ragg) < 1e-2 and rms_rel(agg2, agg) < 2e-3, (rms_rel(agg2, ragg), rms_rel(agg2, agg))
 
 
 @pytest.mark.parametrize("B", [2, 3])
