@@ -9,7 +9,7 @@
 // layout and read by GEMM A as an MN-major A operand (M = hw contiguous) and -- same bytes, LBO/SBO swapped, after an
 // in-place relu pass -- by GEMM B as a K-major A operand (K = hw contiguous).  One CTA per sample sweeps its HW/128
 // tiles, accumulating out[c][j] in TMEM; the next tile's features are prefetched while the current one is consumed.
-#include "umma.cuh"
+#include "tmem_ldst.cuh"
 
 namespace kpf {
 
@@ -46,7 +46,9 @@ __device__ __forceinline__ float3 uvd2xyz_fast(const CamF& c, float un, float vn
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const SpatialParams p) {
+constexpr int K5_NT = 512;   // thread = (cell or channel row = 32 * (warp % 4) + lane, joint group warp / 4 of 8 joints)
+
+__global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const SpatialParams p) {
     extern __shared__ __align__(128) unsigned char k5_smem[];
     uint4* sF = reinterpret_cast<uint4*>(k5_smem);  // [2][2048] double-buffered raw feature tile, index (c/8)*128 + (hw/8)*8 + (c%8)
     uint4* sFr = sF + 4096;                          // [2048]   relu copy
@@ -58,12 +60,12 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ CamF cam;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = warp_index_uniform();  // MMA issue: one elected lane of warp 0 from warp-uniform code (umma.cuh)
+    const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane;   // TMEM lane `row` (cell / channel), joints [8cg, 8cg + 8)
     const int b = blockIdx.x / p.split, sp = blockIdx.x - b * p.split, J = p.J, fs = p.fs, HW = fs * fs, T = HW / 128;
     const int t_begin = sp * (T / p.split), t_end = t_begin + T / p.split;
     __shared__ int s_last;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const uint32_t ACC1 = 0, ACC2 = 32;
     int n_stamp = 0;
     auto stamp = [&]() {
@@ -78,15 +80,18 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         fence_mbar_init();
         load_cam(cam, b, p.center, p.M, p.cube, p.cam, p.img_size, p.flip);
     }
-    for (int i = tid; i < 640; i += 128) sWa[i] = p.wa[i];
+    for (int i = tid; i < 640; i += K5_NT) sWa[i] = p.wa[i];
     if (tid < 32) sBa[tid] = tid < J ? p.ba[tid] : 0.f;
     const __nv_bfloat16* fb = p.feat + (size_t)b * 128 * HW;
-    // tile loader: thread -> (c%8 = tid%8, hw8 = tid/8); 16 passes over c/8
+    // tile loader: thread -> (c%8 = tid%8, hw8 = (tid/8)%16, channel group tid/128 + 4i): 16-byte cp.async, 128 contiguous bytes
+    // of a channel row per 8 lanes
     auto load_tile = [&](int t, uint4* dst) {
-        const int c8 = tid & 7, hw8 = tid >> 3;
-#pragma unroll 4
-        for (int cg = 0; cg < 16; ++cg)
-            cp_async16(dst + cg * 128 + hw8 * 8 + c8, fb + (size_t)(cg * 8 + c8) * HW + t * 128 + hw8 * 8);
+        const int c8 = tid & 7, hw8 = (tid >> 3) & 15;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cgp = (tid >> 7) + 4 * i;
+            cp_async16(dst + cgp * 128 + hw8 * 8 + c8, fb + (size_t)(cgp * 8 + c8) * HW + t * 128 + hw8 * 8);
+        }
     };
     load_tile(t_begin, sF);
     tc_fence_before();
@@ -96,12 +101,12 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         const float* s = p.joints + ((size_t)b * J + tid) * 3;
         sJ[8 * tid + 0] = (s[0] + 1.f) / 2.f * (float)fs;  // generateFeature.py:592-593
         sJ[8 * tid + 1] = (s[1] + 1.f) / 2.f * (float)fs;
-        const float3 q = uvd2xyz(cam, s[0], s[1], s[2]);   // loader.py:800
-        sJ[8 * tid + 2] = q.x;
-        sJ[8 * tid + 3] = q.y;
-        sJ[8 * tid + 4] = q.z;
+        const float3 qj = uvd2xyz(cam, s[0], s[1], s[2]);  // loader.py:800
+        sJ[8 * tid + 2] = qj.x;
+        sJ[8 * tid + 3] = qj.y;
+        sJ[8 * tid + 4] = qj.z;
     }
-    const uint32_t tmem0 = tmem_slot, tmem = tmem0 + lane_off;
+    const uint32_t tmem0 = tmem_slot, tmem = tmem0 + ((uint32_t)(32 * q) << 16);
     uint32_t phase = 0;
     const float sg = 1.f / (1.f + __expf(-p.weight_dis[0]));
     const float inv2s2 = 1.f / (2.f * p.hm_sigma * p.hm_sigma * p.hm_std * p.hm_std);
@@ -115,34 +120,35 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         __syncthreads();       // ... and everybody's; the other buffer's readers (tile t-1) are done
         if (t + 1 < t_end) load_tile(t + 1, sF + ((t + 1 - t_begin) & 1) * 2048);  // overlaps the whole iteration
         if (t == t_begin + 1) stamp();
-        // ---- per-cell geometry (thread = cell): heat-map row (A operand) and GAM (registers)
-        const int m = t * 128 + tid, r = m / fs, col = m - r * fs;
+        // ---- per-cell geometry (thread = cell `row`, joints [8cg, 8cg + 8)): heat-map chunk (A operand) and GAM (registers)
+        const int m = t * 128 + row, r = m / fs, col = m - r * fs;
         const float d = __ldg(p.depth + (size_t)b * p.depth_bs + (size_t)r * p.depth_rs + (size_t)col * p.depth_cs);
-        const float3 q = uvd2xyz_fast(cam, (2.f * col + 1.f) * inv_fs - 1.f, (2.f * r + 1.f) * inv_fs - 1.f, d);
-        float gam[32], hm[32];
+        const float3 qc = uvd2xyz_fast(cam, (2.f * col + 1.f) * inv_fs - 1.f, (2.f * r + 1.f) * inv_fs - 1.f, d);
+        float gam[8], hm[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int i = 0; i < 8; ++i) {
+            const int j = 8 * cg + i;
             if (j < J) {
                 const float dx = (float)col + 0.5f - sJ[8 * j], dy = (float)r + 0.5f - sJ[8 * j + 1];
-                hm[j] = __expf(-(dx * dx + dy * dy) * inv2s2);
-                const float ex = q.x - sJ[8 * j + 2], ey = q.y - sJ[8 * j + 3], ez = q.z - sJ[8 * j + 4];
-                gam[j] = __fdividef(1.f, p.gamma * (ex * ex + ey * ey + ez * ez) + 1.f);
+                hm[i] = __expf(-(dx * dx + dy * dy) * inv2s2);
+                const float ex = qc.x - sJ[8 * j + 2], ey = qc.y - sJ[8 * j + 3], ez = qc.z - sJ[8 * j + 4];
+                gam[i] = __fdividef(1.f, p.gamma * (ex * ex + ey * ey + ez * ez) + 1.f);
             } else {
-                hm[j] = 0.f;
-                gam[j] = 0.f;
+                hm[i] = 0.f;
+                gam[i] = 0.f;
             }
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sHm[c * 128 + tid] = pack8_bf16(hm + 8 * c);
+        sHm[cg * 128 + row] = pack8_bf16(hm);
         if (t == t_begin + 1) stamp();
         // relu copy for GEMM B (same layout)
-        for (int i = tid; i < 2048; i += 128) {
-            uint4 v = cur[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 v = cur[tid + i * K5_NT];
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
             const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < 4; ++k) h[k] = __hmax2(h[k], z);
-            sFr[i] = v;
+            sFr[tid + i * K5_NT] = v;
         }
         if (t == t_begin + 1) stamp();
         fence_proxy_async();
@@ -159,26 +165,26 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
             }
             __syncwarp();
         }
+        const float fw = __ldg(p.fc_w + m);
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
         if (t == t_begin + 1) stamp();
         {
-            float s1[32];
-            tmem_ld32(tmem + ACC1, s1);
-            const float fw = p.fc_w[m];
+            float s1[8];
+            tmem_ld<8>(tmem + ACC1 + 8 * cg, s1);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int i = 0; i < 8; ++i) {
+                const int j = 8 * cg + i;
                 if (j < J) {
-                    const float swv = __fdividef(1.f, 1.f + __expf(-(s1[j] + sBa[j])));
+                    const float swv = __fdividef(1.f, 1.f + __expf(-(s1[i] + sBa[j])));
                     p.sw_out[((size_t)b * J + j) * HW + m] = swv;
-                    s1[j] = fw * (sg * gam[j] + (1.f - sg) * swv);  // model.py:337-338 and fc_spatial2joint_feature's weight
+                    s1[i] = fw * (sg * gam[i] + (1.f - sg) * swv);  // model.py:337-338 and fc_spatial2joint_feature's weight
                 } else {
-                    s1[j] = 0.f;
+                    s1[i] = 0.f;
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) sG[(tid >> 3) * 32 + c * 8 + (tid & 7)] = pack8_bf16(s1 + 8 * c);
+            sG[(row >> 3) * 32 + cg * 8 + (row & 7)] = pack8_bf16(s1);
         }
         if (t == t_begin + 1) stamp();
         fence_proxy_async();
@@ -201,13 +207,13 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
     }
     stamp();
     {
-        float o[32];
-        tmem_ld32(tmem + ACC2, o);  // thread = channel c: this CTA's partial out[c][0..31]
+        float o[8];
+        tmem_ld<8>(tmem + ACC2 + 8 * cg, o);  // thread = (channel `row`, joints [8cg, 8cg + 8)): this CTA's partial out[c][j]
         if (p.split > 1) {
             // deterministic cross-CTA reduction: publish the partial, the last CTA of the sample sums them in split order
-            float4* dst = reinterpret_cast<float4*>(p.scratch + (((size_t)b * p.split + sp) * 128 + tid) * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            float4* dst = reinterpret_cast<float4*>(p.scratch + (((size_t)b * p.split + sp) * 128 + row) * 32 + 8 * cg);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
             __threadfence();
             __syncthreads();
             if (tid == 0) s_last = (atomicAdd(p.counters + b, 1) == p.split - 1);
@@ -215,17 +221,18 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
             if (s_last) {
                 __threadfence();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = 0.f;
-                for (int q = 0; q < p.split; ++q) {
-                    const float4* src = reinterpret_cast<const float4*>(p.scratch + (((size_t)b * p.split + q) * 128 + tid) * 32);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 v = __ldcg(src + i);
-                        o[4 * i] += v.x;
-                        o[4 * i + 1] += v.y;
-                        o[4 * i + 2] += v.z;
-                        o[4 * i + 3] += v.w;
-                    }
+                for (int j = 0; j < 8; ++j) o[j] = 0.f;
+                for (int qq = 0; qq < p.split; ++qq) {
+                    const float4* src = reinterpret_cast<const float4*>(p.scratch + (((size_t)b * p.split + qq) * 128 + row) * 32 + 8 * cg);
+                    const float4 v0 = __ldcg(src), v1 = __ldcg(src + 1);
+                    o[0] += v0.x;
+                    o[1] += v0.y;
+                    o[2] += v0.z;
+                    o[3] += v0.w;
+                    o[4] += v1.x;
+                    o[5] += v1.y;
+                    o[6] += v1.z;
+                    o[7] += v1.w;
                 }
                 if (tid == 0) p.counters[b] = 0;  // ready for the next launch / graph replay
             }
@@ -233,10 +240,11 @@ __global__ void __launch_bounds__(128) spatial_aggregate_tc_kernel(const Spatial
         if (p.split == 1 || s_last) {
             const float fb0 = p.fc_b[0];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int i = 0; i < 8; ++i) {
+                const int j = 8 * cg + i;
                 if (j < J) {
-                    float v = o[j] + fb0;
-                    const size_t idx = ((size_t)b * J + j) * 128 + tid;
+                    float v = o[i] + fb0;
+                    const size_t idx = ((size_t)b * J + j) * 128 + row;
                     if (p.prev) v = fmaxf((v + p.prev[idx]) * 0.5f, 0.f);  // model.py:343-344
                     p.feat_j_out[idx] = v;
                 }
@@ -270,7 +278,7 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joint
     const size_t smem = (size_t)(4096 + 2048 + 512 + 512 + 640) * 16 + 32 * 8 * 4 + 32 * 4;
     cudaError_t e = kpf::set_smem(spatial_aggregate_tc_kernel, smem);
     if (e != cudaSuccess) return (int)e;
-    spatial_aggregate_tc_kernel<<<B * split, 128, smem, stream>>>(p);
+    spatial_aggregate_tc_kernel<<<B * split, K5_NT, smem, stream>>>(p);
     KPF_CHECK_LAUNCH();
     return 0;
 }

@@ -4,6 +4,7 @@ Each function validates shapes/dtypes/devices in Python, allocates outputs with 
 launches the kernel on `torch.cuda.current_stream()`.  There is NO fallback: non-CUDA tensors raise.
 """
 import ctypes
+import os
 
 import torch
 
@@ -593,7 +594,9 @@ def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed,
     sw = torch.empty(B, J, fs, fs, device=feat_rgb.device, dtype=torch.float32)
     fj = torch.empty(B, J, C, device=feat_rgb.device, dtype=torch.float32)
     T = fs * fs // 128
-    split = 4 if T % 4 == 0 else (2 if T % 2 == 0 else 1)
+    # cell tiles of a sample spread over `split` CTAs: as many as still fit in ONE wave of one-CTA-per-SM (measured at B = 64:
+    # split 1 / 2 / 4 / 8 -> 60 / 39 / 47 / 62 us)
+    split = next((s_ for s_ in (8, 4, 2) if T % s_ == 0 and B * s_ <= sm_count(feat_rgb.device)), 1)
     scratch = torch.empty(B, split, 128, 32, device=feat_rgb.device, dtype=torch.float32) if split > 1 else None
     counters = _zero_counters(B, feat_rgb.device) if split > 1 else None
     _call("kpf_spatial_aggregate_tc", _p(feat_rgb), _p(joints), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam), _p(wa_packed),
