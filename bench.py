@@ -358,6 +358,11 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
         e_, acc_, ms_ = ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order)
         part_, jf_ = ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0])
         tok_, r3d_, _ = ops.token_stack(k["tok_init"], desa=part_, jf=jf_)
+        # per-set point clouds / orders for the kernels whose cost depends on the points matching the depth map they came from
+        geo = {}
+        for d in sets:
+            p_, _ = ops.getpcl(d["img"], d["center"], d["cube"], d["M"], d["cam"], N_PTS, seed=0)
+            geo[id(d)] = (p_, ops.spatial_order(p_, d["center"], d["M"], d["cube"], d["cam"], S, H))
     e = 2  # bf16 feature maps
     # name -> (callable, launches per step, algorithmic bytes per launch, algorithmic FLOPs per launch, bound)
     stages = {
@@ -372,8 +377,8 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
                                                                           blk.weight_dis, blk.fc_spatial2joint_feature.weight,
                                                                           blk.fc_spatial2joint_feature.bias), 2,
                                         B * (C * H * H * e + J * H * H * 4 + J * C * 4), B * 12.04e6, "hbm"),
-        "nearest_cells_kernel": (lambda d: ops.img2pcl_index(pcl, d["img"], d["center"], d["M"], d["cube"], d["cam"], S, 4, fs=H, want_i64=False,
-                                                             want_i32=True, order=order), 1, B * (N_PTS * 12 + H * H * 4 + 76 + N_PTS * 4 * 8), B * 8.39e6, "hbm"),
+        "nearest_cells_kernel": (lambda d: ops.img2pcl_index(geo[id(d)][0], d["img"], d["center"], d["M"], d["cube"], d["cam"], S, 4, fs=H,
+                                                             want_i64=False, want_i32=True, order=geo[id(d)][1]), 1, B * (N_PTS * 12 + H * H * 4 + 76 + N_PTS * 4 * 8), B * 8.39e6, "hbm"),
         "repack_kernel": (lambda d: ops.repack_features(d["img_feat"], d["img_feat_rgb"], d["img_offset"][:, 4 * J:]), 1,
                           B * ((2 * C + J) * H * H * e + 288 * H * H * 2), 0.0, "hbm"),
         "offset2joint_kernel": (lambda d: ops.offset2joint_weight(d["img_offset"], d["img"], 0.8), 1, B * (5 * J * H * H * e + H * H * 4), B * 0.3e6,

@@ -112,9 +112,10 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
                      const float* __restrict__ cube, const float* __restrict__ cam, int N, int fs, float img_size, float flip,
                      const int32_t* __restrict__ order, float* __restrict__ closeness, long long* __restrict__ index64,
                      int32_t* __restrict__ index32) {
-    extern __shared__ __align__(16) float4 cells[];
+    extern __shared__ __align__(16) float4 cells[];      // [HW] cell xyz, then [fs][2] per-row bounding boxes (min, max)
     __shared__ CamF c;
     const int b = blockIdx.y, HW = fs * fs;
+    float4* rowbox = cells + HW;
     if (threadIdx.x == 0) load_cam(c, b, center, M, cube, cam, img_size, flip);
     __syncthreads();
     const float ffs = (float)fs;
@@ -125,11 +126,40 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
         cells[m] = make_float4(q.x, q.y, q.z, 0.f);
     }
     __syncthreads();
+    // bounding box of every cell row (one warp per row): whole rows are skipped below when no lane of a warp can improve on it
+    {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int r = w; r < fs; r += nw) {
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int col = lane; col < fs; col += 32) {
+                const float4 q = cells[r * fs + col];
+                lo[0] = fminf(lo[0], q.x);
+                hi[0] = fmaxf(hi[0], q.x);
+                lo[1] = fminf(lo[1], q.y);
+                hi[1] = fmaxf(hi[1], q.y);
+                lo[2] = fminf(lo[2], q.z);
+                hi[2] = fmaxf(hi[2], q.z);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+                    hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+                }
+            }
+            if (lane == 0) {
+                rowbox[2 * r] = make_float4(lo[0], lo[1], lo[2], 0.f);
+                rowbox[2 * r + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+            }
+        }
+    }
+    __syncthreads();
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= N) return;
-    // optional processing order (kpf_spatial_order): neighbouring threads then hold neighbouring points, so a warp's lanes take
-    // the insertion path at the same cells; the outputs are indexed by the point id either way
-    const int n = order ? order[(size_t)b * N + slot] : slot;
+    const bool active = slot < N;   // inactive lanes stay in the loop (warp votes below) but never store
+    // optional processing order (kpf_spatial_order): neighbouring threads then hold neighbouring points, so a warp's lanes prune
+    // the same rows and take the insertion path at the same cells; the outputs are indexed by the point id either way
+    const int n = !active ? 0 : (order ? order[(size_t)b * N + slot] : slot);
     const float* pp = pcl + ((size_t)b * N + n) * 3;
     const float px = pp[0], py = pp[1], pz = pp[2];
     float bd[K];
@@ -182,29 +212,40 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
             for (int cc = 0; cc < 8; ++cc) insert(dist2(cells[m0 + cc]), m0 + cc);
         }
     }
-    // full scan, four cells per iteration: the distance arithmetic of a group is branch-free
-    int m = 0, row = 0, col = 0;
-    for (; m + 4 <= HW; m += 4) {
-        float d2[4];
+    // full scan, four cells per iteration: the distance arithmetic of a group is branch-free.  A cell row is skipped when, for
+    // every lane of the warp, the distance from its point to the row's bounding box already exceeds its K-th best (with a 1e-4
+    // relative margin, far above fp32 rounding, so no candidate -- not even an exact tie -- is ever lost).
+    int m = 0;
+    if (windowed) {
+        for (int row = 0; row < fs; ++row) {
+            const float4 lo = rowbox[2 * row], hi = rowbox[2 * row + 1];
+            const float ex = fmaxf(fmaxf(lo.x - px, px - hi.x), 0.f), ey = fmaxf(fmaxf(lo.y - py, py - hi.y), 0.f),
+                        ez = fmaxf(fmaxf(lo.z - pz, pz - hi.z), 0.f);
+            const float lb = ex * ex + ey * ey + ez * ez;
+            const bool skip = !active || lb > bd[K - 1] * 1.0001f;
+            if (__all_sync(0xffffffffu, skip)) continue;
+            const bool in_rows = (unsigned)(row - wr0) < 3u;
+            for (int col = 0; col < fs; col += 4) {
+                const int mm = row * fs + col;
+                float d2[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) d2[u] = dist2(cells[m + u]);
-        const float mn = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
-        const bool inwin = (unsigned)(row - wr0) < 3u && (unsigned)(col - wc0) < 8u;   // already inserted
-        if (!inwin && mn <= bd[K - 1]) {
+                for (int u = 0; u < 4; ++u) d2[u] = dist2(cells[mm + u]);
+                const float mn = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
+                const bool inwin = in_rows && (unsigned)(col - wc0) < 8u;   // already inserted
+                if (!inwin && mn <= bd[K - 1]) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (d2[u] <= bd[K - 1]) insert(d2[u], m + u);
+                    for (int u = 0; u < 4; ++u)
+                        if (d2[u] <= bd[K - 1]) insert(d2[u], mm + u);
+                }
+            }
         }
-        col += 4;
-        if (col >= fs) {   // only meaningful when fs % 4 == 0 (the windowed case)
-            col = 0;
-            ++row;
-        }
+        m = HW;
     }
-    for (; m < HW; ++m) {
+    for (; m < HW; ++m) {   // map sizes without the windowed fast path
         const float d2 = dist2(cells[m]);
         if (d2 <= bd[K - 1]) insert(d2, m);
     }
+    if (!active) return;
     float cv[K];
     float s = 0.f;
 #pragma unroll
@@ -428,7 +469,7 @@ extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long
     KPF_REQUIRE(B >= 0 && N >= 0 && fs >= 1 && fs * fs <= 8192 && K >= 1 && K <= fs * fs);
     if (B == 0 || N == 0) return 0;
     dim3 grid((N + 255) / 256, B);
-    const size_t smem = (size_t)fs * fs * sizeof(float4);
+    const size_t smem = ((size_t)fs * fs + 2 * (size_t)fs) * sizeof(float4);
 #define KPF_LAUNCH_K2(KK)                                                                                                    \
     case KK: {                                                                                                               \
         cudaError_t e = kpf::set_smem(nearest_cells_kernel<KK>, smem); \
