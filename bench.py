@@ -368,7 +368,7 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
     stages = {
         "token_stack_kernel": (lambda d: ops.token_stack(k["tok_init"], desa=part_, jf=jf_), 4,
                                B * (4 * J * C * 4 + J * C * 4 + J * 12), B * 16.1e6, "tensor"),
-        "desa_fused_kernel": (lambda d: ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0]), 2,
+        "desa_prep_kernel+desa_tile_kernel": (lambda d: ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0]), 2,
                               B * (3 * J * 64 * C * e + N_PTS * 12 + 4 * J * C * 4), B * 270.1e6, "tensor"),
         "point_embed_kernel": (lambda d: ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order), 2,
                                B * ((2 * C + J) * H * H * e + N_PTS * 4 * 8 + N_PTS * C * e), B * 95.4e6, "tensor"),
@@ -379,10 +379,12 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
                                         B * (C * H * H * e + J * H * H * 4 + J * C * 4), B * 12.04e6, "hbm"),
         "nearest_cells_kernel": (lambda d: ops.img2pcl_index(geo[id(d)][0], d["img"], d["center"], d["M"], d["cube"], d["cam"], S, 4, fs=H,
                                                              want_i64=False, want_i32=True, order=geo[id(d)][1]), 1, B * (N_PTS * 12 + H * H * 4 + 76 + N_PTS * 4 * 8), B * 8.39e6, "hbm"),
-        "repack_kernel": (lambda d: ops.repack_features(d["img_feat"], d["img_feat_rgb"], d["img_offset"][:, 4 * J:]), 1,
+        "repack_bf16_kernel": (lambda d: ops.repack_features(d["img_feat"], d["img_feat_rgb"], d["img_offset"][:, 4 * J:]), 1,
                           B * ((2 * C + J) * H * H * e + 288 * H * H * 2), 0.0, "hbm"),
         "offset2joint_kernel": (lambda d: ops.offset2joint_weight(d["img_offset"], d["img"], 0.8), 1, B * (5 * J * H * H * e + H * H * 4), B * 0.3e6,
                                 "hbm"),
+        "spatial_order_kernel": (lambda d: ops.spatial_order(geo[id(d)][0], d["center"], d["M"], d["cube"], d["cam"], S, H), 1,
+                                 B * (N_PTS * 12 + N_PTS * 4), 0.0, "hbm"),
         "backproject_kernel": (lambda d: ops.getpcl(d["img"], d["center"], d["cube"], d["M"], d["cam"], N_PTS, seed=0), 1,
                                B * (S * S * 4 + 76 + N_PTS * 12), B * 0.33e6, "hbm"),
     }
@@ -424,7 +426,7 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
     return {"kernel": top, "bound": r["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
             "us_per_launch": r["us"], "launches_per_step": r["per_step"], "share_of_step": r["us"] * r["per_step"] / tot,
             "algorithmic_bytes": r["bytes"], "algorithmic_flops": r["flops"], "peaks": which,
-            "note": "latency-bound: small serial MMA->epilogue chains on <= 192 CTAs; see DESIGN.md section 4",
+            "note": "latency-bound: one sample per CTA, ~7 dependent MMA->epilogue steps per transformer layer; see DESIGN.md section 4",
             "kernels": {n: {"us": round(v["us"], 1), "per_step": v["per_step"]} for n, v in res.items()}}
 
 
