@@ -314,6 +314,73 @@ offset2joint_kernel(const T* __restrict__ offset, const float* __restrict__ dept
     }
 }
 
+// bf16 fast path of K4a for maps with HW == 8 * blockDim.x cells and fs % 8 == 0: a thread owns 8 consecutive cells of a row,
+// reads each of the joint's five channels with ONE 16-byte load, keeps everything in registers between the max pass and the
+// sum pass, and the four sums share one reduction round.  Same arithmetic per cell as the generic kernel above.
+__global__ void __launch_bounds__(128)
+offset2joint_bf16x8_kernel(const __nv_bfloat16* __restrict__ offset, const float* __restrict__ depth, int S, int J, int fs,
+                           const float* __restrict__ kernel_vec, float* __restrict__ joint_out) {
+    __shared__ float scratch[32];
+    __shared__ float4 part[4];
+    const int j = blockIdx.x, b = blockIdx.y, HW = fs * fs, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const __nv_bfloat16* base = offset + (size_t)b * 5 * J * HW;
+    const int m0 = 8 * tid, r = m0 / fs, col0 = m0 - r * fs;
+    const uint4 vx = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(3 * j) * HW + m0));
+    const uint4 vy = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(3 * j + 1) * HW + m0));
+    const uint4 vz = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(3 * j + 2) * HW + m0));
+    const uint4 vh = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(3 * J + j) * HW + m0));
+    const uint4 vw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(4 * J + j) * HW + m0));
+    const float* drow = depth + (size_t)b * S * S + (size_t)nearest_src(r, S, fs) * S;
+    float d[8], wv[8];
+    const __nv_bfloat16* pw = reinterpret_cast<const __nv_bfloat16*>(&vw);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        d[i] = __ldg(drow + nearest_src(col0 + i, S, fs));
+        wv[i] = d[i] > 0.99f ? -1e8f : __bfloat162float(pw[i]);  // masked_fill(depth.gt(0.99), -1e8)  :488
+        mx = fmaxf(mx, wv[i]);
+    }
+    mx = block_max(mx, scratch);
+    const float ks = kernel_vec[j], ffs = (float)fs;
+    const __nv_bfloat16 *px = reinterpret_cast<const __nv_bfloat16*>(&vx), *py = reinterpret_cast<const __nv_bfloat16*>(&vy),
+                        *pz = reinterpret_cast<const __nv_bfloat16*>(&vz), *ph = reinterpret_cast<const __nv_bfloat16*>(&vh);
+    float se = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    const float cr = cell_coord(r, ffs);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float e = expf(wv[i] - mx);
+        const float msk = d[i] < 0.99f ? 1.f : 0.f;                                   // depth.lt(0.99)  :485
+        const float dist = ks - (__bfloat162float(ph[i]) * msk) * ks;                 // :495
+        const float ox = __bfloat162float(px[i]) * msk, oy = __bfloat162float(py[i]) * msk, oz = __bfloat162float(pz[i]) * msk;
+        se += e;
+        ax += (ox * dist + cell_coord(col0 + i, ffs)) * e;                            // coords ch0 = column  :481
+        ay += (oy * dist + cr) * e;
+        az += (oz * dist + d[i]) * e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        se += __shfl_xor_sync(0xffffffffu, se, o);
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
+    }
+    if (lane == 0) part[w] = make_float4(se, ax, ay, az);
+    __syncthreads();
+    if (tid == 0) {
+        float4 t = part[0];
+        for (int k = 1; k < 4; ++k) {
+            t.x += part[k].x;
+            t.y += part[k].y;
+            t.z += part[k].z;
+            t.w += part[k].w;
+        }
+        float* o = joint_out + ((size_t)b * J + j) * 3;
+        o[0] = t.y / t.x;
+        o[1] = t.z / t.x;
+        o[2] = t.w / t.x;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4b / a7: pcl_joint2offset   model/model.py:503-525 -> [B,N,4J] (3J joint-major unit vectors, then J closeness)
 // ------------------------------------------------------------------------------------------------
@@ -504,6 +571,9 @@ extern "C" int kpf_offset2joint_weight(const void* offset, int dtype, const floa
     if (dtype == KPF_F32) {
         kpf::set_smem(offset2joint_kernel<float>, 0);
         offset2joint_kernel<float><<<grid, 256, 0, stream>>>((const float*)offset, depth, S, J, fs, kernel_vec, joint_out);
+    } else if (dtype == KPF_BF16 && fs * fs == 8 * 128 && fs % 8 == 0 && ((uintptr_t)offset % 16) == 0) {
+        kpf::set_smem(offset2joint_bf16x8_kernel, 0);
+        offset2joint_bf16x8_kernel<<<grid, 128, 0, stream>>>((const __nv_bfloat16*)offset, depth, S, J, fs, kernel_vec, joint_out);
     } else if (dtype == KPF_BF16) {
         kpf::set_smem(offset2joint_kernel<__nv_bfloat16>, 0);
         offset2joint_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)offset, depth, S, J, fs, kernel_vec, joint_out);
