@@ -447,8 +447,9 @@ class KPFusion(nn.Module):
         S = img.shape[-1]
         img_down = img[:, :, ::S // H, ::S // H] if S % H == 0 else F.interpolate(img, [H, H])           # :409, zero-copy view
         joint_xyz = ops.uvd2xyz(joint_uvd, center, M, cube, cam_para, loader.img_size, loader.flip)      # :410
-        # (measured: forking K2 and the K4a + repack branch onto parallel streams inside the graph is SLOWER than this serial
-        #  order on B200 -- 1.283 vs 1.240 ms per step -- so the chain stays single-stream)
+        # (measured twice: forking the K4a -> a5 -> repack branch onto a second stream inside the graph, next to order -> K2, was
+        #  slower with the first kernels (1.283 vs 1.240 ms) and gains 1 % with the current ones (0.559 vs 0.565 ms): K2 fills the
+        #  SMs, so the chain stays single-stream)
         # processing order of the points by feature-map cell: warps / point tiles then touch neighbouring cells (K2's insertions
         # coincide, the point stage's gathers hit the same lines); the results do not depend on it
         order = ops.spatial_order(pcl, center, M, cube, cam_para, loader.img_size, H, loader.flip) if pcl.shape[1] <= 8192 else None
