@@ -1,5 +1,6 @@
 // Shared device helpers for the KeypointFusion B200 kernels (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,6 +21,39 @@ inline cudaError_t set_smem(K* kernel, size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+}  // namespace kpf
+
+namespace kpf {
+// Programmatic dependent launch (PDL).  A kernel started with launch_pdl() may begin while its predecessor in the stream is still
+// running; everything it does before pdl_wait() must therefore (a) read only data no kernel writes (weights, the step's inputs)
+// and (b) write nothing to global memory.  pdl_wait() returns once the predecessor grid has completed and its writes are
+// visible.  EVERY kernel launched this way calls pdl_wait() before it exits -- completion of kernel k must imply completion of
+// kernel k-1, or the chain of dependencies is broken for the kernels behind it.  pdl_launch_dependents() at the top lets the
+// successor's CTAs take free SMs and run their own prologue (TMEM allocation, barrier init, weight TMA) early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KPF_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 }  // namespace kpf
 

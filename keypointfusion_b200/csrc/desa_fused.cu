@@ -52,10 +52,12 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         ++n_stamp;
     };
     stamp();
+    pdl_launch_dependents();
 
     if ((int)blockIdx.x >= p.B) {
         // ================= ball query (pointnet2_ops: first NS hits in index order, padded with the first hit) =================
         const int pi = blockIdx.x - p.B, b = pi / S, sc = pi - b * S;
+        pdl_wait();
         float4* sPcl = reinterpret_cast<float4*>(ds_smem);                          // [N + J] xyz
         uint32_t* sMask = reinterpret_cast<uint32_t*>(sPcl + (N + J + 3) / 4 * 4);   // [J][NW] hit words (bit = point)
         for (int i = tid; i < N + J; i += DS_NT) {
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         mbar_expect_tx(&wbar, 2048 * 16);
         tma_bulk_g2s(sWj, p.wmat, 2048 * 16, &wbar);
     }
+    pdl_wait();   // weights only so far
     if (tid < 32) {
         const float* s = p.joint + ((size_t)b * J + (tid < J ? tid : 0)) * 3;
         sJ[tid] = tid < J ? make_float4(s[0], s[1], s[2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         ++n_stamp;
     };
     stamp();
+    pdl_launch_dependents();
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     if (tid == 0) {
         mbar_init(&wbar, 1);
@@ -279,6 +283,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     tc_fence_after();
     const uint32_t tmem0 = tmem_slot, tmem = tmem0 + ((uint32_t)(32 * q) << 16);
     uint32_t g1_phase = 0, g2_phase = 0, w_phase = 0;
+    pdl_wait();   // indices, contexts and point features come from the previous kernels
 
     auto decode = [&](int item) {
         DesaItem it;
@@ -533,10 +538,12 @@ extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float*
     if (err != cudaSuccess) return (int)err;
     err = kpf::set_smem(desa_tile_kernel, smem_b);
     if (err != cudaSuccess) return (int)err;
-    desa_prep_kernel<<<B + B * S, DS_NT, smem_a, stream>>>(p);
+    err = kpf::launch_pdl(desa_prep_kernel, dim3(B + B * S), dim3(DS_NT), smem_a, stream, p);
+    if (err != cudaSuccess) return (int)err;
     KPF_CHECK_LAUNCH();
     const int JPT = 128 / nsample, total = S * B * ((J + JPT - 1) / JPT);
-    desa_tile_kernel<<<total < num_sms ? total : num_sms, DS_TILE_NT, smem_b, stream>>>(p);
+    err = kpf::launch_pdl(desa_tile_kernel, dim3(total < num_sms ? total : num_sms), dim3(DS_TILE_NT), smem_b, stream, p);
+    if (err != cudaSuccess) return (int)err;
     KPF_CHECK_LAUNCH();
     return 0;
 }

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
     const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane; // epilogues: TMEM lane `row`, columns [32cg, 32cg + 32)
     const int J = p.J, N = p.N, T = N / 128;
 
+    pdl_launch_dependents();
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&wbar, 1);
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         py = __ldg(p.pcl + pn * 3 + 1);
         pz = __ldg(p.pcl + pn * 3 + 2);
     };
+    pdl_wait();   // weights only so far; points, indices and the repacked maps come from the previous kernels
     if ((int)blockIdx.x < p.B * T) fetch_point(blockIdx.x, 0);
 
     for (int tile = blockIdx.x; tile < p.B * T; tile += gridDim.x) {
@@ -413,7 +415,8 @@ extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const floa
     cudaError_t e = kpf::set_smem(point_embed_kernel, PE_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int tiles = B * (N / 128);
-    point_embed_kernel<<<tiles < num_sms ? tiles : num_sms, PE_NT, PE_SMEM, stream>>>(p);
+    e = kpf::launch_pdl(point_embed_kernel, dim3(tiles < num_sms ? tiles : num_sms), dim3(PE_NT), PE_SMEM, stream, p);
+    if (e != cudaSuccess) return (int)e;
     KPF_CHECK_LAUNCH();
     return 0;
 }

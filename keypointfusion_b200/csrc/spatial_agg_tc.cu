@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
         ++n_stamp;
     };
     stamp();
+    pdl_launch_dependents();
 
     if (warp == 0) tmem_alloc(&tmem_slot, 64);
     if (tid == 0) {
@@ -93,10 +94,11 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
             cp_async16(dst + cgp * 128 + hw8 * 8 + c8, fb + (size_t)(cgp * 8 + c8) * HW + t * 128 + hw8 * 8);
         }
     };
-    load_tile(t_begin, sF);
+    load_tile(t_begin, sF);   // features, camera and weights are inputs of the step: fetched before the dependency wait
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();   // joints / prev come from the previous kernels
     if (tid < J) {
         const float* s = p.joints + ((size_t)b * J + tid) * 3;
         sJ[8 * tid + 0] = (s[0] + 1.f) / 2.f * (float)fs;  // generateFeature.py:592-593
@@ -278,7 +280,10 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joint
     const size_t smem = (size_t)(4096 + 2048 + 512 + 512 + 640) * 16 + 32 * 8 * 4 + 32 * 4;
     cudaError_t e = kpf::set_smem(spatial_aggregate_tc_kernel, smem);
     if (e != cudaSuccess) return (int)e;
-    spatial_aggregate_tc_kernel<<<B * split, K5_NT, smem, stream>>>(p);
+    {
+        cudaError_t le = kpf::launch_pdl(spatial_aggregate_tc_kernel, dim3(B * split), dim3(K5_NT), smem, stream, p);
+        if (le != cudaSuccess) return (int)le;
+    }
     KPF_CHECK_LAUNCH();
     return 0;
 }

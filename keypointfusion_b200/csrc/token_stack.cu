@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
     const bool valid = t < J;
     const int warp_u = warp_index_uniform();
 
+    pdl_launch_dependents();
     if (tid < 32) tmem_alloc(&tmem_slot, 512);
     if (tid >= 32 && tid < 32 + G) sSeq[tid - 32] = p.wseq[tid - 32];
     if (tid == 0) {
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         ++n_stamp;
     };
     stamp();
+    pdl_wait();   // everything above touched only weights; the activations below come from the previous kernel
     float head_x[3] = {0.f, 0.f, 0.f};  // this thread's share of residual(x) of the regression head (fp32)
     const float qscale = rsqrtf((float)(C / 4));  // head_dim^-0.5, 4 heads
 
@@ -642,7 +644,8 @@ extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d,
     p.out_jc_c0 = out_jc_c0; p.B = B; p.J = J; p.D = D; p.L = L; p.F = F; p.pre = pre; p.cross = cross; p.Fc = Fc; p.G = n_weights; p.dbg = dbg;
     cudaError_t e = kpf::set_smem(token_stack_kernel, TS_SMEM);
     if (e != cudaSuccess) return (int)e;
-    token_stack_kernel<<<B, TS_NT, TS_SMEM, stream>>>(p);
+    e = kpf::launch_pdl(token_stack_kernel, dim3(B), dim3(TS_NT), TS_SMEM, stream, p);
+    if (e != cudaSuccess) return (int)e;
     KPF_CHECK_LAUNCH();
     return 0;
 }

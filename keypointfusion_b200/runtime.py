@@ -34,7 +34,9 @@ class GraphedFusionPath:
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        # captured on the warm-up stream: per-stream persistent workspaces (ops._zero_counters) already exist, so no fill node
+        # lands inside the graph (it would also cut the programmatic-launch chain between two kernels)
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=self.stream):
             self.out = self._run()
         self.launches_per_replay = self._count
 
