@@ -82,6 +82,28 @@ spatial_order_kernel(const float* __restrict__ pcl, const float* __restrict__ ce
         so_keys[i] = key;
     }
     __syncthreads();
+    if (npow2 <= (int)blockDim.x) {
+        // one key per thread in a register: exchanges inside a warp (j < 32) are shuffles, only the 15 wider ones go through
+        // shared memory (keys are unique, so min / max on both sides of an exchange is a consistent compare-swap)
+        uint32_t key = tid < npow2 ? so_keys[tid] : 0xFFFFFFFFu;
+        for (int k = 2; k <= npow2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                uint32_t other;
+                if (j >= 32) {
+                    __syncthreads();
+                    if (tid < npow2) so_keys[tid] = key;
+                    __syncthreads();
+                    other = tid < npow2 ? so_keys[tid ^ j] : key;
+                } else {
+                    other = __shfl_xor_sync(0xffffffffu, key, j);
+                }
+                const bool keep_min = ((tid & j) == 0) == ((tid & k) == 0);
+                key = keep_min ? min(key, other) : max(key, other);
+            }
+        }
+        if (tid < N) order[(size_t)b * N + tid] = (int32_t)(key & 0x1FFFu);
+        return;
+    }
     for (int k = 2; k <= npow2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < npow2; i += blockDim.x) {

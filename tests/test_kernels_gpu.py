@@ -281,3 +281,15 @@ def test_eval_errors(ops, golden):
     ref_pa = O.xyz2error(golden["f4_aligned"], Bt, center, cube)       # the reference's own aligned joints
     close(pa, ref_pa, rtol=1e-4, atol=1e-3)
     assert float(pa[1].mean()) > 1.0                                    # the reflected sample cannot be aligned by a rotation
+
+
+@pytest.mark.parametrize("N", [37, 300, 1024, 1500])
+def test_spatial_order_is_a_permutation(ops, golden_inputs, N):
+    """Scheduling aid (no reference counterpart): for any N the order must be a permutation of the point ids; both sort paths
+    (one key per thread with warp shuffles for N <= 1024, shared-memory bitonic above) are exercised."""
+    inp = golden_inputs
+    B = inp["img"].shape[0]
+    pcl = torch.rand(B, N, 3, generator=torch.Generator().manual_seed(N)) * 1.6 - 0.8
+    order = ops.spatial_order(cu(pcl), cu(inp["center"]), cu(inp["M"]), cu(inp["cube"]), cu(inp["cam"]), 128, 32)
+    assert order.dtype == torch.int32 and tuple(order.shape) == (B, N)
+    assert torch.equal(torch.sort(order.long().cpu(), dim=1)[0], torch.arange(N).expand(B, -1))
