@@ -279,10 +279,18 @@ def main():
         # public serving API: double-buffered graphs, H2D of step i+1 overlaps compute of step i, host reads step i-1's joints
         from keypointfusion_b200.runtime import PipelinedRunner
         runner = PipelinedRunner(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0)
+        # the caller's host buffers: pinned arenas handed out by the runner (one upload per step), filled with the same data
+        host_sets = []
+        for h in hosts:
+            d = runner.new_host_inputs()
+            for k, v in h.items():
+                d[k].copy_(v)
+            host_sets.append(d)
+        h2d = host_sets[0]["_arena"].numel()
         pending = []
 
         def pipe_step(i):
-            pending.append(runner.submit(pinned[i % NSETS]))
+            pending.append(runner.submit(host_sets[i % NSETS]))
             if world > 1:
                 dist.all_gather_into_tensor(gathered, runner.paths[pending[-1]].out["joints"].contiguous())
             if len(pending) > 1:
