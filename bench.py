@@ -332,7 +332,9 @@ def main():
     line = {"metric": "fusion-path RGB-D samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * J * 3 * 4},
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * J * 3 * 4,
+                    "h2d_gb_per_s": round(h2d * (e2e / world / B) / 1e9, 1),
+                    "note": "upload-bound: one pinned-arena cudaMemcpyAsync per step, overlapped with compute (profiles/h2d_ceiling.py measures the link)"},
             "gpu_launches": launches, "roofline": roof,
             "path_roofline": {"hbm_frac": value / world * PATH_BYTES_PER_SAMPLE / (hbm * 1e9),
                               "tensor_frac": value / world * PATH_FLOPS_PER_SAMPLE / (tfl * 1e12), "peaks": which}}
