@@ -166,6 +166,15 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the fusion path has no CPU fallback)"
     torch.cuda.set_device(local)
+    try:   # pin this rank to the CPUs next to its GPU before any pinned host buffer is first touched (8 ranks feed 8 PCIe links)
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id) if hasattr(props, "pci_bus_id") else None
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus) if bus else pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+    except Exception:
+        pass
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
