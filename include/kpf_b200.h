@@ -168,18 +168,21 @@ int kpf_token_stack(const float* x, const float* y, const float* r3d, const floa
 int kpf_repack_features(const void* f_d, const void* f_rgb, const void* f_w, long long w_batch_stride, int dtype, int B, int C, int J,
                         int HW, void* out, cudaStream_t stream);
 int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
-                    const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out, float* part_acc, float* part_ms,
-                    int num_sms, long long* dbg, cudaStream_t stream);
+                    const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out,
+                    long long e_batch_stride /* elements between samples of e_out, >= N*128; (N+J)*128 or more when kpf_desa_fused follows */,
+                    float* part_acc, float* part_ms, int num_sms, long long* dbg, cudaStream_t stream);
 
 /* ---- 8f-1 DESA on tensor cores (csrc/desa_fused.cu), model/model.py:129-204 + joint embeddings :323-325 ---------------
  * e / part_acc / part_ms: outputs of kpf_point_embed; pcl [B,N,3]; joint [B,J,3]; S scales with radii r0..r3 and
  * `nsample` grouped points each; wmat/wvec from ops.pack_desa.  -> desa_part [B,S,J,128] f32 (per-scale max-pooled MLP
  * outputs) and jf_out [B,J,128] f32 (embedded joint features); the 512->128 fusion conv consumes [desa_part | jf].
- * Two launches (per-sample prep: joint embedding + ball query; persistent tile kernel on `num_sms` CTAs) that hand over
- * through `scratch`: caller workspace of B*(J*128+128)*4 + B*S*J*nsample*2 bytes, 16-byte aligned, contents undefined. */
-int kpf_desa_fused(const void* e, const float* part_acc, const float* part_ms, const float* pcl, const float* joint, const void* wmat,
-                   const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2, float r3, float* desa_part,
-                   float* jf_out, void* scratch, int num_sms, long long* dbg, cudaStream_t stream);
+ * e is [B][>= N+J][128] bf16 with batch stride e_batch_stride: rows < N from kpf_point_embed; the prep launch WRITES the J joint
+ * feature rows behind them (the joints are members N..N+J-1 of the grouped point set, model.py:168-169).
+ * Two launches (prep: joint embedding, its W1 products, ball query; persistent tile kernel on `num_sms` CTAs) that hand over
+ * through `scratch`: caller workspace of B*S*J*128*4 + B*(N+32)*16 + B*S*J*nsample*2 bytes, 16-byte aligned, contents undefined. */
+int kpf_desa_fused(void* e, long long e_batch_stride, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
+                   const void* wmat, const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2, float r3,
+                   float* desa_part, float* jf_out, void* scratch, int num_sms, long long* dbg, cudaStream_t stream);
 
 /* ---- a12 on tensor cores (csrc/spatial_agg_tc.cu): same contract as kpf_spatial_aggregate for bf16 feat_rgb [B,128,fs,fs]
  * with fs*fs % 128 == 0; wa_packed from ops.pack_spatial_wa (atten_spatial.weight in canonical bf16 operand layout).

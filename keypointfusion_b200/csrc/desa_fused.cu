@@ -19,7 +19,8 @@
 namespace kpf {
 
 struct DesaParams {
-    const __nv_bfloat16* e;   // [B,N,128] point features (kpf_point_embed)
+    __nv_bfloat16* e;         // [B][N + J][128] point features (kpf_point_embed, batch stride e_bs); rows N.. = bf16 joint features (prep)
+    long long e_bs;
     const float* part_acc;    // [B,T,128,32]
     const float* part_ms;     // [B,T,2,32]
     const float* pcl;         // [B,N,3]
@@ -28,7 +29,8 @@ struct DesaParams {
     const float* wvec;        // bj[128], Wjx[128][4] ; per scale: b1[128], b2[128]
     float* desa_part;         // [B,S,J,128]
     float* jf_out;            // [B,J,128]
-    float* ctx;               // scratch [B][J*128 + 128]: jf (fp32) | joint xyz padded to [32][4]
+    float* cj;                // scratch [B,S,J,128]: W1_s jf[j] (fp32), subtracted in the tile kernel's layer-1 epilogue
+    float4* xyz4;             // scratch [B][N + 32]: xyz of the grouped point set (N points, then the J joints), one 16-byte load each
     uint16_t* idx;            // scratch [B,S,J,nsample] ball-query indices (>= N: one of the joints)
     int B, N, J, T, S, nsample;
     float radius[4];
@@ -65,6 +67,8 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
             sPcl[i] = make_float4(s[0], s[1], s[2], 0.f);
         }
         __syncthreads();
+        if (sc == 0)
+            for (int i = tid; i < N + J; i += DS_NT) p.xyz4[(size_t)b * (N + 32) + i] = sPcl[i];
         stamp();
         // Phase 1: one thread per point tests all J centres (exact fp32 op order).  A warp's 32 lanes hold 32 CONSECUTIVE
         // points, so one ballot per (centre, point group) IS the hit word.
@@ -207,24 +211,59 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
     stamp();
     mbar_wait(&mma_bar, 0);
     tc_fence_after();
-    {   // jf[j][ch]: thread (lane quarter q, column group cg) -> channel 32q + lane, joints [8cg, 8cg + 8)
-        const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;
+    const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;   // channel 32q + lane, joints [8cg, 8cg + 8)
+    const uint32_t tmem_q = tmem0 + ((uint32_t)(32 * q) << 16);
+    {   // jf[j][ch]
         float d[8];
-        tmem_ld<8>(tmem0 + ((uint32_t)(32 * q) << 16) + 8 * cg, d);
+        tmem_ld<8>(tmem_q + 8 * cg, d);
         const float bj = p.wvec[ch];
         const float4 wx = *reinterpret_cast<const float4*>(p.wvec + 128 + 4 * ch);
-        float* ctx = p.ctx + (size_t)b * (J * 128 + 128);
+        __nv_bfloat16* erow = p.e + (size_t)b * p.e_bs + (size_t)N * 128 + ch;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int j = 8 * cg + i;
+            float v = 0.f;
             if (j < J) {
                 const float4 c = sJ[j];
-                const float v = fmaxf(d[i] + bj + wx.x * c.x + wx.y * c.y + wx.z * c.z, 0.f);
-                ctx[j * 128 + ch] = v;
+                v = fmaxf(d[i] + bj + wx.x * c.x + wx.y * c.y + wx.z * c.z, 0.f);
                 if (p.jf_out) p.jf_out[((size_t)b * J + j) * 128 + ch] = v;
+                erow[(size_t)j * 128] = __float2bfloat16_rn(v);   // the joints are points N .. N+J-1 of the grouped set (model.py:168-169)
             }
+            d[i] = v;
         }
-        if (tid < 32) reinterpret_cast<float4*>(ctx + J * 128)[tid] = sJ[tid];
+        // bf16 jf as the B operand [K = channel][N = joint] of the W1 jf GEMMs (same layout as sAgg, whose reader has completed)
+        sAgg[(ch >> 3) * 32 + cg * 8 + (ch & 7)] = pack8_bf16(d);
+    }
+    // ---- cj[s][j][:] = W1_s jf[j] for every scale: the tile kernel feeds the RAW gathered point features to its layer-1 GEMM and
+    //      subtracts this term in the epilogue ( W1 (feat - jf) = W1 feat - W1 jf ), so its gather is a pure copy
+    for (int sc = 0; sc < S; ++sc) {
+        fence_proxy_async();   // sAgg (generic-proxy writes) -> the MMA's async-proxy reads
+        tc_fence_before();
+        __syncthreads();       // the previous MMA's operand (sWj) and accumulator reads are done
+        if (warp_u == 0) {
+            if (elect_one()) {
+                mbar_expect_tx(&wbar, 2048 * 16);
+                tma_bulk_g2s(sWj, p.wmat + 2048 + (size_t)sc * DS_MAT_PER_SCALE, 2048 * 16, &wbar);
+            }
+            __syncwarp();
+            fence_proxy_async();
+            tc_fence_after();
+            mbar_wait(&wbar, (sc + 1) & 1);
+            if (elect_one()) {
+                umma_gemm(tmem0, smem_u32(sWj), 2048, 128, smem_u32(sAgg), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&mma_bar, (sc + 1) & 1);
+        tc_fence_after();
+        float d[8];
+        tmem_ld<8>(tmem_q + 8 * cg, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = 8 * cg + i;
+            if (j < J) p.cj[(((size_t)b * S + sc) * J + j) * 128 + ch] = d[i];
+        }
     }
     stamp();
     tc_fence_before();
@@ -243,22 +282,23 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     extern __shared__ __align__(128) unsigned char ds_smem[];
     uint4* sW1 = reinterpret_cast<uint4*>(ds_smem);   // [16][128] + tail [2][128]
     uint4* sW2 = sW1 + 2048 + 256;                     // [16][128]
-    uint4* sX = sW2 + 2048;                            // [2] x ([16][128] K-major activations + tail [2][128])
+    uint4* sX = sW2 + 2048;                            // [2] x (K-major activations [16 row groups][16 k-chunks][8 rows] + tail [16][2][8])
     uint4* sH = sX + 2 * DS_XBUF;                      // MN-major [16][16][8]
-    float* sCtx = reinterpret_cast<float*>(sH + 2048); // [2][J*128 + 128] jf | joint xyz of the sample(s) in flight
-    const int ctx_n = p.J * 128 + 128;
-    float* sPart = sCtx + 2 * ctx_n;                   // [2][4][128] per-column-group maxima
-    __shared__ __align__(8) uint64_t wbar, g1_bar, g2_bar, ctx_bar[2];
+    float* sPart = reinterpret_cast<float*>(sH + 2048);   // [2][4][128] per-column-group maxima
+    __shared__ __align__(8) uint64_t wbar, g1_bar, g2_bar;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = warp_index_uniform();
     const bool issuer = warp_u == DS_NT / 32;                     // warp 16: MMA / TMA issue only
     const int q = warp & 3, cg = (warp >> 2) & 3, ch = 32 * q + lane;   // epilogues: channel ch, tile rows [32cg, 32cg + 32)
-    const int r = tid & 127, kq = (tid >> 7) & 3;                 // gather: tile row r, channel chunks [4kq, 4kq + 4)
+    // gather: a thread copies its part of tile rows r and r + 64; lane = (row & 3, g8): the eight g8 lanes of a row read 128
+    // contiguous bytes per cp.async, i.e. ONE 128-byte request per row half instead of eight 16-byte ones -- the copy is bound by
+    // the number of requests the SM can keep in flight, not by bytes
+    const int r = 4 * (warp & 15) + (lane & 3), g8 = lane >> 2;
     const int J = p.J, N = p.N, NS = p.nsample, S = p.S, B = p.B;
     const int JPT = 128 / NS, TPS = (J + JPT - 1) / JPT;          // joints per tile, tiles per (sample, scale)
-    const int jrow = r >> (31 - __clz(NS));                       // r / NS (NS is a power of two): joint of this gather row within the tile
+    const int ns_shift = 31 - __clz(NS);                          // NS is a power of two: joint of tile row x = x >> ns_shift
     const int total = S * B * TPS;
     const int it0 = (int)((long long)total * blockIdx.x / gridDim.x), it1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
     const uint32_t ACC1 = 0, ACC2 = 128;
@@ -274,8 +314,6 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         mbar_init(&wbar, 1);
         mbar_init(&g1_bar, 1);
         mbar_init(&g2_bar, 1);
-        mbar_init(&ctx_bar[0], 1);
-        mbar_init(&ctx_bar[1], 1);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -283,7 +321,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     tc_fence_after();
     const uint32_t tmem0 = tmem_slot, tmem = tmem0 + ((uint32_t)(32 * q) << 16);
     uint32_t g1_phase = 0, g2_phase = 0, w_phase = 0;
-    pdl_wait();   // indices, contexts and point features come from the previous kernels
+    pdl_wait();   // indices, W1 jf terms and point features come from the previous kernels
 
     auto decode = [&](int item) {
         DesaItem it;
@@ -303,105 +341,61 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
             }
         }
     };
-    // ---- gather-side register pipeline (worker warps); every stage walks the items with its own cursor
-    DesaItem c_idx, c_rows, c_store, c_max;
-    int ii_n = 0;            // ball-query index of this thread's row for the item whose rows are fetched next
-    int ii_r = 0;            // ... for the item whose rows are in `pre`
-    uint4 pre[4];            // 4 x 16 B of the point-feature row (channels [32kq, 32kq + 32))
-    float3 pxyz = make_float3(0.f, 0.f, 0.f);
-    int ctx_loads = 0;       // sample contexts requested so far (slot = count & 1)
-    int ctx_b_load = -1;     // sample of the most recent request
-    int ctx_k = -1;          // index of the context the store stage uses
-    int ctx_b_store = -1;
+    // ---- gather side (worker warps): the grouped rows of a tile are copied global -> shared by cp.async, 16 bytes per chunk,
+    //      straight into the K-major operand (W1 (feat - jf) = W1 feat - W1 jf: the subtraction happens in the layer-1 epilogue,
+    //      so no register staging, no conversion); every stage walks the items with its own cursor
+    DesaItem c_idx, c_rows, c_epi, c_max;
+    int ii[2] = {0, 0};      // ball-query indices of this thread's two rows for the item whose rows are copied next (< N + J)
+    float3 pq[2], pc[2];     // xyz of those rows' points and of their centres (g8 == 0 lanes)
+    bool tail_ok[2] = {false, false};
     float inv_r = 1.f;       // 1 / radius of the run's scale
 
     auto fetch_idx = [&]() {
-        const int jj = c_idx.j0 + jrow;
-        ii_n = jj < J ? (int)__ldg(p.idx + (((size_t)c_idx.b * S + c_idx.sc) * J + c_idx.j0) * NS + r) : 0;
+        const uint16_t* base = p.idx + (((size_t)c_idx.b * S + c_idx.sc) * J + c_idx.j0) * NS;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = r + 64 * h;
+            ii[h] = c_idx.j0 + (row >> ns_shift) < J ? (int)__ldg(base + row) : 0;
+        }
         advance(c_idx);
     };
-    auto fetch_rows = [&]() {   // uses ii_n; all warps track the context requests, the issuer warp makes them
-        const int b = c_rows.b;
-        if (b != ctx_b_load) {   // first item of a sample on the gather side (block-uniform branch)
-            if (issuer) {
-                if (elect_one()) {
-                    mbar_expect_tx(&ctx_bar[ctx_loads & 1], (uint32_t)ctx_n * 4);
-                    tma_bulk_g2s(sCtx + (ctx_loads & 1) * ctx_n, p.ctx + (size_t)b * ctx_n, (uint32_t)ctx_n * 4, &ctx_bar[ctx_loads & 1]);
-                }
-                __syncwarp();
-            }
-            ctx_b_load = b;
-            ++ctx_loads;
-        }
+    auto copy_rows = [&](int item) {   // uses ii
+        const DesaItem it = c_rows;
         advance(c_rows);
-        if (issuer) return;
-        ii_r = ii_n;
-        const int i0 = ii_r < N ? ii_r : 0;
-        const uint4* src = reinterpret_cast<const uint4*>(p.e + ((size_t)b * N + i0) * 128) + 4 * kq;
+        const float4* tab = p.xyz4 + (size_t)it.b * (N + 32);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pre[k] = __ldg(src + k);
-        if (kq == 0) {
-            const float* s = p.pcl + ((size_t)b * N + i0) * 3;
-            pxyz = make_float3(__ldg(s), __ldg(s + 1), __ldg(s + 2));
+        for (int h = 0; h < 2; ++h) {
+            const int row = r + 64 * h, jj = it.j0 + (row >> ns_shift);
+            const bool ok = jj < J;
+            const __nv_bfloat16* src = p.e + (size_t)it.b * p.e_bs + (size_t)ii[h] * 128 + 8 * g8;
+            uint4* X = sX + (item & 1) * DS_XBUF + (row >> 3) * 128 + g8 * 8 + (row & 7);
+            const uint32_t nbytes = ok ? 16u : 0u;   // rows beyond the last joint are zero filled
+#pragma unroll
+            for (int k = 0; k < 2; ++k)   // k-chunk 8k + g8 of the row
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(X + k * 64)), "l"(src + 64 * k), "r"(nbytes) : "memory");
+            if (g8 == 0) {   // the xyz tail of the row is computed at the end of the iteration from these loads
+                tail_ok[h] = ok;
+                const float4 a4 = __ldg(tab + ii[h]), c4 = __ldg(tab + N + (ok ? jj : 0));
+                pq[h] = make_float3(a4.x, a4.y, a4.z);
+                pc[h] = make_float3(c4.x, c4.y, c4.z);
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto store_x = [&](int item) {      // uses pre / ii_r / pxyz
-        const DesaItem it = c_store;
-        advance(c_store);
-        if (it.b != ctx_b_store) {   // first tile of a sample on the store side: its context must have landed
-            ctx_b_store = it.b;
-            ++ctx_k;
-            mbar_wait(&ctx_bar[ctx_k & 1], (ctx_k >> 1) & 1);
-        }
-        const float* cx = sCtx + (ctx_k & 1) * ctx_n;
-        uint4* X = sX + (item & 1) * DS_XBUF;
-        const int jj = it.j0 + jrow;
-        const bool ok = jj < J;
-        const float* cf = cx + (ok ? jj : 0) * 128 + 32 * kq;
-        if (!ok) {
+    auto store_tail = [&](int item) {   // group_xyz_norm = (xyz[idx] - centre) / radius   model.py:177
+        if (g8 != 0) return;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) X[(4 * kq + k) * 128 + r] = make_uint4(0, 0, 0, 0);
-        } else if (ii_r < N) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pre[k]);
-                const float4 c0 = *reinterpret_cast<const float4*>(cf + k * 8), c1 = *reinterpret_cast<const float4*>(cf + k * 8 + 4);
-                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 t2 = __bfloat1622float2(h[i]);
-                    f[2 * i] = t2.x - cc[2 * i];
-                    f[2 * i + 1] = t2.y - cc[2 * i + 1];
-                }
-                X[(4 * kq + k) * 128 + r] = pack8_bf16(f);
-            }
-        } else {  // one of the J joints appended to the point set (model.py:168-169)
-            const float* sf = cx + (ii_r - N) * 128 + 32 * kq;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = sf[k * 8 + i] - cf[k * 8 + i];
-                X[(4 * kq + k) * 128 + r] = pack8_bf16(f);
-            }
-        }
-        if (kq == 0) {
-            const float4* cxyz = reinterpret_cast<const float4*>(cx + J * 128);
-            const float4 c = cxyz[ok ? jj : 0];
-            float3 pq = pxyz;
-            if (ii_r >= N) {
-                const float4 t4 = cxyz[ii_r - N];
-                pq = make_float3(t4.x, t4.y, t4.z);
-            }
+        for (int h = 0; h < 2; ++h) {
+            const int row = r + 64 * h;
             float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (ok) {
-                t8[0] = (pq.x - c.x) * inv_r;   // group_xyz_norm = (xyz[idx] - centre) / radius   model.py:177
-                t8[1] = (pq.y - c.y) * inv_r;
-                t8[2] = (pq.z - c.z) * inv_r;
+            if (tail_ok[h]) {
+                t8[0] = (pq[h].x - pc[h].x) * inv_r;
+                t8[1] = (pq[h].y - pc[h].y) * inv_r;
+                t8[2] = (pq[h].z - pc[h].z) * inv_r;
             }
-            X[2048 + r] = pack8_bf16(t8);
-            X[2048 + 128 + r] = make_uint4(0, 0, 0, 0);
+            uint4* X = sX + (item & 1) * DS_XBUF + 2048 + (row >> 3) * 16 + (row & 7);
+            X[0] = pack8_bf16(t8);
+            X[8] = make_uint4(0, 0, 0, 0);
         }
     };
     // maxima of a finished tile: combine the column groups of each joint, store
@@ -423,7 +417,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         const int sc0 = first.sc;
         const int run_end = (sc0 + 1) * B * TPS;
         const int i1 = it1 < run_end ? it1 : run_end;
-        c_idx = c_rows = c_store = c_max = first;
+        c_idx = c_rows = c_epi = c_max = first;
         // every MMA of the previous run has completed (its epilogues ran), so the weight buffers are free
         if (issuer) {
             if (elect_one()) {
@@ -436,12 +430,10 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         const float b1 = p.wvec[128 + 512 + sc0 * 256 + ch], b2 = p.wvec[128 + 512 + sc0 * 256 + 128 + ch];
         inv_r = 1.f / p.radius[sc0];
         bool w_ready = false;
-        // fill: indices of i0, rows of i0, indices of i0 + 1
-        if (!issuer) fetch_idx();
-        fetch_rows();
-        if (!issuer && i0 + 1 < i1) fetch_idx();
+        if (!issuer) fetch_idx();   // fill: indices of i0
         for (int s = i0 - 2; s < i1; ++s) {
             if (s >= i0 - 1) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's rows of tile s + 1 have landed
                 fence_proxy_async();
                 tc_fence_before();
                 __syncthreads();
@@ -457,8 +449,9 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                         if (s + 1 < i1) {   // layer 1 of tile s + 1: D1[c][row] = W1 [feat - jf | xyz]
                             const uint4* X = sX + ((s + 1) & 1) * DS_XBUF;
                             const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
-                            umma_gemm(tmem0 + ACC1, smem_u32(sW1), 2048, 128, smem_u32(X), 2048, 128, id128, 128, false);
-                            umma_gemm(tmem0 + ACC1, smem_u32(sW1 + 2048), 2048, 128, smem_u32(X + 2048), 2048, 128, id128, 16, true);
+                            // B operand: 128 B between k-chunks, 2048 B (main) / 256 B (tail) between 8-row groups
+                            umma_gemm(tmem0 + ACC1, smem_u32(sW1), 2048, 128, smem_u32(X), 128, 2048, id128, 128, false);
+                            umma_gemm(tmem0 + ACC1, smem_u32(sW1 + 2048), 2048, 128, smem_u32(X + 2048), 128, 256, id128, 16, true);
                             umma_commit(&g1_bar);
                         }
                     }
@@ -467,11 +460,18 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                 w_ready = true;
                 if (s - 1 >= i0) store_max(s - 1);   // written before the barrier above
             }
-            // gather side, two / three / four tiles ahead
-            if (!issuer && s + 2 < i1) store_x(s + 2);
-            if (s + 3 < i1) fetch_rows();
             if (!issuer) {
-                if (s + 4 < i1) fetch_idx();
+                // gather side: rows of tile s + 2 (its buffer was last read by layer 1 of tile s, long complete), indices of s + 3
+                const bool have_rows = s + 2 < i1;
+                if (have_rows) copy_rows(s + 2);
+                if (s + 3 < i1) fetch_idx();
+                // layer-1 bias of tile s + 1 minus the W1 jf term of the joint this thread's 32 rows belong to
+                float cjb = b1;
+                if (s >= i0 - 1 && s + 1 < i1) {
+                    const int jj = c_epi.j0 + ((32 * cg) >> ns_shift);
+                    if (jj < J) cjb = b1 - __ldg(p.cj + (((size_t)c_epi.b * S + c_epi.sc) * J + jj) * 128 + ch);
+                    advance(c_epi);
+                }
                 if (s >= i0) {   // layer-2 epilogue of tile s: max over this thread's 32 grouped points  (model.py:197-198)
                     mbar_wait(&g2_bar, g2_phase);
                     g2_phase ^= 1;
@@ -491,10 +491,11 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                         float a[32];
                     tmem_ld<32>(tmem + ACC1 + 32 * cg, a);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + b1, 0.f);
+                    for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + cjb, 0.f);   // relu(W1 feat + tail - W1 jf + b1)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) sH[(ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = pack8_bf16(a + 8 * c);
                 }
+                if (have_rows) store_tail(s + 2);
             }
             if (s <= i0 + 3) stamp();
         }
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
 
 }  // namespace kpf
 
-extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
+extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
                               const void* wmat, const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2,
                               float r3, float* desa_part, float* jf_out, void* scratch, int num_sms, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
@@ -521,18 +522,19 @@ extern "C" int kpf_desa_fused(const void* e, const float* part_acc, const float*
     KPF_REQUIRE(scratch != nullptr && ((uintptr_t)scratch % 16) == 0 && num_sms >= 1);
     if (B == 0) return 0;
     DesaParams p;
-    p.e = (const __nv_bfloat16*)e; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;
+    KPF_REQUIRE(e_batch_stride >= (long long)(N + J) * 128 && e_batch_stride % 8 == 0);
+    p.e = (__nv_bfloat16*)e; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;
     p.wvec = wvec; p.desa_part = desa_part; p.jf_out = jf_out; p.B = B; p.N = N; p.J = J; p.T = N / 128; p.S = S; p.nsample = nsample;
     p.dbg = dbg;
     p.radius[0] = r0; p.radius[1] = r1; p.radius[2] = r2; p.radius[3] = r3;
-    const size_t ctx_n = (size_t)J * 128 + 128;
-    p.ctx = (float*)scratch;
-    p.idx = (uint16_t*)((char*)scratch + (size_t)B * ctx_n * 4);
+    p.cj = (float*)scratch;
+    p.xyz4 = (float4*)((char*)scratch + (size_t)B * S * J * 128 * 4);
+    p.idx = (uint16_t*)((char*)scratch + (size_t)B * S * J * 128 * 4 + (size_t)B * (N + 32) * 16);
     const int NW = (N + J + 31) / 32;
     const size_t smem_jf = (size_t)(2048 + 512) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
     const size_t smem_bq = (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * NW * 4 + 64;
     const size_t smem_a = smem_jf > smem_bq ? smem_jf : smem_bq;
-    const size_t smem_b = (size_t)(DS_MAT_PER_SCALE + 2 * DS_XBUF + 2048) * 16 + 2 * ctx_n * 4 + 2 * 512 * 4 + 64;
+    const size_t smem_b = (size_t)(DS_MAT_PER_SCALE + 2 * DS_XBUF + 2048) * 16 + 2 * 512 * 4 + 64;
     KPF_REQUIRE(smem_a <= 227 * 1024 && smem_b <= 227 * 1024);
     cudaError_t err = kpf::set_smem(desa_prep_kernel, smem_a);
     if (err != cudaSuccess) return (int)err;

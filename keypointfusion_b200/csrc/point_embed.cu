@@ -92,7 +92,8 @@ struct PointParams {
     const int32_t* order;    // [B,N] processing order of the points (kpf_spatial_order) or null = identity
     const uint4* wmat;       // W1a, W1b, W2: 3 x [16][128] uint4
     const float* wvec;       // b1[128], b2[128]
-    __nv_bfloat16* e_out;    // [B,N,128]
+    __nv_bfloat16* e_out;    // [B,N,128] with batch stride e_bs elements (>= N*128: DESA appends its joint rows behind the points)
+    long long e_bs;
     float* part_acc;         // [B,T,128,32]
     float* part_ms;          // [B,T,2,32]  (max, sum)
     int B, N, J, HW;
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         stamp();
         // ---- epilogue: e = relu(relu(acc1 + b1) + acc2 + b2) -> global (bf16) and MN-major A operand (sA2 region)
         {
-            __nv_bfloat16* eo = p.e_out + ((size_t)b * N + sN[tile_par * 128 + row]) * 128 + 32 * cg;
+            __nv_bfloat16* eo = p.e_out + (size_t)b * p.e_bs + (size_t)sN[tile_par * 128 + row] * 128 + 32 * cg;
             float a[32], rr[32];
             tmem_ld_nw<32>(tmem + ACC1 + 32 * cg, a);
             tmem_ld_nw<32>(tmem + ACC2 + 32 * cg, rr);
@@ -402,6 +403,7 @@ extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const voi
 
 extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
                                const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out,
+                               long long e_batch_stride,
                                float* part_acc, float* part_ms, int num_sms, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && J >= 1 && J <= 21 && HW >= 1 && num_sms >= 1);
@@ -409,7 +411,8 @@ extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const floa
     if (B == 0) return 0;
     PointParams p;
     p.featT = (const uint4*)featT; p.idx = idx; p.clos = clos; p.pcl = pcl; p.joint = joint; p.order = order; p.wmat = (const uint4*)wmat; p.wvec = wvec;
-    p.e_out = (__nv_bfloat16*)e_out; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
+    KPF_REQUIRE(e_batch_stride >= (long long)N * 128 && e_batch_stride % 8 == 0);
+    p.e_out = (__nv_bfloat16*)e_out; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
     p.kernel_size = kernel_size;
     p.dbg = dbg;
     cudaError_t e = kpf::set_smem(point_embed_kernel, PE_SMEM);

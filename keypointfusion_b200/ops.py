@@ -507,11 +507,14 @@ def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg
     HW = featT.shape[1]
     T = N // 128
     dev = pcl.device
-    e = torch.empty(B, N, 128, device=dev, dtype=torch.bfloat16)
+    # 32 spare rows per sample behind the points: kpf_desa_fused appends the joints' own feature rows there (they are members
+    # N .. N+J-1 of DESA's grouped point set); the returned tensor is the [B,N,128] view of the points
+    e_full = torch.empty(B, N + 32, 128, device=dev, dtype=torch.bfloat16)
+    e = e_full[:, :N]
     acc = torch.empty(B, T, 128, 32, device=dev, dtype=torch.float32)
     ms = torch.empty(B, T, 2, 32, device=dev, dtype=torch.float32)
     _call("kpf_point_embed", _p(featT), _p(idx32), _p(clos), _p(pcl), _p(joint), _p(order), _p(wmat), _p(wvec), B, N, J, HW,
-          float(kernel_size), _p(e),
+          float(kernel_size), _p(e), e.stride(0),
           _p(acc), _p(ms), sm_count(dev), _p(dbg))
     return e, acc, ms
 
@@ -550,9 +553,13 @@ def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, db
     r = list(radius) + [0.0] * (4 - S)
     part = torch.empty(B, S, J, 128, device=pcl.device, dtype=torch.float32)
     jf = torch.empty(B, J, 128, device=pcl.device, dtype=torch.float32)
-    # workspace between the two kernels: per sample [jf | joint xyz] fp32, then the ball-query indices u16
-    scratch = torch.empty(B * (J * 128 + 128) * 4 + B * S * J * nsample * 2, device=pcl.device, dtype=torch.uint8)
-    _call("kpf_desa_fused", _p(e), _p(part_acc), _p(part_ms), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, S, nsample, float(r[0]),
+    if e.stride(0) < (N + J) * 128 or e.stride(1) != 128 or e.stride(2) != 1:   # not from ops.point_embed: make room for the joint rows
+        e_full = torch.empty(B, N + 32, 128, device=pcl.device, dtype=torch.bfloat16)
+        e_full[:, :N].copy_(e)
+        e = e_full[:, :N]
+    # workspace between the two kernels: W1_s jf terms fp32 [B,S,J,128], padded xyz table [B,N+32,4] f32, ball-query indices u16
+    scratch = torch.empty(B * S * J * 128 * 4 + B * (N + 32) * 16 + B * S * J * nsample * 2, device=pcl.device, dtype=torch.uint8)
+    _call("kpf_desa_fused", _p(e), e.stride(0), _p(part_acc), _p(part_ms), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, S, nsample, float(r[0]),
           float(r[1]), float(r[2]), float(r[3]), _p(part), _p(jf), _p(scratch), sm_count(pcl.device), _p(dbg))
     return part, jf
 
