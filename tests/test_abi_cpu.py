@@ -28,3 +28,22 @@ def test_no_fallback_on_cpu_tensors():
     from keypointfusion_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.uvd2xyz(torch.zeros(1, 2, 3), torch.zeros(1, 3), torch.eye(3)[None], torch.ones(1, 3), torch.ones(1, 4), 128)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: no module of the package (nor the C sources) may import, link or execute it."""
+    import ast
+    import glob
+    import os
+    root = os.path.join(os.path.dirname(__file__), "..", "keypointfusion_b200")
+    for path in glob.glob(os.path.join(root, "**", "*.py"), recursive=True):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n.split(".")[0] == "oracle" for n in names), f"{path} imports the oracle"
+    for path in glob.glob(os.path.join(root, "csrc", "*")):
+        assert "oracle/" not in open(path, errors="ignore").read().replace("oracle/kpf_oracle.py", ""), path
