@@ -43,11 +43,33 @@ __device__ __forceinline__ uint32_t feistel_perm(uint32_t i, uint32_t n, uint32_
     }
 }
 
-__device__ __forceinline__ bool pixel_valid(float v, float hz, float cz, float& dpt) {
+// The reference's float64 np.isclose bands, restated as float thresholds: for a float v, |double(v) - 1| <= band  <=>  lo <= v <= hi
+// with lo / hi the extreme floats that satisfy the double predicate (found by testing the predicate itself on neighbouring floats),
+// and |double(d)| <= 1e-8  <=>  |d| <= z.  Same decisions for every float (NaN included), no fp64 work per pixel.
+struct PixelBands {
+    float lo, hi, z;
+};
+__device__ __forceinline__ bool bg_pred(float v) {
     const double BG_BAND = 1e-8 + 1e-5 * 1.0;  // np.isclose(x, 1)  loader.py:844
-    const bool bg = fabs((double)v - 1.0) <= BG_BAND;
-    dpt = bg ? 0.0f : xadd(xmul(v, hz), cz);   // loader.py:845-847
-    return !(fabs((double)dpt) <= 1e-8);       // ~np.isclose(dpt, 0)  loader.py:880
+    return fabs((double)v - 1.0) <= BG_BAND;
+}
+__device__ __forceinline__ PixelBands make_bands() {
+    PixelBands b;
+    b.hi = (float)(1.0 + (1e-8 + 1e-5));
+    while (!bg_pred(b.hi)) b.hi = nextafterf(b.hi, 0.f);
+    while (bg_pred(nextafterf(b.hi, 2.f))) b.hi = nextafterf(b.hi, 2.f);
+    b.lo = (float)(1.0 - (1e-8 + 1e-5));
+    while (!bg_pred(b.lo)) b.lo = nextafterf(b.lo, 2.f);
+    while (bg_pred(nextafterf(b.lo, 0.f))) b.lo = nextafterf(b.lo, 0.f);
+    b.z = (float)1e-8;
+    while ((double)b.z > 1e-8) b.z = nextafterf(b.z, 0.f);
+    while ((double)nextafterf(b.z, 1.f) <= 1e-8) b.z = nextafterf(b.z, 1.f);
+    return b;
+}
+__device__ __forceinline__ bool pixel_valid(float v, float hz, float cz, const PixelBands& bands, float& dpt) {
+    const bool bg = v >= bands.lo && v <= bands.hi;   // np.isclose(x, 1)  loader.py:844
+    dpt = bg ? 0.0f : xadd(xmul(v, hz), cz);          // loader.py:845-847
+    return !(fabsf(dpt) <= bands.z);                  // ~np.isclose(dpt, 0)  loader.py:880
 }
 
 struct BackprojCam {
@@ -95,6 +117,7 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
     __shared__ BackprojCam sc;
 
     const float hz = xdiv(cube[3 * b + 2], 2.0f), cz = com3D[3 * b + 2];
+    const PixelBands bands = make_bands();
     const float* im = img + (size_t)b * npix;
 
     if (tid == 0) {
@@ -112,13 +135,24 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
 
     // ---- pass 1a: validity bits (kept in registers) + per-(round,warp) counts
     uint64_t vbits = 0;
-    for (int r = 0; r < rounds; ++r) {
-        const int p = r * K1_THREADS + tid;
-        float dpt;
-        const bool ok = p < npix && pixel_valid(__ldg(im + p), hz, cz, dpt);
-        vbits |= (uint64_t)ok << r;
-        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) cnt[r * K1_WARPS + warp] = __popc(bal);
+    for (int r0 = 0; r0 < rounds; r0 += 16) {   // 16 independent loads in flight, then the (serial) ballots
+        float vv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int p = (r0 + u) * K1_THREADS + tid;
+            vv[u] = (r0 + u < rounds && p < npix) ? __ldg(im + p) : 1.0f;   // 1.0 = background = not a point
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int r = r0 + u;
+            if (r < rounds) {   // warp-uniform
+                float dpt;
+                const bool ok = r * K1_THREADS + tid < npix && pixel_valid(vv[u], hz, cz, bands, dpt);
+                vbits |= (uint64_t)ok << r;
+                const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) cnt[r * K1_WARPS + warp] = __popc(bal);
+            }
+        }
     }
     __syncthreads();
     // ---- pass 1b: exclusive scan of cnt[rounds*32] in (round, warp) order == row-major pixel order
@@ -189,7 +223,7 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
             }
             const int pix = list[rank];
             float dpt;
-            pixel_valid(__ldg(im + pix), hz, cz, dpt);
+            pixel_valid(__ldg(im + pix), hz, cz, bands, dpt);
             backproject_point(sc, pix, S, dpt, o, clamp != 0);
         }
     } else {
@@ -198,7 +232,7 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
             if (r < P) {
                 const int pix = list[r];
                 float dpt;
-                pixel_valid(__ldg(im + pix), hz, cz, dpt);
+                pixel_valid(__ldg(im + pix), hz, cz, bands, dpt);
                 backproject_point(sc, pix, S, dpt, o, clamp != 0);
                 if (pix_out) pix_out[(size_t)b * npix + r] = pix;
             } else {

@@ -124,3 +124,44 @@ def test_input_arena_views():
     b.buf.copy_(a.buf)                 # the single-copy upload, on the host
     for k in keys:
         assert torch.equal(b.views[k], inp[k]), k
+
+
+def test_isclose_bands_as_float_thresholds():
+    """K1 tests its pixels against float thresholds instead of the reference's float64 np.isclose bands (backproject.cu:make_bands).
+    Re-derive the thresholds the way the kernel does and check, for EVERY float around the bands, that the decisions are the same."""
+    f32 = np.float32
+    band = 1e-8 + 1e-5 * 1.0
+
+    def bg(v):
+        return abs(float(v) - 1.0) <= band
+
+    def na(x, to):
+        return np.nextafter(f32(x), f32(to))
+    hi = f32(1.0 + band)
+    while not bg(hi):
+        hi = na(hi, 0)
+    while bg(na(hi, 2)):
+        hi = na(hi, 2)
+    lo = f32(1.0 - band)
+    while not bg(lo):
+        lo = na(lo, 2)
+    while bg(na(lo, 0)):
+        lo = na(lo, 0)
+    z = f32(1e-8)
+    while float(z) > 1e-8:
+        z = na(z, 0)
+    while float(na(z, 1)) <= 1e-8:
+        z = na(z, 1)
+    v = f32(1 - 3e-5)
+    n = 0
+    while v < f32(1 + 3e-5):
+        assert bool(np.isclose(float(v), 1.0)) == bg(v) == bool(lo <= v <= hi), v
+        v = na(v, 2)
+        n += 1
+    assert n > 500
+    vs = np.arange(0, 4000, dtype=np.int64)
+    base = np.array([z], dtype=f32).view(np.int32)[0]
+    near = (base + vs - 2000).astype(np.int32).view(f32)          # 4000 consecutive floats around 1e-8
+    for sign in (1.0, -1.0):
+        d = (near * f32(sign)).astype(f32)
+        assert np.array_equal(np.isclose(d.astype(np.float64), 0.0), np.abs(d) <= z)
