@@ -3,15 +3,19 @@
 // desa_prep_kernel   512 threads, two independent roles side by side in one launch:
 //             CTA per sample:  combine the point stage's softmax partials (flash-style) -> joint_agg[J][128]
 //                              jf = relu(Wj [joint_agg | joint_xyz] + b)    (model.py:323-325)   tcgen05 + fp32 xyz term
+//                              jf is also appended, in bf16, as rows N.. of the point-feature tensor e (the joints are members
+//                              of the grouped set, model.py:168-169), and cj[s][j] = W1_s jf[j] is computed for every scale
 //             CTA per (sample, scale): ball query (pointnet2_ops semantics) of the J joints over the N points + the J joints
-//                              themselves -> idx[b][scale][j][nsample]
-// desa_tile_kernel   persistent, one CTA per SM, 512 threads.  Work item = (scale, sample, tile of 128/nsample joints); every
-//             CTA takes a contiguous, scale-major range so the scale's weights stay resident:
-//             X = [feat[idx] - jf[j] | (xyz[idx] - c_j)/r]  ->  h = relu(W1 X + b1)  ->  relu(W2 h + b2)  -> max over nsample
+//                              themselves -> idx[b][scale][j][nsample]; the scale-0 CTA also writes a padded xyz table
+// desa_tile_kernel   persistent, one CTA per SM, 16 worker warps + 1 issuer warp.  Work item = (scale, sample, tile of 128/nsample
+//             joints); every CTA takes a contiguous, scale-major range so the scale's weights stay resident:
+//             X = [feat[idx] - jf[j] | (xyz[idx] - c_j)/r]  ->  h = relu(W1 X + b1)  ->  relu(W2 h + b2)  -> max over nsample,
+//             evaluated as h = relu(W1 [feat[idx] | (xyz[idx] - c_j)/r] - cj + b1): layer 1 reads the RAW gathered rows, so the
+//             gather is a cp.async copy (128-byte requests) straight into the operand and cj is subtracted in the epilogue.
 //             Both GEMMs are computed transposed -- D[c][row] = sum_k W[c][k] X[row][k], weight = M=128 A operand, activations =
 //             N operand -- so thread (lane quarter, column group) owns OUTPUT CHANNEL c and DESA's max-pool over the grouped
 //             points of a joint is a per-thread register reduction.  Software pipeline per iteration s: GEMM2(s) and GEMM1(s+1)
-//             are issued together; while they run the threads write X(s+2) (rows prefetched one iteration earlier, indices two);
+//             are issued together; while they run the rows of tile s+2 are copied (indices fetched one iteration earlier);
 //             then epilogue 2 of s and epilogue 1 of s+1.  One __syncthreads per tile.
 //   output    desa_part[b][scale][j][:], jf[b][j][:]; the 512->128 fusion conv follows in kpf_token_stack.
 #include "tmem_ldst.cuh"
