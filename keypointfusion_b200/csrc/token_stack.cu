@@ -18,7 +18,8 @@
 //     pair yields O_h in the same diagonal blocks, which are exactly the columns each quarter owns.
 //   * Q and K|V (one N = 256 tile) are issued back to back; weights stream through three 32 KB slots by cp.async.bulk, each
 //     transfer gated on the GEMM that last used its slot (table from ops.pack_token_program); per-layer vectors are
-//     double-buffered the same way.  The fp32 residual stream lives in TMEM columns [384, 512).
+//     double-buffered the same way.  The fp32 residual stream stays in registers: a thread owns the same 8 columns of the same
+//     token for the whole program.
 // One elected lane of warp 0 issues MMAs and TMA copies from warp-uniform code (umma.cuh: elect_one).
 #include "tmem_ldst.cuh"
 
@@ -31,7 +32,7 @@ constexpr int TS_MAXG = 64;            // weight tiles per program
 constexpr int TS_NB = 8;               // weight-arrival barriers (transfer g uses g % TS_NB)
 constexpr int TS_VEC = 10 * TS_C;      // floats of per-layer vectors
 constexpr uint32_t TS_LBO = 128 * 16;  // K-major operand with 128 rows: bytes between 8-k groups
-constexpr uint32_t ACC0 = 0, ACC1 = 128, ACC2 = 256, RESID = 384;
+constexpr uint32_t ACC0 = 0, ACC1 = 128, ACC2 = 256;   // TMEM accumulator columns (ACC1..ACC2 are one N = 256 tile for K|V)
 
 struct TokParams {
     const float* x;        // encoder input [B,J,D] (no prologue) | cross: anchor [B,J,C]
@@ -233,6 +234,8 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
     stamp();
     pdl_wait();   // everything above touched only weights; the activations below come from the previous kernel
     float head_x[3] = {0.f, 0.f, 0.f};  // this thread's share of residual(x) of the regression head (fp32)
+    float resid[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // fp32 residual stream: this thread's 8 columns of its token, in
+                                                               // registers for the whole program (a thread always owns the same ones)
     const float qscale = rsqrtf((float)(C / 4));  // head_dim^-0.5, 4 heads
 
     // =========================== cross-attention inputs (crossTR) ===========================
@@ -241,7 +244,8 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         load8<true>(p.x + ((size_t)b * J + t) * C + col0, a, valid);
         load8<true>(qpos + t * C + col0, e, valid);
         load8<true>(p.y + ((size_t)b * J + t) * C + col0, kin, valid);
-        tmem_st_nw<8>(tmem + RESID + col0, a);           // residual = anchor (transfusion_head.py:164)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) resid[i] = a[i];     // residual = anchor (transfusion_head.py:164)
 #pragma unroll
         for (int i = 0; i < 8; ++i) e[i] += a[i];
         store_rep(bufA, ck, pack8_bf16(e));              // q_in = anchor + self_posembed
@@ -249,7 +253,6 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
 #pragma unroll
         for (int i = 0; i < 8; ++i) kin[i] += e[i];
         store_rep(bufB, ck, pack8_bf16(kin));            // k_in = tokens + cross_posembed
-        tmem_wait_st();
     }
 
     // One loop over every transformer layer of the program: iteration 0 is the cross layer when there is one; the encoder's
@@ -360,10 +363,8 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
             float a[8];
             tmem_ld<8>(tmem + ACC0 + col0, a);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = valid ? a[i] + bb[i] + e[i] : 0.f;
-            tmem_st_nw<8>(tmem + RESID + col0, a);
+            for (int i = 0; i < 8; ++i) resid[i] = a[i] = valid ? a[i] + bb[i] + e[i] : 0.f;
             store_rep(bufA, ck, pack8_bf16(a));
-            tmem_wait_st();
             stamp();
         }
 
@@ -478,14 +479,12 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         }
         // ---- residual + LayerNorm on a 128-wide accumulator; the 16 threads of a token exchange partial statistics
         auto resid_ln = [&](uint32_t acc, const float* bias, const float* gam, const float* bet, const float* Wr) {
-            float y[8], r[8];
-            tmem_ld_nw<8>(tmem + acc + col0, y);
-            tmem_ld_nw<8>(tmem + RESID + col0, r);
-            tmem_wait_ld();
+            float y[8];
+            tmem_ld<8>(tmem + acc + col0, y);
             float sum = 0.f, sq = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                y[i] += bias[col0 + i] + r[i];
+                y[i] += bias[col0 + i] + resid[i];
                 sum += y[i];
                 sq += y[i] * y[i];
             }
@@ -504,11 +503,9 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
             const float mean = sum * (1.f / C);
             const float rstd = rsqrtf(fmaxf(sq * (1.f / C) - mean * mean, 0.f) + eps);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = valid ? (y[i] - mean) * rstd * gam[col0 + i] + bet[col0 + i] : 0.f;
-            tmem_st_nw<8>(tmem + RESID + col0, y);
+            for (int i = 0; i < 8; ++i) resid[i] = y[i] = valid ? (y[i] - mean) * rstd * gam[col0 + i] + bet[col0 + i] : 0.f;
             store_rep(bufA, ck, pack8_bf16(y));
             if (Wr) head_acc<8>(head_x, y, Wr + col0, C);
-            tmem_wait_st();
         };
         sync_for_mma();
         if (warp_u == 0) {
@@ -571,8 +568,7 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
     }
 
     if (p.cross && p.L == 0) {
-        float a[8];
-        tmem_ld<8>(tmem + RESID + col0, a);
+        const float* a = resid;
         if (valid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -584,8 +580,7 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
     if (p.L > 0) {
         // ---- regression head: pred = cls_head(h) + residual(x)   (model.py:122-124), fp32, 16 threads per token
         float pr3[3] = {head_x[0], head_x[1], head_x[2]};
-        float a[8];
-        tmem_ld<8>(tmem + RESID + col0, a);
+        const float* a = resid;
         head_acc<8>(pr3, a, Wcls + col0, C);
         if (valid && p.tokens_out) {
             float4* o = reinterpret_cast<float4*>(p.tokens_out + ((size_t)b * J + t) * C + col0);
