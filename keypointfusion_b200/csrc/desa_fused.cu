@@ -523,8 +523,8 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && N + J <= 65535 && J >= 1 && J <= 32 && S >= 1 && S <= 4);
     KPF_REQUIRE(nsample == 32 || nsample == 64 || nsample == 128);
     KPF_REQUIRE(((uintptr_t)wmat % 16) == 0 && ((uintptr_t)e % 16) == 0 && ((uintptr_t)part_acc % 16) == 0 && ((uintptr_t)wvec % 16) == 0);
-    KPF_REQUIRE(scratch != nullptr && ((uintptr_t)scratch % 16) == 0 && num_sms >= 1);
     if (B == 0) return 0;
+    KPF_REQUIRE(scratch != nullptr && ((uintptr_t)scratch % 16) == 0 && num_sms >= 1);
     DesaParams p;
     KPF_REQUIRE(e_batch_stride >= (long long)(N + J) * 128 && e_batch_stride % 8 == 0);
     p.e = (__nv_bfloat16*)e; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;

@@ -269,8 +269,8 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joint
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && C == 128 && J >= 1 && J <= 32 && fs >= 1 && (fs * fs) % 128 == 0);
     KPF_REQUIRE(((uintptr_t)feat_rgb % 16) == 0 && ((uintptr_t)wa_packed % 16) == 0);
-    KPF_REQUIRE(split >= 1 && ((fs * fs) / 128) % split == 0 && (split == 1 || (scratch != nullptr && counters != nullptr)));
     if (B == 0) return 0;
+    KPF_REQUIRE(split >= 1 && ((fs * fs) / 128) % split == 0 && (split == 1 || (scratch != nullptr && counters != nullptr)));
     SpatialParams p;
     p.feat = (const __nv_bfloat16*)feat_rgb; p.joints = joints; p.depth = depth; p.depth_bs = depth_bs; p.depth_rs = depth_rs;
     p.depth_cs = depth_cs; p.center = center; p.M = M; p.cube = cube; p.cam = cam; p.wa = (const uint4*)wa_packed; p.ba = ba;

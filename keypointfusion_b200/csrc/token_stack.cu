@@ -624,6 +624,7 @@ extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d,
                                long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && J >= 1 && J <= 32 && L >= 0 && (cross || L > 0));
+    if (B == 0) return 0;   // an empty batch has no buffers to validate
     KPF_REQUIRE(L == 0 || F == 16 || F == 32 || F == 64 || F == 128);
     KPF_REQUIRE(!cross || (y != nullptr && (Fc == 16 || Fc == 32 || Fc == 64 || Fc == 128)));
     KPF_REQUIRE(L == 0 || D == TS_C || (D > TS_C && D <= TS_C + 16));
@@ -632,7 +633,6 @@ extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d,
     KPF_REQUIRE(n_weights <= TS_MAXG);
     KPF_REQUIRE(n_weights == (cross ? 5 : 0) + (pre ? 4 : 0) + (L > 0 ? 1 + 5 * L : 0));
     KPF_REQUIRE(((uintptr_t)wmat % 16) == 0 && ((uintptr_t)wseq % 16) == 0);
-    if (B == 0) return 0;
     TokParams p;
     p.x = x; p.y = y; p.r3d = r3d; p.desa = desa; p.jf = jf; p.wmat = (const uint4*)wmat; p.wseq = (const int4*)wseq; p.wvec = wvec;
     p.tokens_out = tokens_out; p.pred_out = pred_out; p.out_cj = out_cj; p.out_jc = out_jc; p.out_jc_stride = out_jc_stride;

@@ -22,6 +22,14 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _spatial_numel(t):
+    """elements per (batch, channel) plane of an NC... tensor; valid for empty batches too"""
+    n = 1
+    for d in t.shape[2:]:
+        n *= int(d)
+    return n
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -183,7 +191,7 @@ def gather_taps(feat, index, closeness, out=None, out_c0=0):
     if feat.dtype not in _DT:
         feat = feat.float()
     B, C = feat.shape[:2]
-    HW = feat[0, 0].numel()
+    HW = _spatial_numel(feat)
     inner_ok = feat[0].is_contiguous() if feat.dim() == 3 else feat[0].reshape(C, HW).is_contiguous()
     if not inner_ok:
         feat = feat.contiguous()
@@ -279,7 +287,7 @@ def channel_mean(x):
     x = _feat(x)
     B, C = x.shape[:2]
     out = torch.empty(B, C, device=x.device, dtype=torch.float32)
-    _call("kpf_channel_mean", _p(x), _DT[x.dtype], B * C, x[0, 0].numel(), _p(out))
+    _call("kpf_channel_mean", _p(x), _DT[x.dtype], B * C, _spatial_numel(x), _p(out))
     return out
 
 
@@ -288,7 +296,7 @@ def rgbd_fusion(rgb, depth, gate_w, gate_b, want_attn_mean=False):
     if depth.dtype != rgb.dtype:
         depth = depth.to(rgb.dtype)
     B, C = rgb.shape[:2]
-    HW = rgb[0, 0].numel()
+    HW = _spatial_numel(rgb)
     ro, do, mg = torch.empty_like(rgb), torch.empty_like(rgb), torch.empty_like(rgb)
     asum = torch.zeros(2, device=rgb.device, dtype=torch.float32) if want_attn_mean else None
     gate_w, gate_b = _f32(gate_w), _f32(gate_b)
@@ -301,7 +309,7 @@ def ac_fusion(rgb, depth, w_rgb, b_rgb, w_depth, b_depth):
     if depth.dtype != rgb.dtype:
         depth = depth.to(rgb.dtype)
     B, C = rgb.shape[:2]
-    HW = rgb[0, 0].numel()
+    HW = _spatial_numel(rgb)
     mr, md = channel_mean(rgb), channel_mean(depth)
     ro, do, mg = torch.empty_like(rgb), torch.empty_like(rgb), torch.empty_like(rgb)
     w_rgb, b_rgb, w_depth, b_depth = _f32(w_rgb.reshape(C, C)), _f32(b_rgb), _f32(w_depth.reshape(C, C)), _f32(b_depth)
@@ -315,7 +323,7 @@ def fsp(guide, main, w0, b0, w2, b2):
     if main.dtype != guide.dtype:
         main = main.to(guide.dtype)
     B, C = guide.shape[:2]
-    HW = guide[0, 0].numel()
+    HW = _spatial_numel(guide)
     out = torch.empty_like(main)
     mg, mm = channel_mean(guide), channel_mean(main)  # keep references alive until the launch is enqueued
     w0, b0, w2, b2 = _f32(w0), _f32(b0), _f32(w2), _f32(b2)
@@ -472,8 +480,8 @@ def repack_features(img_feat, img_feat_rgb, weight_map):
     w = weight_map.to(dt)
     B, C = f_d.shape[:2]
     J = w.shape[1]
-    HW = f_d[0, 0].numel()
-    if not w[0].reshape(J, HW).is_contiguous():
+    HW = _spatial_numel(f_d)
+    if B == 0 or not w[0].reshape(J, HW).is_contiguous():   # a channel slice of a larger map is fine as long as each sample is dense
         w = w.contiguous()
     out = torch.empty(B, HW, 288, device=f_d.device, dtype=torch.bfloat16)
     _call("kpf_repack_features", _p(f_d), _p(f_rgb), _p(w), w.stride(0), _DT[dt], B, C, J, HW, _p(out))

@@ -204,3 +204,39 @@ def test_fusion_path_batch_invariance(net):
         assert torch.equal(res_all[k][:3], res_s[k]), (k, d)
     for k in range(2):
         assert torch.equal(sw_all[k][:3], sw_s[k]), k
+
+
+def _edge_run(net, c, sl):
+    from keypointfusion_b200.dataloader.loader import loader
+    from keypointfusion_b200 import ops
+    with torch.no_grad():
+        pcl, _ = ops.getpcl(c["img"][sl], c["center"][sl], c["cube"][sl], c["M"][sl], c["cam"][sl], seed=4)
+        res, sws, _ = net.forward_path(c["img_offset"][sl], c["img_feat"][sl], None, c["img_feat_rgb"][sl], c["img"][sl], pcl,
+                                       loader(img_size=128), c["center"][sl], c["M"][sl], c["cube"][sl], c["cam"][sl], 0.8)
+    return res, sws
+
+
+def _edge_inputs():
+    inp = synth.make_inputs(4, 128, 21, 128, seed=17, bf16_round=True)
+    c = {k: v.to(DEV) for k, v in inp.items()}
+    for k in ("img_feat", "img_feat_rgb", "img_offset"):
+        c[k] = c[k].bfloat16()
+    return c
+
+
+def test_fusion_path_single_sample(net):
+    """B = 1 (one work item per persistent kernel, one CTA per sample) is bit-identical to the same sample inside a larger batch."""
+    from keypointfusion_b200 import ops
+    c = _edge_inputs()
+    real = ops.sm_count
+    res4, sw4 = _edge_run(net, c, slice(0, 4))
+    split4 = next((s_ for s_ in (8, 4, 2) if 4 * s_ <= real(DEV)), 1)
+    ops.sm_count = lambda device: split4          # same K5 split (fp32 summation partition) for the single-sample run
+    try:
+        res1, sw1 = _edge_run(net, c, slice(0, 1))
+    finally:
+        ops.sm_count = real
+    for k in range(2, 6):
+        assert torch.equal(res4[k][:1], res1[k]), k
+    for k in range(2):
+        assert torch.equal(sw4[k][:1], sw1[k]), k
