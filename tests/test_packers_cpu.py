@@ -165,3 +165,32 @@ def test_isclose_bands_as_float_thresholds():
     for sign in (1.0, -1.0):
         d = (near * f32(sign)).astype(f32)
         assert np.array_equal(np.isclose(d.astype(np.float64), 0.0), np.abs(d) <= z)
+
+
+def test_desa_and_spatial_packers_layout():
+    """The offsets the kernels hard-code (desa_fused.cu: Wj at 0, then per scale W1 main 2048 | W1 tail 256 | W2 2048 uint4;
+    spatial_agg_tc.cu: Wa main 512 | heat-map part 128 uint4) match what the packers emit, and the contents survive the round trip."""
+    g = torch.Generator().manual_seed(11)
+    Wj, bj, Wjx, bjx = torch.randn(128, 128, generator=g), torch.randn(128, generator=g), torch.randn(128, 3, generator=g), torch.randn(128, generator=g)
+    scales = [(torch.randn(128, 128, generator=g), torch.randn(128, generator=g), torch.randn(128, 3, generator=g), torch.randn(128, generator=g),
+               torch.randn(128, 128, generator=g), torch.randn(128, generator=g)) for _ in range(3)]
+    wmat, wvec = ops.pack_desa(Wj, bj, Wjx, bjx, scales)
+    per_scale = 2048 + 256 + 2048
+    assert wmat.dtype == torch.bfloat16 and wmat.numel() == (2048 + 3 * per_scale) * 8
+    assert torch.equal(_uncanon(wmat[:2048 * 8], 128, 128), Wj.bfloat16().float())
+    for s_, (Wf0, bf0, Wl0, bl0, W2, b2) in enumerate(scales):
+        o = (2048 + s_ * per_scale) * 8
+        assert torch.equal(_uncanon(wmat[o:o + 2048 * 8], 128, 128), Wf0.bfloat16().float())
+        tail = _uncanon(wmat[o + 2048 * 8:o + (2048 + 256) * 8], 128, 16)
+        assert torch.equal(tail[:, :3], Wl0.bfloat16().float()) and not tail[:, 3:].any()
+        assert torch.equal(_uncanon(wmat[o + (2048 + 256) * 8:o + per_scale * 8], 128, 128), W2.bfloat16().float())
+        assert torch.equal(wvec[128 + 512 + s_ * 256:128 + 512 + s_ * 256 + 128], bf0 + bl0)
+        assert torch.equal(wvec[128 + 512 + s_ * 256 + 128:128 + 512 + (s_ + 1) * 256], b2)
+    assert torch.equal(wvec[:128], bj + bjx) and torch.equal(wvec[128:640].reshape(128, 4)[:, :3], Wjx)
+    J = 21
+    Wa = torch.randn(J, 128 + J, 1, 1, generator=g)
+    wa = ops.pack_spatial_wa(Wa, J)
+    assert wa.numel() == (512 + 128) * 8
+    main, hm = _uncanon(wa[:512 * 8], 32, 128), _uncanon(wa[512 * 8:], 32, 32)
+    assert torch.equal(main[:J], Wa[:, :128, 0, 0].bfloat16().float()) and not main[J:].any()
+    assert torch.equal(hm[:J, :J], Wa[:, 128:, 0, 0].bfloat16().float()) and not hm[J:].any() and not hm[:, J:].any()
