@@ -150,11 +150,13 @@ int kpf_ball_query(const float* xyz, const float* centers, int B, int Np, int J,
  *   - the fusion-conv output (pre), or
  *   - cat([r3d [B,J,D-128], cross output]) (cross != 0: crossTR + final_TR fused, model.py:347-349).
  * Outputs: L > 0 -> tokens_out [B,J,128] (may be NULL), pred_out [B,J,3];  cross only -> out_cj [B,128,J] and/or out_jc.
- * wmat (bf16 canonical operands), wseq ((offset,count) int32 pairs, n_weights of them), wvec (f32): ops.pack_token_program.
- * bf16 tensor-core operands; fp32 accumulation, residual stream, LayerNorm, softmax and regression heads.  J <= 32. */
+ * wmat (16-bit canonical half-K weight tiles, hi and lo planes), wseq ((offset, count, vector layer, 0) int32 quadruples, n_weights
+ * of them), wvec (f32): ops.pack_token_program.  F, Fc (FFN widths) in {16, 128}.
+ * Split-precision tensor-core operands (fmt: 0 = fp16 planes, 1 = bf16 planes; csrc/umma_split.cuh): fp32-class results;
+ * fp32 accumulation, residual stream, LayerNorm, softmax and regression heads.  J <= 32. */
 int kpf_token_stack(const float* x, const float* y, const float* r3d, const float* desa, const float* jf, const void* wmat,
                     const void* wseq, const float* wvec, int n_weights, int cross, int pre, int B, int J, int D, int L, int F, int Fc,
-                    float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride, int out_jc_c0,
+                    int fmt, float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride, int out_jc_c0,
                     long long* dbg /* NULL, or 64 x int64 device: clock64 stamps of CTA 0 (profiling aid) */, cudaStream_t stream);
 
 /* ---- a7-a9 fused point stage (csrc/point_embed.cu), model/model.py:295-320 ------------------------------------------
@@ -216,6 +218,12 @@ int kpf_eval_errors(const float* pred, const float* gt, const float* cube, int B
  * a_mn == 0: A is [128,K] row-major (K-major operand), else A is given transposed [K,128] (MN-major operand);
  * b_mn == 0: B is [N,K] row-major, else B is given as [K,N]. */
 int kpf_umma_selftest(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn, cudaStream_t stream);
+
+/* split-precision forms (csrc/umma_split.cuh): D[128,N] f32 = A[128,K] * B[N,K]^T with fp32 A, B carried as (hi, lo) 16-bit planes
+ * (fmt 0 = fp16, 1 = bf16), A read from shared memory (a_tmem = 0) or from tensor memory (1); a_exact = 1 drops A's lo plane.
+ * cycles (2 x int64 device, may be NULL): one GEMM issue -> completion, eight GEMMs back to back. */
+int kpf_umma_split_selftest(const float* A, const float* B, float* D, int N, int K, int fmt, int a_tmem, int a_exact, long long* cycles,
+                            cudaStream_t stream);
 
 /* cycle micro-benchmarks of the tcgen05 building blocks (out: 8 x int64 device; see csrc/umma_probe.cu) */
 int kpf_umma_probe(long long* out, int N, int K, int reps, cudaStream_t stream);

@@ -1,4 +1,8 @@
-// DESA on tensor cores (model/model.py:129-204 + the joint embeddings :323-325), SURVEY.md 8f-1.  Two kernels:
+// DESA on tensor cores (model/model.py:129-204 + the joint embeddings :323-325), SURVEY.md 8f-1.  Split precision throughout
+// (csrc/umma_split.cuh): every operand is two 16-bit planes, three MMAs per product, so the results are fp32-class.  The point
+// features e arrive as rows [hi 128 | lo 128] (kpf_point_embed); the tile kernel keeps each scale's W1 / W2 planes in TENSOR
+// MEMORY as the A operands (256 of the 512 columns), which frees their shared memory for the second plane of the activations.
+// Two kernels:
 //
 // desa_prep_kernel   512 threads, two independent roles side by side in one launch:
 //             CTA per sample:  combine the point stage's softmax partials (flash-style) -> joint_agg[J][128]
@@ -18,32 +22,32 @@
 //             are issued together; while they run the rows of tile s+2 are copied (indices fetched one iteration earlier);
 //             then epilogue 2 of s and epilogue 1 of s+1.  One __syncthreads per tile.
 //   output    desa_part[b][scale][j][:], jf[b][j][:]; the 512->128 fusion conv follows in kpf_token_stack.
-#include "tmem_ldst.cuh"
+#include "umma_split.cuh"
 
 namespace kpf {
 
 struct DesaParams {
-    __nv_bfloat16* e;         // [B][N + J][128] point features (kpf_point_embed, batch stride e_bs); rows N.. = bf16 joint features (prep)
-    long long e_bs;
+    uint16_t* e;              // [B][N + J][256] point features, rows = [hi 128 | lo 128] 16-bit planes (kpf_point_embed, batch stride
+    long long e_bs;           //   e_bs elements); rows N.. = the joint features (prep)
     const float* part_acc;    // [B,T,128,32]
     const float* part_ms;     // [B,T,2,32]
     const float* pcl;         // [B,N,3]
     const float* joint;       // [B,J,3]
-    const uint4* wmat;        // Wj [16][128] ; per scale: W1 main [16][128], W1 tail [2][128], W2 [16][128]
+    const uint4* wmat;        // canonical (hi | lo) planes: Wj 2 x [16][128] ; per scale: W1 main 2 x [16][128], W1 tail 2 x [2][128], W2 2 x [16][128]
     const float* wvec;        // bj[128], Wjx[128][4] ; per scale: b1[128], b2[128]
     float* desa_part;         // [B,S,J,128]
     float* jf_out;            // [B,J,128]
     float* cj;                // scratch [B,S,J,128]: W1_s jf[j] (fp32), subtracted in the tile kernel's layer-1 epilogue
     float4* xyz4;             // scratch [B][N + 32]: xyz of the grouped point set (N points, then the J joints), one 16-byte load each
     uint16_t* idx;            // scratch [B,S,J,nsample] ball-query indices (>= N: one of the joints)
-    int B, N, J, T, S, nsample;
+    int B, N, J, T, S, nsample, fmt;
     float radius[4];
     long long* dbg;
 };
 
 constexpr int DS_NT = 512;
-constexpr int DS_MAT_PER_SCALE = 2048 + 256 + 2048;
-constexpr int DS_XBUF = 2048 + 256;   // uint4 per activation buffer (main + K tail)
+constexpr int DS_MAT_PER_SCALE = 2 * (2048 + 256 + 2048);
+constexpr int DS_XBUF = 2 * (2048 + 256);   // uint4 per activation buffer: main hi | main lo | K tail hi | K tail lo
 
 // ================================================================================================ prep
 // Two roles in one launch: CTAs [0, B) embed the joints of one sample (softmax-partial combine + tcgen05 GEMM); CTAs
@@ -133,9 +137,9 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
     }
 
     // ================= joint embedding: jf = relu(Wj [joint_agg | joint_xyz] + b)  (model.py:319-325) =================
-    uint4* sWj = reinterpret_cast<uint4*>(ds_smem);             // [16][128] K-major A operand
-    uint4* sAgg = sWj + 2048;                                    // MN-major B operand [16][4][8]: joint_agg[channel][joint]
-    float* sMS = reinterpret_cast<float*>(sAgg + 512);           // [T][2][32] partial max/sum -> [T][32] factors + den[32]
+    uint4* sWj = reinterpret_cast<uint4*>(ds_smem);             // 2 planes x [16][128] K-major A operand
+    uint4* sAgg = sWj + 4096;                                    // 2 planes x MN-major B operand [16][4][8]: joint_agg[channel][joint]
+    float* sMS = reinterpret_cast<float*>(sAgg + 1024);          // [T][2][32] partial max/sum -> [T][32] factors + den[32]
     float4* sJ = reinterpret_cast<float4*>(sMS + T * 64 + 64);   // [32] joint xyz
     __shared__ __align__(8) uint64_t wbar, mma_bar;
     __shared__ uint32_t tmem_slot;
@@ -146,9 +150,14 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         mbar_init(&wbar, 1);
         mbar_init(&mma_bar, 1);
         fence_mbar_init();
-        mbar_expect_tx(&wbar, 2048 * 16);
-        tma_bulk_g2s(sWj, p.wmat, 2048 * 16, &wbar);
+        mbar_expect_tx(&wbar, 4096 * 16);
+        tma_bulk_g2s(sWj, p.wmat, 4096 * 16, &wbar);
     }
+    const int fmt = p.fmt;
+    SmemOp opW, opA;   // A = the weight planes in sWj, B = joint_agg / jf planes in sAgg
+    opW.hi = smem_u32(sWj); opW.lo = opW.hi + 2048 * 16; opW.lbo = 2048; opW.sbo = 128;
+    opA.hi = smem_u32(sAgg); opA.lo = opA.hi + 512 * 16; opA.lbo = 512; opA.sbo = 128;
+    const uint32_t id_jf = umma_idesc_f16(128, 32, false, true, fmt, fmt);
     pdl_wait();   // weights only so far
     if (tid < 32) {
         const float* s = p.joint + ((size_t)b * J + (tid < J ? tid : 0)) * 3;
@@ -192,12 +201,12 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) agg[j] = (4 * jq + j) < J ? agg[j] / sMS[T * 64 + 4 * jq + j] : 0.f;
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(agg[0], agg[1]), hi = __floats2bfloat162_rn(agg[2], agg[3]);
-            uint2 o;
-            o.x = *reinterpret_cast<const uint32_t*>(&lo);
-            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            uint2 oh, ol;
+            split2(fmt, agg[0], agg[1], oh.x, ol.x);
+            split2(fmt, agg[2], agg[3], oh.y, ol.y);
             // (k = channel, n = joint), n contiguous: chunk jq / 2 of the row, half jq & 1
-            reinterpret_cast<uint2*>(sAgg + (ch >> 3) * 32 + (jq >> 1) * 8 + (ch & 7))[jq & 1] = o;
+            reinterpret_cast<uint2*>(sAgg + (ch >> 3) * 32 + (jq >> 1) * 8 + (ch & 7))[jq & 1] = oh;
+            reinterpret_cast<uint2*>(sAgg + 512 + (ch >> 3) * 32 + (jq >> 1) * 8 + (ch & 7))[jq & 1] = ol;
         }
     }
     fence_proxy_async();
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         tc_fence_after();
         mbar_wait(&wbar, 0);
         if (elect_one()) {
-            umma_gemm(tmem0, smem_u32(sWj), 2048, 128, smem_u32(sAgg), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, false);
+            umma_gemm3_ss(tmem0, opW, opA, id_jf, 128, false);
             umma_commit(&mma_bar);
         }
         __syncwarp();
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         tmem_ld<8>(tmem_q + 8 * cg, d);
         const float bj = p.wvec[ch];
         const float4 wx = *reinterpret_cast<const float4*>(p.wvec + 128 + 4 * ch);
-        __nv_bfloat16* erow = p.e + (size_t)b * p.e_bs + (size_t)N * 128 + ch;
+        uint16_t* erow = p.e + (size_t)b * p.e_bs + (size_t)N * 256 + ch;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int j = 8 * cg + i;
@@ -231,12 +240,18 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
                 const float4 c = sJ[j];
                 v = fmaxf(d[i] + bj + wx.x * c.x + wx.y * c.y + wx.z * c.z, 0.f);
                 if (p.jf_out) p.jf_out[((size_t)b * J + j) * 128 + ch] = v;
-                erow[(size_t)j * 128] = __float2bfloat16_rn(v);   // the joints are points N .. N+J-1 of the grouped set (model.py:168-169)
+                uint32_t h2, l2;   // the joints are points N .. N+J-1 of the grouped set (model.py:168-169)
+                split2(fmt, v, 0.f, h2, l2);
+                erow[(size_t)j * 256] = (uint16_t)h2;
+                erow[(size_t)j * 256 + 128] = (uint16_t)l2;
             }
             d[i] = v;
         }
-        // bf16 jf as the B operand [K = channel][N = joint] of the W1 jf GEMMs (same layout as sAgg, whose reader has completed)
-        sAgg[(ch >> 3) * 32 + cg * 8 + (ch & 7)] = pack8_bf16(d);
+        // jf as the B operand [K = channel][N = joint] of the W1 jf GEMMs (same layout as sAgg, whose reader has completed)
+        uint4 oh, ol;
+        split8(fmt, d, oh, ol);
+        sAgg[(ch >> 3) * 32 + cg * 8 + (ch & 7)] = oh;
+        sAgg[512 + (ch >> 3) * 32 + cg * 8 + (ch & 7)] = ol;
     }
     // ---- cj[s][j][:] = W1_s jf[j] for every scale: the tile kernel feeds the RAW gathered point features to its layer-1 GEMM and
     //      subtracts this term in the epilogue ( W1 (feat - jf) = W1 feat - W1 jf ), so its gather is a pure copy
@@ -246,15 +261,15 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         __syncthreads();       // the previous MMA's operand (sWj) and accumulator reads are done
         if (warp_u == 0) {
             if (elect_one()) {
-                mbar_expect_tx(&wbar, 2048 * 16);
-                tma_bulk_g2s(sWj, p.wmat + 2048 + (size_t)sc * DS_MAT_PER_SCALE, 2048 * 16, &wbar);
+                mbar_expect_tx(&wbar, 4096 * 16);
+                tma_bulk_g2s(sWj, p.wmat + 4096 + (size_t)sc * DS_MAT_PER_SCALE, 4096 * 16, &wbar);   // W1 main: hi | lo
             }
             __syncwarp();
             fence_proxy_async();
             tc_fence_after();
             mbar_wait(&wbar, (sc + 1) & 1);
             if (elect_one()) {
-                umma_gemm(tmem0, smem_u32(sWj), 2048, 128, smem_u32(sAgg), 512, 128, umma_idesc_bf16(128, 32, false, true), 128, false);
+                umma_gemm3_ss(tmem0, opW, opA, id_jf, 128, false);
                 umma_commit(&mma_bar);
             }
             __syncwarp();
@@ -284,11 +299,10 @@ struct DesaItem {   // (scale, sample, first joint) of a work item, advanced inc
 
 __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaParams p) {
     extern __shared__ __align__(128) unsigned char ds_smem[];
-    uint4* sW1 = reinterpret_cast<uint4*>(ds_smem);   // [16][128] + tail [2][128]
-    uint4* sW2 = sW1 + 2048 + 256;                     // [16][128]
-    uint4* sX = sW2 + 2048;                            // [2] x (K-major activations [16 row groups][16 k-chunks][8 rows] + tail [16][2][8])
-    uint4* sH = sX + 2 * DS_XBUF;                      // MN-major [16][16][8]
-    float* sPart = reinterpret_cast<float*>(sH + 2048);   // [2][4][128] per-column-group maxima
+    uint4* sW1t = reinterpret_cast<uint4*>(ds_smem);  // W1's K tail (the xyz columns), 2 planes x [2][128]; W1 main / W2 live in tensor memory
+    uint4* sX = sW1t + 512;                            // [2] x (2 planes x K-major activations [16 row groups][16 k-chunks][8 rows] + 2 planes x tail [16][2][8])
+    uint4* sH = sX + 2 * DS_XBUF;                      // 2 planes x MN-major [16][16][8]
+    float* sPart = reinterpret_cast<float*>(sH + 4096);   // [2][4][128] per-column-group maxima
     __shared__ __align__(8) uint64_t wbar, g1_bar, g2_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -305,7 +319,8 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     const int ns_shift = 31 - __clz(NS);                          // NS is a power of two: joint of tile row x = x >> ns_shift
     const int total = S * B * TPS;
     const int it0 = (int)((long long)total * blockIdx.x / gridDim.x), it1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
-    const uint32_t ACC1 = 0, ACC2 = 128;
+    const uint32_t ACC1 = 0, ACC2 = 128, TW1_HI = 256, TW1_LO = 320, TW2_HI = 384, TW2_LO = 448;   // TMEM columns
+    const int fmt = p.fmt;
     int n_stamp = 0;
     auto stamp = [&]() {
         if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 48) p.dbg[16 + n_stamp] = clock64();
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     };
     stamp();
     pdl_launch_dependents();
-    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&wbar, 1);
         mbar_init(&g1_bar, 1);
@@ -371,12 +386,12 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         for (int h = 0; h < 2; ++h) {
             const int row = r + 64 * h, jj = it.j0 + (row >> ns_shift);
             const bool ok = jj < J;
-            const __nv_bfloat16* src = p.e + (size_t)it.b * p.e_bs + (size_t)ii[h] * 128 + 8 * g8;
+            const uint16_t* src = p.e + (size_t)it.b * p.e_bs + (size_t)ii[h] * 256 + 8 * g8;   // row = [hi 128 | lo 128]
             uint4* X = sX + (item & 1) * DS_XBUF + (row >> 3) * 128 + g8 * 8 + (row & 7);
             const uint32_t nbytes = ok ? 16u : 0u;   // rows beyond the last joint are zero filled
 #pragma unroll
-            for (int k = 0; k < 2; ++k)   // k-chunk 8k + g8 of the row
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(X + k * 64)), "l"(src + 64 * k), "r"(nbytes) : "memory");
+            for (int k = 0; k < 4; ++k)   // 16-byte chunk 8k + g8 of the 512-byte row: k-chunk (8k + g8) & 15 of plane k >> 1
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(X + (k >> 1) * 2048 + (k & 1) * 64)), "l"(src + 64 * k), "r"(nbytes) : "memory");
             if (g8 == 0) {   // the xyz tail of the row is computed at the end of the iteration from these loads
                 tail_ok[h] = ok;
                 const float4 a4 = __ldg(tab + ii[h]), c4 = __ldg(tab + N + (ok ? jj : 0));
@@ -397,9 +412,13 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                 t8[1] = (pq[h].y - pc[h].y) * inv_r;
                 t8[2] = (pq[h].z - pc[h].z) * inv_r;
             }
-            uint4* X = sX + (item & 1) * DS_XBUF + 2048 + (row >> 3) * 16 + (row & 7);
-            X[0] = pack8_bf16(t8);
+            uint4* X = sX + (item & 1) * DS_XBUF + 4096 + (row >> 3) * 16 + (row & 7);
+            uint4 th, tl;
+            split8(fmt, t8, th, tl);
+            X[0] = th;
             X[8] = make_uint4(0, 0, 0, 0);
+            X[256] = tl;
+            X[256 + 8] = make_uint4(0, 0, 0, 0);
         }
     };
     // maxima of a finished tile: combine the column groups of each joint, store
@@ -423,13 +442,26 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         const int i1 = it1 < run_end ? it1 : run_end;
         c_idx = c_rows = c_epi = c_max = first;
         // every MMA of the previous run has completed (its epilogues ran), so the weight buffers are free
+        const uint4* ws = p.wmat + 4096 + (size_t)sc0 * DS_MAT_PER_SCALE;   // W1 main hi | lo, W1 tail hi | lo, W2 hi | lo
         if (issuer) {
             if (elect_one()) {
-                const uint4* ws = p.wmat + 2048 + (size_t)sc0 * DS_MAT_PER_SCALE;
-                mbar_expect_tx(&wbar, DS_MAT_PER_SCALE * 16);
-                tma_bulk_g2s(sW1, ws, DS_MAT_PER_SCALE * 16, &wbar);   // W1 | W1 tail | W2 are contiguous on both sides
+                mbar_expect_tx(&wbar, 512 * 16);
+                tma_bulk_g2s(sW1t, ws + 4096, 512 * 16, &wbar);
             }
             __syncwarp();
+        } else {
+            // the scale's W1 main / W2 planes -> tensor memory (A operands): row ch = lane 32q + lane, 16-bit K elements packed two
+            // per column; this thread moves k-chunks [4cg, 4cg + 4) (16 columns) of each of the four planes
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl) {
+                const uint4* src = ws + (pl < 2 ? pl * 2048 : 4096 + 512 + (pl - 2) * 2048);
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = __ldg(src + (4 * cg + k) * 128 + ch);
+                const uint32_t col = (pl == 0 ? TW1_HI : pl == 1 ? TW1_LO : pl == 2 ? TW2_HI : TW2_LO) + 16 * cg;
+                tmem_st_nw<16>(tmem + col, reinterpret_cast<const float*>(v));
+            }
+            tmem_wait_st();
         }
         const float b1 = p.wvec[128 + 512 + sc0 * 256 + ch], b2 = p.wvec[128 + 512 + sc0 * 256 + 128 + ch];
         inv_r = 1.f / p.radius[sc0];
@@ -446,16 +478,25 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                     if (!w_ready) mbar_wait(&wbar, w_phase);
                     if (elect_one()) {
                         if (s >= i0) {   // layer 2 of tile s: D2[c][row] = W2 h
-                            umma_gemm(tmem0 + ACC2, smem_u32(sW2), 2048, 128, smem_u32(sH), 2048, 128, umma_idesc_bf16(128, 128, false, true),
-                                      128, false);
+                            TmemOp a;
+                            a.hi = tmem0 + TW2_HI; a.lo = tmem0 + TW2_LO;
+                            SmemOp hb;
+                            hb.hi = smem_u32(sH); hb.lo = hb.hi + 2048 * 16; hb.lbo = 2048; hb.sbo = 128;
+                            umma_gemm3_ts(tmem0 + ACC2, a, hb, umma_idesc_f16(128, 128, false, true, fmt, fmt), 128, false);
                             umma_commit(&g2_bar);
                         }
                         if (s + 1 < i1) {   // layer 1 of tile s + 1: D1[c][row] = W1 [feat - jf | xyz]
-                            const uint4* X = sX + ((s + 1) & 1) * DS_XBUF;
-                            const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
+                            const uint32_t X = smem_u32(sX + ((s + 1) & 1) * DS_XBUF);
+                            const uint32_t id128 = umma_idesc_f16(128, 128, false, false, fmt, fmt);
                             // B operand: 128 B between k-chunks, 2048 B (main) / 256 B (tail) between 8-row groups
-                            umma_gemm(tmem0 + ACC1, smem_u32(sW1), 2048, 128, smem_u32(X), 128, 2048, id128, 128, false);
-                            umma_gemm(tmem0 + ACC1, smem_u32(sW1 + 2048), 2048, 128, smem_u32(X + 2048), 128, 256, id128, 16, true);
+                            TmemOp a;
+                            a.hi = tmem0 + TW1_HI; a.lo = tmem0 + TW1_LO;
+                            SmemOp xb, ta, tb;
+                            xb.hi = X; xb.lo = X + 2048 * 16; xb.lbo = 128; xb.sbo = 2048;
+                            umma_gemm3_ts(tmem0 + ACC1, a, xb, id128, 128, false);
+                            ta.hi = smem_u32(sW1t); ta.lo = ta.hi + 256 * 16; ta.lbo = 2048; ta.sbo = 128;
+                            tb.hi = X + 4096 * 16; tb.lo = tb.hi + 256 * 16; tb.lbo = 128; tb.sbo = 256;
+                            umma_gemm3_ss(tmem0 + ACC1, ta, tb, id128, 16, true);
                             umma_commit(&g1_bar);
                         }
                     }
@@ -497,7 +538,12 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
 #pragma unroll
                     for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + cjb, 0.f);   // relu(W1 feat + tail - W1 jf + b1)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) sH[(ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = pack8_bf16(a + 8 * c);
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 hh, hl;
+                        split8(fmt, a + 8 * c, hh, hl);
+                        sH[(ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = hh;
+                        sH[2048 + (ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = hl;
+                    }
                 }
                 if (have_rows) store_tail(s + 2);
             }
@@ -511,23 +557,26 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem0, 256);
+    if (warp == 0) tmem_dealloc(tmem0, 512);
 }
 
 }  // namespace kpf
 
 extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
                               const void* wmat, const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2,
-                              float r3, float* desa_part, float* jf_out, void* scratch, int num_sms, long long* dbg, cudaStream_t stream) {
+                              float r3, int fmt, float* desa_part, float* jf_out, void* scratch, int num_sms, long long* dbg,
+                              cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && N + J <= 65535 && J >= 1 && J <= 32 && S >= 1 && S <= 4);
     KPF_REQUIRE(nsample == 32 || nsample == 64 || nsample == 128);
+    KPF_REQUIRE(fmt == FMT_F16 || fmt == FMT_BF16);
     KPF_REQUIRE(((uintptr_t)wmat % 16) == 0 && ((uintptr_t)e % 16) == 0 && ((uintptr_t)part_acc % 16) == 0 && ((uintptr_t)wvec % 16) == 0);
     if (B == 0) return 0;
     KPF_REQUIRE(scratch != nullptr && ((uintptr_t)scratch % 16) == 0 && num_sms >= 1);
     DesaParams p;
-    KPF_REQUIRE(e_batch_stride >= (long long)(N + J) * 128 && e_batch_stride % 8 == 0);
-    p.e = (__nv_bfloat16*)e; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;
+    KPF_REQUIRE(e_batch_stride >= (long long)(N + J) * 256 && e_batch_stride % 8 == 0);
+    p.fmt = fmt;
+    p.e = (uint16_t*)e; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;
     p.wvec = wvec; p.desa_part = desa_part; p.jf_out = jf_out; p.B = B; p.N = N; p.J = J; p.T = N / 128; p.S = S; p.nsample = nsample;
     p.dbg = dbg;
     p.radius[0] = r0; p.radius[1] = r1; p.radius[2] = r2; p.radius[3] = r3;
@@ -535,10 +584,10 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     p.xyz4 = (float4*)((char*)scratch + (size_t)B * S * J * 128 * 4);
     p.idx = (uint16_t*)((char*)scratch + (size_t)B * S * J * 128 * 4 + (size_t)B * (N + 32) * 16);
     const int NW = (N + J + 31) / 32;
-    const size_t smem_jf = (size_t)(2048 + 512) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
+    const size_t smem_jf = (size_t)(4096 + 1024) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
     const size_t smem_bq = (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * NW * 4 + 64;
     const size_t smem_a = smem_jf > smem_bq ? smem_jf : smem_bq;
-    const size_t smem_b = (size_t)(DS_MAT_PER_SCALE + 2 * DS_XBUF + 2048) * 16 + 2 * 512 * 4 + 64;
+    const size_t smem_b = (size_t)(512 + 2 * DS_XBUF + 4096) * 16 + 2 * 512 * 4 + 64;
     KPF_REQUIRE(smem_a <= 227 * 1024 && smem_b <= 227 * 1024);
     cudaError_t err = kpf::set_smem(desa_prep_kernel, smem_a);
     if (err != cudaSuccess) return (int)err;

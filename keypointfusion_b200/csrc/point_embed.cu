@@ -13,7 +13,7 @@
 //       D[c][j] = sum_n e[n][c] p[n][j]                                    tcgen05 with MN-major operands
 //     outputs: e [B,N,128] bf16, and per tile (D, max, sum) partials that the DESA kernel combines flash-style.
 //   Weights (96 KB bf16) stay resident in shared memory; CTAs are persistent over tiles.
-#include "tmem_ldst.cuh"
+#include "umma_split.cuh"
 
 namespace kpf {
 
@@ -84,19 +84,20 @@ repack_bf16_kernel(const __nv_bfloat16* __restrict__ f_d, const __nv_bfloat16* _
 }
 
 struct PointParams {
-    const uint4* featT;      // [B,HW,36] uint4 (288 bf16)
+    const uint4* feat_hi;    // [B,HW,36] uint4 (288 bf16): repacked maps (hi plane; the only one for bf16 maps)
+    const uint4* feat_lo;    // same layout, lo plane of fp32 maps, or null
     const int32_t* idx;      // [B,N,4]
     const float* clos;       // [B,N,4]
     const float* pcl;        // [B,N,3]
     const float* joint;      // [B,J,3]
     const int32_t* order;    // [B,N] processing order of the points (kpf_spatial_order) or null = identity
-    const uint4* wmat;       // W1a, W1b, W2: 3 x [16][128] uint4
+    const uint4* wmat;       // canonical planes: W1 hi [32][128], W1 lo, W2 hi [16][128], W2 lo
     const float* wvec;       // b1[128], b2[128]
-    __nv_bfloat16* e_out;    // [B,N,128] with batch stride e_bs elements (>= N*128: DESA appends its joint rows behind the points)
-    long long e_bs;
-    float* part_acc;         // [B,T,128,32]
+    uint16_t* e_out;         // [B,N,256]: rows [hi 128 | lo 128] 16-bit planes, batch stride e_bs elements (>= N*256: DESA appends its
+    long long e_bs;          //   joint rows behind the points)
+    float* part_acc;         // [B,T,128,32]   T = N / 64
     float* part_ms;          // [B,T,2,32]  (max, sum)
-    int B, N, J, HW;
+    int B, N, J, HW, fmt;
     float kernel_size;
     long long* dbg;
 };
@@ -111,46 +112,72 @@ __device__ __forceinline__ void bf16x8_fma(float* acc, const uint4& v, float w) 
     }
 }
 
-constexpr int PE_NT = 512;   // gather: warp = 8 points x 4 chunk lanes; epilogues: 4 lane quarters x 4 column groups
+constexpr int PE_NT = 512;
+constexpr int PE_TP = 64;    // points per tile
+// TMEM columns: the resident weight planes (A operands, 16-bit pairs), then the two accumulators; after the epilogue has read
+// them the accumulator columns are reused for e^T (the aggregation's A operand) and the aggregation accumulator
+constexpr uint32_t PE_W1H = 0, PE_W1L = 128, PE_W2H = 256, PE_W2L = 320, PE_ACC1 = 384, PE_ACC2 = 448;
+constexpr uint32_t PE_EH = PE_ACC2, PE_EL = PE_ACC2 + 32, PE_ACC3 = PE_ACC1;
 
+// The whole point stage, computed TRANSPOSED: D^T[channel][point] = W[channel][k] X[point][k].  The folded weights (K = 384, two
+// 16-bit planes) stay in TENSOR MEMORY for the life of the persistent CTA as the A operands; a tile is 64 points whose gathered
+// inputs are written as K-major B operand planes; a thread of the epilogue owns one output channel (its TMEM lane) and 16 points.
 __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams p) {
     extern __shared__ __align__(128) unsigned char pe_smem[];
-    uint4* sW = reinterpret_cast<uint4*>(pe_smem);   // [3][2048]
-    uint4* sA1 = sW + 3 * 2048;                       // K-major [16 row groups][32 k-chunks][8 rows] (K = 256); after the MMAs: sP [16][4][8]
-    uint4* sA2 = sA1 + 4096;                          // K-major [16][16][8] (K = 128) = e^T MN-major [16][16][8] after the MMAs
-    float* sJ = reinterpret_cast<float*>(sA2 + 2048); // [32][4] joints of the current sample
-    float* sRed = sJ + 128;                           // [32] per-joint tile maxima
-    float* sB = sRed + 128;                           // b1[128], b2[128]
-    float* sT = sB + 256;                             // [21][129] transposed softmax scratch
-    int* sN = reinterpret_cast<int*>(sT + 21 * 129 + 3);  // [2][128] point ids of the tile in flight / being prefetched
-    __shared__ __align__(8) uint64_t wbar, mma_bar;
+    uint4* sX1 = reinterpret_cast<uint4*>(pe_smem);   // 2 planes x [8 point groups][32 k-chunks][8 points]   (K = 256)
+    uint4* sX2 = sX1 + 2 * 2048;                       // 2 planes x [8][16][8]                                (K = 128)
+    uint4* sP = sX2 + 2 * 1024;                        // 2 planes x MN-major B [8 point groups][4 joint groups][8 points]: softmax numerators
+    uint4* sE = sP + 2 * 256;                          // [64 points][32 chunks]: e rows [hi | lo] staged for the coalesced copy-out
+    float* sJ = reinterpret_cast<float*>(sE + 2048);   // [32][4] joints of the current sample
+    float* sRed = sJ + 128;                            // [32] per-joint tile maxima
+    float* sB = sRed + 32;                             // b1[128], b2[128]
+    float* sT = sB + 256;                              // [21][65] transposed softmax scratch
+    int* sN = reinterpret_cast<int*>(sT + 21 * 65 + 3);   // [2][64] point ids of the tile in flight / being prefetched
+    __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = warp_index_uniform();  // MMA issue: one elected lane of warp 0 from warp-uniform code (umma.cuh)
-    // gather / offsets: a warp takes 8 points; lane = (point p8, sub): the 4 `sub` lanes of a point read 64 contiguous bytes of a
-    // tap row per load (8 L1 wavefronts per warp load instead of 32 with one lane per row) and the 8 points of a warp fill the
-    // 8 rows x 16 B core matrices of the operand, so the stores are conflict free
-    const int r = 8 * warp + (lane & 7), sub = lane >> 3;
-    const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane; // epilogues: TMEM lane `row`, columns [32cg, 32cg + 32)
-    const int J = p.J, N = p.N, T = N / 128;
+    // gather: warp = 8 points x 4 chunk lanes (64 contiguous bytes of a tap row per point per load; the 8 points fill the 8 rows x
+    // 16 B core matrices of the operand, so the stores are conflict free).  Warps 0-7 (grp 0) take the depth-branch and weight-map
+    // chunks and the joint offsets, warps 8-15 (grp 1) the rgb-branch chunks of the same 64 points.
+    const int r = 8 * (warp & 7) + (lane & 7), sub = lane >> 3, grp = warp >> 3;
+    const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;   // epilogues: channel ch (TMEM lane), points [16cg, 16cg + 16)
+    const int J = p.J, N = p.N, T = N / PE_TP, fmt = p.fmt;
 
     pdl_launch_dependents();
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
-        mbar_init(&wbar, 1);
         mbar_init(&mma_bar, 1);
         fence_mbar_init();
-        mbar_expect_tx(&wbar, 3 * 2048 * 16);
-        tma_bulk_g2s(sW, p.wmat, 3 * 2048 * 16, &wbar);
     }
     for (int i = tid; i < 256; i += PE_NT) sB[i] = p.wvec[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem0 = tmem_slot, tmem = tmem0 + ((uint32_t)(32 * q) << 16);
-    const uint32_t ACC1 = 0, ACC2 = 128, ACC3 = 256;
+    {   // weights -> tensor memory: row ch, 16-bit K elements packed two per column; this thread moves a quarter of each plane
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {   // W1 planes: 32 k-chunks = 128 columns, chunks [8cg, 8cg + 8)
+            const uint4* src = p.wmat + pl * 4096;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = __ldg(src + (8 * cg + 4 * h + k) * 128 + ch);
+                tmem_st_nw<16>(tmem + (pl ? PE_W1L : PE_W1H) + 32 * cg + 16 * h, reinterpret_cast<const float*>(v));
+            }
+        }
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {   // W2 planes: 16 k-chunks = 64 columns, chunks [4cg, 4cg + 4)
+            const uint4* src = p.wmat + 8192 + pl * 2048;
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __ldg(src + (4 * cg + k) * 128 + ch);
+            tmem_st_nw<16>(tmem + (pl ? PE_W2L : PE_W2H) + 16 * cg, reinterpret_cast<const float*>(v));
+        }
+        tmem_wait_st();
+    }
     uint32_t phase = 0;
-    bool w_ready = false;
     const float inv_ks = 1.f / p.kernel_size;
     int n_stamp = 0;
     auto stamp = [&]() {
@@ -163,11 +190,11 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
     int4 id = make_int4(0, 0, 0, 0);
     float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
     float px = 0.f, py = 0.f, pz = 0.f;
-    int n_id = 0, tile_par = 0;
+    int tile_par = 0;
     auto fetch_point = [&](int tile, int par) {
         const int b = tile / T, t = tile - b * T;
-        n_id = p.order ? __ldg(p.order + (size_t)b * N + t * 128 + r) : t * 128 + r;   // tile = 128 consecutive points of the order
-        if (sub == 0) sN[par * 128 + r] = n_id;
+        const int n_id = p.order ? __ldg(p.order + (size_t)b * N + t * PE_TP + r) : t * PE_TP + r;   // tile = 64 consecutive points of the order
+        if (sub == 0 && grp == 0) sN[par * PE_TP + r] = n_id;
         const size_t pn = (size_t)b * N + n_id;
         id = __ldg(reinterpret_cast<const int4*>(p.idx + pn * 4));
         cw = __ldg(reinterpret_cast<const float4*>(p.clos + pn * 4));
@@ -180,61 +207,89 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
 
     for (int tile = blockIdx.x; tile < p.B * T; tile += gridDim.x) {
         const int b = tile / T, t = tile - b * T;
-        __syncthreads();  // previous tile's readers of sJ / sRed / sT are done (its MMAs were waited for)
+        __syncthreads();  // previous tile's readers of sJ / sRed / sT / sE are done (its MMAs were waited for)
         if (tid < J) {
             sJ[4 * tid] = p.joint[((size_t)b * J + tid) * 3];
             sJ[4 * tid + 1] = p.joint[((size_t)b * J + tid) * 3 + 1];
             sJ[4 * tid + 2] = p.joint[((size_t)b * J + tid) * 3 + 2];
         }
-        const uint4* r0 = p.featT + ((size_t)b * p.HW + id.x) * PE_CH;
-        const uint4* r1 = p.featT + ((size_t)b * p.HW + id.y) * PE_CH;
-        const uint4* r2 = p.featT + ((size_t)b * p.HW + id.z) * PE_CH;
-        const uint4* r3 = p.featT + ((size_t)b * p.HW + id.w) * PE_CH;
         stamp();
-        // ---- K3: 4-tap gathers: chunk 4i + sub of the 36-chunk row in iteration i (depth 0-15 -> A1, rgb 16-31 -> A2, weight map
-        //      32-35 -> A1 chunks 16-19 and the softmax), three iterations (12 x 16 B) in flight
-        float wraw[8];   // gathered weight-map channels [8 sub, 8 sub + 8) of this point
-        uint4* a1r = sA1 + (r >> 3) * 256 + (r & 7);
-        uint4* a2r = sA2 + (r >> 3) * 128 + (r & 7);
+        // ---- K3: 4-tap gathers of this thread's chunks of the 36-chunk row: grp 0 -> depth 0-15 (A1 chunks 0-15) and weight map
+        //      32-35 (A1 chunks 16-19 and the softmax); grp 1 -> rgb 16-31 (A2 chunks 0-15)
+        float wraw[8];   // grp 0: gathered weight-map channels [8 sub, 8 sub + 8) of this point
+        uint4* x1r = sX1 + (r >> 3) * 256 + (r & 7);
+        uint4* x2r = sX2 + (r >> 3) * 128 + (r & 7);
+        {
+            const size_t rb = (size_t)b * p.HW;
+            const uint4 *h0 = p.feat_hi + (rb + id.x) * PE_CH, *h1 = p.feat_hi + (rb + id.y) * PE_CH, *h2 = p.feat_hi + (rb + id.z) * PE_CH,
+                        *h3 = p.feat_hi + (rb + id.w) * PE_CH;
+            const int nload = grp == 0 ? 5 : 4, c_base = grp == 0 ? 0 : 16;
+            uint4 v[5][4];
 #pragma unroll
-        for (int i0 = 0; i0 < 9; i0 += 3) {
-            uint4 v[3][4];
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int cc = 4 * (i0 + u) + sub;
-                v[u][0] = __ldg(r0 + cc);
-                v[u][1] = __ldg(r1 + cc);
-                v[u][2] = __ldg(r2 + cc);
-                v[u][3] = __ldg(r3 + cc);
-            }
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                bf16x8_fma(acc, v[u][0], cw.x);
-                bf16x8_fma(acc, v[u][1], cw.y);
-                bf16x8_fma(acc, v[u][2], cw.z);
-                bf16x8_fma(acc, v[u][3], cw.w);
-                const int i = i0 + u;   // compile-time after unrolling
-                if (i < 4) {
-                    a1r[(4 * i + sub) * 8] = pack8_bf16(acc);
-                } else if (i < 8) {
-                    a2r[(4 * (i - 4) + sub) * 8] = pack8_bf16(acc);
-                } else {
-                    a1r[(16 + sub) * 8] = pack8_bf16(acc);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) wraw[k] = acc[k];
+            for (int u = 0; u < 5; ++u) {
+                if (u < nload) {
+                    const int cc = (u < 4 ? c_base + 4 * u : 32) + sub;
+                    v[u][0] = __ldg(h0 + cc);
+                    v[u][1] = __ldg(h1 + cc);
+                    v[u][2] = __ldg(h2 + cc);
+                    v[u][3] = __ldg(h3 + cc);
                 }
             }
+            float acc[5][8];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
+                if (u < nload) {
+                    bf16x8_fma(acc[u], v[u][0], cw.x);
+                    bf16x8_fma(acc[u], v[u][1], cw.y);
+                    bf16x8_fma(acc[u], v[u][2], cw.z);
+                    bf16x8_fma(acc[u], v[u][3], cw.w);
+                }
+            }
+            if (p.feat_lo) {   // fp32 maps: add the lo plane's taps
+                const uint4 *l0 = p.feat_lo + (rb + id.x) * PE_CH, *l1 = p.feat_lo + (rb + id.y) * PE_CH, *l2 = p.feat_lo + (rb + id.z) * PE_CH,
+                            *l3 = p.feat_lo + (rb + id.w) * PE_CH;
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    if (u < nload) {
+                        const int cc = (u < 4 ? c_base + 4 * u : 32) + sub;
+                        bf16x8_fma(acc[u], __ldg(l0 + cc), cw.x);
+                        bf16x8_fma(acc[u], __ldg(l1 + cc), cw.y);
+                        bf16x8_fma(acc[u], __ldg(l2 + cc), cw.z);
+                        bf16x8_fma(acc[u], __ldg(l3 + cc), cw.w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                if (u < nload) {
+                    uint4 oh, ol;
+                    split8(fmt, acc[u], oh, ol);
+                    if (grp == 1) {
+                        x2r[(4 * u + sub) * 8] = oh;
+                        x2r[1024 + (4 * u + sub) * 8] = ol;
+                    } else {
+                        const int kc = u < 4 ? 4 * u + sub : 16 + sub;
+                        x1r[kc * 8] = oh;
+                        x1r[2048 + kc * 8] = ol;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wraw[k] = acc[4][k];
         }
         // softmax over the tile's points, step 1: the gathered weights, transposed, for the per-joint maxima
+        if (grp == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (8 * sub + k < J) sT[(8 * sub + k) * 129 + r] = wraw[k];
+            for (int k = 0; k < 8; ++k)
+                if (8 * sub + k < J) sT[(8 * sub + k) * 65 + r] = wraw[k];
+        }
         stamp();
         __syncthreads();  // sJ, sT visible
         // ---- K4b: [unit offset xyz, closeness] of joints [6sub, 6sub + 6), then xyz -> chunks 20 + 3sub .. of A1 (ops.pack_point_embed
-        //      orders W1's columns to match)
-        {
+        //      orders W1's columns to match).  fp32-exact sqrt / divisions: these values feed a split-precision operand.
+        if (grp == 0) {
             float buf[24];
 #pragma unroll
             for (int jj = 0; jj < 6; ++jj) {
@@ -242,9 +297,8 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
                 if (j < J) {
                     const float ox = sJ[4 * j] - px, oy = sJ[4 * j + 1] - py, oz = sJ[4 * j + 2] - pz;
-                    const float d2 = ox * ox + oy * oy + oz * oz;
-                    const float dis = d2 * rsqrtf(fmaxf(d2, 1e-30f));       // bf16 operand: approximate sqrt / divide are ample
-                    const float inv = __fdividef(1.f, dis + 1e-8f);
+                    const float dis = sqrtf(ox * ox + oy * oy + oz * oz);
+                    const float inv = 1.f / (dis + 1e-8f);
                     const float heat = (p.kernel_size - dis) * inv_ks;
                     const float msk = (heat >= 0.f && pz < 0.99f) ? 1.f : 0.f;
                     o0 = ox * inv * msk;
@@ -262,19 +316,24 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
                 buf[4 * jj + 3] = o3;
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) a1r[(20 + 3 * sub + c) * 8] = pack8_bf16(buf + 8 * c);
+            for (int c = 0; c < 3; ++c) {
+                uint4 oh, ol;
+                split8(fmt, buf + 8 * c, oh, ol);
+                x1r[(20 + 3 * sub + c) * 8] = oh;
+                x1r[2048 + (20 + 3 * sub + c) * 8] = ol;
+            }
         }
-        // softmax step 1b: per-joint maximum, 16 threads per joint
+        // softmax step 1b: per-joint maximum over the tile's 64 points, 16 threads per joint
         {
             const int rj = tid >> 4, rs = tid & 15;
             float m = -INFINITY;
             if (rj < J) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) m = fmaxf(m, sT[rj * 129 + rs + 16 * i]);
+                for (int i = 0; i < 4; ++i) m = fmaxf(m, sT[rj * 65 + rs + 16 * i]);
             }
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (rs == 0 && rj < 32) sRed[rj] = rj < J ? m : -INFINITY;
+            if (rs == 0) sRed[rj] = rj < J ? m : -INFINITY;
         }
         stamp();
         fence_proxy_async();
@@ -282,28 +341,37 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         __syncthreads();
         if (warp_u == 0) {
             tc_fence_after();
-            if (!w_ready) mbar_wait(&wbar, 0);
             if (elect_one()) {
-                const uint32_t id128 = umma_idesc_bf16(128, 128, false, false);
-                // A operands: 128 B between k-chunks, 4096 / 2048 B between 8-row groups
-                umma_gemm(tmem0 + ACC1, smem_u32(sA1), 128, 4096, smem_u32(sW), 2048, 128, id128, 128, false);
-                umma_gemm(tmem0 + ACC1, smem_u32(sA1 + 128), 128, 4096, smem_u32(sW + 2048), 2048, 128, id128, 128, true);
-                umma_gemm(tmem0 + ACC2, smem_u32(sA2), 128, 2048, smem_u32(sW + 4096), 2048, 128, id128, 128, false);
+                const uint32_t id64 = umma_idesc_f16(128, PE_TP, false, false, fmt, fmt);
+                TmemOp a;
+                SmemOp xb;
+                // B operands: 128 B between k-chunks, 4096 / 2048 B between 8-point groups
+                a.hi = tmem0 + PE_W1H; a.lo = tmem0 + PE_W1L;
+                xb.hi = smem_u32(sX1); xb.lo = xb.hi + 2048 * 16; xb.lbo = 128; xb.sbo = 4096;
+                umma_gemm3_ts(tmem0 + PE_ACC1, a, xb, id64, 256, false);
+                a.hi = tmem0 + PE_W2H; a.lo = tmem0 + PE_W2L;
+                xb.hi = smem_u32(sX2); xb.lo = xb.hi + 1024 * 16; xb.lbo = 128; xb.sbo = 2048;
+                umma_gemm3_ts(tmem0 + PE_ACC2, a, xb, id64, 128, false);
                 umma_commit(&mma_bar);
             }
             __syncwarp();
         }
-        w_ready = true;
-        // ---- while the MMAs run: next tile's point inputs, and the softmax numerators p = exp(w - max) (bf16-rounded, as the MMA
-        //      will see them) with their per-joint sums
+        // ---- while the MMAs run: next tile's point inputs, and the softmax numerators p = exp(w - max) with their per-joint sums
+        const int my_n = sN[tile_par * PE_TP + (tid >> 3)];   // copy-out below: thread = (point tid / 8, 8 chunk lanes)
         if (tile + (int)gridDim.x < p.B * T) fetch_point(tile + gridDim.x, tile_par ^ 1);
         float* ms = p.part_ms + ((size_t)b * T + t) * 64;
-        float pj[8];   // joints [8 sub, 8 sub + 8) of this point
+        if (grp == 0) {
+            float pj[8];   // joints [8 sub, 8 sub + 8) of this point
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int j = 8 * sub + k;
-            pj[k] = j < J ? __bfloat162float(__float2bfloat16_rn(__expf(wraw[k] - sRed[j]))) : 0.f;
-            if (j < J) sT[j * 129 + r] = pj[k];
+            for (int k = 0; k < 8; ++k) {
+                const int j = 8 * sub + k;
+                pj[k] = j < J ? __expf(wraw[k] - sRed[j]) : 0.f;
+                if (j < J) sT[j * 65 + r] = pj[k];
+            }
+            uint4 oh, ol;
+            split8(fmt, pj, oh, ol);
+            sP[(r >> 3) * 32 + sub * 8 + (r & 7)] = oh;
+            sP[256 + (r >> 3) * 32 + sub * 8 + (r & 7)] = ol;
         }
         if (tid < 32) ms[tid] = sRed[tid];
         __syncthreads();
@@ -312,54 +380,74 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
             float sm_ = 0.f;
             if (rj < J) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sm_ += sT[rj * 129 + rs + 16 * i];
+                for (int i = 0; i < 4; ++i) sm_ += sT[rj * 65 + rs + 16 * i];
             }
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) sm_ += __shfl_xor_sync(0xffffffffu, sm_, o);
-            if (rs == 0 && rj < 32) ms[32 + rj] = rj < J ? sm_ : 0.f;
+            if (rs == 0) ms[32 + rj] = rj < J ? sm_ : 0.f;
         }
         stamp();
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
         stamp();
-        // ---- epilogue: e = relu(relu(acc1 + b1) + acc2 + b2) -> global (bf16) and MN-major A operand (sA2 region)
+        // ---- epilogue: e = relu(relu(acc1 + b1) + acc2 + b2) for channel ch, points [16cg, 16cg + 16)
+        uint32_t eh[8], el[8];
         {
-            __nv_bfloat16* eo = p.e_out + (size_t)b * p.e_bs + (size_t)sN[tile_par * 128 + row] * 128 + 32 * cg;
-            float a[32], rr[32];
-            tmem_ld_nw<32>(tmem + ACC1 + 32 * cg, a);
-            tmem_ld_nw<32>(tmem + ACC2 + 32 * cg, rr);
+            float a[16], rr[16];
+            tmem_ld_nw<16>(tmem + PE_ACC1 + 16 * cg, a);
+            tmem_ld_nw<16>(tmem + PE_ACC2 + 16 * cg, rr);
             tmem_wait_ld();
+            const float b1 = sB[ch], b2 = sB[128 + ch];
+            uint16_t* se = reinterpret_cast<uint16_t*>(sE) + ch;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = fmaxf(fmaxf(a[i] + sB[32 * cg + i], 0.f) + rr[i] + sB[128 + 32 * cg + i], 0.f);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint4 v = pack8_bf16(a + 8 * c);
-                *reinterpret_cast<uint4*>(eo + 8 * c) = v;
-                sA2[(row >> 3) * 128 + (4 * cg + c) * 8 + (row & 7)] = v;  // e^T: M = channel contiguous
+            for (int i = 0; i < 8; ++i) {
+                const float e0 = fmaxf(fmaxf(a[2 * i] + b1, 0.f) + rr[2 * i] + b2, 0.f);
+                const float e1 = fmaxf(fmaxf(a[2 * i + 1] + b1, 0.f) + rr[2 * i + 1] + b2, 0.f);
+                split2(fmt, e0, e1, eh[i], el[i]);
+                // staged rows [point][hi 128 | lo 128]: a warp's 32 channels are 64 contiguous bytes of each
+                se[(16 * cg + 2 * i) * 256] = (uint16_t)eh[i];
+                se[(16 * cg + 2 * i) * 256 + 128] = (uint16_t)el[i];
+                se[(16 * cg + 2 * i + 1) * 256] = (uint16_t)(eh[i] >> 16);
+                se[(16 * cg + 2 * i + 1) * 256 + 128] = (uint16_t)(el[i] >> 16);
             }
         }
-        // p as MN-major B operand [K = 128 points][N = 32 joints] over the (dead) head of sA1
-        sA1[(r >> 3) * 32 + sub * 8 + (r & 7)] = pack8_bf16(pj);
+        tc_fence_before();
+        __syncthreads();   // every warp has read its accumulator columns: they are reused for e^T and the aggregation
+        tc_fence_after();
+        // e^T as the aggregation's A operand in tensor memory: lane = channel, K = the tile's 64 points, 16-bit pairs
+        tmem_st_nw<8>(tmem + PE_EH + 8 * cg, reinterpret_cast<const float*>(eh));
+        tmem_st_nw<8>(tmem + PE_EL + 8 * cg, reinterpret_cast<const float*>(el));
+        tmem_wait_st();
         stamp();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         if (warp_u == 0) {
             tc_fence_after();
-            if (elect_one()) {
-                umma_gemm(tmem0 + ACC3, smem_u32(sA2), 2048, 128, smem_u32(sA1), 512, 128, umma_idesc_bf16(128, 32, true, true), 128, false);
+            if (elect_one()) {   // D[c][j] = sum_n e[n][c] p[n][j]
+                TmemOp a;
+                a.hi = tmem0 + PE_EH; a.lo = tmem0 + PE_EL;
+                SmemOp pb;
+                pb.hi = smem_u32(sP); pb.lo = pb.hi + 256 * 16; pb.lbo = 512; pb.sbo = 128;
+                umma_gemm3_ts(tmem0 + PE_ACC3, a, pb, umma_idesc_f16(128, 32, false, true, fmt, fmt), PE_TP, false);
                 umma_commit(&mma_bar);
             }
             __syncwarp();
         }
+        {   // copy-out of the staged e rows while the aggregation runs: 8 lanes write 128 contiguous bytes of a 512-byte row
+            uint4* dst = reinterpret_cast<uint4*>(p.e_out + (size_t)b * p.e_bs + (size_t)my_n * 256);
+            const uint4* src = sE + (tid >> 3) * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[(tid & 7) + 8 * k] = src[(tid & 7) + 8 * k];
+        }
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
-        {   // D[channel = row][joints 8cg .. 8cg + 8)
+        {   // D[channel = ch][joints 8cg .. 8cg + 8)
             float a[8];
-            tmem_ld<8>(tmem + ACC3 + 8 * cg, a);
-            float4* o = reinterpret_cast<float4*>(p.part_acc + (((size_t)b * T + t) * 128 + row) * 32 + 8 * cg);
+            tmem_ld<8>(tmem + PE_ACC3 + 8 * cg, a);
+            float4* o = reinterpret_cast<float4*>(p.part_acc + (((size_t)b * T + t) * 128 + ch) * 32 + 8 * cg);
             o[0] = make_float4(a[0], a[1], a[2], a[3]);
             o[1] = make_float4(a[4], a[5], a[6], a[7]);
         }
@@ -371,7 +459,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
     if (warp == 0) tmem_dealloc(tmem0, 512);
 }
 
-constexpr size_t PE_SMEM = (size_t)(3 * 2048 + 4096 + 2048) * 16 + (128 + 128 + 256 + 21 * 129 + 3 + 256) * 4;
+constexpr size_t PE_SMEM = (size_t)(2 * 2048 + 2 * 1024 + 2 * 256 + 2048) * 16 + (128 + 32 + 256 + 21 * 65 + 3 + 128) * 4;
 
 }  // namespace kpf
 

@@ -342,12 +342,41 @@ def ball_query(xyz, centers, radius, nsample):
     return idx
 
 
-# ------------------------------------------------------------------------------------------------ tensor-core token stacks
-def _canon(W):
-    """[N,K] -> bf16 SWIZZLE_NONE canonical K-major operand [K/8][N][8] (csrc/umma.cuh), flattened."""
-    N, K = W.shape
+# ------------------------------------------------------------------------------------------------ split-precision operands
+# fp32 weights / activations reach the tensor cores as two 16-bit planes (hi = rn16(x), lo = rn16(x - hi)), three MMAs per product
+# (csrc/umma_split.cuh).  fp16 planes carry 22 mantissa bits (results indistinguishable from an fp32 GEMM), bf16 planes 16 bits
+# with the full fp32 exponent range.  KPF_SPLIT_FMT=bf16 selects the latter, e.g. for a checkpoint with |w| or |activation| > 65504.
+FMT_F16, FMT_BF16 = 0, 1
+SPLIT_FMT = FMT_BF16 if os.environ.get("KPF_SPLIT_FMT", "fp16").lower() in ("bf16", "1") else FMT_F16
+
+
+def _fmt_dtype(fmt):
+    return torch.float16 if fmt == FMT_F16 else torch.bfloat16
+
+
+def split_planes(W, fmt=None):
+    """fp32 tensor -> (hi, lo) 16-bit planes with hi + lo == W to ~2^-22 (fp16) / 2^-16 (bf16) relative."""
+    fmt = SPLIT_FMT if fmt is None else fmt
+    dt = _fmt_dtype(fmt)
+    W = W.detach().float()
+    if fmt == FMT_F16 and W.numel() and float(W.abs().max()) > 6.0e4:
+        raise ValueError("weight magnitude exceeds the fp16 plane range; set KPF_SPLIT_FMT=bf16")
+    hi = W.to(dt)
+    lo = (W - hi.float()).to(dt)
+    return hi, lo
+
+
+def _canon16(W16):
+    """[N,K] 16-bit -> SWIZZLE_NONE canonical K-major operand [K/8][N][8] (csrc/umma.cuh), flattened, as raw int16 bits."""
+    N, K = W16.shape
     assert K % 8 == 0
-    return W.detach().to(torch.bfloat16).reshape(N, K // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+    return W16.reshape(N, K // 8, 8).permute(1, 0, 2).contiguous().reshape(-1).view(torch.int16)
+
+
+def _canon(W, fmt=None):
+    """[N,K] fp32 -> canonical hi plane followed by canonical lo plane (int16 bits)."""
+    hi, lo = split_planes(W, fmt)
+    return torch.cat([_canon16(hi), _canon16(lo)])
 
 
 def _pad(v, n):
@@ -355,12 +384,13 @@ def _pad(v, n):
     return torch.cat([v, v.new_zeros(n - v.numel())]) if v.numel() < n else v
 
 
+# ------------------------------------------------------------------------------------------------ tensor-core token stacks
 class TokenProgram:
     """Packed weights of one kpf_token_stack launch: optional cross layer, optional DESA-fusion prologue, optional encoder."""
 
-    def __init__(self, wmat, wseq, wvec, cross, pre, D, L, F, Fc, J):
+    def __init__(self, wmat, wseq, wvec, cross, pre, D, L, F, Fc, J, fmt):
         self.wmat, self.wseq, self.wvec = wmat, wseq, wvec
-        self.cross, self.pre, self.D, self.L, self.F, self.Fc, self.J = cross, pre, D, L, F, Fc, J
+        self.cross, self.pre, self.D, self.L, self.F, self.Fc, self.J, self.fmt = cross, pre, D, L, F, Fc, J, fmt
         self.n_weights = wseq.shape[0]
 
     def to(self, device):
@@ -368,48 +398,61 @@ class TokenProgram:
         return self
 
 
-def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
+def pack_token_program(J, enc=None, cross=None, fusion=None, C=128, fmt=None):
     """enc = (state_dict, prefix) of a KP_Interaction_TR; cross = (state_dict, prefix) of one TransformerDecoderLayer;
     fusion = (W [128,512], b [128]) BN-folded DESA fusion conv.  Weight order = consumption order of csrc/token_stack.cu.
 
-    wseq row g = (source offset, count, destination offset inside the three 32 KB shared-memory slots) in 16-byte units and
-    the index of the GEMM whose completion frees that destination (-1: free from the start)."""
-    SLOT = 2048
+    wmat is a sequence of ring entries (<= 32 KB each): a [128,128] matrix is two half-K tiles, each = canonical hi plane
+    [8][128] + canonical lo plane; a 16-wide FFN is one entry (W1 hi | W1 lo | W2 hi | W2 lo); the embedding's K tail one entry.
+    wseq row e = (source offset, count) in 16-byte units, the layer whose per-layer vectors the producer loads in front of
+    entry e (-1: none), 0."""
+    fmt = SPLIT_FMT if fmt is None else fmt
     mats, seq, vecs, off = [], [], [], 0
-    last_user = [-1, -1, -1]
 
-    def add(m, slots=None):
+    def add(m):
         nonlocal off
         n = m.numel() // 8
-        if slots is not None:
-            assert n <= SLOT * len(slots)
-            g_ = len(seq)
-            seq.append((off, n, slots[0] * SLOT, max(last_user[s_] for s_ in slots)))
-            for s_ in slots:
-                last_user[s_] = g_
+        assert n <= 2048 and m.numel() % 8 == 0
+        seq.append([off, n, -1, 0])
         mats.append(m)
         off += n
 
+    def add_mat(W):   # [128,128] (as A operand) or [N=128,K=128] (as B operand): two half-K tiles
+        assert tuple(W.shape) == (C, C), W.shape
+        for h in range(2):
+            add(_canon(W[:, 64 * h:64 * (h + 1)], fmt))
+
+    def add_ffn(W1, W2):
+        Fh = W1.shape[0]
+        if Fh == 16:
+            add(torch.cat([_canon(W1, fmt), _canon(W2, fmt)]))     # [16,128] K-major B operand ; [128,16] K-major A operand
+        elif Fh == C:
+            add_mat(W1)
+            add_mat(W2)
+        else:
+            raise NotImplementedError(f"FFN width {Fh}: the token-stack kernel covers 16 (BERT intermediate) and 128 (decoder layer)")
+        return Fh
+
+    layer_base = []
+
     def add_layer(Wq, Wk, Wv, Wo, W1, W2):
-        add(_canon(Wq), (0,))
-        add(_canon(torch.cat([Wk, Wv], 0)), (1, 2))     # one N = 256 tile
-        add(_canon(Wo), (0,))
-        add(_canon(W1), (1,))
-        add(_canon(W2), (2,))
+        layer_base.append(len(seq))
+        for W in (Wq, Wk, Wv, Wo):
+            add_mat(W)
+        return add_ffn(W1, W2)
     Fc = D = L = F_ = 0
     if cross is not None:
         sd, pf = cross
         g = lambda k: sd[pf + k].detach().float()
         Wi, bi = g("multihead_attn.in_proj_weight"), g("multihead_attn.in_proj_bias")
-        Fc = g("linear1.weight").shape[0]
-        add_layer(Wi[:C], Wi[C:2 * C], Wi[2 * C:], g("multihead_attn.out_proj.weight"), g("linear1.weight"), g("linear2.weight"))
+        Fc = add_layer(Wi[:C], Wi[C:2 * C], Wi[2 * C:], g("multihead_attn.out_proj.weight"), g("linear1.weight"), g("linear2.weight"))
         vecs += [g("self_posembed.weight")[:J].reshape(-1), g("cross_posembed.weight")[:J].reshape(-1), bi[:C], bi[C:2 * C], bi[2 * C:],
                  g("multihead_attn.out_proj.bias"), g("norm2.weight"), g("norm2.bias"), _pad(g("linear1.bias"), C), g("linear2.bias"),
                  g("norm3.weight"), g("norm3.bias")]
     if fusion is not None:
         Wfu, bfu = fusion
         for s_ in range(4):
-            add(_canon(Wfu.detach().float()[:, C * s_:C * (s_ + 1)]), (s_ % 3,))
+            add_mat(Wfu.detach().float()[:, C * s_:C * (s_ + 1)])
         vecs.append(bfu.detach().float())
     if enc is not None:
         sd, pf = enc
@@ -417,11 +460,11 @@ def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
         Wemb = g("bert.img_embedding.weight")
         D = Wemb.shape[1]
         shift = D - C
-        add(_canon(Wemb[:, shift:]), (1,))
+        add_mat(Wemb[:, shift:])
         if shift > 0:
             T = Wemb.new_zeros(C, 16)
             T[:, :shift] = Wemb[:, :shift]
-            add(_canon(T))   # K-tail sits right behind the main part, outside the sequence
+            add(_canon(T, fmt))   # K tail: [2][128] hi | lo
         Wres = g("residual.weight")                       # [3, D] -> 16-byte aligned rows: [3][16] lead (zero padded) | [3][128] features
         lead = Wres.new_zeros(3, 16)
         lead[:, :shift] = Wres[:, :shift]
@@ -429,16 +472,22 @@ def pack_token_program(J, enc=None, cross=None, fusion=None, C=128):
                  Wres[:, shift:].reshape(-1), _pad(g("residual.bias"), 4), g("cls_head.weight").reshape(-1), _pad(g("cls_head.bias"), 4)]
         while f"{pf}bert.encoder.layer.{L}.attention.self.query.weight" in sd:
             lp = f"bert.encoder.layer.{L}."
-            F_ = g(lp + "intermediate.dense.weight").shape[0]
-            add_layer(*(g(lp + k_ + ".weight") for k_ in ("attention.self.query", "attention.self.key", "attention.self.value",
-                                                          "attention.output.dense", "intermediate.dense", "output.dense")))
+            F_ = add_layer(*(g(lp + k_ + ".weight") for k_ in ("attention.self.query", "attention.self.key", "attention.self.value",
+                                                               "attention.output.dense", "intermediate.dense", "output.dense")))
             vecs += [g(lp + "attention.self.query.bias"), g(lp + "attention.self.key.bias"), g(lp + "attention.self.value.bias"),
                      g(lp + "attention.output.dense.bias"), g(lp + "attention.output.LayerNorm.weight"),
                      g(lp + "attention.output.LayerNorm.bias"), _pad(g(lp + "intermediate.dense.bias"), C), g(lp + "output.dense.bias"),
                      g(lp + "output.LayerNorm.weight"), g(lp + "output.LayerNorm.bias")]
             L += 1
+    # vector prefetch schedule: layer 0's vectors in front of the first entry, layer it+1's in front of layer it's V weights
+    # (by then the ring guarantees layer it-1 has finished, so the buffer they overwrite is free: csrc/token_stack.cu)
+    if layer_base:
+        seq[0][2] = 0
+        for it, base in enumerate(layer_base[:-1]):
+            seq[base + 4][2] = it + 1
     return TokenProgram(torch.cat(mats).contiguous(), torch.tensor(seq, dtype=torch.int32).contiguous(),
-                        torch.cat([v.reshape(-1) for v in vecs]).contiguous(), int(cross is not None), int(fusion is not None), D, L, F_, Fc, J)
+                        torch.cat([v.reshape(-1) for v in vecs]).contiguous(), int(cross is not None), int(fusion is not None), D, L, F_, Fc, J,
+                        fmt)
 
 
 def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=True, out_jc=None, out_jc_c0=0, want_cj=False, dbg=None):
@@ -457,7 +506,7 @@ def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=Tr
     out_cj = torch.empty(B, 128, J, device=dev, dtype=torch.float32) if (want_cj and pk.L == 0) else None
     stride = out_jc.shape[-1] if out_jc is not None else 0
     _call("kpf_token_stack", _p(x), _p(y), _p(r3d), _p(desa), _p(jf), _p(pk.wmat), _p(pk.wseq), _p(pk.wvec), pk.n_weights, pk.cross, pk.pre,
-          B, J, pk.D, pk.L, pk.F, pk.Fc, _p(tokens), _p(pred), _p(out_cj), _p(out_jc), stride, out_jc_c0, _p(dbg))
+          B, J, pk.D, pk.L, pk.F, pk.Fc, pk.fmt, _p(tokens), _p(pred), _p(out_cj), _p(out_jc), stride, out_jc_c0, _p(dbg))
     return tokens, pred, out_cj
 
 

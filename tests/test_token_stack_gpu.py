@@ -1,6 +1,7 @@
-"""GPU: tensor-core token stacks (csrc/token_stack.cu) vs the fp32 oracle.  bf16 operands -> north_star's 1e-2 relative
-bar, taken as the RMS relative error ||a-b||/||b|| after FOUR stacked transformer layers (individual entries pass through
-zero, so an entry-wise relative bound is meaningless); the worst entry is additionally held to 3e-2 of max|ref|."""
+"""GPU: tensor-core token stacks (csrc/token_stack.cu) vs the fp32 oracle.  Split-precision operands (two 16-bit planes, three
+MMAs per product) -> fp32-class results: north_star's 1e-3 fp32 bar with two orders of margin.  RMS relative error
+||a-b||/||b|| after FOUR stacked transformer layers <= TOL (individual entries pass through zero, so an entry-wise relative
+bound is meaningless); the worst entry is additionally held to WORST of max|ref|."""
 import numpy as np
 import pytest
 import torch
@@ -12,11 +13,21 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def rel_err(a, b, worst_bound=3e-2):
+def _tol():
+    from keypointfusion_b200 import ops
+    return (2e-5, 1e-4) if ops.SPLIT_FMT == ops.FMT_F16 else (3e-4, 1.5e-3)   # fp16 planes: 22 bits ; bf16 planes: 16 bits
+
+
+def rel_err(a, b, what=""):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     worst = float((a - b).abs().max() / b.abs().max())
-    assert worst < worst_bound, worst
-    return float((a - b).norm() / b.norm())
+    rms = float((a - b).norm() / b.norm())
+    print(f"[token stack] {what}: rms rel {rms:.2e}, worst entry {worst:.2e} of max|ref|")
+    assert worst < _tol()[1], worst
+    return rms
+
+
+TOL = _tol()[0]
 
 
 @pytest.mark.parametrize("which,D", [("init_TR", 128), ("final_TR", 131)])
@@ -32,8 +43,8 @@ def test_token_encoder(path_params, which, D, B):
         x[:, :, :3] *= 0.3
     tok, pred, _ = ops.token_stack(pk, x=x.to(DEV))
     rtok, rpred = O.kp_interaction_tr(path_params, prefix, x)
-    assert rel_err(tok, rtok) < 1e-2
-    assert rel_err(pred, rpred) < 1e-2
+    assert rel_err(tok, rtok) < TOL
+    assert rel_err(pred, rpred) < TOL
 
 
 @pytest.mark.parametrize("B", [2, 13])
@@ -50,10 +61,10 @@ def test_token_cross(golden, golden_meta, B):
     jc = torch.zeros(B, 21, 131, device=DEV)
     out = ops.token_stack(pk, x=a.to(DEV), y=k.to(DEV), out_jc=jc, out_jc_c0=3, want_cj=True)[2]
     ref = O.updated_decoder(sd, "", a, k)
-    assert rel_err(out, ref) < 1e-2
+    assert rel_err(out, ref) < TOL
     assert torch.equal(jc[:, :, 3:], out.permute(0, 2, 1)) and not jc[:, :, :3].any()
     if B == 2:
-        assert rel_err(out, torch.from_numpy(golden["a13_out"])) < 1e-2
+        assert rel_err(out, torch.from_numpy(golden["a13_out"])) < TOL
 
 
 @pytest.mark.parametrize("B", [3, 9])
@@ -71,7 +82,7 @@ def test_fused_programs(path_params, B):
     tok, pred, _ = ops.token_stack(pk, desa=part.to(DEV), jf=jf.to(DEV))
     x = torch.relu(torch.nn.functional.linear(torch.cat([part.permute(0, 2, 1, 3).reshape(B, 21, -1), jf], -1), Wfu, bfu))
     rtok, rpred = O.kp_interaction_tr(p, "block1.init_TR.", x)
-    assert rel_err(tok, rtok) < 1e-2 and rel_err(pred, rpred) < 1e-2
+    assert rel_err(tok, rtok) < TOL and rel_err(pred, rpred) < TOL
     # crossTR + final_TR
     a = torch.from_numpy(rs.standard_normal((B, 21, 128)).astype(np.float32))
     r3d = torch.from_numpy(rs.uniform(-0.5, 0.5, (B, 21, 3)).astype(np.float32))
@@ -79,4 +90,4 @@ def test_fused_programs(path_params, B):
     tok2, pred2, _ = ops.token_stack(pk2, x=a.to(DEV), y=rtok.to(DEV), r3d=r3d.to(DEV))
     rc = O.updated_decoder(p, "block1.crossTR.", a, rtok).permute(0, 2, 1)
     rtok2, rpred2 = O.kp_interaction_tr(p, "block1.final_TR.", torch.cat([r3d, rc], 2))
-    assert rel_err(tok2, rtok2) < 1e-2 and rel_err(pred2, rpred2) < 1e-2
+    assert rel_err(tok2, rtok2) < TOL and rel_err(pred2, rpred2) < TOL
