@@ -161,40 +161,53 @@ int kpf_token_stack(const float* x, const float* y, const float* r3d, const floa
 
 /* ---- a7-a9 fused point stage (csrc/point_embed.cu), model/model.py:295-320 ------------------------------------------
  * kpf_repack_features: f_d, f_rgb [B,128,HW], f_w [B,J,HW] (batch stride w_batch_stride elements; = img_offset[:,4J:])
- *   -> out [B,HW,288] bf16 channels-last rows (128 | 128 | J zero-padded to 32).
- * kpf_point_embed: featT from above; idx [B,N,4] i32 / clos [B,N,4] f32 from kpf_img2pcl_index (K = 4); pcl [B,N,3];
- *   joint [B,J,3] (J <= 21); order NULL or [B,N] i32 (kpf_spatial_order: tile t = points order[128t .. 128t+128));
- *   wmat/wvec from ops.pack_point_embed -> e_out [B,N,128] bf16 (point features after the four
- *   folded Conv1d+BN embeddings and both relus), part_acc [B,N/128,128,32] f32 and part_ms [B,N/128,2,32] f32: per
- *   128-point tile the softmax-aggregation numerators sum_n e[n][c]*exp(w[n][j]-max_tile) and (max_tile, sum_tile). */
+ *   -> out [B,HW,288] bf16 channels-last rows (128 | 128 | J zero-padded to 32).  bf16 maps are exact in that one plane
+ *   (out_lo = NULL); fp32 maps (dtype KPF_F32) are carried as two bf16 planes, out = rn(x) and out_lo = rn(x - out).
+ * kpf_point_embed: feat_hi / feat_lo (NULL for bf16 maps) from above; idx [B,N,4] i32 / clos [B,N,4] f32 from kpf_img2pcl_index
+ *   (K = 4); pcl [B,N,3]; joint [B,J,3] (J <= 21); order NULL or [B,N] i32 (kpf_spatial_order: tile t = points
+ *   order[64t .. 64t+64)); wmat/wvec from ops.pack_point_embed -> e_out [B,N,256] 16-bit: per point the features after the four
+ *   folded Conv1d+BN embeddings and both relus as a row [hi 128 | lo 128] of two planes in format fmt (0 = fp16, 1 = bf16);
+ *   part_acc [B,N/64,128,32] f32 and part_ms [B,N/64,2,32] f32: per 64-point tile the softmax-aggregation numerators
+ *   sum_n e[n][c]*exp(w[n][j]-max_tile) and (max_tile, sum_tile).  N % 64 == 0.  Split-precision tensor-core GEMMs
+ *   (csrc/umma_split.cuh), weights resident in tensor memory: fp32-class results. */
 int kpf_repack_features(const void* f_d, const void* f_rgb, const void* f_w, long long w_batch_stride, int dtype, int B, int C, int J,
-                        int HW, void* out, cudaStream_t stream);
-int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
-                    const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out,
-                    long long e_batch_stride /* elements between samples of e_out, >= N*128; (N+J)*128 or more when kpf_desa_fused follows */,
+                        int HW, void* out, void* out_lo, cudaStream_t stream);
+int kpf_point_embed(const void* feat_hi, const void* feat_lo, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
+                    const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, int fmt,
+                    void* e_out,
+                    long long e_batch_stride /* 16-bit elements between samples of e_out, >= N*256; (N+J)*256 or more when kpf_desa_fused follows */,
                     float* part_acc, float* part_ms, int num_sms, long long* dbg, cudaStream_t stream);
 
 /* ---- 8f-1 DESA on tensor cores (csrc/desa_fused.cu), model/model.py:129-204 + joint embeddings :323-325 ---------------
  * e / part_acc / part_ms: outputs of kpf_point_embed; pcl [B,N,3]; joint [B,J,3]; S scales with radii r0..r3 and
  * `nsample` grouped points each; wmat/wvec from ops.pack_desa.  -> desa_part [B,S,J,128] f32 (per-scale max-pooled MLP
  * outputs) and jf_out [B,J,128] f32 (embedded joint features); the 512->128 fusion conv consumes [desa_part | jf].
- * e is [B][>= N+J][128] bf16 with batch stride e_batch_stride: rows < N from kpf_point_embed; the prep launch WRITES the J joint
- * feature rows behind them (the joints are members N..N+J-1 of the grouped point set, model.py:168-169).
- * Two launches (prep: joint embedding, its W1 products, ball query; persistent tile kernel on `num_sms` CTAs) that hand over
- * through `scratch`: caller workspace of B*S*J*128*4 + B*(N+32)*16 + B*S*J*nsample*2 bytes, 16-byte aligned, contents undefined. */
+ * e is [B][>= N+J][256] 16-bit rows [hi | lo] (format fmt) with batch stride e_batch_stride: rows < N from kpf_point_embed; the prep
+ * launch WRITES the J joint feature rows behind them (the joints are members N..N+J-1 of the grouped point set, model.py:168-169).
+ * Two launches (prep: joint embedding, its W1 products, ball query; persistent tile kernel on `num_sms` CTAs, W1 / W2 planes in
+ * tensor memory) that hand over through `scratch`: caller workspace of B*S*J*128*4 + B*(N+32)*16 + B*S*J*nsample*2 bytes,
+ * 16-byte aligned, contents undefined.  Split-precision GEMMs: fp32-class results. */
 int kpf_desa_fused(void* e, long long e_batch_stride, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
                    const void* wmat, const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2, float r3,
+                   int fmt, const float* jf_in /* NULL, or [B,J,128]: joint features given (stand-alone DESA.forward, model.py:166); the
+                   joint embedding is skipped and part_acc / part_ms may be NULL */,
                    float* desa_part, float* jf_out, void* scratch, int num_sms, long long* dbg, cudaStream_t stream);
 
-/* ---- a12 on tensor cores (csrc/spatial_agg_tc.cu): same contract as kpf_spatial_aggregate for bf16 feat_rgb [B,128,fs,fs]
- * with fs*fs % 128 == 0; wa_packed from ops.pack_spatial_wa (atten_spatial.weight in canonical bf16 operand layout).
+/* ---- a12 on tensor cores (csrc/spatial_agg_tc.cu): same contract as kpf_spatial_aggregate for feat_rgb [B,128,fs,fs] with
+ * fs*fs % 128 == 0, given as bf16 (feat_rgb_lo = NULL: exact in one plane) or as the two bf16 planes of an fp32 map
+ * (kpf_split_planes); wa_packed from ops.pack_spatial_wa (atten_spatial.weight as canonical 16-bit planes, format fmt).
+ * Split-precision GEMMs (csrc/umma_split.cuh; fmt 0 = fp16 planes, 1 = bf16 planes for the computed operands): fp32-class results.
  * split > 1: each sample's cell tiles are spread over `split` CTAs; caller workspace scratch [B,split,128,32] f32 and
  * counters [B] i32 (ZERO on entry; the kernel leaves them zero again), reduction order fixed (deterministic). */
-int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joints, const float* depth, long long depth_bs, int depth_rs, int depth_cs,
-                             const float* center, const float* M, const float* cube, const float* cam, const void* wa_packed,
-                             const float* ba, const float* weight_dis, const float* fc_w, const float* fc_b, const float* prev, int B, int C,
-                             int J, int fs, float img_size, float flip, float hm_std, float hm_sigma, float gamma, float* sw_out,
-                             float* feat_j_out, float* scratch, int* counters, int split, long long* dbg, cudaStream_t stream);
+int kpf_spatial_aggregate_tc(const void* feat_rgb, const void* feat_rgb_lo, const float* joints, const float* depth, long long depth_bs,
+                             int depth_rs, int depth_cs, const float* center, const float* M, const float* cube, const float* cam,
+                             const void* wa_packed, const float* ba, const float* weight_dis, const float* fc_w, const float* fc_b,
+                             const float* prev, int B, int C, int J, int fs, float img_size, float flip, float hm_std, float hm_sigma,
+                             float gamma, int fmt, float* sw_out, float* feat_j_out, float* scratch, int* counters, int split,
+                             long long* dbg, cudaStream_t stream);
+
+/* x [n] f32 -> hi [n] bf16 = rn(x), lo [n] bf16 = rn(x - hi): how an fp32 feature map enters the split-precision kernels. n % 4 == 0. */
+int kpf_split_planes(const float* x, long long n, void* hi, void* lo, cudaStream_t stream);
 
 /* ---- 8f-3 crop + normalise front end for in-the-wild frames (demo_RGBD.py:253-276, :378-385, :410-569) ------------------
  * depth_u16 [B,Hf,Wf] uint16 (mm), rgb_u8 [B,Hf,Wf,3] uint8 (BGR as cv2 reads it); bbox [B,4] f64 (x,y,w,h);

@@ -59,6 +59,11 @@ def check(rc, name):
     if rc != 0:
         if rc < 0:
             raise RuntimeError(f"{name}: {ERRORS.get(rc, rc)}")
-        import torch
-        msg = ctypes.c_char_p(torch.cuda.cudart().cudaGetErrorString(rc)) if False else None
+        try:   # positive codes are cudaError_t values
+            rt = ctypes.CDLL("libcudart.so")
+            rt.cudaGetErrorString.restype = ctypes.c_char_p
+            msg = rt.cudaGetErrorString(ctypes.c_int(rc)).decode()
+        except OSError:
+            import torch
+            msg = torch.cuda.cudart().cudaGetErrorString(torch.cuda.cudart().cudaError(rc)) if hasattr(torch.cuda.cudart(), "cudaError") else ""
         raise RuntimeError(f"{name}: CUDA error {rc}" + (f" ({msg})" if msg else ""))

@@ -37,6 +37,7 @@ struct DesaParams {
     const float* wvec;        // bj[128], Wjx[128][4] ; per scale: b1[128], b2[128]
     float* desa_part;         // [B,S,J,128]
     float* jf_out;            // [B,J,128]
+    const float* jf_in;       // null, or [B,J,128]: the joints' features are GIVEN (stand-alone DESA.forward); the embedding is skipped
     float* cj;                // scratch [B,S,J,128]: W1_s jf[j] (fp32), subtracted in the tile kernel's layer-1 epilogue
     float4* xyz4;             // scratch [B][N + 32]: xyz of the grouped point set (N points, then the J joints), one 16-byte load each
     uint16_t* idx;            // scratch [B,S,J,nsample] ball-query indices (>= N: one of the joints)
@@ -163,13 +164,16 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         const float* s = p.joint + ((size_t)b * J + (tid < J ? tid : 0)) * 3;
         sJ[tid] = tid < J ? make_float4(s[0], s[1], s[2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int i = tid; i < T * 64; i += DS_NT) sMS[i] = p.part_ms[(size_t)b * T * 64 + i];
+    const bool given = p.jf_in != nullptr;
+    if (!given)
+        for (int i = tid; i < T * 64; i += DS_NT) sMS[i] = p.part_ms[(size_t)b * T * 64 + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem0 = tmem_slot;
+    uint32_t mph = 0;   // mma_bar phase
     // scale factors exp(m_t - m) and the softmax denominator, per joint
-    if (tid < 32) {
+    if (!given && tid < 32) {
         float m = -INFINITY;
         for (int t = 0; t < T; ++t) m = fmaxf(m, sMS[t * 64 + tid]);
         float den = 0.f;
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
     stamp();
     // ---- joint_agg[c][j] (softmax over all N points of the gathered weight map): 8 lanes read one channel's 128-byte row of
     //      a partial per load (4 L1 wavefronts per warp load); thread = (channel, 4 joints), two channel halves
-    {
+    if (!given) {
         const int jq = lane & 7;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -214,21 +218,26 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
     __syncthreads();
     if (warp_u == 0) {
         tc_fence_after();
-        mbar_wait(&wbar, 0);
-        if (elect_one()) {
-            umma_gemm3_ss(tmem0, opW, opA, id_jf, 128, false);
-            umma_commit(&mma_bar);
+        mbar_wait(&wbar, 0);   // (also when the embedding is skipped: the buffer is refilled below)
+        if (!given) {
+            if (elect_one()) {
+                umma_gemm3_ss(tmem0, opW, opA, id_jf, 128, false);
+                umma_commit(&mma_bar);
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     stamp();
-    mbar_wait(&mma_bar, 0);
-    tc_fence_after();
+    if (!given) {
+        mbar_wait(&mma_bar, mph);
+        mph ^= 1;
+        tc_fence_after();
+    }
     const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;   // channel 32q + lane, joints [8cg, 8cg + 8)
     const uint32_t tmem_q = tmem0 + ((uint32_t)(32 * q) << 16);
     {   // jf[j][ch]
         float d[8];
-        tmem_ld<8>(tmem_q + 8 * cg, d);
+        if (!given) tmem_ld<8>(tmem_q + 8 * cg, d);
         const float bj = p.wvec[ch];
         const float4 wx = *reinterpret_cast<const float4*>(p.wvec + 128 + 4 * ch);
         uint16_t* erow = p.e + (size_t)b * p.e_bs + (size_t)N * 256 + ch;
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
             float v = 0.f;
             if (j < J) {
                 const float4 c = sJ[j];
-                v = fmaxf(d[i] + bj + wx.x * c.x + wx.y * c.y + wx.z * c.z, 0.f);
+                v = given ? __ldg(p.jf_in + ((size_t)b * J + j) * 128 + ch) : fmaxf(d[i] + bj + wx.x * c.x + wx.y * c.y + wx.z * c.z, 0.f);
                 if (p.jf_out) p.jf_out[((size_t)b * J + j) * 128 + ch] = v;
                 uint32_t h2, l2;   // the joints are points N .. N+J-1 of the grouped set (model.py:168-169)
                 split2(fmt, v, 0.f, h2, l2);
@@ -274,7 +283,8 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
             }
             __syncwarp();
         }
-        mbar_wait(&mma_bar, (sc + 1) & 1);
+        mbar_wait(&mma_bar, mph);
+        mph ^= 1;
         tc_fence_after();
         float d[8];
         tmem_ld<8>(tmem_q + 8 * cg, d);
@@ -564,10 +574,10 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
 
 extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
                               const void* wmat, const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2,
-                              float r3, int fmt, float* desa_part, float* jf_out, void* scratch, int num_sms, long long* dbg,
-                              cudaStream_t stream) {
+                              float r3, int fmt, const float* jf_in, float* desa_part, float* jf_out, void* scratch, int num_sms,
+                              long long* dbg, cudaStream_t stream) {
     using namespace kpf;
-    KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && N + J <= 65535 && J >= 1 && J <= 32 && S >= 1 && S <= 4);
+    KPF_REQUIRE(B >= 0 && N >= 64 && N % 64 == 0 && N + J <= 65535 && J >= 1 && J <= 32 && S >= 1 && S <= 4);
     KPF_REQUIRE(nsample == 32 || nsample == 64 || nsample == 128);
     KPF_REQUIRE(fmt == FMT_F16 || fmt == FMT_BF16);
     KPF_REQUIRE(((uintptr_t)wmat % 16) == 0 && ((uintptr_t)e % 16) == 0 && ((uintptr_t)part_acc % 16) == 0 && ((uintptr_t)wvec % 16) == 0);
@@ -575,9 +585,10 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     KPF_REQUIRE(scratch != nullptr && ((uintptr_t)scratch % 16) == 0 && num_sms >= 1);
     DesaParams p;
     KPF_REQUIRE(e_batch_stride >= (long long)(N + J) * 256 && e_batch_stride % 8 == 0);
-    p.fmt = fmt;
+    KPF_REQUIRE(jf_in != nullptr || (part_acc != nullptr && part_ms != nullptr));
+    p.fmt = fmt; p.jf_in = jf_in;
     p.e = (uint16_t*)e; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;
-    p.wvec = wvec; p.desa_part = desa_part; p.jf_out = jf_out; p.B = B; p.N = N; p.J = J; p.T = N / 128; p.S = S; p.nsample = nsample;
+    p.wvec = wvec; p.desa_part = desa_part; p.jf_out = jf_out; p.B = B; p.N = N; p.J = J; p.T = N / 64;   /* kpf_point_embed's tile = 64 points */ p.S = S; p.nsample = nsample;
     p.dbg = dbg;
     p.radius[0] = r0; p.radius[1] = r1; p.radius[2] = r2; p.radius[3] = r3;
     p.cj = (float*)scratch;

@@ -23,7 +23,7 @@ constexpr int PE_CH = PE_CP / 8;
 template <typename T>
 __global__ void __launch_bounds__(256)
 repack_kernel(const T* __restrict__ f_d, const T* __restrict__ f_rgb, const T* __restrict__ f_w, long long w_bs, int C, int J, int HW,
-              __nv_bfloat16* __restrict__ out) {
+              __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, h0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -40,7 +40,12 @@ repack_kernel(const T* __restrict__ f_d, const T* __restrict__ f_rgb, const T* _
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int h = h0 + r, c = c0 + tx;
-        if (h < HW && c < PE_CP) out[((size_t)b * HW + h) * PE_CP + c] = __float2bfloat16_rn(tile[tx][r]);
+        if (h < HW && c < PE_CP) {
+            const float v = tile[tx][r];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            out[((size_t)b * HW + h) * PE_CP + c] = hi;
+            if (out_lo) out_lo[((size_t)b * HW + h) * PE_CP + c] = __float2bfloat16_rn(v - __bfloat162float(hi));   // fp32 maps: second plane
+        }
     }
 }
 
@@ -464,15 +469,16 @@ constexpr size_t PE_SMEM = (size_t)(2 * 2048 + 2 * 1024 + 2 * 256 + 2048) * 16 +
 }  // namespace kpf
 
 extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const void* f_w, long long w_batch_stride, int dtype, int B, int C,
-                                   int J, int HW, void* out, cudaStream_t stream) {
+                                   int J, int HW, void* out, void* out_lo, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && C == 128 && J >= 1 && J <= 32 && HW >= 1);
     if (B == 0) return 0;
+    KPF_REQUIRE((dtype == KPF_F32) == (out_lo != nullptr));   // fp32 maps carry a second (lo) plane, bf16 maps are exact in one
     dim3 grid((HW + 31) / 32, PE_CP / 32, B);
     if (dtype == KPF_F32) {
         kpf::set_smem(repack_kernel<float>, 0);
         repack_kernel<float><<<grid, 256, 0, stream>>>((const float*)f_d, (const float*)f_rgb, (const float*)f_w, w_batch_stride, C, J, HW,
-                                                      (__nv_bfloat16*)out);
+                                                      (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo);
     } else if (dtype == KPF_BF16 && HW % 128 == 0 && ((uintptr_t)f_d % 16) == 0 && ((uintptr_t)f_rgb % 16) == 0 && ((uintptr_t)f_w % 16) == 0 &&
                w_batch_stride % 8 == 0) {
         kpf::set_smem(repack_bf16_kernel, 0);
@@ -481,7 +487,7 @@ extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const voi
     } else if (dtype == KPF_BF16) {
         kpf::set_smem(repack_kernel<__nv_bfloat16>, 0);
         repack_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)f_d, (const __nv_bfloat16*)f_rgb,
-                                                              (const __nv_bfloat16*)f_w, w_batch_stride, C, J, HW, (__nv_bfloat16*)out);
+                                                              (const __nv_bfloat16*)f_w, w_batch_stride, C, J, HW, (__nv_bfloat16*)out, nullptr);
     } else {
         return KPF_ERR_UNSUPPORTED;
     }
@@ -489,23 +495,26 @@ extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const voi
     return 0;
 }
 
-extern "C" int kpf_point_embed(const void* featT, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
-                               const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, void* e_out,
-                               long long e_batch_stride,
-                               float* part_acc, float* part_ms, int num_sms, long long* dbg, cudaStream_t stream) {
+extern "C" int kpf_point_embed(const void* feat_hi, const void* feat_lo, const int32_t* idx, const float* clos, const float* pcl,
+                               const float* joint, const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW,
+                               float kernel_size, int fmt, void* e_out, long long e_batch_stride, float* part_acc, float* part_ms,
+                               int num_sms, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
-    KPF_REQUIRE(B >= 0 && N >= 128 && N % 128 == 0 && J >= 1 && J <= 21 && HW >= 1 && num_sms >= 1);
-    KPF_REQUIRE(((uintptr_t)featT % 16) == 0 && ((uintptr_t)wmat % 16) == 0 && ((uintptr_t)idx % 16) == 0 && ((uintptr_t)clos % 16) == 0);
+    KPF_REQUIRE(B >= 0 && N >= PE_TP && N % PE_TP == 0 && J >= 1 && J <= 21 && HW >= 1 && num_sms >= 1);
+    KPF_REQUIRE(fmt == FMT_F16 || fmt == FMT_BF16);
+    KPF_REQUIRE(((uintptr_t)feat_hi % 16) == 0 && ((uintptr_t)feat_lo % 16) == 0 && ((uintptr_t)wmat % 16) == 0 && ((uintptr_t)idx % 16) == 0 &&
+                ((uintptr_t)clos % 16) == 0 && ((uintptr_t)e_out % 16) == 0);
     if (B == 0) return 0;
     PointParams p;
-    p.featT = (const uint4*)featT; p.idx = idx; p.clos = clos; p.pcl = pcl; p.joint = joint; p.order = order; p.wmat = (const uint4*)wmat; p.wvec = wvec;
-    KPF_REQUIRE(e_batch_stride >= (long long)N * 128 && e_batch_stride % 8 == 0);
-    p.e_out = (__nv_bfloat16*)e_out; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
-    p.kernel_size = kernel_size;
+    p.feat_hi = (const uint4*)feat_hi; p.feat_lo = (const uint4*)feat_lo; p.idx = idx; p.clos = clos; p.pcl = pcl; p.joint = joint; p.order = order;
+    p.wmat = (const uint4*)wmat; p.wvec = wvec;
+    KPF_REQUIRE(e_batch_stride >= (long long)N * 256 && e_batch_stride % 8 == 0);
+    p.e_out = (uint16_t*)e_out; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
+    p.kernel_size = kernel_size; p.fmt = fmt;
     p.dbg = dbg;
     cudaError_t e = kpf::set_smem(point_embed_kernel, PE_SMEM);
     if (e != cudaSuccess) return (int)e;
-    const int tiles = B * (N / 128);
+    const int tiles = B * (N / PE_TP);
     e = kpf::launch_pdl(point_embed_kernel, dim3(tiles < num_sms ? tiles : num_sms), dim3(PE_NT), PE_SMEM, stream, p);
     if (e != cudaSuccess) return (int)e;
     KPF_CHECK_LAUNCH();

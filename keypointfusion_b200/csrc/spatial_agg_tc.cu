@@ -5,22 +5,26 @@
 //   epilogue sw = sigmoid(S1 + ba) -> global ; G[hw][j] = fc_w[hw] (sg GAM + (1-sg) sw)    (thread = cell)
 //   GEMM B   out[c][j] += sum_hw relu(F[c][hw]) G[hw][j]                                   M = 128 channels, N = 32, K = 128 cells
 //
+// Split precision (csrc/umma_split.cuh): the bf16 feature map is exact in one plane (fp32 maps arrive as two bf16 planes from
+// kpf_split_planes); its GEMM partners (Wa's feature part, G) are THREE bf16 planes (both operands of an MMA must share a format);
+// the heat map and Wa's heat-map part are two planes in format fmt.  fp32-class results.
 // The NCHW feature tile [128 c x 128 hw] is staged ONCE per tile with 16-byte cp.async into the SWIZZLE_NONE canonical
 // layout and read by GEMM A as an MN-major A operand (M = hw contiguous) and -- same bytes, LBO/SBO swapped, after an
 // in-place relu pass -- by GEMM B as a K-major A operand (K = hw contiguous).  One CTA per sample sweeps its HW/128
 // tiles, accumulating out[c][j] in TMEM; the next tile's features are prefetched while the current one is consumed.
-#include "tmem_ldst.cuh"
+#include "umma_split.cuh"
 
 namespace kpf {
 
 struct SpatialParams {
-    const __nv_bfloat16* feat;   // [B,128,HW]
+    const __nv_bfloat16* feat;   // [B,128,HW]  (hi plane)
+    const __nv_bfloat16* feat_lo;   // lo plane of an fp32 map, or null
     const float* joints;         // [B,J,3] (uvd)
     const float* depth;
     long long depth_bs;
     int depth_rs, depth_cs;
     const float *center, *M, *cube, *cam;
-    const uint4* wa;             // canonical bf16: Wa[:, :128] as [16][32], Wa[:, 128:] as [4][32]
+    const uint4* wa;             // canonical 16-bit planes: Wa[:, :128] as [16][32] x 3 bf16 planes, Wa[:, 128:] as [4][32] hi | lo (fmt)
     const float *ba, *weight_dis, *fc_w, *fc_b, *prev;
     float *sw_out, *feat_j_out;
     int B, J, fs;
@@ -28,21 +32,11 @@ struct SpatialParams {
     long long* dbg;
     float* scratch;   // [B][split][128][32] partial out[c][j]
     int* counters;    // [B], zero on entry, zero again on exit
-    int split;
+    int split, fmt;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-// uvd -> xyz with approximate division: this kernel only feeds bf16 tensor-core operands (GAM), unlike K2 it produces no indices
-__device__ __forceinline__ float3 uvd2xyz_fast(const CamF& c, float un, float vn, float dn) {
-    const float u = (un + 1.0f) * c.hs, v = (vn + 1.0f) * c.hs, d = dn * c.hz + c.cz;
-    const float xw = c.mi[0] * u + c.mi[1] * v + c.mi[2], yw = c.mi[3] * u + c.mi[4] * v + c.mi[5];
-    float3 o;
-    o.x = __fdividef(__fdividef((xw - c.fu) * d, c.fx) - c.cx, c.hx);
-    o.y = __fdividef(__fdividef(c.flip * (yw - c.fv) * d, c.fy) - c.cy, c.hy);
-    o.z = dn;
-    return o;
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -50,13 +44,17 @@ constexpr int K5_NT = 512;   // thread = (cell or channel row = 32 * (warp % 4) 
 
 __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const SpatialParams p) {
     extern __shared__ __align__(128) unsigned char k5_smem[];
-    uint4* sF = reinterpret_cast<uint4*>(k5_smem);  // [2][2048] double-buffered raw feature tile, index (c/8)*128 + (hw/8)*8 + (c%8)
-    uint4* sFr = sF + 4096;                          // [2048]   relu copy
-    uint4* sHm = sFr + 2048;                         // [4][128] heat-map rows, K-major A operand (K = 32 joints)
-    uint4* sG = sHm + 512;                           // [16][4][8] G, MN-major B operand [K = 128 cells][N = 32]
-    uint4* sWa = sG + 512;                           // [16][32] + [4][32]
-    float* sJ = reinterpret_cast<float*>(sWa + 640); // [32][8]: hm centre (x,y), xyz
+    const bool has_lo = p.feat_lo != nullptr;
+    const int NP = has_lo ? 2 : 1;                   // feature planes
+    uint4* sHm = reinterpret_cast<uint4*>(k5_smem); // 2 planes x [4][128] heat-map rows, K-major A operand (K = 32 joints)
+    const int NBUF = has_lo ? 1 : 2;                 // fp32 maps: two planes per tile leave no room for the prefetch buffer
+    uint4* sG = sHm + 1024;                          // 3 bf16 planes x [16][4][8] G, MN-major B operand [K = 128 cells][N = 32]
+    uint4* sWa = sG + 1536;                          // [16][32] x 3 bf16 planes, [4][32] hi | lo
+    float* sJ = reinterpret_cast<float*>(sWa + 1792); // [32][8]: hm centre (x,y), xyz
+    uint4* sF = reinterpret_cast<uint4*>(sJ + 256 + 32);   // [NBUF buffers][NP planes][2048] raw feature tile, index (c/8)*128 + (hw/8)*8 + (c%8)
+    uint4* sFr = sF + NBUF * NP * 2048;              // [NP planes][2048] relu copy
     float* sBa = sJ + 256;                           // [32] atten_spatial bias
+    const int fmt = p.fmt;
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ CamF cam;
@@ -81,9 +79,10 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
         fence_mbar_init();
         load_cam(cam, b, p.center, p.M, p.cube, p.cam, p.img_size, p.flip);
     }
-    for (int i = tid; i < 640; i += K5_NT) sWa[i] = p.wa[i];
+    for (int i = tid; i < 1792; i += K5_NT) sWa[i] = p.wa[i];
     if (tid < 32) sBa[tid] = tid < J ? p.ba[tid] : 0.f;
     const __nv_bfloat16* fb = p.feat + (size_t)b * 128 * HW;
+    const __nv_bfloat16* fbl = has_lo ? p.feat_lo + (size_t)b * 128 * HW : nullptr;
     // tile loader: thread -> (c%8 = tid%8, hw8 = (tid/8)%16, channel group tid/128 + 4i): 16-byte cp.async, 128 contiguous bytes
     // of a channel row per 8 lanes
     auto load_tile = [&](int t, uint4* dst) {
@@ -92,6 +91,7 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
         for (int i = 0; i < 4; ++i) {
             const int cgp = (tid >> 7) + 4 * i;
             cp_async16(dst + cgp * 128 + hw8 * 8 + c8, fb + (size_t)(cgp * 8 + c8) * HW + t * 128 + hw8 * 8);
+            if (has_lo) cp_async16(dst + 2048 + cgp * 128 + hw8 * 8 + c8, fbl + (size_t)(cgp * 8 + c8) * HW + t * 128 + hw8 * 8);
         }
     };
     load_tile(t_begin, sF);   // features, camera and weights are inputs of the step: fetched before the dependency wait
@@ -110,47 +110,64 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
     }
     const uint32_t tmem0 = tmem_slot, tmem = tmem0 + ((uint32_t)(32 * q) << 16);
     uint32_t phase = 0;
-    const float sg = 1.f / (1.f + __expf(-p.weight_dis[0]));
-    const float inv2s2 = 1.f / (2.f * p.hm_sigma * p.hm_sigma * p.hm_std * p.hm_std);
-    const float inv_fs = 1.f / (float)fs;
+    const float sg = 1.f / (1.f + expf(-p.weight_dis[0]));
+    const float inv2s2 = 1.f / (2.f * p.hm_sigma * p.hm_sigma);
+    const float ffs = (float)fs;
     __syncthreads();
 
     stamp();
     for (int t = t_begin; t < t_end; ++t) {
-        uint4* cur = sF + ((t - t_begin) & 1) * 2048;
+        uint4* cur = sF + ((t - t_begin) & (NBUF - 1)) * NP * 2048;
+        if (NBUF == 1 && t > t_begin) load_tile(t, sF);   // single buffer: its readers (tile t-1's MMAs) were waited for
         cp_async_wait_all();   // this thread's part of tile t has landed ...
         __syncthreads();       // ... and everybody's; the other buffer's readers (tile t-1) are done
-        if (t + 1 < t_end) load_tile(t + 1, sF + ((t + 1 - t_begin) & 1) * 2048);  // overlaps the whole iteration
+        if (NBUF == 2 && t + 1 < t_end) load_tile(t + 1, sF + ((t + 1 - t_begin) & 1) * NP * 2048);  // overlaps the whole iteration
         if (t == t_begin + 1) stamp();
         // ---- per-cell geometry (thread = cell `row`, joints [8cg, 8cg + 8)): heat-map chunk (A operand) and GAM (registers)
         const int m = t * 128 + row, r = m / fs, col = m - r * fs;
         const float d = __ldg(p.depth + (size_t)b * p.depth_bs + (size_t)r * p.depth_rs + (size_t)col * p.depth_cs);
-        const float3 qc = uvd2xyz_fast(cam, (2.f * col + 1.f) * inv_fs - 1.f, (2.f * r + 1.f) * inv_fs - 1.f, d);
+        const float3 qc = uvd2xyz(cam, cell_coord(col, ffs), cell_coord(r, ffs), d);   // same arithmetic as the fp32 kernel (spatial_agg.cu)
         float gam[8], hm[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int j = 8 * cg + i;
             if (j < J) {
-                const float dx = (float)col + 0.5f - sJ[8 * j], dy = (float)r + 0.5f - sJ[8 * j + 1];
-                hm[i] = __expf(-(dx * dx + dy * dy) * inv2s2);
+                const float dx = ((float)col + 0.5f - sJ[8 * j]) / p.hm_std, dy = ((float)r + 0.5f - sJ[8 * j + 1]) / p.hm_std;
+                hm[i] = expf(-(dx * dx + dy * dy) * inv2s2);
                 const float ex = qc.x - sJ[8 * j + 2], ey = qc.y - sJ[8 * j + 3], ez = qc.z - sJ[8 * j + 4];
-                gam[i] = __fdividef(1.f, p.gamma * (ex * ex + ey * ey + ez * ez) + 1.f);
+                gam[i] = 1.f / (p.gamma * (ex * ex + ey * ey + ez * ez) + 1.f);
             } else {
                 hm[i] = 0.f;
                 gam[i] = 0.f;
             }
         }
-        sHm[cg * 128 + row] = pack8_bf16(hm);
+        {
+            uint4 oh, ol;
+            split8(fmt, hm, oh, ol);
+            sHm[cg * 128 + row] = oh;
+            sHm[512 + cg * 128 + row] = ol;
+        }
         if (t == t_begin + 1) stamp();
         // relu copy for GEMM B (same layout)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint4 v = cur[tid + i * K5_NT];
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-            const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+            uint32_t* h = reinterpret_cast<uint32_t*>(&v);
+            uint32_t keep[4];   // 0xffff per 16-bit element whose hi plane is positive: relu(hi + lo) keeps or drops both planes together
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h[k] = __hmax2(h[k], z);
+            for (int k = 0; k < 4; ++k) {
+                keep[k] = ((h[k] & 0x8000u) ? 0u : 0xffffu) | ((h[k] & 0x80000000u) ? 0u : 0xffff0000u);
+                h[k] &= keep[k];
+            }
             sFr[tid + i * K5_NT] = v;
+            if (has_lo) {
+                uint4 l = cur[2048 + tid + i * K5_NT];
+                l.x &= keep[0];
+                l.y &= keep[1];
+                l.z &= keep[2];
+                l.w &= keep[3];
+                sFr[2048 + tid + i * K5_NT] = l;
+            }
         }
         if (t == t_begin + 1) stamp();
         fence_proxy_async();
@@ -159,10 +176,15 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
         if (warp_u == 0) {
             tc_fence_after();
             if (elect_one()) {
-                // GEMM A: A = F tile MN-major (LBO 2048 between channel groups, SBO 128 between cell groups)
-                umma_gemm(tmem0 + ACC1, smem_u32(cur), 2048, 128, smem_u32(sWa), 512, 128, umma_idesc_bf16(128, 32, true, false), 128, false);
-                umma_gemm(tmem0 + ACC1, smem_u32(sHm), 2048, 128, smem_u32(sWa + 512), 512, 128, umma_idesc_bf16(128, 32, false, false), 32,
-                          true);
+                // GEMM A: A = F tile MN-major (LBO 2048 between channel groups, SBO 128 between cell groups), bf16 plane(s);
+                //         B = Wa's feature part, three bf16 planes
+                const uint32_t fa = smem_u32(cur);
+                umma_gemm_map_x3(tmem0 + ACC1, fa, has_lo ? fa + 2048 * 16 : 0u, 2048, 128, smem_u32(sWa), 512 * 16, 512, 128,
+                                 umma_idesc_f16(128, 32, true, false, FMT_BF16, FMT_BF16), 128, false);
+                SmemOp a, bo;
+                a.hi = smem_u32(sHm); a.lo = a.hi + 512 * 16; a.lbo = 2048; a.sbo = 128;
+                bo.hi = smem_u32(sWa + 1536); bo.lo = bo.hi + 128 * 16; bo.lbo = 512; bo.sbo = 128;
+                umma_gemm3_ss(tmem0 + ACC1, a, bo, umma_idesc_f16(128, 32, false, false, fmt, fmt), 32, true);
                 umma_commit(&mma_bar);
             }
             __syncwarp();
@@ -179,14 +201,18 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
             for (int i = 0; i < 8; ++i) {
                 const int j = 8 * cg + i;
                 if (j < J) {
-                    const float swv = __fdividef(1.f, 1.f + __expf(-(s1[i] + sBa[j])));
+                    const float swv = 1.f / (1.f + expf(-(s1[i] + sBa[j])));
                     p.sw_out[((size_t)b * J + j) * HW + m] = swv;
                     s1[i] = fw * (sg * gam[i] + (1.f - sg) * swv);  // model.py:337-338 and fc_spatial2joint_feature's weight
                 } else {
                     s1[i] = 0.f;
                 }
             }
-            sG[(row >> 3) * 32 + cg * 8 + (row & 7)] = pack8_bf16(s1);
+            uint4 oh, om, ol;
+            split8x3_bf16(s1, oh, om, ol);
+            sG[(row >> 3) * 32 + cg * 8 + (row & 7)] = oh;
+            sG[512 + (row >> 3) * 32 + cg * 8 + (row & 7)] = om;
+            sG[1024 + (row >> 3) * 32 + cg * 8 + (row & 7)] = ol;
         }
         if (t == t_begin + 1) stamp();
         fence_proxy_async();
@@ -196,8 +222,9 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
             tc_fence_after();
             if (elect_one()) {
                 // GEMM B: A = relu(F) tile read K-major (K = cells): LBO 128 between cell groups, SBO 2048 between channel groups
-                umma_gemm(tmem0 + ACC2, smem_u32(sFr), 128, 2048, smem_u32(sG), 512, 128, umma_idesc_bf16(128, 32, false, true), 128,
-                          t > t_begin);
+                const uint32_t fr = smem_u32(sFr);
+                umma_gemm_map_x3(tmem0 + ACC2, fr, has_lo ? fr + 2048 * 16 : 0u, 128, 2048, smem_u32(sG), 512 * 16, 512, 128,
+                                 umma_idesc_f16(128, 32, false, true, FMT_BF16, FMT_BF16), 128, t > t_begin);
                 umma_commit(&mma_bar);
             }
             __syncwarp();
@@ -260,24 +287,48 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
 
 }  // namespace kpf
 
-extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const float* joints, const float* depth, long long depth_bs, int depth_rs,
+// fp32 -> two bf16 planes (hi = rn(x), lo = rn(x - hi)), elementwise: how an fp32 feature map enters the split-precision kernels
+__global__ void __launch_bounds__(256) split_planes_kernel(const float4* __restrict__ x, long long n4, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        uint2 h, l;
+        kpf::split2<kpf::FMT_BF16>(v.x, v.y, h.x, l.x);
+        kpf::split2<kpf::FMT_BF16>(v.z, v.w, h.y, l.y);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+extern "C" int kpf_split_planes(const float* x, long long n, void* hi, void* lo, cudaStream_t stream) {
+    KPF_REQUIRE(n >= 0 && n % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)hi % 8) == 0 && ((uintptr_t)lo % 8) == 0);
+    if (n == 0) return 0;
+    const long long n4 = n / 4;
+    const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    split_planes_kernel<<<grid, 256, 0, stream>>>((const float4*)x, n4, (uint2*)hi, (uint2*)lo);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const void* feat_rgb_lo, const float* joints, const float* depth, long long depth_bs, int depth_rs,
                                         int depth_cs, const float* center, const float* M, const float* cube, const float* cam,
                                         const void* wa_packed, const float* ba, const float* weight_dis, const float* fc_w,
                                         const float* fc_b, const float* prev, int B, int C, int J, int fs, float img_size, float flip,
-                                        float hm_std, float hm_sigma, float gamma, float* sw_out, float* feat_j_out, float* scratch, int* counters, int split, long long* dbg,
-                                        cudaStream_t stream) {
+                                        float hm_std, float hm_sigma, float gamma, int fmt, float* sw_out, float* feat_j_out, float* scratch,
+                                        int* counters, int split, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && C == 128 && J >= 1 && J <= 32 && fs >= 1 && (fs * fs) % 128 == 0);
-    KPF_REQUIRE(((uintptr_t)feat_rgb % 16) == 0 && ((uintptr_t)wa_packed % 16) == 0);
+    KPF_REQUIRE(((uintptr_t)feat_rgb % 16) == 0 && ((uintptr_t)feat_rgb_lo % 16) == 0 && ((uintptr_t)wa_packed % 16) == 0);
+    KPF_REQUIRE(fmt == FMT_F16 || fmt == FMT_BF16);
     if (B == 0) return 0;
     KPF_REQUIRE(split >= 1 && ((fs * fs) / 128) % split == 0 && (split == 1 || (scratch != nullptr && counters != nullptr)));
     SpatialParams p;
-    p.feat = (const __nv_bfloat16*)feat_rgb; p.joints = joints; p.depth = depth; p.depth_bs = depth_bs; p.depth_rs = depth_rs;
+    p.feat = (const __nv_bfloat16*)feat_rgb; p.feat_lo = (const __nv_bfloat16*)feat_rgb_lo; p.fmt = fmt; p.joints = joints; p.depth = depth; p.depth_bs = depth_bs; p.depth_rs = depth_rs;
     p.depth_cs = depth_cs; p.center = center; p.M = M; p.cube = cube; p.cam = cam; p.wa = (const uint4*)wa_packed; p.ba = ba;
     p.weight_dis = weight_dis; p.fc_w = fc_w; p.fc_b = fc_b; p.prev = prev; p.sw_out = sw_out; p.feat_j_out = feat_j_out;
     p.dbg = dbg; p.scratch = scratch; p.counters = counters; p.split = split;
     p.B = B; p.J = J; p.fs = fs; p.img_size = img_size; p.flip = flip; p.hm_std = hm_std; p.hm_sigma = hm_sigma; p.gamma = gamma;
-    const size_t smem = (size_t)(4096 + 2048 + 512 + 512 + 640) * 16 + 32 * 8 * 4 + 32 * 4;
+    const int NP = feat_rgb_lo ? 2 : 1, NBUF = feat_rgb_lo ? 1 : 2;
+    const size_t smem = (size_t)(1024 + 1536 + 1792 + (NBUF + 1) * NP * 2048) * 16 + 32 * 8 * 4 + 32 * 4;
     cudaError_t e = kpf::set_smem(spatial_aggregate_tc_kernel, smem);
     if (e != cudaSuccess) return (int)e;
     {

@@ -272,41 +272,54 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         write_act(bufY, e);      // k_in = tokens + cross_posembed
     }
 
+    // ---- DESA fusion conv: x = relu(W_fu [desa_0 | desa_1 | desa_2 | jf] + b_fu): four accumulating K = 128 GEMMs (model.py:160-164)
+    auto fusion_prologue = [&](float* a) {
+        float v[8];
+        const float* dsrc = p.desa + (size_t)b * 3 * J * C;
+        load_tok(dsrc, C, v);
+        write_act(bufX, v);
+        load_tok(dsrc + (size_t)J * C, C, v);
+        write_act(bufY, v);
+        load_tok(dsrc + (size_t)2 * J * C, C, v);
+        write_act(bufQ, v);
+        load_tok(p.jf + (size_t)b * J * C, C, v);
+        write_act(bufK, v);
+        sync_for_mma();
+        if (warp_u == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                issue_proj(ACC_X, bufX, g, false);
+                issue_proj(ACC_X, bufY, g + 2, true);
+                issue_proj(ACC_X, bufQ, g + 4, true);
+                issue_proj(ACC_X, bufK, g + 6, true);
+                umma_commit(&bars[0]);
+            }
+            __syncwarp();
+        }
+        g += 8;
+        const float bb = __ldg(bfu + f);
+        wait_bar(0);
+        tmem_ld<8>(tmem + ACC_X + 8 * c, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = tokv[i] ? fmaxf(a[i] + bb, 0.f) : 0.f;
+    };
+    if (p.pre && p.L == 0) {   // prologue-only program (stand-alone DESA.forward): the fusion conv's output is the result
+        float a[8];
+        fusion_prologue(a);
+        if (p.tokens_out) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (tokv[i]) p.tokens_out[((size_t)b * J + 8 * c + i) * C + f] = a[i];
+        }
+    }
+
     for (int it = 0; it < n_layers; ++it) {
         const bool is_cross = p.cross && it == 0;
         if (it == (p.cross ? 1 : 0) && p.L > 0) {
             // =========================== encoder input stage (KP_Interaction_TR) ===========================
             if (p.pre) {
-                // ---- DESA fusion conv: x = relu(W_fu [desa_0 | desa_1 | desa_2 | jf] + b_fu): four accumulating K = 128 GEMMs
-                float v[8];
-                const float* dsrc = p.desa + (size_t)b * 3 * J * C;
-                load_tok(dsrc, C, v);
-                write_act(bufX, v);
-                load_tok(dsrc + (size_t)J * C, C, v);
-                write_act(bufY, v);
-                load_tok(dsrc + (size_t)2 * J * C, C, v);
-                write_act(bufQ, v);
-                load_tok(p.jf + (size_t)b * J * C, C, v);
-                write_act(bufK, v);
-                sync_for_mma();
-                if (warp_u == 0) {
-                    tc_fence_after();
-                    if (elect_one()) {
-                        issue_proj(ACC_X, bufX, g, false);
-                        issue_proj(ACC_X, bufY, g + 2, true);
-                        issue_proj(ACC_X, bufQ, g + 4, true);
-                        issue_proj(ACC_X, bufK, g + 6, true);
-                        umma_commit(&bars[0]);
-                    }
-                    __syncwarp();
-                }
-                g += 8;
-                const float bb = __ldg(bfu + f);
-                wait_bar(0);
                 float a[8];
-                tmem_ld<8>(tmem + ACC_X + 8 * c, a);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = tokv[i] ? fmaxf(a[i] + bb, 0.f) : 0.f;
+                fusion_prologue(a);
                 head_partial(0, a, Wres_feat);
                 write_act(bufX, a);
             }
@@ -695,13 +708,13 @@ extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d,
                                int Fc, int fmt, float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride,
                                int out_jc_c0, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
-    KPF_REQUIRE(B >= 0 && J >= 1 && J <= 32 && L >= 0 && (cross || L > 0));
+    KPF_REQUIRE(B >= 0 && J >= 1 && J <= 32 && L >= 0 && (cross || pre || L > 0));
     KPF_REQUIRE(fmt == FMT_F16 || fmt == FMT_BF16);
     if (B == 0) return 0;   // an empty batch has no buffers to validate
     KPF_REQUIRE(L == 0 || F == 16 || F == 128);
     KPF_REQUIRE(!cross || (y != nullptr && (Fc == 16 || Fc == 128)));
     KPF_REQUIRE(L == 0 || D == TS_C || (D > TS_C && D <= TS_C + 16));
-    KPF_REQUIRE(!pre || (desa != nullptr && jf != nullptr && !cross && D == TS_C));
+    KPF_REQUIRE(!pre || (desa != nullptr && jf != nullptr && !cross && (L == 0 || D == TS_C)));
     KPF_REQUIRE(!(cross && L > 0) || (r3d != nullptr && D > TS_C));
     KPF_REQUIRE(n_weights <= TS_MAXG);
     const int per_cross = 8 + (Fc == 16 ? 1 : 4), per_layer = 8 + (F == 16 ? 1 : 4);

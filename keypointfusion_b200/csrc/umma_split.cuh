@@ -3,8 +3,9 @@
 // The dropped lo x lo term and the rounding of lo are both 2^-2p relative (p = 8 for bf16 planes, 11 for fp16 planes), so the
 // contraction is good to ~2^-16 (bf16) / ~2^-21 (fp16) per product instead of 2^-9 -- what the 0.05 mm joint bar needs
 // (DESIGN.md section 2).  An operand that is exactly representable in 16 bits (a bf16 feature map) has no lo plane and its lo
-// MMAs are skipped.  kind::f16 takes the A and B element formats independently, so a bf16 map can meet fp16-split weights in
-// one instruction.
+// MMAs are skipped.  The instruction descriptor has separate A / B format fields, but an fp16 x bf16 pairing traps as an illegal
+// instruction on sm_100a (measured), so both operands of an MMA use ONE format: where a bf16 feature map is an operand, the other
+// side is carried as THREE bf16 planes (24 bits, split3_bf16) instead of two fp16 planes.
 //
 // A may also come from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): row m of A = TMEM lane m, K runs along the columns,
 // two 16-bit elements per 32-bit column (low half = even k).  Weights that stay resident for a whole kernel live there, which
@@ -157,6 +158,35 @@ __device__ __forceinline__ void split8(int fmt, const float* v, uint4& hi, uint4
     split2(fmt, v[4], v[5], hi.z, lo.z);
     split2(fmt, v[6], v[7], hi.w, lo.w);
 }
+// fp32 -> three bf16 planes (hi + mid + lo carries 24 mantissa bits, full fp32 range): the partner of a bf16 feature-map operand
+__device__ __forceinline__ void split3_bf16(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const float ra = a - hf.x, rb = b - hf.y;
+    const __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
+    const float2 mf = __bfloat1622float2(m);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    mid = *reinterpret_cast<const uint32_t*>(&m);
+    lo = pack2_bf16(ra - mf.x, rb - mf.y);
+}
+__device__ __forceinline__ void split8x3_bf16(const float* v, uint4& hi, uint4& mid, uint4& lo) {
+    split3_bf16(v[0], v[1], hi.x, mid.x, lo.x);
+    split3_bf16(v[2], v[3], hi.y, mid.y, lo.y);
+    split3_bf16(v[4], v[5], hi.z, mid.z, lo.z);
+    split3_bf16(v[6], v[7], hi.w, mid.w, lo.w);
+}
+// D (+)= A B^T with A = a bf16 feature-map operand (one exact plane, or hi + lo of an fp32 map) and B = three bf16 planes at
+// b_addr + {0, 1, 2} * b_plane_bytes: A_hi (B_hi + B_mid + B_lo) [+ A_lo (B_hi + B_mid)], smallest terms first.
+__device__ __forceinline__ void umma_gemm_map_x3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo /* 0: none */, uint32_t a_lbo, uint32_t a_sbo,
+                                                 uint32_t b_addr, uint32_t b_plane_bytes, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int K,
+                                                 bool accumulate) {
+    umma_gemm(tmem_d, a_hi, a_lbo, a_sbo, b_addr + 2 * b_plane_bytes, b_lbo, b_sbo, idesc, K, accumulate);
+    if (a_lo) umma_gemm(tmem_d, a_lo, a_lbo, a_sbo, b_addr + b_plane_bytes, b_lbo, b_sbo, idesc, K, true);
+    umma_gemm(tmem_d, a_hi, a_lbo, a_sbo, b_addr + b_plane_bytes, b_lbo, b_sbo, idesc, K, true);
+    if (a_lo) umma_gemm(tmem_d, a_lo, a_lbo, a_sbo, b_addr, b_lbo, b_sbo, idesc, K, true);
+    umma_gemm(tmem_d, a_hi, a_lbo, a_sbo, b_addr, b_lbo, b_sbo, idesc, K, true);
+}
+
 // the value the MMAs see for x (hi + lo), for callers that must stay consistent with an operand they wrote
 __device__ __forceinline__ float split_value(int fmt, float x) {
     if (fmt == FMT_BF16) {

@@ -6,6 +6,14 @@ import torch.nn as nn
 from .. import ops
 
 
+def _inference_only(module, *tensors):
+    """These modules sit inside TRAINED backbones in the reference (model/resnet.py:438-498); the kernels have no backward, so
+    running them under autograd would silently drop the gradients of the gates and of everything upstream."""
+    if module.training or (torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)):
+        raise RuntimeError(f"{type(module).__name__}: inference only (no autograd through the B200 kernels); call .eval() and run under "
+                           "torch.no_grad()")
+
+
 class FilterLayer(nn.Module):
     # model/fusion_layer.py:6-22
     def __init__(self, in_planes, out_planes, reduction=16):
@@ -16,6 +24,7 @@ class FilterLayer(nn.Module):
         self.out_planes = out_planes
 
     def forward(self, x):
+        _inference_only(self, x)
         b, c = x.shape[:2]
         y = ops.channel_mean(x)
         y = torch.sigmoid(torch.addmm(self.fc[2].bias, torch.relu(torch.addmm(self.fc[0].bias, y, self.fc[0].weight.t())),
@@ -30,6 +39,7 @@ class FSP(nn.Module):
         self.filter = FilterLayer(2 * in_planes, out_planes, reduction)
 
     def forward(self, guidePath, mainPath):
+        _inference_only(self, guidePath, mainPath)
         fc = self.filter.fc
         return ops.fsp(guidePath, mainPath, fc[0].weight, fc[0].bias, fc[2].weight, fc[2].bias)
 
@@ -50,6 +60,7 @@ class RGBDFusion(nn.Module):
 
     def forward(self, x, train_writer=None, global_step=0, layer_stage=0):
         rgb, depth = x
+        _inference_only(self, rgb, depth)
         gw = torch.cat([self.gate_rgb.weight.reshape(1, -1), self.gate_depth.weight.reshape(1, -1)], 0)
         gb = torch.cat([self.gate_rgb.bias, self.gate_depth.bias])
         rgb_out, depth_out, merge, amean = ops.rgbd_fusion(rgb, depth, gw, gb, want_attn_mean=train_writer is not None)
@@ -74,6 +85,7 @@ class ACFusion(nn.Module):
 
     def forward(self, x, train_writer=None, global_step=0, layer_stage=0):
         rgb, depth = x
+        _inference_only(self, rgb, depth)
         rgb_out, depth_out, merge = ops.ac_fusion(rgb, depth, self.cam_rgb.weight, self.cam_rgb.bias, self.cam_depth.weight,
                                                   self.cam_depth.bias)
         return [rgb_out, depth_out], merge

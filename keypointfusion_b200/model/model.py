@@ -60,30 +60,45 @@ def _fold_bn(conv_w, conv_b, bn):
     return W.contiguous(), b.contiguous()
 
 
+def _param_fingerprint(module):
+    """(data_ptr, version) of every parameter and buffer below `module`: changes on .to(), load_state_dict (a copy_ bumps the
+    version counter), in-place edits and optimiser steps."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
 class _KernelCache:
-    """Mixin: lazily built, device-resident folded/packed weights, dropped whenever parameters move or are reloaded."""
+    """Mixin: lazily built, device-resident folded/packed weights.  The cache is keyed on the parameters' storage pointers and
+    version counters, so it is rebuilt after ANY change of the weights -- a parent-level `net.load_state_dict(ckpt)` (which
+    recurses through `_load_from_state_dict` and never calls a child's `load_state_dict`), `.to()`, an in-place edit -- and a
+    DataParallel replica (whose parameters are different tensors) never reuses the source module's device-0 cache."""
 
     def invalidate(self):
         self.__dict__["_kc"] = None
+        self.__dict__["_kc_key"] = None
         for m in self.children():
             if hasattr(m, "invalidate"):
                 m.invalidate()
 
-    def _apply(self, fn, *a, **k):
-        self.__dict__["_kc"] = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self.invalidate()
-        return super().load_state_dict(*a, **k)
-
     def kc(self):
+        key = _param_fingerprint(self)
         c = self.__dict__.get("_kc")
-        if c is None:
+        if c is None or self.__dict__.get("_kc_key") != key:
             with torch.no_grad():
                 c = self._build_kc()
             self.__dict__["_kc"] = c
+            self.__dict__["_kc_key"] = key
         return c
+
+
+def _inference_only(module, *tensors):
+    """The kernels have no backward and fold BatchNorm with running statistics: refuse to run where that would silently drop
+    gradients or use the wrong statistics (a model swapped into the reference's train.py must not 'train')."""
+    if module.training:
+        raise RuntimeError(f"{type(module).__name__}: inference only (BatchNorm folded with running statistics, dropout = identity, no "
+                           "autograd through the B200 kernels); call .eval()")
+    if torch.is_grad_enabled() and (any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors)):
+        raise RuntimeError(f"{type(module).__name__}: an input requires grad but the B200 kernels have no backward; wrap the call in "
+                           "torch.no_grad() or detach the inputs")
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -107,6 +122,16 @@ class _BertEmbeddings(nn.Module):
         self.position_embeddings = nn.Embedding(c.max_position_embeddings, c.hidden_size)
         self.token_type_embeddings = nn.Embedding(c.type_vocab_size, c.hidden_size)
         self.LayerNorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        # transformers 4.25.1 (the reference's pin) registers this as a PERSISTENT buffer, so the released checkpoints carry
+        # `...bert.embeddings.position_ids`; newer transformers dropped it from the state_dict.  Registered persistent here and
+        # tolerated when missing (see _load_from_state_dict) so that both key lists load with strict=True.
+        self.register_buffer("position_ids", torch.arange(c.max_position_embeddings).expand((1, -1)).clone(), persistent=True)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        if prefix + "position_ids" not in state_dict:
+            state_dict = dict(state_dict)
+            state_dict[prefix + "position_ids"] = self.position_ids
+        return super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
 
 class _BertSelfAttention(nn.Module):
@@ -194,34 +219,21 @@ class KP_Interaction_TR(_KernelCache, nn.Module):  # model.py:106-126
     def _build_kc(self):
         return {}
 
-    def forward_tc(self, img_feats, want_tokens=True):
-        """bf16 tensor-core path (csrc/token_stack.cu): same contract as forward()."""
+    def forward(self, img_feats, *unused, want_tokens=True, **unused_kw):
+        """img_feats [B,J,D] -> (tokens [B,J,hidden], pred [B,J,3]).  model.py:45-103, :116-126 -- one launch of the
+        split-precision tcgen05 token-stack kernel (csrc/token_stack.cu)."""
+        _inference_only(self, img_feats)
+        c = self.config
+        J, D = img_feats.shape[1], img_feats.shape[2]
+        if (c.hidden_size, c.num_attention_heads) != (128, 4) or J > 32 or not (D == 128 or 128 < D <= 144):
+            raise NotImplementedError("token-stack kernel: hidden 128, 4 heads, <= 32 tokens, 128 <= input dim <= 144 (no fallback path)")
         k = self.kc()
-        J = img_feats.shape[1]
         if J not in k:  # the position-embedding slice depends on the token count
             k[J] = ops.pack_token_program(J, enc=(self.state_dict(), "")).to(img_feats.device)
         tokens, pred, _ = ops.token_stack(k[J], x=img_feats, want_tokens=want_tokens)
         return tokens, pred
 
-    def forward(self, img_feats, *unused, precision="fp32", **unused_kw):
-        """img_feats [B,J,D] -> (tokens [B,J,hidden], pred [B,J,3]).  model.py:45-103, :116-126."""
-        if precision == "bf16":
-            return self.forward_tc(img_feats)
-        c = self.config
-        B, L, _ = img_feats.shape
-        x = img_feats.float()
-        h = self.bert.position_embeddings.weight[:L].unsqueeze(0) + F.linear(x, self.bert.img_embedding.weight, self.bert.img_embedding.bias)
-        H, hd = c.num_attention_heads, c.hidden_size // c.num_attention_heads
-        for lyr in self.bert.encoder.layer:
-            a = lyr.attention
-            q = a.self.query(h).view(B, L, H, hd).transpose(1, 2)
-            k = a.self.key(h).view(B, L, H, hd).transpose(1, 2)
-            v = a.self.value(h).view(B, L, H, hd).transpose(1, 2)
-            ctx = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, c.hidden_size)
-            h = a.output.LayerNorm(a.output.dense(ctx) + h)
-            h = lyr.output.LayerNorm(lyr.output.dense(F.gelu(lyr.intermediate.dense(h))) + h)
-        pred = self.cls_head(h) + self.residual(x)
-        return h, pred
+    forward_tc = forward
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -263,24 +275,24 @@ class DESA(_KernelCache, nn.Module):
         return k
 
     def forward(self, pcl_feat, node_feat, pcl_xyz, node_xyz):
-        """pcl_feat [B,N,C], node_feat [B,J,C], pcl_xyz [B,N,3], node_xyz [B,J,3] -> [B,J,C].  model.py:166-204."""
+        """pcl_feat [B,N,C], node_feat [B,J,C], pcl_xyz [B,N,3], node_xyz [B,J,3] -> [B,J,C].  model.py:166-204.
+        Stand-alone call of the fused kernels: ball query + grouped two-layer MLP + max-pool (csrc/desa_fused.cu, the joints'
+        features given instead of embedded there) and the 512 -> 128 fusion conv (csrc/token_stack.cu, prologue-only program).
+        Inside Block_KPFusion the same kernels run with the joint embedding and init_TR fused in."""
+        _inference_only(self, pcl_feat, node_feat)
         k = self.kc()
         B, J, C = node_feat.shape
-        xyz = torch.cat((pcl_xyz, node_xyz), dim=1).contiguous()
-        feat = torch.cat((pcl_feat, node_feat), dim=1)
-        bi = torch.arange(B, device=xyz.device).view(B, 1, 1)
-        outs = []
-        for i in range(self.scale_num):
-            r = self.radius[i]
-            idx = ops.ball_query(xyz, node_xyz, r, self.S[i]).long()
-            gx = (xyz[bi, idx] - node_xyz.unsqueeze(2)) / r
-            gf = feat[bi, idx] - node_feat.unsqueeze(2)
-            g = F.relu(F.linear(gx, *k["l0"][i]) + F.linear(gf, *k["f0"][i]))
-            for W, b in k["mlp"][i]:
-                g = F.relu(F.linear(g, W, b))
-            outs.append(g.max(dim=2)[0])
-        outs.append(node_feat)
-        return F.relu(F.linear(torch.cat(outs, dim=-1), *k["fusion"]))
+        N = pcl_feat.shape[1]
+        if k["scales"] is None or C != 128 or N % 64 or J > 32 or len(set(self.S)) != 1 or self.scale_num > 4:
+            raise NotImplementedError("DESA kernels: 128 channels, one nsample for all scales, N % 64 == 0, single-conv MLPs (no fallback path)")
+        dev = node_feat.device
+        if "ds" not in k:
+            eye, z = torch.eye(128, device=dev), torch.zeros(128, device=dev)
+            k["ds"] = ops.pack_desa(eye, z, torch.zeros(128, 3, device=dev), z, k["scales"])
+            k["fu"] = ops.pack_token_program(J, fusion=k["fusion"]).to(dev)
+        e = ops.e_from_float(pcl_feat.float())
+        part, _ = ops.desa_fused(e, None, None, pcl_xyz, node_xyz, k["ds"][0], k["ds"][1], self.radius, self.S[0], jf_in=node_feat)
+        return ops.token_stack(k["fu"], desa=part, jf=node_feat)[0]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -323,7 +335,6 @@ class Block_KPFusion(_KernelCache, nn.Module):
         self.cls_head = nn.Linear(128, 3)                               # model.py:270 (after apply)
         self.weight_dis = nn.Parameter(torch.zeros([1]))
         self.GFM_ = GFM()
-        self.precision = "auto"   # "auto": bf16 tensor-core path when the feature maps are bf16, fp32 otherwise
 
     def _init_weights(self, m):  # model.py:275-285
         if isinstance(m, nn.Conv2d):
@@ -351,67 +362,41 @@ class Block_KPFusion(_KernelCache, nn.Module):
         tok_init = ops.pack_token_program(self.joint_num, enc=(self.init_TR.state_dict(), ""), fusion=self.FA.kc()["fusion"]).to(dev)
         tok_final = ops.pack_token_program(self.joint_num, cross=(self.crossTR.decoder[-1].state_dict(), ""),
                                            enc=(self.final_TR.state_dict(), "")).to(dev)
-        return dict(tok_init=tok_init, tok_final=tok_final, wa_packed=wa_packed, ds_wmat=ds_wmat, ds_wvec=ds_wvec, W_pcl=torch.cat([Wf, Wx, Wp], 1).contiguous(), b_pcl=(bf + bx + bp).contiguous(), W_rgb=Wr, b_rgb=br,
-                    W_joint=torch.cat([Wj, Wjx], 1).contiguous(), b_joint=(bj + bjx).contiguous(), pe_wmat=pe_wmat, pe_wvec=pe_wvec)
+        return dict(tok_init=tok_init, tok_final=tok_final, wa_packed=wa_packed, ds_wmat=ds_wmat, ds_wvec=ds_wvec, pe_wmat=pe_wmat,
+                    pe_wvec=pe_wvec)
 
     def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
-                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None, point_order=None):
+                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None, rgb_planes=None, point_order=None):
+        """model.py:287-351.  Five launches, all hand-written split-precision tcgen05 kernels (fp32-class results for bf16 AND
+        fp32 feature maps -- an fp32 map is carried as two bf16 planes):
+            point stage (K4b + K3 + embeddings + softmax partials) -> DESA -> [fusion conv + init_TR] -> K5 -> [crossTR + final_TR]
+        `featT` / `rgb_planes`: the repacked maps / the rgb map's planes when the caller (KPFusion.forward_path) already made them
+        for both blocks."""
+        _inference_only(self, img_feat, img_feature_rgb, joint_xyz, img_offset)
         k = self.kc()
         B, N, _ = pcl.shape
         C, H = img_feat.shape[1], img_feat.shape[2]
         J = self.joint_num
-        prec = self.precision if self.precision != "auto" else ("bf16" if img_feat.dtype == torch.bfloat16 else "fp32")
+        if not (N % 64 == 0 and J <= 21 and self.FA.kc()["scales"] is not None and len(set(self.FA.S)) == 1 and self.FA.scale_num == 3
+                and C == 128 and (H * H) % 128 == 0):
+            raise NotImplementedError("Block_KPFusion kernels: N % 64 == 0 points, J <= 21 joints, 128-channel maps with H*H % 128 == 0, "
+                                      "three DESA scales sharing nsample (no fallback path)")
         pcl = pcl.float().contiguous()
         joint_xyz = joint_xyz.detach().float().contiguous()
-        fused = (prec == "bf16" and N % 128 == 0 and J <= 21 and self.FA.kc()["scales"] is not None and len(set(self.FA.S)) == 1
-                 and self.FA.scale_num == 3 and img_feature_rgb.dtype == torch.bfloat16 and C == 128 and (H * H) % 128 == 0)
-        if fused:
-            # tensor-core path, five launches per block:
-            #   point stage (K4b + K3 + embeddings + softmax partials) -> DESA -> [fusion conv + init_TR] -> K5 -> [crossTR + final_TR]
-            if featT is None:
-                featT = ops.repack_features(img_feat, img_feature_rgb, img_offset[:, J * 4:])
-            e, p_acc, p_ms = ops.point_embed(featT, pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8,
-                                             order=point_order)
-            part, jf = ops.desa_fused(e, p_acc, p_ms, pcl, joint_xyz, k["ds_wmat"], k["ds_wvec"], self.FA.radius, self.FA.S[0])
-            outfeature_init_TR, refined_3d_joints, _ = ops.token_stack(k["tok_init"], desa=part, jf=jf)        # model.py:203, :330
-            spatial_weight_loss, img_feat_j = ops.spatial_aggregate_tc(
-                img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, k["wa_packed"], self.atten_spatial.bias,
-                self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias, prev=updated_2d_feature,
-                img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)             # model.py:334-344
-            _, refined_2d_joints, _ = ops.token_stack(k["tok_final"], x=img_feat_j, y=outfeature_init_TR, r3d=refined_3d_joints,
-                                                      want_tokens=False)                                      # model.py:347-349
-            return refined_3d_joints, refined_2d_joints, img_feat_j, spatial_weight_loss, None
-        # general path (fp32 features, or shapes the fused kernels do not cover): per-row kernels + library GEMMs for the
-        # GEMM-shaped next-row pieces
-        # RGB keypoint aggregation (model.py:295-306): K4b + K3
-        pcl_offset = ops.pcl_joint2offset(joint_xyz, pcl, 0.8)
-        pcl_feat = ops.gather_taps(img_feat, pcl_index, pcl_closeness).float()
-        pcl_feat_rgb = ops.gather_taps(img_feature_rgb, pcl_index, pcl_closeness).float()
-        pcl_weight = ops.gather_taps(img_offset[:, J * 4:], pcl_index, pcl_closeness).float()
-        # decoupled generation of RGB-D point features (model.py:312-317): folded Conv1d+BN embeddings
-        e = F.relu(F.linear(torch.cat((pcl_feat, pcl, pcl_weight, pcl_offset), dim=-1), k["W_pcl"], k["b_pcl"]))
-        e = F.relu(e + F.linear(pcl_feat_rgb, k["W_rgb"], k["b_rgb"]))
-        attention = F.softmax(pcl_weight.permute(0, 2, 1), dim=-1)                       # model.py:319
-        joint_feat = torch.matmul(attention, e)                                          # model.py:320
-        joint_feat = F.relu(F.linear(torch.cat((joint_feat, joint_xyz), dim=-1), k["W_joint"], k["b_joint"]))  # :323-325
-        joint_feat = self.FA(e, joint_feat, pcl, joint_xyz)                              # model.py:327
-        outfeature_init_TR, refined_3d_joints = self.init_TR(joint_feat, precision=prec)  # model.py:330
-        # depth keypoint aggregation (model.py:334-344): K4c + K5 fused
-        if prec == "bf16" and img_feature_rgb.dtype == torch.bfloat16 and C == 128 and (H * H) % 128 == 0 and J <= 32:
-            spatial_weight_loss, img_feat_j = ops.spatial_aggregate_tc(
-                img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, k["wa_packed"], self.atten_spatial.bias,
-                self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias, prev=updated_2d_feature,
-                img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)
-        else:
-            spatial_weight_loss, img_feat_j = ops.spatial_aggregate(
-                img_feature_rgb, refined_3d_joints, img_down, center, M, cube, cam_para, self.atten_spatial.weight,
-                self.atten_spatial.bias, self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias,
-                prev=updated_2d_feature, img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)
-        # inter-modal keypoint feature interaction (model.py:347-349): K6 writes straight into final_TR's input
-        tr_in = torch.empty(B, J, 3 + self.dim, device=pcl.device, dtype=torch.float32)
-        tr_in[:, :, :3] = refined_3d_joints
-        self.crossTR(img_feat_j, outfeature_init_TR, out_jc=tr_in, out_jc_c0=3, want_cj=False, precision=prec)
-        _, refined_2d_joints = self.final_TR(tr_in, precision=prec)
+        if featT is None:
+            featT = ops.repack_features(img_feat, img_feature_rgb, img_offset[:, J * 4:])
+        if rgb_planes is None:
+            rgb_planes = (img_feature_rgb, None) if img_feature_rgb.dtype == torch.bfloat16 else ops.split_map(img_feature_rgb)
+        e, p_acc, p_ms = ops.point_embed(featT, pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8,
+                                         order=point_order)                                               # model.py:295-320
+        part, jf = ops.desa_fused(e, p_acc, p_ms, pcl, joint_xyz, k["ds_wmat"], k["ds_wvec"], self.FA.radius, self.FA.S[0])   # :323-327
+        outfeature_init_TR, refined_3d_joints, _ = ops.token_stack(k["tok_init"], desa=part, jf=jf)        # model.py:203, :330
+        spatial_weight_loss, img_feat_j = ops.spatial_aggregate_tc(
+            rgb_planes, refined_3d_joints, img_down, center, M, cube, cam_para, k["wa_packed"], self.atten_spatial.bias,
+            self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias, prev=updated_2d_feature,
+            img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)             # model.py:334-344
+        _, refined_2d_joints, _ = ops.token_stack(k["tok_final"], x=img_feat_j, y=outfeature_init_TR, r3d=refined_3d_joints,
+                                                  want_tokens=False)                                      # model.py:347-349
         return refined_3d_joints, refined_2d_joints, img_feat_j, spatial_weight_loss, None
 
 
@@ -457,14 +442,15 @@ class KPFusion(nn.Module):
                                                         want_i64=False, want_i32=True, order=order)     # :411
         updated_2d_feature = [None] * (self.num_stages + 1)
         spatial_weight = [None] * self.num_stages
-        featT = None
-        if img_feat.dtype == torch.bfloat16 and self.block1.precision in ("auto", "bf16"):
-            featT = ops.repack_features(img_feat, img_feat_rgb, img_offset[:, J * 4:])   # shared by both blocks
+        # shared by both blocks: the channels-last repack of the three maps (one plane for bf16 maps, two for fp32 maps) and the
+        # rgb map's NCHW plane(s) for K5
+        featT = ops.repack_features(img_feat, img_feat_rgb, img_offset[:, J * 4:])
+        rgb_planes = (img_feat_rgb.contiguous(), None) if img_feat_rgb.dtype == torch.bfloat16 else ops.split_map(img_feat_rgb)
         for i in range(self.num_stages):                                                                 # :417-424
             block = getattr(self, f"block{i + 1}")
             r3d, r2d, updated_2d_feature[i + 1], spatial_weight[i], _ = block(
                 img_feat, img_feat_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature[i], loader, img_down,
-                center, M, cube, cam_para, writer, ii, featT=featT, point_order=order)
+                center, M, cube, cam_para, writer, ii, featT=featT, rgb_planes=rgb_planes, point_order=order)
             result.append(r3d)
             result.append(r2d)
             joint_xyz = r2d

@@ -91,26 +91,32 @@ class TransformerDecoderLayer(nn.Module):
         self._wpack = None
         self._tc = None
 
+    def _key(self, J):   # rebuilt after ANY weight change, however it was made (see model._KernelCache)
+        return (J,) + tuple((t.data_ptr(), t._version) for t in self.parameters())
+
     def packed_tc(self, J):
-        dev = self.linear1.weight.device
-        if self._tc is None or self._tc.wmat.device != dev or self._tc.J != J:
-            self._tc = ops.pack_token_program(J, cross=(self.state_dict(), ""), C=self.d_model).to(dev)
-        return self._tc
+        key = self._key(J)
+        if self._tc is None or self._tc[0] != key:
+            self._tc = (key, ops.pack_token_program(J, cross=(self.state_dict(), ""), C=self.d_model).to(self.linear1.weight.device))
+        return self._tc[1]
 
     def packed(self, J):
-        if self._wpack is None or self._wpack.device != self.linear1.weight.device:
-            sd = {k: v for k, v in self.state_dict().items()}
-            self._wpack = ops.pack_decoder_layer(sd, "", J, self.d_model)
-        return self._wpack
+        key = self._key(J)
+        if self._wpack is None or self._wpack[0] != key:
+            self._wpack = (key, ops.pack_decoder_layer(dict(self.state_dict()), "", J, self.d_model))
+        return self._wpack[1]
 
     def forward(self, query, key, query_pos=None, key_pos=None, attn_mask=None, out_jc=None, out_jc_c0=0, want_cj=True,
                 precision="fp32"):
         """query [B,J,C], key [B,J,C] -> [B,C,J] (transfusion_head.py:132-173, cross_only, index position embeddings).
-        precision "fp32": CUDA-core kernel (csrc/cross_attn.cu); "bf16": tcgen05 kernel (csrc/token_stack.cu)."""
+        precision "fp32": CUDA-core kernel (csrc/cross_attn.cu); "tc": split-precision tcgen05 kernel (csrc/token_stack.cu, the one
+        Block_KPFusion fuses with final_TR) -- both hand-written, both fp32-class."""
+        if self.training or (torch.is_grad_enabled() and (query.requires_grad or key.requires_grad)):
+            raise RuntimeError("TransformerDecoderLayer: inference only (no autograd through the B200 kernels); use .eval() and torch.no_grad()")
         if not self.cross_only or attn_mask is not None or self.self_posembed is None or self.cross_posembed is None:
             raise NotImplementedError("only the cross_only configuration updatedDecoder builds (transfusion_head.py:652-661)")
         J = query.shape[1]
-        if precision == "bf16" and self.d_model == 128 and self.nhead == 4 and J <= 32:
+        if precision in ("tc", "bf16") and self.d_model == 128 and self.nhead == 4 and J <= 32 and self.dim_feedforward in (16, 128):
             return ops.token_stack(self.packed_tc(J), x=query, y=key, out_jc=out_jc, out_jc_c0=out_jc_c0, want_cj=want_cj)[2]
         return ops.cross_decoder_layer(query, key, self.packed(J), self.nhead, self.dim_feedforward, out_jc, out_jc_c0, want_cj)
 
@@ -144,14 +150,6 @@ class updatedDecoder(nn.Module):
         for layer in self.decoder:
             layer._wpack = None
             layer._tc = None
-
-    def _apply(self, fn, *a, **k):
-        self.invalidate()
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self.invalidate()
-        return super().load_state_dict(*a, **k)
 
     def forward(self, anchor_feats, img_feats, out_jc=None, out_jc_c0=0, want_cj=True, precision="fp32"):
         """anchor_feats [B,J,C] (queries), img_feats [B,J,C] (keys) -> [B,C,J].  Every layer of the reference gets the

@@ -1,4 +1,4 @@
-"""Tensor-level wrappers over the C ABI (include/kpf_b200.h) + `torch.library` custom-op registration.
+"""Tensor-level wrappers over the C ABI (include/kpf_b200.h); `custom_ops.py` registers them with `torch.library`.
 
 Each function validates shapes/dtypes/devices in Python, allocates outputs with torch (PyTorch owns all memory) and
 launches the kernel on `torch.cuda.current_stream()`.  There is NO fallback: non-CUDA tensors raise.
@@ -14,12 +14,14 @@ F32, BF16 = 0, 1
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+_arg_devices = set()   # devices of the tensors whose pointers were taken since the last launch
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    if t is None:
+        return None
+    _arg_devices.add(t.device)
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _spatial_numel(t):
@@ -62,8 +64,18 @@ _KERNELS_PER_CALL = {"kpf_desa_fused": 2}   # entry points that launch more than
 
 
 def _call(name, *args):
+    """Launch on the device the ARGUMENTS live on (not the thread's current device): `net.to('cuda:1')` without a
+    `torch.cuda.set_device(1)` must work like every stock torch op; tensors on different devices are an error."""
     global _launches
-    rc = getattr(_lib.lib(), name)(*args, _stream())
+    devs = set(_arg_devices)
+    _arg_devices.clear()
+    if len(devs) > 1:
+        raise RuntimeError(f"{name}: arguments live on different devices {sorted(str(d) for d in devs)}")
+    dev = devs.pop() if devs else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda":
+        raise RuntimeError("keypointfusion_b200 kernels need CUDA tensors (no CPU fallback exists for this path)")
+    with torch.cuda.device(dev):
+        rc = getattr(_lib.lib(), name)(*args, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, name)
     _launches += _KERNELS_PER_CALL.get(name, 1)
 
@@ -249,6 +261,8 @@ def spatial_aggregate(feat_rgb, joints, img, center, M, cube, cam, Wa, ba, weigh
     J = joints.shape[1]
     d, bs, rs, cs, fs = _depth_view(img, fs)
     Wa, ba, weight_dis, fc_w, fc_b = _f32(Wa.reshape(J, C + J)), _f32(ba), _f32(weight_dis), _f32(fc_w.reshape(-1)), _f32(fc_b)
+    if fc_w.numel() != fs * fs or Wa.shape != (J, C + J):
+        raise ValueError(f"atten_spatial / fc_spatial2joint_feature shapes {tuple(Wa.shape)}, {fc_w.numel()} do not match a {C}-channel {fs}x{fs} map")
     prev = _f32(prev) if prev is not None else None
     dev = feat_rgb.device
     sw = torch.empty(B, J, fs, fs, device=dev, dtype=torch.float32)
@@ -501,7 +515,7 @@ def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=Tr
     r3d = _f32(r3d) if r3d is not None else None
     desa = _f32(desa) if desa is not None else None
     jf = _f32(jf) if jf is not None else None
-    tokens = torch.empty(B, J, 128, device=dev, dtype=torch.float32) if (want_tokens and pk.L > 0) else None
+    tokens = torch.empty(B, J, 128, device=dev, dtype=torch.float32) if (want_tokens and (pk.L > 0 or (pk.pre and not pk.cross))) else None
     pred = torch.empty(B, J, 3, device=dev, dtype=torch.float32) if pk.L > 0 else None
     out_cj = torch.empty(B, 128, J, device=dev, dtype=torch.float32) if (want_cj and pk.L == 0) else None
     stride = out_jc.shape[-1] if out_jc is not None else 0
@@ -522,7 +536,8 @@ def sm_count(device):
 
 
 def repack_features(img_feat, img_feat_rgb, weight_map):
-    """NCHW maps -> channels-last bf16 rows [B,HW,288] (128 depth-branch | 128 rgb-branch | J weight channels padded to 32)."""
+    """NCHW maps -> channels-last bf16 rows [B,HW,288] (128 depth-branch | 128 rgb-branch | J weight channels padded to 32).
+    Returns (hi, lo): bf16 maps are exact in one plane (lo = None); fp32 maps are carried as two bf16 planes hi + lo."""
     _need_cuda(img_feat, img_feat_rgb, weight_map)
     dt = img_feat.dtype if img_feat.dtype in _DT else torch.float32
     f_d, f_rgb = img_feat.to(dt).contiguous(), img_feat_rgb.to(dt).contiguous()
@@ -533,14 +548,16 @@ def repack_features(img_feat, img_feat_rgb, weight_map):
     if B == 0 or not w[0].reshape(J, HW).is_contiguous():   # a channel slice of a larger map is fine as long as each sample is dense
         w = w.contiguous()
     out = torch.empty(B, HW, 288, device=f_d.device, dtype=torch.bfloat16)
-    _call("kpf_repack_features", _p(f_d), _p(f_rgb), _p(w), w.stride(0), _DT[dt], B, C, J, HW, _p(out))
-    return out
+    lo = torch.empty_like(out) if dt == torch.float32 else None
+    _call("kpf_repack_features", _p(f_d), _p(f_rgb), _p(w), w.stride(0), _DT[dt], B, C, J, HW, _p(out), _p(lo))
+    return out, lo
 
 
-def pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, J):
-    """BN-folded point-embedding weights (pcl_feat_emb, pcl_xyz_emb, pcl_pose_emb, pcl_feat_emb_RGB) -> (wmat bf16, wvec f32).
+def pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, J, fmt=None):
+    """BN-folded point-embedding weights (pcl_feat_emb, pcl_xyz_emb, pcl_pose_emb, pcl_feat_emb_RGB) -> (wmat 16-bit planes, wvec f32).
     A1 column order: [depth feats 128 | weight map J (+pad to 32) | (unit offset xyz, closeness) per joint, xyz 3 (+pad to 96)]
-    (the reference's pcl_pose_emb input is [weight J | unit offsets 3J joint-major | closeness J], model.py:312-317)."""
+    (the reference's pcl_pose_emb input is [weight J | unit offsets 3J joint-major | closeness J], model.py:312-317).
+    wmat = canonical W1 [128,256] hi | lo, W2 [128,128] hi | lo (csrc/point_embed.cu keeps them in tensor memory)."""
     C = Wf.shape[0]
     W1 = Wf.new_zeros(C, 256)
     W1[:, :128] = Wf
@@ -549,35 +566,58 @@ def pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, J):
         W1[:, 160 + 4 * j:160 + 4 * j + 3] = Wp[:, J + 3 * j:J + 3 * j + 3]
         W1[:, 160 + 4 * j + 3] = Wp[:, 4 * J + j]
     W1[:, 160 + 4 * J:160 + 4 * J + 3] = Wx
-    wmat = torch.cat([_canon(W1[:, :128]), _canon(W1[:, 128:]), _canon(Wr)]).contiguous()
+    wmat = torch.cat([_canon(W1, fmt), _canon(Wr, fmt)]).contiguous()
     wvec = torch.cat([(bf + bx + bp).float(), br.float()]).contiguous()
     return wmat, wvec
 
 
-def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg=None, order=None):
-    """-> e [B,N,128] bf16, part_acc [B,T,128,32] f32, part_ms [B,T,2,32] f32  (T = N/128)."""
-    _need_cuda(featT, idx32, clos, pcl, joint)
+E_ROW = 256   # 16-bit elements per point-feature row: [hi 128 | lo 128]
+
+
+def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg=None, order=None, fmt=None):
+    """featT = (hi, lo | None) from repack_features.
+    -> e [B,N,256] int16 (rows [hi 128 | lo 128] in the split format), part_acc [B,T,128,32] f32, part_ms [B,T,2,32] f32  (T = N/64)."""
+    fmt = SPLIT_FMT if fmt is None else fmt
+    feat_hi, feat_lo = featT if isinstance(featT, (tuple, list)) else (featT, None)
+    _need_cuda(feat_hi, idx32, clos, pcl, joint)
     pcl, joint, clos = _f32(pcl), _f32(joint), _f32(clos)
     idx32 = idx32.to(torch.int32).contiguous()
     B, N, _ = pcl.shape
     J = joint.shape[1]
-    HW = featT.shape[1]
-    T = N // 128
+    HW = feat_hi.shape[1]
+    if N % 64 or J > 21 or feat_hi.shape[2] != 288:
+        raise NotImplementedError("the point stage covers N % 64 == 0 points, J <= 21 joints and 128-channel maps (no fallback path)")
+    T = N // 64
     dev = pcl.device
     # 32 spare rows per sample behind the points: kpf_desa_fused appends the joints' own feature rows there (they are members
-    # N .. N+J-1 of DESA's grouped point set); the returned tensor is the [B,N,128] view of the points
-    e_full = torch.empty(B, N + 32, 128, device=dev, dtype=torch.bfloat16)
+    # N .. N+J-1 of DESA's grouped point set); the returned tensor is the [B,N,256] view of the points
+    e_full = torch.empty(B, N + 32, E_ROW, device=dev, dtype=torch.int16)
     e = e_full[:, :N]
     acc = torch.empty(B, T, 128, 32, device=dev, dtype=torch.float32)
     ms = torch.empty(B, T, 2, 32, device=dev, dtype=torch.float32)
-    _call("kpf_point_embed", _p(featT), _p(idx32), _p(clos), _p(pcl), _p(joint), _p(order), _p(wmat), _p(wvec), B, N, J, HW,
-          float(kernel_size), _p(e), e.stride(0),
-          _p(acc), _p(ms), sm_count(dev), _p(dbg))
+    _call("kpf_point_embed", _p(feat_hi), _p(feat_lo), _p(idx32), _p(clos), _p(pcl), _p(joint), _p(order), _p(wmat), _p(wvec), B, N, J, HW,
+          float(kernel_size), fmt, _p(e), e.stride(0), _p(acc), _p(ms), sm_count(dev), _p(dbg))
     return e, acc, ms
 
 
+def e_to_float(e, fmt=None):
+    """[B,N,256] int16 point-feature rows -> [B,N,128] f32 (hi + lo); test / inspection helper."""
+    dt = _fmt_dtype(SPLIT_FMT if fmt is None else fmt)
+    return e[..., :128].contiguous().view(dt).float() + e[..., 128:].contiguous().view(dt).float()
+
+
+def e_from_float(x, fmt=None, spare_rows=32):
+    """[B,N,128] f32 -> [B,N,256] int16 rows (a view of a [B,N+spare_rows,256] buffer, as kpf_desa_fused wants)."""
+    hi, lo = split_planes(x, fmt)
+    B, N, _ = x.shape
+    full = torch.zeros(B, N + spare_rows, E_ROW, device=x.device, dtype=torch.int16)
+    full[:, :N, :128] = hi.view(torch.int16)
+    full[:, :N, 128:] = lo.view(torch.int16)
+    return full[:, :N]
+
+
 def combine_point_partials(acc, ms, J):
-    """flash-style combination of the per-tile softmax partials -> joint_agg [B,J,128] (torch glue used by tests / fp32 path)."""
+    """flash-style combination of the per-tile softmax partials -> joint_agg [B,J,128] (torch glue used by tests)."""
     m_t, s_t = ms[:, :, 0, :J], ms[:, :, 1, :J]                      # B T J
     m = m_t.max(dim=1, keepdim=True)[0]
     sc = torch.exp(m_t - m)                                          # B T J
@@ -587,22 +627,24 @@ def combine_point_partials(acc, ms, J):
 
 
 # ------------------------------------------------------------------------------------------------ fused DESA
-def pack_desa(Wj, bj, Wjx, bjx, scales):
+def pack_desa(Wj, bj, Wjx, bjx, scales, fmt=None):
     """Wj [128,128], Wjx [128,3] (BN-folded joint_feat_emb / joint_xyz_emb); scales: list of (Wf0, bf0, Wl0, bl0, W2, b2), all BN-folded.
-    -> (wmat bf16, wvec f32) for kpf_desa_fused."""
-    mats = [_canon(Wj)]
+    -> (wmat 16-bit canonical planes: Wj hi | lo ; per scale W1 main hi | lo, W1 tail hi | lo, W2 hi | lo ; wvec f32) for kpf_desa_fused."""
+    mats = [_canon(Wj, fmt)]
     wx = Wj.new_zeros(128, 4)
     wx[:, :3] = Wjx
     vecs = [(bj + bjx).float(), wx.reshape(-1).float()]
     for Wf0, bf0, Wl0, bl0, W2, b2 in scales:
         tail = Wf0.new_zeros(128, 16)
         tail[:, :3] = Wl0
-        mats += [_canon(Wf0), _canon(tail), _canon(W2)]
+        mats += [_canon(Wf0, fmt), _canon(tail, fmt), _canon(W2, fmt)]
         vecs += [(bf0 + bl0).float(), b2.float()]
     return torch.cat(mats).contiguous(), torch.cat(vecs).contiguous()
 
 
-def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, dbg=None):
+def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, dbg=None, fmt=None, jf_in=None, keep_scratch=None):
+    """e: [B,N,256] int16 rows from point_embed (or e_from_float).  jf_in [B,J,128]: the joints' features are given (no embedding)."""
+    fmt = SPLIT_FMT if fmt is None else fmt
     pcl, joint = _f32(pcl), _f32(joint)
     B, N, _ = pcl.shape
     J = joint.shape[1]
@@ -610,14 +652,18 @@ def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, db
     r = list(radius) + [0.0] * (4 - S)
     part = torch.empty(B, S, J, 128, device=pcl.device, dtype=torch.float32)
     jf = torch.empty(B, J, 128, device=pcl.device, dtype=torch.float32)
-    if e.stride(0) < (N + J) * 128 or e.stride(1) != 128 or e.stride(2) != 1:   # not from ops.point_embed: make room for the joint rows
-        e_full = torch.empty(B, N + 32, 128, device=pcl.device, dtype=torch.bfloat16)
+    assert e.dtype == torch.int16 and e.shape[-1] == E_ROW
+    if e.stride(0) < (N + J) * E_ROW or e.stride(1) != E_ROW or e.stride(2) != 1:   # not from ops.point_embed: make room for the joint rows
+        e_full = torch.empty(B, N + 32, E_ROW, device=pcl.device, dtype=torch.int16)
         e_full[:, :N].copy_(e)
         e = e_full[:, :N]
     # workspace between the two kernels: W1_s jf terms fp32 [B,S,J,128], padded xyz table [B,N+32,4] f32, ball-query indices u16
     scratch = torch.empty(B * S * J * 128 * 4 + B * (N + 32) * 16 + B * S * J * nsample * 2, device=pcl.device, dtype=torch.uint8)
     _call("kpf_desa_fused", _p(e), e.stride(0), _p(part_acc), _p(part_ms), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, S, nsample, float(r[0]),
-          float(r[1]), float(r[2]), float(r[3]), _p(part), _p(jf), _p(scratch), sm_count(pcl.device), _p(dbg))
+          float(r[1]), float(r[2]), float(r[3]), fmt, _p(_f32(jf_in) if jf_in is not None else None), _p(part), _p(jf), _p(scratch),
+          sm_count(pcl.device), _p(dbg))
+    if keep_scratch is not None:   # tests read the ball-query indices back out of the hand-over workspace
+        keep_scratch["buf"] = scratch
     return part, jf
 
 
@@ -634,26 +680,58 @@ def _zero_counters(n, device):
     return c
 
 
-def pack_spatial_wa(Wa, J, C=128):
-    """atten_spatial.weight [J, C+J(,1,1)] -> canonical bf16 B operands: Wa[:, :C] as [16][32][8], Wa[:, C:] as [4][32][8]."""
+def split_planes3_bf16(W):
+    """fp32 -> three bf16 planes (hi + mid + lo = W to 2^-24): the GEMM partner of a bf16 feature-map operand (both operands of an
+    MMA share one format, csrc/umma_split.cuh)."""
+    W = W.detach().float()
+    hi = W.bfloat16()
+    r = W - hi.float()
+    mid = r.bfloat16()
+    lo = (r - mid.float()).bfloat16()
+    return hi, mid, lo
+
+
+def pack_spatial_wa(Wa, J, C=128, fmt=None):
+    """atten_spatial.weight [J, C+J(,1,1)] -> canonical 16-bit B operand planes: Wa[:, :C] as [16][32][8] x 3 bf16 planes (it multiplies the
+    bf16 feature map), Wa[:, C:] as [4][32][8] hi | lo in the split format (it multiplies the computed heat map)."""
     Wa = Wa.detach().float().reshape(J, C + J)
     main = Wa.new_zeros(32, C)
     main[:J] = Wa[:, :C]
     hm = Wa.new_zeros(32, 32)
     hm[:J, :J] = Wa[:, C:]
-    return torch.cat([_canon(main), _canon(hm)]).contiguous()
+    return torch.cat([_canon16(p_) for p_ in split_planes3_bf16(main)] + [_canon(hm, fmt)]).contiguous()
+
+
+def split_map(x):
+    """fp32 tensor -> (hi, lo) bf16 planes of the same shape (kpf_split_planes)."""
+    x = _f32(x)
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    n = x.numel()
+    if n % 4:
+        raise NotImplementedError("split_map: element count must be a multiple of 4")
+    _call("kpf_split_planes", _p(x), n, _p(hi), _p(lo))
+    return hi, lo
 
 
 def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed, ba, weight_dis, fc_w, fc_b, prev=None, img_size=128,
-                         flip=1.0, hm_std=0.8, hm_sigma=1.0, gamma=10.0, dbg=None):
+                         flip=1.0, hm_std=0.8, hm_sigma=1.0, gamma=10.0, dbg=None, fmt=None):
+    """feat_rgb: bf16 [B,128,fs,fs], or a (hi, lo) pair of bf16 planes (split_map of an fp32 map)."""
+    fmt = SPLIT_FMT if fmt is None else fmt
+    feat_rgb, feat_lo = feat_rgb if isinstance(feat_rgb, (tuple, list)) else (feat_rgb, None)
     _need_cuda(feat_rgb)
-    assert feat_rgb.dtype == torch.bfloat16
+    assert feat_rgb.dtype == torch.bfloat16 and (feat_lo is None or feat_lo.dtype == torch.bfloat16)
     feat_rgb = feat_rgb.contiguous()
+    feat_lo = feat_lo.contiguous() if feat_lo is not None else None
     B, C, fs, _ = feat_rgb.shape
     joints, center, M, cube, cam = _f32(joints), _f32(center), _f32(M), _f32(cube), _f32(cam)
     J = joints.shape[1]
     d, bs, rs, cs, fs = _depth_view(img, fs)
     ba, weight_dis, fc_w, fc_b = _f32(ba), _f32(weight_dis), _f32(fc_w.reshape(-1)), _f32(fc_b)
+    if fc_w.numel() != fs * fs:
+        raise ValueError(f"fc_spatial2joint_feature has {fc_w.numel()} inputs but the feature map has {fs}x{fs} cells (model.py:264 pins 32x32)")
+    if C != 128 or (fs * fs) % 128 or J > 32:
+        raise NotImplementedError("spatial aggregation covers 128-channel maps with fs*fs % 128 == 0 and J <= 32 (no fallback path)")
     prev = _f32(prev) if prev is not None else None
     sw = torch.empty(B, J, fs, fs, device=feat_rgb.device, dtype=torch.float32)
     fj = torch.empty(B, J, C, device=feat_rgb.device, dtype=torch.float32)
@@ -663,9 +741,9 @@ def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed,
     split = next((s_ for s_ in (8, 4, 2) if T % s_ == 0 and B * s_ <= sm_count(feat_rgb.device)), 1)
     scratch = torch.empty(B, split, 128, 32, device=feat_rgb.device, dtype=torch.float32) if split > 1 else None
     counters = _zero_counters(B, feat_rgb.device) if split > 1 else None
-    _call("kpf_spatial_aggregate_tc", _p(feat_rgb), _p(joints), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam), _p(wa_packed),
-          _p(ba), _p(weight_dis), _p(fc_w), _p(fc_b), _p(prev), B, C, J, fs, float(img_size), float(flip), float(hm_std), float(hm_sigma),
-          float(gamma), _p(sw), _p(fj), _p(scratch), _p(counters), split, _p(dbg))
+    _call("kpf_spatial_aggregate_tc", _p(feat_rgb), _p(feat_lo), _p(joints), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam),
+          _p(wa_packed), _p(ba), _p(weight_dis), _p(fc_w), _p(fc_b), _p(prev), B, C, J, fs, float(img_size), float(flip), float(hm_std),
+          float(hm_sigma), float(gamma), fmt, _p(sw), _p(fj), _p(scratch), _p(counters), split, _p(dbg))
     return sw, fj
 
 

@@ -481,24 +481,28 @@ def _bn2d(p, prefix, x):  # x [..., C]
     return (x - p[prefix + "running_mean"]) * s + p[prefix + "bias"]
 
 
-def ball_query(xyz, centers, radius, nsample):
+def ball_query(xyz, centers, radius, nsample, return_counts=False):
     """pointnet2_ops 3.0.0 ball_query: first `nsample` indices (ascending) with d2 < r*r, rest = first hit,
-    zero-initialised.  d2 = ((dx*dx+dy*dy)+dz*dz) fp32, r2 = fl32(r)*fl32(r).  numpy, exact."""
+    zero-initialised.  d2 = ((dx*dx+dy*dy)+dz*dz) fp32, r2 = fl32(r)*fl32(r).  numpy, exact.
+    return_counts: also the number of points inside each ball (before truncation to nsample), [B,J]."""
     xyz = np.asarray(xyz, f32)
     centers = np.asarray(centers, f32)
     B, N, _ = xyz.shape
     J = centers.shape[1]
     r2 = f32(radius) * f32(radius)
     idx = np.zeros((B, J, nsample), np.int32)
+    counts = np.zeros((B, J), np.int64)
     for b in range(B):
         d = centers[b][:, None, :] - xyz[b][None, :, :]
         d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
         for j in range(J):
-            hits = np.flatnonzero(d2[j] < r2)[:nsample]
+            allhits = np.flatnonzero(d2[j] < r2)
+            counts[b, j] = allhits.size
+            hits = allhits[:nsample]
             if hits.size:
                 idx[b, j, :] = hits[0]
                 idx[b, j, :hits.size] = hits
-    return idx
+    return (idx, counts) if return_counts else idx
 
 
 def desa(p, prefix, pcl_feat, node_feat, pcl_xyz, node_xyz, radius=(0.1, 0.2, 0.4), nsample=(64, 64, 64)):

@@ -125,16 +125,18 @@ def test_helper_objects(golden, golden_inputs):
     assert pcl.shape == (2, 1024, 3) and np.array_equal(pu.last_count.cpu().numpy(), golden["getpcl_counts"])
 
 
-def test_fusion_path_bf16_tensor_core(net, path_params, capsys):
-    """bf16 feature maps select the tcgen05 token stacks.  Bars: features <= 1e-2 relative (RMS); the joints' error is
-    measured and reported -- with O(1)-gain random weights bf16 operand rounding alone moves joints by ~0.1-0.3 mm, so the
-    0.05 mm bar is an fp32-path bar (test_fusion_path_end_to_end)."""
+@pytest.mark.parametrize("maps", ["bf16", "fp32"])
+def test_fusion_path_tensor_core_meets_joint_bar(net, path_params, capsys, maps):
+    """The benchmarked configuration (BASELINE config 2: bf16 feature maps) and fp32 maps, end to end on the hand-written
+    split-precision tcgen05 kernels, vs the oracle on the SAME maps.  north_star bars: every one of the four joint sets
+    <= 0.05 mm mean error and <= 1e-2 relative (here: two orders better), spatial weights <= 1e-3 relative."""
     from keypointfusion_b200.dataloader.loader import loader
     from keypointfusion_b200 import ops
-    inp = synth.make_inputs(4, 128, 21, 128, seed=33, bf16_round=True)
+    inp = synth.make_inputs(4, 128, 21, 128, seed=33, bf16_round=maps == "bf16")
     c = {k: v.to(DEV) for k, v in inp.items()}
-    for k in ("img_feat", "img_feat_rgb", "img_offset"):
-        c[k] = c[k].bfloat16()
+    if maps == "bf16":
+        for k in ("img_feat", "img_feat_rgb", "img_offset"):
+            c[k] = c[k].bfloat16()
     with torch.no_grad():
         pcl, _ = ops.getpcl(c["img"], c["center"], c["cube"], c["M"], c["cam"], seed=4)
         res, sws, _ = net.forward_path(c["img_offset"], c["img_feat"], None, c["img_feat_rgb"], c["img"], pcl, loader(img_size=128),
@@ -144,17 +146,13 @@ def test_fusion_path_bf16_tensor_core(net, path_params, capsys):
     errs = [mm_err(res[2 + k], ores[k].numpy()) for k in range(4)]
     rels = [float((res[2 + k].float().cpu() - ores[k]).norm() / ores[k].norm()) for k in range(4)]
     with capsys.disabled():
-        print("\n[bf16 path] joints r3d_1, r2d_1, r3d_2, r2d_2: mean error mm", ["%.3f" % e for e in errs], "relative", ["%.4f" % r for r in rels])
+        print(f"\n[{maps} maps] joints r3d_1, r2d_1, r3d_2, r2d_2: mean error mm", ["%.5f" % e for e in errs], "relative", ["%.2e" % r for r in rels])
     for k in range(2):
         a, b = sws[k].float().cpu(), osw[k]
-        assert float((a - b).norm() / b.norm()) < 1e-2
-    # stage-1 joints come straight out of bf16 features: 1e-2 relative class.  Stage 2 re-enters thresholded geometry (DESA ball
-    # membership, closeness masks) with stage-1's joints; the ORACLE itself amplifies a 1 % perturbation of those joints to
-    # ~12 % / ~7 % of r3d_2 / r2d_2 with these O(1)-gain random weights (measured, DESIGN.md "bf16 error budget"), so the
-    # end-to-end stage-2 bound is 12x the stage-1 error, and block 2 is pinned separately below on the oracle's stage-1 outputs.
-    assert max(rels[:2]) < 2e-2, rels
-    assert max(rels[2:]) < 12 * max(rels[:2]), rels
-    t1 = ex["block1"]
+        assert float((a - b).norm() / b.norm()) < 1e-3
+    assert max(errs) <= 0.05, errs          # north_star: final joint positions within 0.05 mm mean error -- ALL four sets
+    assert max(rels) <= 1e-3, rels
+    # block 2 in isolation on the oracle's stage-1 outputs (pins block 2 without stage 1's error in its inputs)
     with torch.no_grad():
         (o3, o2, ofj, osw1, _), _ = O.block_kpfusion(path_params, "block1.", inp["img_feat"], inp["img_feat_rgb"], pcl.cpu(), ex["joint_xyz0"],
                                                      ex["closeness"], ex["index"], inp["img_offset"], None, O.nearest_down(inp["img"], 32),
@@ -162,10 +160,40 @@ def test_fusion_path_bf16_tensor_core(net, path_params, capsys):
         r3d, r2d, fj, sw, _ = net.block2(c["img_feat"], c["img_feat_rgb"], pcl, o2.to(DEV), ex["closeness"].to(DEV), ex["index"].to(DEV).int(),
                                          c["img_offset"], ofj.to(DEV), loader(img_size=128), c["img"][:, :, ::4, ::4], c["center"], c["M"],
                                          c["cube"], c["cam"])
-    iso = [float((r3d.float().cpu() - ores[2]).norm() / ores[2].norm()), float((r2d.float().cpu() - ores[3]).norm() / ores[3].norm())]
+    iso = [mm_err(r3d, ores[2].numpy()), mm_err(r2d, ores[3].numpy())]
     with capsys.disabled():
-        print("[bf16 path] block 2 in isolation (oracle stage-1 inputs): relative", ["%.4f" % r for r in iso])
-    assert iso[0] < 2e-2 and iso[1] < 3e-2, iso   # r2d stacks K5 + two more 4-layer bf16 token stacks on top of r3d
+        print(f"[{maps} maps] block 2 in isolation (oracle stage-1 inputs): mean error mm", ["%.5f" % r for r in iso])
+    assert max(iso) <= 0.05, iso
+
+
+def test_block_runs_no_library_gemm(net, capsys):
+    """the fp32-input route must not fall back to cuBLAS / ATen GEMM, softmax or LayerNorm kernels.  Profile one
+    fp32-map forward_path with the torch profiler and check the kernel names: everything in the step is `kpf::*` apart from
+    dtype-cast / copy elementwise kernels of the wrappers."""
+    from torch.profiler import ProfilerActivity, profile
+    from keypointfusion_b200.dataloader.loader import loader
+    from keypointfusion_b200 import ops
+    inp = synth.make_inputs(2, 128, 21, 128, seed=12)
+    c = {k: v.to(DEV) for k, v in inp.items()}
+    with torch.no_grad():
+        pcl, _ = ops.getpcl(c["img"], c["center"], c["cube"], c["M"], c["cam"], seed=4)
+
+        def run():
+            return net.forward_path(c["img_offset"], c["img_feat"], None, c["img_feat_rgb"], c["img"], pcl, loader(img_size=128),
+                                    c["center"], c["M"], c["cube"], c["cam"], 0.8)
+        run()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run()
+            torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ours = [n for n in names if "kpf::" in n or "kpf" in n.lower()]
+    bad = [n for n in names if any(t in n.lower() for t in ("gemm", "cutlass", "cublas", "softmax", "layer_norm", "layernorm", "sgemm", "bmm",
+                                                             "flash", "attention"))]
+    with capsys.disabled():
+        print("\n[fp32 route] kernels in one step:", len(names), "distinct;", len(ours), "kpf kernels; library-like:", bad)
+    assert not bad, bad
+    assert len(ours) >= 10
 
 
 def test_fusion_path_batch_invariance(net):

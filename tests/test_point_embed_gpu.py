@@ -1,4 +1,5 @@
-"""GPU: fused point stage (repack + gather + embeddings + softmax-aggregation partials on tcgen05) vs the fp32 oracle."""
+"""GPU: fused point stage (repack + gather + embeddings + softmax-aggregation partials) and DESA on split-precision tcgen05 GEMMs
+vs the fp32 oracle: fp32-class bars (RMS relative <= TOL, two orders inside north_star's 1e-3), bit-exact ball-query indices."""
 import numpy as np
 import pytest
 import torch
@@ -15,21 +16,37 @@ def rms_rel(a, b):
     return float((a - b).norm() / b.norm())
 
 
+def _tol():
+    from keypointfusion_b200 import ops
+    return 2e-5 if ops.SPLIT_FMT == ops.FMT_F16 else 3e-4   # fp16 planes: 22 bits ; bf16 planes: 16 bits
+
+
+def worst_rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
 def test_repack(golden_inputs):
     from keypointfusion_b200 import ops
     i = golden_inputs
     for dt in (torch.float32, torch.bfloat16):
-        out = ops.repack_features(i["img_feat"].to(DEV, dt), i["img_feat_rgb"].to(DEV, dt), i["img_offset"][:, 84:].to(DEV, dt))
+        out, lo = ops.repack_features(i["img_feat"].to(DEV, dt), i["img_feat_rgb"].to(DEV, dt), i["img_offset"][:, 84:].to(DEV, dt))
         ref = torch.cat([i["img_feat"], i["img_feat_rgb"], i["img_offset"][:, 84:], torch.zeros(2, 11, 32, 32)], 1)
-        ref = ref.reshape(2, 288, 1024).permute(0, 2, 1).to(dt).bfloat16()
-        assert torch.equal(out.cpu(), ref)
+        ref = ref.reshape(2, 288, 1024).permute(0, 2, 1).to(dt)
+        assert torch.equal(out.cpu(), ref.bfloat16())
+        if dt == torch.float32:   # fp32 maps: a second plane carries x - bf16(x), so hi + lo is x to 2^-16
+            assert torch.equal(lo.cpu(), (ref - ref.bfloat16().float()).bfloat16())
+            assert float(((out.float() + lo.float()).cpu() - ref).abs().max()) <= 2.0 ** -15 * float(ref.abs().max())
+        else:
+            assert lo is None
 
 
-@pytest.mark.parametrize("B", [2, 5])
-def test_point_embed(golden, golden_inputs, path_params, B):
+@pytest.mark.parametrize("B,maps", [(2, "bf16"), (5, "bf16"), (3, "fp32")])
+def test_point_embed(golden, golden_inputs, path_params, B, maps):
     from keypointfusion_b200 import ops
     from keypointfusion_b200.model.model import Block_KPFusion
-    inp = synth.make_inputs(B, 128, 21, 128, seed=50 + B, bf16_round=True)
+    inp = synth.make_inputs(B, 128, 21, 128, seed=50 + B, bf16_round=maps == "bf16")
+    mdt = torch.bfloat16 if maps == "bf16" else torch.float32
     g = [inp[k].numpy() for k in ("center", "M", "cube", "cam")]
     c = {k: v.to(DEV) for k, v in inp.items()}
     pcl, _ = ops.getpcl(c["img"], c["center"], c["cube"], c["M"], c["cam"], seed=2)
@@ -39,10 +56,11 @@ def test_point_embed(golden, golden_inputs, path_params, B):
     blk.load_state_dict({k[len("block1."):]: v for k, v in path_params.items() if k.startswith("block1.")})
     blk = blk.to(DEV).eval()
     k = blk.kc()
-    featT = ops.repack_features(c["img_feat"].bfloat16(), c["img_feat_rgb"].bfloat16(), c["img_offset"][:, 84:].bfloat16())
-    e, acc, ms = ops.point_embed(featT, idx, close, pcl, joint.to(DEV), k["pe_wmat"], k["pe_wvec"], 0.8)
+    featT = ops.repack_features(c["img_feat"].to(mdt), c["img_feat_rgb"].to(mdt), c["img_offset"][:, 84:].to(mdt))
+    e16, acc, ms = ops.point_embed(featT, idx, close, pcl, joint.to(DEV), k["pe_wmat"], k["pe_wvec"], 0.8)
+    e = ops.e_to_float(e16)
     agg = ops.combine_point_partials(acc, ms, 21)
-    # oracle on the same (bf16-rounded) maps
+    # oracle on the same maps (bf16 maps are exact in one plane; fp32 maps enter as two bf16 planes = 16 mantissa bits)
     p = path_params
     pc, ix, cl = pcl.cpu(), idx.cpu().long(), close.cpu()
     off = O.pcl_joint2offset(joint, pc, 0.8)
@@ -52,8 +70,10 @@ def test_point_embed(golden, golden_inputs, path_params, B):
                     O.conv_bn(p, "block1.pcl_pose_emb.", torch.cat([pw, off], -1)))
     ee = torch.relu(ee + O.conv_bn(p, "block1.pcl_feat_emb_RGB.", pr))
     ragg = torch.softmax(pw.permute(0, 2, 1), -1) @ ee
-    assert rms_rel(e, ee) < 1e-2, rms_rel(e, ee)
-    assert rms_rel(agg, ragg) < 1e-2, rms_rel(agg, ragg)
+    tol = _tol() if maps == "bf16" else 3e-5
+    print(f"[point stage] maps {maps}: e rms rel {rms_rel(e, ee):.2e} worst {worst_rel(e, ee):.2e}; aggregation rms rel {rms_rel(agg, ragg):.2e}")
+    assert rms_rel(e, ee) < tol and worst_rel(e, ee) < 10 * tol, (rms_rel(e, ee), worst_rel(e, ee))
+    assert rms_rel(agg, ragg) < tol and worst_rel(agg, ragg) < 10 * tol, rms_rel(agg, ragg)
     # spatial processing order (scheduling aid): K2 and the point features are bit-identical, the aggregation only regroups
     order = ops.spatial_order(pcl, c["center"], c["M"], c["cube"], c["cam"], 128, 32)
     assert torch.equal(torch.sort(order.long(), dim=1)[0].cpu(), torch.arange(pcl.shape[1]).expand(B, -1))
@@ -61,26 +81,85 @@ def test_point_embed(golden, golden_inputs, path_params, B):
                                         order=order)
     assert torch.equal(idx2, idx) and torch.equal(close2, close)
     e2, acc2, ms2 = ops.point_embed(featT, idx, close, pcl, joint.to(DEV), k["pe_wmat"], k["pe_wvec"], 0.8, order=order)
-    assert torch.equal(e2, e)
+    assert torch.equal(e2, e16)
     agg2 = ops.combine_point_partials(acc2, ms2, 21)
-    assert rms_rel(agg2, ragg) < 1e-2 and rms_rel(agg2, agg) < 2e-3, (rms_rel(agg2, ragg), rms_rel(agg2, agg))
+    assert rms_rel(agg2, ragg) < tol and rms_rel(agg2, agg) < tol, (rms_rel(agg2, ragg), rms_rel(agg2, agg))
 
 
-@pytest.mark.parametrize("B", [2, 3])
-def test_desa_fused(path_params, B):
-    """point stage -> DESA kernel vs the oracle's joint embeddings + DESA (same ball-query membership: centres are inputs)."""
+def _desa_setup(path_params, B, seed):
     from keypointfusion_b200 import ops
     from keypointfusion_b200.model.model import Block_KPFusion
-    import torch.nn.functional as F
-    inp = synth.make_inputs(B, 128, 21, 128, seed=70 + B, bf16_round=True)
+    inp = synth.make_inputs(B, 128, 21, 128, seed=seed, bf16_round=True)
     c = {k: v.to(DEV) for k, v in inp.items()}
     pcl, _ = ops.getpcl(c["img"], c["center"], c["cube"], c["M"], c["cam"], seed=2)
     close, _, idx = ops.img2pcl_index(pcl, c["img"], c["center"], c["M"], c["cube"], c["cam"], 128, 4, fs=32, want_i64=False, want_i32=True)
-    # joints placed on points of the cloud so that every ball is well populated
-    joint = pcl[:, ::48][:, :21].contiguous() + 0.01
     blk = Block_KPFusion(21)
     blk.load_state_dict({k[len("block1."):]: v for k, v in path_params.items() if k.startswith("block1.")})
     blk = blk.to(DEV).eval()
+    return inp, c, pcl, close, idx, blk
+
+
+def _joint_sets(pcl, which):
+    """Centre placements that exercise the ball query's branches (pointnet2_ops semantics, model.py:158, :174)."""
+    B = pcl.shape[0]
+    if which == "dense":      # on the cloud: every ball well populated (> nsample hits at the large radii)
+        return pcl[:, ::48][:, :21].contiguous() + 0.01
+    if which == "sparse":     # just off the cloud's rim and far away: < nsample hits (padding with the first hit), and balls that
+        j = pcl[:, ::48][:, :21].contiguous().clone()     # contain nothing but the centre itself
+        j[:, ::3, 2] += 0.35
+        j[:, 1::3, :2] += 0.3
+        j[:, 20] = torch.tensor([3.0, 3.0, 3.0], device=pcl.device)
+        return j
+    # "edge": centres at EXACTLY radius distance (d2 == r2 must be excluded: strict <) from a cloud point along x, for each scale
+    j = pcl[:, 100:121].contiguous().clone()
+    for k, r in enumerate((0.1, 0.2, 0.4)):
+        j[:, k::3, 0] = pcl[:, 100 + k:121:3, 0] + r
+    return j
+
+
+@pytest.mark.parametrize("which", ["dense", "sparse", "edge"])
+def test_ball_query_indices_exact(path_params, which):
+    """kpf_ball_query (stand-alone) AND the fused prep kernel's indices == the oracle's ball query, bit for bit, incl. sparse balls
+    (< nsample hits -> padded with the first hit), saturated balls (> nsample hits -> the first nsample in index order), the
+    d2 == r2 boundary and centres far from the cloud.  The fused kernel's indices are read back from its scratch workspace."""
+    from keypointfusion_b200 import ops
+    B = 3
+    inp, c, pcl, close, idx, blk = _desa_setup(path_params, B, 81)
+    joint = _joint_sets(pcl, which)
+    N, J, NS = pcl.shape[1], 21, 64
+    xyz = torch.cat([pcl, joint], 1).contiguous()
+    counts = []
+    for r in (0.1, 0.2, 0.4):
+        got = ops.ball_query(xyz, joint, r, NS).cpu().numpy()
+        ref, cnt = O.ball_query(xyz.cpu().numpy(), joint.cpu().numpy(), r, NS, return_counts=True)
+        assert np.array_equal(got, ref), (which, r)
+        counts.append(cnt)
+    counts = np.stack(counts)
+    if which == "dense":
+        assert (counts[2] > NS).any()
+    if which == "sparse":
+        assert (counts[0] < NS).any() and (counts == 1).any()     # a ball holding only its own centre
+    # fused path: same indices out of desa_prep_kernel (u16, scale-major per sample)
+    k = blk.kc()
+    featT = ops.repack_features(c["img_feat"].bfloat16(), c["img_feat_rgb"].bfloat16(), c["img_offset"][:, 84:].bfloat16())
+    e, acc, ms = ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8)
+    scratch = {}
+    ops.desa_fused(e, acc, ms, pcl, joint, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, NS, keep_scratch=scratch)
+    torch.cuda.synchronize()
+    off = B * 3 * J * 128 * 4 + B * (N + 32) * 16
+    fused = scratch["buf"][off:off + B * 3 * J * NS * 2].view(torch.int16).cpu().numpy().astype(np.uint16).reshape(B, 3, J, NS)
+    for s_, r in enumerate((0.1, 0.2, 0.4)):
+        ref = O.ball_query(xyz.cpu().numpy(), joint.cpu().numpy(), r, NS)
+        assert np.array_equal(fused[:, s_].astype(np.int64), ref.astype(np.int64)), (which, r)
+
+
+@pytest.mark.parametrize("B,which", [(2, "dense"), (3, "dense"), (2, "sparse"), (2, "edge")])
+def test_desa_fused(path_params, B, which):
+    """point stage -> DESA kernel vs the oracle's joint embeddings + DESA (same ball-query membership: centres are inputs)."""
+    from keypointfusion_b200 import ops
+    import torch.nn.functional as F
+    inp, c, pcl, close, idx, blk = _desa_setup(path_params, B, 70 + B)
+    joint = _joint_sets(pcl, which)
     k = blk.kc()
     featT = ops.repack_features(c["img_feat"].bfloat16(), c["img_feat_rgb"].bfloat16(), c["img_offset"][:, 84:].bfloat16())
     e, acc, ms = ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8)
@@ -98,5 +177,9 @@ def test_desa_fused(path_params, B):
     ee = torch.relu(ee + O.conv_bn(p, "block1.pcl_feat_emb_RGB.", pr))
     rjf = torch.relu(O.conv_bn(p, "block1.joint_feat_emb.", torch.softmax(pw.permute(0, 2, 1), -1) @ ee) + O.conv_bn(p, "block1.joint_xyz_emb.", jt))
     rout = O.desa(p, "block1.FA.", ee, rjf, pc, jt)
-    assert rms_rel(jf, rjf) < 1e-2, rms_rel(jf, rjf)
-    assert rms_rel(out, rout) < 1e-2, rms_rel(out, rout)
+    print(f"[desa {which}] jf rms rel {rms_rel(jf, rjf):.2e}; desa output rms rel {rms_rel(out, rout):.2e} worst {worst_rel(out, rout):.2e}")
+    assert rms_rel(jf, rjf) < _tol(), rms_rel(jf, rjf)
+    assert rms_rel(out, rout) < _tol() and worst_rel(out, rout) < 10 * _tol(), rms_rel(out, rout)
+    # the stand-alone drop-in module (model.py:166-204 signature) runs the same kernels with the joint features given
+    mod = blk.FA(ee.to(DEV), rjf.to(DEV), pcl, joint)
+    assert rms_rel(mod, rout) < _tol(), rms_rel(mod, rout)

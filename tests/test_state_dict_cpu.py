@@ -15,7 +15,13 @@ def _same(mod, ref):
 
 
 def test_block_keys(golden_meta):
-    _same(Block_KPFusion(joint_num=21), golden_meta["Block_KPFusion_keys"])
+    """The key list was dumped from the reference running under transformers 5.x, which no longer saves BertEmbeddings.position_ids;
+    the reference's pin (4.25.1, requirements.txt:40) registers it as a persistent buffer, so released checkpoints carry it.  The
+    drop-in exposes the 4.25.1 list (superset) and loads either (tests/test_packers_cpu.py)."""
+    ref = dict(golden_meta["Block_KPFusion_keys"])
+    for tr in ("init_TR", "final_TR"):
+        ref[f"{tr}.bert.embeddings.position_ids"] = [1, 512]
+    _same(Block_KPFusion(joint_num=21), ref)
 
 
 def test_decoder_and_fusion_keys(golden_meta):
@@ -33,7 +39,7 @@ def test_kpfusion_loads_reference_style_checkpoint(golden_meta, path_params):
     ck = {"module." + k: v for k, v in path_params.items()}
     own = net.state_dict()
     filt = {k[len("module."):]: v for k, v in ck.items() if k[len("module."):] in own}
-    assert len(filt) == len(own)
+    assert len(filt) == len([k for k in own if not k.endswith("position_ids")])   # (position_ids: only 4.25.1-era checkpoints carry it)
 
 
 def test_init_matches_reference_rules():

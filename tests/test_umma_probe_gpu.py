@@ -75,7 +75,7 @@ def test_block_kernel_phase_clocks(path_params, capsys):
             print(f"\n[{name}] total cycles {int(t[n - 1] - t[0])}:", [(labels[i] if i < len(labels) else f"d{i}", int(x)) for i, x in enumerate(d)])
     for _ in range(2):
         d1 = torch.zeros(64, dtype=torch.int64, device="cuda")
-        e, acc, ms = ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8, dbg=d1)
+        e, acc, ms = ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8, dbg=d1)   # featT = (hi, None)
         d2 = torch.zeros(64, dtype=torch.int64, device="cuda")
         part, jf = ops.desa_fused(e, acc, ms, pcl, joint, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, 64, dbg=d2)
         d3 = torch.zeros(64, dtype=torch.int64, device="cuda")
