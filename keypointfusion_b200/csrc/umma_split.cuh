@@ -47,79 +47,101 @@ struct TmemOp {
 };
 constexpr uint32_t NO_PLANE = 0xffffffffu;
 
-// D[128 x N] (+)= A B^T over K (multiple of 16), split precision, both operands from shared memory.  Issued by ONE thread.
-// Order: the two small cross terms first, then hi x hi.
-__device__ __forceinline__ void umma_gemm3_ss(uint32_t tmem_d, const SmemOp a, const SmemOp b, uint32_t idesc, int K, bool accumulate) {
-    const uint64_t a_step = (uint64_t)((2 * a.lbo) >> 4), b_step = (uint64_t)((2 * b.lbo) >> 4);
-    bool acc = accumulate;
-    if (a.lo) {
-        uint64_t ad = umma_smem_desc(a.lo, a.lbo, a.sbo), bd = umma_smem_desc(b.hi, b.lbo, b.sbo);
-#pragma unroll 1
-        for (int ks = 0; ks < K / 16; ++ks) {
-            umma_bf16(tmem_d, ad, bd, idesc, acc);
-            acc = true;
-            ad += a_step;
-            bd += b_step;
-        }
+// ---- MMA issue with the 64-bit shared-memory descriptor kept as two 32-bit halves.  Only the low half (start address | LBO) moves
+// along K, by a constant that folds into an immediate once the K loop is unrolled; the 64-bit add-with-carry, the per-iteration
+// R2UR of the accumulator address / instruction descriptor and the loop control of the rolled form cost ~16 uniform-datapath
+// instructions per MMA (~42 cycles per MMA measured, against a 16-cycle tensor-pipe floor at N = 32).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+
+__device__ __forceinline__ void umma_issue_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_issue_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// one plane pair over KS = K / 16 steps, fully unrolled
+template <int KS>
+__device__ __forceinline__ void umma_planes_ss(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_addr,
+                                               uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, uint32_t& acc) {
+    const uint32_t al = desc_lo(a_addr, a_lbo), ah = desc_hi(a_sbo), bl = desc_lo(b_addr, b_lbo), bh = desc_hi(b_sbo);
+    const uint32_t a_step = (2 * a_lbo) >> 4, b_step = (2 * b_lbo) >> 4;   // start-address field, 16-byte units
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        umma_issue_ss(tmem_d, al + ks * a_step, ah, bl + ks * b_step, bh, idesc, acc);
+        acc = 1u;
     }
-    if (b.lo) {
-        uint64_t ad = umma_smem_desc(a.hi, a.lbo, a.sbo), bd = umma_smem_desc(b.lo, b.lbo, b.sbo);
-#pragma unroll 1
-        for (int ks = 0; ks < K / 16; ++ks) {
-            umma_bf16(tmem_d, ad, bd, idesc, acc);
-            acc = true;
-            ad += a_step;
-            bd += b_step;
-        }
-    }
-    {
-        uint64_t ad = umma_smem_desc(a.hi, a.lbo, a.sbo), bd = umma_smem_desc(b.hi, b.lbo, b.sbo);
-#pragma unroll 1
-        for (int ks = 0; ks < K / 16; ++ks) {
-            umma_bf16(tmem_d, ad, bd, idesc, acc);
-            acc = true;
-            ad += a_step;
-            bd += b_step;
-        }
+}
+template <int KS>
+__device__ __forceinline__ void umma_planes_ts(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo,
+                                               uint32_t idesc, uint32_t& acc) {
+    const uint32_t bl = desc_lo(b_addr, b_lbo), bh = desc_hi(b_sbo);
+    const uint32_t b_step = (2 * b_lbo) >> 4;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        umma_issue_ts(tmem_d, a_tmem + 8 * ks, bl + ks * b_step, bh, idesc, acc);
+        acc = 1u;
     }
 }
 
+// D[128 x N] (+)= A B^T over K = 16 KS, split precision, both operands from shared memory.  Issued by ONE thread.
+// Order: the two small cross terms first, then hi x hi.
+template <int KS>
+__device__ __forceinline__ void umma_gemm3_ss_t(uint32_t tmem_d, const SmemOp a, const SmemOp b, uint32_t idesc, bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u;
+    if (a.lo) umma_planes_ss<KS>(tmem_d, a.lo, a.lbo, a.sbo, b.hi, b.lbo, b.sbo, idesc, acc);
+    if (b.lo) umma_planes_ss<KS>(tmem_d, a.hi, a.lbo, a.sbo, b.lo, b.lbo, b.sbo, idesc, acc);
+    umma_planes_ss<KS>(tmem_d, a.hi, a.lbo, a.sbo, b.hi, b.lbo, b.sbo, idesc, acc);
+}
 // Same with A in tensor memory (8 columns per K = 16 step).
+template <int KS>
+__device__ __forceinline__ void umma_gemm3_ts_t(uint32_t tmem_d, const TmemOp a, const SmemOp b, uint32_t idesc, bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u;
+    if (a.lo != NO_PLANE) umma_planes_ts<KS>(tmem_d, a.lo, b.hi, b.lbo, b.sbo, idesc, acc);
+    if (b.lo) umma_planes_ts<KS>(tmem_d, a.hi, b.lo, b.lbo, b.sbo, idesc, acc);
+    umma_planes_ts<KS>(tmem_d, a.hi, b.hi, b.lbo, b.sbo, idesc, acc);
+}
+// run-time K front ends (K in {16, 32, 64, 128, 256})
+__device__ __forceinline__ void umma_gemm3_ss(uint32_t tmem_d, const SmemOp a, const SmemOp b, uint32_t idesc, int K, bool accumulate) {
+    switch (K) {
+        case 16: umma_gemm3_ss_t<1>(tmem_d, a, b, idesc, accumulate); break;
+        case 32: umma_gemm3_ss_t<2>(tmem_d, a, b, idesc, accumulate); break;
+        case 64: umma_gemm3_ss_t<4>(tmem_d, a, b, idesc, accumulate); break;
+        case 128: umma_gemm3_ss_t<8>(tmem_d, a, b, idesc, accumulate); break;
+        default: umma_gemm3_ss_t<16>(tmem_d, a, b, idesc, accumulate); break;
+    }
+}
 __device__ __forceinline__ void umma_gemm3_ts(uint32_t tmem_d, const TmemOp a, const SmemOp b, uint32_t idesc, int K, bool accumulate) {
-    const uint64_t b_step = (uint64_t)((2 * b.lbo) >> 4);
-    bool acc = accumulate;
-    if (a.lo != NO_PLANE) {
-        uint64_t bd = umma_smem_desc(b.hi, b.lbo, b.sbo);
-        uint32_t at = a.lo;
-#pragma unroll 1
-        for (int ks = 0; ks < K / 16; ++ks) {
-            umma_f16_ts(tmem_d, at, bd, idesc, acc);
-            acc = true;
-            at += 8;
-            bd += b_step;
-        }
-    }
-    if (b.lo) {
-        uint64_t bd = umma_smem_desc(b.lo, b.lbo, b.sbo);
-        uint32_t at = a.hi;
-#pragma unroll 1
-        for (int ks = 0; ks < K / 16; ++ks) {
-            umma_f16_ts(tmem_d, at, bd, idesc, acc);
-            acc = true;
-            at += 8;
-            bd += b_step;
-        }
-    }
-    {
-        uint64_t bd = umma_smem_desc(b.hi, b.lbo, b.sbo);
-        uint32_t at = a.hi;
-#pragma unroll 1
-        for (int ks = 0; ks < K / 16; ++ks) {
-            umma_f16_ts(tmem_d, at, bd, idesc, acc);
-            acc = true;
-            at += 8;
-            bd += b_step;
-        }
+    switch (K) {
+        case 16: umma_gemm3_ts_t<1>(tmem_d, a, b, idesc, accumulate); break;
+        case 32: umma_gemm3_ts_t<2>(tmem_d, a, b, idesc, accumulate); break;
+        case 64: umma_gemm3_ts_t<4>(tmem_d, a, b, idesc, accumulate); break;
+        case 128: umma_gemm3_ts_t<8>(tmem_d, a, b, idesc, accumulate); break;
+        default: umma_gemm3_ts_t<16>(tmem_d, a, b, idesc, accumulate); break;
     }
 }
 

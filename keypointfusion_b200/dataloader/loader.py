@@ -2,6 +2,7 @@
 the object KPFusion.forward receives as its `loader` argument (model/model.py:395, train.py:324)."""
 import torch
 
+from .. import custom_ops  # noqa: F401  (registers torch.ops.kpf.*)
 from .. import ops
 
 
@@ -16,20 +17,19 @@ class loader(object):
 
     # dataloader/loader.py:775-789
     def uvd_nl2xyznl_tensor(self, uvd, center, m, cube, cam_paras):
-        return ops.uvd2xyz(uvd, center, m, cube, cam_paras, self.img_size, self.flip)
+        return torch.ops.kpf.uvd2xyz(uvd, center, m, cube, cam_paras, float(self.img_size), float(self.flip))
 
     # dataloader/loader.py:821-834
     def xyz_nl2uvdnl_tensor(self, joint_xyz, center, M, cube_size, cam_paras):
-        return ops.xyz2uvd(joint_xyz, center, M, cube_size, cam_paras, self.img_size, self.flip)
+        return torch.ops.kpf.xyz2uvd(joint_xyz, center, M, cube_size, cam_paras, float(self.img_size), float(self.flip))
 
     # dataloader/loader.py:936-967
     def img2pcl_index(self, pcl, img, center, M, cube, cam_para, select_num=9):
-        close, i64, _ = ops.img2pcl_index(pcl, img, center, M, cube, cam_para, self.img_size, select_num, self.flip)
-        return close, i64
+        return torch.ops.kpf.img2pcl_index(pcl, img, center, M, cube, cam_para, float(self.img_size), select_num, float(self.flip), True, None)
 
     # dataloader/loader.py:791-819
     def img2anchor_dis(self, joint_uvd, img, center, M, cube, cam_para, gamma=10):
-        return ops.img2anchor_dis(joint_uvd, img, center, M, cube, cam_para, self.img_size, gamma, self.flip)
+        return torch.ops.kpf.img2anchor_dis(joint_uvd, img, center, M, cube, cam_para, float(self.img_size), float(gamma), float(self.flip))
 
     # dataloader/loader.py:993-1005
     def img2pcl(self, img):

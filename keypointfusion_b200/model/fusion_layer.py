@@ -3,6 +3,7 @@ structure; forward runs on the B200 kernels (K7).  Inference only (no autograd t
 import torch
 import torch.nn as nn
 
+from .. import custom_ops  # noqa: F401  (registers torch.ops.kpf.*)
 from .. import ops
 
 
@@ -41,7 +42,7 @@ class FSP(nn.Module):
     def forward(self, guidePath, mainPath):
         _inference_only(self, guidePath, mainPath)
         fc = self.filter.fc
-        return ops.fsp(guidePath, mainPath, fc[0].weight, fc[0].bias, fc[2].weight, fc[2].bias)
+        return torch.ops.kpf.fsp(guidePath, mainPath, fc[0].weight, fc[0].bias, fc[2].weight, fc[2].bias)
 
 
 class RGBDFusion(nn.Module):
@@ -63,7 +64,10 @@ class RGBDFusion(nn.Module):
         _inference_only(self, rgb, depth)
         gw = torch.cat([self.gate_rgb.weight.reshape(1, -1), self.gate_depth.weight.reshape(1, -1)], 0)
         gb = torch.cat([self.gate_rgb.bias, self.gate_depth.bias])
-        rgb_out, depth_out, merge, amean = ops.rgbd_fusion(rgb, depth, gw, gb, want_attn_mean=train_writer is not None)
+        if train_writer is None:
+            rgb_out, depth_out, merge = torch.ops.kpf.rgbd_fusion(rgb, depth, gw, gb)
+            return [rgb_out, depth_out], merge
+        rgb_out, depth_out, merge, amean = ops.rgbd_fusion(rgb, depth, gw, gb, want_attn_mean=True)
         if train_writer is not None:  # model/fusion_layer.py:68-72 (a full reduction + host sync: optional slow path)
             train_writer.add_scalar('RGB_weight_fusion_stage{}'.format(layer_stage), amean[0].detach(), global_step)
             train_writer.add_scalar('Depth_weight_fusion_stage{}'.format(layer_stage), amean[1].detach(), global_step)
@@ -86,6 +90,6 @@ class ACFusion(nn.Module):
     def forward(self, x, train_writer=None, global_step=0, layer_stage=0):
         rgb, depth = x
         _inference_only(self, rgb, depth)
-        rgb_out, depth_out, merge = ops.ac_fusion(rgb, depth, self.cam_rgb.weight, self.cam_rgb.bias, self.cam_depth.weight,
-                                                  self.cam_depth.bias)
+        rgb_out, depth_out, merge = torch.ops.kpf.ac_fusion(rgb, depth, self.cam_rgb.weight, self.cam_rgb.bias, self.cam_depth.weight,
+                                                            self.cam_depth.bias)
         return [rgb_out, depth_out], merge

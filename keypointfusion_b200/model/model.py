@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import custom_ops as cops   # registers torch.ops.kpf.*
 from .. import ops
 from ..util.generateFeature import GFM
 from ..util.img2pcl import Pcl_utils
@@ -30,15 +31,25 @@ def img2pcl(img):  # model.py:429-437
     return torch.cat((u, v, img), dim=1).view(B, 3, H * W).permute(0, 2, 1)
 
 
+def _is_scalar(k):
+    return not torch.is_tensor(k)
+
+
 def joint2offset(joint, img, kernel_size, feature_size):  # model.py:440-463 (no +1e-8 under the sqrt, :455)
-    return ops.joint2offset(joint, img, kernel_size, feature_size, eps=0.0)
+    if _is_scalar(kernel_size):
+        return torch.ops.kpf.joint2offset(joint, img, float(kernel_size), feature_size, 0.0)
+    return ops.joint2offset(joint, img, kernel_size, feature_size, eps=0.0)   # per-joint kernel tensor (generateFeature.py:76-80)
 
 
 def offset2joint_weight(offset, depth, kernel_size):  # model.py:466-500
+    if _is_scalar(kernel_size):
+        return torch.ops.kpf.offset2joint_weight(offset, depth, float(kernel_size))
     return ops.offset2joint_weight(offset, depth, kernel_size)
 
 
 def pcl_joint2offset(joint, pcl, kernel_size):  # model.py:503-525
+    if _is_scalar(kernel_size):
+        return torch.ops.kpf.pcl_joint2offset(joint, pcl, float(kernel_size))
     return ops.pcl_joint2offset(joint, pcl, kernel_size)
 
 
@@ -80,8 +91,12 @@ class _KernelCache:
                 m.invalidate()
 
     def kc(self):
-        key = _param_fingerprint(self)
         c = self.__dict__.get("_kc")
+        if torch.compiler.is_compiling():   # tracing: the packed weights are graph constants; build them with one eager call first
+            if c is None:
+                raise RuntimeError(f"{type(self).__name__}: run one eager forward before torch.compile so the packed weights exist")
+            return c
+        key = _param_fingerprint(self)
         if c is None or self.__dict__.get("_kc_key") != key:
             with torch.no_grad():
                 c = self._build_kc()
@@ -230,8 +245,7 @@ class KP_Interaction_TR(_KernelCache, nn.Module):  # model.py:106-126
         k = self.kc()
         if J not in k:  # the position-embedding slice depends on the token count
             k[J] = ops.pack_token_program(J, enc=(self.state_dict(), "")).to(img_feats.device)
-        tokens, pred, _ = ops.token_stack(k[J], x=img_feats, want_tokens=want_tokens)
-        return tokens, pred
+        return cops.run_token_program(k[J], x=img_feats, want_tokens=want_tokens)
 
     forward_tc = forward
 
@@ -292,7 +306,7 @@ class DESA(_KernelCache, nn.Module):
             k["fu"] = ops.pack_token_program(J, fusion=k["fusion"]).to(dev)
         e = ops.e_from_float(pcl_feat.float())
         part, _ = ops.desa_fused(e, None, None, pcl_xyz, node_xyz, k["ds"][0], k["ds"][1], self.radius, self.S[0], jf_in=node_feat)
-        return ops.token_stack(k["fu"], desa=part, jf=node_feat)[0]
+        return cops.run_token_program(k["fu"], desa=part, jf=node_feat)[0]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -383,21 +397,34 @@ class Block_KPFusion(_KernelCache, nn.Module):
                                       "three DESA scales sharing nsample (no fallback path)")
         pcl = pcl.float().contiguous()
         joint_xyz = joint_xyz.detach().float().contiguous()
+        K = torch.ops.kpf
+        fmt = ops.SPLIT_FMT
         if featT is None:
-            featT = ops.repack_features(img_feat, img_feature_rgb, img_offset[:, J * 4:])
+            featT = K.repack_features(img_feat, img_feature_rgb, img_offset[:, J * 4:])
         if rgb_planes is None:
-            rgb_planes = (img_feature_rgb, None) if img_feature_rgb.dtype == torch.bfloat16 else ops.split_map(img_feature_rgb)
-        e, p_acc, p_ms = ops.point_embed(featT, pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8,
-                                         order=point_order)                                               # model.py:295-320
-        part, jf = ops.desa_fused(e, p_acc, p_ms, pcl, joint_xyz, k["ds_wmat"], k["ds_wvec"], self.FA.radius, self.FA.S[0])   # :323-327
-        outfeature_init_TR, refined_3d_joints, _ = ops.token_stack(k["tok_init"], desa=part, jf=jf)        # model.py:203, :330
-        spatial_weight_loss, img_feat_j = ops.spatial_aggregate_tc(
-            rgb_planes, refined_3d_joints, img_down, center, M, cube, cam_para, k["wa_packed"], self.atten_spatial.bias,
-            self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias, prev=updated_2d_feature,
-            img_size=loader.img_size, flip=loader.flip, hm_std=0.8, hm_sigma=1.0, gamma=10.0)             # model.py:334-344
-        _, refined_2d_joints, _ = ops.token_stack(k["tok_final"], x=img_feat_j, y=outfeature_init_TR, r3d=refined_3d_joints,
-                                                  want_tokens=False)                                      # model.py:347-349
+            rgb_planes = _rgb_planes(img_feature_rgb)
+        if pcl_index.dtype != torch.int32:
+            pcl_index = pcl_index.to(torch.int32)
+        e, p_acc, p_ms = K.point_embed(featT[0], featT[1], pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8, fmt,
+                                       point_order)                                                       # model.py:295-320
+        r = self.FA.radius
+        part, jf = K.desa_fused(e, p_acc, p_ms, pcl, joint_xyz, k["ds_wmat"], k["ds_wvec"], float(r[0]), float(r[1]), float(r[2]),
+                                self.FA.S[0], fmt)                                                        # model.py:323-327
+        outfeature_init_TR, refined_3d_joints = cops.run_token_program(k["tok_init"], desa=part, jf=jf)   # model.py:203, :330
+        spatial_weight_loss, img_feat_j = K.spatial_aggregate_tc(
+            rgb_planes[0], rgb_planes[1], refined_3d_joints, img_down, center, M, cube, cam_para, k["wa_packed"], self.atten_spatial.bias,
+            self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias, float(loader.img_size),
+            float(loader.flip), 0.8, 1.0, 10.0, fmt, updated_2d_feature)                                  # model.py:334-344
+        _, refined_2d_joints = cops.run_token_program(k["tok_final"], x=img_feat_j, y=outfeature_init_TR, r3d=refined_3d_joints,
+                                                      want_tokens=False)                                  # model.py:347-349
         return refined_3d_joints, refined_2d_joints, img_feat_j, spatial_weight_loss, None
+
+
+def _rgb_planes(img_feat_rgb):
+    """The rgb-branch map as K5's operand planes: a bf16 map is exact in one plane (second = empty tensor); an fp32 map is split."""
+    if img_feat_rgb.dtype == torch.bfloat16:
+        return img_feat_rgb.contiguous(), img_feat_rgb.new_empty(0)
+    return torch.ops.kpf.split_map(img_feat_rgb.float().contiguous())
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -427,25 +454,23 @@ class KPFusion(nn.Module):
         """model.py:399-426: everything after the backbones."""
         J = self.joint_num
         H = img_feat.shape[2]
-        joint_uvd = ops.offset2joint_weight(img_offset, img, kernel)                                     # :399
+        K = torch.ops.kpf
+        img_size, flip = float(loader.img_size), float(loader.flip)
+        joint_uvd = offset2joint_weight(img_offset, img, kernel)                                         # :399
         result = [img_offset, img_offset_rgb]
         S = img.shape[-1]
         img_down = img[:, :, ::S // H, ::S // H] if S % H == 0 else F.interpolate(img, [H, H])           # :409, zero-copy view
-        joint_xyz = ops.uvd2xyz(joint_uvd, center, M, cube, cam_para, loader.img_size, loader.flip)      # :410
-        # (measured twice: forking the K4a -> a5 -> repack branch onto a second stream inside the graph, next to order -> K2, was
-        #  slower with the first kernels (1.283 vs 1.240 ms) and gains 1 % with the current ones (0.559 vs 0.565 ms): K2 fills the
-        #  SMs, so the chain stays single-stream)
+        joint_xyz = K.uvd2xyz(joint_uvd, center, M, cube, cam_para, img_size, flip)                      # :410
         # processing order of the points by feature-map cell: warps / point tiles then touch neighbouring cells (K2's insertions
         # coincide, the point stage's gathers hit the same lines); the results do not depend on it
-        order = ops.spatial_order(pcl, center, M, cube, cam_para, loader.img_size, H, loader.flip) if pcl.shape[1] <= 8192 else None
-        pcl_closeness, _, pcl_index = ops.img2pcl_index(pcl, img_down, center, M, cube, cam_para, loader.img_size, 4, loader.flip,
-                                                        want_i64=False, want_i32=True, order=order)     # :411
+        order = K.spatial_order(pcl, center, M, cube, cam_para, img_size, H, flip) if pcl.shape[1] <= 8192 else None
+        pcl_closeness, pcl_index = K.img2pcl_index(pcl, img_down, center, M, cube, cam_para, img_size, 4, flip, False, order)   # :411
         updated_2d_feature = [None] * (self.num_stages + 1)
         spatial_weight = [None] * self.num_stages
         # shared by both blocks: the channels-last repack of the three maps (one plane for bf16 maps, two for fp32 maps) and the
         # rgb map's NCHW plane(s) for K5
-        featT = ops.repack_features(img_feat, img_feat_rgb, img_offset[:, J * 4:])
-        rgb_planes = (img_feat_rgb.contiguous(), None) if img_feat_rgb.dtype == torch.bfloat16 else ops.split_map(img_feat_rgb)
+        featT = K.repack_features(img_feat, img_feat_rgb, img_offset[:, J * 4:])
+        rgb_planes = _rgb_planes(img_feat_rgb)
         for i in range(self.num_stages):                                                                 # :417-424
             block = getattr(self, f"block{i + 1}")
             r3d, r2d, updated_2d_feature[i + 1], spatial_weight[i], _ = block(

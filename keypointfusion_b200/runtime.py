@@ -19,6 +19,7 @@ class GraphedFusionPath:
         `__call__()` then replays with no staging copy and reads whatever those tensors hold at replay time."""
         self.net, self.loader, self.sample_num, self.kernel, self.seed = net, loader, sample_num, kernel, seed
         self.chains = max(1, min(chains, example["img"].shape[0]))
+        self.sm_share = float(__import__("os").environ.get("KPF_SM_SHARE", "1.0"))   # x SMs / chains per chain's persistent kernels
         dev = next(net.parameters()).device
         self.side = [torch.cuda.Stream(device=dev) for _ in range(self.chains - 1)]
         if bind:
@@ -65,7 +66,9 @@ class GraphedFusionPath:
             st = main if c == 0 else self.side[c - 1]
             if c > 0:
                 st.wait_stream(main)              # fork
-            with torch.cuda.stream(st):
+            # SM partitioning: each concurrent chain's persistent kernels take their share of the SMs, so that e.g. one chain's
+            # (one CTA per sample) token stack and another chain's point stage / DESA tiles are co-resident
+            with torch.cuda.stream(st), ops.sm_budget(max(1, int(ops.sm_count(self.static["img"].device) * self.sm_share / self.chains))):
                 res, sw, pcl = self._chain(sub)
                 self.joints_all[lo:hi].copy_(res[-1])
             outs.append((res, sw, pcl))
