@@ -103,6 +103,7 @@ struct PointParams {
     float* part_acc;         // [B,T,128,32]   T = N / 64
     float* part_ms;          // [B,T,2,32]  (max, sum)
     int B, N, J, HW, fmt;
+    int probe;               // profiling aid (KPF_PE_PROBE): bit 0 = gather from row 0 only (L1 hits), bit 1 = skip the main MMAs
     float kernel_size;
     long long* dbg;
 };
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         uint4* x2r = sX2 + (r >> 3) * 128 + (r & 7);
         {
             const size_t rb = (size_t)b * p.HW;
+            if (p.probe & 1) id = make_int4(0, 0, 0, 0);
             const uint4 *h0 = p.feat_hi + (rb + id.x) * PE_CH, *h1 = p.feat_hi + (rb + id.y) * PE_CH, *h2 = p.feat_hi + (rb + id.z) * PE_CH,
                         *h3 = p.feat_hi + (rb + id.w) * PE_CH;
             const int nload = grp == 0 ? 5 : 4, c_base = grp == 0 ? 0 : 16;
@@ -353,10 +355,10 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
                 // B operands: 128 B between k-chunks, 4096 / 2048 B between 8-point groups
                 a.hi = tmem0 + PE_W1H; a.lo = tmem0 + PE_W1L;
                 xb.hi = smem_u32(sX1); xb.lo = xb.hi + 2048 * 16; xb.lbo = 128; xb.sbo = 4096;
-                umma_gemm3_ts(tmem0 + PE_ACC1, a, xb, id64, 256, false);
+                if (!(p.probe & 2)) umma_gemm3_ts(tmem0 + PE_ACC1, a, xb, id64, 256, false);
                 a.hi = tmem0 + PE_W2H; a.lo = tmem0 + PE_W2L;
                 xb.hi = smem_u32(sX2); xb.lo = xb.hi + 1024 * 16; xb.lbo = 128; xb.sbo = 2048;
-                umma_gemm3_ts(tmem0 + PE_ACC2, a, xb, id64, 128, false);
+                if (!(p.probe & 2)) umma_gemm3_ts(tmem0 + PE_ACC2, a, xb, id64, 128, false);
                 umma_commit(&mma_bar);
             }
             __syncwarp();
@@ -511,6 +513,10 @@ extern "C" int kpf_point_embed(const void* feat_hi, const void* feat_lo, const i
     KPF_REQUIRE(e_batch_stride >= (long long)N * 256 && e_batch_stride % 8 == 0);
     p.e_out = (uint16_t*)e_out; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.B = B; p.N = N; p.J = J; p.HW = HW;
     p.kernel_size = kernel_size; p.fmt = fmt;
+    {
+        static const int probe = [] { const char* e = getenv("KPF_PE_PROBE"); return e ? atoi(e) : 0; }();
+        p.probe = probe;
+    }
     p.dbg = dbg;
     cudaError_t e = kpf::set_smem(point_embed_kernel, PE_SMEM);
     if (e != cudaSuccess) return (int)e;

@@ -247,6 +247,12 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         ++n_stamp;
     };
     stamp();
+    int n_fine = 0;
+    bool fine_on = false;   // fine stamps (dbg[32..63]) inside the first encoder layer
+    auto fine = [&]() {
+        if (fine_on && p.dbg && blockIdx.x == 0 && tid == 0 && n_fine < 32) p.dbg[32 + n_fine] = clock64();
+        ++n_fine;
+    };
     if (tid < 128) sLead[tid] = 0.f;
     wsync();      // sLead is rewritten by warp 0 in the input stage
     pdl_wait();   // everything above touched only weights; the activations below come from the previous kernel
@@ -389,16 +395,20 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         const int act = is_cross ? 0 : 1;                 // relu | erf-gelu
         const float eps = is_cross ? 1e-5f : 1e-12f;
 
-        // ---- Q and K projections back to back; V follows S (its weights take the ring slots Q's free)
+        // ---- K and Q projections back to back (ring order K, Q, V, O: V's weights take the slots K frees, the earliest possible);
+        //      V follows S
+        fine_on = (it == (p.cross ? 1 : 0));
+        n_fine = 0;
+        fine();
         sync_for_mma();
         if (warp_u == 0) {
             tc_fence_after();
             if (elect_one()) {
                 if (it >= 1) mbar_arrive(&vec_empty[(it - 1) & 1]);   // everybody is past the previous layer's vector reads
-                issue_proj(ACC_Q, bufX, g, false);
-                umma_commit(&bars[0]);
-                issue_proj(ACC_K, kv_src, g + 2, false);
+                issue_proj(ACC_K, kv_src, g, false);
                 umma_commit(&bars[1]);
+                issue_proj(ACC_Q, bufX, g + 2, false);
+                umma_commit(&bars[0]);
             }
             __syncwarp();
         }
@@ -408,18 +418,8 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         const float* b1 = sv + 6 * C;
         // chunk of the head-major attention operands: K index d = lane, row 32q + token
         const uint32_t qidx = (uint32_t)((lane >> 3) * 128 + (4 * q + c) * 8 + (lane & 7));
-        wait_bar(0);
-        {   // Q^T -> MN-major A operand of S
-            float a[8];
-            tmem_ld<8>(tmem + ACC_Q + 8 * c, a);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = tokv[i] ? (a[i] + bq) * qscale : 0.f;
-            uint4 hi, lo;
-            split8(fmt, a, hi, lo);
-            bufQ[qidx] = hi;
-            bufQ[TS_PLANE + qidx] = lo;
-        }
         wait_bar(1);
+        fine();
         {   // K^T -> MN-major B operand of S
             float a[8];
             tmem_ld<8>(tmem + ACC_K + 8 * c, a);
@@ -429,6 +429,19 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
             split8(fmt, a, hi, lo);
             bufK[qidx] = hi;
             bufK[TS_PLANE + qidx] = lo;
+        }
+        fine();
+        wait_bar(0);
+        fine();
+        {   // Q^T -> MN-major A operand of S
+            float a[8];
+            tmem_ld<8>(tmem + ACC_Q + 8 * c, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = tokv[i] ? (a[i] + bq) * qscale : 0.f;
+            uint4 hi, lo;
+            split8(fmt, a, hi, lo);
+            bufQ[qidx] = hi;
+            bufQ[TS_PLANE + qidx] = lo;
         }
         stamp();
         // ---- S for all four heads: D[32h+t][32h'+k] = Q_h[t] . K_h'[k] (diagonal blocks h = h' are the scores); then V^T
@@ -446,7 +459,9 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
             }
             __syncwarp();
         }
+        fine();
         wait_bar(0);
+        fine();
         {   // softmax of row t = lane of head q: every key group takes the row maximum over all keys and exponentiates its 8 keys;
             // P stays un-normalised, the partial sums meet when O is read out
             float sa[32], own[8];
@@ -469,7 +484,9 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
             bufQ[c * 128 + f] = hi;
             bufQ[TS_PLANE + c * 128 + f] = lo;
         }
+        fine();
         wait_bar(1);
+        fine();
         {   // V^T (lane = 32h + d, K = keys) -> A operand planes in tensor memory
             float a[8];
             tmem_ld<8>(tmem + ACC_V + 8 * c, a);
@@ -508,7 +525,9 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
 #pragma unroll
             for (int i = 0; i < 8; ++i) inv[i] = tokv[i] ? 1.f / s8[i] : 0.f;
         }
+        fine();
         wait_bar(0);
+        fine();
         stamp();
         {   // O^T -> activation operand of the output projection
             float a[8];
@@ -561,8 +580,11 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
             }
             __syncwarp();
         }
+        fine();
         wait_bar(0);
+        fine();
         resid_ln(bo_, g1, be1);
+        fine();
         stamp();
         // ---- FFN-1, token-major: D[token][F] = X^T W1^T.  A = bufX read as an MN-major A operand (rows >= 32 alias other data
         //      and only produce unused accumulator lanes), B = W1 [N = F][K = 128] K-major
@@ -594,7 +616,9 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
             }
             __syncwarp();
         }
+        fine();
         wait_bar(0);
+        fine();
         if (q == 0) {   // lanes 0..31 of the accumulator = tokens: the four quarter-0 warps take F/4 hidden units each
             const bool tv = lane < J;
             if (F == 16) {
@@ -656,8 +680,11 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
             }
             __syncwarp();
         }
+        fine();
         wait_bar(0);
+        fine();
         resid_ln(b2, g2, be2);
+        fine();
         g += 8 + nffn;
         stamp();
     }

@@ -451,7 +451,7 @@ def pack_token_program(J, enc=None, cross=None, fusion=None, C=128, fmt=None):
 
     def add_layer(Wq, Wk, Wv, Wo, W1, W2):
         layer_base.append(len(seq))
-        for W in (Wq, Wk, Wv, Wo):
+        for W in (Wk, Wq, Wv, Wo):   # consumption order of csrc/token_stack.cu: K first, so that V's weights can follow into K's slots
             add_mat(W)
         return add_ffn(W1, W2)
     Fc = D = L = F_ = 0

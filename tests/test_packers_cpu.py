@@ -92,8 +92,8 @@ def test_token_program_tiles_reconstruct_weights(path_params):
     p = path_params
     pk = ops.pack_token_program(21, enc=(p, "block1.init_TR."))
     seq = pk.wseq.tolist()
-    # entries: embedding (2), then per layer Q, K, V, O (2 each), FFN (1)
-    for name, e0 in (("query", 2), ("key", 4), ("value", 6)):
+    # entries: embedding (2), then per layer K, Q, V, O (2 each), FFN (1)
+    for name, e0 in (("key", 2), ("query", 4), ("value", 6)):
         W = p[f"block1.init_TR.bert.encoder.layer.0.attention.self.{name}.weight"]
         halves = []
         for h in range(2):
