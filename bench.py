@@ -103,6 +103,24 @@ def run_step(net, loader, d, seed):
     return res[-1]
 
 
+def joint_error_mm(net, ldr, host, n):
+    """mean joint error (mm) of the four joint sets on the first n samples of a timed input set vs the oracle (checker only)."""
+    from oracle import kpf_oracle as O
+    from keypointfusion_b200 import ops
+    from keypointfusion_b200.model.model import KPFusion
+    dev = next(net.parameters()).device
+    d = {k: v[:n].to(dev) for k, v in host.items()}
+    with torch.no_grad():
+        pcl, _ = ops.getpcl(d["img"], d["center"], d["cube"], d["M"], d["cam"], N_PTS, seed=0)
+        res, _, _ = net.forward_path(d["img_offset"], d["img_feat"], None, d["img_feat_rgb"], d["img"], pcl, ldr, d["center"], d["M"],
+                                     d["cube"], d["cam"], 0.8)
+        p = synth.fill_state_dict(KPFusion(joint_num=J), seed=0)
+        g = [host[k][:n].numpy() for k in ("center", "M", "cube", "cam")]
+        ores, _, _ = O.fusion_path(p, host["img"][:n], pcl.cpu(), host["img_offset"][:n].float(), host["img_feat"][:n].float(),
+                                   host["img_feat_rgb"][:n].float(), *g)
+    return [round(float(np.linalg.norm((res[2 + i].float().cpu().numpy() - ores[i].numpy()) * 125.0, axis=-1).mean()), 5) for i in range(4)]
+
+
 def cpu_reference_leg(B, iters, warm=1):
     """The reference algorithm on the host cores (oracle port), whole fusion path incl. getpcl. -> samples/s."""
     from oracle import kpf_oracle as O  # cpu_baseline leg only
@@ -137,6 +155,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--chains", type=int, default=1, help="sub-batch kernel chains captured on parallel streams inside the graph")
     ap.add_argument("--breakdown", action="store_true", help="also print per-stage CUDA-event times to stderr")
+    ap.add_argument("--config", default="path", choices=["path", "sweep", "full", "demo"],
+                    help="path: BASELINE configs[1] (default, the headline line); sweep: config 4; full: config 3; demo: config 5")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-this-GPU leg")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -166,6 +187,8 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the fusion path has no CPU fallback)"
     torch.cuda.set_device(local)
+    if a.config != "path":
+        return other_configs(a, rank, world, local)
     try:   # pin this rank to the CPUs next to its GPU before any pinned host buffer is first touched (8 ranks feed 8 PCIe links)
         import pynvml
         pynvml.nvmlInit()
@@ -347,12 +370,69 @@ def main():
             "gpu_launches": launches, "roofline": roof,
             "path_roofline": {"hbm_frac": value / world * PATH_BYTES_PER_SAMPLE / (hbm * 1e9),
                               "tensor_frac": value / world * PATH_FLOPS_PER_SAMPLE / (tfl * 1e12), "peaks": which}}
+    if rank == 0 and world == 1:
+        # parity of the exact configuration that was timed: a 4-sample slice of resident set 0 against the CPU oracle (the kernels are
+        # batch invariant, tests/test_modules_gpu.py)
+        line["joint_err_mm"] = joint_error_mm(net, ldr, hosts[0], 4)
+        if not a.no_eager_baseline:
+            import bench_extra as X
+            line["cuda_eager_baseline"] = X.cuda_eager_leg(dev, hosts[0])
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             sample_B, iters = 16, 3
             v, s_it = cpu_reference_leg(sample_B, iters)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{iters} passes over a {sample_B}-crop slice of the workload, torch threads={os.cpu_count()}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def other_configs(a, rank, world, local):
+    """BASELINE.json configs 3, 4, 5 (bench_extra.py): one JSON line each, same keys as the headline line where they apply."""
+    import bench_extra as X
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    hbm, tfl, which = load_peaks()
+    sampler = ClockSampler(local)
+    sampler.start()
+    W = max(a.warmup, 3)
+    base = {"n_gpus": world, "steps": a.steps, "warmup": W, "higher_is_better": True, "vs_baseline": None, "data": "synthetic"}
+    if a.config == "sweep":
+        assert world == 1, "the kernel sweep is a single-GPU configuration"
+        rows = X.sweep(dev, hbm)
+        k1 = next(r for r in rows if r["kernel"].startswith("backproject") and r["S"] == 128)
+        line = dict(base, metric="kernel sweep: back-projection + keypoint gather GB/s over crop sizes 64-256 and 21-42 joints",
+                    value=k1["GBs"], unit="GB/s (K1 at S=128; all rows in `sweep`)", scaling="weak", dtype="f32/bf16",
+                    config={"workload": "BASELINE.json configs[3]: K1, K2, K3, K4a, K4d over S in {64,96,128,192,256}, J in {21,42}, K7 at the ResNet-18 "
+                                        "stage shapes; batch 64; inputs rotate over resident sets (> L2 where the working set allows)"},
+                    sweep=rows, roofline={"bound": "hbm", "achieved": k1["GBs"], "peak": hbm, "unit": "GB/s", "frac": k1["GBs"] / hbm,
+                                          "traffic": None, "kernel": "backproject_kernel", "peaks": which})
+    else:
+        fn = X.full_model if a.config == "full" else X.demo
+        r = fn(dev, world, rank, a.steps, W, barrier=barrier)
+        ms = torch.tensor([r["ms_per_step"]], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            r["value"] = world * r["batch_per_gpu"] / (float(ms) / 1e3)
+            r["ms_per_step"] = float(ms)
+        wl = ("BASELINE.json configs[2]: full model inference = 2 x stock-PyTorch ConvNeXt-T UNet stand-in backbones (bf16, channels_last; out "
+              "of scope, utils/standin_backbone.py) + the fusion path, batch 512 sharded over the ranks") if a.config == "full" else \
+             ("BASELINE.json configs[4]: 640x480 uint16 depth + uint8 BGR frames -> bbox centre, crops (crop.cu), back-projection (K1), stand-in "
+              "backbones, fusion path; batch 128 sharded over the ranks")
+        line = dict(base, metric="full-model RGB-D samples/sec" if a.config == "full" else "in-the-wild RGB-D frames/sec",
+                    unit="samples/s", scaling="strong", dtype="bf16", config={"workload": wl, "batch_per_gpu": r["batch_per_gpu"],
+                                                                             "parallelism": f"batch-sharded x{world}"}, **r)
+    line["clocks"] = sampler.stop()
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

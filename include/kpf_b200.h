@@ -81,9 +81,11 @@ int kpf_pcl_joint2offset(const float* joint, const float* pcl, const float* kern
 /* ---- a8  model/model.py:297-306 K-tap weighted gathers ------------------------------------------------------------
  * feat: [B,C,HW] (dtype) with batch stride feat_batch_stride elements (lets a channel slice of a wider map be
  * passed); index [B,N,K] i64 (index_is_i64 != 0) or i32; closeness [B,N,K] f32.
- * out (dtype): element (b,n,c) at out[(b*N+n)*out_stride + out_c0 + c]  (out_stride >= out_c0 + C). */
+ * out (dtype): element (b,n,c) at out[(b*N+n)*out_stride + out_c0 + c]  (out_stride >= out_c0 + C).
+ * workspace: caller buffer of B*HW*ceil8(C) elements of dtype, 16-byte aligned (the map as channels-last rows; contents undefined).
+ * Two launches: TMA-staged transposition to rows, then the row gather. */
 int kpf_gather_taps(const void* feat, int dtype, long long feat_batch_stride, int B, int C, int HW, const void* index,
-                    int index_is_i64, const float* closeness, int N, int K, void* out, int out_stride, int out_c0,
+                    int index_is_i64, const float* closeness, int N, int K, void* out, int out_stride, int out_c0, void* workspace,
                     cudaStream_t stream);
 
 /* ---- a10  util/generateFeature.py:584-600 GFM.joint2heatmap: joint [B,J,joint_stride>=2] -> out [B,J,S,S] -------- */

@@ -1,72 +1,149 @@
 // K3 / a8: K-tap weighted gather of feature maps at the nearest-cell indices (model/model.py:297-306).
 //   out[b,n,c] = sum_k closeness[b,n,k] * feat[b,c,index[b,n,k]]
-// One CTA per (channel tile, sample).  The [CT x HW] feature tile is contiguous in the NCHW map, so it is
-// staged into shared memory by the TMA engine with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) completing
-// on an mbarrier; the random tap reads then hit shared memory, and each point's CT outputs are written as
-// one contiguous run of the [B,N,C] result.  HBM-bound: (C*HW + N*C)*e + N*K*12 bytes per sample.
+// The map is channel-major (NCHW) and the result point-major, so a tap of one point is C values HW apart: two kernels.
+//   rows_kernel   : [B,C,HW] -> [B,HW,Cp] (Cp = C rounded up to 8): a [32 channels x 64 cells] tile per CTA staged by the TMA engine
+//                   (1-D bulk copies of the 64-cell runs, cp.async.bulk -> SASS UBLKCP, completing on an mbarrier), transposed out of
+//                   shared memory with 16-byte stores.  One read + one write of the map at copy speed.
+//   gather_rows   : a tap is now ONE contiguous row: the lanes of a point read 16-byte chunks of its K rows (served by L2: the rows
+//                   were just written), accumulate in fp32 and write the point's C outputs as one contiguous run.
+// HBM-bound: (C*HW + N*C)*e + N*K*12 algorithmic bytes per sample (the row copy adds one L2-resident round trip of C*HW*e).
+// (Round 1's single kernel staged [16 x HW] channel tiles and read the taps out of shared memory: every lane of a warp hit the same
+//  bank -- the rows are 2048 B apart -- and it ran at 5 % of HBM.)
 #include "common.cuh"
 
 namespace kpf {
 
-template <typename T, typename I, int CT>
+constexpr int GR_CH = 32, GR_CELLS = 64;
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-gather_taps_kernel(const T* __restrict__ feat, long long feat_bs, int C, int HW, const I* __restrict__ index,
-                   const float* __restrict__ closeness, int N, int K, T* __restrict__ out, int out_stride, int out_c0) {
-    extern __shared__ __align__(128) unsigned char gsm[];
-    T* tile = reinterpret_cast<T*>(gsm);
+rows_kernel(const T* __restrict__ feat, long long feat_bs, int C, int HW, int Cp, T* __restrict__ rows) {
+    __shared__ __align__(128) T tile[GR_CH][GR_CELLS];
     __shared__ __align__(8) uint64_t bar;
-    const int b = blockIdx.y, c0 = blockIdx.x * CT;
-    const int ct = min(CT, C - c0);
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t row_bytes = (uint32_t)HW * sizeof(T);
-        mbar_expect_tx(&bar, row_bytes * ct);
-        const T* src = feat + (size_t)b * feat_bs + (size_t)c0 * HW;
-        for (int c = 0; c < ct; ++c) tma_bulk_g2s(tile + (size_t)c * HW, src + (size_t)c * HW, row_bytes, &bar);
-    }
-    mbar_wait(&bar, 0);
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const size_t o = ((size_t)b * N + n) * K;
-        float acc[CT];
-#pragma unroll
-        for (int c = 0; c < CT; ++c) acc[c] = 0.f;
-        for (int k = 0; k < K; ++k) {
-            const int idx = (int)index[o + k];
-            const float w = closeness[o + k];
-#pragma unroll
-            for (int c = 0; c < CT; ++c)
-                if (c < ct) acc[c] += to_f32(tile[c * HW + idx]) * w;
+    const int b = blockIdx.z, c0 = blockIdx.y * GR_CH, h0 = blockIdx.x * GR_CELLS, tid = threadIdx.x;
+    const int ct = min(GR_CH, C - c0), cells = min(GR_CELLS, HW - h0);
+    const T* src = feat + (size_t)b * feat_bs + (size_t)c0 * HW + h0;
+    const bool tma_ok = cells == GR_CELLS && ((size_t)HW * sizeof(T)) % 16 == 0 && ((uintptr_t)src % 16) == 0;
+    if (tma_ok) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
         }
-        T* dst = out + ((size_t)b * N + n) * out_stride + out_c0 + c0;
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (uint32_t)(ct * GR_CELLS * sizeof(T)));
+            for (int c = 0; c < ct; ++c) tma_bulk_g2s(&tile[c][0], src + (size_t)c * HW, GR_CELLS * sizeof(T), &bar);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (int i = tid; i < ct * GR_CELLS; i += 256) {
+            const int c = i / GR_CELLS, h = i - c * GR_CELLS;
+            tile[c][h] = h < cells ? src[(size_t)c * HW + h] : T(0);
+        }
+        __syncthreads();
+    }
+    // out: thread -> (cell, 8-channel group): a 16-byte (bf16) / 32-byte (f32) run of the cell's row
+    for (int i = tid; i < GR_CELLS * (GR_CH / 8); i += 256) {
+        const int g = i & (GR_CH / 8 - 1), cell = i >> 2;
+        if (cell >= cells || c0 + 8 * g >= Cp) continue;
+        T v[8];
 #pragma unroll
-        for (int c = 0; c < CT; ++c)
-            if (c < ct) dst[c] = from_f32<T>(acc[c]);
+        for (int k = 0; k < 8; ++k) v[k] = (8 * g + k < ct) ? tile[8 * g + k][cell] : T(0);
+        T* dst = rows + ((size_t)b * HW + h0 + cell) * Cp + c0 + 8 * g;
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+        } else {
+            reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(v)[0];
+            reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(v)[1];
+        }
+    }
+}
+
+template <typename T> struct Chunk;   // 16 bytes of a row
+template <> struct Chunk<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void fma(float* acc, const uint4& v, float w) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+            acc[2 * i] += f.x * w;
+            acc[2 * i + 1] += f.y * w;
+        }
+    }
+    static __device__ __forceinline__ uint4 pack(const float* a) {
+        uint4 o;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(a[0], a[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(a[2], a[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(a[4], a[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(a[6], a[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+        return o;
+    }
+};
+template <> struct Chunk<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void fma(float* acc, const uint4& v, float w) {
+        const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += f[i] * w;
+    }
+    static __device__ __forceinline__ uint4 pack(const float* a) { return *reinterpret_cast<const uint4*>(a); }
+};
+
+// thread -> (point, 16-byte chunk of the row); K <= 16 taps, four row loads in flight
+template <typename T, typename I>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const T* __restrict__ rows, int Cp, int C, int HW, const I* __restrict__ index, const float* __restrict__ closeness,
+                   long long n_points, int N, int K, T* __restrict__ out, int out_stride, int out_c0) {
+    constexpr int CN = Chunk<T>::N;
+    const int chunks = Cp / CN;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pt = t / chunks;
+    const int ck = (int)(t - pt * chunks);
+    if (pt >= n_points) return;
+    const long long b = pt / N;
+    const T* base = rows + (size_t)b * HW * Cp + (size_t)ck * CN;
+    float acc[CN];
+#pragma unroll
+    for (int i = 0; i < CN; ++i) acc[i] = 0.f;
+    const I* ix = index + pt * K;
+    const float* cw = closeness + pt * K;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        uint4 v[4];
+        float w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool ok = k0 + u < K;
+            w[u] = ok ? __ldg(cw + k0 + u) : 0.f;
+            const long long cell = ok ? (long long)ix[k0 + u] : 0;
+            v[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)cell * Cp));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Chunk<T>::fma(acc, v[u], w[u]);
+    }
+    T* dst = out + (size_t)pt * out_stride + out_c0 + ck * CN;
+    if (ck * CN + CN <= C && ((uintptr_t)dst % 16) == 0) {
+        *reinterpret_cast<uint4*>(dst) = Chunk<T>::pack(acc);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CN; ++i)
+            if (ck * CN + i < C) dst[i] = from_f32<T>(acc[i]);
     }
 }
 
 template <typename T, typename I>
 static int launch_gather(const T* feat, long long feat_bs, int B, int C, int HW, const I* index, const float* closeness, int N,
-                         int K, T* out, int out_stride, int out_c0, cudaStream_t stream) {
-    const size_t row = (size_t)HW * sizeof(T);
-    if (row % 16 != 0 || ((uintptr_t)feat % 16) != 0 || ((size_t)feat_bs * sizeof(T)) % 16 != 0) return KPF_ERR_BAD_ARGUMENT;
-#define KPF_GATHER(CTV)                                                                                                      \
-    {                                                                                                                        \
-        const size_t smem = row * CTV;                                                                                       \
-        cudaError_t e = kpf::set_smem(gather_taps_kernel<T, I, CTV>, smem); \
-        if (e != cudaSuccess) return (int)e;                                                                                 \
-        dim3 grid((C + CTV - 1) / CTV, B);                                                                                   \
-        gather_taps_kernel<T, I, CTV><<<grid, 256, smem, stream>>>(feat, feat_bs, C, HW, index, closeness, N, K, out, out_stride, out_c0); \
-    }
-    if (row * 16 <= 96 * 1024) KPF_GATHER(16)
-    else if (row * 8 <= 128 * 1024) KPF_GATHER(8)
-    else if (row * 2 <= 200 * 1024) KPF_GATHER(2)
-    else return KPF_ERR_UNSUPPORTED;
-#undef KPF_GATHER
+                         int K, T* out, int out_stride, int out_c0, T* rows, cudaStream_t stream) {
+    const int Cp = (C + 7) / 8 * 8;
+    dim3 g1((HW + GR_CELLS - 1) / GR_CELLS, (C + GR_CH - 1) / GR_CH, B);
+    rows_kernel<T><<<g1, 256, 0, stream>>>(feat, feat_bs, C, HW, Cp, rows);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const long long n_points = (long long)B * N, threads = n_points * (Cp / Chunk<T>::N);
+    gather_rows_kernel<T, I><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(rows, Cp, C, HW, index, closeness, n_points, N, K, out,
+                                                                                   out_stride, out_c0);
+    e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -74,24 +151,26 @@ static int launch_gather(const T* feat, long long feat_bs, int B, int C, int HW,
 
 extern "C" int kpf_gather_taps(const void* feat, int dtype, long long feat_batch_stride, int B, int C, int HW, const void* index,
                                int index_is_i64, const float* closeness, int N, int K, void* out, int out_stride, int out_c0,
-                               cudaStream_t stream) {
+                               void* workspace, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && C >= 1 && HW >= 1 && N >= 0 && K >= 1 && out_stride >= C + out_c0);
     if (B == 0 || N == 0) return 0;
+    KPF_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 16) == 0);
     if (dtype == KPF_F32) {
         if (index_is_i64)
             return launch_gather<float, long long>((const float*)feat, feat_batch_stride, B, C, HW, (const long long*)index, closeness,
-                                                   N, K, (float*)out, out_stride, out_c0, stream);
+                                                   N, K, (float*)out, out_stride, out_c0, (float*)workspace, stream);
         return launch_gather<float, int32_t>((const float*)feat, feat_batch_stride, B, C, HW, (const int32_t*)index, closeness, N, K,
-                                             (float*)out, out_stride, out_c0, stream);
+                                             (float*)out, out_stride, out_c0, (float*)workspace, stream);
     }
     if (dtype == KPF_BF16) {
         if (index_is_i64)
             return launch_gather<__nv_bfloat16, long long>((const __nv_bfloat16*)feat, feat_batch_stride, B, C, HW,
                                                            (const long long*)index, closeness, N, K, (__nv_bfloat16*)out, out_stride,
-                                                           out_c0, stream);
+                                                           out_c0, (__nv_bfloat16*)workspace, stream);
         return launch_gather<__nv_bfloat16, int32_t>((const __nv_bfloat16*)feat, feat_batch_stride, B, C, HW, (const int32_t*)index,
-                                                     closeness, N, K, (__nv_bfloat16*)out, out_stride, out_c0, stream);
+                                                     closeness, N, K, (__nv_bfloat16*)out, out_stride, out_c0,
+                                                     (__nv_bfloat16*)workspace, stream);
     }
     return KPF_ERR_UNSUPPORTED;
 }

@@ -481,8 +481,14 @@ class KPFusion(nn.Module):
             joint_xyz = r2d
         return result, spatial_weight, None
 
+    @staticmethod
+    def _as_backbone_input(x, backbone):
+        """the crops arrive fp32; a backbone kept in bf16 / channels_last (stock PyTorch, the caller's choice) gets them in its own dtype"""
+        p = next(backbone.parameters(), None)
+        return x if p is None or p.dtype == x.dtype else x.to(p.dtype)
+
     def forward(self, img_rgb, img, pcl, loader, center, M, cube, cam_para, kernel=0.8, writer=None, ii=0):
-        img_offset, img_feat = self.backbone_d(img)              # model.py:397 (stock PyTorch)
-        img_offset_rgb, img_feat_rgb = self.backbone_rgb(img_rgb)  # model.py:398
+        img_offset, img_feat = self.backbone_d(self._as_backbone_input(img, self.backbone_d))                  # model.py:397 (stock PyTorch)
+        img_offset_rgb, img_feat_rgb = self.backbone_rgb(self._as_backbone_input(img_rgb, self.backbone_rgb))  # model.py:398
         return self.forward_path(img_offset.detach(), img_feat, img_offset_rgb, img_feat_rgb, img, pcl, loader, center, M, cube,
                                  cam_para, kernel, writer, ii)

@@ -60,7 +60,7 @@ def launch_count():
     return _launches
 
 
-_KERNELS_PER_CALL = {"kpf_desa_fused": 2}   # entry points that launch more than one kernel
+_KERNELS_PER_CALL = {"kpf_desa_fused": 2, "kpf_gather_taps": 2}   # entry points that launch more than one kernel
 
 
 def _call(name, *args):
@@ -217,8 +217,9 @@ def gather_taps(feat, index, closeness, out=None, out_c0=0):
         out = torch.empty(B, N, C, device=feat.device, dtype=feat.dtype)
         out_c0 = 0
     assert out.dtype == feat.dtype and out.is_contiguous()
+    rows = torch.empty(B, HW, (C + 7) // 8 * 8, device=feat.device, dtype=feat.dtype)   # the map as channels-last rows (workspace)
     _call("kpf_gather_taps", _p(feat), _DT[feat.dtype], bs, B, C, HW, _p(index), int(index.dtype == torch.int64), _p(closeness), N, K,
-          _p(out), out.shape[-1], out_c0)
+          _p(out), out.shape[-1], out_c0, _p(rows))
     return out
 
 

@@ -25,9 +25,10 @@ class Pcl_utils(object):
         return pcl
 
     def depthTopcl(self, dpt, T, paras, background_val=torch.tensor(0.)):
-        """Every valid pixel back-projected to camera space, ordered row-major; rows past the per-sample count are
-        zero.  `dpt` here is the NORMALISED crop like getpcl's input is not available at this level in the
-        reference (util/img2pcl.py:42-64 is broken), so this entry returns normalised points for unit cube/centre."""
+        """dpt [B,S,S] depth crop in mm (0 = invalid), T [B,3,3] crop transform, paras [B,4] (fx,fy,fu,fv) -> (xyz [B,S*S,3] camera-space
+        mm, count [B]): every valid pixel back-projected like the numpy depthToPCL the reference actually runs (loader.py:874-893; its
+        torch port util/img2pcl.py:42-64 crashes), ordered row-major; rows past the per-sample count are zero.  Runs kpf_backproject_all
+        with centre 0 and cube 2 (so the normalisation is the identity); a pixel within 1e-5 of exactly 1.0 mm counts as background."""
         B = dpt.shape[0]
         zeros = torch.zeros(B, 3, device=dpt.device)
         two = torch.full((B, 3), 2.0, device=dpt.device)

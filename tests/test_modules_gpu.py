@@ -268,3 +268,73 @@ def test_fusion_path_single_sample(net):
         assert torch.equal(res4[k][:1], res1[k]), k
     for k in range(2):
         assert torch.equal(sw4[k][:1], sw1[k]), k
+
+
+def test_kpfusion_forward_with_backbones(path_params):
+    """KPFusion.forward end to end (model.py:395-426) with stock-PyTorch backbones of the reference's contract attached (a small
+    instance of utils/standin_backbone.py): backbone outputs -> fusion path, vs the oracle fed the SAME backbone outputs."""
+    from keypointfusion_b200 import ops
+    from keypointfusion_b200.dataloader.loader import loader
+    from keypointfusion_b200.model.model import KPFusion
+    from keypointfusion_b200.utils.standin_backbone import StandInBackbone
+    torch.manual_seed(3)
+    mk = lambda cin: StandInBackbone(cin, 21, depths=(1, 1, 1, 1), dims=(16, 32, 64, 128))
+    net = KPFusion(joint_num=21, backbone_rgb=mk(3), backbone_d=mk(1))
+    sd = net.state_dict()
+    sd.update(path_params)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    for m in (net.backbone_d, net.backbone_rgb):     # make the heads' outputs O(1) so the path is exercised with realistic magnitudes
+        for f in m.finals:
+            torch.nn.init.normal_(f.weight, std=0.2)
+    inp = synth.make_inputs(2, 128, 21, 128, seed=44)
+    c = {k: v.to(DEV) for k, v in inp.items()}
+    with torch.no_grad():
+        pcl, _ = ops.getpcl(c["img"], c["center"], c["cube"], c["M"], c["cam"], seed=4)
+        res, sw, _ = net(c["img_rgb"], c["img"], pcl, loader(img_size=128), c["center"], c["M"], c["cube"], c["cam"], 0.8)
+        off, feat = net.backbone_d(c["img"])
+        off_rgb, feat_rgb = net.backbone_rgb(c["img_rgb"])
+    assert torch.equal(res[0], off) and torch.equal(res[1], off_rgb)          # result[0:2] are the backbones' offset maps (model.py:426)
+    ores, osw, _ = O.fusion_path(path_params, inp["img"], pcl.cpu(), off.float().cpu(), feat.float().cpu(), feat_rgb.float().cpu(),
+                                 inp["center"].numpy(), inp["M"].numpy(), inp["cube"].numpy(), inp["cam"].numpy())
+    for k in range(4):
+        assert mm_err(res[2 + k], ores[k].numpy()) <= 0.05, k
+    # and with the backbones held in bf16 (the caller's choice): the path consumes bf16 maps, KPFusion.forward casts the crops
+    net.backbone_d.bfloat16(), net.backbone_rgb.bfloat16()
+    seen = {}
+    hooks = [net.backbone_d.register_forward_hook(lambda m, i, o: seen.__setitem__("d", o)),
+             net.backbone_rgb.register_forward_hook(lambda m, i, o: seen.__setitem__("rgb", o))]
+    with torch.no_grad():
+        res16, _, _ = net(c["img_rgb"], c["img"], pcl, loader(img_size=128), c["center"], c["M"], c["cube"], c["cam"], 0.8)
+    for h in hooks:
+        h.remove()
+    (off16, feat16), (_, feat_rgb16) = seen["d"], seen["rgb"]     # the maps this very forward produced (bf16 cuDNN runs need not repeat bit for bit)
+    assert off16.dtype == torch.bfloat16 and res16[2].dtype == torch.float32
+    ores16, _, _ = O.fusion_path(path_params, inp["img"], pcl.cpu(), off16.float().cpu(), feat16.float().cpu(), feat_rgb16.float().cpu(),
+                                 inp["center"].numpy(), inp["M"].numpy(), inp["cube"].numpy(), inp["cam"].numpy())
+    for k in range(4):
+        assert mm_err(res16[2 + k], ores16[k].numpy()) <= 0.05, k
+
+
+def test_pcl_utils_depthTopcl(golden_inputs):
+    """Pcl_utils.depthTopcl (util/img2pcl.py:42-64; the reference's version crashes): every valid pixel of a depth map
+    (mm, 0 = invalid) back-projected through T^-1 and the pinhole model, row-major order == the numpy depthToPCL the reference
+    runs (loader.py:874-893), via the oracle."""
+    from keypointfusion_b200.util.img2pcl import Pcl_utils
+    i = golden_inputs
+    B, S = 2, 128
+    dpt = (i["img"][:, 0] * 125.0 + i["center"][:, 2].view(B, 1, 1)).clone()
+    dpt[i["img"][:, 0] == 1.0] = 0.0                                          # background -> 0 (invalid), loader.py:845-847
+    xyz, count = Pcl_utils().depthTopcl(dpt.to(DEV), i["M"].to(DEV), i["cam"].to(DEV))
+    for b in range(B):
+        d = dpt[b].numpy()
+        rr, cc = np.nonzero(np.abs(d) > 1e-8)
+        Mi = np.linalg.inv(i["M"][b].numpy().astype(np.float64))
+        q = Mi @ np.stack([cc + 0.5, rr + 0.5, np.ones_like(rr, dtype=np.float64)])
+        q = q / q[2]
+        fx, fy, fu, fv = i["cam"][b].numpy().astype(np.float64)
+        ref = np.stack([(q[0] - fu) / fx * d[rr, cc], (q[1] - fv) / fy * d[rr, cc], d[rr, cc].astype(np.float64)], 1)
+        assert int(count[b]) == len(rr)
+        got = xyz[b, :len(rr)].cpu().numpy()
+        assert np.allclose(got, ref, rtol=2e-5, atol=2e-3), np.abs(got - ref).max()
+        assert not xyz[b, len(rr):].any()
