@@ -215,11 +215,23 @@ def main():
     pinned = [{k: v.pin_memory() for k, v in h.items()} for h in hosts]
     gathered = torch.empty(world * B, J, 3, device=dev) if world > 1 else None
 
-    from keypointfusion_b200.runtime import GraphedFusionPath
-    graphed = None if a.no_graph else GraphedFusionPath(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains)
+    from keypointfusion_b200.runtime import GraphedFusionPath, PeerExchange
+    # the exchange step: fused into the last kernel of the path (peer stores over NVLink + arrival counter, runtime.PeerExchange),
+    # captured inside the graph; KPF_EXCHANGE=nccl falls back to a per-step ncclAllGather issued from the host
+    comm = "none"
+    px = None
+    if world > 1 and not a.no_graph and os.environ.get("KPF_EXCHANGE", "peer") == "peer":
+        try:
+            px = PeerExchange(B, J, dev)
+            comm = "fused peer stores into symmetric memory (no NCCL call on the data path; NCCL_DEBUG logs stay empty)"
+        except Exception as ex:   # no peer access / symmetric memory on this box
+            print(f"[bench] PeerExchange unavailable ({type(ex).__name__}: {ex}); using ncclAllGather", file=sys.stderr)
+    if world > 1 and px is None:
+        comm = "ncclAllGather of [B_local,21,3] per step, issued from the host"
+    graphed = None if a.no_graph else GraphedFusionPath(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains, exchange=px)
     # device-resident leg: one graph captured directly over each resident input set (no staging copies in the timed region)
-    bound = {} if a.no_graph else {id(d): GraphedFusionPath(net, ldr, d, sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains, bind=True)
-                                   for d in sets}
+    bound = {} if a.no_graph else {id(d): GraphedFusionPath(net, ldr, d, sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains, bind=True,
+                                                            exchange=px) for d in sets}
 
     def step(i, d):
         """d: a dict of device tensors (resident inputs) or of pinned host tensors (e2e)."""
@@ -231,8 +243,8 @@ def main():
             if not d["img"].is_cuda:
                 d = {k: v.to(dev, non_blocking=True) for k, v in d.items()}
             joints = run_step(net, ldr, d, seed=i)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, joints.contiguous())  # the path's one exchange step
+        if world > 1 and px is None:
+            dist.all_gather_into_tensor(gathered, joints.contiguous())  # the path's one exchange step (NCCL fallback)
         return joints
 
     def barrier():
@@ -244,11 +256,15 @@ def main():
         with torch.no_grad():
             for i in range(warmup):
                 fn(i)
+            if px is not None:
+                px.flush()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(steps):
                 fn(warmup + i)
+            if px is not None:
+                px.flush()          # the last step's gather completes inside the timed region
             e1.record()
             barrier()
         ms = e0.elapsed_time(e1)
@@ -310,7 +326,7 @@ def main():
     else:
         # public serving API: double-buffered graphs, H2D of step i+1 overlaps compute of step i, host reads step i-1's joints
         from keypointfusion_b200.runtime import PipelinedRunner
-        runner = PipelinedRunner(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0)
+        runner = PipelinedRunner(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0, exchange=px)
         # the caller's host buffers: pinned arenas handed out by the runner (one upload per step), filled with the same data
         host_sets = []
         for h in hosts:
@@ -323,7 +339,7 @@ def main():
 
         def pipe_step(i):
             pending.append(runner.submit(host_sets[i % NSETS]))
-            if world > 1:
+            if world > 1 and px is None:
                 dist.all_gather_into_tensor(gathered, runner.paths[pending[-1]].out["joints"].contiguous())
             if len(pending) > 1:
                 runner.fetch(pending.pop(0))       # host-side read of the previous step's result
@@ -332,6 +348,8 @@ def main():
                 pipe_step(i)
             while pending:
                 runner.fetch(pending.pop(0))
+            if px is not None:
+                px.flush()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -339,6 +357,8 @@ def main():
                 pipe_step(W + i)
             while pending:
                 runner.fetch(pending.pop(0))       # the last result is read inside the timed region too
+            if px is not None:
+                px.flush()
             e1.record()
             barrier()
         ms_e2e = e0.elapsed_time(e1)
@@ -367,7 +387,7 @@ def main():
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * J * 3 * 4,
                     "h2d_gb_per_s": round(h2d * (e2e / world / B) / 1e9, 1),
                     "note": "upload-bound: one pinned-arena cudaMemcpyAsync per step, overlapped with compute (profiles/h2d_ceiling.py measures the link)"},
-            "gpu_launches": launches, "roofline": roof,
+            "gpu_launches": launches, "comm": comm, "roofline": roof,
             "path_roofline": {"hbm_frac": value / world * PATH_BYTES_PER_SAMPLE / (hbm * 1e9),
                               "tensor_frac": value / world * PATH_FLOPS_PER_SAMPLE / (tfl * 1e12), "peaks": which}}
     if rank == 0 and world == 1:

@@ -159,7 +159,23 @@ int kpf_ball_query(const float* xyz, const float* centers, int B, int Np, int J,
 int kpf_token_stack(const float* x, const float* y, const float* r3d, const float* desa, const float* jf, const void* wmat,
                     const void* wseq, const float* wvec, int n_weights, int cross, int pre, int B, int J, int D, int L, int F, int Fc,
                     int fmt, float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride, int out_jc_c0,
+                    const void* peer_bases, const int* xstep, int world, int row0, int rows_total /* fused exchange step, see below */,
                     long long* dbg /* NULL, or 64 x int64 device: clock64 stamps of CTA 0 (profiling aid) */, cudaStream_t stream);
+
+/* ---- the path's one exchange step, fused into the kernel that produces the joints (the reference gathers through
+ * DataParallel, train.py:81).  Every rank owns an exchange buffer at the SAME offsets in peer-accessible (symmetric) memory:
+ *   bytes [0,64): header, u32 `arrived` at 0 (zero initially);  then two halves of [rows_total, J, 3] f32 (double buffered by step parity).
+ * kpf_token_stack with peer_bases != NULL (device array of `world` u64 base addresses of those buffers, xstep = device int step counter,
+ * row0 = this rank's first row) stores pred ALSO into half (*xstep & 1), rows [row0, row0+B), of EVERY rank's buffer with peer stores
+ * over NVLink and then counts the sample as arrived on every rank (system-scope release add).
+ * kpf_exchange_wait is the receiving side; `inflight` is a device int flag (zero initially) saying a step's joints are on their way:
+ *   mode 0, launched at the START of a step: completes the previous step if one is in flight (waits until `samples_per_step`
+ *           (= rows_total) samples have arrived here, increments *xstep) -- by then the other ranks have long finished it, so no
+ *           per-step rank skew sits on the critical path -- and marks the new step in flight;
+ *   mode 1: completes the step in flight (end of a run / before a consumer reads the gathered tensor).
+ * The gathered joints of the step whose index was *xstep when it ran are in half (index & 1).
+ * No NCCL call, no host involvement; every rank must run the same number of steps. */
+int kpf_exchange_wait(const void* exchange_buffer, int* xstep, int samples_per_step, int* inflight, int mode, cudaStream_t stream);
 
 /* ---- a7-a9 fused point stage (csrc/point_embed.cu), model/model.py:295-320 ------------------------------------------
  * kpf_repack_features: f_d, f_rgb [B,128,HW], f_w [B,J,HW] (batch stride w_batch_stride elements; = img_offset[:,4J:])

@@ -55,7 +55,15 @@ struct TokParams {
     int out_jc_stride, out_jc_c0;
     int B, J, D, L, F, pre, cross, Fc, G, fmt;
     long long* dbg;        // optional: clock64 stamps of CTA 0 (profiling aid)
+    // fused exchange step: pred is ALSO stored straight into every rank's gathered-joints buffer over NVLink
+    const unsigned long long* peer_bases;   // null, or [world] base addresses of the ranks' symmetric exchange buffers
+    const int* xstep;                       // device step counter (its parity selects the half of the double-buffered result)
+    int world, row0, rows_total;            // this rank's first row and the total rows of the gathered tensor
 };
+
+// Exchange buffer layout (identical on every rank; 64-byte header, then two [rows_total, J, 3] f32 halves):
+//   u32 arrived : cumulative count of samples whose joints have landed here, from all ranks (system-scope release adds)
+constexpr int XCHG_HEADER_FLOATS = 16;
 
 // erf-GELU with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7)
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -717,7 +725,18 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) o += sHead[((part * 4 + qq) * 4 + cc) * 32 + 3 * i + k];
                 p.pred_out[((size_t)b * J + t) * 3 + k] = o;
+                if (p.peer_bases) {   // the exchange step: the same value into every rank's gathered tensor, peer stores over NVLink
+                    const size_t off = XCHG_HEADER_FLOATS + ((size_t)(*p.xstep & 1) * p.rows_total + p.row0 + b) * J * 3 + (size_t)t * 3 + k;
+                    for (int r = 0; r < p.world; ++r) reinterpret_cast<float*>(p.peer_bases[r])[off] = o;
+                }
             }
+        }
+        if (p.peer_bases) {
+            __threadfence_system();   // this thread's peer stores are visible system-wide ...
+            wsync();
+            if (tid == 0)             // ... before the sample is counted as arrived on every rank
+                for (int r = 0; r < p.world; ++r)
+                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.peer_bases[r]) : "memory");
         }
     }
     stamp();
@@ -730,10 +749,39 @@ constexpr size_t TS_SMEM = (size_t)(TS_RING * TS_SLOT + 8 * TS_PLANE + 128) * 16
 
 }  // namespace kpf
 
+// The receiving side of the fused exchange.  `inflight` (device flag) says whether a step's joints are still on their way:
+//   mode 0 (begin a step): if a step is in flight, wait until all `per_step` samples of it have landed here and advance the step counter
+//                          (so the wait for step s overlaps nothing but is issued at the START of step s+1, when the other ranks have
+//                          long finished step s: no per-step rank skew on the critical path); then mark the new step in flight;
+//   mode 1 (flush)       : complete the step in flight, if any (end of a run, or before a consumer reads the gathered tensor).
+// One thread; the spin is clock-bounded like every wait in this library.
+__global__ void exchange_wait_kernel(const unsigned int* arrived, int* xstep, unsigned int per_step, int* inflight, int mode) {
+    if (*inflight) {
+        const unsigned int expected = ((unsigned int)*xstep + 1u) * per_step;
+        const long long t0 = clock64();
+        while (true) {
+            unsigned int v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(arrived) : "memory");
+            if ((int)(v - expected) >= 0) break;
+            if (clock64() - t0 > 8000000000ll) __trap();   // ~4 s: a rank that never arrives is a failed launch, not a hung GPU
+        }
+        *xstep = *xstep + 1;
+    }
+    *inflight = mode == 0 ? 1 : 0;
+}
+
+extern "C" int kpf_exchange_wait(const void* exchange_buffer, int* xstep, int samples_per_step, int* inflight, int mode, cudaStream_t stream) {
+    KPF_REQUIRE(exchange_buffer != nullptr && xstep != nullptr && inflight != nullptr && samples_per_step >= 1 && (mode == 0 || mode == 1));
+    exchange_wait_kernel<<<1, 1, 0, stream>>>((const unsigned int*)exchange_buffer, xstep, (unsigned int)samples_per_step, inflight, mode);
+    KPF_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d, const float* desa, const float* jf, const void* wmat,
                                const void* wseq, const float* wvec, int n_weights, int cross, int pre, int B, int J, int D, int L, int F,
                                int Fc, int fmt, float* tokens_out, float* pred_out, float* out_cj, float* out_jc, int out_jc_stride,
-                               int out_jc_c0, long long* dbg, cudaStream_t stream) {
+                               int out_jc_c0, const void* peer_bases, const int* xstep, int world, int row0, int rows_total,
+                               long long* dbg, cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(B >= 0 && J >= 1 && J <= 32 && L >= 0 && (cross || pre || L > 0));
     KPF_REQUIRE(fmt == FMT_F16 || fmt == FMT_BF16);
@@ -752,6 +800,8 @@ extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d,
     p.tokens_out = tokens_out; p.pred_out = pred_out; p.out_cj = out_cj; p.out_jc = out_jc; p.out_jc_stride = out_jc_stride;
     p.out_jc_c0 = out_jc_c0; p.B = B; p.J = J; p.D = D; p.L = L; p.F = F; p.pre = pre; p.cross = cross; p.Fc = Fc; p.G = n_weights; p.fmt = fmt;
     p.dbg = dbg;
+    KPF_REQUIRE(peer_bases == nullptr || (xstep != nullptr && world >= 1 && row0 >= 0 && row0 + B <= rows_total && L > 0));
+    p.peer_bases = (const unsigned long long*)peer_bases; p.xstep = xstep; p.world = world; p.row0 = row0; p.rows_total = rows_total;
     cudaError_t e = kpf::set_smem(token_stack_kernel, TS_SMEM);
     if (e != cudaSuccess) return (int)e;
     e = kpf::launch_pdl(token_stack_kernel, dim3(B), dim3(TS_NT), TS_SMEM, stream, p);

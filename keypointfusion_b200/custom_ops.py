@@ -210,20 +210,24 @@ def _(e, part_acc, part_ms, pcl, joint, wmat, wvec, r0, r1, r2, nsample, fmt):
 @_op("token_stack")
 def token_stack(wmat: Tensor, wseq: Tensor, wvec: Tensor, cross: int, pre: int, D: int, L: int, F: int, Fc: int, J: int, fmt: int,
                 want_tokens: bool, x: Optional[Tensor] = None, y: Optional[Tensor] = None, r3d: Optional[Tensor] = None,
-                desa: Optional[Tensor] = None, jf: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
-    """-> (tokens [B,J,128] or EMPTY, pred [B,J,3] or EMPTY); cross-only programs: tokens = the layer output [B,J,128]."""
+                desa: Optional[Tensor] = None, jf: Optional[Tensor] = None, peer_ptrs: Optional[Tensor] = None,
+                xstep: Optional[Tensor] = None, row0: int = 0, rows_total: int = 0) -> Tuple[Tensor, Tensor]:
+    """-> (tokens [B,J,128] or EMPTY, pred [B,J,3] or EMPTY); cross-only programs: tokens = the layer output [B,J,128].
+    peer_ptrs / xstep / row0 / rows_total: the fused exchange step (writes into the ranks' symmetric buffers, which are not arguments)."""
     pk = ops.TokenProgram(wmat, wseq, wvec, cross, pre, D, L, F, Fc, J, fmt)
+    xch = (peer_ptrs, xstep, row0, rows_total) if peer_ptrs is not None else None
     ref = x if x is not None else desa
     if L == 0 and cross:   # cross layer alone: [B,J,128] through the strided output
         out = torch.empty(ref.shape[0], J, 128, device=ref.device, dtype=torch.float32)
         ops.token_stack(pk, x=x, y=y, out_jc=out, out_jc_c0=0)
         return out, _empty(ref.device)
-    tokens, pred, _ = ops.token_stack(pk, x=x, y=y, r3d=r3d, desa=desa, jf=jf, want_tokens=want_tokens)
+    tokens, pred, _ = ops.token_stack(pk, x=x, y=y, r3d=r3d, desa=desa, jf=jf, want_tokens=want_tokens, exchange=xch)
     return (tokens if tokens is not None else _empty(ref.device)), (pred if pred is not None else _empty(ref.device))
 
 
 @token_stack.register_fake
-def _(wmat, wseq, wvec, cross, pre, D, L, F, Fc, J, fmt, want_tokens, x=None, y=None, r3d=None, desa=None, jf=None):
+def _(wmat, wseq, wvec, cross, pre, D, L, F, Fc, J, fmt, want_tokens, x=None, y=None, r3d=None, desa=None, jf=None, peer_ptrs=None, xstep=None,
+      row0=0, rows_total=0):
     ref = x if x is not None else desa
     B = ref.shape[0]
     has_tok = (L == 0 and cross) or (want_tokens and (L > 0 or (pre and not cross)))
@@ -317,10 +321,12 @@ def _(pred, gt, cube):
     return pred.new_empty(B, J, dtype=torch.float32), pred.new_empty(B, J, dtype=torch.float32)
 
 
-def run_token_program(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=True):
-    """TokenProgram (plain Python holder of three tensors + ints) -> the custom op.  Returns (tokens | None, pred | None)."""
+def run_token_program(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=True, exchange=None):
+    """TokenProgram (plain Python holder of three tensors + ints) -> the custom op.  Returns (tokens | None, pred | None).
+    exchange: a runtime.PeerExchange (the fused exchange step) or None."""
+    xa = (exchange.peer_ptrs, exchange.xstep, exchange.row0, exchange.rows_total) if exchange is not None else (None, None, 0, 0)
     tok, pred = torch.ops.kpf.token_stack(pk.wmat, pk.wseq, pk.wvec, pk.cross, pk.pre, pk.D, pk.L, pk.F, pk.Fc, pk.J, pk.fmt, want_tokens,
-                                          x, y, r3d, desa, jf)
+                                          x, y, r3d, desa, jf, *xa)
     return (tok if tok.numel() else None), (pred if pred.numel() else None)
 
 

@@ -380,7 +380,7 @@ class Block_KPFusion(_KernelCache, nn.Module):
                     pe_wvec=pe_wvec)
 
     def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
-                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None, rgb_planes=None, point_order=None):
+                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None, rgb_planes=None, point_order=None, exchange=None):
         """model.py:287-351.  Five launches, all hand-written split-precision tcgen05 kernels (fp32-class results for bf16 AND
         fp32 feature maps -- an fp32 map is carried as two bf16 planes):
             point stage (K4b + K3 + embeddings + softmax partials) -> DESA -> [fusion conv + init_TR] -> K5 -> [crossTR + final_TR]
@@ -416,7 +416,7 @@ class Block_KPFusion(_KernelCache, nn.Module):
             self.weight_dis, self.fc_spatial2joint_feature.weight, self.fc_spatial2joint_feature.bias, float(loader.img_size),
             float(loader.flip), 0.8, 1.0, 10.0, fmt, updated_2d_feature)                                  # model.py:334-344
         _, refined_2d_joints = cops.run_token_program(k["tok_final"], x=img_feat_j, y=outfeature_init_TR, r3d=refined_3d_joints,
-                                                      want_tokens=False)                                  # model.py:347-349
+                                                      want_tokens=False, exchange=exchange)               # model.py:347-349
         return refined_3d_joints, refined_2d_joints, img_feat_j, spatial_weight_loss, None
 
 
@@ -450,8 +450,9 @@ class KPFusion(nn.Module):
             setattr(self, f"block{i + 1}", Block_KPFusion(joint_num=joint_num))
 
     def forward_path(self, img_offset, img_feat, img_offset_rgb, img_feat_rgb, img, pcl, loader, center, M, cube, cam_para, kernel=0.8,
-                     writer=None, ii=0):
-        """model.py:399-426: everything after the backbones."""
+                     writer=None, ii=0, exchange=None):
+        """model.py:399-426: everything after the backbones.  exchange: a runtime.PeerExchange -- the last block's final kernel then
+        also writes its joints into every rank's gathered tensor (the path's one exchange step, fused)."""
         J = self.joint_num
         H = img_feat.shape[2]
         K = torch.ops.kpf
@@ -475,7 +476,8 @@ class KPFusion(nn.Module):
             block = getattr(self, f"block{i + 1}")
             r3d, r2d, updated_2d_feature[i + 1], spatial_weight[i], _ = block(
                 img_feat, img_feat_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature[i], loader, img_down,
-                center, M, cube, cam_para, writer, ii, featT=featT, rgb_planes=rgb_planes, point_order=order)
+                center, M, cube, cam_para, writer, ii, featT=featT, rgb_planes=rgb_planes, point_order=order,
+                exchange=exchange if i == self.num_stages - 1 else None)
             result.append(r3d)
             result.append(r2d)
             joint_xyz = r2d

@@ -505,8 +505,11 @@ def pack_token_program(J, enc=None, cross=None, fusion=None, C=128, fmt=None):
                         fmt)
 
 
-def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=True, out_jc=None, out_jc_c0=0, want_cj=False, dbg=None):
-    """Run one packed token program.  Returns (tokens [B,J,128] | None, pred [B,J,3] | None, out_cj [B,128,J] | None)."""
+def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=True, out_jc=None, out_jc_c0=0, want_cj=False, dbg=None,
+                exchange=None):
+    """Run one packed token program.  Returns (tokens [B,J,128] | None, pred [B,J,3] | None, out_cj [B,128,J] | None).
+    exchange = (peer_ptrs [world] i64 device, xstep [1] i32 device, row0, rows_total): pred is also stored into every rank's gathered
+    buffer (runtime.PeerExchange)."""
     ref = x if x is not None else desa
     dev = ref.device
     B = ref.shape[0]
@@ -521,8 +524,16 @@ def token_stack(pk, x=None, y=None, r3d=None, desa=None, jf=None, want_tokens=Tr
     out_cj = torch.empty(B, 128, J, device=dev, dtype=torch.float32) if (want_cj and pk.L == 0) else None
     stride = out_jc.shape[-1] if out_jc is not None else 0
     _call("kpf_token_stack", _p(x), _p(y), _p(r3d), _p(desa), _p(jf), _p(pk.wmat), _p(pk.wseq), _p(pk.wvec), pk.n_weights, pk.cross, pk.pre,
-          B, J, pk.D, pk.L, pk.F, pk.Fc, pk.fmt, _p(tokens), _p(pred), _p(out_cj), _p(out_jc), stride, out_jc_c0, _p(dbg))
+          B, J, pk.D, pk.L, pk.F, pk.Fc, pk.fmt, _p(tokens), _p(pred), _p(out_cj), _p(out_jc), stride, out_jc_c0,
+          _p(exchange[0]) if exchange else None, _p(exchange[1]) if exchange else None, exchange[0].numel() if exchange else 0,
+          int(exchange[2]) if exchange else 0, int(exchange[3]) if exchange else 0, _p(dbg))
     return tokens, pred, out_cj
+
+
+def exchange_wait(buf, xstep, samples_per_step, inflight, flush=False):
+    """Receiving side of the fused exchange (runtime.PeerExchange; include/kpf_b200.h: kpf_exchange_wait): begin a step (completing the
+    previous one if it is in flight) or, with flush=True, complete the step in flight."""
+    _call("kpf_exchange_wait", _p(buf), _p(xstep), int(samples_per_step), _p(inflight), 1 if flush else 0)
 
 
 # ------------------------------------------------------------------------------------------------ fused point stage

@@ -12,12 +12,13 @@ class GraphedFusionPath:
     img_offset [B,5J,H,H] (bf16 or f32), center [B,3], M [B,3,3], cube [B,3], cam [B,4]."""
     KEYS = ("img", "img_feat", "img_feat_rgb", "img_offset", "center", "M", "cube", "cam")
 
-    def __init__(self, net, loader, example, sample_num=1024, kernel=0.8, seed=0, warmup=2, chains=1, bind=False):
+    def __init__(self, net, loader, example, sample_num=1024, kernel=0.8, seed=0, warmup=2, chains=1, bind=False, exchange=None):
         """chains > 1: the batch is split into `chains` contiguous sub-batches whose (latency-bound, small-grid) kernel chains
         are captured on parallel streams inside the one graph, so they overlap on the 148 SMs; results are identical.
         bind=True: capture directly over the caller's (device-resident) `example` tensors instead of private static buffers;
         `__call__()` then replays with no staging copy and reads whatever those tensors hold at replay time."""
         self.net, self.loader, self.sample_num, self.kernel, self.seed = net, loader, sample_num, kernel, seed
+        self.exchange = exchange    # a PeerExchange: the fused all-gather of the joints is part of the captured graph
         self.chains = max(1, min(chains, example["img"].shape[0]))
         self.sm_share = float(__import__("os").environ.get("KPF_SM_SHARE", "1.0"))   # x SMs / chains per chain's persistent kernels
         dev = next(net.parameters()).device
@@ -34,6 +35,10 @@ class GraphedFusionPath:
                 self._run()
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
+        if exchange is not None:
+            with torch.cuda.stream(self.stream):
+                exchange.flush()    # complete the last warm-up step's gather
+            exchange.sync_ranks()   # every rank has finished the same number of (exchanging) warm-up steps before anyone captures
         self.graph = torch.cuda.CUDAGraph()
         # captured on the warm-up stream: per-stream persistent workspaces (ops._zero_counters) already exist, so no fill node
         # lands inside the graph (it would also cut the programmatic-launch chain between two kernels)
@@ -42,9 +47,11 @@ class GraphedFusionPath:
         self.launches_per_replay = self._count
 
     def _chain(self, s):
+        if self.exchange is not None:
+            self.exchange.begin_step()   # completes the PREVIOUS step's gather (normally already there) and opens this one
         pcl, count = ops.getpcl(s["img"], s["center"], s["cube"], s["M"], s["cam"], self.sample_num, seed=self.seed)
         res, sw, _ = self.net.forward_path(s["img_offset"], s["img_feat"], None, s["img_feat_rgb"], s["img"], pcl, self.loader, s["center"],
-                                           s["M"], s["cube"], s["cam"], self.kernel)
+                                           s["M"], s["cube"], s["cam"], self.kernel, exchange=self.exchange)
         return res, sw, pcl
 
     def _run(self):
@@ -95,6 +102,55 @@ def all_gather_joints(joints, out=None):
         out = joints.new_empty((dist.get_world_size() * joints.shape[0],) + tuple(joints.shape[1:]))
     dist.all_gather_into_tensor(out, joints)
     return out
+
+
+class PeerExchange:
+    """The path's one exchange step without NCCL: every rank's final kernel stores its [B_local,J,3] joints straight into EVERY rank's
+    gathered tensor over NVLink (peer stores into symmetric memory) and counts the samples as arrived; `wait()` enqueues the one-thread
+    kernel that holds the stream until all `world * B_local` samples of the step are there (include/kpf_b200.h: kpf_exchange_wait).
+    The gathered tensor is double buffered by step parity, so a fast rank's next step never overwrites what a slow rank still reads.
+
+    Symmetric memory comes from torch.distributed._symmetric_memory (CUDA IPC / fabric handles over NVLink on one node); all ranks
+    must construct this collectively and run the same number of steps."""
+    HEADER_FLOATS = 16
+
+    def __init__(self, b_local, joints, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.b_local, self.J = int(b_local), int(joints)
+        self.rows_total, self.row0 = self.world * self.b_local, self.rank * self.b_local
+        half = self.rows_total * self.J * 3
+        self.buf = symm.empty(self.HEADER_FLOATS + 2 * half, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.peer_ptrs = torch.tensor([int(p_) for p_ in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.xstep = torch.zeros(1, dtype=torch.int32, device=device)      # steps completed (device side: graph replays advance it)
+        self.inflight = torch.zeros(1, dtype=torch.int32, device=device)   # a step's joints are on their way
+        self.halves = [self.buf[self.HEADER_FLOATS + h * half:self.HEADER_FLOATS + (h + 1) * half].view(self.rows_total, self.J, 3) for h in (0, 1)]
+        torch.cuda.synchronize(device)
+        self.sync_ranks()
+
+    def sync_ranks(self):
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.buf.device)
+        dist.barrier(self.group)
+
+    def begin_step(self):
+        """Enqueue at the START of a step: completes the previous step's gather if one is in flight (the other ranks finished it long
+        ago, so this normally does not stall) and opens the new step."""
+        ops.exchange_wait(self.buf, self.xstep, self.rows_total, self.inflight)
+
+    def flush(self):
+        """Complete the step in flight (end of a run, or before the gathered tensor is read)."""
+        ops.exchange_wait(self.buf, self.xstep, self.rows_total, self.inflight, flush=True)
+
+    def gathered(self):
+        """[world * B_local, J, 3] joints of the most recently COMPLETED step (call flush() first to complete the one in flight);
+        reads the device step counter (one host sync)."""
+        done = int(self.xstep.item())
+        return self.halves[(done - 1) & 1]
 
 
 def shard_batch(n_items, rank, world):
