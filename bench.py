@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--config", default="path", choices=["path", "sweep", "full", "demo"],
                     help="path: BASELINE configs[1] (default, the headline line); sweep: config 4; full: config 3; demo: config 5")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-this-GPU leg")
+    ap.add_argument("--overlap", type=int, default=2, help="consecutive steps kept in flight on this many streams (1 = strictly serial)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -215,14 +216,18 @@ def main():
     pinned = [{k: v.pin_memory() for k, v in h.items()} for h in hosts]
     gathered = torch.empty(world * B, J, 3, device=dev) if world > 1 else None
 
-    from keypointfusion_b200.runtime import GraphedFusionPath, PeerExchange
+    from keypointfusion_b200.runtime import GraphedFusionPath, OverlappedSteps, PeerExchange
+    S_OV = 1 if a.no_graph else max(1, a.overlap)
+    assert NSETS % S_OV == 0, "--overlap must divide the number of resident input sets (4)"
     # the exchange step: fused into the last kernel of the path (peer stores over NVLink + arrival counter, runtime.PeerExchange),
     # captured inside the graph; KPF_EXCHANGE=nccl falls back to a per-step ncclAllGather issued from the host
     comm = "none"
     px = None
+    pxs = []          # one exchange per in-flight stream (a PeerExchange's step counter lives on one stream)
     if world > 1 and not a.no_graph and os.environ.get("KPF_EXCHANGE", "peer") == "peer":
         try:
-            px = PeerExchange(B, J, dev)
+            pxs = [PeerExchange(B, J, dev) for _ in range(S_OV)]
+            px = pxs[0]
             comm = "fused peer stores into symmetric memory (no NCCL call on the data path; NCCL_DEBUG logs stay empty)"
         except Exception as ex:   # no peer access / symmetric memory on this box
             print(f"[bench] PeerExchange unavailable ({type(ex).__name__}: {ex}); using ncclAllGather", file=sys.stderr)
@@ -231,7 +236,9 @@ def main():
     graphed = None if a.no_graph else GraphedFusionPath(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains, exchange=px)
     # device-resident leg: one graph captured directly over each resident input set (no staging copies in the timed region)
     bound = {} if a.no_graph else {id(d): GraphedFusionPath(net, ldr, d, sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains, bind=True,
-                                                            exchange=px) for d in sets}
+                                                            exchange=pxs[j % S_OV] if pxs else None) for j, d in enumerate(sets)}
+    overlapped = None if a.no_graph else OverlappedSteps([bound[id(d)] for d in sets], S_OV)
+    config["overlap"] = f"{S_OV} consecutive steps in flight (step i on stream i % {S_OV}); every step is a full, independent batch"
 
     def step(i, d):
         """d: a dict of device tensors (resident inputs) or of pinned host tensors (e2e)."""
@@ -252,19 +259,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def flush_exchanges(streams=None):
+        for k, x in enumerate(pxs):
+            if streams is not None:
+                with torch.cuda.stream(streams[k]):
+                    x.flush()
+            else:
+                x.flush()
+
+    def timed(fn, steps, warmup, ov=None):
+        """ov: an OverlappedSteps whose streams carry the steps (fork at the start event, join before the end event)"""
         with torch.no_grad():
             for i in range(warmup):
                 fn(i)
-            if px is not None:
-                px.flush()
+            flush_exchanges(ov.streams if ov else None)
+            if ov:
+                ov.join()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            if ov:
+                ov.fork()
             for i in range(steps):
                 fn(warmup + i)
-            if px is not None:
-                px.flush()          # the last step's gather completes inside the timed region
+            flush_exchanges(ov.streams if ov else None)   # the last steps' gathers complete inside the timed region
+            if ov:
+                ov.join()
             e1.record()
             barrier()
         ms = e0.elapsed_time(e1)
@@ -308,7 +328,10 @@ def main():
                 prev_end = t
         return
     n0 = ops.launch_count()
-    ms = timed(lambda i: step(i, sets[i % NSETS]), a.steps, W)
+    if overlapped is not None and S_OV > 1:
+        ms = timed(lambda i: overlapped.submit(), a.steps, W, ov=overlapped)
+    else:
+        ms = timed(lambda i: step(i, sets[i % NSETS]), a.steps, W)
     if graphed is not None:
         launches = graphed.launches_per_replay * a.steps   # kernels of ours replayed by the graph inside the K timed steps
     else:

@@ -92,6 +92,41 @@ class GraphedFusionPath:
         return self.out
 
 
+class OverlappedSteps:
+    """Keep `n_streams` consecutive steps (independent batches) in flight: step i is replayed on stream i % n_streams.  The path is a
+    long dependent chain of latency-bound kernels, several of which use only part of the machine (a token stack is one CTA per
+    sample: 64 of 148 SMs at batch 64), so a second step's kernels fill the idle SMs: +13-15 % samples/s at batch 64 (measured,
+    profiles/probe_overlap_steps.py).  `paths`: GraphedFusionPath objects captured with bind=True; path j must always run on the
+    same stream (len(paths) % n_streams == 0), which also keeps a PeerExchange bound to one stream."""
+
+    def __init__(self, paths, n_streams=2):
+        assert len(paths) % n_streams == 0
+        self.paths, self.n = list(paths), n_streams
+        dev = paths[0].static["img"].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        self.i = 0
+
+    def fork(self):
+        """the streams start after everything already enqueued on the current stream"""
+        ev = torch.cuda.Event()
+        ev.record()
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def submit(self):
+        p = self.paths[self.i % len(self.paths)]
+        with torch.cuda.stream(self.streams[self.i % self.n]):
+            p.graph.replay()
+        self.i += 1
+        return p.out
+
+    def join(self):
+        """the current stream continues after every step submitted so far"""
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            cur.wait_stream(s)
+
+
 def all_gather_joints(joints, out=None):
     """The path's one exchange step: [B_local,J,3] per rank -> [world*B_local,J,3] on every rank (NCCL over NVLink)."""
     import torch.distributed as dist

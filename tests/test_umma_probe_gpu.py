@@ -33,8 +33,14 @@ def test_token_stack_phase_clocks(path_params, capsys):
     jf = torch.rand(B, 21, 128, device="cuda")
     dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
     for _ in range(3):
+        torch.cuda.synchronize()          # an isolated launch: the first stamp then is the kernel's own start, not a predecessor's tail
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         ops.token_stack(pk, desa=part, jf=jf, dbg=dbg)
+        e1.record()
     torch.cuda.synchronize()
+    with capsys.disabled():
+        print(f"\n[token_stack] isolated launch (no successor overlapping on the idle SMs): {e0.elapsed_time(e1) * 1e3:.1f} us")
     t = dbg.cpu().numpy()[:32]
     n = int((t > 0).sum())
     d = np.diff(t[:n])
