@@ -54,6 +54,7 @@ constexpr int DS_XBUF = 2 * (2048 + 256);   // uint4 per activation buffer: main
 // ================================================================================================ prep
 // Two roles in one launch: CTAs [0, B) embed the joints of one sample (softmax-partial combine + tcgen05 GEMM); CTAs
 // [B, B + B*S) run the ball query of one (sample, scale).  The roles are independent and run side by side on different SMs.
+template <int FMT>
 __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p) {
     extern __shared__ __align__(128) unsigned char ds_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         mbar_expect_tx(&wbar, 4096 * 16);
         tma_bulk_g2s(sWj, p.wmat, 4096 * 16, &wbar);
     }
-    const int fmt = p.fmt;
+    constexpr int fmt = FMT;
     SmemOp opW, opA;   // A = the weight planes in sWj, B = joint_agg / jf planes in sAgg
     opW.hi = smem_u32(sWj); opW.lo = opW.hi + 2048 * 16; opW.lbo = 2048; opW.sbo = 128;
     opA.hi = smem_u32(sAgg); opA.lo = opA.hi + 512 * 16; opA.lbo = 512; opA.sbo = 128;
@@ -308,6 +309,7 @@ struct DesaItem {   // (scale, sample, first joint) of a work item, advanced inc
     int sc, b, j0;
 };
 
+template <int FMT>
 __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaParams p) {
     extern __shared__ __align__(128) unsigned char ds_smem[];
     uint4* sW1t = reinterpret_cast<uint4*>(ds_smem);  // W1's K tail (the xyz columns), 2 planes x [2][128]; W1 main / W2 live in tensor memory
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     const int total = S * B * TPS;
     const int it0 = (int)((long long)total * blockIdx.x / gridDim.x), it1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
     const uint32_t ACC1 = 0, ACC2 = 128, TW1_HI = 256, TW1_LO = 320, TW2_HI = 384, TW2_LO = 448;   // TMEM columns
-    const int fmt = p.fmt;
+    constexpr int fmt = FMT;
     int n_stamp = 0;
     auto stamp = [&]() {
         if (p.dbg && blockIdx.x == 0 && tid == 0 && n_stamp < 48) p.dbg[16 + n_stamp] = clock64();
@@ -607,15 +609,17 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     const size_t smem_a = smem_jf > smem_bq ? smem_jf : smem_bq;
     const size_t smem_b = (size_t)(512 + 2 * DS_XBUF + 4096) * 16 + 2 * 512 * 4 + 64;
     KPF_REQUIRE(smem_a <= 227 * 1024 && smem_b <= 227 * 1024);
-    cudaError_t err = kpf::set_smem(desa_prep_kernel, smem_a);
+    auto prep = fmt == FMT_F16 ? desa_prep_kernel<FMT_F16> : desa_prep_kernel<FMT_BF16>;
+    auto tile = fmt == FMT_F16 ? desa_tile_kernel<FMT_F16> : desa_tile_kernel<FMT_BF16>;
+    cudaError_t err = kpf::set_smem(prep, smem_a);
     if (err != cudaSuccess) return (int)err;
-    err = kpf::set_smem(desa_tile_kernel, smem_b);
+    err = kpf::set_smem(tile, smem_b);
     if (err != cudaSuccess) return (int)err;
-    err = kpf::launch_pdl(desa_prep_kernel, dim3(B + B * S), dim3(DS_NT), smem_a, stream, p);
+    err = kpf::launch_pdl(prep, dim3(B + B * S), dim3(DS_NT), smem_a, stream, p);
     if (err != cudaSuccess) return (int)err;
     KPF_CHECK_LAUNCH();
     const int JPT = 128 / nsample, total = S * B * ((J + JPT - 1) / JPT);
-    err = kpf::launch_pdl(desa_tile_kernel, dim3(total < num_sms ? total : num_sms), dim3(DS_TILE_NT), smem_b, stream, p);
+    err = kpf::launch_pdl(tile, dim3(total < num_sms ? total : num_sms), dim3(DS_TILE_NT), smem_b, stream, p);
     if (err != cudaSuccess) return (int)err;
     KPF_CHECK_LAUNCH();
     return 0;

@@ -128,6 +128,7 @@ constexpr uint32_t PE_EH = PE_ACC2, PE_EL = PE_ACC2 + 32, PE_ACC3 = PE_ACC1;
 // The whole point stage, computed TRANSPOSED: D^T[channel][point] = W[channel][k] X[point][k].  The folded weights (K = 384, two
 // 16-bit planes) stay in TENSOR MEMORY for the life of the persistent CTA as the A operands; a tile is 64 points whose gathered
 // inputs are written as K-major B operand planes; a thread of the epilogue owns one output channel (its TMEM lane) and 16 points.
+template <int FMT>
 __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams p) {
     extern __shared__ __align__(128) unsigned char pe_smem[];
     uint4* sX1 = reinterpret_cast<uint4*>(pe_smem);   // 2 planes x [8 point groups][32 k-chunks][8 points]   (K = 256)
@@ -148,7 +149,8 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
     // chunks and the joint offsets, warps 8-15 (grp 1) the rgb-branch chunks of the same 64 points.
     const int r = 8 * (warp & 7) + (lane & 7), sub = lane >> 3, grp = warp >> 3;
     const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;   // epilogues: channel ch (TMEM lane), points [16cg, 16cg + 16)
-    const int J = p.J, N = p.N, T = N / PE_TP, fmt = p.fmt;
+    const int J = p.J, N = p.N, T = N / PE_TP;
+    constexpr int fmt = FMT;
 
     pdl_launch_dependents();
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -518,10 +520,11 @@ extern "C" int kpf_point_embed(const void* feat_hi, const void* feat_lo, const i
         p.probe = probe;
     }
     p.dbg = dbg;
-    cudaError_t e = kpf::set_smem(point_embed_kernel, PE_SMEM);
+    auto kern = fmt == FMT_F16 ? point_embed_kernel<FMT_F16> : point_embed_kernel<FMT_BF16>;
+    cudaError_t e = kpf::set_smem(kern, PE_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int tiles = B * (N / PE_TP);
-    e = kpf::launch_pdl(point_embed_kernel, dim3(tiles < num_sms ? tiles : num_sms), dim3(PE_NT), PE_SMEM, stream, p);
+    e = kpf::launch_pdl(kern, dim3(tiles < num_sms ? tiles : num_sms), dim3(PE_NT), PE_SMEM, stream, p);
     if (e != cudaSuccess) return (int)e;
     KPF_CHECK_LAUNCH();
     return 0;

@@ -42,6 +42,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int K5_NT = 512;   // thread = (cell or channel row = 32 * (warp % 4) + lane, joint group warp / 4 of 8 joints)
 
+template <int FMT>
 __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const SpatialParams p) {
     extern __shared__ __align__(128) unsigned char k5_smem[];
     const bool has_lo = p.feat_lo != nullptr;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
     uint4* sF = reinterpret_cast<uint4*>(sJ + 256 + 32);   // [NBUF buffers][NP planes][2048] raw feature tile, index (c/8)*128 + (hw/8)*8 + (c%8)
     uint4* sFr = sF + NBUF * NP * 2048;              // [NP planes][2048] relu copy
     float* sBa = sJ + 256;                           // [32] atten_spatial bias
-    const int fmt = p.fmt;
+    constexpr int fmt = FMT;
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ CamF cam;
@@ -329,10 +330,11 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const void* feat_r
     p.B = B; p.J = J; p.fs = fs; p.img_size = img_size; p.flip = flip; p.hm_std = hm_std; p.hm_sigma = hm_sigma; p.gamma = gamma;
     const int NP = feat_rgb_lo ? 2 : 1, NBUF = feat_rgb_lo ? 1 : 2;
     const size_t smem = (size_t)(1024 + 1536 + 1792 + (NBUF + 1) * NP * 2048) * 16 + 32 * 8 * 4 + 32 * 4;
-    cudaError_t e = kpf::set_smem(spatial_aggregate_tc_kernel, smem);
+    auto kern = fmt == FMT_F16 ? spatial_aggregate_tc_kernel<FMT_F16> : spatial_aggregate_tc_kernel<FMT_BF16>;
+    cudaError_t e = kpf::set_smem(kern, smem);
     if (e != cudaSuccess) return (int)e;
     {
-        cudaError_t le = kpf::launch_pdl(spatial_aggregate_tc_kernel, dim3(B * split), dim3(K5_NT), smem, stream, p);
+        cudaError_t le = kpf::launch_pdl(kern, dim3(B * split), dim3(K5_NT), smem, stream, p);
         if (le != cudaSuccess) return (int)le;
     }
     KPF_CHECK_LAUNCH();

@@ -93,6 +93,10 @@ __device__ __forceinline__ void warp_reduce_scatter(float* v, int lane) {
     for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
 }
 
+// FMT: the split format of the operand planes, a template parameter so that every split8 / instruction descriptor folds to one path
+// (a run-time format doubled the conversion code of every epilogue; the kernel is instruction-fetch sensitive: `no_instruction`
+// was 3 of 11 stall cycles per instruction, profiles/stalls_r2_a.txt)
+template <int FMT>
 __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p) {
     extern __shared__ __align__(128) unsigned char ts_smem[];
     uint4* wslot = reinterpret_cast<uint4*>(ts_smem);   // [4][2048]    weight ring
@@ -111,7 +115,8 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, q = w & 3, c = (w >> 2) & 3;
     const int f = 32 * q + lane;              // this thread's feature = TMEM lane
-    const int J = p.J, C = TS_C, G = p.G, fmt = p.fmt;
+    const int J = p.J, C = TS_C, G = p.G;
+    constexpr int fmt = FMT;
     const int b = blockIdx.x;
     const int warp_u = warp_index_uniform();
     const bool producer = warp_u == TS_WORKERS / 32;
@@ -317,13 +322,13 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = tokv[i] ? fmaxf(a[i] + bb, 0.f) : 0.f;
     };
-    if (p.pre && p.L == 0) {   // prologue-only program (stand-alone DESA.forward): the fusion conv's output is the result
-        float a[8];
-        fusion_prologue(a);
-        if (p.tokens_out) {
+    float pre_a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // the fusion conv's output (one instantiation of the prologue: code size)
+    if (p.pre) {
+        fusion_prologue(pre_a);
+        if (p.L == 0 && p.tokens_out) {   // prologue-only program (stand-alone DESA.forward): the fusion conv's output is the result
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                if (tokv[i]) p.tokens_out[((size_t)b * J + 8 * c + i) * C + f] = a[i];
+                if (tokv[i]) p.tokens_out[((size_t)b * J + 8 * c + i) * C + f] = pre_a[i];
         }
     }
 
@@ -332,10 +337,8 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
         if (it == (p.cross ? 1 : 0) && p.L > 0) {
             // =========================== encoder input stage (KP_Interaction_TR) ===========================
             if (p.pre) {
-                float a[8];
-                fusion_prologue(a);
-                head_partial(0, a, Wres_feat);
-                write_act(bufX, a);
+                head_partial(0, pre_a, Wres_feat);
+                write_act(bufX, pre_a);
             }
             if (!p.pre && !p.cross) {
                 float v[8];
@@ -644,17 +647,17 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stack_kernel(const TokParams p
                 reinterpret_cast<uint2*>(bufY + (c >> 1) * 32 + lane)[c & 1] = hi;
                 reinterpret_cast<uint2*>(bufY + TS_PLANE + (c >> 1) * 32 + lane)[c & 1] = lo;
             } else {
-                float a[32];
-                tmem_ld<32>(tmem0 + ACC_F + 32 * c, a);
+#pragma unroll 1
+                for (int j4 = 0; j4 < 4; ++j4) {   // rolled: eight hidden units per trip (code size; this path runs once per program)
+                    float a[8];
+                    tmem_ld<8>(tmem0 + ACC_F + 32 * c + 8 * j4, a);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float u = a[i] + b1[32 * c + i];
-                    a[i] = tv ? (act == 1 ? gelu_erf(u) : fmaxf(u, 0.f)) : 0.f;
-                }
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
+                    for (int i = 0; i < 8; ++i) {
+                        const float u = a[i] + b1[32 * c + 8 * j4 + i];
+                        a[i] = tv ? (act == 1 ? gelu_erf(u) : fmaxf(u, 0.f)) : 0.f;
+                    }
                     uint4 hi, lo;
-                    split8(fmt, a + 8 * j4, hi, lo);
+                    split8(fmt, a, hi, lo);
                     bufY[(4 * c + j4) * 32 + lane] = hi;
                     bufY[TS_PLANE + (4 * c + j4) * 32 + lane] = lo;
                 }
@@ -802,9 +805,10 @@ extern "C" int kpf_token_stack(const float* x, const float* y, const float* r3d,
     p.dbg = dbg;
     KPF_REQUIRE(peer_bases == nullptr || (xstep != nullptr && world >= 1 && row0 >= 0 && row0 + B <= rows_total && L > 0));
     p.peer_bases = (const unsigned long long*)peer_bases; p.xstep = xstep; p.world = world; p.row0 = row0; p.rows_total = rows_total;
-    cudaError_t e = kpf::set_smem(token_stack_kernel, TS_SMEM);
+    auto kern = fmt == FMT_F16 ? token_stack_kernel<FMT_F16> : token_stack_kernel<FMT_BF16>;
+    cudaError_t e = kpf::set_smem(kern, TS_SMEM);
     if (e != cudaSuccess) return (int)e;
-    e = kpf::launch_pdl(token_stack_kernel, dim3(B), dim3(TS_NT), TS_SMEM, stream, p);
+    e = kpf::launch_pdl(kern, dim3(B), dim3(TS_NT), TS_SMEM, stream, p);
     if (e != cudaSuccess) return (int)e;
     KPF_CHECK_LAUNCH();
     return 0;
