@@ -256,6 +256,18 @@ int kpf_umma_selftest(const void* A, const void* B, float* D, int N, int K, int 
 int kpf_umma_split_selftest(const float* A, const float* B, float* D, int N, int K, int fmt, int a_tmem, int a_exact, long long* cycles,
                             cudaStream_t stream);
 
+/* TMA row gather self-test (csrc/tma_gather.cuh): table = [rows][256] 16-bit ([hi 128 | lo 128] fp16 planes of a [rows][128] fp32
+ * matrix X), idx [N] i32 -> D[128,N] f32 = A[128,128] X[idx]^T.  The rows are fetched with cp.async.bulk.tensor ... tile::gather4
+ * (four rows per instruction, 128-byte swizzle) and consumed as a SWIZZLE_128B K-major operand.  N % 16 == 0, N <= 256.
+ * cycles (3 x int64 device, may be NULL): the gather (cold), the 24 MMAs, the gather repeated (L2-hot). */
+int kpf_tma_gather_selftest(const void* table, long long rows, const float* A, const int* idx, float* D, int N, long long* cycles,
+                            cudaStream_t stream);
+
+/* cycle probe of 512-byte row gathers into shared memory (profiles/probe_gather.py): every one of `ctas` CTAs gathers n_rows rows
+ * (idx [ctas][n_rows] i32) four times; out[cta] = cycles of the last repetition.  mode 0 TMA gather4, 1 bulk 512 B copies,
+ * 2 cp.async (128-byte requests), 3 LDG.128 + STS, 4 cp.async (a row per warp instruction). */
+int kpf_gather_probe(const void* table, long long rows, const int* idx, int n_rows, int ctas, int mode, long long* out, cudaStream_t stream);
+
 /* cycle micro-benchmarks of the tcgen05 building blocks (out: 8 x int64 device; see csrc/umma_probe.cu) */
 int kpf_umma_probe(long long* out, int N, int K, int reps, cudaStream_t stream);
 

@@ -49,7 +49,8 @@ struct DesaParams {
 
 constexpr int DS_NT = 512;
 constexpr int DS_MAT_PER_SCALE = 2 * (2048 + 256 + 2048);
-constexpr int DS_XBUF = 2 * (2048 + 256);   // uint4 per activation buffer: main hi | main lo | K tail hi | K tail lo
+constexpr int DS_XBUF = 2 * (2048 + 128);   // uint4 per activation buffer: main hi | main lo | K tail hi | K tail lo (one 16-byte chunk per row:
+                                            // the tail's second k-chunk is all zero and never stored, the descriptor re-reads the first)
 
 // ================================================================================================ prep
 // Two roles in one launch: CTAs [0, B) embed the joints of one sample (softmax-partial combine + tcgen05 GEMM); CTAs
@@ -316,6 +317,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     uint4* sX = sW1t + 512;                            // [2] x (2 planes x K-major activations [16 row groups][16 k-chunks][8 rows] + 2 planes x tail [16][2][8])
     uint4* sH = sX + 2 * DS_XBUF;                      // 2 planes x MN-major [16][16][8]
     float* sPart = reinterpret_cast<float*>(sH + 4096);   // [2][4][128] per-column-group maxima
+    float4* sXyz = reinterpret_cast<float4*>(sPart + 1024);   // [2][128][2] xyz of a tile's grouped points and of their centres (cp.async staging)
     __shared__ __align__(8) uint64_t wbar, g1_bar, g2_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -378,8 +380,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     //      so no register staging, no conversion); every stage walks the items with its own cursor
     DesaItem c_idx, c_rows, c_epi, c_max;
     int ii[2] = {0, 0};      // ball-query indices of this thread's two rows for the item whose rows are copied next (< N + J)
-    float3 pq[2], pc[2];     // xyz of those rows' points and of their centres (g8 == 0 lanes)
-    bool tail_ok[2] = {false, false};
+    bool tail_ok[2] = {false, false};   // this thread's rows of the tile copied last belong to real joints
     float inv_r = 1.f;       // 1 / radius of the run's scale
 
     auto fetch_idx = [&]() {
@@ -407,11 +408,11 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // 16-byte chunk 8k + g8 of the 512-byte row: k-chunk (8k + g8) & 15 of plane k >> 1
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(X + (k >> 1) * 2048 + (k & 1) * 64)), "l"(src + 64 * k), "r"(nbytes) : "memory");
-            if (g8 == 0) {   // the xyz tail of the row is computed at the end of the iteration from these loads
+            if (g8 == 0) {   // xyz of the row's point and of its centre -> staging; the tail is built from it one iteration later
+                float4* st = sXyz + ((item & 1) * 128 + row) * 2;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st)), "l"(tab + ii[h]) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st + 1)), "l"(tab + N + (ok ? jj : 0)) : "memory");
                 tail_ok[h] = ok;
-                const float4 a4 = __ldg(tab + ii[h]), c4 = __ldg(tab + N + (ok ? jj : 0));
-                pq[h] = make_float3(a4.x, a4.y, a4.z);
-                pc[h] = make_float3(c4.x, c4.y, c4.z);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -421,19 +422,19 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int row = r + 64 * h;
+            const float4* st = sXyz + ((item & 1) * 128 + row) * 2;
+            const float4 a4 = st[0], c4 = st[1];
             float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (tail_ok[h]) {
-                t8[0] = (pq[h].x - pc[h].x) * inv_r;
-                t8[1] = (pq[h].y - pc[h].y) * inv_r;
-                t8[2] = (pq[h].z - pc[h].z) * inv_r;
+                t8[0] = (a4.x - c4.x) * inv_r;
+                t8[1] = (a4.y - c4.y) * inv_r;
+                t8[2] = (a4.z - c4.z) * inv_r;
             }
-            uint4* X = sX + (item & 1) * DS_XBUF + 4096 + (row >> 3) * 16 + (row & 7);
+            uint4* X = sX + (item & 1) * DS_XBUF + 4096 + (row >> 3) * 8 + (row & 7);
             uint4 th, tl;
             split8(fmt, t8, th, tl);
             X[0] = th;
-            X[8] = make_uint4(0, 0, 0, 0);
-            X[256] = tl;
-            X[256 + 8] = make_uint4(0, 0, 0, 0);
+            X[128] = tl;
         }
     };
     // maxima of a finished tile: combine the column groups of each joint, store
@@ -485,6 +486,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         for (int s = i0 - 2; s < i1; ++s) {
             if (s >= i0 - 1) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's rows of tile s + 1 have landed
+                if (!issuer && s + 1 < i1) store_tail(s + 1);          // ... and their xyz: the operand's K tail
                 fence_proxy_async();
                 tc_fence_before();
                 __syncthreads();
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                             xb.hi = X; xb.lo = X + 2048 * 16; xb.lbo = 128; xb.sbo = 2048;
                             if (!(p.probe & 2)) umma_gemm3_ts(tmem0 + ACC1, a, xb, id128, 128, false);
                             ta.hi = smem_u32(sW1t); ta.lo = ta.hi + 256 * 16; ta.lbo = 2048; ta.sbo = 128;
-                            tb.hi = X + 4096 * 16; tb.lo = tb.hi + 256 * 16; tb.lbo = 128; tb.sbo = 256;
+                            tb.hi = X + 4096 * 16; tb.lo = tb.hi + 128 * 16; tb.lbo = 0; tb.sbo = 128;   // lbo 0: k-chunk 1 (zero weights) re-reads chunk 0
                             if (!(p.probe & 2)) umma_gemm3_ss(tmem0 + ACC1, ta, tb, id128, 16, true);
                             umma_commit(&g1_bar);
                         }
@@ -526,21 +528,24 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                 if (have_rows) copy_rows(s + 2);
                 if (s + 3 < i1) fetch_idx();
                 // layer-1 bias of tile s + 1 minus the W1 jf term of the joint this thread's 32 rows belong to
-                float cjb = b1;
+                float cjv = 0.f;   // loaded here, consumed after the layer-2 epilogue (the subtraction sits behind the wait below on purpose)
                 if (s >= i0 - 1 && s + 1 < i1) {
                     const int jj = c_epi.j0 + ((32 * cg) >> ns_shift);
-                    if (jj < J) cjb = b1 - __ldg(p.cj + (((size_t)c_epi.b * S + c_epi.sc) * J + jj) * 128 + ch);
+                    if (jj < J) cjv = __ldg(p.cj + (((size_t)c_epi.b * S + c_epi.sc) * J + jj) * 128 + ch);
                     advance(c_epi);
                 }
                 if (s >= i0) {   // layer-2 epilogue of tile s: max over this thread's 32 grouped points  (model.py:197-198)
                     mbar_wait(&g2_bar, g2_phase);
                     g2_phase ^= 1;
                     tc_fence_after();
-                        float a[32];
-                    tmem_ld<32>(tmem + ACC2 + 32 * cg, a);
-                    float mx = a[0];
+                    float mx = -INFINITY;
 #pragma unroll
-                    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, a[i]);
+                    for (int hf = 0; hf < 2; ++hf) {   // two 16-column reads: half the live registers of one 32-column read
+                        float a[16];
+                        tmem_ld<16>(tmem + ACC2 + 32 * cg + 16 * hf, a);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, a[i]);
+                    }
                     sPart[(s & 1) * 512 + cg * 128 + ch] = fmaxf(mx + b2, 0.f);   // max_i relu(a_i + b2)
                     tc_fence_before();
                     }
@@ -548,19 +553,22 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                     mbar_wait(&g1_bar, g1_phase);
                     g1_phase ^= 1;
                     tc_fence_after();
-                        float a[32];
-                    tmem_ld<32>(tmem + ACC1 + 32 * cg, a);
+                    const float cjb = b1 - cjv;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i] + cjb, 0.f);   // relu(W1 feat + tail - W1 jf + b1)
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float a[16];
+                        tmem_ld<16>(tmem + ACC1 + 32 * cg + 16 * hf, a);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint4 hh, hl;
-                        split8(fmt, a + 8 * c, hh, hl);
-                        sH[(ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = hh;
-                        sH[2048 + (ch >> 3) * 128 + (4 * cg + c) * 8 + (ch & 7)] = hl;
+                        for (int i = 0; i < 16; ++i) a[i] = fmaxf(a[i] + cjb, 0.f);   // relu(W1 feat + tail - W1 jf + b1)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint4 hh, hl;
+                            split8(fmt, a + 8 * c, hh, hl);
+                            sH[(ch >> 3) * 128 + (4 * cg + 2 * hf + c) * 8 + (ch & 7)] = hh;
+                            sH[2048 + (ch >> 3) * 128 + (4 * cg + 2 * hf + c) * 8 + (ch & 7)] = hl;
+                        }
                     }
                 }
-                if (have_rows) store_tail(s + 2);
             }
             if (s <= i0 + 3) stamp();
         }
@@ -607,7 +615,7 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     const size_t smem_jf = (size_t)(4096 + 1024) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
     const size_t smem_bq = (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * NW * 4 + 64;
     const size_t smem_a = smem_jf > smem_bq ? smem_jf : smem_bq;
-    const size_t smem_b = (size_t)(512 + 2 * DS_XBUF + 4096) * 16 + 2 * 512 * 4 + 64;
+    const size_t smem_b = (size_t)(512 + 2 * DS_XBUF + 4096) * 16 + 2 * 512 * 4 + 2 * 128 * 2 * 16 + 64;
     KPF_REQUIRE(smem_a <= 227 * 1024 && smem_b <= 227 * 1024);
     auto prep = fmt == FMT_F16 ? desa_prep_kernel<FMT_F16> : desa_prep_kernel<FMT_BF16>;
     auto tile = fmt == FMT_F16 ? desa_tile_kernel<FMT_F16> : desa_tile_kernel<FMT_BF16>;
