@@ -259,8 +259,9 @@ int kpf_umma_split_selftest(const float* A, const float* B, float* D, int N, int
 /* TMA row gather self-test (csrc/tma_gather.cuh): table = [rows][256] 16-bit ([hi 128 | lo 128] fp16 planes of a [rows][128] fp32
  * matrix X), idx [N] i32 -> D[128,N] f32 = A[128,128] X[idx]^T.  The rows are fetched with cp.async.bulk.tensor ... tile::gather4
  * (four rows per instruction, 128-byte swizzle) and consumed as a SWIZZLE_128B K-major operand.  N % 16 == 0, N <= 256.
- * cycles (3 x int64 device, may be NULL): the gather (cold), the 24 MMAs, the gather repeated (L2-hot). */
-int kpf_tma_gather_selftest(const void* table, long long rows, const float* A, const int* idx, float* D, int N, long long* cycles,
+ * a_tmem: A operand planes read from tensor memory instead of shared memory.
+ * cycles (4 x int64 device, may be NULL): the gather (cold), one GEMM (24 MMAs), the gather repeated (L2-hot), eight GEMMs. */
+int kpf_tma_gather_selftest(const void* table, long long rows, const float* A, const int* idx, float* D, int N, int a_tmem, long long* cycles,
                             cudaStream_t stream);
 
 /* cycle probe of 512-byte row gathers into shared memory (profiles/probe_gather.py): every one of `ctas` CTAs gathers n_rows rows

@@ -70,42 +70,54 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
 
     if ((int)blockIdx.x >= p.B) {
         // ================= ball query (pointnet2_ops: first NS hits in index order, padded with the first hit) =================
-        const int pi = blockIdx.x - p.B, b = pi / S, sc = pi - b * S;
+        // one CTA per sample, all S scales: the distances are computed once and compared against every radius
+        const int b = blockIdx.x - p.B;
         pdl_wait();
         float4* sPcl = reinterpret_cast<float4*>(ds_smem);                          // [N + J] xyz
-        uint32_t* sMask = reinterpret_cast<uint32_t*>(sPcl + (N + J + 3) / 4 * 4);   // [J][NW] hit words (bit = point)
+        uint32_t* sMask = reinterpret_cast<uint32_t*>(sPcl + (N + J + 3) / 4 * 4);   // [S][J][NW] hit words (bit = point)
         for (int i = tid; i < N + J; i += DS_NT) {
             const float* s = i < N ? p.pcl + ((size_t)b * N + i) * 3 : p.joint + ((size_t)b * J + (i - N)) * 3;
             sPcl[i] = make_float4(s[0], s[1], s[2], 0.f);
         }
         __syncthreads();
-        if (sc == 0)
-            for (int i = tid; i < N + J; i += DS_NT) p.xyz4[(size_t)b * (N + 32) + i] = sPcl[i];
+        for (int i = tid; i < N + J; i += DS_NT) p.xyz4[(size_t)b * (N + 32) + i] = sPcl[i];
         stamp();
-        // Phase 1: one thread per point tests all J centres (exact fp32 op order).  A warp's 32 lanes hold 32 CONSECUTIVE
-        // points, so one ballot per (centre, point group) IS the hit word.
+        // Phase 1: thread = (32-point word, centre): lane = centre j, warp = word.  Every lane walks the word's 32 points (one
+        // broadcast shared-memory read per point), computes d2 ONCE in the exact fp32 op order and sets the point's bit in the hit
+        // word of every scale whose r^2 it is under.  No ballots, no cross-lane traffic; hit word layout sMask[(sc J + j) NW + word].
         const int NW = (N + J + 31) / 32;
-        const float r2 = xmul(p.radius[sc], p.radius[sc]);
-        for (int base = 0; base + 32 * warp < N + J; base += DS_NT) {   // warp-uniform: warps without points skip the round
-            const int n = base + tid;
-            const float4 q = n < N + J ? sPcl[n] : make_float4(1e30f, 1e30f, 1e30f, 0.f);
-            const int wi = (base >> 5) + warp;
-#pragma unroll 3
-            for (int j = 0; j < J; ++j) {
-                const float4 c = sPcl[N + j];
-                const float dx = xsub(c.x, q.x), dy = xsub(c.y, q.y), dz = xsub(c.z, q.z);
-                const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-                const uint32_t bal = __ballot_sync(0xffffffffu, d2 < r2);
-                if (lane == 0) sMask[j * NW + wi] = bal;
+        float r2[4];
+#pragma unroll
+        for (int sc = 0; sc < 4; ++sc) r2[sc] = xmul(p.radius[sc < S ? sc : 0], p.radius[sc < S ? sc : 0]);
+        if (lane < J) {
+            const float4 c = sPcl[N + lane];
+            for (int wi = warp; wi < NW; wi += DS_NT / 32) {
+                uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+                const int n0 = wi * 32, cnt = min(32, N + J - n0);
+#pragma unroll 4
+                for (int i = 0; i < cnt; ++i) {
+                    const float4 q = sPcl[n0 + i];
+                    const float dx = xsub(c.x, q.x), dy = xsub(c.y, q.y), dz = xsub(c.z, q.z);
+                    const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+                    const uint32_t bit = 1u << i;
+                    m0 |= d2 < r2[0] ? bit : 0u;
+                    m1 |= d2 < r2[1] ? bit : 0u;
+                    m2 |= d2 < r2[2] ? bit : 0u;
+                    m3 |= d2 < r2[3] ? bit : 0u;
+                }
+                sMask[(0 * J + lane) * NW + wi] = m0;
+                if (S > 1) sMask[(1 * J + lane) * NW + wi] = m1;
+                if (S > 2) sMask[(2 * J + lane) * NW + wi] = m2;
+                if (S > 3) sMask[(3 * J + lane) * NW + wi] = m3;
             }
         }
         __syncthreads();
         stamp();
         // Phase 2: one warp per centre: popcount prefix over its hit words, then every lane expands the set bits of its word(s)
         // into their slots
-        for (int j = warp; j < J; j += DS_NT / 32) {
-            const uint32_t* wj = sMask + j * NW;
-            uint16_t* out = p.idx + (((size_t)b * S + sc) * J + j) * NS;
+        for (int pj = warp; pj < S * J; pj += DS_NT / 32) {   // pj = sc * J + j: the layout of sMask and of idx[b]
+            const uint32_t* wj = sMask + pj * NW;
+            uint16_t* out = p.idx + ((size_t)b * S * J + pj) * NS;
             int carry = 0, first = -1;
             for (int w0 = 0; w0 < NW && carry < NS; w0 += 32) {
                 const int wi = w0 + lane;
@@ -141,21 +153,28 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
     }
 
     // ================= joint embedding: jf = relu(Wj [joint_agg | joint_xyz] + b)  (model.py:319-325) =================
-    uint4* sWj = reinterpret_cast<uint4*>(ds_smem);             // 2 planes x [16][128] K-major A operand
-    uint4* sAgg = sWj + 4096;                                    // 2 planes x MN-major B operand [16][4][8]: joint_agg[channel][joint]
+    uint4* sWj = reinterpret_cast<uint4*>(ds_smem);             // 2 planes x [16][128] K-major A operand: Wj, later W1 of scale 2 (3)
+    uint4* sW1 = sWj + 4096;                                     // [2] such buffers: W1 of scales 0 and 1, prefetched at kernel start
+    uint4* sAgg = sW1 + 2 * 4096;                                // 2 planes x MN-major B operand [16][4][8]: joint_agg[channel][joint]
     float* sMS = reinterpret_cast<float*>(sAgg + 1024);          // [T][2][32] partial max/sum -> [T][32] factors + den[32]
     float4* sJ = reinterpret_cast<float4*>(sMS + T * 64 + 64);   // [32] joint xyz
-    __shared__ __align__(8) uint64_t wbar, mma_bar;
+    __shared__ __align__(8) uint64_t wbar, w1bar[2], mma_bar;
     __shared__ uint32_t tmem_slot;
     const int warp_u = warp_index_uniform();
     const int b = blockIdx.x;
-    if (warp == 0) tmem_alloc(&tmem_slot, 32);
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);   // accumulators: jf [0, 32), cj of the scales in flight [32, 128)
     if (tid == 0) {
         mbar_init(&wbar, 1);
+        mbar_init(&w1bar[0], 1);
+        mbar_init(&w1bar[1], 1);
         mbar_init(&mma_bar, 1);
         fence_mbar_init();
         mbar_expect_tx(&wbar, 4096 * 16);
         tma_bulk_g2s(sWj, p.wmat, 4096 * 16, &wbar);
+        for (int sc = 0; sc < 2 && sc < S; ++sc) {   // the first two scales' W1 (weights: no dependence on the previous kernel)
+            mbar_expect_tx(&w1bar[sc], 4096 * 16);
+            tma_bulk_g2s(sW1 + sc * 4096, p.wmat + 4096 + (size_t)sc * DS_MAT_PER_SCALE, 4096 * 16, &w1bar[sc]);
+        }
     }
     constexpr int fmt = FMT;
     SmemOp opW, opA;   // A = the weight planes in sWj, B = joint_agg / jf planes in sAgg
@@ -236,6 +255,10 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         mph ^= 1;
         tc_fence_after();
     }
+    if (tid == 0 && S > 2) {   // Wj has been read (or was never needed): its buffer takes W1 of scale 2 while the epilogue runs
+        mbar_expect_tx(&wbar, 4096 * 16);
+        tma_bulk_g2s(sWj, p.wmat + 4096 + (size_t)2 * DS_MAT_PER_SCALE, 4096 * 16, &wbar);
+    }
     const int q = warp & 3, cg = warp >> 2, ch = 32 * q + lane;   // channel 32q + lane, joints [8cg, 8cg + 8)
     const uint32_t tmem_q = tmem0 + ((uint32_t)(32 * q) << 16);
     {   // jf[j][ch]
@@ -267,21 +290,58 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
     }
     // ---- cj[s][j][:] = W1_s jf[j] for every scale: the tile kernel feeds the RAW gathered point features to its layer-1 GEMM and
     //      subtracts this term in the epilogue ( W1 (feat - jf) = W1 feat - W1 jf ), so its gather is a pure copy
-    for (int sc = 0; sc < S; ++sc) {
-        fence_proxy_async();   // sAgg (generic-proxy writes) -> the MMA's async-proxy reads
-        tc_fence_before();
-        __syncthreads();       // the previous MMA's operand (sWj) and accumulator reads are done
-        if (warp_u == 0) {
+    //      Scales 0..2 are issued back to back into their own accumulators (weights already in shared memory); a fourth scale
+    //      reuses buffer 0 afterwards.
+    const int S3 = S < 3 ? S : 3;
+    fence_proxy_async();   // sAgg (generic-proxy writes) -> the MMAs' async-proxy reads
+    tc_fence_before();
+    __syncthreads();
+    if (warp_u == 0) {
+        tc_fence_after();
+        for (int sc = 0; sc < S3; ++sc) {
+            if (sc < 2) mbar_wait(&w1bar[sc], 0);
+            else mbar_wait(&wbar, 1);
             if (elect_one()) {
-                mbar_expect_tx(&wbar, 4096 * 16);
-                tma_bulk_g2s(sWj, p.wmat + 4096 + (size_t)sc * DS_MAT_PER_SCALE, 4096 * 16, &wbar);   // W1 main: hi | lo
+                SmemOp w = opW;
+                if (sc < 2) {
+                    w.hi = smem_u32(sW1 + sc * 4096);
+                    w.lo = w.hi + 2048 * 16;
+                }
+                umma_gemm3_ss(tmem0 + 32 * (sc + 1), w, opA, id_jf, 128, false);
             }
             __syncwarp();
-            fence_proxy_async();
-            tc_fence_after();
-            mbar_wait(&wbar, (sc + 1) & 1);
+        }
+        if (elect_one()) umma_commit(&mma_bar);
+        __syncwarp();
+    }
+    mbar_wait(&mma_bar, mph);
+    mph ^= 1;
+    tc_fence_after();
+    for (int sc = 0; sc < S3; ++sc) {
+        float d[8];
+        tmem_ld<8>(tmem_q + 32 * (sc + 1) + 8 * cg, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = 8 * cg + i;
+            if (j < J) p.cj[(((size_t)b * S + sc) * J + j) * 128 + ch] = d[i];
+        }
+    }
+    if (S > 3) {   // fourth scale: buffer 0 again (its GEMM has completed), accumulator 1 (read above)
+        tc_fence_before();
+        __syncthreads();
+        if (warp_u == 0) {
             if (elect_one()) {
-                umma_gemm3_ss(tmem0, opW, opA, id_jf, 128, false);
+                mbar_expect_tx(&w1bar[0], 4096 * 16);
+                tma_bulk_g2s(sW1, p.wmat + 4096 + (size_t)3 * DS_MAT_PER_SCALE, 4096 * 16, &w1bar[0]);
+            }
+            __syncwarp();
+            tc_fence_after();
+            mbar_wait(&w1bar[0], 1);
+            if (elect_one()) {
+                SmemOp w = opW;
+                w.hi = smem_u32(sW1);
+                w.lo = w.hi + 2048 * 16;
+                umma_gemm3_ss(tmem0 + 32, w, opA, id_jf, 128, false);
                 umma_commit(&mma_bar);
             }
             __syncwarp();
@@ -290,17 +350,17 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         mph ^= 1;
         tc_fence_after();
         float d[8];
-        tmem_ld<8>(tmem_q + 8 * cg, d);
+        tmem_ld<8>(tmem_q + 32 + 8 * cg, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int j = 8 * cg + i;
-            if (j < J) p.cj[(((size_t)b * S + sc) * J + j) * 128 + ch] = d[i];
+            if (j < J) p.cj[(((size_t)b * S + 3) * J + j) * 128 + ch] = d[i];
         }
     }
     stamp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem0, 32);
+    if (warp == 0) tmem_dealloc(tmem0, 128);
 }
 
 // ================================================================================================ tiles
@@ -612,8 +672,8 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     p.xyz4 = (float4*)((char*)scratch + (size_t)B * S * J * 128 * 4);
     p.idx = (uint16_t*)((char*)scratch + (size_t)B * S * J * 128 * 4 + (size_t)B * (N + 32) * 16);
     const int NW = (N + J + 31) / 32;
-    const size_t smem_jf = (size_t)(4096 + 1024) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
-    const size_t smem_bq = (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)J * NW * 4 + 64;
+    const size_t smem_jf = (size_t)(3 * 4096 + 1024) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
+    const size_t smem_bq = (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)S * J * NW * 4 + 64;
     const size_t smem_a = smem_jf > smem_bq ? smem_jf : smem_bq;
     const size_t smem_b = (size_t)(512 + 2 * DS_XBUF + 4096) * 16 + 2 * 512 * 4 + 2 * 128 * 2 * 16 + 64;
     KPF_REQUIRE(smem_a <= 227 * 1024 && smem_b <= 227 * 1024);
@@ -623,7 +683,7 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     if (err != cudaSuccess) return (int)err;
     err = kpf::set_smem(tile, smem_b);
     if (err != cudaSuccess) return (int)err;
-    err = kpf::launch_pdl(prep, dim3(B + B * S), dim3(DS_NT), smem_a, stream, p);
+    err = kpf::launch_pdl(prep, dim3(2 * B), dim3(DS_NT), smem_a, stream, p);
     if (err != cudaSuccess) return (int)err;
     KPF_CHECK_LAUNCH();
     const int JPT = 128 / nsample, total = S * B * ((J + JPT - 1) / JPT);

@@ -1,7 +1,7 @@
 // Self-test + cycle probe of the TMA row gather (csrc/tma_gather.cuh) feeding a SWIZZLE_128B K-major B operand (tests/test_umma_gpu.py):
 //   D[128 x N] = A[128 x 128] X[idx[n]][0..128)^T    A fp32 carried as fp16 planes (shared memory, no swizzle), X = rows of a
 //   [R][256] 16-bit table ([hi 128 | lo 128] fp16 planes: the layout of kpf_point_embed's e), gathered four rows per instruction.
-//   cycles[0] = gather of the N rows (both planes), cold; cycles[1] = the 24 MMAs; cycles[2] = the same gather again (L2-hot).
+//   cycles[0] = gather of the N rows (both planes), cold; [1] = one GEMM (24 MMAs); [2] = the gather again (L2-hot); [3] = eight GEMMs.
 #include "tma_gather.cuh"
 #include "umma_split.cuh"
 
@@ -9,7 +9,7 @@ namespace kpf {
 
 __global__ void __launch_bounds__(128)
 tma_gather_selftest_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ A, const int* __restrict__ idx, float* __restrict__ D,
-                           int N, long long* cycles) {
+                           int N, int a_tmem, long long* cycles) {
     extern __shared__ __align__(1024) unsigned char sm[];
     __shared__ __align__(8) uint64_t bar, gbar;
     __shared__ uint32_t tmem_slot;
@@ -19,7 +19,7 @@ tma_gather_selftest_kernel(const __grid_constant__ CUtensorMap tmap, const float
     unsigned char* sXb = sm;
     uint4* sAh = reinterpret_cast<uint4*>(sm + 4 * N * 128);
     uint4* sAl = sAh + 16 * 128;
-    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_init(&gbar, 1);
@@ -36,7 +36,13 @@ tma_gather_selftest_kernel(const __grid_constant__ CUtensorMap tmap, const float
         split8(FMT_F16, v, hi, lo);
         sAh[kc * 128 + tid] = hi;
         sAl[kc * 128 + tid] = lo;
+        if (a_tmem) {   // the same planes as tensor-memory A operands (columns 256.., 320..)
+            tmem_st_nw<4>(lane_base + 256 + kc * 4, reinterpret_cast<const float*>(&hi));
+            tmem_st_nw<4>(lane_base + 320 + kc * 4, reinterpret_cast<const float*>(&lo));
+        }
     }
+    if (a_tmem) tmem_wait_st();
+    tc_fence_before();
     fence_proxy_async();
     __syncthreads();
     long long t0 = 0, t1 = 0, t_hot = 0;
@@ -61,34 +67,42 @@ tma_gather_selftest_kernel(const __grid_constant__ CUtensorMap tmap, const float
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp_u == 0) {
-        if (elect_one()) {
-            const uint32_t idesc = umma_idesc_f16(128, N, false, false, FMT_F16, FMT_F16);
-            const uint32_t xb = smem_u32(sXb), bh = desc_hi_sw128(1024);
-            const uint32_t ah = desc_hi(128);
-            uint32_t acc = 0;
-            // three plane products: A_lo X_hi, A_hi X_lo, A_hi X_hi
-            for (int term = 0; term < 3; ++term) {
-                const uint32_t a_addr = smem_u32(term == 0 ? sAl : sAh);
-                const uint32_t x_addr = xb + (term == 1 ? 2u : 0u) * (uint32_t)N * 128;
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t al = desc_lo(a_addr + ks * 2 * 2048, 2048);
-                    const uint32_t bl = desc_lo_sw128(x_addr + (ks >> 2) * (uint32_t)N * 128 + (ks & 3) * 32);
-                    umma_issue_ss(tmem, al, ah, bl, bh, idesc, acc);
-                    acc = 1u;
-                }
-            }
-            umma_commit(&bar);
-        }
-        __syncwarp();
-    }
-    mbar_wait(&bar, 0);
-    tc_fence_after();
-    const long long t2 = clock64();
     if (tid == 0 && cycles) {
         cycles[0] = t_hot;      // cold gather
-        cycles[1] = t2 - t1;    // MMAs
         cycles[2] = t1 - t0;    // L2-hot gather
+    }
+    for (int reps = 1; reps <= 8; reps *= 8) {   // one GEMM, then eight back to back (steady-state cycles per MMA); same result
+        __syncthreads();
+        const long long t2 = clock64();
+        if (warp_u == 0) {
+            if (elect_one()) {
+                const uint32_t idesc = umma_idesc_f16(128, N, false, false, FMT_F16, FMT_F16);
+                const uint32_t xb = smem_u32(sXb), bh = desc_hi_sw128(1024);
+                const uint32_t ah = desc_hi(128);
+                for (int r = 0; r < reps; ++r) {
+                    uint32_t acc = 0;
+                    // three plane products: A_lo X_hi, A_hi X_lo, A_hi X_hi
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t a_addr = smem_u32(term == 0 ? sAl : sAh);
+                        const uint32_t a_t = tmem + (term == 0 ? 320u : 256u);
+                        const uint32_t x_addr = xb + (term == 1 ? 2u : 0u) * (uint32_t)N * 128;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint32_t bl = desc_lo_sw128(x_addr + (ks >> 2) * (uint32_t)N * 128 + (ks & 3) * 32);
+                            if (a_tmem) umma_issue_ts(tmem, a_t + 8 * ks, bl, bh, idesc, acc);
+                            else umma_issue_ss(tmem, desc_lo(a_addr + ks * 2 * 2048, 2048), ah, bl, bh, idesc, acc);
+                            acc = 1u;
+                        }
+                    }
+                }
+                umma_commit(&bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&bar, reps == 1 ? 0 : 1);
+        tc_fence_after();
+        const long long t3 = clock64();
+        if (tid == 0 && cycles) cycles[reps == 1 ? 1 : 3] = t3 - t2;
     }
     for (int c0 = 0; c0 < N; c0 += 16) {
         float v[16];
@@ -97,7 +111,7 @@ tma_gather_selftest_kernel(const __grid_constant__ CUtensorMap tmap, const float
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 
@@ -181,7 +195,7 @@ gather_probe_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __res
 
 }  // namespace kpf
 
-extern "C" int kpf_tma_gather_selftest(const void* table, long long rows, const float* A, const int* idx, float* D, int N, long long* cycles,
+extern "C" int kpf_tma_gather_selftest(const void* table, long long rows, const float* A, const int* idx, float* D, int N, int a_tmem, long long* cycles,
                                        cudaStream_t stream) {
     using namespace kpf;
     KPF_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && rows >= 1 && ((uintptr_t)table % 16) == 0 && ((uintptr_t)idx % 16) == 0);
@@ -191,7 +205,7 @@ extern "C" int kpf_tma_gather_selftest(const void* table, long long rows, const 
     const size_t smem = (size_t)4 * N * 128 + 2 * 16 * 128 * 16 + 1024;
     cudaError_t e = kpf::set_smem(tma_gather_selftest_kernel, smem);
     if (e != cudaSuccess) return (int)e;
-    tma_gather_selftest_kernel<<<1, 128, smem, stream>>>(map, A, idx, D, N, cycles);
+    tma_gather_selftest_kernel<<<1, 128, smem, stream>>>(map, A, idx, D, N, a_tmem, cycles);
     KPF_CHECK_LAUNCH();
     return 0;
 }
