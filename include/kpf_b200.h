@@ -27,6 +27,7 @@ typedef struct CUstream_st* cudaStream_t;
 
 enum { KPF_F32 = 0, KPF_BF16 = 1 };
 enum { KPF_ERR_BAD_ARGUMENT = -1, KPF_ERR_UNSUPPORTED = -2 };
+#define KPF_POINT_EMBED_STAGE_BYTES_PER_TILE 79200   /* kpf_point_embed stage_out / stage_in: bytes per 64-point tile */
 
 /* Library ABI version (bumped on any signature change). */
 int kpf_abi_version(void);
@@ -187,14 +188,19 @@ int kpf_exchange_wait(const void* exchange_buffer, int* xstep, int samples_per_s
  *   folded Conv1d+BN embeddings and both relus as a row [hi 128 | lo 128] of two planes in format fmt (0 = fp16, 1 = bf16);
  *   part_acc [B,N/64,128,32] f32 and part_ms [B,N/64,2,32] f32: per 64-point tile the softmax-aggregation numerators
  *   sum_n e[n][c]*exp(w[n][j]-max_tile) and (max_tile, sum_tile).  N % 64 == 0.  Split-precision tensor-core GEMMs
- *   (csrc/umma_split.cuh), weights resident in tensor memory: fp32-class results. */
+ *   (csrc/umma_split.cuh), weights resident in tensor memory: fp32-class results.
+ *   stage_out / stage_in (either or both NULL, never both set): the gathered inputs do not depend on the joints, and the two
+ *   blocks of KPFusion gather the same taps (model.py:297-306 per block).  With stage_out the launch also stores every tile's
+ *   gathered operand image ([B*N/64] x KPF_POINT_EMBED_STAGE_BYTES_PER_TILE bytes, 16-byte aligned); a later launch on the
+ *   same maps / idx / clos / order passes it as stage_in and loads the images with the TMA engine instead of gathering
+ *   (feat_hi / feat_lo / idx / clos are then not read).  Results are bit-identical to the unstaged launch. */
 int kpf_repack_features(const void* f_d, const void* f_rgb, const void* f_w, long long w_batch_stride, int dtype, int B, int C, int J,
                         int HW, void* out, void* out_lo, cudaStream_t stream);
 int kpf_point_embed(const void* feat_hi, const void* feat_lo, const int32_t* idx, const float* clos, const float* pcl, const float* joint,
                     const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW, float kernel_size, int fmt,
                     void* e_out,
                     long long e_batch_stride /* 16-bit elements between samples of e_out, >= N*256; (N+J)*256 or more when kpf_desa_fused follows */,
-                    float* part_acc, float* part_ms, int num_sms, long long* dbg, cudaStream_t stream);
+                    float* part_acc, float* part_ms, void* stage_out, const void* stage_in, int num_sms, long long* dbg, cudaStream_t stream);
 
 /* ---- 8f-1 DESA on tensor cores (csrc/desa_fused.cu), model/model.py:129-204 + joint embeddings :323-325 ---------------
  * e / part_acc / part_ms: outputs of kpf_point_embed; pcl [B,N,3]; joint [B,J,3]; S scales with radii r0..r3 and

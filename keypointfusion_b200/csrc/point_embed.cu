@@ -102,6 +102,11 @@ struct PointParams {
     long long e_bs;          //   joint rows behind the points)
     float* part_acc;         // [B,T,128,32]   T = N / 64
     float* part_ms;          // [B,T,2,32]  (max, sum)
+    // The gathered inputs do not depend on the joints, and both blocks of KPFusion gather the same taps of the same maps
+    // (model.py:297-306 runs per block): a launch can store every tile's gathered operand image (stage_out) and a later launch on
+    // the same points can load it with the TMA engine instead of gathering again (stage_in).  [B*T][PE_STAGE_BYTES], 16-byte aligned.
+    unsigned char* stage_out;
+    const unsigned char* stage_in;
     int B, N, J, HW, fmt;
     int probe;               // profiling aid (KPF_PE_PROBE): bit 0 = gather from row 0 only (L1 hits), bit 1 = skip the main MMAs
     float kernel_size;
@@ -124,12 +129,25 @@ constexpr int PE_TP = 64;    // points per tile
 // them the accumulator columns are reused for e^T (the aggregation's A operand) and the aggregation accumulator
 constexpr uint32_t PE_W1H = 0, PE_W1L = 128, PE_W2H = 256, PE_W2L = 320, PE_ACC1 = 384, PE_ACC2 = 448;
 constexpr uint32_t PE_EH = PE_ACC2, PE_EL = PE_ACC2 + 32, PE_ACC3 = PE_ACC1;
+// staged tile image: the feature chunks (k-chunks 0..19) of the 8 point groups of both A1 planes, the A2 planes, the raw gathered
+// weight-map values (sT: [21][65] f32 + 3 pad)
+constexpr int PE_ST_X1 = 20 * 8 * 16;                      // bytes per (plane, point group) run of sX1
+constexpr int PE_ST_T = (21 * 65 + 3) * 4;                 // bytes of sT
+constexpr int PE_STAGE_BYTES = 16 * PE_ST_X1 + 2 * 1024 * 16 + PE_ST_T;
+
+// bulk copy shared -> global through the TMA engine (SASS: UBLKCP); bytes % 16 == 0, 16 B aligned
+__device__ __forceinline__ void tma_bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
 
 // The whole point stage, computed TRANSPOSED: D^T[channel][point] = W[channel][k] X[point][k].  The folded weights (K = 384, two
 // 16-bit planes) stay in TENSOR MEMORY for the life of the persistent CTA as the A operands; a tile is 64 points whose gathered
 // inputs are written as K-major B operand planes; a thread of the epilogue owns one output channel (its TMEM lane) and 16 points.
-template <int FMT>
+// STAGE: 0 = gather; 1 = gather and store the tiles' operand images (stage_out); 2 = load them instead of gathering (stage_in).
+// A template parameter: the launches that do not stage carry none of its code or registers.
+template <int FMT, int STAGE>
 __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams p) {
+    constexpr bool ST_OUT = STAGE == 1, ST_IN = STAGE == 2;
     extern __shared__ __align__(128) unsigned char pe_smem[];
     uint4* sX1 = reinterpret_cast<uint4*>(pe_smem);   // 2 planes x [8 point groups][32 k-chunks][8 points]   (K = 256)
     uint4* sX2 = sX1 + 2 * 2048;                       // 2 planes x [8][16][8]                                (K = 128)
@@ -140,7 +158,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
     float* sB = sRed + 32;                             // b1[128], b2[128]
     float* sT = sB + 256;                              // [21][65] transposed softmax scratch
     int* sN = reinterpret_cast<int*>(sT + 21 * 65 + 3);   // [2][64] point ids of the tile in flight / being prefetched
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t mma_bar, in_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = warp_index_uniform();  // MMA issue: one elected lane of warp 0 from warp-uniform code (umma.cuh)
@@ -156,6 +174,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&mma_bar, 1);
+        mbar_init(&in_bar, 1);
         fence_mbar_init();
     }
     for (int i = tid; i < 256; i += PE_NT) sB[i] = p.wvec[i];
@@ -204,14 +223,29 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         const int n_id = p.order ? __ldg(p.order + (size_t)b * N + t * PE_TP + r) : t * PE_TP + r;   // tile = 64 consecutive points of the order
         if (sub == 0 && grp == 0) sN[par * PE_TP + r] = n_id;
         const size_t pn = (size_t)b * N + n_id;
-        id = __ldg(reinterpret_cast<const int4*>(p.idx + pn * 4));
-        cw = __ldg(reinterpret_cast<const float4*>(p.clos + pn * 4));
+        if (!ST_IN) {
+            id = __ldg(reinterpret_cast<const int4*>(p.idx + pn * 4));
+            cw = __ldg(reinterpret_cast<const float4*>(p.clos + pn * 4));
+        }
         px = __ldg(p.pcl + pn * 3);
         py = __ldg(p.pcl + pn * 3 + 1);
         pz = __ldg(p.pcl + pn * 3 + 2);
     };
+    // staged input: warp 0 pulls a tile's image into sX1 (feature chunks) / sX2 / sT with 18 bulk copies, one per lane
+    auto load_stage = [&](int tile) {   // call from all lanes of warp 0
+        const unsigned char* src = p.stage_in + (size_t)tile * PE_STAGE_BYTES;
+        if (lane == 0) mbar_expect_tx(&in_bar, PE_STAGE_BYTES);
+        __syncwarp();
+        if (lane < 16) tma_bulk_g2s(sX1 + (lane >> 3) * 2048 + (lane & 7) * 256, src + (size_t)lane * PE_ST_X1, PE_ST_X1, &in_bar);
+        else if (lane == 16) tma_bulk_g2s(sX2, src + 16 * PE_ST_X1, 2 * 1024 * 16, &in_bar);
+        else if (lane == 17) tma_bulk_g2s(sT, src + 16 * PE_ST_X1 + 2 * 1024 * 16, PE_ST_T, &in_bar);
+    };
+    uint32_t in_phase = 0;
     pdl_wait();   // weights only so far; points, indices and the repacked maps come from the previous kernels
-    if ((int)blockIdx.x < p.B * T) fetch_point(blockIdx.x, 0);
+    if ((int)blockIdx.x < p.B * T) {
+        fetch_point(blockIdx.x, 0);
+        if (ST_IN && warp == 0) load_stage(blockIdx.x);
+    }
 
     for (int tile = blockIdx.x; tile < p.B * T; tile += gridDim.x) {
         const int b = tile / T, t = tile - b * T;
@@ -227,7 +261,14 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         float wraw[8];   // grp 0: gathered weight-map channels [8 sub, 8 sub + 8) of this point
         uint4* x1r = sX1 + (r >> 3) * 256 + (r & 7);
         uint4* x2r = sX2 + (r >> 3) * 128 + (r & 7);
-        {
+        if (ST_IN) {   // the tile's gathered image was staged by an earlier launch: it is (being) copied in by the TMA engine
+            mbar_wait(&in_bar, in_phase);
+            in_phase ^= 1;
+            if (grp == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wraw[k] = 8 * sub + k < J ? sT[(8 * sub + k) * 65 + r] : 0.f;
+            }
+        } else {
             const size_t rb = (size_t)b * p.HW;
             if (p.probe & 1) id = make_int4(0, 0, 0, 0);
             const uint4 *h0 = p.feat_hi + (rb + id.x) * PE_CH, *h1 = p.feat_hi + (rb + id.y) * PE_CH, *h2 = p.feat_hi + (rb + id.z) * PE_CH,
@@ -289,20 +330,29 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
             for (int k = 0; k < 8; ++k) wraw[k] = acc[4][k];
         }
         // softmax over the tile's points, step 1: the gathered weights, transposed, for the per-joint maxima
-        if (grp == 0) {
+        if (grp == 0 && !ST_IN) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (8 * sub + k < J) sT[(8 * sub + k) * 65 + r] = wraw[k];
         }
         stamp();
+        if (ST_OUT) fence_proxy_async();   // the operand chunks and sT are read by the bulk stores below (async proxy)
         __syncthreads();  // sJ, sT visible
-        // ---- K4b: [unit offset xyz, closeness] of joints [6sub, 6sub + 6), then xyz -> chunks 20 + 3sub .. of A1 (ops.pack_point_embed
-        //      orders W1's columns to match).  fp32-exact sqrt / divisions: these values feed a split-precision operand.
-        if (grp == 0) {
-            float buf[24];
+        if (ST_OUT && warp == 0 && lane < 18) {   // store this tile's gathered image for a later launch (the 18 runs load_stage reads)
+            unsigned char* dst = p.stage_out + (size_t)tile * PE_STAGE_BYTES;
+            if (lane < 16) tma_bulk_s2g(dst + (size_t)lane * PE_ST_X1, sX1 + (lane >> 3) * 2048 + (lane & 7) * 256, PE_ST_X1);
+            else if (lane == 16) tma_bulk_s2g(dst + 16 * PE_ST_X1, sX2, 2 * 1024 * 16);
+            else tma_bulk_s2g(dst + 16 * PE_ST_X1 + 2 * 1024 * 16, sT, PE_ST_T);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // ---- K4b: items 0..J-1 = [unit offset xyz, closeness] of a joint, item J = the point's xyz; item i fills half (i & 1) of
+        //      k-chunk 20 + i / 2 of A1 (ops.pack_point_embed orders W1's columns to match).  The eight threads of a point (four
+        //      chunk lanes x two groups) take three items each.  fp32-exact sqrt / divisions: the values feed a split-precision operand.
+        {
+            const int u = sub + 4 * grp;
 #pragma unroll
-            for (int jj = 0; jj < 6; ++jj) {
-                const int j = 6 * sub + jj;
+            for (int jj = 0; jj < 3; ++jj) {
+                const int j = 3 * u + jj;
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
                 if (j < J) {
                     const float ox = sJ[4 * j] - px, oy = sJ[4 * j + 1] - py, oz = sJ[4 * j + 2] - pz;
@@ -319,17 +369,11 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
                     o1 = py;
                     o2 = pz;
                 }
-                buf[4 * jj] = o0;
-                buf[4 * jj + 1] = o1;
-                buf[4 * jj + 2] = o2;
-                buf[4 * jj + 3] = o3;
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                uint4 oh, ol;
-                split8(fmt, buf + 8 * c, oh, ol);
-                x1r[(20 + 3 * sub + c) * 8] = oh;
-                x1r[2048 + (20 + 3 * sub + c) * 8] = ol;
+                uint2 oh, ol;
+                split2(fmt, o0, o1, oh.x, ol.x);
+                split2(fmt, o2, o3, oh.y, ol.y);
+                reinterpret_cast<uint2*>(x1r + (20 + (j >> 1)) * 8)[j & 1] = oh;
+                reinterpret_cast<uint2*>(x1r + 2048 + (20 + (j >> 1)) * 8)[j & 1] = ol;
             }
         }
         // softmax step 1b: per-joint maximum over the tile's 64 points, 16 threads per joint
@@ -345,6 +389,8 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
             if (rs == 0) sRed[rj] = rj < J ? m : -INFINITY;
         }
         stamp();
+        // the bulk stores have read their sources: sT is rewritten after the barrier below, the operands by the next tile
+        if (ST_OUT && warp == 0 && lane < 18) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -424,6 +470,11 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         tc_fence_before();
         __syncthreads();   // every warp has read its accumulator columns: they are reused for e^T and the aggregation
         tc_fence_after();
+        // the main MMAs have completed and everybody is past the softmax sums: sX1 / sX2 / sT are free for the next tile's image
+        if (ST_IN && warp == 0 && tile + (int)gridDim.x < p.B * T) {
+            fence_proxy_async();
+            load_stage(tile + gridDim.x);
+        }
         // e^T as the aggregation's A operand in tensor memory: lane = channel, K = the tile's 64 points, 16-bit pairs
         tmem_st_nw<8>(tmem + PE_EH + 8 * cg, reinterpret_cast<const float*>(eh));
         tmem_st_nw<8>(tmem + PE_EL + 8 * cg, reinterpret_cast<const float*>(el));
@@ -464,6 +515,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         tile_par ^= 1;
         stamp();
     }
+    if (ST_OUT && warp == 0 && lane < 18) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staged images are written
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem0, 512);
 }
@@ -502,8 +554,9 @@ extern "C" int kpf_repack_features(const void* f_d, const void* f_rgb, const voi
 extern "C" int kpf_point_embed(const void* feat_hi, const void* feat_lo, const int32_t* idx, const float* clos, const float* pcl,
                                const float* joint, const int32_t* order, const void* wmat, const float* wvec, int B, int N, int J, int HW,
                                float kernel_size, int fmt, void* e_out, long long e_batch_stride, float* part_acc, float* part_ms,
-                               int num_sms, long long* dbg, cudaStream_t stream) {
+                               void* stage_out, const void* stage_in, int num_sms, long long* dbg, cudaStream_t stream) {
     using namespace kpf;
+    KPF_REQUIRE(((uintptr_t)stage_out % 16) == 0 && ((uintptr_t)stage_in % 16) == 0 && !(stage_out && stage_in));
     KPF_REQUIRE(B >= 0 && N >= PE_TP && N % PE_TP == 0 && J >= 1 && J <= 21 && HW >= 1 && num_sms >= 1);
     KPF_REQUIRE(fmt == FMT_F16 || fmt == FMT_BF16);
     KPF_REQUIRE(((uintptr_t)feat_hi % 16) == 0 && ((uintptr_t)feat_lo % 16) == 0 && ((uintptr_t)wmat % 16) == 0 && ((uintptr_t)idx % 16) == 0 &&
@@ -520,7 +573,10 @@ extern "C" int kpf_point_embed(const void* feat_hi, const void* feat_lo, const i
         p.probe = probe;
     }
     p.dbg = dbg;
-    auto kern = fmt == FMT_F16 ? point_embed_kernel<FMT_F16> : point_embed_kernel<FMT_BF16>;
+    p.stage_out = (unsigned char*)stage_out; p.stage_in = (const unsigned char*)stage_in;
+    const int st = stage_out ? 1 : stage_in ? 2 : 0;
+    auto kern = fmt == FMT_F16 ? (st == 0 ? point_embed_kernel<FMT_F16, 0> : st == 1 ? point_embed_kernel<FMT_F16, 1> : point_embed_kernel<FMT_F16, 2>)
+                               : (st == 0 ? point_embed_kernel<FMT_BF16, 0> : st == 1 ? point_embed_kernel<FMT_BF16, 1> : point_embed_kernel<FMT_BF16, 2>);
     cudaError_t e = kpf::set_smem(kern, PE_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int tiles = B * (N / PE_TP);
@@ -529,3 +585,5 @@ extern "C" int kpf_point_embed(const void* feat_hi, const void* feat_lo, const i
     KPF_CHECK_LAUNCH();
     return 0;
 }
+
+static_assert(kpf::PE_STAGE_BYTES == KPF_POINT_EMBED_STAGE_BYTES_PER_TILE, "include/kpf_b200.h states the staged tile size");

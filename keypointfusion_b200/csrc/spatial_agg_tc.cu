@@ -116,6 +116,13 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
     const float ffs = (float)fs;
     __syncthreads();
 
+    // depth of this thread's cell, fetched one tile ahead (an L2 round trip at the head of every tile otherwise)
+    auto cell_depth = [&](int t) {
+        const int m = t * 128 + row, r = m / fs, col = m - r * fs;
+        return __ldg(p.depth + (size_t)b * p.depth_bs + (size_t)r * p.depth_rs + (size_t)col * p.depth_cs);
+    };
+    float d_next = cell_depth(t_begin);
+    bool gemm_b_pending = false;   // GEMM B of the previous tile: waited for only where its operands are rewritten
     stamp();
     for (int t = t_begin; t < t_end; ++t) {
         uint4* cur = sF + ((t - t_begin) & (NBUF - 1)) * NP * 2048;
@@ -126,7 +133,8 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
         if (t == t_begin + 1) stamp();
         // ---- per-cell geometry (thread = cell `row`, joints [8cg, 8cg + 8)): heat-map chunk (A operand) and GAM (registers)
         const int m = t * 128 + row, r = m / fs, col = m - r * fs;
-        const float d = __ldg(p.depth + (size_t)b * p.depth_bs + (size_t)r * p.depth_rs + (size_t)col * p.depth_cs);
+        const float d = d_next;
+        if (t + 1 < t_end) d_next = cell_depth(t + 1);
         const float3 qc = uvd2xyz(cam, cell_coord(col, ffs), cell_coord(r, ffs), d);   // same arithmetic as the fp32 kernel (spatial_agg.cu)
         float gam[8], hm[8];
 #pragma unroll
@@ -141,6 +149,12 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
                 hm[i] = 0.f;
                 gam[i] = 0.f;
             }
+        }
+        if (gemm_b_pending) {   // the geometry above ran under GEMM B of tile t - 1; sHm / sFr / sG are rewritten from here on
+            mbar_wait(&mma_bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+            gemm_b_pending = false;
         }
         {
             uint4 oh, ol;
@@ -230,11 +244,12 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
             }
             __syncwarp();
         }
-        mbar_wait(&mma_bar, phase);  // sFr / sG / sHm are rewritten by the next tile
-        phase ^= 1;
-        tc_fence_after();
+        gemm_b_pending = true;
         if (t == t_begin + 1) stamp();
     }
+    mbar_wait(&mma_bar, phase);   // the last tile's GEMM B
+    phase ^= 1;
+    tc_fence_after();
     stamp();
     {
         float o[8];

@@ -195,6 +195,21 @@ def _(feat_hi, feat_lo, idx32, clos, pcl, joint, wmat, wvec, kernel_size, fmt, o
     return _e_like(pcl), pcl.new_empty(B, N // 64, 128, 32, dtype=torch.float32), pcl.new_empty(B, N // 64, 2, 32, dtype=torch.float32)
 
 
+@_op("point_embed_staged", mutates=("stage",))
+def point_embed_staged(feat_hi: Tensor, feat_lo: Tensor, idx32: Tensor, clos: Tensor, pcl: Tensor, joint: Tensor, wmat: Tensor, wvec: Tensor,
+                       kernel_size: float, fmt: int, stage: Tensor, read: bool, order: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """point_embed that also stores (read = False) or instead loads (read = True) the tiles' gathered operand images in `stage`
+    (ops.point_embed_stage): the second block of KPFusion gathers the same taps as the first (model.py:297-306 per block)."""
+    return ops.point_embed((feat_hi, feat_lo if feat_lo.numel() else None), idx32, clos, pcl, joint, wmat, wvec, kernel_size, order=order, fmt=fmt,
+                           stage_in=stage if read else None, stage_out=None if read else stage)
+
+
+@point_embed_staged.register_fake
+def _(feat_hi, feat_lo, idx32, clos, pcl, joint, wmat, wvec, kernel_size, fmt, stage, read, order=None):
+    B, N = pcl.shape[:2]
+    return _e_like(pcl), pcl.new_empty(B, N // 64, 128, 32, dtype=torch.float32), pcl.new_empty(B, N // 64, 2, 32, dtype=torch.float32)
+
+
 @_op("desa_fused", mutates=("e",))
 def desa_fused(e: Tensor, part_acc: Tensor, part_ms: Tensor, pcl: Tensor, joint: Tensor, wmat: Tensor, wvec: Tensor, r0: float, r1: float,
                r2: float, nsample: int, fmt: int) -> Tuple[Tensor, Tensor]:

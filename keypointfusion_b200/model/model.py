@@ -380,12 +380,15 @@ class Block_KPFusion(_KernelCache, nn.Module):
                     pe_wvec=pe_wvec)
 
     def forward(self, img_feat, img_feature_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature, loader,
-                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None, rgb_planes=None, point_order=None, exchange=None):
+                img_down, center, M, cube, cam_para, writer=None, ii=0, featT=None, rgb_planes=None, point_order=None, exchange=None,
+                pe_stage=None, pe_stage_read=False):
         """model.py:287-351.  Five launches, all hand-written split-precision tcgen05 kernels (fp32-class results for bf16 AND
         fp32 feature maps -- an fp32 map is carried as two bf16 planes):
             point stage (K4b + K3 + embeddings + softmax partials) -> DESA -> [fusion conv + init_TR] -> K5 -> [crossTR + final_TR]
         `featT` / `rgb_planes`: the repacked maps / the rgb map's planes when the caller (KPFusion.forward_path) already made them
-        for both blocks."""
+        for both blocks.  `pe_stage` (ops.point_embed_stage): the point stage stores its gathered, joint-independent operand tiles
+        there (pe_stage_read False) or loads them from there instead of gathering again (True: a block that runs on the same
+        maps, taps and point order as the one that filled it -- block 2 after block 1)."""
         _inference_only(self, img_feat, img_feature_rgb, joint_xyz, img_offset)
         k = self.kc()
         B, N, _ = pcl.shape
@@ -405,8 +408,12 @@ class Block_KPFusion(_KernelCache, nn.Module):
             rgb_planes = _rgb_planes(img_feature_rgb)
         if pcl_index.dtype != torch.int32:
             pcl_index = pcl_index.to(torch.int32)
-        e, p_acc, p_ms = K.point_embed(featT[0], featT[1], pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8, fmt,
-                                       point_order)                                                       # model.py:295-320
+        if pe_stage is None:
+            e, p_acc, p_ms = K.point_embed(featT[0], featT[1], pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8, fmt,
+                                           point_order)                                                   # model.py:295-320
+        else:
+            e, p_acc, p_ms = K.point_embed_staged(featT[0], featT[1], pcl_index, pcl_closeness, pcl, joint_xyz, k["pe_wmat"], k["pe_wvec"], 0.8,
+                                                  fmt, pe_stage, pe_stage_read, point_order)
         r = self.FA.radius
         part, jf = K.desa_fused(e, p_acc, p_ms, pcl, joint_xyz, k["ds_wmat"], k["ds_wvec"], float(r[0]), float(r[1]), float(r[2]),
                                 self.FA.S[0], fmt)                                                        # model.py:323-327
@@ -472,12 +479,15 @@ class KPFusion(nn.Module):
         # rgb map's NCHW plane(s) for K5
         featT = K.repack_features(img_feat, img_feat_rgb, img_offset[:, J * 4:])
         rgb_planes = _rgb_planes(img_feat_rgb)
+        # ... and the gathered point-stage operands: both blocks gather the same taps (model.py:297-306 per block); block 1 stores
+        # its tiles, the later blocks load them with the TMA engine
+        pe_stage = ops.point_embed_stage(pcl.shape[0], pcl.shape[1], pcl.device) if self.num_stages > 1 and pcl.shape[1] % 64 == 0 else None
         for i in range(self.num_stages):                                                                 # :417-424
             block = getattr(self, f"block{i + 1}")
             r3d, r2d, updated_2d_feature[i + 1], spatial_weight[i], _ = block(
                 img_feat, img_feat_rgb, pcl, joint_xyz, pcl_closeness, pcl_index, img_offset, updated_2d_feature[i], loader, img_down,
                 center, M, cube, cam_para, writer, ii, featT=featT, rgb_planes=rgb_planes, point_order=order,
-                exchange=exchange if i == self.num_stages - 1 else None)
+                exchange=exchange if i == self.num_stages - 1 else None, pe_stage=pe_stage, pe_stage_read=i > 0)
             result.append(r3d)
             result.append(r2d)
             joint_xyz = r2d

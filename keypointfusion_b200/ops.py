@@ -604,9 +604,19 @@ def pack_point_embed(Wf, bf, Wx, bx, Wp, bp, Wr, br, J, fmt=None):
 E_ROW = 256   # 16-bit elements per point-feature row: [hi 128 | lo 128]
 
 
-def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg=None, order=None, fmt=None):
+PE_STAGE_BYTES_PER_TILE = 79200   # include/kpf_b200.h: KPF_POINT_EMBED_STAGE_BYTES_PER_TILE
+
+
+def point_embed_stage(B, N, device):
+    """workspace for point_embed(stage_out=...) -> point_embed(stage_in=...): the gathered operand image of every 64-point tile"""
+    return torch.empty(int(B) * (int(N) // 64) * PE_STAGE_BYTES_PER_TILE, device=device, dtype=torch.uint8)
+
+
+def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg=None, order=None, fmt=None, stage_out=None, stage_in=None):
     """featT = (hi, lo | None) from repack_features.
-    -> e [B,N,256] int16 (rows [hi 128 | lo 128] in the split format), part_acc [B,T,128,32] f32, part_ms [B,T,2,32] f32  (T = N/64)."""
+    -> e [B,N,256] int16 (rows [hi 128 | lo 128] in the split format), part_acc [B,T,128,32] f32, part_ms [B,T,2,32] f32  (T = N/64).
+    stage_out: also store the gathered (joint-independent) operand image of every tile into this point_embed_stage buffer;
+    stage_in: load those images (a launch on the same maps / taps / order filled them) instead of gathering: block 2 of KPFusion."""
     fmt = SPLIT_FMT if fmt is None else fmt
     feat_hi, feat_lo = featT if isinstance(featT, (tuple, list)) else (featT, None)
     _need_cuda(feat_hi, idx32, clos, pcl, joint)
@@ -626,7 +636,7 @@ def point_embed(featT, idx32, clos, pcl, joint, wmat, wvec, kernel_size=0.8, dbg
     acc = torch.empty(B, T, 128, 32, device=dev, dtype=torch.float32)
     ms = torch.empty(B, T, 2, 32, device=dev, dtype=torch.float32)
     _call("kpf_point_embed", _p(feat_hi), _p(feat_lo), _p(idx32), _p(clos), _p(pcl), _p(joint), _p(order), _p(wmat), _p(wvec), B, N, J, HW,
-          float(kernel_size), fmt, _p(e), e.stride(0), _p(acc), _p(ms), sm_count(dev), _p(dbg))
+          float(kernel_size), fmt, _p(e), e.stride(0), _p(acc), _p(ms), _p(stage_out), _p(stage_in), sm_count(dev), _p(dbg))
     return e, acc, ms
 
 

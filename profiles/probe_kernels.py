@@ -31,6 +31,9 @@ def t(fn, n=10):
     return e0.elapsed_time(e1) * 1e3 / (5 * n)
 e, acc, ms = ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8, order=order)
 print("point_embed us", t(lambda: ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8, order=order)))
+stage = ops.point_embed_stage(B, pcl.shape[1], dev)
+print("point_embed + stage_out us", t(lambda: ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8, order=order, stage_out=stage)))
+print("point_embed from stage_in us", t(lambda: ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8, order=order, stage_in=stage)))
 print("desa us", t(lambda: ops.desa_fused(e, acc, ms, pcl, joint, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, 64)))
 # clock stamps of the DESA kernels (CTA 0 / thread 0; prep: the joint-embedding role dbg[0..7] and the ball-query role dbg[8..15]; tile: dbg[16..])
 dbg = torch.zeros(128, dtype=torch.int64, device=dev)

@@ -183,3 +183,32 @@ def test_desa_fused(path_params, B, which):
     # the stand-alone drop-in module (model.py:166-204 signature) runs the same kernels with the joint features given
     mod = blk.FA(ee.to(DEV), rjf.to(DEV), pcl, joint)
     assert rms_rel(mod, rout) < _tol(), rms_rel(mod, rout)
+
+
+@pytest.mark.parametrize("maps", ["bf16", "fp32"])
+@pytest.mark.parametrize("B", [2, 5, 64])
+def test_point_embed_staged_tiles(path_params, B, maps):
+    """Block 2 of KPFusion gathers the same taps of the same maps as block 1 (model.py:297-306 runs per block).  A launch that
+    stores its gathered operand tiles (stage_out) followed by one that loads them (stage_in: other joints, the other block's
+    weights, no gather) must be BIT-identical to gathering again -- with and without the spatial processing order."""
+    from keypointfusion_b200 import ops
+    inp, c, pcl, close, idx, blk = _desa_setup(path_params, B, 90 + B)
+    from keypointfusion_b200.model.model import KPFusion
+    net = KPFusion(joint_num=21)
+    net.load_state_dict(path_params)
+    net = net.to(DEV).eval()
+    k1, k2 = net.block1.kc(), net.block2.kc()
+    cast = (lambda t: t.bfloat16()) if maps == "bf16" else (lambda t: t.float())
+    featT = ops.repack_features(cast(c["img_feat"]), cast(c["img_feat_rgb"]), cast(c["img_offset"][:, 84:]))
+    j1, j2 = _joint_sets(pcl, "dense"), _joint_sets(pcl, "sparse")
+    for order in (None, ops.spatial_order(pcl, c["center"], c["M"], c["cube"], c["cam"], 128, 32)):
+        stage = ops.point_embed_stage(B, pcl.shape[1], pcl.device)
+        stage.fill_(0x5a)
+        a = ops.point_embed(featT, idx, close, pcl, j1, k1["pe_wmat"], k1["pe_wvec"], 0.8, order=order, stage_out=stage)
+        ref1 = ops.point_embed(featT, idx, close, pcl, j1, k1["pe_wmat"], k1["pe_wvec"], 0.8, order=order)
+        for x, y in zip(a, ref1):
+            assert torch.equal(x, y)                      # storing the tiles does not change the launch's own results
+        got = ops.point_embed(featT, idx, close, pcl, j2, k2["pe_wmat"], k2["pe_wvec"], 0.8, order=order, stage_in=stage)
+        ref2 = ops.point_embed(featT, idx, close, pcl, j2, k2["pe_wmat"], k2["pe_wvec"], 0.8, order=order)
+        for x, y in zip(got, ref2):
+            assert torch.equal(x, y)
