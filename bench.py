@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--config", default="path", choices=["path", "sweep", "full", "demo"],
                     help="path: BASELINE configs[1] (default, the headline line); sweep: config 4; full: config 3; demo: config 5")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-this-GPU leg")
-    ap.add_argument("--overlap", type=int, default=2, help="consecutive steps kept in flight on this many streams (1 = strictly serial)")
+    ap.add_argument("--overlap", type=int, default=4, help="consecutive steps kept in flight on this many streams (1 = strictly serial; measured at batch 64: 1 / 2 / 3 / 4 / 6 / 8 -> 0.736 / 0.604 / 0.543 / 0.505 / 0.497 / 0.512 ms per step)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -167,7 +167,6 @@ def main():
     config = {"workload": "fusion path only (getpcl + offset2joint + img2pcl_index + 2 x Block_KPFusion), batch 64 synthetic RGB-D crops "
                           "128x128, 21 joints, 1024 points, bf16 feature maps [BASELINE.json configs[1]]",
               "batch_per_gpu": B, "parallelism": f"batch-sharded x{world}",
-              "l2": "inputs rotate over 4 resident sets (~200 MB) > 126 MB L2; no flush kernel inside the timed region",
               "launch": "one CUDA graph replay per step; each resident input set has its own graph captured over it (no staging copies); the e2e leg uploads pinned host inputs into the graphs' static buffers every step"}
 
     if a.impl == "reference":
@@ -210,15 +209,15 @@ def main():
     sampler.start()
     net = build_net(dev)
     ldr = Loader(img_size=S)
-    NSETS = 4
+    S_OV = 1 if a.no_graph else max(1, a.overlap)
+    NSETS = S_OV * ((4 + S_OV - 1) // S_OV)   # >= 4 resident input sets (> L2 together), a multiple of the steps in flight
+    config["l2"] = f"inputs rotate over {NSETS} resident sets (~{NSETS * 51} MB) > 126 MB L2; no flush kernel inside the timed region"
     hosts = [host_inputs(B, seed=1000 * rank + s) for s in range(NSETS)]
     sets = [{k: v.to(dev) for k, v in h.items()} for h in hosts]
     pinned = [{k: v.pin_memory() for k, v in h.items()} for h in hosts]
     gathered = torch.empty(world * B, J, 3, device=dev) if world > 1 else None
 
     from keypointfusion_b200.runtime import GraphedFusionPath, OverlappedSteps, PeerExchange
-    S_OV = 1 if a.no_graph else max(1, a.overlap)
-    assert NSETS % S_OV == 0, "--overlap must divide the number of resident input sets (4)"
     # the exchange step: fused into the last kernel of the path (peer stores over NVLink + arrival counter, runtime.PeerExchange),
     # captured inside the graph; KPF_EXCHANGE=nccl falls back to a per-step ncclAllGather issued from the host
     comm = "none"
@@ -500,20 +499,31 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
         e_, acc_, ms_ = ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order)
         part_, jf_ = ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0])
         tok_, r3d_, _ = ops.token_stack(k["tok_init"], desa=part_, jf=jf_)
+        fj_ = torch.randn(B, J, C, device=pcl.device)
+        stage_ = ops.point_embed_stage(B, N_PTS, pcl.device)
+        ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order, stage_out=stage_)
         # per-set point clouds / orders for the kernels whose cost depends on the points matching the depth map they came from
         geo = {}
         for d in sets:
             p_, _ = ops.getpcl(d["img"], d["center"], d["cube"], d["M"], d["cam"], N_PTS, seed=0)
             geo[id(d)] = (p_, ops.spatial_order(p_, d["center"], d["M"], d["cube"], d["cam"], S, H))
     e = 2  # bf16 feature maps
-    # name -> (callable, launches per step, algorithmic bytes per launch, algorithmic FLOPs per launch, bound)
+    # name[variant] -> (callable, launches per step, algorithmic bytes per launch, algorithmic FLOPs per launch, bound); the variants
+    # of a kernel (its two token programs; the point stage storing / loading the gathered tiles) are averaged by launches per step
+    T_ = N_PTS // 64
     stages = {
-        "token_stack_kernel": (lambda d: ops.token_stack(k["tok_init"], desa=part_, jf=jf_), 4,
-                               B * (4 * J * C * 4 + J * C * 4 + J * 12), B * 16.1e6, "tensor"),
+        "token_stack_kernel[tok_init]": (lambda d: ops.token_stack(k["tok_init"], desa=part_, jf=jf_), 2,
+                                         B * (4 * J * C * 4 + J * C * 4 + J * 12), B * 16.05e6, "tensor"),
+        "token_stack_kernel[tok_final]": (lambda d: ops.token_stack(k["tok_final"], x=fj_, y=tok_, r3d=r3d_, want_tokens=False), 2,
+                                          B * (2 * J * C * 4 + J * 12 + J * 12), B * 17.67e6, "tensor"),
         "desa_prep_kernel+desa_tile_kernel": (lambda d: ops.desa_fused(e_, acc_, ms_, pcl, joints, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0]), 2,
                               B * (3 * J * 64 * C * e + N_PTS * 12 + 4 * J * C * 4), B * 270.1e6, "tensor"),
-        "point_embed_kernel": (lambda d: ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order), 2,
-                               B * ((2 * C + J) * H * H * e + N_PTS * 4 * 8 + N_PTS * C * e), B * 95.4e6, "tensor"),
+        "point_embed_kernel[stage_out]": (lambda d: ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order,
+                                                                    stage_out=stage_), 1,
+                                          B * ((2 * C + J) * H * H * e + N_PTS * 4 * 8 + N_PTS * C * e * 2 + T_ * ops.PE_STAGE_BYTES_PER_TILE), B * 95.4e6, "tensor"),
+        "point_embed_kernel[stage_in]": (lambda d: ops.point_embed(featT, idx, close, pcl, joints, k["pe_wmat"], k["pe_wvec"], 0.8, order=order,
+                                                                   stage_in=stage_), 1,
+                                         B * (T_ * ops.PE_STAGE_BYTES_PER_TILE + N_PTS * 16 + N_PTS * C * e * 2), B * 95.4e6, "tensor"),
         "spatial_aggregate_tc_kernel": (lambda d: ops.spatial_aggregate_tc(d["img_feat_rgb"], joints, d["img"][:, :, ::4, ::4], d["center"], d["M"],
                                                                           d["cube"], d["cam"], k["wa_packed"], blk.atten_spatial.bias,
                                                                           blk.weight_dis, blk.fc_spatial2joint_feature.weight,
@@ -554,6 +564,16 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
         if verbose:
             print(f"[breakdown] {name:30s} x{per_step}  {us:8.1f} us  {alg_bytes / us / 1e3:8.1f} GB/s  {alg_flops / us / 1e6:8.2f} TFLOP/s (algorithmic)",
                   file=sys.stderr)
+    variants = res
+    res = {}
+    for name, v in variants.items():   # variants of one kernel -> its per-launch average, weighted by launches per step
+        a = res.setdefault(name.split("[")[0], dict(us=0.0, per_step=0, bytes=0.0, flops=0.0, bound=v["bound"]))
+        for f in ("us", "bytes", "flops"):
+            a[f] += v[f] * v["per_step"]
+        a["per_step"] += v["per_step"]
+    for a in res.values():
+        for f in ("us", "bytes", "flops"):
+            a[f] /= a["per_step"]
     tot = sum(r["us"] * r["per_step"] for r in res.values())
     top = max(res, key=lambda n: res[n]["us"] * res[n]["per_step"])
     r = res[top]
@@ -568,8 +588,10 @@ def dominant_kernel_roofline(net, ldr, sets, hbm, tfl, which, verbose):
     return {"kernel": top, "bound": r["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
             "us_per_launch": r["us"], "launches_per_step": r["per_step"], "share_of_step": r["us"] * r["per_step"] / tot,
             "algorithmic_bytes": r["bytes"], "algorithmic_flops": r["flops"], "peaks": which,
-            "note": "latency-bound: one sample per CTA, ~7 dependent MMA->epilogue steps per transformer layer; see DESIGN.md section 4",
-            "kernels": {n: {"us": round(v["us"], 1), "per_step": v["per_step"]} for n, v in res.items()}}
+            "note": "both token programs timed (tok_init, tok_final), averaged by launches; latency-bound: one sample per CTA, ~7 dependent "
+                    "MMA->epilogue steps per transformer layer, identical time for 1..148 samples (profiles/probe_token.py); see DESIGN.md section 4",
+            "traffic_source": "profiles/dram_bytes_per_launch.json (ncu dram__bytes of the same kernels, profiles/collect.sh; bench.py cannot read DRAM counters itself)",
+            "kernels": {n: {"us": round(v["us"], 1), "per_step": v["per_step"]} for n, v in variants.items()}}
 
 
 if __name__ == "__main__":
