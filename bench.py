@@ -289,9 +289,13 @@ def main():
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            rank_ms[:] = [float(x) / steps for x in every]   # evidence for the scaling run: the job's time is the slowest rank's
+            ms = max(float(x) for x in every)
         return ms
+
+    rank_ms = []
 
     W = max(a.warmup, 3)
     if os.environ.get("KPF_PROFILE"):  # `ncu --profile-from-start off`: capture exactly two warm steps, nothing else
@@ -331,6 +335,7 @@ def main():
         ms = timed(lambda i: overlapped.submit(), a.steps, W, ov=overlapped)
     else:
         ms = timed(lambda i: step(i, sets[i % NSETS]), a.steps, W)
+    device_rank_ms = list(rank_ms)   # per-rank ms per step of the device-resident leg (world > 1)
     if graphed is not None:
         launches = graphed.launches_per_replay * a.steps   # kernels of ours replayed by the graph inside the K timed steps
     else:
@@ -412,6 +417,8 @@ def main():
             "gpu_launches": launches, "comm": comm, "roofline": roof,
             "path_roofline": {"hbm_frac": value / world * PATH_BYTES_PER_SAMPLE / (hbm * 1e9),
                               "tensor_frac": value / world * PATH_FLOPS_PER_SAMPLE / (tfl * 1e12), "peaks": which}}
+    if world > 1:
+        line["rank_ms_per_step"] = [round(x, 4) for x in device_rank_ms]
     if rank == 0 and world == 1:
         # parity of the exact configuration that was timed: a 4-sample slice of resident set 0 against the CPU oracle (the kernels are
         # batch invariant, tests/test_modules_gpu.py)
