@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
     uint4* sF = reinterpret_cast<uint4*>(sJ + 256 + 32);   // [NBUF buffers][NP planes][2048] raw feature tile, index (c/8)*128 + (hw/8)*8 + (c%8)
     uint4* sFr = sF + NBUF * NP * 2048;              // [NP planes][2048] relu copy
     float* sBa = sJ + 256;                           // [32] atten_spatial bias
+    float* sD2 = reinterpret_cast<float*>(sFr + NP * 2048);   // [2][32 joints][fs]: ((cell + 0.5 - centre) / std)^2 per column / per row
     constexpr int fmt = FMT;
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
@@ -115,6 +116,14 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
     const float inv2s2 = 1.f / (2.f * p.hm_sigma * p.hm_sigma);
     const float ffs = (float)fs;
     __syncthreads();
+    // the heat map's squared, std-normalised distances are separable: one division per (joint, column) and (joint, row) instead
+    // of two per (joint, cell); the sum and the exponential below are unchanged (bit-identical heat map)
+    for (int i = tid; i < 2 * 32 * fs; i += K5_NT) {
+        const int ax = i / (32 * fs), j = (i / fs) & 31, c = i - (i / fs) * fs;
+        const float dd = j < J ? ((float)c + 0.5f - sJ[8 * j + ax]) / p.hm_std : 0.f;
+        sD2[(ax * 32 + j) * fs + c] = dd * dd;
+    }
+    __syncthreads();
 
     // depth of this thread's cell, fetched one tile ahead (an L2 round trip at the head of every tile otherwise)
     auto cell_depth = [&](int t) {
@@ -141,8 +150,7 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
         for (int i = 0; i < 8; ++i) {
             const int j = 8 * cg + i;
             if (j < J) {
-                const float dx = ((float)col + 0.5f - sJ[8 * j]) / p.hm_std, dy = ((float)r + 0.5f - sJ[8 * j + 1]) / p.hm_std;
-                hm[i] = expf(-(dx * dx + dy * dy) * inv2s2);
+                hm[i] = expf(-(sD2[j * fs + col] + sD2[(32 + j) * fs + r]) * inv2s2);
                 const float ex = qc.x - sJ[8 * j + 2], ey = qc.y - sJ[8 * j + 3], ez = qc.z - sJ[8 * j + 4];
                 gam[i] = 1.f / (p.gamma * (ex * ex + ey * ey + ez * ez) + 1.f);
             } else {
@@ -344,7 +352,8 @@ extern "C" int kpf_spatial_aggregate_tc(const void* feat_rgb, const void* feat_r
     p.dbg = dbg; p.scratch = scratch; p.counters = counters; p.split = split;
     p.B = B; p.J = J; p.fs = fs; p.img_size = img_size; p.flip = flip; p.hm_std = hm_std; p.hm_sigma = hm_sigma; p.gamma = gamma;
     const int NP = feat_rgb_lo ? 2 : 1, NBUF = feat_rgb_lo ? 1 : 2;
-    const size_t smem = (size_t)(1024 + 1536 + 1792 + (NBUF + 1) * NP * 2048) * 16 + 32 * 8 * 4 + 32 * 4;
+    const size_t smem = (size_t)(1024 + 1536 + 1792 + (NBUF + 1) * NP * 2048) * 16 + 32 * 8 * 4 + 32 * 4 + (size_t)2 * 32 * fs * 4;
+    KPF_REQUIRE(smem <= 227 * 1024);
     auto kern = fmt == FMT_F16 ? spatial_aggregate_tc_kernel<FMT_F16> : spatial_aggregate_tc_kernel<FMT_BF16>;
     cudaError_t e = kpf::set_smem(kern, smem);
     if (e != cudaSuccess) return (int)e;
