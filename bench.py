@@ -210,6 +210,8 @@ def main():
     net = build_net(dev)
     ldr = Loader(img_size=S)
     S_OV = 1 if a.no_graph else max(1, a.overlap)
+    if world > 1 and os.environ.get("KPF_EXCHANGE", "peer") == "nccl":
+        S_OV = 1   # the host-issued all-gather fallback follows every step on the current stream: steps are not overlapped
     NSETS = S_OV * ((4 + S_OV - 1) // S_OV)   # >= 4 resident input sets (> L2 together), a multiple of the steps in flight
     config["l2"] = f"inputs rotate over {NSETS} resident sets (~{NSETS * 51} MB) > 126 MB L2; no flush kernel inside the timed region"
     hosts = [host_inputs(B, seed=1000 * rank + s) for s in range(NSETS)]
@@ -230,8 +232,9 @@ def main():
             comm = "fused peer stores into symmetric memory (no NCCL call on the data path; NCCL_DEBUG logs stay empty)"
         except Exception as ex:   # no peer access / symmetric memory on this box
             print(f"[bench] PeerExchange unavailable ({type(ex).__name__}: {ex}); using ncclAllGather", file=sys.stderr)
+    no_exchange = os.environ.get("KPF_EXCHANGE") == "off"   # diagnosis only: N independent replicas, no exchange step at all
     if world > 1 and px is None:
-        comm = "ncclAllGather of [B_local,21,3] per step, issued from the host"
+        comm = "DIAGNOSTIC: exchange step switched off (independent replicas)" if no_exchange else "ncclAllGather of [B_local,21,3] per step, issued from the host"
     graphed = None if a.no_graph else GraphedFusionPath(net, ldr, sets[0], sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains, exchange=px)
     # device-resident leg: one graph captured directly over each resident input set (no staging copies in the timed region)
     bound = {} if a.no_graph else {id(d): GraphedFusionPath(net, ldr, d, sample_num=N_PTS, kernel=0.8, seed=0, chains=a.chains, bind=True,
@@ -249,7 +252,7 @@ def main():
             if not d["img"].is_cuda:
                 d = {k: v.to(dev, non_blocking=True) for k, v in d.items()}
             joints = run_step(net, ldr, d, seed=i)
-        if world > 1 and px is None:
+        if world > 1 and px is None and not no_exchange:
             dist.all_gather_into_tensor(gathered, joints.contiguous())  # the path's one exchange step (NCCL fallback)
         return joints
 
