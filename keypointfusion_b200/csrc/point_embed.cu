@@ -124,6 +124,8 @@ __device__ __forceinline__ void bf16x8_fma(float* acc, const uint4& v, float w) 
 }
 
 constexpr int PE_NT = 512;
+constexpr int PE_ISSUER = 15;   // the warp whose elected lane issues the MMAs: one of group 1 (warps 8-15), which has no softmax work to
+                                // do while the MMAs are being issued (tcgen05.mma issue blocks at the tensor pipe's rate)
 constexpr int PE_TP = 64;    // points per tile
 // TMEM columns: the resident weight planes (A operands, 16-bit pairs), then the two accumulators; after the epilogue has read
 // them the accumulator columns are reused for e^T (the aggregation's A operand) and the aggregation accumulator
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (warp_u == 0) {
+        if (warp_u == PE_ISSUER) {
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t id64 = umma_idesc_f16(128, PE_TP, false, false, fmt, fmt);
@@ -429,16 +431,16 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
             sP[256 + (r >> 3) * 32 + sub * 8 + (r & 7)] = ol;
         }
         if (tid < 32) ms[tid] = sRed[tid];
-        __syncthreads();
-        {
-            const int rj = tid >> 4, rs = tid & 15;
+        if (grp == 0) {   // the numerators and their sums involve only warps 0-7: their own barrier, so nobody waits for the MMA issuer here
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int rj = tid >> 3, rs = tid & 7;
             float sm_ = 0.f;
             if (rj < J) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) sm_ += sT[rj * 65 + rs + 16 * i];
+                for (int i = 0; i < 8; ++i) sm_ += sT[rj * 65 + rs + 8 * i];
             }
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) sm_ += __shfl_xor_sync(0xffffffffu, sm_, o);
+            for (int o = 1; o < 8; o <<= 1) sm_ += __shfl_xor_sync(0xffffffffu, sm_, o);
             if (rs == 0) ms[32 + rj] = rj < J ? sm_ : 0.f;
         }
         stamp();
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(PE_NT, 1) point_embed_kernel(const PointParams
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (warp_u == 0) {
+        if (warp_u == PE_ISSUER) {
             tc_fence_after();
             if (elect_one()) {   // D[c][j] = sum_n e[n][c] p[n][j]
                 TmemOp a;
