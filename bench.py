@@ -461,11 +461,14 @@ def other_configs(a, rank, world, local):
     if a.config == "sweep":
         assert world == 1, "the kernel sweep is a single-GPU configuration"
         rows = X.sweep(dev, hbm)
+        # the same kernels at config 3's batch (512 crops per GPU): at batch 64 a launch moves 2-15 MB, i.e. 0.3-2 us of HBM time --
+        # below the duration of ANY kernel launch -- so the batch-64 rows measure latency, these measure bandwidth
+        rows += X.sweep(dev, hbm, B=512, sizes=(128,), k7=False)
         k1 = next(r for r in rows if r["kernel"].startswith("backproject") and r["S"] == 128)
         line = dict(base, metric="kernel sweep: back-projection + keypoint gather GB/s over crop sizes 64-256 and 21-42 joints",
                     value=k1["GBs"], unit="GB/s (K1 at S=128; all rows in `sweep`)", scaling="weak", dtype="f32/bf16",
                     config={"workload": "BASELINE.json configs[3]: K1, K2, K3, K4a, K4d over S in {64,96,128,192,256}, J in {21,42}, K7 at the ResNet-18 "
-                                        "stage shapes; batch 64; inputs rotate over resident sets (> L2 where the working set allows)"},
+                                        "stage shapes; batch 64, and batch 512 (config 3's) at S=128; inputs rotate over resident sets (> L2 where the working set allows)"},
                     sweep=rows, roofline={"bound": "hbm", "achieved": k1["GBs"], "peak": hbm, "unit": "GB/s", "frac": k1["GBs"] / hbm,
                                           "traffic": None, "kernel": "backproject_kernel", "peaks": which})
     else:

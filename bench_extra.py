@@ -55,7 +55,7 @@ def _graph_us(fn, args_sets, reps=5):
 
 
 # ------------------------------------------------------------------------------------------------ config 4: kernel sweep
-def sweep(dev, hbm_gbs, B=64):
+def sweep(dev, hbm_gbs, B=64, sizes=(64, 96, 128, 192, 256), k7=True):
     """Bandwidth-bound kernels of north_star items (1) and (2) over S in {64..256}, J in {21, 42}.  Inputs rotate over enough resident
     sets to exceed the 126 MB L2 where the working set allows (stated per row as `sets`)."""
     from keypointfusion_b200 import ops
@@ -64,9 +64,9 @@ def sweep(dev, hbm_gbs, B=64):
 
     def add(kernel, S, Jn, us, alg_bytes, sets, note=""):
         gbs = alg_bytes / us / 1e3
-        rows.append({"kernel": kernel, "S": S, "J": Jn, "us": round(us, 2), "alg_MB": round(alg_bytes / 1e6, 3), "GBs": round(gbs, 1),
+        rows.append({"kernel": kernel, "B": B, "S": S, "J": Jn, "us": round(us, 2), "alg_MB": round(alg_bytes / 1e6, 3), "GBs": round(gbs, 1),
                      "hbm_frac": round(gbs / hbm_gbs, 4), "sets": sets, **({"note": note} if note else {})})
-    for S in (64, 96, 128, 192, 256):
+    for S in sizes:
         H = S // 4
         nsets = max(2, min(16, int(140e6 / (B * (2 * C + 5 * 42) * H * H * 2)) + 1))
         base = [synth.make_inputs(B, S, 21, C, seed=10 + s) for s in range(2)]
@@ -103,7 +103,7 @@ def sweep(dev, hbm_gbs, B=64):
             us = _graph_us(lambda im: ops.joint2offset(jt, im, 0.8, H), [(imgs[i],) for i in range(nsets)])
             add("joint2offset_kernel (K4d)", S, Jn, us, B * (4 * Jn * H * H * 4 + H * H * 4), nsets)
     # K7 RGBDFusion at the four ResNet-18 stage shapes of a 128 crop (model/resnet.py:439-442)
-    for Cc, h in ((64, 32), (128, 16), (256, 8), (512, 4)):
+    for Cc, h in ((64, 32), (128, 16), (256, 8), (512, 4)) if k7 else ():
         n = max(2, min(32, int(140e6 / (B * Cc * h * h * 2 * 2)) + 1))
         xs = [(torch.randn(B, Cc, h, h, device=dev).bfloat16(), torch.randn(B, Cc, h, h, device=dev).bfloat16()) for _ in range(n)]
         gw, gb = torch.randn(2, 2 * Cc, device=dev), torch.randn(2, device=dev)

@@ -121,6 +121,35 @@ int kpf_spatial_aggregate(const void* feat_rgb, int dtype, const float* joints, 
 int kpf_cross_decoder_layer(const float* anchor, const float* tokens, const float* wpack, int B, int J, int C, int F, int heads,
                             float* out_cj, float* out_jc, int out_jc_stride, int out_jc_c0, cudaStream_t stream);
 
+/* ---- 8b exports off the live path: general-shape attention  model/transfusion_head.py:16-91, :94-173, :176-300, :303-556,
+ * :560-632 (detrDecoder), :711-783 (spatial_aggregate_TR).  All fp32; strides are in ELEMENTS.
+ * kpf_linear_rows: Y[(b,p)][o] = act(((X[(b,p)][:] + pos_row[:]) . W[o][:] + bias[o]) * scale)  = F.linear (:403-468) with the
+ *   with_pos_embed addition (:141-142) and the q scaling (:468) folded in.  X element (b,p,k) at X[b*x_bs + p*x_ps + k*x_ks];
+ *   pos (optional) likewise, or -- when pos_idx [B*P] i64 is given -- row pos_idx[b*P+p] of an nn.Embedding table
+ *   (pos_ps = its row stride); W [O][K] row-major; bias [O] or NULL; Y element (b,p,o) at Y[b*y_bs + p*y_ps + o*y_os]. */
+int kpf_linear_rows(const float* X, long long x_bs, long long x_ps, long long x_ks, const float* pos, long long pos_bs, long long pos_ps,
+                    long long pos_ks, const long long* pos_idx, const float* W, const float* bias, int B, int P, int K, int O, float scale,
+                    int relu, float* Y, long long y_bs, long long y_ps, long long y_os, cudaStream_t stream);
+
+/* softmax(Q K^T + attn_mask, key_padding_mask -> -inf) V per head (:519-546).  Q (already scaled) / K / V / O element (b,p,c) at
+ * base[b*bs + p*ps + c], C = H * head_dim, head_dim <= 64; attn_mask additive [Pq][Pk] f32 or NULL; key_padding_mask [B][Pk] u8
+ * (non-zero = masked) or NULL; stats [B][Pq][H][2] (row max, row sum) optional, required when weights_out [B][Pq][Pk] (the
+ * head-averaged attention weights, :551-554) is requested. */
+int kpf_mha_core(const float* Q, long long q_bs, long long q_ps, const float* K, long long k_bs, long long k_ps, const float* V,
+                 long long v_bs, long long v_ps, const float* attn_mask, const unsigned char* key_padding_mask, int B, int Pq, int Pk, int C,
+                 int H, float* O, long long o_bs, long long o_ps, float* stats, float* weights_out, cudaStream_t stream);
+
+/* y = LayerNorm(x + r) * gamma + beta over C (:150-151, :164-169): x element (b,p,c) at x[b*x_bs + p*x_ps + c*x_cs]; r [B*P][C] or
+ * NULL; y element (b,p,c) at y[b*y_bs + p*y_ps + c*y_cs] (y_cs = P, y_ps = 1 writes the reference's [B,C,P] result, :172). */
+int kpf_add_layernorm_rows(const float* x, long long x_bs, long long x_ps, long long x_cs, const float* r, const float* gamma,
+                           const float* beta, int B, int P, int C, float eps, float* y, long long y_bs, long long y_ps, long long y_cs,
+                           cudaStream_t stream);
+
+/* DetrSinePositionEmbedding.forward (:75-91): mask [B][H][W] f32 (NULL = all ones), dim_t [D] = temperature ** (2 * (i // 2) / D)
+ * -> out [B][2D][H][W] f32 (pos_y channels, then pos_x; even channels sin, odd cos). */
+int kpf_sine_posembed(const float* mask, const float* dim_t, int B, int H, int W, int D, int normalize, float scale, float* out,
+                      cudaStream_t stream);
+
 /* ---- a14  model/fusion_layer.py:56-83 RGBDFusion.forward ------------------------------------------------------------
  * rgb, depth [B,C,HW] (dtype); gate_w [2][2C] = (gate_rgb.weight, gate_depth.weight), gate_b [2];
  * outputs (dtype) [B,C,HW]; attn_sum [2] f32 (pre-zeroed) accumulates the two attention maps (train_writer path) or NULL. */

@@ -5,6 +5,8 @@
 // loads, ballot compaction, block scan); pass 2 back-projects only the `sample_num` selected points in fp64
 // (matching the reference's float64 numpy arithmetic) and writes them as fp32.  HBM-bound: S*S*4 B read,
 // sample_num*12 B written per sample.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace kpf {
@@ -49,11 +51,13 @@ __device__ __forceinline__ uint32_t feistel_perm(uint32_t i, uint32_t n, uint32_
 struct PixelBands {
     float lo, hi, z;
 };
-__device__ __forceinline__ bool bg_pred(float v) {
+// Evaluated ONCE on the host (the launchers below) and passed by value: every thread used to walk these nextafterf loops itself,
+// ~200 of the kernel's ~1500 instructions per warp.  Host and device doubles are the same IEEE arithmetic, so the floats are the same.
+static inline bool bg_pred(float v) {
     const double BG_BAND = 1e-8 + 1e-5 * 1.0;  // np.isclose(x, 1)  loader.py:844
     return fabs((double)v - 1.0) <= BG_BAND;
 }
-__device__ __forceinline__ PixelBands make_bands() {
+static inline PixelBands make_bands() {
     PixelBands b;
     b.hi = (float)(1.0 + (1e-8 + 1e-5));
     while (!bg_pred(b.hi)) b.hi = nextafterf(b.hi, 0.f);
@@ -105,8 +109,8 @@ template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3D, const float* __restrict__ cube,
                    const float* __restrict__ M, const float* __restrict__ cam, int S, int sample_num,
-                   const int32_t* __restrict__ ranks, uint32_t seed, int clamp, float flip, float* __restrict__ pcl_out,
-                   int32_t* __restrict__ pix_out, int32_t* __restrict__ count_out) {
+                   const int32_t* __restrict__ ranks, uint32_t seed, int clamp, float flip, const PixelBands bands,
+                   float* __restrict__ pcl_out, int32_t* __restrict__ pix_out, int32_t* __restrict__ count_out) {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = S * S;
@@ -117,7 +121,6 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
     __shared__ BackprojCam sc;
 
     const float hz = xdiv(cube[3 * b + 2], 2.0f), cz = com3D[3 * b + 2];
-    const PixelBands bands = make_bands();
     const float* im = img + (size_t)b * npix;
 
     if (tid == 0) {
@@ -260,7 +263,8 @@ extern "C" int kpf_getpcl(const float* img, const float* com3D, const float* cub
     const size_t smem = k1_smem_bytes(S);
     cudaError_t e = kpf::set_smem(backproject_kernel<0>, smem);
     if (e != cudaSuccess) return (int)e;
-    backproject_kernel<0><<<B, K1_THREADS, smem, stream>>>(img, com3D, cube, M, cam, S, sample_num, ranks, seed, clamp, flip,
+    static const PixelBands bands = make_bands();
+    backproject_kernel<0><<<B, K1_THREADS, smem, stream>>>(img, com3D, cube, M, cam, S, sample_num, ranks, seed, clamp, flip, bands,
                                                           pcl_out, nullptr, count_out);
     KPF_CHECK_LAUNCH();
     return 0;
@@ -275,7 +279,8 @@ extern "C" int kpf_backproject_all(const float* img, const float* com3D, const f
     const size_t smem = k1_smem_bytes(S);
     cudaError_t e = kpf::set_smem(backproject_kernel<1>, smem);
     if (e != cudaSuccess) return (int)e;
-    backproject_kernel<1><<<B, K1_THREADS, smem, stream>>>(img, com3D, cube, M, cam, S, 0, nullptr, 0u, 0, flip, xyz_out, pix_out,
+    static const PixelBands bands = make_bands();
+    backproject_kernel<1><<<B, K1_THREADS, smem, stream>>>(img, com3D, cube, M, cam, S, 0, nullptr, 0u, 0, flip, bands, xyz_out, pix_out,
                                                           count_out);
     KPF_CHECK_LAUNCH();
     return 0;

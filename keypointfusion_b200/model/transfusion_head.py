@@ -1,6 +1,11 @@
-"""Drop-in for the live part of the reference's model/transfusion_head.py: MultiheadAttention, TransformerDecoderLayer
-and updatedDecoder, with the reference's constructor arguments, init and state_dict keys.  updatedDecoder.forward runs
-the fused B200 decoder-layer kernel (K6).  Inference only."""
+"""Drop-in for the reference's model/transfusion_head.py with its constructor arguments, init and state_dict keys.
+Live part (KPFusion uses it): TransformerDecoderLayer(cross_only) + updatedDecoder -> the fused decoder-layer kernels (K6:
+csrc/cross_attn.cu, csrc/token_stack.cu).  The rest of the file's exports -- MultiheadAttention for any (L, S) with
+masks and averaged weights, TransformerDecoderLayer with self-attention / tensor position embeddings, detrDecoder,
+spatial_aggregate_TR and the three position-embedding classes -- run on the general-shape fp32 kernels of csrc/attn_general.cu.
+No torch matmul / softmax / LayerNorm anywhere.  Inference only."""
+import math
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -9,6 +14,82 @@ from torch.nn.init import constant_, xavier_normal_, xavier_uniform_
 from torch.nn.parameter import Parameter
 
 from .. import ops
+
+
+class PositionEmbeddingLearned(nn.Module):
+    """model/transfusion_head.py:16-32: Conv1d(k=1) -> BatchNorm1d -> ReLU -> Conv1d(k=1) over [B,P,in] -> [B,F,P].
+    Two launches of the rows GEMM (csrc/attn_general.cu); BatchNorm folded from its running statistics (inference)."""
+
+    def __init__(self, input_channel, num_pos_feats=288):
+        super().__init__()
+        self.position_embedding_head = nn.Sequential(
+            nn.Conv1d(input_channel, num_pos_feats, kernel_size=1),
+            nn.BatchNorm1d(num_pos_feats),
+            nn.ReLU(inplace=True),
+            nn.Conv1d(num_pos_feats, num_pos_feats, kernel_size=1))
+
+    def forward(self, xyz):
+        if self.training:
+            raise RuntimeError("PositionEmbeddingLearned: inference only (BatchNorm is folded from its running statistics)")
+        c1, bn, _, c2 = self.position_embedding_head
+        g = bn.weight / torch.sqrt(bn.running_var + bn.eps)          # fold: y = g (W x + b - mean) + beta
+        w1 = c1.weight[:, :, 0] * g[:, None]
+        b1 = (c1.bias - bn.running_mean) * g + bn.bias
+        h = ops.linear_rows(xyz, w1, b1, relu=True)                   # [B,P,F]
+        B, P, Fo = h.shape[0], h.shape[1], c2.weight.shape[0]
+        out = torch.empty(B, Fo, P, device=h.device, dtype=torch.float32)
+        ops.linear_rows(h, c2.weight[:, :, 0], c2.bias, out=out.transpose(1, 2))   # written channel-major: [B,F,P]  (:31)
+        return out
+
+
+class DetrLearnedPositionEmbedding(nn.Module):
+    """model/transfusion_head.py:34-54: row / column embedding tables broadcast over the map -> [B, 2*dim, H, W].
+    Pure indexing (two table look-ups, broadcast, concatenation): no arithmetic, so no kernel."""
+
+    def __init__(self, embedding_dim=256):
+        super().__init__()
+        self.row_embeddings = nn.Embedding(50, embedding_dim)
+        self.column_embeddings = nn.Embedding(50, embedding_dim)
+
+    def forward(self, pixel_values, pixel_mask=None):
+        height, width = pixel_values.shape[-2:]
+        x_emb = self.column_embeddings.weight[:width]      # [W,D]
+        y_emb = self.row_embeddings.weight[:height]        # [H,D]
+        pos = torch.cat([x_emb.unsqueeze(0).expand(height, -1, -1), y_emb.unsqueeze(1).expand(-1, width, -1)], dim=-1)
+        return pos.permute(2, 0, 1).unsqueeze(0).repeat(pixel_values.shape[0], 1, 1, 1)
+
+
+class DetrSinePositionEmbedding(nn.Module):
+    """model/transfusion_head.py:57-91 -> [B, 2*embedding_dim, H, W] (kpf_sine_posembed)."""
+
+    def __init__(self, embedding_dim=64, temperature=10000, normalize=False, scale=None):
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.temperature = temperature
+        self.normalize = normalize
+        if scale is not None and normalize is False:
+            raise ValueError("normalize should be True if scale is passed")
+        if scale is None:
+            scale = 2 * math.pi
+        self.scale = scale
+        self._dim_t = None
+
+    def dim_t(self, device):   # :84-85, evaluated once with the reference's own expression (no state_dict entry)
+        if self._dim_t is None or self._dim_t.device != device:
+            d = torch.arange(self.embedding_dim, dtype=torch.float32, device=device)
+            self._dim_t = self.temperature ** (2 * torch.div(d, 2, rounding_mode="floor") / self.embedding_dim)
+        return self._dim_t
+
+    def forward(self, pixel_values, pixel_mask):
+        if pixel_mask is None:
+            raise ValueError("No pixel mask provided")
+        B, H, W = pixel_mask.shape
+        return ops.sine_posembed(self.dim_t(pixel_values.device), B, H, W, mask=pixel_mask, normalize=self.normalize, scale=self.scale)
+
+    def full_mask(self, H, W, device):
+        """The embedding of an all-ones mask (what detrDecoder / spatial_aggregate_TR pass, :612, :770): [1, 2*dim, H, W], the same
+        for every sample of a batch."""
+        return ops.sine_posembed(self.dim_t(device), 1, H, W, mask=None, normalize=self.normalize, scale=self.scale)
 
 
 class MultiheadAttention(nn.Module):
@@ -40,29 +121,27 @@ class MultiheadAttention(nn.Module):
             constant_(self.out_proj.bias, 0.)
 
     def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None):
-        """General (any L, S) path of multi_head_attention_forward (transfusion_head.py:303-556) without the two
-        torch.equal host syncs (:373-374): q/k/v projections are always applied with their own weight slices, which
-        is what every branch computes.  Runs as device library calls; the fused kernel path is updatedDecoder."""
+        """multi_head_attention_forward (transfusion_head.py:303-556) for any L, S on the kernels of csrc/attn_general.cu, without the
+        two torch.equal host syncs (:373-374): the q / k / v projections always use their own slices of in_proj_weight, which is what
+        every branch of the reference computes.  The [L,N,E] / [S,N,E] inputs and the [L,N,E] output are addressed in place through
+        strides (no transposed copies).  attn_mask: additive float [L,S] (or bool, True = masked); key_padding_mask: bool [N,S]."""
+        if self.training and self.dropout > 0:
+            raise RuntimeError("MultiheadAttention: inference only (attention dropout is not implemented in the B200 kernels)")
         E, H, hd = self.embed_dim, self.num_heads, self.head_dim
         L, N, _ = query.shape
-        S = key.shape[0]
         W, b = self.in_proj_weight, self.in_proj_bias
-        q = F.linear(query, W[:E], None if b is None else b[:E]) * (float(hd) ** -0.5)
-        k = F.linear(key, W[E:2 * E], None if b is None else b[E:2 * E])
-        v = F.linear(value, W[2 * E:], None if b is None else b[2 * E:])
-        q = q.contiguous().view(L, N * H, hd).transpose(0, 1)
-        k = k.contiguous().view(S, N * H, hd).transpose(0, 1)
-        v = v.contiguous().view(S, N * H, hd).transpose(0, 1)
-        w = torch.bmm(q, k.transpose(1, 2))
-        if attn_mask is not None:
-            w = w + attn_mask.unsqueeze(0)
-        if key_padding_mask is not None:
-            w = w.view(N, H, L, S).masked_fill(key_padding_mask.unsqueeze(1).unsqueeze(2), float('-inf')).view(N * H, L, S)
-        w = F.softmax(w, dim=-1)
-        w = F.dropout(w, p=self.dropout, training=self.training)
-        o = torch.bmm(w, v).transpose(0, 1).contiguous().view(L, N, E)
-        o = F.linear(o, self.out_proj.weight, self.out_proj.bias)
-        return o, (w.view(N, H, L, S).sum(dim=1) / H if need_weights else None)
+        bq, bk, bv = (None, None, None) if b is None else (b[:E], b[E:2 * E], b[2 * E:])
+        q = ops.linear_rows(query.transpose(0, 1), W[:E], bq, scale=float(hd) ** -0.5)     # [N,L,E]   :403, :468
+        if key is value:
+            kv = ops.linear_rows(key.transpose(0, 1), W[E:], None if b is None else b[E:])  # [N,S,2E]  :418
+            k, v = kv[..., :E], kv[..., E:]
+        else:
+            k = ops.linear_rows(key.transpose(0, 1), W[E:2 * E], bk)
+            v = ops.linear_rows(value.transpose(0, 1), W[2 * E:], bv)
+        a, w = ops.mha_core(q, k, v, H, attn_mask=attn_mask, key_padding_mask=key_padding_mask, need_weights=need_weights)
+        out = torch.empty(L, N, E, device=query.device, dtype=torch.float32)
+        ops.linear_rows(a, self.out_proj.weight, self.out_proj.bias, out=out.transpose(0, 1))    # :546
+        return out, w
 
 
 class TransformerDecoderLayer(nn.Module):
@@ -106,19 +185,63 @@ class TransformerDecoderLayer(nn.Module):
             self._wpack = (key, ops.pack_decoder_layer(dict(self.state_dict()), "", J, self.d_model))
         return self._wpack[1]
 
+    def _pos_args(self, embed, pos, P):
+        """-> kwargs for ops.linear_rows: the position term of with_pos_embed (transfusion_head.py:141-155).  `embed` an nn.Embedding:
+        `pos` are indices [B,P] (None = arange, what every decoder of the reference passes) looked up inside the kernel; `embed` None:
+        `pos` is the embedding itself, [B or 1,P,C] with any strides; any other module is evaluated and must return [B,P,C]."""
+        if isinstance(embed, nn.Embedding):
+            if pos is None:
+                return dict(pos=embed.weight[:P].unsqueeze(0))
+            return dict(pos=embed.weight, pos_index=pos)
+        if embed is not None:
+            pos = embed(pos)
+        return dict(pos=pos) if pos is not None else {}
+
     def forward(self, query, key, query_pos=None, key_pos=None, attn_mask=None, out_jc=None, out_jc_c0=0, want_cj=True,
                 precision="fp32"):
-        """query [B,J,C], key [B,J,C] -> [B,C,J] (transfusion_head.py:132-173, cross_only, index position embeddings).
-        precision "fp32": CUDA-core kernel (csrc/cross_attn.cu); "tc": split-precision tcgen05 kernel (csrc/token_stack.cu, the one
-        Block_KPFusion fuses with final_TR) -- both hand-written, both fp32-class."""
+        """query [B,Pq,C], key [B,Pk,C] (any strides) -> [B,C,Pq] (transfusion_head.py:132-173).
+        The configuration updatedDecoder builds (cross_only, two nn.Embedding position tables indexed by the token number, Pq = Pk =
+        J <= 32) runs as ONE fused kernel: precision "fp32" = CUDA cores (csrc/cross_attn.cu), "tc" = split-precision tcgen05
+        (csrc/token_stack.cu, the one Block_KPFusion fuses with final_TR).  Everything else -- self-attention (cross_only=False), H*W
+        keys (detrDecoder) or H*W queries (spatial_aggregate_TR), tensor position embeddings, attn_mask -- runs on the general-shape
+        fp32 kernels of csrc/attn_general.cu.  All hand-written, all fp32-class."""
         if self.training or (torch.is_grad_enabled() and (query.requires_grad or key.requires_grad)):
             raise RuntimeError("TransformerDecoderLayer: inference only (no autograd through the B200 kernels); use .eval() and torch.no_grad()")
-        if not self.cross_only or attn_mask is not None or self.self_posembed is None or self.cross_posembed is None:
-            raise NotImplementedError("only the cross_only configuration updatedDecoder builds (transfusion_head.py:652-661)")
-        J = query.shape[1]
-        if precision in ("tc", "bf16") and self.d_model == 128 and self.nhead == 4 and J <= 32 and self.dim_feedforward in (16, 128):
-            return ops.token_stack(self.packed_tc(J), x=query, y=key, out_jc=out_jc, out_jc_c0=out_jc_c0, want_cj=want_cj)[2]
-        return ops.cross_decoder_layer(query, key, self.packed(J), self.nhead, self.dim_feedforward, out_jc, out_jc_c0, want_cj)
+        B, Pq, C = query.shape
+        Pk = key.shape[1]
+        fused = (self.cross_only and attn_mask is None and query_pos is None and key_pos is None and Pq == Pk and Pq <= 32
+                 and isinstance(self.self_posembed, nn.Embedding) and isinstance(self.cross_posembed, nn.Embedding)
+                 and self.self_posembed.num_embeddings == Pq and self.cross_posembed.num_embeddings == Pk)
+        if fused:
+            J = Pq
+            if precision in ("tc", "bf16") and self.d_model == 128 and self.nhead == 4 and self.dim_feedforward in (16, 128):
+                return ops.token_stack(self.packed_tc(J), x=query, y=key, out_jc=out_jc, out_jc_c0=out_jc_c0, want_cj=want_cj)[2]
+            if C <= 256 and self.dim_feedforward <= 256:
+                return ops.cross_decoder_layer(query, key, self.packed(J), self.nhead, self.dim_feedforward, out_jc, out_jc_c0, want_cj)
+        if out_jc is not None:
+            raise NotImplementedError("out_jc is an extension of the fused 21-token path only")
+        H, hd = self.nhead, C // self.nhead
+        qpos = self._pos_args(self.self_posembed, query_pos, Pq)
+        kpos = self._pos_args(self.cross_posembed, key_pos, Pk)
+        x = query
+        if not self.cross_only:   # :157-161  q = k = v = query + pos
+            m = self.self_attn
+            W, b = m.in_proj_weight, m.in_proj_bias
+            q = ops.linear_rows(x, W[:C], None if b is None else b[:C], scale=float(hd) ** -0.5, **qpos)
+            kv = ops.linear_rows(x, W[C:], None if b is None else b[C:], **qpos)     # [B,Pq,2C]
+            a, _ = ops.mha_core(q, kv[..., :C], kv[..., C:], H)
+            a = ops.linear_rows(a, m.out_proj.weight, m.out_proj.bias)
+            x = ops.add_layernorm_rows(x, a, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        m = self.multihead_attn   # :163-167  value = key + key_pos as well
+        W, b = m.in_proj_weight, m.in_proj_bias
+        q = ops.linear_rows(x, W[:C], None if b is None else b[:C], scale=float(hd) ** -0.5, **qpos)
+        kv = ops.linear_rows(key, W[C:], None if b is None else b[C:], **kpos)       # [B,Pk,2C]
+        a, _ = ops.mha_core(q, kv[..., :C], kv[..., C:], H, attn_mask=attn_mask)
+        a = ops.linear_rows(a, m.out_proj.weight, m.out_proj.bias)
+        x = ops.add_layernorm_rows(x, a, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        h = ops.linear_rows(x, self.linear1.weight, self.linear1.bias, relu=True)    # :169-171
+        y = ops.linear_rows(h, self.linear2.weight, self.linear2.bias)
+        return ops.add_layernorm_rows(x, y, self.norm3.weight, self.norm3.bias, self.norm3.eps, channel_major=True)   # :172 [B,C,Pq]
 
 
 class updatedDecoder(nn.Module):
@@ -158,3 +281,69 @@ class updatedDecoder(nn.Module):
         B, J, C = img_feats.shape
         assert anchor_feats.shape[1] == self.joint_num and J == self.joint_num
         return self.decoder[-1](anchor_feats, img_feats, out_jc=out_jc, out_jc_c0=out_jc_c0, want_cj=want_cj, precision=precision)
+
+
+class _SineDecoder(nn.Module):
+    """Shared constructor body of detrDecoder / spatial_aggregate_TR (transfusion_head.py:561-604, :712-755)."""
+
+    def _build(self, joint_num, hidden_channel, num_heads, ffn_channel, dropout, num_decoder_layers, activation, bn_momentum, self_pos,
+               cross_pos, sine_name):
+        self.decoder = nn.ModuleList()
+        self.bn_momentum = bn_momentum
+        self.num_decoder_layers = num_decoder_layers
+        for i in range(self.num_decoder_layers):
+            self.decoder.append(TransformerDecoderLayer(
+                hidden_channel, num_heads, ffn_channel, dropout, activation,
+                self_posembed=nn.Embedding(joint_num, hidden_channel) if self_pos else None,
+                cross_posembed=nn.Embedding(joint_num, hidden_channel) if cross_pos else None, cross_only=True))
+        self.joint_num = joint_num
+        setattr(self, sine_name, DetrSinePositionEmbedding(hidden_channel // 2, normalize=True))
+        self.init_weights()
+
+    def init_weights(self):
+        for m in self.decoder.parameters():
+            if m.dim() > 1:
+                nn.init.xavier_uniform_(m)
+        for m in self.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m.momentum = self.bn_momentum
+
+
+class detrDecoder(_SineDecoder):
+    """model/transfusion_head.py:560-632: the J joint tokens attend over the H*W cells of an image feature map (keys = values =
+    cells + sine position embedding; queries = tokens + a learned per-joint embedding)."""
+
+    def __init__(self, joint_num=21, hidden_channel=128, num_heads=4, ffn_channel=128, dropout=0.1, num_decoder_layers=3,
+                 activation='relu', bn_momentum=0.1, img_feature_seq_length=1024):
+        super(detrDecoder, self).__init__()
+        self._build(joint_num, hidden_channel, num_heads, ffn_channel, dropout, num_decoder_layers, activation, bn_momentum,
+                    self_pos=True, cross_pos=False, sine_name="key_position_embedding")
+
+    def forward(self, anchor_feats, img_feats):
+        """anchor_feats [B,J,C], img_feats [B,C,W,H] -> [B,C,J].  Every layer of the reference gets the same inputs and only the last
+        output is returned (:627-631): layers 0..n-2 are dead compute and are skipped.  The feature map and its position embedding
+        are read in place as [B,H*W,C] rows through strides (the reference's flatten + permute, :614-615, without the copies)."""
+        B, C, W, H = img_feats.shape
+        assert anchor_feats.shape[1] == self.joint_num
+        key_pos = self.key_position_embedding.full_mask(W, H, img_feats.device).flatten(2).permute(0, 2, 1)   # [1,WH,C]
+        keys = img_feats.flatten(2).permute(0, 2, 1)                                                           # [B,WH,C] view
+        return self.decoder[-1](anchor_feats, keys, None, key_pos)
+
+
+class spatial_aggregate_TR(_SineDecoder):
+    """model/transfusion_head.py:711-783: the H*W cells of an image feature map (queries, + sine position embedding) attend over the
+    J joint tokens (keys = values = tokens + a learned per-joint embedding)."""
+
+    def __init__(self, joint_num=21, hidden_channel=128, num_heads=4, ffn_channel=128, dropout=0.1, num_decoder_layers=3,
+                 activation='relu', bn_momentum=0.1, img_feature_seq_length=1024):
+        super(spatial_aggregate_TR, self).__init__()
+        self._build(joint_num, hidden_channel, num_heads, ffn_channel, dropout, num_decoder_layers, activation, bn_momentum,
+                    self_pos=False, cross_pos=True, sine_name="query_position_embedding")
+
+    def forward(self, img_feats, anchor_feats):
+        """img_feats [B,C,W,H], anchor_feats [B,J,C] -> [B,C,W*H]  (:758-783; last layer only, like the reference's return value)."""
+        B, C, W, H = img_feats.shape
+        assert anchor_feats.shape[1] == self.joint_num
+        query_pos = self.query_position_embedding.full_mask(W, H, img_feats.device).flatten(2).permute(0, 2, 1)
+        queries = img_feats.flatten(2).permute(0, 2, 1)
+        return self.decoder[-1](queries, anchor_feats, query_pos, None)

@@ -297,6 +297,109 @@ def cross_decoder_layer(anchor, tokens, wpack, heads, ffn, out_jc=None, out_jc_c
     return out_cj
 
 
+# ------------------------------------------------------------------------------------------------ 8b: general-shape attention
+def _rows3(t, name):
+    """fp32 CUDA tensor [B,P,K] with ARBITRARY strides (views such as `x.transpose(0, 1)` or `feat.flatten(2).permute(0, 2, 1)` are
+    addressed in place; nothing is copied)."""
+    _need_cuda(t)
+    if t.dim() != 3:
+        raise ValueError(f"{name}: expected a [B,P,K] tensor, got {tuple(t.shape)}")
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def linear_rows(x, weight, bias=None, pos=None, pos_index=None, scale=1.0, relu=False, out=None):
+    """out[b,p,:] = act(((x[b,p,:] + pos_row) @ weight.T + bias) * scale)   (csrc/attn_general.cu).
+    x [B,P,K] any strides; weight [O,K]; pos None | [B or 1,P,K] any strides | an nn.Embedding table [n,K] with pos_index [B,P] i64;
+    out None (-> new contiguous [B,P,O]) or a preallocated [B,P,O] VIEW with any strides (e.g. a [P,B,O] tensor transposed)."""
+    x = _rows3(x, "linear_rows")
+    B, P, K = x.shape
+    weight = _f32(weight)
+    O = weight.shape[0]
+    if weight.shape != (O, K):
+        raise ValueError(f"linear_rows: weight {tuple(weight.shape)} does not match K = {K}")
+    bias = None if bias is None else _f32(bias)
+    pb = pp = pk = 0
+    idx = None
+    if pos_index is not None:
+        pos = _f32(pos)
+        _need_cuda(pos_index)
+        idx = pos_index.to(torch.int64).expand(B, P).contiguous()
+        pp, pk = pos.stride(0), pos.stride(1)
+    elif pos is not None:
+        pos = _rows3(pos, "linear_rows (pos)")
+        if pos.shape[1:] != (P, K) or pos.shape[0] not in (1, B):
+            raise ValueError(f"linear_rows: pos {tuple(pos.shape)} does not match x {tuple(x.shape)}")
+        pb, pp, pk = (0 if pos.shape[0] == 1 else pos.stride(0)), pos.stride(1), pos.stride(2)
+    if out is None:
+        out = torch.empty(B, P, O, device=x.device, dtype=torch.float32)
+    elif out.shape != (B, P, O) or out.dtype != torch.float32:
+        raise ValueError(f"linear_rows: out {tuple(out.shape)} / {out.dtype}, expected {(B, P, O)} float32")
+    _call("kpf_linear_rows", _p(x), x.stride(0), x.stride(1), x.stride(2), _p(pos), pb, pp, pk, _p(idx), _p(weight), _p(bias), B, P, K, O,
+          float(scale), int(bool(relu)), _p(out), out.stride(0), out.stride(1), out.stride(2))
+    return out
+
+
+def mha_core(q, k, v, num_heads, attn_mask=None, key_padding_mask=None, need_weights=False):
+    """softmax(q k^T + masks) v per head.  q [B,Pq,C] (already scaled), k / v [B,Pk,C]: unit stride over C, any batch / row strides
+    (e.g. the two halves of a fused [B,Pk,2C] projection).  -> (out [B,Pq,C], head-averaged weights [B,Pq,Pk] or None)."""
+    q, k, v = _rows3(q, "mha_core"), _rows3(k, "mha_core"), _rows3(v, "mha_core")
+    q, k, v = (t if t.stride(2) == 1 else t.contiguous() for t in (q, k, v))
+    B, Pq, C = q.shape
+    Pk = k.shape[1]
+    if k.shape != (B, Pk, C) or v.shape != (B, Pk, C) or C % num_heads or C // num_heads > 64:
+        raise ValueError(f"mha_core: q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)}, {num_heads} heads (head_dim <= 64)")
+    if attn_mask is not None:
+        _need_cuda(attn_mask)
+        if attn_mask.dtype == torch.bool:   # newer torch semantics: True = not allowed
+            attn_mask = torch.zeros(attn_mask.shape, device=q.device).masked_fill_(attn_mask, float("-inf"))
+        attn_mask = _f32(attn_mask)
+        if attn_mask.shape != (Pq, Pk):
+            raise ValueError(f"mha_core: attn_mask {tuple(attn_mask.shape)}, expected {(Pq, Pk)}")
+    if key_padding_mask is not None:
+        _need_cuda(key_padding_mask)
+        if key_padding_mask.shape != (B, Pk):
+            raise ValueError(f"mha_core: key_padding_mask {tuple(key_padding_mask.shape)}, expected {(B, Pk)}")
+        key_padding_mask = key_padding_mask.to(torch.uint8).contiguous()
+    out = torch.empty(B, Pq, C, device=q.device, dtype=torch.float32)
+    stats = torch.empty(B, Pq, num_heads, 2, device=q.device, dtype=torch.float32) if need_weights else None
+    w = torch.empty(B, Pq, Pk, device=q.device, dtype=torch.float32) if need_weights else None
+    _call("kpf_mha_core", _p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0), v.stride(1), _p(attn_mask),
+          _p(key_padding_mask), B, Pq, Pk, C, num_heads, _p(out), out.stride(0), out.stride(1), _p(stats), _p(w))
+    return out, w
+
+
+def add_layernorm_rows(x, r, gamma, beta, eps=1e-5, channel_major=False):
+    """LayerNorm(x + r) over the last dimension.  x [B,P,C] (any strides), r [B,P,C] or None -> [B,P,C], or the reference's
+    channel-major [B,C,P] (transfusion_head.py:172) when channel_major."""
+    x = _rows3(x, "add_layernorm_rows")
+    B, P, C = x.shape
+    r = None if r is None else _f32(r)
+    if r is not None and r.shape != (B, P, C):
+        raise ValueError(f"add_layernorm_rows: r {tuple(r.shape)} != x {tuple(x.shape)}")
+    gamma, beta = _f32(gamma), _f32(beta)
+    if channel_major:
+        y = torch.empty(B, C, P, device=x.device, dtype=torch.float32)
+        ys = (C * P, 1, P)
+    else:
+        y = torch.empty(B, P, C, device=x.device, dtype=torch.float32)
+        ys = (P * C, C, 1)
+    _call("kpf_add_layernorm_rows", _p(x), x.stride(0), x.stride(1), x.stride(2), _p(r), _p(gamma), _p(beta), B, P, C, float(eps), _p(y), *ys)
+    return y
+
+
+def sine_posembed(dim_t, B, H, W, mask=None, normalize=False, scale=6.283185307179586):
+    """DetrSinePositionEmbedding.forward (transfusion_head.py:75-91): -> [B, 2*len(dim_t), H, W] f32."""
+    dim_t = _f32(dim_t)
+    D = dim_t.numel()
+    if mask is not None:
+        mask = _f32(mask)
+        if mask.shape != (B, H, W):
+            raise ValueError(f"sine_posembed: mask {tuple(mask.shape)}, expected {(B, H, W)}")
+    out = torch.empty(B, 2 * D, H, W, device=dim_t.device, dtype=torch.float32)
+    _call("kpf_sine_posembed", _p(mask), _p(dim_t), B, H, W, D, int(bool(normalize)), float(scale), _p(out))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ a14, a15
 def channel_mean(x):
     x = _feat(x)

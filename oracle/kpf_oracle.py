@@ -467,6 +467,98 @@ def updated_decoder(p, prefix, anchor_feats, img_feats, num_layers=4, num_heads=
 
 
 # ----------------------------------------------------------------------------------------------
+# 8b exports off the live path: general-shape attention (model/transfusion_head.py:16-91, :94-173, :303-556, :560-632, :711-783)
+# pinned against tests/golden/golden_heads.npz (made by tests/golden/make_golden_heads.py from the unmodified reference)
+# ----------------------------------------------------------------------------------------------
+def mha_forward(p, prefix, query, key, value, num_heads, key_padding_mask=None, attn_mask=None):
+    """multi_head_attention_forward, general branch (transfusion_head.py:303-556): query [L,N,E], key / value [S,N,E] ->
+    (out [L,N,E], head-averaged weights [N,L,S])."""
+    L, N, E = query.shape
+    S = key.shape[0]
+    hd = E // num_heads
+    W, b = p[prefix + "in_proj_weight"], p[prefix + "in_proj_bias"]
+    q = F.linear(query, W[:E], b[:E]) * (float(hd) ** -0.5)                    # :403, :468
+    k = F.linear(key, W[E:2 * E], b[E:2 * E])
+    v = F.linear(value, W[2 * E:], b[2 * E:])
+    q = q.contiguous().view(L, N * num_heads, hd).transpose(0, 1)              # :497-501
+    k = k.contiguous().view(S, N * num_heads, hd).transpose(0, 1)
+    v = v.contiguous().view(S, N * num_heads, hd).transpose(0, 1)
+    w = torch.bmm(q, k.transpose(1, 2))                                        # :524
+    if attn_mask is not None:
+        w = w + attn_mask.unsqueeze(0)                                         # :527-529
+    if key_padding_mask is not None:                                           # :531-537
+        w = w.view(N, num_heads, L, S).masked_fill(key_padding_mask.unsqueeze(1).unsqueeze(2), float("-inf")).view(N * num_heads, L, S)
+    w = torch.softmax(w, dim=-1)
+    o = torch.bmm(w, v).transpose(0, 1).contiguous().view(L, N, E)             # :543-545
+    o = F.linear(o, p[prefix + "out_proj.weight"], p[prefix + "out_proj.bias"])
+    return o, w.view(N, num_heads, L, S).sum(dim=1) / num_heads               # :551-554
+
+
+def decoder_layer(p, prefix, query, key, query_pos, key_pos, num_heads=4, cross_only=True, attn_mask=None):
+    """TransformerDecoderLayer.forward (transfusion_head.py:132-173) with the position embeddings given as tensors
+    (query_pos [B or 1,Pq,C], key_pos [B or 1,Pk,C]; None = no embedding) -> [B,C,Pq]."""
+    C = query.shape[-1]
+    qp = 0 if query_pos is None else query_pos
+    kp = 0 if key_pos is None else key_pos
+    x = query.permute(1, 0, 2)                                                 # :154-155  [P,B,C]
+    if not cross_only:                                                         # :157-161
+        qq = (query + qp).permute(1, 0, 2)
+        x = F.layer_norm(x + mha_forward(p, prefix + "self_attn.", qq, qq, qq, num_heads)[0], (C,), p[prefix + "norm1.weight"],
+                         p[prefix + "norm1.bias"], 1e-5)
+    kk = (key + kp).permute(1, 0, 2)
+    qq = x + (qp.permute(1, 0, 2) if torch.is_tensor(qp) else 0)
+    a = mha_forward(p, prefix + "multihead_attn.", qq, kk, kk, num_heads, attn_mask=attn_mask)[0]   # :163-165
+    x = F.layer_norm(x + a, (C,), p[prefix + "norm2.weight"], p[prefix + "norm2.bias"], 1e-5)
+    y = F.linear(torch.relu(F.linear(x, p[prefix + "linear1.weight"], p[prefix + "linear1.bias"])),
+                 p[prefix + "linear2.weight"], p[prefix + "linear2.bias"])                          # :167-169
+    x = F.layer_norm(x + y, (C,), p[prefix + "norm3.weight"], p[prefix + "norm3.bias"], 1e-5)
+    return x.permute(1, 2, 0)                                                  # :172
+
+
+def sine_position_embedding(mask, embedding_dim, temperature=10000, normalize=False, scale=2 * math.pi):
+    """DetrSinePositionEmbedding.forward (transfusion_head.py:75-91): mask [B,H,W] -> [B, 2*embedding_dim, H, W]."""
+    y_embed = mask.cumsum(1, dtype=torch.float32)
+    x_embed = mask.cumsum(2, dtype=torch.float32)
+    if normalize:
+        y_embed = y_embed / (y_embed[:, -1:, :] + 1e-6) * scale
+        x_embed = x_embed / (x_embed[:, :, -1:] + 1e-6) * scale
+    dim_t = torch.arange(embedding_dim, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / embedding_dim)
+    pos_x = x_embed[:, :, :, None] / dim_t
+    pos_y = y_embed[:, :, :, None] / dim_t
+    pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+def detr_decoder(p, prefix, anchor_feats, img_feats, num_layers, num_heads=4):
+    """detrDecoder.forward (transfusion_head.py:605-632): joint tokens attend over the map's cells; last layer only."""
+    B, C, W, H = img_feats.shape
+    J = anchor_feats.shape[1]
+    key_pos = sine_position_embedding(torch.ones(B, W, H), C // 2, normalize=True).flatten(2).permute(0, 2, 1)
+    lp = f"{prefix}decoder.{num_layers - 1}."
+    return decoder_layer(p, lp, anchor_feats, img_feats.flatten(2).permute(0, 2, 1), p[lp + "self_posembed.weight"][:J].unsqueeze(0),
+                         key_pos, num_heads)
+
+
+def spatial_aggregate_tr(p, prefix, img_feats, anchor_feats, num_layers, num_heads=4):
+    """spatial_aggregate_TR.forward (transfusion_head.py:758-783): the map's cells attend over the joint tokens; last layer only."""
+    B, C, W, H = img_feats.shape
+    J = anchor_feats.shape[1]
+    query_pos = sine_position_embedding(torch.ones(B, W, H), C // 2, normalize=True).flatten(2).permute(0, 2, 1)
+    lp = f"{prefix}decoder.{num_layers - 1}."
+    return decoder_layer(p, lp, img_feats.flatten(2).permute(0, 2, 1), anchor_feats, query_pos,
+                         p[lp + "cross_posembed.weight"][:J].unsqueeze(0), num_heads)
+
+
+def position_embedding_learned(p, prefix, xyz, eps=1e-5):
+    """PositionEmbeddingLearned.forward (transfusion_head.py:29-32), eval-mode BatchNorm: [B,P,in] -> [B,F,P]."""
+    h = F.linear(xyz, p[prefix + "0.weight"][:, :, 0], p[prefix + "0.bias"])
+    h = (h - p[prefix + "1.running_mean"]) / torch.sqrt(p[prefix + "1.running_var"] + eps) * p[prefix + "1.weight"] + p[prefix + "1.bias"]
+    return F.linear(torch.relu(h), p[prefix + "3.weight"][:, :, 0], p[prefix + "3.bias"]).permute(0, 2, 1)
+
+
+# ----------------------------------------------------------------------------------------------
 # "next" rows needed to close the block: a9 embeddings, DESA, BERT token encoders
 # ----------------------------------------------------------------------------------------------
 def conv_bn(p, prefix, x):
