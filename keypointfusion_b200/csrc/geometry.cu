@@ -336,70 +336,103 @@ offset2joint_kernel(const T* __restrict__ offset, const float* __restrict__ dept
     }
 }
 
-// bf16 fast path of K4a for maps with HW == 8 * blockDim.x cells and fs % 8 == 0: a thread owns 8 consecutive cells of a row,
-// reads each of the joint's five channels with ONE 16-byte load, keeps everything in registers between the max pass and the
-// sum pass, and the four sums share one reduction round.  Same arithmetic per cell as the generic kernel above.
-__global__ void __launch_bounds__(128)
+// bf16 fast path of K4a for maps with HW == 8 * blockDim.x cells and fs % 8 == 0.  A CTA takes K4A_JPC joints of one sample; a thread
+// owns 8 consecutive cells of a row and reads each channel row of a joint with ONE 16-byte load.  The kernel is a stream over
+// 10 KB per joint, so what matters is how many loads are in flight and how few block-wide round trips interrupt them:
+//   phase A  the depth of the 8 cells (once per CTA, not per joint) and the weight rows of ALL the CTA's joints -> masked weights in
+//            registers, the joints' maxima with one reduction round;
+//   phase B  per joint the four remaining rows, the NEXT joint's loads issued before the current joint's arithmetic;
+//   phase C  one reduction round for all 4 * K4A_JPC sums.
+// Two barriers per CTA instead of two per joint.  Same arithmetic per cell as the generic kernel above.
+template <int K4A_JPC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 offset2joint_bf16x8_kernel(const __nv_bfloat16* __restrict__ offset, const float* __restrict__ depth, int S, int J, int fs,
                            const float* __restrict__ kernel_vec, float* __restrict__ joint_out) {
-    __shared__ float scratch[32];
-    __shared__ float4 part[4];
-    const int j = blockIdx.x, b = blockIdx.y, HW = fs * fs, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    __shared__ float smx[4][K4A_JPC];
+    __shared__ float part[4][4 * K4A_JPC];
+    __shared__ float coord[128];   // cell_coord(i), i < fs <= 128 (HW = 1024, fs % 8 == 0): fs IEEE divisions per CTA instead of 9 per thread
+    const int j0 = blockIdx.x * K4A_JPC, b = blockIdx.y, HW = fs * fs, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const __nv_bfloat16* base = offset + (size_t)b * 5 * J * HW;
     const int m0 = 8 * tid, r = m0 / fs, col0 = m0 - r * fs;
-    const uint4 vx = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(3 * j) * HW + m0));
-    const uint4 vy = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(3 * j + 1) * HW + m0));
-    const uint4 vz = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(3 * j + 2) * HW + m0));
-    const uint4 vh = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(3 * J + j) * HW + m0));
-    const uint4 vw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(4 * J + j) * HW + m0));
-    const float* drow = depth + (size_t)b * S * S + (size_t)nearest_src(r, S, fs) * S;
-    float d[8], wv[8];
-    const __nv_bfloat16* pw = reinterpret_cast<const __nv_bfloat16*>(&vw);
-    float mx = -INFINITY;
+    if (tid < fs) coord[tid] = cell_coord(tid, (float)fs);   // read after the barrier of phase A
+    auto row16 = [&](int ch) { return __ldg(reinterpret_cast<const uint4*>(base + (size_t)ch * HW + m0)); };
+    // ---- phase A
+    uint4 vw[K4A_JPC];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        d[i] = __ldg(drow + nearest_src(col0 + i, S, fs));
-        wv[i] = d[i] > 0.99f ? -1e8f : __bfloat162float(pw[i]);  // masked_fill(depth.gt(0.99), -1e8)  :488
-        mx = fmaxf(mx, wv[i]);
-    }
-    mx = block_max(mx, scratch);
-    const float ks = kernel_vec[j], ffs = (float)fs;
-    const __nv_bfloat16 *px = reinterpret_cast<const __nv_bfloat16*>(&vx), *py = reinterpret_cast<const __nv_bfloat16*>(&vy),
-                        *pz = reinterpret_cast<const __nv_bfloat16*>(&vz), *ph = reinterpret_cast<const __nv_bfloat16*>(&vh);
-    float se = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    const float cr = cell_coord(r, ffs);
+    for (int jj = 0; jj < K4A_JPC; ++jj) vw[jj] = j0 + jj < J ? row16(4 * J + j0 + jj) : make_uint4(0, 0, 0, 0);
+    uint4 nx[4];   // the first joint's other four rows are already on their way
+    nx[0] = row16(3 * j0); nx[1] = row16(3 * j0 + 1); nx[2] = row16(3 * j0 + 2); nx[3] = row16(3 * J + j0);
+    // nearest down-sample (model.py:409): floor(dst * (S / fs)) is dst * (S / fs) in integers when fs divides S (the float product is exact)
+    const int step = S % fs == 0 ? S / fs : 0;
+    const float* drow = depth + (size_t)b * S * S + (size_t)(step ? r * step : nearest_src(r, S, fs)) * S;
+    float d[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float e = expf(wv[i] - mx);
-        const float msk = d[i] < 0.99f ? 1.f : 0.f;                                   // depth.lt(0.99)  :485
-        const float dist = ks - (__bfloat162float(ph[i]) * msk) * ks;                 // :495
-        const float ox = __bfloat162float(px[i]) * msk, oy = __bfloat162float(py[i]) * msk, oz = __bfloat162float(pz[i]) * msk;
-        se += e;
-        ax += (ox * dist + cell_coord(col0 + i, ffs)) * e;                            // coords ch0 = column  :481
-        ay += (oy * dist + cr) * e;
-        az += (oz * dist + d[i]) * e;
-    }
+    for (int i = 0; i < 8; ++i) d[i] = __ldg(drow + (step ? (col0 + i) * step : nearest_src(col0 + i, S, fs)));
+    float wv[K4A_JPC][8], mx[K4A_JPC];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        se += __shfl_xor_sync(0xffffffffu, se, o);
-        ax += __shfl_xor_sync(0xffffffffu, ax, o);
-        ay += __shfl_xor_sync(0xffffffffu, ay, o);
-        az += __shfl_xor_sync(0xffffffffu, az, o);
-    }
-    if (lane == 0) part[w] = make_float4(se, ax, ay, az);
-    __syncthreads();
-    if (tid == 0) {
-        float4 t = part[0];
-        for (int k = 1; k < 4; ++k) {
-            t.x += part[k].x;
-            t.y += part[k].y;
-            t.z += part[k].z;
-            t.w += part[k].w;
+    for (int jj = 0; jj < K4A_JPC; ++jj) {
+        const __nv_bfloat16* pw = reinterpret_cast<const __nv_bfloat16*>(&vw[jj]);
+        mx[jj] = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            wv[jj][i] = d[i] > 0.99f ? -1e8f : __bfloat162float(pw[i]);  // masked_fill(depth.gt(0.99), -1e8)  :488
+            mx[jj] = fmaxf(mx[jj], wv[jj][i]);
         }
-        float* o = joint_out + ((size_t)b * J + j) * 3;
-        o[0] = t.y / t.x;
-        o[1] = t.z / t.x;
-        o[2] = t.w / t.x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx[jj] = fmaxf(mx[jj], __shfl_xor_sync(0xffffffffu, mx[jj], o));
+        if (lane == 0) smx[w][jj] = mx[jj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int jj = 0; jj < K4A_JPC; ++jj) mx[jj] = fmaxf(fmaxf(smx[0][jj], smx[1][jj]), fmaxf(smx[2][jj], smx[3][jj]));
+    // ---- phase B
+    const float cr = coord[r];
+    float cc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cc[i] = coord[col0 + i];
+    float acc[K4A_JPC][4];
+#pragma unroll
+    for (int jj = 0; jj < K4A_JPC; ++jj) {
+        const uint4 vx = nx[0], vy = nx[1], vz = nx[2], vh = nx[3];
+        if (jj + 1 < K4A_JPC && j0 + jj + 1 < J) {
+            const int j = j0 + jj + 1;
+            nx[0] = row16(3 * j); nx[1] = row16(3 * j + 1); nx[2] = row16(3 * j + 2); nx[3] = row16(3 * J + j);
+        }
+        const float ks = j0 + jj < J ? __ldg(kernel_vec + j0 + jj) : 0.f;
+        const __nv_bfloat16 *px = reinterpret_cast<const __nv_bfloat16*>(&vx), *py = reinterpret_cast<const __nv_bfloat16*>(&vy),
+                            *pz = reinterpret_cast<const __nv_bfloat16*>(&vz), *ph = reinterpret_cast<const __nv_bfloat16*>(&vh);
+        float se = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float e = expf(wv[jj][i] - mx[jj]);
+            // depth.lt(0.99) mask (:485): a masked cell's offsets are zero, i.e. it contributes its own coordinates -- same value as the
+            // generic kernel's (o * 0) * dist + c, with one select instead of four multiplications
+            const float dist = d[i] < 0.99f ? ks - __bfloat162float(ph[i]) * ks : 0.f;    // :495
+            se += e;
+            ax += (__bfloat162float(px[i]) * dist + cc[i]) * e;                           // coords ch0 = column  :481
+            ay += (__bfloat162float(py[i]) * dist + cr) * e;
+            az += (__bfloat162float(pz[i]) * dist + d[i]) * e;
+        }
+        acc[jj][0] = se; acc[jj][1] = ax; acc[jj][2] = ay; acc[jj][3] = az;
+    }
+    // ---- phase C
+#pragma unroll
+    for (int jj = 0; jj < K4A_JPC; ++jj)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = acc[jj][k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) part[w][4 * jj + k] = v;
+        }
+    __syncthreads();
+    if (tid < 3 * K4A_JPC) {
+        const int jj = tid / 3, k = tid - 3 * jj;
+        if (j0 + jj < J) {
+            const float se = ((part[0][4 * jj] + part[1][4 * jj]) + part[2][4 * jj]) + part[3][4 * jj];
+            const float a = ((part[0][4 * jj + 1 + k] + part[1][4 * jj + 1 + k]) + part[2][4 * jj + 1 + k]) + part[3][4 * jj + 1 + k];
+            joint_out[((size_t)b * J + j0 + jj) * 3 + k] = a / se;
+        }
     }
 }
 
@@ -594,8 +627,19 @@ extern "C" int kpf_offset2joint_weight(const void* offset, int dtype, const floa
         kpf::set_smem(offset2joint_kernel<float>, 0);
         offset2joint_kernel<float><<<grid, 256, 0, stream>>>((const float*)offset, depth, S, J, fs, kernel_vec, joint_out);
     } else if (dtype == KPF_BF16 && fs * fs == 8 * 128 && fs % 8 == 0 && ((uintptr_t)offset % 16) == 0) {
-        kpf::set_smem(offset2joint_bf16x8_kernel, 0);
-        offset2joint_bf16x8_kernel<<<grid, 128, 0, stream>>>((const __nv_bfloat16*)offset, depth, S, J, fs, kernel_vec, joint_out);
+        // joints per CTA: 7 amortise the per-CTA setup best once the grid fills the GPU several times over (batch 512: 37 us vs 41 us,
+        // 3.0 TB/s); 3 keep enough CTAs at small batches (batch 64: 8.7 us vs 10.1 us) -- profiles/probe_k4a.py
+        static const int variant = [] { const char* e = getenv("KPF_K4A_VARIANT"); return e ? atoi(e) : 0; }();   // tuning aid: 1 / 2 force
+#define KPF_K4A(JPC, MINB)                                                                                                   \
+    do {                                                                                                                     \
+        kpf::set_smem(offset2joint_bf16x8_kernel<JPC, MINB>, 0);                                                             \
+        grid.x = (J + JPC - 1) / JPC;                                                                                        \
+        offset2joint_bf16x8_kernel<JPC, MINB><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)offset, depth, S, J, fs, kernel_vec, joint_out); \
+    } while (0)
+        const bool big = variant == 2 || (variant == 0 && (long long)B * ((J + 6) / 7) >= 4 * 148);
+        if (big) KPF_K4A(7, 4);
+        else KPF_K4A(3, 5);
+#undef KPF_K4A
     } else if (dtype == KPF_BF16) {
         kpf::set_smem(offset2joint_kernel<__nv_bfloat16>, 0);
         offset2joint_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)offset, depth, S, J, fs, kernel_vec, joint_out);
