@@ -83,8 +83,9 @@ int kpf_pcl_joint2offset(const float* joint, const float* pcl, const float* kern
  * feat: [B,C,HW] (dtype) with batch stride feat_batch_stride elements (lets a channel slice of a wider map be
  * passed); index [B,N,K] i64 (index_is_i64 != 0) or i32; closeness [B,N,K] f32.
  * out (dtype): element (b,n,c) at out[(b*N+n)*out_stride + out_c0 + c]  (out_stride >= out_c0 + C).
- * workspace: caller buffer of B*HW*ceil8(C) elements of dtype, 16-byte aligned (the map as channels-last rows; contents undefined).
- * Two launches: TMA-staged transposition to rows, then the row gather. */
+ * One launch when HW * 16 bytes <= 96 KB (the [channels x HW] slab of a channel block is transposed into shared memory and the taps
+ * are read there; workspace may be NULL); larger maps take two launches through `workspace`, a caller buffer of B*HW*ceil8(C) elements
+ * of dtype, 16-byte aligned (the map as channels-last rows; contents undefined). */
 int kpf_gather_taps(const void* feat, int dtype, long long feat_batch_stride, int B, int C, int HW, const void* index,
                     int index_is_i64, const float* closeness, int N, int K, void* out, int out_stride, int out_c0, void* workspace,
                     cudaStream_t stream);

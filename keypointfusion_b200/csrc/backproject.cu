@@ -1,8 +1,8 @@
 // K1: depth crop -> normalised point cloud.
 //   reference: dataloader/loader.py:843-853 (getpcl), :874-893 (depthToPCL), :1173-1186 (resample);
 //   API shell util/img2pcl.py:11-40 (Pcl_utils.getpcl).  Oracle: oracle/kpf_oracle.py getpcl/getpcl_sample.
-// One CTA per sample.  Pass 1 builds the row-major ordered list of valid pixels in shared memory (coalesced
-// loads, ballot compaction, block scan); pass 2 back-projects only the `sample_num` selected points in fp64
+// One CTA per sample.  Pass 1 builds the row-major ordered list of valid pixels in shared memory (a run of
+// consecutive pixels per thread, 16-byte loads, one block scan of the threads' counts); pass 2 back-projects only the `sample_num` selected points in fp64
 // (matching the reference's float64 numpy arithmetic) and writes them as fp32.  HBM-bound: S*S*4 B read,
 // sample_num*12 B written per sample.
 #include <cmath>
@@ -114,10 +114,8 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
     extern __shared__ __align__(16) unsigned char k1_smem[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = S * S;
-    const int rounds = (npix + K1_THREADS - 1) / K1_THREADS;  // <= 64 (S <= 256)
     uint16_t* list = reinterpret_cast<uint16_t*>(k1_smem);                               // [npix]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(k1_smem + (((size_t)npix * 2 + 15) & ~(size_t)15));  // [rounds*32 + 1]
-    __shared__ uint32_t warp_tot[K1_WARPS];
+    __shared__ uint32_t warp_tot[K1_WARPS], total;
     __shared__ BackprojCam sc;
 
     const float hz = xdiv(cube[3 * b + 2], 2.0f), cz = com3D[3 * b + 2];
@@ -136,38 +134,42 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
         sc.flip = (double)flip;
     }
 
-    // ---- pass 1a: validity bits (kept in registers) + per-(round,warp) counts
+    // ---- pass 1: a thread owns a run of `ppt` consecutive pixels (<= 64: S <= 256), so row-major order = thread order and the ordered
+    //      compaction needs ONE exclusive scan over the threads' counts (the round-robin assignment it replaces took a ballot + popc
+    //      per pixel round twice over: ~650 of the kernel's ~1500 instructions per warp, profiles/stalls_r2_final.txt)
+    const int ppt = (npix + K1_THREADS - 1) / K1_THREADS;
+    const int p0 = tid * ppt;
     uint64_t vbits = 0;
-    for (int r0 = 0; r0 < rounds; r0 += 16) {   // 16 independent loads in flight, then the (serial) ballots
-        float vv[16];
+    const bool vec = (ppt & 3) == 0 && (npix & 3) == 0 && (((uintptr_t)im) & 15) == 0;
+    if (vec) {
+        for (int i0 = 0; i0 < ppt; i0 += 16) {   // up to four 16-byte loads in flight
+            float4 vv[4];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int p = (r0 + u) * K1_THREADS + tid;
-            vv[u] = (r0 + u < rounds && p < npix) ? __ldg(im + p) : 1.0f;   // 1.0 = background = not a point
-        }
+            for (int u = 0; u < 4; ++u) {
+                const int p = p0 + i0 + 4 * u;
+                vv[u] = (i0 + 4 * u < ppt && p < npix) ? __ldg(reinterpret_cast<const float4*>(im + p)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int r = r0 + u;
-            if (r < rounds) {   // warp-uniform
-                float dpt;
-                const bool ok = r * K1_THREADS + tid < npix && pixel_valid(vv[u], hz, cz, bands, dpt);
-                vbits |= (uint64_t)ok << r;
-                const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-                if (lane == 0) cnt[r * K1_WARPS + warp] = __popc(bal);
+            for (int u = 0; u < 4; ++u) {
+                const float f[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float dpt;
+                    const int i = i0 + 4 * u + e;
+                    const bool ok = i < ppt && p0 + i < npix && pixel_valid(f[e], hz, cz, bands, dpt);   // padding = 1.0 = background
+                    vbits |= (uint64_t)ok << i;
+                }
             }
         }
+    } else {
+        for (int i = 0; i < ppt; ++i) {
+            float dpt;
+            const bool ok = p0 + i < npix && pixel_valid(__ldg(im + p0 + i), hz, cz, bands, dpt);
+            vbits |= (uint64_t)ok << i;
+        }
     }
-    __syncthreads();
-    // ---- pass 1b: exclusive scan of cnt[rounds*32] in (round, warp) order == row-major pixel order
-    const int n_cnt = rounds * K1_WARPS;
-    const int per = (n_cnt + K1_THREADS - 1) / K1_THREADS;  // <= 2
-    uint32_t local[2] = {0, 0}, lsum = 0;
-    for (int k = 0; k < per; ++k) {
-        const int i = tid * per + k;
-        local[k] = i < n_cnt ? cnt[i] : 0;
-        lsum += local[k];
-    }
-    uint32_t incl = lsum;
+    const uint32_t mine = (uint32_t)__popcll(vbits);
+    uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -183,23 +185,18 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
             if (lane >= o) wi += t;
         }
         warp_tot[lane] = wi - w;  // exclusive warp offsets
-        if (lane == 31) cnt[n_cnt] = wi;
+        if (lane == 31) total = wi;
     }
     __syncthreads();
-    uint32_t run = warp_tot[warp] + incl - lsum;
-    __syncthreads();
-    for (int k = 0; k < per; ++k) {
-        const int i = tid * per + k;
-        if (i < n_cnt) cnt[i] = run;
-        run += local[k];
-    }
-    __syncthreads();
-    const int P = (int)cnt[n_cnt];
-    // ---- pass 1c: ordered compaction
-    for (int r = 0; r < rounds; ++r) {
-        const bool ok = (vbits >> r) & 1ull;
-        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-        if (ok) list[cnt[r * K1_WARPS + warp] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(r * K1_THREADS + tid);
+    const int P = (int)total;
+    {
+        uint32_t at = warp_tot[warp] + incl - mine;
+        uint64_t bits = vbits;
+        while (bits) {   // the thread's valid pixels in ascending order
+            const int i = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            list[at++] = (uint16_t)(p0 + i);
+        }
     }
     __syncthreads();
     if (tid == 0 && count_out) count_out[b] = P;
@@ -246,11 +243,7 @@ backproject_kernel(const float* __restrict__ img, const float* __restrict__ com3
     }
 }
 
-static size_t k1_smem_bytes(int S) {
-    const int npix = S * S;
-    const int rounds = (npix + K1_THREADS - 1) / K1_THREADS;
-    return (((size_t)npix * 2 + 15) & ~(size_t)15) + ((size_t)rounds * K1_WARPS + 1) * 4;
-}
+static size_t k1_smem_bytes(int S) { return (((size_t)S * S * 2 + 15) & ~(size_t)15); }
 
 }  // namespace kpf
 

@@ -217,7 +217,8 @@ def gather_taps(feat, index, closeness, out=None, out_c0=0):
         out = torch.empty(B, N, C, device=feat.device, dtype=feat.dtype)
         out_c0 = 0
     assert out.dtype == feat.dtype and out.is_contiguous()
-    rows = torch.empty(B, HW, (C + 7) // 8 * 8, device=feat.device, dtype=feat.dtype)   # the map as channels-last rows (workspace)
+    # maps whose 16-byte-row slab fits shared memory take the one-kernel path (csrc/gather.cu); larger ones need a channels-last workspace
+    rows = torch.empty(B, HW, (C + 7) // 8 * 8, device=feat.device, dtype=feat.dtype) if HW * 16 > 96 * 1024 else None
     _call("kpf_gather_taps", _p(feat), _DT[feat.dtype], bs, B, C, HW, _p(index), int(index.dtype == torch.int64), _p(closeness), N, K,
           _p(out), out.shape[-1], out_c0, _p(rows))
     return out

@@ -302,3 +302,21 @@ def test_spatial_order_is_a_permutation(ops, golden_inputs, N):
     order = ops.spatial_order(cu(pcl), cu(inp["center"]), cu(inp["M"]), cu(inp["cube"]), cu(inp["cam"]), 128, 32)
     assert order.dtype == torch.int32 and tuple(order.shape) == (B, N)
     assert torch.equal(torch.sort(order.long().cpu(), dim=1)[0], torch.arange(N).expand(B, -1))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("fs,C,K", [(15, 12, 9), (32, 37, 4), (48, 128, 4), (80, 12, 9)])
+def test_gather_taps_shapes_and_fallback(ops, dtype, fs, C, K):
+    """K3 beyond the benchmark shape: odd map sizes (scalar loader), channel counts that are no multiple of the 16-byte chunk, 9 taps,
+    a channel slice of a wider map, and an 80 x 80 map whose slab does not fit shared memory (two-kernel workspace path)."""
+    g = torch.Generator().manual_seed(fs * 131 + C)
+    B, N, HW = 2, 300, fs * fs
+    wide = torch.randn(B, C + 5, fs, fs, generator=g).to(dtype)
+    feat = wide[:, 3:3 + C]
+    idx = torch.randint(0, HW, (B, N, K), generator=g)
+    cl = torch.rand(B, N, K, generator=g)
+    ref = torch.einsum("bnkc,bnk->bnc", feat.float().reshape(B, C, HW).transpose(1, 2)[torch.arange(B)[:, None, None], idx], cl)
+    out = ops.gather_taps(cu(wide)[:, 3:3 + C], cu(idx), cu(cl))
+    assert out.dtype == dtype and out.shape == (B, N, C)
+    tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=2e-2)
+    close(out.float(), ref, **tol)
