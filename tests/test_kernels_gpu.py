@@ -320,3 +320,22 @@ def test_gather_taps_shapes_and_fallback(ops, dtype, fs, C, K):
     assert out.dtype == dtype and out.shape == (B, N, C)
     tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=2e-2)
     close(out.float(), ref, **tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,h,w", [(64, 32, 32), (128, 16, 16), (256, 8, 8), (512, 4, 4), (96, 24, 24), (40, 7, 7), (8, 2, 2)])
+def test_rgbd_fusion_stage_shapes(ops, dtype, C, h, w):
+    """K7 at the four ResNet-18 stage shapes of a 128 crop (model/resnet.py:439-442: the chunked kernel with 32 / 8 / 2 / 2 chunk
+    columns per CTA), a 24 x 24 map (partial last CTA), and two maps whose HW is no multiple of the 16-byte chunk (generic kernel)."""
+    g = torch.Generator().manual_seed(C + h)
+    B = 3
+    r, d = torch.randn(B, C, h, w, generator=g).to(dtype), torch.randn(B, C, h, w, generator=g).to(dtype)
+    p = {"gate_rgb.weight": torch.randn(1, 2 * C, 1, 1, generator=g) / (2 * C) ** 0.5, "gate_rgb.bias": torch.randn(1, generator=g) * 0.1,
+         "gate_depth.weight": torch.randn(1, 2 * C, 1, 1, generator=g) / (2 * C) ** 0.5, "gate_depth.bias": torch.randn(1, generator=g) * 0.1}
+    gw = torch.cat([p["gate_rgb.weight"].reshape(1, -1), p["gate_depth.weight"].reshape(1, -1)], 0)
+    gb = torch.cat([p["gate_rgb.bias"], p["gate_depth.bias"]])
+    ro, do, mg, am = ops.rgbd_fusion(cu(r), cu(d), cu(gw), cu(gb), want_attn_mean=True)
+    (rro, rdo), rmg = O.rgbd_fusion(p, r.float(), d.float())
+    tol = dict(rtol=1e-4, atol=2e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    close(ro, rro, **tol), close(do, rdo, **tol), close(mg, rmg, **tol)
+    assert abs(float(am.sum()) - 1.0) < 1e-4     # the two attention maps sum to one at every pixel
