@@ -374,9 +374,12 @@ template <int FMT>
 __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaParams p) {
     extern __shared__ __align__(128) unsigned char ds_smem[];
     uint4* sW1t = reinterpret_cast<uint4*>(ds_smem);  // W1's K tail (the xyz columns), 2 planes x [2][128]; W1 main / W2 live in tensor memory
-    uint4* sX = sW1t + 512;                            // [2] x (2 planes x K-major activations [16 row groups][16 k-chunks][8 rows] + 2 planes x tail [16][2][8])
-    uint4* sH = sX + 2 * DS_XBUF;                      // 2 planes x MN-major [16][16][8]
-    float* sPart = reinterpret_cast<float*>(sH + 4096);   // [2][4][128] per-column-group maxima
+    // Three activation buffers, tile t lives in buffer t % 3 for three iterations: its gathered rows are copied in (K-major B operand of
+    // layer 1: 2 planes x [16 row groups][16 k-chunks][8 rows] + 2 planes x tail [16][2][8]); once layer 1 has read them, the layer-1
+    // epilogue writes h = relu(.) over the SAME bytes (MN-major B operand of layer 2: 2 planes x [16][16][8]); layer 2 reads it one
+    // iteration later.  No separate h buffer, so the epilogue of tile t + 1 never waits for layer 2 of tile t to release one.
+    uint4* sX = sW1t + 512;
+    float* sPart = reinterpret_cast<float*>(sX + 3 * DS_XBUF);   // [2][4][128] per-column-group maxima
     float4* sXyz = reinterpret_cast<float4*>(sPart + 1024);   // [2][128][2] xyz of a tile's grouped points and of their centres (cp.async staging)
     __shared__ __align__(8) uint64_t wbar, g1_bar, g2_bar;
     __shared__ uint32_t tmem_slot;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
             const int row = r + 64 * h, jj = it.j0 + (row >> ns_shift);
             const bool ok = jj < J;
             const uint16_t* src = p.e + (size_t)it.b * p.e_bs + (size_t)ii[h] * 256 + 8 * g8;   // row = [hi 128 | lo 128]
-            uint4* X = sX + (item & 1) * DS_XBUF + (row >> 3) * 128 + g8 * 8 + (row & 7);
+            uint4* X = sX + (item % 3) * DS_XBUF + (row >> 3) * 128 + g8 * 8 + (row & 7);
             const uint32_t nbytes = ok ? 16u : 0u;   // rows beyond the last joint are zero filled
             // (.cg: the rows stream through L2 only -- measured 9 % faster than .ca, whose L1 is ~30 KB next to 225 KB of shared memory)
             if (!(p.probe & 1))
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                 t8[1] = (a4.y - c4.y) * inv_r;
                 t8[2] = (a4.z - c4.z) * inv_r;
             }
-            uint4* X = sX + (item & 1) * DS_XBUF + 4096 + (row >> 3) * 8 + (row & 7);
+            uint4* X = sX + (item % 3) * DS_XBUF + 4096 + (row >> 3) * 8 + (row & 7);
             uint4 th, tl;
             split8(fmt, t8, th, tl);
             X[0] = th;
@@ -554,16 +557,11 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                     tc_fence_after();
                     if (!w_ready) mbar_wait(&wbar, w_phase);
                     if (elect_one()) {
-                        if (s >= i0) {   // layer 2 of tile s: D2[c][row] = W2 h
-                            TmemOp a;
-                            a.hi = tmem0 + TW2_HI; a.lo = tmem0 + TW2_LO;
-                            SmemOp hb;
-                            hb.hi = smem_u32(sH); hb.lo = hb.hi + 2048 * 16; hb.lbo = 2048; hb.sbo = 128;
-                            if (!(p.probe & 2)) umma_gemm3_ts(tmem0 + ACC2, a, hb, umma_idesc_f16(128, 128, false, true, fmt, fmt), 128, false);
-                            umma_commit(&g2_bar);
-                        }
+                        // Layer 1 of tile s + 1 goes FIRST: its (long) epilogue then runs under layer 2 of tile s, whose (short) epilogue
+                        // follows.  (Layer 2 first left the tensor pipe idle for the whole layer-1 epilogue of every tile; that order was
+                        // forced by a single h buffer, which layer 2 of tile s had to release before the epilogue of tile s + 1 could write.)
                         if (s + 1 < i1) {   // layer 1 of tile s + 1: D1[c][row] = W1 [feat - jf | xyz]
-                            const uint32_t X = smem_u32(sX + ((s + 1) & 1) * DS_XBUF);
+                            const uint32_t X = smem_u32(sX + ((s + 1) % 3) * DS_XBUF);
                             const uint32_t id128 = umma_idesc_f16(128, 128, false, false, fmt, fmt);
                             // B operand: 128 B between k-chunks, 2048 B (main) / 256 B (tail) between 8-row groups
                             TmemOp a;
@@ -576,6 +574,14 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                             if (!(p.probe & 2)) umma_gemm3_ss(tmem0 + ACC1, ta, tb, id128, 16, true);
                             umma_commit(&g1_bar);
                         }
+                        if (s >= i0) {   // layer 2 of tile s: D2[c][row] = W2 h
+                            TmemOp a;
+                            a.hi = tmem0 + TW2_HI; a.lo = tmem0 + TW2_LO;
+                            SmemOp hb;
+                            hb.hi = smem_u32(sX + (s % 3) * DS_XBUF); hb.lo = hb.hi + 2048 * 16; hb.lbo = 2048; hb.sbo = 128;
+                            if (!(p.probe & 2)) umma_gemm3_ts(tmem0 + ACC2, a, hb, umma_idesc_f16(128, 128, false, true, fmt, fmt), 128, false);
+                            umma_commit(&g2_bar);
+                        }
                     }
                     __syncwarp();
                 }
@@ -583,7 +589,8 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                 if (s - 1 >= i0) store_max(s - 1);   // written before the barrier above
             }
             if (!issuer) {
-                // gather side: rows of tile s + 2 (its buffer was last read by layer 1 of tile s, long complete), indices of s + 3
+                // gather side: rows of tile s + 2 (its buffer held tile s - 1, whose layer 2 every thread waited for in the previous
+                // iteration), indices of s + 3
                 const bool have_rows = s + 2 < i1;
                 if (have_rows) copy_rows(s + 2);
                 if (s + 3 < i1) fetch_idx();
@@ -594,28 +601,14 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                     if (jj < J) cjv = __ldg(p.cj + (((size_t)c_epi.b * S + c_epi.sc) * J + jj) * 128 + ch);
                     advance(c_epi);
                 }
-                if (s >= i0) {   // layer-2 epilogue of tile s: max over this thread's 32 grouped points  (model.py:197-198)
-                    mbar_wait(&g2_bar, g2_phase);
-                    g2_phase ^= 1;
-                    tc_fence_after();
-                    float mx = -INFINITY;
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {   // two 16-column reads: half the live registers of one 32-column read
-                        float a[16];
-                        tmem_ld<16>(tmem + ACC2 + 32 * cg + 16 * hf, a);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, a[i]);
-                    }
-                    sPart[(s & 1) * 512 + cg * 128 + ch] = fmaxf(mx + b2, 0.f);   // max_i relu(a_i + b2)
-                    tc_fence_before();
-                    }
-                if (s >= i0 - 1 && s + 1 < i1) {   // layer-1 epilogue of tile s + 1: h[c][row] = relu(D1 + b1) -> MN-major B operand
+                if (s >= i0 - 1 && s + 1 < i1) {   // layer-1 epilogue of tile s + 1: h[c][row] = relu(D1 + b1) -> MN-major B operand, in place
                     mbar_wait(&g1_bar, g1_phase);
                     g1_phase ^= 1;
                     tc_fence_after();
                     const float cjb = b1 - cjv;
+                    uint4* H = sX + ((s + 1) % 3) * DS_XBUF;   // layer 1 has consumed the rows that lived here
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
+                    for (int hf = 0; hf < 2; ++hf) {   // two 16-column reads: half the live registers of one 32-column read
                         float a[16];
                         tmem_ld<16>(tmem + ACC1 + 32 * cg + 16 * hf, a);
 #pragma unroll
@@ -624,10 +617,25 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                         for (int c = 0; c < 2; ++c) {
                             uint4 hh, hl;
                             split8(fmt, a + 8 * c, hh, hl);
-                            sH[(ch >> 3) * 128 + (4 * cg + 2 * hf + c) * 8 + (ch & 7)] = hh;
-                            sH[2048 + (ch >> 3) * 128 + (4 * cg + 2 * hf + c) * 8 + (ch & 7)] = hl;
+                            H[(ch >> 3) * 128 + (4 * cg + 2 * hf + c) * 8 + (ch & 7)] = hh;
+                            H[2048 + (ch >> 3) * 128 + (4 * cg + 2 * hf + c) * 8 + (ch & 7)] = hl;
                         }
                     }
+                }
+                if (s >= i0) {   // layer-2 epilogue of tile s: max over this thread's 32 grouped points  (model.py:197-198)
+                    mbar_wait(&g2_bar, g2_phase);
+                    g2_phase ^= 1;
+                    tc_fence_after();
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float a[16];
+                        tmem_ld<16>(tmem + ACC2 + 32 * cg + 16 * hf, a);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, a[i]);
+                    }
+                    sPart[(s & 1) * 512 + cg * 128 + ch] = fmaxf(mx + b2, 0.f);   // max_i relu(a_i + b2)
+                    tc_fence_before();
                 }
             }
             if (s <= i0 + 3) stamp();
@@ -675,7 +683,7 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     const size_t smem_jf = (size_t)(3 * 4096 + 1024) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
     const size_t smem_bq = (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)S * J * NW * 4 + 64;
     const size_t smem_a = smem_jf > smem_bq ? smem_jf : smem_bq;
-    const size_t smem_b = (size_t)(512 + 2 * DS_XBUF + 4096) * 16 + 2 * 512 * 4 + 2 * 128 * 2 * 16 + 64;
+    const size_t smem_b = (size_t)(512 + 3 * DS_XBUF) * 16 + 2 * 512 * 4 + 2 * 128 * 2 * 16 + 64;
     KPF_REQUIRE(smem_a <= 227 * 1024 && smem_b <= 227 * 1024);
     auto prep = fmt == FMT_F16 ? desa_prep_kernel<FMT_F16> : desa_prep_kernel<FMT_BF16>;
     auto tile = fmt == FMT_F16 ? desa_tile_kernel<FMT_F16> : desa_tile_kernel<FMT_BF16>;
