@@ -455,30 +455,47 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         }
         advance(c_idx);
     };
-    auto copy_rows = [&](int item) {   // uses ii
-        const DesaItem it = c_rows;
-        advance(c_rows);
-        const float4* tab = p.xyz4 + (size_t)it.b * (N + 32);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int row = r + 64 * h, jj = it.j0 + (row >> ns_shift);
-            const bool ok = jj < J;
-            const uint16_t* src = p.e + (size_t)it.b * p.e_bs + (size_t)ii[h] * 256 + 8 * g8;   // row = [hi 128 | lo 128]
-            uint4* X = sX + (item % 3) * DS_XBUF + (row >> 3) * 128 + g8 * 8 + (row & 7);
-            const uint32_t nbytes = ok ? 16u : 0u;   // rows beyond the last joint are zero filled
-            // (.cg: the rows stream through L2 only -- measured 9 % faster than .ca, whose L1 is ~30 KB next to 225 KB of shared memory)
-            if (!(p.probe & 1))
-#pragma unroll
-            for (int k = 0; k < 4; ++k)   // 16-byte chunk 8k + g8 of the 512-byte row: k-chunk (8k + g8) & 15 of plane k >> 1
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(X + (k >> 1) * 2048 + (k & 1) * 64)), "l"(src + 64 * k), "r"(nbytes) : "memory");
-            if (g8 == 0) {   // xyz of the row's point and of its centre -> staging; the tail is built from it one iteration later
-                float4* st = sXyz + ((item & 1) * 128 + row) * 2;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st)), "l"(tab + ii[h]) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st + 1)), "l"(tab + N + (ok ? jj : 0)) : "memory");
-                tail_ok[h] = ok;
-            }
+    // One part of a tile's row copy: part = 4 h + k = 16-byte chunk group k of this thread's row r + 64 h (uses ii; the item cursor is
+    // captured by part 0, the group is committed by part 7).  The eight parts are issued at eight points of an iteration, between the
+    // pieces of the epilogues, NOT back to back: a burst of 6144 cp.async fills the SM's memory-instruction queue and every warp's
+    // next shared-memory / TMEM / global instruction -- i.e. the epilogues -- queues up behind it.  Measured per launch, the kernel alone
+    // over L2-resident rows (profiles/probe_kernels.py, same box): one burst 84.1 us, two halves 81, four parts 77.0, eight parts 74.8
+    // (with the copy switched off: 57 us).  Inside the running step (four steps in flight, rows partly from DRAM) the gain is within
+    // the run-to-run noise: 0.497 vs 0.501 ms per step, means of three alternating runs (KPF_DESA_PROBE=4 restores the burst).
+    DesaItem it_copy = {0, 0, 0};
+    const bool burst = (p.probe & 4) != 0;   // A/B switch (KPF_DESA_PROBE=4): the whole copy at the point of part 0, as one burst
+    auto copy_one = [&](int item, int part) {
+        if (part == 0) {
+            it_copy = c_rows;
+            advance(c_rows);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int h = part >> 2, k = part & 3;
+        const int row = r + 64 * h, jj = it_copy.j0 + (row >> ns_shift);
+        const bool ok = jj < J;
+        const uint16_t* src = p.e + (size_t)it_copy.b * p.e_bs + (size_t)ii[h] * 256 + 8 * g8;
+        uint4* X = sX + (item % 3) * DS_XBUF + (row >> 3) * 128 + g8 * 8 + (row & 7);
+        const uint32_t nbytes = ok ? 16u : 0u;
+        // 16-byte chunk 8k + g8 of the 512-byte row [hi 128 | lo 128]: k-chunk (8k + g8) & 15 of plane k >> 1; the eight g8 lanes of a row
+        // read 128 contiguous bytes = ONE request.  (.cg: the rows stream through L2 only -- measured 9 % faster than .ca, whose L1 is
+        // ~30 KB next to 225 KB of shared memory.)  Rows beyond the last joint are zero filled (src-size 0).
+        if (!(p.probe & 1))
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(X + (k >> 1) * 2048 + (k & 1) * 64)), "l"(src + 64 * k), "r"(nbytes) : "memory");
+        if (k == 0 && g8 == 0) {   // xyz of the row's point and of its centre -> staging; the tail is built from it one iteration later
+            const float4* tab = p.xyz4 + (size_t)it_copy.b * (N + 32);
+            float4* st = sXyz + ((item & 1) * 128 + row) * 2;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st)), "l"(tab + ii[h]) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st + 1)), "l"(tab + N + (ok ? jj : 0)) : "memory");
+            tail_ok[h] = ok;
+        }
+        if (part == 7) asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto copy_part = [&](int item, int part) {
+        if (!burst) {
+            copy_one(item, part);
+        } else if (part == 0) {
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) copy_one(item, q8);
+        }
     };
     auto store_tail = [&](int item) {   // group_xyz_norm = (xyz[idx] - centre) / radius   model.py:177
         if (g8 != 0) return;
@@ -591,15 +608,18 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
             if (!issuer) {
                 // gather side: rows of tile s + 2 (its buffer held tile s - 1, whose layer 2 every thread waited for in the previous
                 // iteration), indices of s + 3
-                const bool have_rows = s + 2 < i1;
-                if (have_rows) copy_rows(s + 2);
-                if (s + 3 < i1) fetch_idx();
+                const bool fine = s + 2 < i1;   // tile s + 2 exists: its row copy is issued in eight parts across this iteration (copy_part)
+                if (fine) copy_part(s + 2, 0);
                 // layer-1 bias of tile s + 1 minus the W1 jf term of the joint this thread's 32 rows belong to
                 float cjv = 0.f;   // loaded here, consumed after the layer-2 epilogue (the subtraction sits behind the wait below on purpose)
                 if (s >= i0 - 1 && s + 1 < i1) {
                     const int jj = c_epi.j0 + ((32 * cg) >> ns_shift);
                     if (jj < J) cjv = __ldg(p.cj + (((size_t)c_epi.b * S + c_epi.sc) * J + jj) * 128 + ch);
                     advance(c_epi);
+                }
+                if (fine) {
+                    copy_part(s + 2, 1);
+                    copy_part(s + 2, 2);
                 }
                 if (s >= i0 - 1 && s + 1 < i1) {   // layer-1 epilogue of tile s + 1: h[c][row] = relu(D1 + b1) -> MN-major B operand, in place
                     mbar_wait(&g1_bar, g1_phase);
@@ -620,7 +640,11 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                             H[(ch >> 3) * 128 + (4 * cg + 2 * hf + c) * 8 + (ch & 7)] = hh;
                             H[2048 + (ch >> 3) * 128 + (4 * cg + 2 * hf + c) * 8 + (ch & 7)] = hl;
                         }
+                        if (fine) copy_part(s + 2, 3 + hf);
                     }
+                } else if (fine) {
+                    copy_part(s + 2, 3);
+                    copy_part(s + 2, 4);
                 }
                 if (s >= i0) {   // layer-2 epilogue of tile s: max over this thread's 32 grouped points  (model.py:197-198)
                     mbar_wait(&g2_bar, g2_phase);
@@ -633,10 +657,16 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                         tmem_ld<16>(tmem + ACC2 + 32 * cg + 16 * hf, a);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) mx = fmaxf(mx, a[i]);
+                        if (fine) copy_part(s + 2, 5 + hf);
                     }
                     sPart[(s & 1) * 512 + cg * 128 + ch] = fmaxf(mx + b2, 0.f);   // max_i relu(a_i + b2)
                     tc_fence_before();
+                } else if (fine) {
+                    copy_part(s + 2, 5);
+                    copy_part(s + 2, 6);
                 }
+                if (fine) copy_part(s + 2, 7);
+                if (s + 3 < i1) fetch_idx();
             }
             if (s <= i0 + 3) stamp();
         }

@@ -87,10 +87,13 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
     const __nv_bfloat16* fbl = has_lo ? p.feat_lo + (size_t)b * 128 * HW : nullptr;
     // tile loader: thread -> (c%8 = tid%8, hw8 = (tid/8)%16, channel group tid/128 + 4i): 16-byte cp.async, 128 contiguous bytes
     // of a channel row per 8 lanes
-    auto load_tile = [&](int t, uint4* dst) {
+    // (parts [i0, i1) of the four: the prefetch of the NEXT tile is issued in four parts across an iteration, not as one burst that
+    //  fills the memory-instruction queue in front of the geometry's and the epilogues' shared-memory accesses -- see desa_fused.cu)
+    auto load_tile = [&](int t, uint4* dst, int i0 = 0, int i1 = 4) {
         const int c8 = tid & 7, hw8 = (tid >> 3) & 15;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+            if (i < i0 || i >= i1) continue;
             const int cgp = (tid >> 7) + 4 * i;
             cp_async16(dst + cgp * 128 + hw8 * 8 + c8, fb + (size_t)(cgp * 8 + c8) * HW + t * 128 + hw8 * 8);
             if (has_lo) cp_async16(dst + 2048 + cgp * 128 + hw8 * 8 + c8, fbl + (size_t)(cgp * 8 + c8) * HW + t * 128 + hw8 * 8);
@@ -138,7 +141,9 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
         if (NBUF == 1 && t > t_begin) load_tile(t, sF);   // single buffer: its readers (tile t-1's MMAs) were waited for
         cp_async_wait_all();   // this thread's part of tile t has landed ...
         __syncthreads();       // ... and everybody's; the other buffer's readers (tile t-1) are done
-        if (NBUF == 2 && t + 1 < t_end) load_tile(t + 1, sF + ((t + 1 - t_begin) & 1) * NP * 2048);  // overlaps the whole iteration
+        const bool prefetch = NBUF == 2 && t + 1 < t_end;   // overlaps the whole iteration
+        uint4* nxt = sF + ((t + 1 - t_begin) & 1) * NP * 2048;
+        if (prefetch) load_tile(t + 1, nxt, 0, 1);
         if (t == t_begin + 1) stamp();
         // ---- per-cell geometry (thread = cell `row`, joints [8cg, 8cg + 8)): heat-map chunk (A operand) and GAM (registers)
         const int m = t * 128 + row, r = m / fs, col = m - r * fs;
@@ -171,6 +176,7 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
             sHm[512 + cg * 128 + row] = ol;
         }
         if (t == t_begin + 1) stamp();
+        if (prefetch) load_tile(t + 1, nxt, 1, 2);
         // relu copy for GEMM B (same layout)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
             __syncwarp();
         }
         const float fw = __ldg(p.fc_w + m);
+        if (prefetch) load_tile(t + 1, nxt, 2, 3);
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(K5_NT, 1) spatial_aggregate_tc_kernel(const Sp
             sG[512 + (row >> 3) * 32 + cg * 8 + (row & 7)] = om;
             sG[1024 + (row >> 3) * 32 + cg * 8 + (row & 7)] = ol;
         }
+        if (prefetch) load_tile(t + 1, nxt, 3, 4);
         if (t == t_begin + 1) stamp();
         fence_proxy_async();
         tc_fence_before();
