@@ -278,6 +278,55 @@ def _(anchor, tokens, wpack, heads, ffn):
     return anchor.new_empty(B, C, J, dtype=torch.float32)
 
 
+# ------------------------------------------------------------------------------------------------ 8b: general-shape attention (off the live path)
+@_op("linear_rows")
+def linear_rows(x: Tensor, weight: Tensor, bias: Optional[Tensor], pos: Optional[Tensor], pos_index: Optional[Tensor], scale: float,
+                relu: bool, out_layout: int) -> Tensor:
+    return ops.linear_rows(x, weight, bias, pos=pos, pos_index=pos_index, scale=scale, relu=relu, out_layout=out_layout)
+
+
+@linear_rows.register_fake
+def _(x, weight, bias, pos, pos_index, scale, relu, out_layout):
+    B, P, O = x.shape[0], x.shape[1], weight.shape[0]
+    shape = (B, O, P) if out_layout == ops.ROWS_BOP else (P, B, O) if out_layout == ops.ROWS_PBO else (B, P, O)
+    return x.new_empty(shape, dtype=torch.float32)
+
+
+@_op("mha_core")
+def mha_core(q: Tensor, k: Tensor, v: Tensor, num_heads: int, attn_mask: Optional[Tensor], key_padding_mask: Optional[Tensor],
+             need_weights: bool) -> Tuple[Tensor, Tensor]:
+    out, w = ops.mha_core(q, k, v, num_heads, attn_mask=attn_mask, key_padding_mask=key_padding_mask, need_weights=need_weights)
+    return out, (w if w is not None else _empty(q.device))
+
+
+@mha_core.register_fake
+def _(q, k, v, num_heads, attn_mask, key_padding_mask, need_weights):
+    B, Pq, C = q.shape
+    return q.new_empty(B, Pq, C, dtype=torch.float32), (q.new_empty(B, Pq, k.shape[1], dtype=torch.float32) if need_weights
+                                                         else q.new_empty(0, dtype=torch.float32))
+
+
+@_op("add_layernorm_rows")
+def add_layernorm_rows(x: Tensor, r: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float, channel_major: bool) -> Tensor:
+    return ops.add_layernorm_rows(x, r, gamma, beta, eps, channel_major)
+
+
+@add_layernorm_rows.register_fake
+def _(x, r, gamma, beta, eps, channel_major):
+    B, P, C = x.shape
+    return x.new_empty((B, C, P) if channel_major else (B, P, C), dtype=torch.float32)
+
+
+@_op("sine_posembed")
+def sine_posembed(dim_t: Tensor, B: int, H: int, W: int, mask: Optional[Tensor], normalize: bool, scale: float) -> Tensor:
+    return ops.sine_posembed(dim_t, B, H, W, mask=mask, normalize=normalize, scale=scale)
+
+
+@sine_posembed.register_fake
+def _(dim_t, B, H, W, mask, normalize, scale):
+    return dim_t.new_empty(B, 2 * dim_t.numel(), H, W, dtype=torch.float32)
+
+
 @_op("ball_query")
 def ball_query(xyz: Tensor, centers: Tensor, radius: float, nsample: int) -> Tensor:
     return ops.ball_query(xyz, centers, radius, nsample)

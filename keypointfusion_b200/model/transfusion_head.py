@@ -13,7 +13,23 @@ from torch.nn import Linear
 from torch.nn.init import constant_, xavier_normal_, xavier_uniform_
 from torch.nn.parameter import Parameter
 
+from .. import custom_ops as _cops   # noqa: F401  (registers torch.ops.kpf.*)
 from .. import ops
+
+_K = torch.ops.kpf   # the general-shape kernels are reached through their custom ops, like the hot path (traceable by torch.compile)
+
+
+def _linear(x, weight, bias=None, pos=None, pos_index=None, scale=1.0, relu=False, out_layout=ops.ROWS_BPO):
+    return _K.linear_rows(x, weight, bias, pos, pos_index, float(scale), bool(relu), int(out_layout))
+
+
+def _attend(q, k, v, heads, attn_mask=None, key_padding_mask=None, need_weights=False):
+    out, w = _K.mha_core(q, k, v, int(heads), attn_mask, key_padding_mask, bool(need_weights))
+    return out, (w if need_weights else None)
+
+
+def _add_ln(x, r, norm, channel_major=False):
+    return _K.add_layernorm_rows(x, r, norm.weight, norm.bias, float(norm.eps), bool(channel_major))
 
 
 class PositionEmbeddingLearned(nn.Module):
@@ -35,11 +51,8 @@ class PositionEmbeddingLearned(nn.Module):
         g = bn.weight / torch.sqrt(bn.running_var + bn.eps)          # fold: y = g (W x + b - mean) + beta
         w1 = c1.weight[:, :, 0] * g[:, None]
         b1 = (c1.bias - bn.running_mean) * g + bn.bias
-        h = ops.linear_rows(xyz, w1, b1, relu=True)                   # [B,P,F]
-        B, P, Fo = h.shape[0], h.shape[1], c2.weight.shape[0]
-        out = torch.empty(B, Fo, P, device=h.device, dtype=torch.float32)
-        ops.linear_rows(h, c2.weight[:, :, 0], c2.bias, out=out.transpose(1, 2))   # written channel-major: [B,F,P]  (:31)
-        return out
+        h = _linear(xyz, w1, b1, relu=True)                                            # [B,P,F]
+        return _linear(h, c2.weight[:, :, 0], c2.bias, out_layout=ops.ROWS_BOP)        # written channel-major: [B,F,P]  (:31)
 
 
 class DetrLearnedPositionEmbedding(nn.Module):
@@ -84,12 +97,12 @@ class DetrSinePositionEmbedding(nn.Module):
         if pixel_mask is None:
             raise ValueError("No pixel mask provided")
         B, H, W = pixel_mask.shape
-        return ops.sine_posembed(self.dim_t(pixel_values.device), B, H, W, mask=pixel_mask, normalize=self.normalize, scale=self.scale)
+        return _K.sine_posembed(self.dim_t(pixel_values.device), B, H, W, pixel_mask, bool(self.normalize), float(self.scale))
 
     def full_mask(self, H, W, device):
         """The embedding of an all-ones mask (what detrDecoder / spatial_aggregate_TR pass, :612, :770): [1, 2*dim, H, W], the same
         for every sample of a batch."""
-        return ops.sine_posembed(self.dim_t(device), 1, H, W, mask=None, normalize=self.normalize, scale=self.scale)
+        return _K.sine_posembed(self.dim_t(device), 1, H, W, None, bool(self.normalize), float(self.scale))
 
 
 class MultiheadAttention(nn.Module):
@@ -131,16 +144,15 @@ class MultiheadAttention(nn.Module):
         L, N, _ = query.shape
         W, b = self.in_proj_weight, self.in_proj_bias
         bq, bk, bv = (None, None, None) if b is None else (b[:E], b[E:2 * E], b[2 * E:])
-        q = ops.linear_rows(query.transpose(0, 1), W[:E], bq, scale=float(hd) ** -0.5)     # [N,L,E]   :403, :468
+        q = _linear(query.transpose(0, 1), W[:E], bq, scale=float(hd) ** -0.5)             # [N,L,E]   :403, :468
         if key is value:
-            kv = ops.linear_rows(key.transpose(0, 1), W[E:], None if b is None else b[E:])  # [N,S,2E]  :418
+            kv = _linear(key.transpose(0, 1), W[E:], None if b is None else b[E:])          # [N,S,2E]  :418
             k, v = kv[..., :E], kv[..., E:]
         else:
-            k = ops.linear_rows(key.transpose(0, 1), W[E:2 * E], bk)
-            v = ops.linear_rows(value.transpose(0, 1), W[2 * E:], bv)
-        a, w = ops.mha_core(q, k, v, H, attn_mask=attn_mask, key_padding_mask=key_padding_mask, need_weights=need_weights)
-        out = torch.empty(L, N, E, device=query.device, dtype=torch.float32)
-        ops.linear_rows(a, self.out_proj.weight, self.out_proj.bias, out=out.transpose(0, 1))    # :546
+            k = _linear(key.transpose(0, 1), W[E:2 * E], bk)
+            v = _linear(value.transpose(0, 1), W[2 * E:], bv)
+        a, w = _attend(q, k, v, H, attn_mask=attn_mask, key_padding_mask=key_padding_mask, need_weights=need_weights)
+        out = _linear(a, self.out_proj.weight, self.out_proj.bias, out_layout=ops.ROWS_PBO)   # written sequence-first: [L,N,E]  :546
         return out, w
 
 
@@ -227,21 +239,21 @@ class TransformerDecoderLayer(nn.Module):
         if not self.cross_only:   # :157-161  q = k = v = query + pos
             m = self.self_attn
             W, b = m.in_proj_weight, m.in_proj_bias
-            q = ops.linear_rows(x, W[:C], None if b is None else b[:C], scale=float(hd) ** -0.5, **qpos)
-            kv = ops.linear_rows(x, W[C:], None if b is None else b[C:], **qpos)     # [B,Pq,2C]
-            a, _ = ops.mha_core(q, kv[..., :C], kv[..., C:], H)
-            a = ops.linear_rows(a, m.out_proj.weight, m.out_proj.bias)
-            x = ops.add_layernorm_rows(x, a, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            q = _linear(x, W[:C], None if b is None else b[:C], scale=float(hd) ** -0.5, **qpos)
+            kv = _linear(x, W[C:], None if b is None else b[C:], **qpos)             # [B,Pq,2C]
+            a, _ = _attend(q, kv[..., :C], kv[..., C:], H)
+            a = _linear(a, m.out_proj.weight, m.out_proj.bias)
+            x = _add_ln(x, a, self.norm1)
         m = self.multihead_attn   # :163-167  value = key + key_pos as well
         W, b = m.in_proj_weight, m.in_proj_bias
-        q = ops.linear_rows(x, W[:C], None if b is None else b[:C], scale=float(hd) ** -0.5, **qpos)
-        kv = ops.linear_rows(key, W[C:], None if b is None else b[C:], **kpos)       # [B,Pk,2C]
-        a, _ = ops.mha_core(q, kv[..., :C], kv[..., C:], H, attn_mask=attn_mask)
-        a = ops.linear_rows(a, m.out_proj.weight, m.out_proj.bias)
-        x = ops.add_layernorm_rows(x, a, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        h = ops.linear_rows(x, self.linear1.weight, self.linear1.bias, relu=True)    # :169-171
-        y = ops.linear_rows(h, self.linear2.weight, self.linear2.bias)
-        return ops.add_layernorm_rows(x, y, self.norm3.weight, self.norm3.bias, self.norm3.eps, channel_major=True)   # :172 [B,C,Pq]
+        q = _linear(x, W[:C], None if b is None else b[:C], scale=float(hd) ** -0.5, **qpos)
+        kv = _linear(key, W[C:], None if b is None else b[C:], **kpos)               # [B,Pk,2C]
+        a, _ = _attend(q, kv[..., :C], kv[..., C:], H, attn_mask=attn_mask)
+        a = _linear(a, m.out_proj.weight, m.out_proj.bias)
+        x = _add_ln(x, a, self.norm2)
+        h = _linear(x, self.linear1.weight, self.linear1.bias, relu=True)            # :169-171
+        y = _linear(h, self.linear2.weight, self.linear2.bias)
+        return _add_ln(x, y, self.norm3, channel_major=True)                         # :172 [B,C,Pq]
 
 
 class updatedDecoder(nn.Module):

@@ -308,10 +308,14 @@ def _rows3(t, name):
     return t if t.dtype == torch.float32 else t.float()
 
 
-def linear_rows(x, weight, bias=None, pos=None, pos_index=None, scale=1.0, relu=False, out=None):
+ROWS_BPO, ROWS_BOP, ROWS_PBO = 0, 1, 2   # linear_rows output layouts: [B,P,O] | channel-major [B,O,P] | sequence-first [P,B,O]
+
+
+def linear_rows(x, weight, bias=None, pos=None, pos_index=None, scale=1.0, relu=False, out=None, out_layout=ROWS_BPO):
     """out[b,p,:] = act(((x[b,p,:] + pos_row) @ weight.T + bias) * scale)   (csrc/attn_general.cu).
     x [B,P,K] any strides; weight [O,K]; pos None | [B or 1,P,K] any strides | an nn.Embedding table [n,K] with pos_index [B,P] i64;
-    out None (-> new contiguous [B,P,O]) or a preallocated [B,P,O] VIEW with any strides (e.g. a [P,B,O] tensor transposed)."""
+    out None -> a new contiguous tensor in `out_layout` ([B,P,O]; ROWS_BOP: [B,O,P]; ROWS_PBO: [P,B,O] -- written in place through
+    strides, no transposed copy), or a preallocated [B,P,O] VIEW with any strides."""
     x = _rows3(x, "linear_rows")
     B, P, K = x.shape
     weight = _f32(weight)
@@ -331,13 +335,21 @@ def linear_rows(x, weight, bias=None, pos=None, pos_index=None, scale=1.0, relu=
         if pos.shape[1:] != (P, K) or pos.shape[0] not in (1, B):
             raise ValueError(f"linear_rows: pos {tuple(pos.shape)} does not match x {tuple(x.shape)}")
         pb, pp, pk = (0 if pos.shape[0] == 1 else pos.stride(0)), pos.stride(1), pos.stride(2)
+    ret = None
     if out is None:
-        out = torch.empty(B, P, O, device=x.device, dtype=torch.float32)
+        if out_layout == ROWS_BOP:
+            ret = torch.empty(B, O, P, device=x.device, dtype=torch.float32)
+            out = ret.transpose(1, 2)
+        elif out_layout == ROWS_PBO:
+            ret = torch.empty(P, B, O, device=x.device, dtype=torch.float32)
+            out = ret.transpose(0, 1)
+        else:
+            ret = out = torch.empty(B, P, O, device=x.device, dtype=torch.float32)
     elif out.shape != (B, P, O) or out.dtype != torch.float32:
         raise ValueError(f"linear_rows: out {tuple(out.shape)} / {out.dtype}, expected {(B, P, O)} float32")
     _call("kpf_linear_rows", _p(x), x.stride(0), x.stride(1), x.stride(2), _p(pos), pb, pp, pk, _p(idx), _p(weight), _p(bias), B, P, K, O,
           float(scale), int(bool(relu)), _p(out), out.stride(0), out.stride(1), out.stride(2))
-    return out
+    return out if ret is None else ret
 
 
 def mha_core(q, k, v, num_heads, attn_mask=None, key_padding_mask=None, need_weights=False):

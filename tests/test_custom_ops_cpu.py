@@ -42,3 +42,22 @@ def test_fusion_path_shape_propagates_under_fake_tensors(maps):
     assert [tuple(r.shape) for r in res[2:]] == [(B, 21, 3)] * 4 and all(r.dtype == torch.float32 for r in res[2:])
     assert [tuple(w.shape) for w in sw] == [(B, 21, 32, 32)] * 2
     assert res[2].device.type == "cuda"
+
+
+def test_general_attention_heads_shape_propagate_under_fake_tensors():
+    """The exports of transfusion_head.py off the live path reach their kernels through torch.ops.kpf.* too: detrDecoder,
+    spatial_aggregate_TR, MultiheadAttention and the position embeddings trace with FakeTensors (no GPU, no launch)."""
+    from keypointfusion_b200.model import transfusion_head as T
+    need = {"linear_rows", "mha_core", "add_layernorm_rows", "sine_posembed"}
+    assert need <= set(custom_ops.REGISTERED)
+    det, sat, mha = T.detrDecoder(num_decoder_layers=2).eval(), T.spatial_aggregate_TR(num_decoder_layers=2).eval(), T.MultiheadAttention(128, 4).eval()
+    pel, sine = T.PositionEmbeddingLearned(3, 32).eval(), T.DetrSinePositionEmbedding(64, normalize=True)
+    with torch.no_grad(), FakeTensorMode(allow_non_fake_inputs=True):
+        dev = "cuda"
+        anchors, img = torch.empty(3, 21, 128, device=dev), torch.empty(3, 128, 32, 32, device=dev)
+        assert tuple(det.to(dev)(anchors, img).shape) == (3, 128, 21)
+        assert tuple(sat.to(dev)(img, anchors).shape) == (3, 128, 1024)
+        o, w = mha.to(dev)(torch.empty(7, 2, 128, device=dev), torch.empty(45, 2, 128, device=dev), torch.empty(45, 2, 128, device=dev))
+        assert tuple(o.shape) == (7, 2, 128) and tuple(w.shape) == (2, 7, 45)
+        assert tuple(pel.to(dev)(torch.empty(2, 50, 3, device=dev)).shape) == (2, 32, 50)
+        assert tuple(sine(img, torch.empty(3, 32, 32, device=dev)).shape) == (3, 128, 32, 32)

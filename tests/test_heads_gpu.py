@@ -177,3 +177,38 @@ def test_mha_matches_torch_functional_and_the_live_golden(golden, golden_meta):
         o, w = m(d(golden["a13_mha_q"]), kk, kk)
     close(o, golden["a13_mha_out"], 2e-5, "live layer's attention: out")
     close(w, golden["a13_mha_w"], 1e-6, "live layer's attention: weights")
+
+
+def test_general_ops_opcheck_and_compile():
+    """torch.library.opcheck for the four general-shape custom ops (strided inputs, every optional argument) and a fullgraph
+    torch.compile of detrDecoder: the decoders trace as opaque kpf ops, like the hot path."""
+    from torch.library import opcheck
+    K = torch.ops.kpf
+    tests = ("test_schema", "test_faketensor")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(9, 2, 40, generator=g).to(DEV).transpose(0, 1)                       # [B,P,K] view of a [P,B,K] tensor
+    W, b = torch.randn(24, 40, generator=g).to(DEV), torch.randn(24, generator=g).to(DEV)
+    table, idx = torch.randn(12, 40, generator=g).to(DEV), torch.randint(0, 12, (2, 9), generator=g).to(DEV)
+    for layout in (0, 1, 2):
+        opcheck(K.linear_rows, (x, W, b, table, idx, 0.5, True, layout), test_utils=tests)
+    opcheck(K.linear_rows, (x, W, None, torch.randn(1, 9, 40, generator=g).to(DEV), None, 1.0, False, 0), test_utils=tests)
+    q, kv = torch.randn(2, 9, 64, generator=g).to(DEV), torch.randn(2, 33, 128, generator=g).to(DEV)
+    am, kpm = torch.randn(9, 33, generator=g).to(DEV), (torch.rand(2, 33, generator=g) > 0.8).to(DEV)
+    opcheck(K.mha_core, (q, kv[..., :64], kv[..., 64:], 4, am, kpm, True), test_utils=tests)
+    opcheck(K.mha_core, (q, kv[..., :64], kv[..., 64:], 2, None, None, False), test_utils=tests)
+    gam, bet = torch.rand(64, generator=g).to(DEV), torch.randn(64, generator=g).to(DEV)
+    for cm in (False, True):
+        opcheck(K.add_layernorm_rows, (q, torch.randn(2, 9, 64, generator=g).to(DEV), gam, bet, 1e-5, cm), test_utils=tests)
+    opcheck(K.add_layernorm_rows, (torch.randn(2, 64, 9, generator=g).to(DEV).transpose(1, 2), None, gam, bet, 1e-5, True), test_utils=tests)
+    opcheck(K.sine_posembed, (torch.rand(16, generator=g).to(DEV) + 1, 2, 6, 5, torch.ones(2, 6, 5, device=DEV), True, 6.283), test_utils=tests)
+    opcheck(K.sine_posembed, (torch.rand(16, generator=g).to(DEV) + 1, 1, 6, 5, None, False, 6.283), test_utils=tests)
+
+    det = T.detrDecoder(joint_num=21, num_decoder_layers=2)
+    synth.fill_state_dict(det, 4)
+    det = det.to(DEV).eval()
+    anchors, img = torch.randn(3, 21, 128, generator=g).to(DEV), torch.randn(3, 128, 16, 16, generator=g).to(DEV)
+    with torch.no_grad():
+        eager = det(anchors, img)
+        torch._dynamo.reset()
+        got = torch.compile(det, fullgraph=True, backend="aot_eager")(anchors, img)
+    assert torch.equal(eager, got)
