@@ -127,8 +127,14 @@ spatial_order_kernel(const float* __restrict__ pcl, const float* __restrict__ ce
 //   cell cloud of the sample (H*W x float4) lives in shared memory; one thread per point keeps a sorted
 //   top-K in registers; ties -> lower cell index (lexicographic (d2, index) order, = the reference's stable ascending scan).
 // ------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(256)
+//   K2_RQ warps share a group of 32 points: warp (group, rq) seeds its list from the point's window and scans the cell rows rq,
+//   rq + K2_RQ, ... only; the lists (each the exact top K of the window plus its rows) meet through shared memory and warp rq = 0 merges them
+//   (same lexicographic order, duplicates from the shared window dropped by index) -- bit-identical results.  The point of it: 65 k
+//   points are 2048 warps, 14 per SM at batch 64, far too few to hide the dependent non-contracted arithmetic; a quarter of the rows
+//   per warp gives four times the warps.  Measured: TWO warps per group (K2_RQ = 2, 512 threads = 256 points per CTA) is the optimum,
+//   43.4 -> 36.7 us; four lose to their redundant window seeding and the merge (see the launcher).
+template <int K, int K2_RQ, int K2_NT>
+__global__ void __launch_bounds__(K2_NT)
 nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ depth, long long depth_bs, int depth_rs,
                      int depth_cs, const float* __restrict__ center, const float* __restrict__ M,
                      const float* __restrict__ cube, const float* __restrict__ cam, int N, int fs, float img_size, float flip,
@@ -138,6 +144,8 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
     __shared__ CamF c;
     const int b = blockIdx.y, HW = fs * fs;
     float4* rowbox = cells + HW;
+    float* mrg_d = reinterpret_cast<float*>(rowbox + 2 * fs);                 // [groups][K2_RQ - 1][K][32] merge lists: distances ...
+    int* mrg_i = reinterpret_cast<int*>(mrg_d + (K2_NT / 32 / K2_RQ) * (K2_RQ - 1) * K * 32);   // ... and cell indices
     if (threadIdx.x == 0) load_cam(c, b, center, M, cube, cam, img_size, flip);
     __syncthreads();
     const float ffs = (float)fs;
@@ -177,7 +185,9 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
         }
     }
     __syncthreads();
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int K2_PTS = K2_NT / K2_RQ;
+    const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, pgrp = warp_ / K2_RQ, rq = warp_ % K2_RQ;
+    const int slot = blockIdx.x * K2_PTS + pgrp * 32 + lane_;
     const bool active = slot < N;   // inactive lanes stay in the loop (warp votes below) but never store
     // optional processing order (kpf_spatial_order): neighbouring threads then hold neighbouring points, so a warp's lanes prune
     // the same rows and take the insertion path at the same cells; the outputs are indexed by the point id either way
@@ -239,7 +249,7 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
     // relative margin, far above fp32 rounding, so no candidate -- not even an exact tie -- is ever lost).
     int m = 0;
     if (windowed) {
-        for (int row = 0; row < fs; ++row) {
+        for (int row = rq; row < fs; row += K2_RQ) {
             const float4 lo = rowbox[2 * row], hi = rowbox[2 * row + 1];
             const float ex = fmaxf(fmaxf(lo.x - px, px - hi.x), 0.f), ey = fmaxf(fmaxf(lo.y - py, py - hi.y), 0.f),
                         ez = fmaxf(fmaxf(lo.z - pz, pz - hi.z), 0.f);
@@ -263,11 +273,36 @@ nearest_cells_kernel(const float* __restrict__ pcl, const float* __restrict__ de
         }
         m = HW;
     }
-    for (; m < HW; ++m) {   // map sizes without the windowed fast path
+    for (m += rq; m < HW; m += K2_RQ) {   // map sizes without the windowed fast path: every K2_RQ-th cell
         const float d2 = dist2(cells[m]);
         if (d2 <= bd[K - 1]) insert(d2, m);
     }
-    if (!active) return;
+    // ---- merge the four row-quarter lists of a point group (warps rq = 1..3 publish, warp rq = 0 inserts)
+    if (rq > 0) {
+        float* md = mrg_d + ((pgrp * (K2_RQ - 1) + rq - 1) * K) * 32 + lane_;
+        int* mi = mrg_i + ((pgrp * (K2_RQ - 1) + rq - 1) * K) * 32 + lane_;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            md[k * 32] = bd[k];
+            mi[k * 32] = bi[k];
+        }
+    }
+    __syncthreads();
+    if (rq > 0 || !active) return;
+    for (int o = 0; o < K2_RQ - 1; ++o) {
+        const float* md = mrg_d + ((pgrp * (K2_RQ - 1) + o) * K) * 32 + lane_;
+        const int* mi = mrg_i + ((pgrp * (K2_RQ - 1) + o) * K) * 32 + lane_;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float cd = md[k * 32];
+            const int ci = mi[k * 32];
+            if (!(cd <= bd[K - 1])) continue;   // cannot enter (also skips the +inf fillers of a short list)
+            bool dup = false;                    // a window cell is in every list: the same cell never enters twice
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) dup |= bi[kk] == ci && bd[kk] == cd;
+            if (!dup) insert(cd, ci);
+        }
+    }
     float cv[K];
     float s = 0.f;
 #pragma unroll
@@ -590,14 +625,29 @@ extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long
                                  int32_t* index32, cudaStream_t stream) {
     KPF_REQUIRE(B >= 0 && N >= 0 && fs >= 1 && fs * fs <= 8192 && K >= 1 && K <= fs * fs);
     if (B == 0 || N == 0) return 0;
-    dim3 grid((N + 255) / 256, B);
-    const size_t smem = ((size_t)fs * fs + 2 * (size_t)fs) * sizeof(float4);
+    // (row quarters per point group, threads per CTA): measured at batch 64, S = 128, K = 4 (profiles/probe_k2.py): (1, 256) 43.4 us,
+    // (2, 256) 39.4, (2, 512) 36.7, (4, 512) 49.9, (4, 1024) 48.8 -- two warps per point group pay for their second window seeding and
+    // the merge, four do not; seeding each warp only from the window rows it scans itself (no redundant seeding) loosens the bound and
+    // is far slower (49 / 86 us with two / four warps).  KPF_K2_VARIANT=1 / 2 / 3 select (1, 256) / (2, 256) / (4, 512) for comparison.
+    static const int variant = [] { const char* e = getenv("KPF_K2_VARIANT"); return e ? atoi(e) : 0; }();
+    const int RQ = variant == 1 ? 1 : variant == 3 ? 4 : 2;
+    const int NT = variant == 1 || variant == 2 ? 256 : 512;
+    const int PTS = NT / RQ;
+    dim3 grid((N + PTS - 1) / PTS, B);
+    const size_t smem = ((size_t)fs * fs + 2 * (size_t)fs) * sizeof(float4) + (size_t)(NT / 32 / RQ) * (RQ - 1) * K * 32 * 8;
+#define KPF_LAUNCH_K2V(KK, RQV, NTV)                                                                                         \
+    {                                                                                                                        \
+        cudaError_t e = kpf::set_smem(nearest_cells_kernel<KK, RQV, NTV>, smem);                                             \
+        if (e != cudaSuccess) return (int)e;                                                                                 \
+        nearest_cells_kernel<KK, RQV, NTV><<<grid, NTV, smem, stream>>>(pcl, depth, depth_bs, depth_rs, depth_cs, center, M, cube, cam, N, \
+                                                                       fs, img_size, flip, order, closeness, index64, index32); \
+    }
 #define KPF_LAUNCH_K2(KK)                                                                                                    \
     case KK: {                                                                                                               \
-        cudaError_t e = kpf::set_smem(nearest_cells_kernel<KK>, smem); \
-        if (e != cudaSuccess) return (int)e;                                                                                 \
-        nearest_cells_kernel<KK><<<grid, 256, smem, stream>>>(pcl, depth, depth_bs, depth_rs, depth_cs, center, M, cube, cam, N, \
-                                                             fs, img_size, flip, order, closeness, index64, index32);        \
+        if (variant == 1) KPF_LAUNCH_K2V(KK, 1, 256)                                                                         \
+        else if (variant == 2) KPF_LAUNCH_K2V(KK, 2, 256)                                                                    \
+        else if (variant == 3) KPF_LAUNCH_K2V(KK, 4, 512)                                                                    \
+        else KPF_LAUNCH_K2V(KK, 2, 512)                                                                                      \
     } break;
     switch (K) {
         KPF_LAUNCH_K2(1)
@@ -614,6 +664,7 @@ extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long
             return KPF_ERR_UNSUPPORTED;
     }
 #undef KPF_LAUNCH_K2
+#undef KPF_LAUNCH_K2V
     KPF_CHECK_LAUNCH();
     return 0;
 }
