@@ -628,10 +628,10 @@ extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long
     // (row quarters per point group, threads per CTA): measured at batch 64, S = 128, K = 4 (profiles/probe_k2.py): (1, 256) 43.4 us,
     // (2, 256) 39.4, (2, 512) 36.7, (4, 512) 49.9, (4, 1024) 48.8 -- two warps per point group pay for their second window seeding and
     // the merge, four do not; seeding each warp only from the window rows it scans itself (no redundant seeding) loosens the bound and
-    // is far slower (49 / 86 us with two / four warps).  KPF_K2_VARIANT=1 / 2 / 3 select (1, 256) / (2, 256) / (4, 512) for comparison.
+    // is far slower (49 / 86 us with two / four warps).  KPF_K2_VARIANT=1 selects (1, 256) for comparison (the other variants are not compiled in).
     static const int variant = [] { const char* e = getenv("KPF_K2_VARIANT"); return e ? atoi(e) : 0; }();
-    const int RQ = variant == 1 ? 1 : variant == 3 ? 4 : 2;
-    const int NT = variant == 1 || variant == 2 ? 256 : 512;
+    const int RQ = variant == 1 ? 1 : 2;
+    const int NT = variant == 1 ? 256 : 512;
     const int PTS = NT / RQ;
     dim3 grid((N + PTS - 1) / PTS, B);
     const size_t smem = ((size_t)fs * fs + 2 * (size_t)fs) * sizeof(float4) + (size_t)(NT / 32 / RQ) * (RQ - 1) * K * 32 * 8;
@@ -645,8 +645,6 @@ extern "C" int kpf_img2pcl_index(const float* pcl, const float* depth, long long
 #define KPF_LAUNCH_K2(KK)                                                                                                    \
     case KK: {                                                                                                               \
         if (variant == 1) KPF_LAUNCH_K2V(KK, 1, 256)                                                                         \
-        else if (variant == 2) KPF_LAUNCH_K2V(KK, 2, 256)                                                                    \
-        else if (variant == 3) KPF_LAUNCH_K2V(KK, 4, 512)                                                                    \
         else KPF_LAUNCH_K2V(KK, 2, 512)                                                                                      \
     } break;
     switch (K) {
