@@ -239,8 +239,10 @@ int kpf_point_embed(const void* feat_hi, const void* feat_lo, const int32_t* idx
  * e is [B][>= N+J][256] 16-bit rows [hi | lo] (format fmt) with batch stride e_batch_stride: rows < N from kpf_point_embed; the prep
  * launch WRITES the J joint feature rows behind them (the joints are members N..N+J-1 of the grouped point set, model.py:168-169).
  * Two launches (prep: joint embedding, its W1 products, ball query; persistent tile kernel on `num_sms` CTAs, W1 / W2 planes in
- * tensor memory) that hand over through `scratch`: caller workspace of B*S*J*128*4 + B*(N+32)*16 + B*S*J*nsample*2 bytes,
- * 16-byte aligned, contents undefined.  Split-precision GEMMs: fp32-class results. */
+ * tensor memory) that hand over through `scratch`: caller workspace of B*S*J*128*4 + B*(N+32)*16 + B*S*J*nsample*2 + B*S*4 bytes,
+ * 16-byte aligned, contents undefined.  A scale whose widest ball of the launch holds <= 16 / 32 points is grouped 16 / 32 rows per
+ * joint instead of nsample (the ball query pads with copies of the first hit; the max-pool does not see copies): same bits, fewer
+ * tiles.  Split-precision GEMMs: fp32-class results. */
 int kpf_desa_fused(void* e, long long e_batch_stride, const float* part_acc, const float* part_ms, const float* pcl, const float* joint,
                    const void* wmat, const float* wvec, int B, int N, int J, int S, int nsample, float r0, float r1, float r2, float r3,
                    int fmt, const float* jf_in /* NULL, or [B,J,128]: joint features given (stand-alone DESA.forward, model.py:166); the

@@ -41,8 +41,10 @@ struct DesaParams {
     float* cj;                // scratch [B,S,J,128]: W1_s jf[j] (fp32), subtracted in the tile kernel's layer-1 epilogue
     float4* xyz4;             // scratch [B][N + 32]: xyz of the grouped point set (N points, then the J joints), one 16-byte load each
     uint16_t* idx;            // scratch [B,S,J,nsample] ball-query indices (>= N: one of the joints)
+    int* gw;                  // scratch [B,S]: the largest ball population (capped at nsample) among the sample's J balls of a scale
     int B, N, J, T, S, nsample, fmt;
-    int probe;                // profiling aid (KPF_DESA_PROBE): bit 0 = skip the row copies, bit 1 = skip the MMAs (results are garbage)
+    int probe;                // profiling aid (KPF_DESA_PROBE): bit 0 = skip the row copies, bit 1 = skip the MMAs (results are garbage),
+                              //   bit 2 = row copy as one burst, bit 3 = always group nsample rows per joint (no narrow groups)
     float radius[4];
     long long* dbg;
 };
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
         pdl_wait();
         float4* sPcl = reinterpret_cast<float4*>(ds_smem);                          // [N + J] xyz
         uint32_t* sMask = reinterpret_cast<uint32_t*>(sPcl + (N + J + 3) / 4 * 4);   // [S][J][NW] hit words (bit = point)
+        __shared__ int sGw[4];
+        if (tid < 4) sGw[tid] = 0;
         for (int i = tid; i < N + J; i += DS_NT) {
             const float* s = i < N ? p.pcl + ((size_t)b * N + i) * 3 : p.joint + ((size_t)b * J + (i - N)) * 3;
             sPcl[i] = make_float4(s[0], s[1], s[2], 0.f);
@@ -147,7 +151,11 @@ __global__ void __launch_bounds__(DS_NT, 1) desa_prep_kernel(const DesaParams p)
             if (first < 0) first = 0;
             const int cnt = carry < NS ? carry : NS;
             for (int s2 = cnt + lane; s2 < NS; s2 += 32) out[s2] = (uint16_t)first;
+            if (lane == 0) atomicMax(&sGw[pj / J], cnt);
         }
+        // the widest ball of each scale: the tile kernel groups only as many rows per joint as the widest ball of the launch needs
+        __syncthreads();
+        if (tid < S) p.gw[(size_t)b * S + tid] = sGw[tid];
         stamp();
         return;
     }
@@ -383,6 +391,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     float4* sXyz = reinterpret_cast<float4*>(sPart + 1024);   // [2][128][2] xyz of a tile's grouped points and of their centres (cp.async staging)
     __shared__ __align__(8) uint64_t wbar, g1_bar, g2_bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ int sGw[4], sNs[4], sBase[5];   // per scale: widest ball of the launch, rows grouped per joint, first work item
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = warp_index_uniform();
@@ -392,11 +401,13 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     // contiguous bytes per cp.async, i.e. ONE 128-byte request per row half instead of eight 16-byte ones -- the copy is bound by
     // the number of requests the SM can keep in flight, not by bytes
     const int r = 4 * (warp & 15) + (lane & 3), g8 = lane >> 2;
-    const int J = p.J, N = p.N, NS = p.nsample, S = p.S, B = p.B;
-    const int JPT = 128 / NS, TPS = (J + JPT - 1) / JPT;          // joints per tile, tiles per (sample, scale)
-    const int ns_shift = 31 - __clz(NS);                          // NS is a power of two: joint of tile row x = x >> ns_shift
-    const int total = S * B * TPS;
-    const int it0 = (int)((long long)total * blockIdx.x / gridDim.x), it1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+    const int J = p.J, N = p.N, NSTRIDE = p.nsample, S = p.S, B = p.B;
+    // Rows grouped per joint.  pointnet2's ball query pads a ball of fewer than nsample hits with copies of its first hit, and a max
+    // over copies is the max over the originals: a scale whose widest ball (over the whole launch, desa_prep's gw) holds <= 16 / 32
+    // points is grouped NS = 16 / 32 rows per joint instead of nsample -- 8 / 4 joints per 128-row tile, bit-identical maxima, a
+    // quarter / half of the tiles.  NS, JPT, TPS, ns_shift are constants of a RUN (items of one scale), set at the top of each run.
+    int NS = NSTRIDE, JPT = 128 / NS, TPS = (J + JPT - 1) / JPT;  // joints per tile, tiles per (sample, scale)
+    int ns_shift = 31 - __clz(NS);                                // NS is a power of two: joint of tile row x = x >> ns_shift
     const uint32_t ACC1 = 0, ACC2 = 128, TW1_HI = 256, TW1_LO = 320, TW2_HI = 384, TW2_LO = 448;   // TMEM columns
     constexpr int fmt = FMT;
     int n_stamp = 0;
@@ -413,6 +424,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
         mbar_init(&g2_bar, 1);
         fence_mbar_init();
     }
+    if (tid < 4) sGw[tid] = 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -420,13 +432,41 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     uint32_t g1_phase = 0, g2_phase = 0, w_phase = 0;
     pdl_wait();   // indices, W1 jf terms and point features come from the previous kernels
 
-    auto decode = [&](int item) {
+    for (int i = tid; i < B * S; i += DS_TILE_NT) atomicMax(&sGw[i % S], __ldg(p.gw + i));
+    __syncthreads();
+    if (tid == 0) {
+        int base = 0;
+        for (int sc = 0; sc < S; ++sc) {
+            int n = 16;
+            while (n < sGw[sc]) n <<= 1;
+            if (n > NSTRIDE || (p.probe & 8)) n = NSTRIDE;
+            sNs[sc] = n;
+            sBase[sc] = base;
+            const int jpt = 128 / n;
+            base += B * ((J + jpt - 1) / jpt);
+        }
+        for (int sc = S; sc < 5; ++sc) sBase[sc] = base;
+    }
+    __syncthreads();
+    const int total = sBase[S];
+    const int it0 = (int)((long long)total * blockIdx.x / gridDim.x), it1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+
+    auto decode = [&](int item) {   // uses the run constants of the item's scale: set_run(scale_of(item)) first
         DesaItem it;
-        it.sc = item / (B * TPS);
-        const int rem = item - it.sc * (B * TPS);
+        it.sc = 0;
+        while (it.sc + 1 < S && item >= sBase[it.sc + 1]) ++it.sc;
+        const int rem = item - sBase[it.sc];
         it.b = rem / TPS;
         it.j0 = (rem - it.b * TPS) * JPT;
         return it;
+    };
+    auto set_run = [&](int item) {
+        int sc = 0;
+        while (sc + 1 < S && item >= sBase[sc + 1]) ++sc;
+        NS = sNs[sc];
+        JPT = 128 / NS;
+        TPS = (J + JPT - 1) / JPT;
+        ns_shift = 31 - __clz(NS);
     };
     auto advance = [&](DesaItem& it) {
         it.j0 += JPT;
@@ -447,11 +487,11 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
     float inv_r = 1.f;       // 1 / radius of the run's scale
 
     auto fetch_idx = [&]() {
-        const uint16_t* base = p.idx + (((size_t)c_idx.b * S + c_idx.sc) * J + c_idx.j0) * NS;
+        const uint16_t* base = p.idx + (((size_t)c_idx.b * S + c_idx.sc) * J + c_idx.j0) * NSTRIDE;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int row = r + 64 * h;
-            ii[h] = c_idx.j0 + (row >> ns_shift) < J ? (int)__ldg(base + row) : 0;
+            const int row = r + 64 * h, jo = row >> ns_shift;   // the first NS of a joint's NSTRIDE indices
+            ii[h] = c_idx.j0 + jo < J ? (int)__ldg(base + jo * NSTRIDE + (row & (NS - 1))) : 0;
         }
         advance(c_idx);
     };
@@ -532,9 +572,11 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
 
     // ---- runs of items that share a scale (= weights)
     for (int i0 = it0; i0 < it1;) {
+        set_run(i0);
         const DesaItem first = decode(i0);
         const int sc0 = first.sc;
-        const int run_end = (sc0 + 1) * B * TPS;
+        const int run_end = sBase[sc0 + 1];
+        const bool direct = NS <= 32;   // a thread's 32 tile rows hold whole joints: it stores its maxima itself (no sPart, no store_max)
         const int i1 = it1 < run_end ? it1 : run_end;
         c_idx = c_rows = c_epi = c_max = first;
         // every MMA of the previous run has completed (its epilogues ran), so the weight buffers are free
@@ -603,7 +645,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                     __syncwarp();
                 }
                 w_ready = true;
-                if (s - 1 >= i0) store_max(s - 1);   // written before the barrier above
+                if (!direct && s - 1 >= i0) store_max(s - 1);   // written before the barrier above
             }
             if (!issuer) {
                 // gather side: rows of tile s + 2 (its buffer held tile s - 1, whose layer 2 every thread waited for in the previous
@@ -611,10 +653,12 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                 const bool fine = s + 2 < i1;   // tile s + 2 exists: its row copy is issued in eight parts across this iteration (copy_part)
                 if (fine) copy_part(s + 2, 0);
                 // layer-1 bias of tile s + 1 minus the W1 jf term of the joint this thread's 32 rows belong to
-                float cjv = 0.f;   // loaded here, consumed after the layer-2 epilogue (the subtraction sits behind the wait below on purpose)
+                float cjv[2] = {0.f, 0.f};   // per 16-row half (two joints when NS = 16); loaded here, consumed after the layer-2 epilogue
                 if (s >= i0 - 1 && s + 1 < i1) {
-                    const int jj = c_epi.j0 + ((32 * cg) >> ns_shift);
-                    if (jj < J) cjv = __ldg(p.cj + (((size_t)c_epi.b * S + c_epi.sc) * J + jj) * 128 + ch);
+                    const float* cjb = p.cj + (((size_t)c_epi.b * S + c_epi.sc) * J) * 128 + ch;
+                    const int j0h = c_epi.j0 + ((32 * cg) >> ns_shift), j1h = c_epi.j0 + ((32 * cg + 16) >> ns_shift);
+                    if (j0h < J) cjv[0] = __ldg(cjb + (size_t)j0h * 128);
+                    cjv[1] = j1h == j0h ? cjv[0] : (j1h < J ? __ldg(cjb + (size_t)j1h * 128) : 0.f);
                     advance(c_epi);
                 }
                 if (fine) {
@@ -625,12 +669,12 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                     mbar_wait(&g1_bar, g1_phase);
                     g1_phase ^= 1;
                     tc_fence_after();
-                    const float cjb = b1 - cjv;
                     uint4* H = sX + ((s + 1) % 3) * DS_XBUF;   // layer 1 has consumed the rows that lived here
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {   // two 16-column reads: half the live registers of one 32-column read
                         float a[16];
                         tmem_ld<16>(tmem + ACC1 + 32 * cg + 16 * hf, a);
+                        const float cjb = b1 - cjv[hf];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) a[i] = fmaxf(a[i] + cjb, 0.f);   // relu(W1 feat + tail - W1 jf + b1)
 #pragma unroll
@@ -650,16 +694,29 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
                     mbar_wait(&g2_bar, g2_phase);
                     g2_phase ^= 1;
                     tc_fence_after();
-                    float mx = -INFINITY;
+                    float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         float a[16];
                         tmem_ld<16>(tmem + ACC2 + 32 * cg + 16 * hf, a);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, a[i]);
+                        for (int i = 0; i < 16; ++i) mx[hf] = fmaxf(mx[hf], a[i]);
                         if (fine) copy_part(s + 2, 5 + hf);
                     }
-                    sPart[(s & 1) * 512 + cg * 128 + ch] = fmaxf(mx + b2, 0.f);   // max_i relu(a_i + b2)
+                    if (!direct) {
+                        sPart[(s & 1) * 512 + cg * 128 + ch] = fmaxf(fmaxf(mx[0], mx[1]) + b2, 0.f);   // max_i relu(a_i + b2)
+                    } else {   // narrow groups: this thread's rows are one joint (NS = 32) or two (NS = 16)
+                        const DesaItem it = c_max;
+                        advance(c_max);
+                        float* dst = p.desa_part + (((size_t)it.b * S + it.sc) * J) * 128 + ch;
+                        const int j0h = it.j0 + ((32 * cg) >> ns_shift), j1h = it.j0 + ((32 * cg + 16) >> ns_shift);
+                        if (j0h == j1h) {
+                            if (j0h < J) dst[(size_t)j0h * 128] = fmaxf(fmaxf(mx[0], mx[1]) + b2, 0.f);
+                        } else {
+                            if (j0h < J) dst[(size_t)j0h * 128] = fmaxf(mx[0] + b2, 0.f);
+                            if (j1h < J) dst[(size_t)j1h * 128] = fmaxf(mx[1] + b2, 0.f);
+                        }
+                    }
                     tc_fence_before();
                 } else if (fine) {
                     copy_part(s + 2, 5);
@@ -671,7 +728,7 @@ __global__ void __launch_bounds__(DS_TILE_NT, 1) desa_tile_kernel(const DesaPara
             if (s <= i0 + 3) stamp();
         }
         __syncthreads();
-        store_max(i1 - 1);
+        if (!direct) store_max(i1 - 1);
         w_phase ^= 1;
         i0 = i1;
         stamp();
@@ -699,8 +756,8 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     KPF_REQUIRE(jf_in != nullptr || (part_acc != nullptr && part_ms != nullptr));
     p.fmt = fmt; p.jf_in = jf_in;
     {
-        static const int probe = [] { const char* e = getenv("KPF_DESA_PROBE"); return e ? atoi(e) : 0; }();
-        p.probe = probe;
+        const char* pe = getenv("KPF_DESA_PROBE");   // read per call (a captured graph keeps the value of its capture)
+        p.probe = pe ? atoi(pe) : 0;
     }
     p.e = (uint16_t*)e; p.e_bs = e_batch_stride; p.part_acc = part_acc; p.part_ms = part_ms; p.pcl = pcl; p.joint = joint; p.wmat = (const uint4*)wmat;
     p.wvec = wvec; p.desa_part = desa_part; p.jf_out = jf_out; p.B = B; p.N = N; p.J = J; p.T = N / 64;   /* kpf_point_embed's tile = 64 points */ p.S = S; p.nsample = nsample;
@@ -709,6 +766,7 @@ extern "C" int kpf_desa_fused(void* e, long long e_batch_stride, const float* pa
     p.cj = (float*)scratch;
     p.xyz4 = (float4*)((char*)scratch + (size_t)B * S * J * 128 * 4);
     p.idx = (uint16_t*)((char*)scratch + (size_t)B * S * J * 128 * 4 + (size_t)B * (N + 32) * 16);
+    p.gw = (int*)((char*)scratch + (size_t)B * S * J * 128 * 4 + (size_t)B * (N + 32) * 16 + (size_t)B * S * J * nsample * 2);
     const int NW = (N + J + 31) / 32;
     const size_t smem_jf = (size_t)(3 * 4096 + 1024) * 16 + (size_t)(p.T * 64 + 64) * 4 + 32 * 16 + 64;
     const size_t smem_bq = (size_t)((N + J + 3) / 4 * 4) * 16 + (size_t)S * J * NW * 4 + 64;

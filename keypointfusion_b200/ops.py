@@ -814,7 +814,8 @@ def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, db
         e_full[:, :N].copy_(e)
         e = e_full[:, :N]
     # workspace between the two kernels: W1_s jf terms fp32 [B,S,J,128], padded xyz table [B,N+32,4] f32, ball-query indices u16
-    scratch = torch.empty(B * S * J * 128 * 4 + B * (N + 32) * 16 + B * S * J * nsample * 2, device=pcl.device, dtype=torch.uint8)
+    # [B,S,J,nsample], widest ball per (sample, scale) i32 [B,S]
+    scratch = torch.empty(B * S * J * 128 * 4 + B * (N + 32) * 16 + B * S * J * nsample * 2 + B * S * 4, device=pcl.device, dtype=torch.uint8)
     _call("kpf_desa_fused", _p(e), e.stride(0), _p(part_acc), _p(part_ms), _p(pcl), _p(joint), _p(wmat), _p(wvec), B, N, J, S, nsample, float(r[0]),
           float(r[1]), float(r[2]), float(r[3]), fmt, _p(_f32(jf_in) if jf_in is not None else None), _p(part), _p(jf), _p(scratch),
           sm_count(pcl.device), _p(dbg))

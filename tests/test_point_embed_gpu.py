@@ -151,19 +151,38 @@ def test_ball_query_indices_exact(path_params, which):
     for s_, r in enumerate((0.1, 0.2, 0.4)):
         ref = O.ball_query(xyz.cpu().numpy(), joint.cpu().numpy(), r, NS)
         assert np.array_equal(fused[:, s_].astype(np.int64), ref.astype(np.int64)), (which, r)
+    # ... and the widest ball per (sample, scale), which sets how many rows per joint the tile kernel groups (16 / 32 / nsample)
+    off_gw = off + B * 3 * J * NS * 2
+    gw = scratch["buf"][off_gw:off_gw + B * 3 * 4].view(torch.int32).cpu().numpy().reshape(B, 3)
+    assert np.array_equal(gw, np.minimum(counts, NS).reshape(3, B, J).max(-1).T), (which, gw)
+    if which == "sparse":
+        assert gw[:, 0].max() <= 16      # the narrow-group path of the tile kernel is what test_desa_fused[sparse] runs
 
 
-@pytest.mark.parametrize("B,which", [(2, "dense"), (3, "dense"), (2, "sparse"), (2, "edge")])
-def test_desa_fused(path_params, B, which):
-    """point stage -> DESA kernel vs the oracle's joint embeddings + DESA (same ball-query membership: centres are inputs)."""
+@pytest.mark.parametrize("B,which,radii", [(2, "dense", None), (3, "dense", None), (2, "sparse", None), (2, "edge", None),
+                                           (3, "dense", (0.06, 0.12, 0.15)), (2, "sparse", (0.15, 0.3, 0.6))])
+def test_desa_fused(path_params, B, which, radii):
+    """point stage -> DESA kernel vs the oracle's joint embeddings + DESA (same ball-query membership: centres are inputs).
+    The radii variants move the scales between the tile kernel's group widths (16 / 32 / nsample rows per joint)."""
     from keypointfusion_b200 import ops
     import torch.nn.functional as F
     inp, c, pcl, close, idx, blk = _desa_setup(path_params, B, 70 + B)
     joint = _joint_sets(pcl, which)
+    if radii is not None:
+        blk.FA.radius = list(radii)
     k = blk.kc()
     featT = ops.repack_features(c["img_feat"].bfloat16(), c["img_feat_rgb"].bfloat16(), c["img_offset"][:, 84:].bfloat16())
     e, acc, ms = ops.point_embed(featT, idx, close, pcl, joint, k["pe_wmat"], k["pe_wvec"], 0.8)
     part, jf = ops.desa_fused(e, acc, ms, pcl, joint, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0])
+    # narrow groups (a scale whose widest ball holds <= 16 / 32 points is tiled 16 / 32 rows per joint) leave every bit unchanged:
+    # KPF_DESA_PROBE=8 forces nsample rows per joint
+    import os
+    os.environ["KPF_DESA_PROBE"] = "8"
+    try:
+        part_w, jf_w = ops.desa_fused(e, acc, ms, pcl, joint, k["ds_wmat"], k["ds_wvec"], blk.FA.radius, blk.FA.S[0])
+    finally:
+        del os.environ["KPF_DESA_PROBE"]
+    assert torch.equal(part, part_w) and torch.equal(jf, jf_w)
     fu = blk.FA.kc()["fusion"]
     out = F.relu(F.linear(torch.cat([part.permute(0, 2, 1, 3).reshape(B, 21, -1), jf], -1), *fu))
     # oracle
@@ -176,7 +195,7 @@ def test_desa_fused(path_params, B, which):
                     O.conv_bn(p, "block1.pcl_pose_emb.", torch.cat([pw, off], -1)))
     ee = torch.relu(ee + O.conv_bn(p, "block1.pcl_feat_emb_RGB.", pr))
     rjf = torch.relu(O.conv_bn(p, "block1.joint_feat_emb.", torch.softmax(pw.permute(0, 2, 1), -1) @ ee) + O.conv_bn(p, "block1.joint_xyz_emb.", jt))
-    rout = O.desa(p, "block1.FA.", ee, rjf, pc, jt)
+    rout = O.desa(p, "block1.FA.", ee, rjf, pc, jt, radius=tuple(blk.FA.radius))
     print(f"[desa {which}] jf rms rel {rms_rel(jf, rjf):.2e}; desa output rms rel {rms_rel(out, rout):.2e} worst {worst_rel(out, rout):.2e}")
     assert rms_rel(jf, rjf) < _tol(), rms_rel(jf, rjf)
     assert rms_rel(out, rout) < _tol() and worst_rel(out, rout) < 10 * _tol(), rms_rel(out, rout)
