@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--config", default="path", choices=["path", "sweep", "full", "demo"],
                     help="path: BASELINE configs[1] (default, the headline line); sweep: config 4; full: config 3; demo: config 5")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-this-GPU leg")
-    ap.add_argument("--overlap", type=int, default=4, help="consecutive steps kept in flight on this many streams (1 = strictly serial; measured at batch 64: 1 / 2 / 3 / 4 / 6 / 8 -> 0.736 / 0.604 / 0.543 / 0.505 / 0.497 / 0.512 ms per step)")
+    ap.add_argument("--overlap", type=int, default=6, help="consecutive steps kept in flight on this many streams (1 = strictly serial; measured at batch 64 earlier in round 2: 1 / 2 / 3 / 4 / 6 / 8 -> 0.736 / 0.604 / 0.543 / 0.505 / 0.497 / 0.512 ms per step; final build, one K5 CTA per sample: 4 / 5 / 6 / 8 -> 0.473 / 0.466 / 0.464 / 0.466, profiles/ab_overlap_r2.txt)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -212,6 +212,8 @@ def main():
     S_OV = 1 if a.no_graph else max(1, a.overlap)
     if world > 1 and os.environ.get("KPF_EXCHANGE", "peer") == "nccl":
         S_OV = 1   # the host-issued all-gather fallback follows every step on the current stream: steps are not overlapped
+    if S_OV > 1:
+        ops.K5_SPLIT = 1   # steps in flight: SM-time, not the latency of one launch, is what counts (ops.spatial_aggregate_tc)
     NSETS = S_OV * ((4 + S_OV - 1) // S_OV)   # >= 4 resident input sets (> L2 together), a multiple of the steps in flight
     config["l2"] = f"inputs rotate over {NSETS} resident sets (~{NSETS * 51} MB) > 126 MB L2; no flush kernel inside the timed region"
     hosts = [host_inputs(B, seed=1000 * rank + s) for s in range(NSETS)]

@@ -826,6 +826,7 @@ def desa_fused(e, part_acc, part_ms, pcl, joint, wmat, wvec, radius, nsample, db
 
 # ------------------------------------------------------------------------------------------------ a12 on tensor cores
 _counter_cache = {}
+K5_SPLIT = None   # None: spread a sample's cell tiles over as many CTAs as fit one wave (latency); 1: one CTA per sample (SM-time)
 
 
 def _zero_counters(n, device):
@@ -896,6 +897,13 @@ def spatial_aggregate_tc(feat_rgb, joints, img, center, M, cube, cam, wa_packed,
     # cell tiles of a sample spread over `split` CTAs: as many as still fit in ONE wave of one-CTA-per-SM (measured at B = 64:
     # split 1 / 2 / 4 / 8 -> 60 / 39 / 47 / 62 us)
     split = next((s_ for s_ in (8, 4, 2) if T % s_ == 0 and B * s_ <= sm_count(feat_rgb.device)), 1)
+    # ... which is the LATENCY optimum of a launch that has the GPU to itself.  With several steps in flight what counts is the launch's
+    # SM-time, and the per-CTA prologue (weights, tables, first tile) is paid `split` times: one CTA per sample is 60 us x 64 SMs against
+    # 35 us x 128.  K5_SPLIT (set by the caller that overlaps steps, before it captures its graphs; env KPF_K5_SPLIT for A/B runs)
+    # overrides the policy: bench.py at batch 64, six steps in flight, split 2 -> 1: 0.479 -> 0.464 ms per step (profiles/ab_overlap_r2.txt)
+    forced = int(os.environ["KPF_K5_SPLIT"]) if os.environ.get("KPF_K5_SPLIT") else K5_SPLIT
+    if forced and T % forced == 0:
+        split = forced
     scratch = torch.empty(B, split, 128, 32, device=feat_rgb.device, dtype=torch.float32) if split > 1 else None
     counters = _zero_counters(B, feat_rgb.device) if split > 1 else None
     _call("kpf_spatial_aggregate_tc", _p(feat_rgb), _p(feat_lo), _p(joints), _p(d), bs, rs, cs, _p(center), _p(M), _p(cube), _p(cam),
