@@ -11,8 +11,10 @@
 //                              of the grouped set, model.py:168-169), and cj[s][j] = W1_s jf[j] is computed for every scale
 //             CTA per (sample, scale): ball query (pointnet2_ops semantics) of the J joints over the N points + the J joints
 //                              themselves -> idx[b][scale][j][nsample]; the scale-0 CTA also writes a padded xyz table
-// desa_tile_kernel   persistent, one CTA per SM, 16 worker warps + 1 issuer warp.  Work item = (scale, sample, tile of 128/nsample
-//             joints); every CTA takes a contiguous, scale-major range so the scale's weights stay resident:
+// desa_tile_kernel   persistent, one CTA per SM, 16 worker warps + 1 issuer warp.  Work item = (scale, sample, tile of 128/NS
+//             joints), NS = rows grouped per joint = nsample, or 16 / 32 for a scale whose widest ball of the launch holds no more
+//             points than that (the padding copies of the first hit are not multiplied: same maxima, fewer tiles); every CTA takes
+//             a contiguous, scale-major range so the scale's weights stay resident:
 //             X = [feat[idx] - jf[j] | (xyz[idx] - c_j)/r]  ->  h = relu(W1 X + b1)  ->  relu(W2 h + b2)  -> max over nsample,
 //             evaluated as h = relu(W1 [feat[idx] | (xyz[idx] - c_j)/r] - cj + b1): layer 1 reads the RAW gathered rows, so the
 //             gather is a cp.async copy (128-byte requests) straight into the operand and cj is subtracted in the epilogue.
